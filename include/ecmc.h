@@ -1,0 +1,271 @@
+/* ecmc.h -- C ABI of libecmc_b200.so, the B200-native batched event-chain Monte Carlo engine.
+ *
+ * This is the drop-in boundary for ONE hot path of JeLLyFysh (reference paths are relative to the
+ * reference checkout): the body of the mediator loop, jellyfysh/mediator/single_process_mediator.py:91-156,
+ * i.e. for the active particle of a Markov chain: compute every candidate event time, take the argmin that
+ * the scheduler would pop, apply the out-state (lifting) and commit it. The engine advances thousands of
+ * independent chains at once on one GPU; everything else of the reference (factory, taggers' tag graph,
+ * sampling / output handlers, end of run) stays on the host and calls in here.
+ *
+ * Conventions (same spirit as the reference's cffi modules, e.g.
+ * jellyfysh/potential/merged_image_coulomb_potential/merged_image_coulomb_potential_build.py:36-44 and
+ * jellyfysh/scheduler/heap_scheduler/heap_build.py:37-55): plain C, opaque handle owned by the caller,
+ * caller-allocated output buffers, int status returns (0 = ok, <0 = error, message via ecmc_last_error),
+ * no callbacks into the host language, no torch types, one handle = one GPU, one host thread per handle.
+ * There is NO CPU fallback: every entry point that computes needs a CUDA device and fails otherwise.
+ */
+#ifndef ECMC_B200_H
+#define ECMC_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECMC_ABI_VERSION 1
+#define ECMC_MAX_DIM 3
+
+/* ---- status codes ---------------------------------------------------------------------------------- */
+#define ECMC_OK 0
+#define ECMC_ERR_INVALID (-1)   /* bad argument / unsupported program          */
+#define ECMC_ERR_CUDA (-2)      /* CUDA runtime error (no device, OOM, launch) */
+#define ECMC_ERR_STATE (-3)     /* call order violated (e.g. run before start) */
+#define ECMC_ERR_CAPACITY (-4)  /* a device-side capacity (surplus list, occupants) overflowed */
+
+/* ---- potentials -----------------------------------------------------------------------------------
+ * Parameter carriers for the reference's potential classes. params[] meaning per kind:
+ *  INVERSE_POWER            [0]=power [1]=prefactor          jellyfysh/potential/inverse_power_potential.py:32-179
+ *  LENNARD_JONES            [0]=prefactor [1]=characteristic_length
+ *                                                            jellyfysh/potential/lennard_jones_potential.py:31-135
+ *  DISPLACED_EVEN_POWER     [0]=prefactor [1]=equilibrium_separation [2]=power
+ *                                                            jellyfysh/potential/displaced_even_power_potential.py:73-142
+ *  HARD_SPHERE              [0]=radius                       jellyfysh/potential/hard_sphere_potential.py:33-126
+ *  HARD_DIPOLE              [0]=minimum_separation [1]=maximum_separation
+ *                                                            jellyfysh/potential/hard_dipole_potential.py:33-141
+ *  MERGED_IMAGE_COULOMB     [0]=prefactor [1]=alpha [2]=fourier_cutoff [3]=position_cutoff
+ *                              jellyfysh/potential/merged_image_coulomb_potential/merged_image_coulomb_potential.c:77-274
+ *  INVERSE_POWER_COULOMB_BOUNDING [0]=prefactor
+ *                jellyfysh/potential/inverse_power_coulomb_bounding_potential/inverse_power_coulomb_bounding_potential.c:53-139
+ */
+enum EcmcPotentialKind {
+    ECMC_POT_NONE = 0,
+    ECMC_POT_INVERSE_POWER = 1,
+    ECMC_POT_LENNARD_JONES = 2,
+    ECMC_POT_DISPLACED_EVEN_POWER = 3,
+    ECMC_POT_HARD_SPHERE = 4,
+    ECMC_POT_HARD_DIPOLE = 5,
+    ECMC_POT_MERGED_IMAGE_COULOMB = 6,
+    ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING = 7
+};
+
+typedef struct EcmcPotential {
+    int32_t kind;      /* EcmcPotentialKind */
+    int32_t reserved;
+    double params[6];
+} EcmcPotential;
+
+/* ---- pair event handlers --------------------------------------------------------------------------- */
+enum EcmcPairHandlerKind {
+    ECMC_PAIR_NONE = 0,
+    /* TwoLeafUnitEventHandler: invertible potential, event always accepted.
+     * jellyfysh/event_handler/two_leaf_unit_event_handler.py:105-154 */
+    ECMC_PAIR_TWO_LEAF_UNIT = 1,
+    /* TwoLeafUnitBoundingPotentialEventHandler: candidate from an invertible bounding potential, confirmed
+     * against the real potential's derivative.
+     * jellyfysh/event_handler/two_leaf_unit_bounding_potential_event_handler.py:112-168 */
+    ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING = 2
+};
+
+/* ---- cell-veto tables -------------------------------------------------------------------------------
+ * Walker alias table for one direction of motion and one sign, as built by the reference at init
+ * (jellyfysh/event_handler/walker.py:69-103; jellyfysh/event_handler/abstracts/cell_veto_event_handler.py:134-159).
+ * Entry e is (cell_a[e] with rate_a[e], cell_b[e]); cell_b[e] < 0 for single-item entries. Cells are flat
+ * indices sum_d id_d * prod_{d'<d} cells_per_side[d'] of the cell *relative to cell zero*. */
+typedef struct EcmcWalkerTable {
+    int32_t n_entries;
+    int32_t reserved;
+    const int32_t *cell_a;
+    const int32_t *cell_b;
+    const double *rate_a;
+    double total_rate;
+    double mean_rate;
+} EcmcWalkerTable;
+
+typedef struct EcmcVetoTables {
+    EcmcWalkerTable upper[ECMC_MAX_DIM]; /* per direction of motion; used when the charge factor is > 0 */
+    EcmcWalkerTable lower[ECMC_MAX_DIM]; /* used when the charge factor is < 0 (n_entries may be 0 if unused) */
+    /* derivative bounds [n_cells][dimension][2] = (upper_bound, -lower_bound) per relative cell; entries of
+     * nearby (excluded) cells are ignored. */
+    const double *bounds;
+} EcmcVetoTables;
+
+/* ---- the program: one configuration of the hot path, shared by all chains of a handle ---------------- */
+typedef struct EcmcProgram {
+    int32_t abi_version;      /* must be ECMC_ABI_VERSION */
+    int32_t dimension;        /* 2 or 3; HypercubicSetting, jellyfysh/setting/hypercubic_setting.py:200-223 */
+    int32_t n_particles;      /* point masses (leaf units) per chain */
+    int32_t reserved0;
+    double system_length;
+    double beta;
+    /* CuboidPeriodicCells + SingleActiveCellOccupancy */
+    int32_t cells_per_side[ECMC_MAX_DIM];
+    int32_t neighbor_layers;
+    int32_t max_occupants;    /* occupants stored per cell (reference maximum_number_occupants; >= 1) */
+    int32_t max_surplus;      /* capacity of the per-chain surplus list */
+    /* nearby + surplus pair factor */
+    int32_t pair_handler;     /* EcmcPairHandlerKind */
+    int32_t pair_use_charge;  /* 1: potentials get (charge_active, charge_target); 0: (1.0, 1.0) / none */
+    EcmcPotential pair_potential;
+    EcmcPotential pair_bounding_potential; /* only for ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING */
+    /* LeafUnitCellVetoEventHandler for all non-nearby cells */
+    int32_t veto_enabled;
+    int32_t veto_use_charge;
+    EcmcPotential veto_potential;
+    double veto_target_charge; /* InnerPointEstimator target charge (charge_correction_factor) */
+    const EcmcVetoTables *veto_tables;
+    /* chain control: SingleIndependentActivePeriodicDirectionEndOfChainEventHandler +
+     * InitialChainStartOfRunEventHandler */
+    double chain_time;
+    double speed;
+    int32_t initial_direction;
+    int32_t initial_active;
+    /* counter-based random stream, see DESIGN.md "Random stream" */
+    uint32_t seed;
+    uint32_t reserved1;
+} EcmcProgram;
+
+/* ---- per-chain lifting state ("who is active, where is the clock") ------------------------------------
+ * Replaces TreeLiftingState (jellyfysh/state_handler/lifting_state/tree_lifting_state.py:56-147) plus the
+ * persistent end-of-chain candidate and a candidate that survived a host control event (sampling). */
+typedef struct EcmcChainState {
+    int32_t active;           /* identifier of the active particle */
+    int32_t direction;        /* direction of motion */
+    double time_q, time_r;    /* time stamp of the active particle as (quotient, remainder), base/time.py */
+    double eoc_q, eoc_r;      /* scheduled end-of-chain event time */
+    int32_t eoc_next_active;  /* particle drawn (randint) when the end-of-chain candidate was created */
+    int32_t active_cell;      /* flat cell index the occupancy system attributes to the active particle */
+    uint64_t event_counter;   /* events committed so far: the random-stream event index */
+    uint32_t stream;          /* random-stream id of this chain (Philox key word 0) */
+    int32_t pending_kind;     /* EcmcEventKind of a candidate kept across a host control event, or 0 */
+    int32_t pending_target;   /* pair: target id; veto: target cell */
+    int32_t reserved;
+    double pending_q, pending_r;
+    double pending_rate;      /* bounding event rate stored by the handler for the confirmation step */
+} EcmcChainState;
+
+enum EcmcEventKind {
+    ECMC_EVENT_NONE = 0,
+    ECMC_EVENT_PAIR = 1,          /* nearby-cell or surplus pair factor */
+    ECMC_EVENT_CELL_VETO = 2,
+    ECMC_EVENT_CELL_BOUNDARY = 3,
+    ECMC_EVENT_END_OF_CHAIN = 4
+};
+
+/* One committed event, as the scheduler + winning handler of the reference would report it. */
+typedef struct EcmcEventRecord {
+    int32_t kind;             /* EcmcEventKind of the winner (argmin) */
+    int32_t target;           /* pair / accepted or rejected veto: target particle (-1: empty veto cell) */
+    int32_t target_cell;      /* veto: sampled target cell; boundary: new cell; else -1 */
+    int32_t accepted;         /* 1 if the velocity was handed over (lifting happened) */
+    int32_t n_candidates;     /* finite candidate times that entered the argmin */
+    int32_t new_active;       /* active particle after the event */
+    int32_t new_direction;
+    int32_t reserved;
+    double time_q, time_r;    /* event time */
+    double active_pos[ECMC_MAX_DIM]; /* position of the (old) active particle after the event */
+} EcmcEventRecord;
+
+typedef struct EcmcStats {
+    uint64_t events;            /* events committed by this call, all chains */
+    uint64_t pair_events;
+    uint64_t veto_events;
+    uint64_t veto_accepted;
+    uint64_t boundary_events;
+    uint64_t end_of_chain_events;
+    uint64_t candidates;        /* finite candidates that entered an argmin */
+    uint64_t bound_violations;  /* real derivative exceeded its bound (reference: bounding_potential_warning) */
+    uint64_t capacity_errors;   /* surplus / occupant overflow (fatal: results invalid) */
+    uint64_t reserved[3];
+} EcmcStats;
+
+typedef struct EcmcHandle EcmcHandle;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------- */
+/* Build an engine for n_chains independent chains on CUDA device `device`. Copies the program and its tables. */
+int ecmc_create(const EcmcProgram *program, int device, int n_chains, EcmcHandle **out);
+void ecmc_destroy(EcmcHandle *h);
+const char *ecmc_last_error(const EcmcHandle *h); /* h may be NULL: error of the last failed ecmc_create */
+int ecmc_abi_version(void);
+
+/* ---- state (replaces TreeStateHandler extract/insert, jellyfysh/state_handler/tree_state_handler.py:104-230) */
+/* positions: [n_chains][n_particles][dimension] doubles; charges: [n_chains][n_particles] or NULL (all 1.0). */
+int ecmc_upload_positions(EcmcHandle *h, const double *positions, const double *charges);
+int ecmc_download_positions(EcmcHandle *h, double *positions);
+/* InitialChainStartOfRunEventHandler (initial_chain_start_of_run_event_handler.py:92-131) +
+ * SingleActiveCellOccupancy.initialize (single_active_cell_occupancy.py:95-121): bins all particles,
+ * activates program.initial_active at time 0 and schedules the first end-of-chain event.
+ * streams: n_chains random-stream ids, or NULL for first_stream + chain index. */
+int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_stream);
+/* explicit lifting / cell state, for resuming and for event-by-event parity checks */
+int ecmc_upload_chain_states(EcmcHandle *h, const EcmcChainState *states);
+int ecmc_download_chain_states(EcmcHandle *h, EcmcChainState *states);
+/* occupants: [n_chains][n_cells][max_occupants] (-1 = empty); surplus: [n_chains][max_surplus];
+ * n_surplus: [n_chains] */
+int ecmc_upload_cells(EcmcHandle *h, const int32_t *occupants, const int32_t *surplus, const int32_t *n_surplus);
+int ecmc_download_cells(EcmcHandle *h, int32_t *occupants, int32_t *surplus, int32_t *n_surplus);
+
+/* ---- the hot path -------------------------------------------------------------------------------------- */
+/* Advance every chain until its next event time would reach (until_q, until_r) or it has committed
+ * max_events_per_chain events in this call, whichever is first (max_events_per_chain <= 0: no event limit;
+ * until_q = +inf: no time limit). Chains stopped by the time limit are time-sliced to it, as a sampling
+ * handler does (jellyfysh/event_handler/fixed_interval_sampling_event_handler.py:96-109).
+ * Asynchronous on the handle's stream; stats (may be NULL) are valid after ecmc_sync. */
+int ecmc_run(EcmcHandle *h, double until_q, double until_r, int64_t max_events_per_chain);
+int ecmc_sync(EcmcHandle *h, EcmcStats *stats);
+/* Same, but additionally writes the first `records_per_chain` events of every chain of this call to
+ * records[n_chains][records_per_chain] (host buffer, filled at return; kind == ECMC_EVENT_NONE marks unused
+ * slots). Synchronous. Used by the parity tests. */
+int ecmc_run_recorded(EcmcHandle *h, double until_q, double until_r, int64_t max_events_per_chain,
+                      EcmcEventRecord *records, int32_t records_per_chain, EcmcStats *stats);
+/* Host-buffer convenience for the plugin layer: upload positions -> start -> run -> download, one call. */
+int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
+                       double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
+                       EcmcStats *stats);
+/* The CUDA stream the handle launches on (a cudaStream_t), so callers can time with events on it. */
+void *ecmc_stream(EcmcHandle *h);
+/* Seconds of device time (CUDA events on the handle's stream) spent in event kernels since create. */
+double ecmc_kernel_seconds(EcmcHandle *h);
+uint64_t ecmc_kernel_launches(EcmcHandle *h);
+
+/* ---- batched potential arithmetic on the device -------------------------------------------------------
+ * Back the host-side Potential classes (derivative / displacement of jellyfysh/potential/potential.py:154-301)
+ * and the init-time estimators. separations: [n][dimension]; charges: [n][2] or NULL; out: [n].
+ * direction is the direction of motion, speed the (positive) velocity component. */
+int ecmc_potential_derivative(const EcmcPotential *potential, int dimension, double system_length, int direction,
+                              double speed, size_t n, const double *separations, const double *charges,
+                              double *out, int device);
+int ecmc_potential_displacement(const EcmcPotential *potential, int dimension, double system_length, int direction,
+                                double speed, size_t n, const double *separations, const double *charges,
+                                const double *potential_changes, double *out, int device);
+/* Draws of the counter-based random stream, for host-side reproduction: out[n] uniform doubles in [0,1)
+ * of (seed, stream, event, slot), starting at draw index `first`. Pure host function (no device needed). */
+void ecmc_random_doubles(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t first, size_t n,
+                         double *out);
+void ecmc_random_words(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t first, size_t n,
+                       uint32_t *out);
+
+/* Random-stream slots: (kind << 24) | index. See DESIGN.md. */
+#define ECMC_SLOT_PAIR_TIME 1u       /* index = target particle; double 0 -> expovariate(beta) */
+#define ECMC_SLOT_VETO_TIME 2u       /* double 0 -> Walker uniform, double 1 -> expovariate(beta) */
+#define ECMC_SLOT_VETO_CHOICE 3u     /* words -> random.choice over the Walker table (rejection loop) */
+#define ECMC_SLOT_CONFIRM 4u         /* double 0 -> uniform(0, bounding rate) in the out-state */
+#define ECMC_SLOT_END_OF_CHAIN 5u    /* words -> randint(0, n_particles - 1) (rejection loop) */
+#define ECMC_SLOT_LIFTING 6u         /* doubles -> Lifting.insert / RatioLifting draws */
+#define ECMC_SLOT(kind, index) (((uint32_t)(kind) << 24) | ((uint32_t)(index) & 0xFFFFFFu))
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECMC_B200_H */

@@ -1,0 +1,134 @@
+"""ctypes mirror of include/ecmc.h (the C ABI of libecmc_b200.so). Plain data only, no computation."""
+import ctypes as C
+
+ECMC_ABI_VERSION = 1
+ECMC_MAX_DIM = 3
+
+ECMC_OK = 0
+ECMC_ERR_INVALID = -1
+ECMC_ERR_CUDA = -2
+ECMC_ERR_STATE = -3
+ECMC_ERR_CAPACITY = -4
+
+POT_NONE = 0
+POT_INVERSE_POWER = 1
+POT_LENNARD_JONES = 2
+POT_DISPLACED_EVEN_POWER = 3
+POT_HARD_SPHERE = 4
+POT_HARD_DIPOLE = 5
+POT_MERGED_IMAGE_COULOMB = 6
+POT_INVERSE_POWER_COULOMB_BOUNDING = 7
+
+PAIR_NONE = 0
+PAIR_TWO_LEAF_UNIT = 1
+PAIR_TWO_LEAF_UNIT_BOUNDING = 2
+
+EVENT_NONE = 0
+EVENT_PAIR = 1
+EVENT_CELL_VETO = 2
+EVENT_CELL_BOUNDARY = 3
+EVENT_END_OF_CHAIN = 4
+EVENT_NAMES = {EVENT_NONE: "none", EVENT_PAIR: "pair", EVENT_CELL_VETO: "cell_veto",
+               EVENT_CELL_BOUNDARY: "cell_boundary", EVENT_END_OF_CHAIN: "end_of_chain"}
+
+SLOT_PAIR_TIME = 1
+SLOT_VETO_TIME = 2
+SLOT_VETO_CHOICE = 3
+SLOT_CONFIRM = 4
+SLOT_END_OF_CHAIN = 5
+SLOT_LIFTING = 6
+
+
+def slot(kind: int, index: int = 0) -> int:
+    """ECMC_SLOT(kind, index) of include/ecmc.h."""
+    return ((kind << 24) | (index & 0xFFFFFF)) & 0xFFFFFFFF
+
+
+class EcmcPotential(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("params", C.c_double * 6)]
+
+    @classmethod
+    def make(cls, kind: int, *params: float) -> "EcmcPotential":
+        p = cls()
+        p.kind = kind
+        for i, value in enumerate(params):
+            p.params[i] = float(value)
+        return p
+
+
+class EcmcWalkerTable(C.Structure):
+    _fields_ = [("n_entries", C.c_int32), ("reserved", C.c_int32),
+                ("cell_a", C.POINTER(C.c_int32)), ("cell_b", C.POINTER(C.c_int32)),
+                ("rate_a", C.POINTER(C.c_double)),
+                ("total_rate", C.c_double), ("mean_rate", C.c_double)]
+
+
+class EcmcVetoTables(C.Structure):
+    _fields_ = [("upper", EcmcWalkerTable * ECMC_MAX_DIM), ("lower", EcmcWalkerTable * ECMC_MAX_DIM),
+                ("bounds", C.POINTER(C.c_double))]
+
+
+class EcmcProgram(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("dimension", C.c_int32), ("n_particles", C.c_int32),
+                ("reserved0", C.c_int32),
+                ("system_length", C.c_double), ("beta", C.c_double),
+                ("cells_per_side", C.c_int32 * ECMC_MAX_DIM), ("neighbor_layers", C.c_int32),
+                ("max_occupants", C.c_int32), ("max_surplus", C.c_int32),
+                ("pair_handler", C.c_int32), ("pair_use_charge", C.c_int32),
+                ("pair_potential", EcmcPotential), ("pair_bounding_potential", EcmcPotential),
+                ("veto_enabled", C.c_int32), ("veto_use_charge", C.c_int32),
+                ("veto_potential", EcmcPotential), ("veto_target_charge", C.c_double),
+                ("veto_tables", C.POINTER(EcmcVetoTables)),
+                ("chain_time", C.c_double), ("speed", C.c_double),
+                ("initial_direction", C.c_int32), ("initial_active", C.c_int32),
+                ("seed", C.c_uint32), ("reserved1", C.c_uint32)]
+
+
+class EcmcChainState(C.Structure):
+    _fields_ = [("active", C.c_int32), ("direction", C.c_int32),
+                ("time_q", C.c_double), ("time_r", C.c_double),
+                ("eoc_q", C.c_double), ("eoc_r", C.c_double),
+                ("eoc_next_active", C.c_int32), ("active_cell", C.c_int32),
+                ("event_counter", C.c_uint64),
+                ("stream", C.c_uint32), ("pending_kind", C.c_int32),
+                ("pending_target", C.c_int32), ("reserved", C.c_int32),
+                ("pending_q", C.c_double), ("pending_r", C.c_double), ("pending_rate", C.c_double)]
+
+
+class EcmcEventRecord(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("target", C.c_int32), ("target_cell", C.c_int32), ("accepted", C.c_int32),
+                ("n_candidates", C.c_int32), ("new_active", C.c_int32), ("new_direction", C.c_int32),
+                ("reserved", C.c_int32),
+                ("time_q", C.c_double), ("time_r", C.c_double), ("active_pos", C.c_double * ECMC_MAX_DIM)]
+
+
+class EcmcStats(C.Structure):
+    _fields_ = [("events", C.c_uint64), ("pair_events", C.c_uint64), ("veto_events", C.c_uint64),
+                ("veto_accepted", C.c_uint64), ("boundary_events", C.c_uint64),
+                ("end_of_chain_events", C.c_uint64), ("candidates", C.c_uint64),
+                ("bound_violations", C.c_uint64), ("capacity_errors", C.c_uint64),
+                ("reserved", C.c_uint64 * 3)]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
+
+
+# numpy dtypes with the same memory layout (records / chain states are exchanged as arrays)
+def record_dtype():
+    import numpy as np
+    return np.dtype([("kind", "<i4"), ("target", "<i4"), ("target_cell", "<i4"), ("accepted", "<i4"),
+                     ("n_candidates", "<i4"), ("new_active", "<i4"), ("new_direction", "<i4"), ("reserved", "<i4"),
+                     ("time_q", "<f8"), ("time_r", "<f8"), ("active_pos", "<f8", (ECMC_MAX_DIM,))])
+
+
+def chain_state_dtype():
+    import numpy as np
+    return np.dtype([("active", "<i4"), ("direction", "<i4"), ("time_q", "<f8"), ("time_r", "<f8"),
+                     ("eoc_q", "<f8"), ("eoc_r", "<f8"), ("eoc_next_active", "<i4"), ("active_cell", "<i4"),
+                     ("event_counter", "<u8"), ("stream", "<u4"), ("pending_kind", "<i4"),
+                     ("pending_target", "<i4"), ("reserved", "<i4"),
+                     ("pending_q", "<f8"), ("pending_r", "<f8"), ("pending_rate", "<f8")])
+
+
+assert C.sizeof(EcmcEventRecord) == 72
+assert C.sizeof(EcmcChainState) == 96

@@ -1,0 +1,1397 @@
+/* ecmc_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * A plain-C restatement of the JeLLyFysh algorithms on the hot path (next-event-time computation for the
+ * active particle -> argmin -> lifting -> commit), written function by function after the reference's
+ * Python / C sources, with the same operation order, Python float semantics (`%`, divmod, `**` = libm pow)
+ * and libm calls. Paths cited below are relative to the reference checkout.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use this file.
+ * The product (jellyfysh_b200/, libecmc_b200.so) never links, imports or calls it.
+ *
+ * Parity pinning: tests/test_oracle_*.py check this file against (i) the known-answer constants of the
+ * reference's own unit tests and (ii) golden vectors and whole-chain traces recorded from the running
+ * reference (tests/golden/make_golden.py).
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#include "../include/ecmc.h"
+
+#define ORC_API __attribute__((visibility("default")))
+#define ORC_INF (1.0 / 0.0)
+
+/* ================================================================================================== */
+/* Python float semantics                                                                             */
+/* ================================================================================================== */
+
+/* CPython float_rem (Objects/floatobject.c): result has the sign of the divisor. Used by
+ * jellyfysh/setting/hypercubic_setting.py:117,172. */
+static double py_mod(double vx, double wx) {
+    double mod = fmod(vx, wx);
+    if (mod) {
+        if ((wx < 0) != (mod < 0)) mod += wx;
+    } else {
+        mod = copysign(0.0, wx);
+    }
+    return mod;
+}
+
+/* CPython float_divmod. Used by jellyfysh/base/time.py:101,131. */
+static void py_divmod(double vx, double wx, double *quotient, double *remainder) {
+    double mod = fmod(vx, wx);
+    double div = (vx - mod) / wx;
+    double floordiv;
+    if (mod) {
+        if ((wx < 0) != (mod < 0)) {
+            mod += wx;
+            div -= 1.0;
+        }
+    } else {
+        mod = copysign(0.0, wx);
+    }
+    if (div) {
+        floordiv = floor(div);
+        if (div - floordiv > 0.5) floordiv += 1.0;
+    } else {
+        floordiv = copysign(0.0, vx / wx);
+    }
+    *quotient = floordiv;
+    *remainder = mod;
+}
+
+/* ================================================================================================== */
+/* base/time.py                                                                                       */
+/* ================================================================================================== */
+typedef struct { double q, r; } otime;
+
+/* Time.__add__, jellyfysh/base/time.py:115-133 */
+static otime time_add(otime t, double other) {
+    otime out;
+    if (!isinf(other)) {
+        double add_q, new_r;
+        py_divmod(t.r + other, 1.0, &add_q, &new_r);
+        out.q = t.q + add_q;
+        out.r = new_r;
+    } else {
+        out.q = other;
+        out.r = other;
+    }
+    return out;
+}
+/* Time.__sub__, jellyfysh/base/time.py:135-149 */
+static double time_sub(otime a, otime b) { return a.q - b.q + a.r - b.r; }
+/* Time.__lt__, jellyfysh/base/time.py:167-182; same comparison as heap.c:176-178 */
+static int time_lt(otime a, otime b) { return a.q < b.q || (a.q == b.q && a.r < b.r); }
+/* Time.from_float, jellyfysh/base/time.py:87-101 */
+static otime time_from_float(double t) {
+    otime out;
+    if (!isinf(t)) py_divmod(t, 1.0, &out.q, &out.r);
+    else { out.q = t; out.r = t; }
+    return out;
+}
+
+ORC_API void orc_time_add(double q, double r, double other, double *out_q, double *out_r) {
+    otime t = {q, r};
+    t = time_add(t, other);
+    *out_q = t.q; *out_r = t.r;
+}
+ORC_API double orc_time_sub(double q1, double r1, double q2, double r2) {
+    otime a = {q1, r1}, b = {q2, r2};
+    return time_sub(a, b);
+}
+ORC_API void orc_time_from_float(double t, double *out_q, double *out_r) {
+    otime x = time_from_float(t);
+    *out_q = x.q; *out_r = x.r;
+}
+
+/* ================================================================================================== */
+/* setting/hypercubic_setting.py: periodic boundaries                                                 */
+/* ================================================================================================== */
+/* correct_position_entry, hypercubic_setting.py:117 */
+static double correct_position_entry(double x, double L) { return py_mod(x, L); }
+/* correct_separation_entry, hypercubic_setting.py:172 */
+static double correct_separation_entry(double s, double L) {
+    double half = L / 2.0;
+    return py_mod(s + half, L) - half;
+}
+/* separation_vector, hypercubic_setting.py:138-140 */
+static void separation_vector(const double *ref, const double *target, int D, double L, double *sep) {
+    for (int d = 0; d < D; d++) sep[d] = correct_separation_entry(target[d] - ref[d], L);
+}
+ORC_API double orc_correct_position_entry(double x, double L) { return correct_position_entry(x, L); }
+ORC_API double orc_correct_separation_entry(double s, double L) { return correct_separation_entry(s, L); }
+
+/* ================================================================================================== */
+/* base/vectors.py                                                                                    */
+/* ================================================================================================== */
+/* Python's builtin sum() over floats. CPython >= 3.12 (the interpreter the reference runs under in this
+ * container and on the GPU box) uses Neumaier compensated summation (Python/bltinmodule.c, builtin_sum_impl);
+ * PyPy and CPython < 3.12 add naively. The start value is int 0, so the first float is taken as is.
+ * Mode 1 (default) = CPython >= 3.12, mode 0 = naive. */
+static int g_sum_mode = 1;
+ORC_API void orc_set_sum_mode(int compensated) { g_sum_mode = compensated; }
+typedef struct { double f, c; int n; } pysum;
+static void pysum_init(pysum *s) { s->f = 0.0; s->c = 0.0; s->n = 0; }
+static void pysum_add(pysum *s, double x) {
+    if (s->n++ == 0) { s->f = 0 + x; return; }
+    if (!g_sum_mode) { s->f = s->f + x; return; }
+    double t = s->f + x;
+    if (fabs(s->f) >= fabs(x)) s->c += (s->f - t) + x;
+    else s->c += (x - t) + s->f;
+    s->f = t;
+}
+static double pysum_result(const pysum *s) {
+    if (s->n == 0) return 0.0;
+    double f = s->f;
+    if (g_sum_mode && s->c && isfinite(s->c)) f += s->c;
+    return f;
+}
+/* norm_sq, base/vectors.py:60 */
+static double v_norm_sq(const double *v, int D) {
+    pysum s;
+    pysum_init(&s);
+    for (int d = 0; d < D; d++) pysum_add(&s, v[d] * v[d]);
+    return pysum_result(&s);
+}
+/* norm: `** 0.5` is libm pow, base/vectors.py:43 */
+static double v_norm(const double *v, int D) { return pow(v_norm_sq(v, D), 0.5); }
+
+/* math.sqrt raises ValueError on a negative argument; the reference uses this as control flow
+ * (jellyfysh/potential/abstracts.py:440-454). *err is set instead. */
+static double checked_sqrt(double x, int *err) {
+    if (x < 0.0) { *err = 1; return NAN; }
+    return sqrt(x);
+}
+static double other_components_sq(const double *v, int D, int dir) {
+    pysum s;
+    pysum_init(&s);
+    for (int d = 0; d < D; d++)
+        if (d != dir) pysum_add(&s, pow(v[d], 2.0));
+    return pysum_result(&s);
+}
+/* displacement_until_new_norm_sq_component_positive, base/vectors.py:153-182 */
+static double disp_new_norm_sq_positive(const double *v, int D, double new_norm_sq, int dir, int *err) {
+    return v[dir] - checked_sqrt(new_norm_sq - other_components_sq(v, D, dir), err);
+}
+/* displacement_until_new_norm_sq_component_negative, base/vectors.py:185-214 */
+static double disp_new_norm_sq_negative(const double *v, int D, double new_norm_sq, int dir, int *err) {
+    return v[dir] + checked_sqrt(new_norm_sq - other_components_sq(v, D, dir), err);
+}
+
+/* ================================================================================================== */
+/* potential/inverse_power_potential.py                                                               */
+/* ================================================================================================== */
+typedef struct {
+    double power, prefactor;
+    double two_over_power, power_over_two, power_plus_two;
+} inverse_power;
+
+static inverse_power ip_make(double power, double prefactor) {
+    inverse_power p;
+    p.power = power; p.prefactor = prefactor;
+    p.two_over_power = 2.0 / power;       /* inverse_power_potential.py:66 */
+    p.power_over_two = power / 2.0;       /* :67 */
+    p.power_plus_two = power + 2;         /* :68 */
+    return p;
+}
+/* standard_velocity_derivative, inverse_power_potential.py:71-94 */
+static double ip_derivative(const inverse_power *p, int dir, const double *sep, int D, double c1, double c2) {
+    return p->power * sep[dir] / pow(v_norm(sep, D), p->power_plus_two) * p->prefactor * c1 * c2;
+}
+/* potential, inverse_power_potential.py:126-143 */
+static double ip_potential(const inverse_power *p, double charge_product, const double *sep, int D) {
+    return charge_product * p->prefactor / pow(v_norm_sq(sep, D), p->power_over_two);
+}
+/* _displacement_repulsive, inverse_power_potential.py:145-160 */
+static double ip_displacement_repulsive(const inverse_power *p, int dir, double cp, double dU, double *sep, int D,
+                                        int *err) {
+    if (sep[dir] <= 0.0) return ORC_INF;
+    double tmp[ECMC_MAX_DIM];
+    memcpy(tmp, sep, sizeof(double) * D);
+    tmp[dir] = 0.0;
+    double maximum_potential = ip_potential(p, cp, tmp, D);
+    double current_potential = ip_potential(p, cp, sep, D);
+    if (dU < maximum_potential - current_potential) {
+        double new_norm_sq = pow(cp * p->prefactor / (current_potential + dU), p->two_over_power);
+        return disp_new_norm_sq_positive(sep, D, new_norm_sq, dir, err);
+    }
+    return ORC_INF;
+}
+/* _displacement_attractive, inverse_power_potential.py:162-179 */
+static double ip_displacement_attractive(const inverse_power *p, int dir, double cp, double dU, double *sep, int D,
+                                         int *err) {
+    double current_displacement = 0.0;
+    if (sep[dir] > 0.0) {
+        current_displacement += sep[dir];
+        sep[dir] = 0.0;
+    }
+    double current_potential = ip_potential(p, cp, sep, D);
+    if (current_potential + dU >= 0.0) return ORC_INF;
+    double new_norm_sq = pow(cp * p->prefactor / (current_potential + dU), p->two_over_power);
+    current_displacement += disp_new_norm_sq_negative(sep, D, new_norm_sq, dir, err);
+    return current_displacement;
+}
+/* standard_velocity_displacement, inverse_power_potential.py:96-124 */
+static double ip_displacement(const inverse_power *p, int dir, double *sep, int D, double c1, double c2, double dU,
+                              int *err) {
+    double cp = c1 * c2;
+    double prefactor_product = p->prefactor * cp;
+    return prefactor_product > 0 ? ip_displacement_repulsive(p, dir, cp, dU, sep, D, err)
+                                 : ip_displacement_attractive(p, dir, cp, dU, sep, D, err);
+}
+
+/* ================================================================================================== */
+/* potential/abstracts.py: MexicanHatPotential; lennard_jones_potential.py; displaced_even_power...   */
+/* ================================================================================================== */
+typedef struct {
+    int kind; /* ECMC_POT_LENNARD_JONES or ECMC_POT_DISPLACED_EVEN_POWER */
+    double prefactor, equilibrium_separation, equilibrium_separation_squared;
+    /* LJ */
+    double characteristic_length;
+    inverse_power six, twelve;
+    /* displaced even power */
+    double power, inverse_power_;
+} mexican_hat;
+
+/* LennardJonesPotential.__init__, lennard_jones_potential.py:42-61 */
+static mexican_hat lj_make(double prefactor, double characteristic_length) {
+    mexican_hat m;
+    memset(&m, 0, sizeof(m));
+    m.kind = ECMC_POT_LENNARD_JONES;
+    m.prefactor = prefactor;
+    m.equilibrium_separation = characteristic_length * pow(2.0, 1.0 / 6.0);
+    m.equilibrium_separation_squared = pow(m.equilibrium_separation, 2.0); /* abstracts.py:323 */
+    m.characteristic_length = characteristic_length;
+    m.six = ip_make(6.0, -prefactor * pow(characteristic_length, 6.0));
+    m.twelve = ip_make(12.0, prefactor * pow(characteristic_length, 12.0));
+    return m;
+}
+/* DisplacedEvenPowerPotential.__init__, displaced_even_power_potential.py:45-71 */
+static mexican_hat dep_make(double prefactor, double equilibrium_separation, double power) {
+    mexican_hat m;
+    memset(&m, 0, sizeof(m));
+    m.kind = ECMC_POT_DISPLACED_EVEN_POWER;
+    m.prefactor = prefactor;
+    m.equilibrium_separation = equilibrium_separation;
+    m.equilibrium_separation_squared = equilibrium_separation * equilibrium_separation;
+    m.power = power;
+    m.inverse_power_ = 1.0 / power;
+    return m;
+}
+static double mh_potential(const mexican_hat *m, const double *sep, int D) {
+    if (m->kind == ECMC_POT_LENNARD_JONES) {
+        /* lennard_jones_potential.py:83-98 */
+        return ip_potential(&m->six, 1.0, sep, D) + ip_potential(&m->twelve, 1.0, sep, D);
+    }
+    /* displaced_even_power_potential.py:96-111 */
+    double distance_from_minimum = v_norm(sep, D) - m->equilibrium_separation;
+    return m->prefactor * pow(distance_from_minimum, m->power);
+}
+static double mh_invert_inside(const mexican_hat *m, double potential) {
+    if (m->kind == ECMC_POT_LENNARD_JONES) {
+        /* lennard_jones_potential.py:100-115 */
+        double sigma_over_r_six = (1 + pow(1 + 4 * potential / m->prefactor, 0.5)) / 2;
+        return m->characteristic_length / pow(sigma_over_r_six, 1.0 / 6.0);
+    }
+    /* displaced_even_power_potential.py:113-127 */
+    return m->equilibrium_separation - pow(potential / m->prefactor, m->inverse_power_);
+}
+static double mh_invert_outside(const mexican_hat *m, double potential) {
+    if (m->kind == ECMC_POT_LENNARD_JONES) {
+        /* lennard_jones_potential.py:117-135 */
+        if (potential >= 0.0) return ORC_INF;
+        double sigma_over_r_six = (1 - pow(1 + 4 * potential / m->prefactor, 0.5)) / 2;
+        return m->characteristic_length / pow(sigma_over_r_six, 1.0 / 6.0);
+    }
+    /* displaced_even_power_potential.py:129-142 */
+    return m->equilibrium_separation + pow(potential / m->prefactor, m->inverse_power_);
+}
+static double mh_derivative(const mexican_hat *m, int dir, const double *sep, int D) {
+    if (m->kind == ECMC_POT_LENNARD_JONES) {
+        /* lennard_jones_potential.py:63-81 */
+        return ip_derivative(&m->six, dir, sep, D, 1.0, 1.0) + ip_derivative(&m->twelve, dir, sep, D, 1.0, 1.0);
+    }
+    /* displaced_even_power_potential.py:73-94 */
+    double n = v_norm(sep, D);
+    return -m->power * m->prefactor * pow(n - m->equilibrium_separation, m->power - 1) * sep[dir] / n;
+}
+
+static double mh_front_inside(const mexican_hat *m, int dir, double dU, double *sep, int D, int *err);
+
+/* _displacement_front_outside_sphere, abstracts.py:384-410 */
+static double mh_front_outside(const mexican_hat *m, int dir, double current_potential, double dU, const double *sep,
+                               int D, int *err) {
+    double new_norm = mh_invert_outside(m, current_potential + dU);
+    return disp_new_norm_sq_negative(sep, D, new_norm * new_norm, dir, err);
+}
+/* _displacement_behind_inside_sphere, abstracts.py:489-530 */
+static double mh_behind_inside(const mexican_hat *m, int dir, double current_potential, double dU, double *sep, int D,
+                               int *err) {
+    double at_max[ECMC_MAX_DIM];
+    memcpy(at_max, sep, sizeof(double) * D);
+    at_max[dir] = 0.0;
+    double maximum_potential_inside = mh_potential(m, at_max, D);
+    double potential_difference = maximum_potential_inside - current_potential;
+    double displacement;
+    if (dU < potential_difference) {
+        double new_norm = mh_invert_inside(m, current_potential + dU);
+        displacement = disp_new_norm_sq_positive(sep, D, new_norm * new_norm, dir, err);
+    } else {
+        displacement = sep[dir];
+        sep[dir] = 0.0;
+        dU -= potential_difference;
+        displacement += mh_front_inside(m, dir, dU, sep, D, err);
+    }
+    return displacement;
+}
+/* _displacement_front_inside_sphere, abstracts.py:456-487 */
+static double mh_front_inside(const mexican_hat *m, int dir, double dU, double *sep, int D, int *err) {
+    double displacement = disp_new_norm_sq_negative(sep, D, m->equilibrium_separation_squared, dir, err);
+    if (*err) return NAN;
+    sep[dir] -= displacement;
+    double current_potential = mh_potential(m, sep, D);
+    displacement += mh_front_outside(m, dir, current_potential, dU, sep, D, err);
+    return displacement;
+}
+/* _displacement_behind_outside_sphere, abstracts.py:412-454: the try block covers every call, the
+ * except ValueError branch restarts from the (possibly already modified) separation. */
+static double mh_behind_outside(const mexican_hat *m, int dir, double dU, double *sep, int D, int *err) {
+    int local_err = 0;
+    double displacement = disp_new_norm_sq_positive(sep, D, m->equilibrium_separation_squared, dir, &local_err);
+    if (!local_err) {
+        sep[dir] -= displacement;
+        double current_potential = mh_potential(m, sep, D);
+        displacement += mh_behind_inside(m, dir, current_potential, dU, sep, D, &local_err);
+    }
+    if (local_err) {
+        displacement = sep[dir];
+        sep[dir] = 0.0;
+        double current_potential = mh_potential(m, sep, D);
+        displacement += mh_front_outside(m, dir, current_potential, dU, sep, D, err);
+    }
+    return displacement;
+}
+/* standard_velocity_displacement, abstracts.py:336-382 */
+static double mh_displacement(const mexican_hat *m, int dir, double *sep, int D, double dU, int *err) {
+    double norm_of_separation = v_norm(sep, D);
+    double displacement;
+    if (norm_of_separation >= m->equilibrium_separation) {
+        if (sep[dir] <= 0.0) {
+            double current_potential = mh_potential(m, sep, D);
+            displacement = mh_front_outside(m, dir, current_potential, dU, sep, D, err);
+        } else {
+            displacement = mh_behind_outside(m, dir, dU, sep, D, err);
+        }
+    } else {
+        if (sep[dir] <= 0.0) {
+            displacement = mh_front_inside(m, dir, dU, sep, D, err);
+        } else {
+            double current_potential = mh_potential(m, sep, D);
+            displacement = mh_behind_inside(m, dir, current_potential, dU, sep, D, err);
+        }
+    }
+    return displacement;
+}
+
+/* ================================================================================================== */
+/* potential/hard_sphere_potential.py, hard_dipole_potential.py (general velocity)                    */
+/* ================================================================================================== */
+static double v_dot(const double *a, const double *b, int D) {
+    pysum s;
+    pysum_init(&s);
+    for (int d = 0; d < D; d++) pysum_add(&s, a[d] * b[d]);
+    return pysum_result(&s);
+}
+/* HardSpherePotential.displacement, hard_sphere_potential.py:65-99 */
+static double hs_displacement(double radius, const double *velocity, const double *sep, int D) {
+    double diameter_squared = 4.0 * radius * radius;
+    double velocity_squared = v_norm_sq(velocity, D);
+    double separation_squared = v_norm_sq(sep, D);
+    double vds = v_dot(velocity, sep, D);
+    double square_root_term = vds * vds - velocity_squared * (separation_squared - diameter_squared);
+    return (square_root_term >= 0.0 && vds >= 0.0) ? (vds - sqrt(square_root_term)) / velocity_squared : ORC_INF;
+}
+/* HardDipolePotential.displacement, hard_dipole_potential.py:75-114 */
+static double hd_displacement(double min_sep, double max_sep, const double *velocity, const double *sep, int D) {
+    double min_sq = min_sep * min_sep, max_sq = max_sep * max_sep;
+    double velocity_squared = v_norm_sq(velocity, D);
+    double separation_squared = v_norm_sq(sep, D);
+    double vds = v_dot(velocity, sep, D);
+    if (vds >= 0.0) {
+        double minimum_term = vds * vds - velocity_squared * (separation_squared - min_sq);
+        if (minimum_term >= 0.0) return (vds - sqrt(minimum_term)) / velocity_squared;
+    }
+    double maximum_term = vds * vds - velocity_squared * (separation_squared - max_sq);
+    return (vds + sqrt(maximum_term)) / velocity_squared;
+}
+
+/* ================================================================================================== */
+/* potential/merged_image_coulomb_potential/merged_image_coulomb_potential.c                          */
+/* ================================================================================================== */
+typedef struct {
+    int fourier_cutoff, fourier_cutoff_sq, position_cutoff, position_cutoff_sq;
+    double alpha_over_length, two_alpha_over_length_root_pi, system_length, two_pi_over_length;
+    double prefactor;
+    double *fourier_array; /* [(fc+1)^3], index (i*(fc+1)+j)*(fc+1)+k */
+} mic_potential;
+
+/* construct_merged_image_coulomb_potential, merged_image_coulomb_potential.c:77-119 */
+static int mic_make(mic_potential *p, double prefactor, double alpha, int fourier_cutoff, int position_cutoff,
+                    double system_length) {
+    int n = fourier_cutoff + 1;
+    p->fourier_array = (double *)calloc((size_t)n * n * n, sizeof(double));
+    if (!p->fourier_array) return -1;
+    for (int k = 0; k < n; k++)
+        for (int j = 0; j < n; j++)
+            for (int i = 1; i < n; i++) {
+                double coefficient;
+                if (j == 0 && k == 0) coefficient = 1.0;
+                else if (k == 0 || j == 0) coefficient = 2.0;
+                else coefficient = 4.0;
+                double norm_sq = i * i + j * j + k * k;
+                p->fourier_array[(i * n + j) * n + k] =
+                    4.0 * i * coefficient / (norm_sq * system_length * system_length)
+                    * exp(-M_PI * M_PI * norm_sq / (alpha * alpha));
+            }
+    p->fourier_cutoff = fourier_cutoff;
+    p->fourier_cutoff_sq = fourier_cutoff * fourier_cutoff;
+    p->position_cutoff = position_cutoff;
+    p->position_cutoff_sq = position_cutoff * position_cutoff;
+    p->alpha_over_length = alpha / system_length;
+    p->two_alpha_over_length_root_pi = 2.0 * alpha / (system_length * sqrt(M_PI));
+    p->system_length = system_length;
+    p->two_pi_over_length = 2.0 * M_PI / system_length;
+    p->prefactor = prefactor;
+    return 0;
+}
+/* derivative, merged_image_coulomb_potential.c:205-274 */
+static double mic_c_derivative(const mic_potential *p, double sx, double sy, double sz) {
+    double derivative = 0.0;
+    double vector_norm, vector_sq, vector_x, vector_y_sq, vector_z_sq;
+    int cutoff_x, cutoff_y;
+    int i, j, k;
+    int n = p->fourier_cutoff + 1;
+    for (k = -p->position_cutoff; k < p->position_cutoff + 1; k++) {
+        vector_z_sq = (sz + k * p->system_length) * (sz + k * p->system_length);
+        cutoff_y = (int)sqrt(p->position_cutoff_sq - k * k);
+        for (j = -cutoff_y; j < cutoff_y + 1; j++) {
+            vector_y_sq = (sy + j * p->system_length) * (sy + j * p->system_length);
+            cutoff_x = (int)sqrt(p->position_cutoff_sq - j * j - k * k);
+            for (i = -cutoff_x; i < cutoff_x + 1; i++) {
+                vector_x = sx + i * p->system_length;
+                vector_sq = vector_x * vector_x + vector_y_sq + vector_z_sq;
+                vector_norm = sqrt(vector_sq);
+                derivative += vector_x * (p->two_alpha_over_length_root_pi
+                                          + erfc(p->alpha_over_length * vector_norm) / vector_norm) / vector_sq;
+            }
+        }
+    }
+    double delta_cos_x = cos(p->two_pi_over_length * sx);
+    double delta_sin_x = sin(p->two_pi_over_length * sx);
+    double delta_cos_y = cos(p->two_pi_over_length * sy);
+    double delta_sin_y = sin(p->two_pi_over_length * sy);
+    double delta_cos_z = cos(p->two_pi_over_length * sz);
+    double delta_sin_z = sin(p->two_pi_over_length * sz);
+    double cos_x = delta_cos_x, sin_x = delta_sin_x;
+    double cos_y = 1.0, sin_y = 0.0, cos_z = 1.0, sin_z = 0.0;
+    double store_cos_value;
+    for (i = 1; i < p->fourier_cutoff + 1; i++) {
+        cutoff_y = (int)sqrt(p->fourier_cutoff_sq - i * i);
+        for (j = 0; j < cutoff_y + 1; j++) {
+            cutoff_x = (int)sqrt(p->fourier_cutoff_sq - i * i - j * j);
+            for (k = 0; k < cutoff_x + 1; k++) {
+                derivative += p->fourier_array[(i * n + j) * n + k] * sin_x * cos_y * cos_z;
+                if (k != cutoff_x) {
+                    store_cos_value = cos_z;
+                    cos_z = store_cos_value * delta_cos_z - sin_z * delta_sin_z;
+                    sin_z = sin_z * delta_cos_z + store_cos_value * delta_sin_z;
+                } else if (j != cutoff_y) {
+                    store_cos_value = cos_y;
+                    cos_y = store_cos_value * delta_cos_y - sin_y * delta_sin_y;
+                    sin_y = sin_y * delta_cos_y + store_cos_value * delta_sin_y;
+                    cos_z = 1.0;
+                    sin_z = 0.0;
+                } else if (i != p->fourier_cutoff) {
+                    store_cos_value = cos_x;
+                    cos_x = store_cos_value * delta_cos_x - sin_x * delta_sin_x;
+                    sin_x = sin_x * delta_cos_x + store_cos_value * delta_sin_x;
+                    cos_y = 1.0;
+                    sin_y = 0.0;
+                    cos_z = 1.0;
+                    sin_z = 0.0;
+                }
+            }
+        }
+    }
+    return derivative;
+}
+/* permutation_3d, base/vectors.py:217-239 */
+static void permutation_3d(const double *v, int dir, double *out) {
+    out[0] = v[dir % 3]; out[1] = v[(dir + 1) % 3]; out[2] = v[(dir + 2) % 3];
+}
+/* MergedImageCoulombPotential.standard_velocity_derivative, merged_image_coulomb_potential.py:128-154 */
+static double mic_derivative(const mic_potential *p, int dir, const double *sep, double c1, double c2) {
+    double s[3];
+    permutation_3d(sep, dir, s);
+    return p->prefactor * c1 * c2 * mic_c_derivative(p, s[0], s[1], s[2]);
+}
+
+/* ================================================================================================== */
+/* potential/inverse_power_coulomb_bounding_potential/inverse_power_coulomb_bounding_potential.c      */
+/* ================================================================================================== */
+/* derivative, .c:53-55 */
+static double ipcb_c_derivative(double pp, double sx, double sy, double sz) {
+    return pp * sx / pow(sx * sx + sy * sy + sz * sz, 3.0 / 2.0);
+}
+/* potential, .c:66-68 */
+static double ipcb_c_potential(double pp, double sx, double sy, double sz) {
+    return pp / sqrt(sx * sx + sy * sy + sz * sz);
+}
+/* displacement, .c:85-139 */
+static double ipcb_c_displacement(double pp, double sx, double sy, double sz, double potential_change, double L) {
+    double half = L / 2.0;
+    double current_potential = ipcb_c_potential(pp, sx, sy, sz);
+    double potential_zero = ipcb_c_potential(pp, 0.0, sy, sz);
+    double potential_half_length = ipcb_c_potential(pp, half, sy, sz);
+    double per_length = fabs(potential_zero - potential_half_length);
+    double displacement = floor(potential_change / per_length) * L;
+    potential_change = fmod(potential_change, per_length);
+    double new_norm;
+    if (pp > 0.0) {
+        if (sx <= 0.0) {
+            displacement += half + sx;
+            sx = half;
+            current_potential = potential_half_length;
+        } else {
+            if (potential_change >= potential_zero - current_potential) {
+                potential_change -= (potential_zero - current_potential);
+                displacement += sx + half;
+                sx = half;
+                current_potential = potential_half_length;
+            }
+        }
+        new_norm = pp / (current_potential + potential_change);
+        displacement += (sx - sqrt(new_norm * new_norm - (sy * sy + sz * sz)));
+    } else {
+        if (sx > 0.0) {
+            displacement += sx;
+            sx = 0.0;
+            current_potential = potential_zero;
+        } else {
+            if (potential_change >= potential_half_length - current_potential) {
+                potential_change -= (potential_half_length - current_potential);
+                displacement += sx + L;
+                sx = 0.0;
+                current_potential = potential_zero;
+            }
+        }
+        new_norm = pp / (current_potential + potential_change);
+        displacement += (sx + sqrt(new_norm * new_norm - (sy * sy + sz * sz)));
+    }
+    return displacement;
+}
+/* InversePowerCoulombBoundingPotential wrappers, inverse_power_coulomb_bounding_potential.py:84-140 */
+static double ipcb_derivative(double prefactor, int dir, const double *sep, double c1, double c2) {
+    double s[3];
+    permutation_3d(sep, dir, s);
+    return ipcb_c_derivative(prefactor * c1 * c2, s[0], s[1], s[2]);
+}
+static double ipcb_displacement(double prefactor, int dir, const double *sep, double c1, double c2, double dU,
+                                double L) {
+    double s[3];
+    permutation_3d(sep, dir, s);
+    return ipcb_c_displacement(prefactor * c1 * c2, s[0], s[1], s[2], dU, L);
+}
+
+/* ================================================================================================== */
+/* Generic potential object driven by EcmcPotential                                                   */
+/* ================================================================================================== */
+typedef struct {
+    int kind;
+    inverse_power ip;
+    mexican_hat mh;
+    mic_potential mic;
+    double p0, p1; /* hard sphere radius / dipole min,max / ipcb prefactor */
+    double L;
+} opotential;
+
+static int pot_make(opotential *o, const EcmcPotential *p, double L) {
+    memset(o, 0, sizeof(*o));
+    o->kind = p->kind;
+    o->L = L;
+    switch (p->kind) {
+    case ECMC_POT_NONE: return 0;
+    case ECMC_POT_INVERSE_POWER: o->ip = ip_make(p->params[0], p->params[1]); return 0;
+    case ECMC_POT_LENNARD_JONES: o->mh = lj_make(p->params[0], p->params[1]); return 0;
+    case ECMC_POT_DISPLACED_EVEN_POWER: o->mh = dep_make(p->params[0], p->params[1], p->params[2]); return 0;
+    case ECMC_POT_HARD_SPHERE: o->p0 = p->params[0]; return 0;
+    case ECMC_POT_HARD_DIPOLE: o->p0 = p->params[0]; o->p1 = p->params[1]; return 0;
+    case ECMC_POT_MERGED_IMAGE_COULOMB:
+        return mic_make(&o->mic, p->params[0], p->params[1], (int)p->params[2], (int)p->params[3], L);
+    case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING: o->p0 = p->params[0]; return 0;
+    default: return -1;
+    }
+}
+static void pot_free(opotential *o) {
+    if (o->kind == ECMC_POT_MERGED_IMAGE_COULOMB) free(o->mic.fourier_array);
+    o->mic.fourier_array = NULL;
+}
+/* Potential.derivative for a standard velocity (StandardVelocityPotential.derivative, abstracts.py:80-103):
+ * standard_velocity_derivative(direction, ...) * speed */
+static double pot_derivative(const opotential *o, int dir, double speed, const double *sep, int D, double c1,
+                             double c2) {
+    switch (o->kind) {
+    case ECMC_POT_INVERSE_POWER: return ip_derivative(&o->ip, dir, sep, D, c1, c2) * speed;
+    case ECMC_POT_LENNARD_JONES:
+    case ECMC_POT_DISPLACED_EVEN_POWER: return mh_derivative(&o->mh, dir, sep, D) * speed;
+    case ECMC_POT_MERGED_IMAGE_COULOMB: return mic_derivative(&o->mic, dir, sep, c1, c2) * speed;
+    case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING: return ipcb_derivative(o->p0, dir, sep, c1, c2) * speed;
+    default: return NAN;
+    }
+}
+/* InvertiblePotential.displacement: time displacement. For standard-velocity potentials
+ * standard_velocity_displacement(...) / speed (abstracts.py:212-243); hard potentials take the velocity. */
+static double pot_displacement(const opotential *o, int dir, double speed, double *sep, int D, double c1, double c2,
+                               double dU) {
+    int err = 0;
+    double velocity[ECMC_MAX_DIM] = {0.0, 0.0, 0.0};
+    velocity[dir] = speed;
+    switch (o->kind) {
+    case ECMC_POT_INVERSE_POWER: return ip_displacement(&o->ip, dir, sep, D, c1, c2, dU, &err) / speed;
+    case ECMC_POT_LENNARD_JONES:
+    case ECMC_POT_DISPLACED_EVEN_POWER: return mh_displacement(&o->mh, dir, sep, D, dU, &err) / speed;
+    case ECMC_POT_HARD_SPHERE: return hs_displacement(o->p0, velocity, sep, D);
+    case ECMC_POT_HARD_DIPOLE: return hd_displacement(o->p0, o->p1, velocity, sep, D);
+    case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING: return ipcb_displacement(o->p0, dir, sep, c1, c2, dU, o->L) / speed;
+    default: return NAN;
+    }
+}
+static int pot_needs_potential_change(int kind) {
+    return !(kind == ECMC_POT_HARD_SPHERE || kind == ECMC_POT_HARD_DIPOLE);
+}
+
+/* Scalar entry points for the known-answer tests. sep has `dimension` entries and may be modified. */
+ORC_API double orc_potential_derivative(const EcmcPotential *p, int dimension, double L, int dir, double speed,
+                                        const double *sep, double c1, double c2) {
+    opotential o;
+    if (pot_make(&o, p, L)) return NAN;
+    double r = pot_derivative(&o, dir, speed, sep, dimension, c1, c2);
+    pot_free(&o);
+    return r;
+}
+ORC_API double orc_potential_displacement(const EcmcPotential *p, int dimension, double L, int dir, double speed,
+                                          const double *sep, double c1, double c2, double dU) {
+    opotential o;
+    double s[ECMC_MAX_DIM] = {0, 0, 0};
+    if (pot_make(&o, p, L)) return NAN;
+    memcpy(s, sep, sizeof(double) * dimension);
+    double r = pot_displacement(&o, dir, speed, s, dimension, c1, c2, dU);
+    pot_free(&o);
+    return r;
+}
+/* general-velocity hard potentials (hard-disk configs use non-axis velocities in the no-cell variant) */
+ORC_API double orc_hard_sphere_displacement(double radius, int dimension, const double *velocity, const double *sep) {
+    return hs_displacement(radius, velocity, sep, dimension);
+}
+ORC_API double orc_hard_dipole_displacement(double min_sep, double max_sep, int dimension, const double *velocity,
+                                            const double *sep) {
+    return hd_displacement(min_sep, max_sep, velocity, sep, dimension);
+}
+ORC_API void orc_potential_derivative_batch(const EcmcPotential *p, int dimension, double L, int dir, double speed,
+                                            size_t n, const double *seps, const double *charges, double *out) {
+    opotential o;
+    if (pot_make(&o, p, L)) return;
+    for (size_t i = 0; i < n; i++) {
+        double c1 = charges ? charges[2 * i] : 1.0, c2 = charges ? charges[2 * i + 1] : 1.0;
+        out[i] = pot_derivative(&o, dir, speed, seps + i * dimension, dimension, c1, c2);
+    }
+    pot_free(&o);
+}
+ORC_API void orc_potential_displacement_batch(const EcmcPotential *p, int dimension, double L, int dir, double speed,
+                                              size_t n, const double *seps, const double *charges, const double *dUs,
+                                              double *out) {
+    opotential o;
+    if (pot_make(&o, p, L)) return;
+    for (size_t i = 0; i < n; i++) {
+        double s[ECMC_MAX_DIM] = {0, 0, 0};
+        memcpy(s, seps + i * dimension, sizeof(double) * dimension);
+        double c1 = charges ? charges[2 * i] : 1.0, c2 = charges ? charges[2 * i + 1] : 1.0;
+        out[i] = pot_displacement(&o, dir, speed, s, dimension, c1, c2, dUs ? dUs[i] : 0.0);
+    }
+    pot_free(&o);
+}
+
+/* ================================================================================================== */
+/* Random stream (spec in DESIGN.md): Philox4x32-10, key = (stream, seed),                            */
+/* counter = (event_lo, event_hi, slot, block). Doubles are built like CPython's random():            */
+/* (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.                                                         */
+/* ================================================================================================== */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int round = 0; round < 10; round++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+static uint32_t rng_word(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t index) {
+    uint32_t c[4] = {(uint32_t)event, (uint32_t)(event >> 32), slot, index >> 2};
+    philox4x32_10(c, stream, seed);
+    return c[index & 3];
+}
+static double rng_double(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t index) {
+    uint32_t c[4] = {(uint32_t)event, (uint32_t)(event >> 32), slot, index >> 1};
+    philox4x32_10(c, stream, seed);
+    uint32_t a = c[2 * (index & 1)] >> 5, b = c[2 * (index & 1) + 1] >> 6;
+    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+}
+ORC_API void orc_random_doubles(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t first,
+                                size_t n, double *out) {
+    for (size_t i = 0; i < n; i++) out[i] = rng_double(seed, stream, event, slot, first + (uint32_t)i);
+}
+ORC_API void orc_random_words(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t first,
+                              size_t n, uint32_t *out) {
+    for (size_t i = 0; i < n; i++) out[i] = rng_word(seed, stream, event, slot, first + (uint32_t)i);
+}
+/* random.expovariate(lambd) = -log(1 - random()) / lambd (CPython Lib/random.py) */
+static double rng_expovariate(double u, double lambd) { return -log(1.0 - u) / lambd; }
+/* random._randbelow_with_getrandbits(n): k = n.bit_length(); r = getrandbits(k) until r < n.
+ * getrandbits(k) of this stream = next word >> (32 - k). */
+static uint32_t rng_randbelow(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t n) {
+    int k = 0;
+    while ((n >> k) != 0) k++;
+    uint32_t index = 0;
+    for (;;) {
+        uint32_t r = rng_word(seed, stream, event, slot, index++) >> (32 - k);
+        if (r < n) return r;
+    }
+}
+
+/* ================================================================================================== */
+/* activator/internal_state/cell_occupancy/cells: CuboidPeriodicCells                                 */
+/* ================================================================================================== */
+typedef struct {
+    int D;
+    int per_side[ECMC_MAX_DIM];
+    int cumulative[ECMC_MAX_DIM];
+    int n_cells;
+    int neighbor_layers;
+    double side_length[ECMC_MAX_DIM];
+    double L;
+    double *cell_min; /* [n_cells][D] */
+    double *cell_max;
+} ocells;
+
+static double next_float_up(double x) {
+    /* cuboid_cells.py:_next_float_up */
+    if (isnan(x) || (isinf(x) && x > 0)) return x;
+    if (x == 0.0) x = 0.0;
+    int64_t n;
+    memcpy(&n, &x, 8);
+    if (n >= 0) n += 1; else n -= 1;
+    memcpy(&x, &n, 8);
+    return x;
+}
+static double next_float_down(double x) { return -next_float_up(-x); }
+
+static void cell_identifier(const ocells *c, int cell, int *id) {
+    for (int d = 0; d < c->D; d++) id[d] = (cell / c->cumulative[d]) % c->per_side[d];
+}
+/* CuboidCells.__init__, cuboid_cells.py:95-146 */
+static int cells_make(ocells *c, int D, const int *per_side, int neighbor_layers, double L) {
+    c->D = D; c->L = L; c->neighbor_layers = neighbor_layers;
+    c->n_cells = 1;
+    for (int d = 0; d < D; d++) {
+        c->per_side[d] = per_side[d];
+        c->side_length[d] = L / per_side[d];
+        c->cumulative[d] = c->n_cells;
+        c->n_cells *= per_side[d];
+    }
+    c->cell_min = (double *)malloc(sizeof(double) * c->n_cells * D);
+    c->cell_max = (double *)malloc(sizeof(double) * c->n_cells * D);
+    if (!c->cell_min || !c->cell_max) return -1;
+    for (int cell = 0; cell < c->n_cells; cell++) {
+        int id[ECMC_MAX_DIM];
+        cell_identifier(c, cell, id);
+        for (int d = 0; d < D; d++) {
+            double h = c->side_length[d];
+            double lower = id[d] * h;
+            double upper = (id[d] + 1) * h;
+            if (lower > 0.0) {
+                while ((int)(lower / h) == id[d]) lower = next_float_down(lower);
+                while ((int)(lower / h) < id[d]) lower = next_float_up(lower);
+            }
+            while ((int)(upper / h) == id[d]) upper = next_float_up(upper);
+            while ((int)(upper / h) > id[d]) upper = next_float_down(upper);
+            c->cell_min[cell * D + d] = lower;
+            c->cell_max[cell * D + d] = upper;
+        }
+    }
+    return 0;
+}
+static void cells_free(ocells *c) { free(c->cell_min); free(c->cell_max); c->cell_min = c->cell_max = NULL; }
+/* position_to_cell, cuboid_cells.py:190-211: int(x / cell_len) truncates */
+static int position_to_cell(const ocells *c, const double *pos) {
+    int cell = 0;
+    for (int d = 0; d < c->D; d++) cell += (int)(pos[d] / c->side_length[d]) * c->cumulative[d];
+    return cell;
+}
+/* CuboidPeriodicCells.neighbor_cell (positive direction), cuboid_periodic_cells.py:102-139 */
+static int neighbor_cell_positive(const ocells *c, int cell, int dir) {
+    int id[ECMC_MAX_DIM];
+    cell_identifier(c, cell, id);
+    int n = 0;
+    for (int d = 0; d < c->D; d++)
+        n += (d != dir ? id[d] : (id[d] + 1) % c->per_side[d]) * c->cumulative[d];
+    return n;
+}
+/* translate, cuboid_periodic_cells.py:182-207 */
+static int cells_translate(const ocells *c, int cell, int relative_cell) {
+    double p[ECMC_MAX_DIM];
+    for (int d = 0; d < c->D; d++)
+        p[d] = correct_position_entry((c->cell_max[cell * c->D + d] + c->cell_min[cell * c->D + d]) / 2.0
+                                      + c->cell_min[relative_cell * c->D + d], c->L);
+    return position_to_cell(c, p);
+}
+/* relative_cell, cuboid_periodic_cells.py:155-180 */
+static int cells_relative(const ocells *c, int cell, int reference_cell) {
+    double p[ECMC_MAX_DIM];
+    for (int d = 0; d < c->D; d++)
+        p[d] = correct_position_entry((c->cell_max[cell * c->D + d] + c->cell_min[cell * c->D + d]) / 2.0
+                                      - c->cell_min[reference_cell * c->D + d], c->L);
+    return position_to_cell(c, p);
+}
+/* _yield_nearby_cells, cuboid_periodic_cells.py:74-100; returns count, duplicates removed (it is a set) */
+static int nearby_cells(const ocells *c, int cell, int *out) {
+    int id[ECMC_MAX_DIM], off[ECMC_MAX_DIM];
+    int nl = c->neighbor_layers, w = 2 * nl + 1, total = 1, count = 0;
+    cell_identifier(c, cell, id);
+    for (int d = 0; d < c->D; d++) total *= w;
+    for (int t = 0; t < total; t++) {
+        int rem = t, idx = 0;
+        for (int d = 0; d < c->D; d++) { off[d] = rem % w - nl; rem /= w; }
+        for (int d = 0; d < c->D; d++) {
+            int v = (id[d] + off[d]) % c->per_side[d];
+            if (v < 0) v += c->per_side[d];
+            idx += v * c->cumulative[d];
+        }
+        int dup = 0;
+        for (int i = 0; i < count; i++) if (out[i] == idx) { dup = 1; break; }
+        if (!dup) out[count++] = idx;
+    }
+    return count;
+}
+
+ORC_API int orc_cells_geometry(int D, const int *per_side, double L, double *cell_min, double *cell_max) {
+    ocells c;
+    if (cells_make(&c, D, per_side, 1, L)) return -1;
+    memcpy(cell_min, c.cell_min, sizeof(double) * c.n_cells * D);
+    memcpy(cell_max, c.cell_max, sizeof(double) * c.n_cells * D);
+    cells_free(&c);
+    return 0;
+}
+ORC_API int orc_position_to_cell(int D, const int *per_side, double L, const double *pos) {
+    ocells c;
+    c.D = D; c.L = L;
+    int n = 1;
+    for (int d = 0; d < D; d++) { c.per_side[d] = per_side[d]; c.side_length[d] = L / per_side[d]; c.cumulative[d] = n; n *= per_side[d]; }
+    return position_to_cell(&c, pos);
+}
+ORC_API int orc_cells_translate(int D, const int *per_side, double L, int cell, int relative_cell) {
+    ocells c;
+    if (cells_make(&c, D, per_side, 1, L)) return -1;
+    int r = cells_translate(&c, cell, relative_cell);
+    cells_free(&c);
+    return r;
+}
+ORC_API int orc_cells_relative(int D, const int *per_side, double L, int cell, int reference_cell) {
+    ocells c;
+    if (cells_make(&c, D, per_side, 1, L)) return -1;
+    int r = cells_relative(&c, cell, reference_cell);
+    cells_free(&c);
+    return r;
+}
+ORC_API int orc_nearby_cells(int D, const int *per_side, int neighbor_layers, double L, int cell, int *out) {
+    ocells c;
+    c.D = D; c.L = L; c.neighbor_layers = neighbor_layers;
+    int n = 1;
+    for (int d = 0; d < D; d++) { c.per_side[d] = per_side[d]; c.cumulative[d] = n; n *= per_side[d]; }
+    return nearby_cells(&c, cell, out);
+}
+
+/* ================================================================================================== */
+/* The chain: state + one iteration of the mediator loop                                              */
+/* ================================================================================================== */
+typedef struct OrcChain {
+    EcmcProgram prog;
+    int D, N;
+    double L;
+    ocells cells;
+    opotential pair_pot, pair_bound, veto_pot;
+    /* copied veto tables */
+    EcmcWalkerTable upper[ECMC_MAX_DIM], lower[ECMC_MAX_DIM];
+    double *bounds;
+    int *nearby_offsets; /* nearby cells of cell zero (relative) */
+    unsigned char *is_nearby_of_zero;
+    /* state */
+    double *pos;    /* [N][D] */
+    double *charge; /* [N] */
+    int *occ;       /* [n_cells][max_occ] */
+    int *surplus;   /* [max_surplus] */
+    int n_surplus;
+    EcmcChainState st;
+    int started;
+    EcmcStats stats;
+} OrcChain;
+
+static int copy_walker(EcmcWalkerTable *dst, const EcmcWalkerTable *src) {
+    *dst = *src;
+    if (src->n_entries <= 0) { dst->cell_a = dst->cell_b = NULL; dst->rate_a = NULL; return 0; }
+    int32_t *a = (int32_t *)malloc(sizeof(int32_t) * src->n_entries);
+    int32_t *b = (int32_t *)malloc(sizeof(int32_t) * src->n_entries);
+    double *r = (double *)malloc(sizeof(double) * src->n_entries);
+    if (!a || !b || !r) return -1;
+    memcpy(a, src->cell_a, sizeof(int32_t) * src->n_entries);
+    memcpy(b, src->cell_b, sizeof(int32_t) * src->n_entries);
+    memcpy(r, src->rate_a, sizeof(double) * src->n_entries);
+    dst->cell_a = a; dst->cell_b = b; dst->rate_a = r;
+    return 0;
+}
+
+ORC_API void orc_chain_destroy(OrcChain *c) {
+    if (!c) return;
+    for (int d = 0; d < ECMC_MAX_DIM; d++) {
+        free((void *)c->upper[d].cell_a); free((void *)c->upper[d].cell_b); free((void *)c->upper[d].rate_a);
+        free((void *)c->lower[d].cell_a); free((void *)c->lower[d].cell_b); free((void *)c->lower[d].rate_a);
+    }
+    free(c->bounds); free(c->nearby_offsets); free(c->is_nearby_of_zero);
+    free(c->pos); free(c->charge); free(c->occ); free(c->surplus);
+    cells_free(&c->cells);
+    pot_free(&c->pair_pot); pot_free(&c->pair_bound); pot_free(&c->veto_pot);
+    free(c);
+}
+
+ORC_API OrcChain *orc_chain_create(const EcmcProgram *prog) {
+    if (!prog || prog->abi_version != ECMC_ABI_VERSION) return NULL;
+    OrcChain *c = (OrcChain *)calloc(1, sizeof(OrcChain));
+    if (!c) return NULL;
+    c->prog = *prog;
+    c->D = prog->dimension; c->N = prog->n_particles; c->L = prog->system_length;
+    if (cells_make(&c->cells, c->D, prog->cells_per_side, prog->neighbor_layers, c->L)) goto fail;
+    if (pot_make(&c->pair_pot, &prog->pair_potential, c->L)) goto fail;
+    if (pot_make(&c->pair_bound, &prog->pair_bounding_potential, c->L)) goto fail;
+    if (pot_make(&c->veto_pot, &prog->veto_potential, c->L)) goto fail;
+    c->is_nearby_of_zero = (unsigned char *)calloc(c->cells.n_cells, 1);
+    c->nearby_offsets = (int *)malloc(sizeof(int) * c->cells.n_cells);
+    if (!c->is_nearby_of_zero || !c->nearby_offsets) goto fail;
+    {
+        int n = nearby_cells(&c->cells, 0, c->nearby_offsets);
+        for (int i = 0; i < n; i++) c->is_nearby_of_zero[c->nearby_offsets[i]] = 1;
+    }
+    if (prog->veto_enabled) {
+        if (!prog->veto_tables) goto fail;
+        for (int d = 0; d < c->D; d++) {
+            if (copy_walker(&c->upper[d], &prog->veto_tables->upper[d])) goto fail;
+            if (copy_walker(&c->lower[d], &prog->veto_tables->lower[d])) goto fail;
+        }
+        size_t nb = (size_t)c->cells.n_cells * c->D * 2;
+        c->bounds = (double *)malloc(sizeof(double) * nb);
+        if (!c->bounds) goto fail;
+        memcpy(c->bounds, prog->veto_tables->bounds, sizeof(double) * nb);
+    }
+    c->prog.veto_tables = NULL;
+    c->pos = (double *)calloc((size_t)c->N * c->D, sizeof(double));
+    c->charge = (double *)malloc(sizeof(double) * c->N);
+    c->occ = (int *)malloc(sizeof(int) * c->cells.n_cells * prog->max_occupants);
+    c->surplus = (int *)malloc(sizeof(int) * (prog->max_surplus > 0 ? prog->max_surplus : 1));
+    if (!c->pos || !c->charge || !c->occ || !c->surplus) goto fail;
+    for (int i = 0; i < c->N; i++) c->charge[i] = 1.0;
+    return c;
+fail:
+    orc_chain_destroy(c);
+    return NULL;
+}
+
+ORC_API void orc_chain_set_positions(OrcChain *c, const double *pos, const double *charge) {
+    memcpy(c->pos, pos, sizeof(double) * c->N * c->D);
+    if (charge) memcpy(c->charge, charge, sizeof(double) * c->N);
+}
+ORC_API void orc_chain_get_positions(const OrcChain *c, double *pos) {
+    memcpy(pos, c->pos, sizeof(double) * c->N * c->D);
+}
+ORC_API void orc_chain_get_state(const OrcChain *c, EcmcChainState *st) { *st = c->st; }
+ORC_API void orc_chain_set_state(OrcChain *c, const EcmcChainState *st) { c->st = *st; c->started = 1; }
+ORC_API void orc_chain_get_cells(const OrcChain *c, int32_t *occ, int32_t *surplus, int32_t *n_surplus) {
+    memcpy(occ, c->occ, sizeof(int) * c->cells.n_cells * c->prog.max_occupants);
+    memcpy(surplus, c->surplus, sizeof(int) * c->n_surplus);
+    *n_surplus = c->n_surplus;
+}
+ORC_API void orc_chain_set_cells(OrcChain *c, const int32_t *occ, const int32_t *surplus, int32_t n_surplus) {
+    memcpy(c->occ, occ, sizeof(int) * c->cells.n_cells * c->prog.max_occupants);
+    memcpy(c->surplus, surplus, sizeof(int) * n_surplus);
+    c->n_surplus = n_surplus;
+}
+ORC_API void orc_chain_get_stats(const OrcChain *c, EcmcStats *s) { *s = c->stats; }
+
+/* occupancy helpers: SingleActiveCellOccupancy, single_active_cell_occupancy.py */
+static int occ_count(const OrcChain *c, int cell) {
+    int n = 0;
+    for (int s = 0; s < c->prog.max_occupants; s++) if (c->occ[cell * c->prog.max_occupants + s] >= 0) n++;
+    return n;
+}
+static void occ_insert(OrcChain *c, int cell, int id) {
+    /* :117-121 and :176-180: append to occupants if below the maximum, else to surplus */
+    if (occ_count(c, cell) < c->prog.max_occupants) {
+        for (int s = 0; s < c->prog.max_occupants; s++)
+            if (c->occ[cell * c->prog.max_occupants + s] < 0) { c->occ[cell * c->prog.max_occupants + s] = id; return; }
+    }
+    if (c->n_surplus >= c->prog.max_surplus) { c->stats.capacity_errors++; return; }
+    c->surplus[c->n_surplus++] = id;
+}
+static void occ_remove(OrcChain *c, int cell, int id) {
+    /* :186-193: remove from the occupants (the surplus is NOT promoted: the guarding expression
+     * `not self._surplus.get(cell, True)` is only true for an empty list, which never exists) or, on
+     * ValueError, from the surplus */
+    int m = c->prog.max_occupants;
+    for (int s = 0; s < m; s++)
+        if (c->occ[cell * m + s] == id) {
+            /* keep list order like list.remove */
+            for (int t = s; t + 1 < m; t++) c->occ[cell * m + t] = c->occ[cell * m + t + 1];
+            c->occ[cell * m + m - 1] = -1;
+            return;
+        }
+    for (int s = 0; s < c->n_surplus; s++)
+        if (c->surplus[s] == id) {
+            for (int t = s; t + 1 < c->n_surplus; t++) c->surplus[t] = c->surplus[t + 1];
+            c->n_surplus--;
+            return;
+        }
+    c->stats.capacity_errors++;
+}
+
+/* EndOfChainEventHandler.send_event_time for the candidate created at the start of a chain
+ * (abstracts/end_of_chain_event_handler.py:80-105; single_independent_active_periodic_direction_...:203-237):
+ * new_chain_time = (last_committed - current) + chain_time with last_committed == current at creation. */
+static void schedule_end_of_chain(OrcChain *c) {
+    otime now = {c->st.time_q, c->st.time_r};
+    double new_chain_time = time_sub(now, now) + c->prog.chain_time;
+    otime t = time_add(now, new_chain_time);
+    c->st.eoc_q = t.q; c->st.eoc_r = t.r;
+    c->st.eoc_next_active = (int)rng_randbelow(c->prog.seed, c->st.stream, c->st.event_counter,
+                                               ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)c->N);
+}
+
+/* Start of run: SingleActiveCellOccupancy.initialize (:95-121), InitialChainStartOfRunEventHandler
+ * (initial_chain_start_of_run_event_handler.py:92-131), then the first internal-state update (:149-203). */
+ORC_API void orc_chain_start(OrcChain *c, uint32_t stream) {
+    int m = c->prog.max_occupants;
+    for (int i = 0; i < c->cells.n_cells * m; i++) c->occ[i] = -1;
+    c->n_surplus = 0;
+    for (int i = 0; i < c->N; i++) occ_insert(c, position_to_cell(&c->cells, c->pos + i * c->D), i);
+    memset(&c->st, 0, sizeof(c->st));
+    c->st.stream = stream;
+    c->st.active = c->prog.initial_active;
+    c->st.direction = c->prog.initial_direction;
+    c->st.time_q = 0.0; c->st.time_r = 0.0;
+    c->st.event_counter = 0;
+    c->st.active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
+    occ_remove(c, c->st.active_cell, c->st.active);
+    schedule_end_of_chain(c);
+    c->st.pending_kind = ECMC_EVENT_NONE;
+    c->started = 1;
+    memset(&c->stats, 0, sizeof(c->stats));
+}
+
+typedef struct {
+    int kind, target, target_cell;
+    otime t;
+    double rate;
+} candidate;
+
+/* One pair candidate: TwoLeafUnitEventHandler.send_event_time (two_leaf_unit_event_handler.py:105-138) or
+ * TwoLeafUnitBoundingPotentialEventHandler.send_event_time (two_leaf_unit_bounding_potential_event_handler.py:112-146) */
+static otime pair_candidate_time(OrcChain *c, int target) {
+    const double *pa = c->pos + c->st.active * c->D, *pt = c->pos + target * c->D;
+    double sep[ECMC_MAX_DIM] = {0, 0, 0};
+    separation_vector(pa, pt, c->D, c->L, sep);
+    double c1 = c->prog.pair_use_charge ? c->charge[c->st.active] : 1.0;
+    double c2 = c->prog.pair_use_charge ? c->charge[target] : 1.0;
+    const opotential *pot = c->prog.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING ? &c->pair_bound : &c->pair_pot;
+    double dU = 0.0;
+    if (pot_needs_potential_change(pot->kind)) {
+        double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter,
+                              ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target), 0);
+        dU = rng_expovariate(u, c->prog.beta);
+    }
+    double dt = pot_displacement(pot, c->st.direction, c->prog.speed, sep, c->D, c1, c2, dU);
+    otime now = {c->st.time_q, c->st.time_r};
+    return time_add(now, dt);
+}
+
+/* CellVetoEventHandler.send_event_time, abstracts/cell_veto_event_handler.py:200-238; Walker.sample_cell,
+ * walker.py:105-118; InnerPointEstimator.charge_correction_factor, inner_point_estimator.py:165-192 */
+static candidate veto_candidate(OrcChain *c) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_CELL_VETO; cand.target = -1;
+    int dir = c->st.direction;
+    double charge_factor = 1.0;
+    if (c->prog.veto_use_charge)
+        charge_factor = c->charge[c->st.active] * 1.0 / c->prog.veto_target_charge;
+    const EcmcWalkerTable *w;
+    int rate_index;
+    if (charge_factor > 0.0) { w = &c->upper[dir]; rate_index = 0; }
+    else { charge_factor *= -1.0; w = &c->lower[dir]; rate_index = 1; }
+    double total_rate = w->total_rate * charge_factor;
+    uint32_t e = rng_randbelow(c->prog.seed, c->st.stream, c->st.event_counter,
+                               ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0), (uint32_t)w->n_entries);
+    double u0 = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0), 0);
+    double u1 = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0), 1);
+    /* random.uniform(0.0, mean) = 0.0 + (mean - 0.0) * random() */
+    int relative_cell = (0.0 + (w->mean_rate - 0.0) * u0 <= w->rate_a[e]) ? w->cell_a[e] : w->cell_b[e];
+    cand.rate = c->bounds[(relative_cell * c->D + dir) * 2 + rate_index] * charge_factor;
+    /* the active cell is recomputed from the position, cell_veto_event_handler.py:216 */
+    int active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
+    cand.target_cell = cells_translate(&c->cells, active_cell, relative_cell);
+    double dt = rng_expovariate(u1, c->prog.beta) / (total_rate * c->prog.speed);
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, dt);
+    return cand;
+}
+
+/* CellBoundaryEventHandler.send_event_time, cell_boundary_event_handler.py:122-156 (positive velocity) */
+static candidate boundary_candidate(OrcChain *c, double *boundary_out) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_CELL_BOUNDARY; cand.target = -1; cand.rate = 0.0;
+    int dir = c->st.direction;
+    const double *pa = c->pos + c->st.active * c->D;
+    int cell = position_to_cell(&c->cells, pa);
+    int neighbor = neighbor_cell_positive(&c->cells, cell, dir);
+    double neighbor_boundary = c->cells.cell_min[neighbor * c->D + dir];
+    double separation = neighbor_boundary - pa[dir];
+    if (separation < 0.0) separation = separation + c->L; /* next_image, hypercubic_setting.py:191 */
+    double time_to_boundary = separation / c->prog.speed;
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, time_to_boundary);
+    cand.target_cell = neighbor;
+    *boundary_out = neighbor_boundary;
+    return cand;
+}
+
+/* BasicEventHandler._time_slice_unit for the active particle, abstracts/abstracts.py:82-95 */
+static void time_slice_active(OrcChain *c, otime event_time) {
+    double *pa = c->pos + c->st.active * c->D;
+    otime stamp = {c->st.time_q, c->st.time_r};
+    double dt = time_sub(event_time, stamp);
+    for (int d = 0; d < c->D; d++) {
+        double v = d == c->st.direction ? c->prog.speed : 0.0;
+        pa[d] = correct_position_entry(pa[d] + v * dt, c->L);
+    }
+    c->st.time_q = event_time.q; c->st.time_r = event_time.r;
+}
+
+/* The internal-state update the activator runs at the top of the next iteration
+ * (SingleActiveCellOccupancy.update, single_active_cell_occupancy.py:149-203) */
+static void occupancy_update(OrcChain *c, int new_active) {
+    if (new_active != c->st.active) {
+        occ_insert(c, c->st.active_cell, c->st.active);
+        c->st.active = new_active;
+        c->st.active_cell = position_to_cell(&c->cells, c->pos + new_active * c->D);
+        occ_remove(c, c->st.active_cell, new_active);
+    } else {
+        c->st.active_cell = position_to_cell(&c->cells, c->pos + new_active * c->D);
+    }
+}
+
+static int lt_candidate(const candidate *a, const candidate *b) { return time_lt(a->t, b->t); }
+
+/* One iteration of SingleProcessMediator.run (single_process_mediator.py:91-156) restricted to device
+ * events. Returns 0 if the next event time is not < until (nothing committed, candidate kept pending). */
+static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
+    candidate best;
+    int n_cand = 0;
+    double boundary_position = 0.0;
+    best.kind = ECMC_EVENT_NONE; best.t.q = ORC_INF; best.t.r = ORC_INF; best.target = -1; best.target_cell = -1;
+    best.rate = 0.0;
+    if (c->st.pending_kind != ECMC_EVENT_NONE) {
+        /* a candidate that survived a host control event: nothing is recomputed, no draws are consumed */
+        best.kind = c->st.pending_kind;
+        best.t.q = c->st.pending_q; best.t.r = c->st.pending_r;
+        best.rate = c->st.pending_rate;
+        if (best.kind == ECMC_EVENT_PAIR) best.target = c->st.pending_target;
+        else best.target_cell = c->st.pending_target;
+        if (best.kind == ECMC_EVENT_CELL_BOUNDARY)
+            boundary_position = c->cells.cell_min[best.target_cell * c->D + c->st.direction];
+        n_cand = 0;
+    } else {
+        /* ExcludedCellsTagger, excluded_cells_tagger.py:129-132 */
+        int nearby[125];
+        int active_cell = c->st.active_cell;
+        int nn = nearby_cells(&c->cells, active_cell, nearby);
+        int m = c->prog.max_occupants;
+        if (c->prog.pair_handler != ECMC_PAIR_NONE) {
+            for (int i = 0; i < nn; i++)
+                for (int s = 0; s < m; s++) {
+                    int t = c->occ[nearby[i] * m + s];
+                    if (t < 0) continue;
+                    candidate cand;
+                    cand.kind = ECMC_EVENT_PAIR; cand.target = t; cand.target_cell = -1; cand.rate = 0.0;
+                    cand.t = pair_candidate_time(c, t);
+                    if (!isinf(cand.t.q)) { /* heap_scheduler.py:139: only finite times are pushed */
+                        n_cand++;
+                        if (lt_candidate(&cand, &best)) best = cand;
+                    }
+                }
+            /* SurplusCellsTagger, surplus_cells_tagger.py:129-131 */
+            for (int s = 0; s < c->n_surplus; s++) {
+                candidate cand;
+                cand.kind = ECMC_EVENT_PAIR; cand.target = c->surplus[s]; cand.target_cell = -1; cand.rate = 0.0;
+                cand.t = pair_candidate_time(c, cand.target);
+                if (!isinf(cand.t.q)) {
+                    n_cand++;
+                    if (lt_candidate(&cand, &best)) best = cand;
+                }
+            }
+        }
+        if (c->prog.veto_enabled) {
+            candidate cand = veto_candidate(c);
+            if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
+        }
+        {
+            candidate cand = boundary_candidate(c, &boundary_position);
+            n_cand++;
+            if (lt_candidate(&cand, &best)) best = cand;
+        }
+    }
+    {
+        /* the end-of-chain candidate lives in the scheduler since the chain started */
+        candidate interaction = best;
+        candidate cand;
+        cand.kind = ECMC_EVENT_END_OF_CHAIN; cand.target = c->st.eoc_next_active; cand.target_cell = -1; cand.rate = 0.0;
+        cand.t.q = c->st.eoc_q; cand.t.r = c->st.eoc_r;
+        n_cand++;
+        if (lt_candidate(&cand, &best)) best = cand;
+        if (!time_lt(best.t, until)) {
+            /* host control event first: the interaction winner stays in the scheduler (no trash), like the
+             * end-of-chain candidate which persists anyway */
+            c->st.pending_kind = interaction.kind;
+            c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
+            c->st.pending_rate = interaction.rate;
+            c->st.pending_target = interaction.kind == ECMC_EVENT_PAIR ? interaction.target : interaction.target_cell;
+            return 0;
+        }
+    }
+    c->st.pending_kind = ECMC_EVENT_NONE;
+
+    int old_active = c->st.active;
+    int new_active = old_active;
+    int accepted = 0;
+    int rec_target = -1;
+    time_slice_active(c, best.t);
+    double c_act = c->charge[old_active];
+    switch (best.kind) {
+    case ECMC_EVENT_PAIR: {
+        rec_target = best.target;
+        if (c->prog.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT) {
+            /* TwoLeafUnitEventHandler.send_out_state, two_leaf_unit_event_handler.py:140-154 */
+            accepted = 1;
+        } else {
+            /* TwoLeafUnitBoundingPotentialEventHandler.send_out_state (:148-168) +
+             * _calculate_out_state_of_two_leaf_unit_bounding_potential (event_handler_with_bounding_potential.py:75-101) */
+            double sep[ECMC_MAX_DIM] = {0, 0, 0};
+            separation_vector(c->pos + old_active * c->D, c->pos + best.target * c->D, c->D, c->L, sep);
+            double c1 = c->prog.pair_use_charge ? c_act : 1.0;
+            double c2 = c->prog.pair_use_charge ? c->charge[best.target] : 1.0;
+            double bounding_rate = pot_derivative(&c->pair_bound, c->st.direction, c->prog.speed, sep, c->D, c1, c2);
+            double real = pot_derivative(&c->pair_pot, c->st.direction, c->prog.speed, sep, c->D, c1, c2);
+            if (real > 0) {
+                if (bounding_rate < real) c->stats.bound_violations++;
+                double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+                if (0 + (bounding_rate - 0) * u < real) accepted = 1;
+            }
+        }
+        if (accepted) new_active = best.target;
+        c->stats.pair_events++;
+        break;
+    }
+    case ECMC_EVENT_CELL_VETO: {
+        /* mediator.get_arguments_cell_veto_event_handler (mediator/mediator.py:265-292) +
+         * LeafUnitCellVetoEventHandler.send_out_state (leaf_unit_cell_veto_event_handler.py:117-149) */
+        int t = c->occ[best.target_cell * c->prog.max_occupants];
+        rec_target = t;
+        if (t >= 0) {
+            double sep[ECMC_MAX_DIM] = {0, 0, 0};
+            separation_vector(c->pos + old_active * c->D, c->pos + t * c->D, c->D, c->L, sep);
+            double c1 = c->prog.veto_use_charge ? c_act : 1.0;
+            double c2 = c->prog.veto_use_charge ? c->charge[t] : 1.0;
+            double real = pot_derivative(&c->veto_pot, c->st.direction, c->prog.speed, sep, c->D, c1, c2);
+            if (real > 0) {
+                if (best.rate < real) c->stats.bound_violations++;
+                double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+                if (0 + (best.rate - 0) * u < real) { accepted = 1; new_active = t; }
+            }
+        }
+        c->stats.veto_events++;
+        if (accepted) c->stats.veto_accepted++;
+        break;
+    }
+    case ECMC_EVENT_CELL_BOUNDARY:
+        /* CellBoundaryEventHandler.send_out_state, cell_boundary_event_handler.py:158-173 */
+        c->pos[old_active * c->D + c->st.direction] = boundary_position;
+        c->stats.boundary_events++;
+        break;
+    case ECMC_EVENT_END_OF_CHAIN:
+        /* EndOfChainEventHandler.send_out_state (abstracts/end_of_chain_event_handler.py:107-187) with
+         * _get_new_velocity (single_independent_active_periodic_direction_...:183-201) */
+        new_active = c->st.eoc_next_active;
+        rec_target = new_active;
+        accepted = 1;
+        c->stats.end_of_chain_events++;
+        break;
+    default: break;
+    }
+    if (rec) {
+        memset(rec, 0, sizeof(*rec));
+        rec->kind = best.kind;
+        rec->target = rec_target;
+        rec->target_cell = best.target_cell;
+        rec->accepted = accepted;
+        rec->n_candidates = n_cand;
+        rec->time_q = best.t.q; rec->time_r = best.t.r;
+        for (int d = 0; d < c->D; d++) rec->active_pos[d] = c->pos[old_active * c->D + d];
+    }
+    c->st.event_counter++;
+    c->stats.events++;
+    c->stats.candidates += (uint64_t)n_cand;
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN) c->st.direction = (c->st.direction + 1) % c->D;
+    occupancy_update(c, new_active);
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN) schedule_end_of_chain(c);
+    if (rec) { rec->new_active = c->st.active; rec->new_direction = c->st.direction; }
+    return 1;
+}
+
+/* Advance until the next event time reaches `until` or max_events were committed. Returns #events. */
+ORC_API int64_t orc_chain_run(OrcChain *c, double until_q, double until_r, int64_t max_events, EcmcEventRecord *records,
+                              int64_t max_records) {
+    otime until = {until_q, until_r};
+    int64_t n = 0;
+    while (max_events <= 0 || n < max_events) {
+        EcmcEventRecord *rec = (records && n < max_records) ? records + n : NULL;
+        if (!chain_step(c, until, rec)) {
+            /* sampling / end-of-run handler time-slices the active unit
+             * (fixed_interval_sampling_event_handler.py:96-109) */
+            time_slice_active(c, until);
+            break;
+        }
+        n++;
+    }
+    return n;
+}

@@ -1,0 +1,308 @@
+"""INI texts (reference grammar, shipped classes only) of the synthetic configurations of SURVEY.md section 8(d),
+and the matching start configurations. Shared by the golden generator, the tests and bench.py."""
+import numpy as np
+
+_INTERACTION_TAGS_LJ = "lj_nearby, lj_surplus, lj_cell_veto, cell_boundary"
+
+
+def lennard_jones_ini(n, system_length, cells_per_side, neighbor_layers=1, beta=1.0, prefactor=4.0,
+                      characteristic_length=1.0, estimator_prefactor=1.5, points_per_side=4, chain_time=10.0,
+                      end_of_run_time=1.0e9, sampling_interval=None, nearby_handlers=27, surplus_handlers=16,
+                      empirical_bound=None):
+    """C2 / C5 of SURVEY.md 8(d): 3D Lennard-Jones atoms, LJ inverted exactly for nearby cells and the surplus,
+    cell-veto (InnerPointEstimator) for all other cells."""
+    tags = _INTERACTION_TAGS_LJ
+    sampling = ""
+    sampling_tag = ""
+    if sampling_interval is not None:
+        sampling_tag = ", sampling"
+        sampling = f"""
+[Sampling]
+create = sampling
+trash = sampling
+event_handler = fixed_interval_sampling_event_handler
+
+[FixedIntervalSamplingEventHandler]
+sampling_interval = {sampling_interval!r}
+output_handler = separation_output_handler
+"""
+    output_handlers = "output_handlers = separation_output_handler" if sampling_interval is not None else ""
+    eb = "" if empirical_bound is None else f"empirical_bound = {empirical_bound!r}\n"
+    return f"""
+[Run]
+mediator = single_process_mediator
+setting = hypercubic_setting
+
+[HypercubicSetting]
+system_length = {system_length!r}
+beta = {beta!r}
+dimension = 3
+
+[SingleProcessMediator]
+state_handler = tree_state_handler
+scheduler = heap_scheduler
+activator = tag_activator
+input_output_handler = input_output_handler
+
+[TagActivator]
+taggers =
+    lj_cell_veto (cell_veto_tagger),
+    lj_nearby (excluded_cells_tagger),
+    cell_boundary (cell_boundary_tagger),
+    lj_surplus (surplus_cells_tagger),
+    {"sampling (no_in_state_tagger)," if sampling_interval is not None else ""}
+    end_of_chain (active_global_state_in_state_tagger),
+    end_of_run (no_in_state_tagger),
+    start_of_run (no_in_state_tagger)
+internal_states = single_active_cell_occupancy
+
+[LjCellVeto]
+create = {tags}
+trash = {tags}
+event_handler = leaf_unit_cell_veto_event_handler
+internal_state_label = single_active_cell_occupancy
+
+[LeafUnitCellVetoEventHandler]
+estimator = inner_point_estimator
+
+[InnerPointEstimator]
+potential = lennard_jones_potential
+prefactor = {estimator_prefactor!r}
+points_per_side = {points_per_side}
+{eb}
+[LennardJonesPotential]
+prefactor = {prefactor!r}
+characteristic_length = {characteristic_length!r}
+
+[LjNearby]
+create = {tags}
+trash = {tags}
+internal_state_label = single_active_cell_occupancy
+event_handler = two_leaf_unit_event_handler
+number_event_handlers = {nearby_handlers}
+
+[TwoLeafUnitEventHandler]
+potential = lennard_jones_potential
+
+[LjSurplus]
+create = {tags}
+trash = {tags}
+internal_state_label = single_active_cell_occupancy
+event_handler = two_leaf_unit_event_handler
+number_event_handlers = {surplus_handlers}
+
+[CellBoundary]
+create = {tags}
+trash = {tags}
+internal_state_label = single_active_cell_occupancy
+event_handler = cell_boundary_event_handler
+
+[SingleActiveCellOccupancy]
+cells = cuboid_periodic_cells
+cell_level = 1
+
+[CuboidPeriodicCells]
+cells_per_side = {cells_per_side}
+neighbor_layers = {neighbor_layers}
+{sampling}
+[EndOfChain]
+create = end_of_chain, {tags}
+trash = end_of_chain, {tags}
+event_handler = single_independent_active_periodic_direction_end_of_chain_event_handler
+
+[SingleIndependentActivePeriodicDirectionEndOfChainEventHandler]
+chain_time = {chain_time!r}
+
+[EndOfRun]
+create = end_of_run
+trash = end_of_chain, {tags}{sampling_tag}, end_of_run
+event_handler = final_time_end_of_run_event_handler
+
+[FinalTimeEndOfRunEventHandler]
+end_of_run_time = {end_of_run_time!r}
+
+[StartOfRun]
+trash = start_of_run
+create = end_of_chain, {tags}{sampling_tag}, end_of_run
+event_handler = initial_chain_start_of_run_event_handler
+
+[InitialChainStartOfRunEventHandler]
+initial_direction_of_motion = 0
+speed = 1.0
+initial_active_identifier = 0
+
+[TreeStateHandler]
+physical_state = tree_physical_state
+lifting_state = tree_lifting_state
+
+[InputOutputHandler]
+{output_handlers}
+input_handler = random_input_handler
+
+[RandomInputHandler]
+random_node_creator = atom_random_node_creator
+number_of_root_nodes = {n}
+
+[AtomRandomNodeCreator]
+{"" if sampling_interval is None else """
+[SeparationOutputHandler]
+filename = /tmp/jf_b200_golden_separation.dat
+"""}"""
+
+
+_INTERACTION_TAGS_COULOMB = "coulomb_nearby, coulomb_cell_veto, cell_boundary, coulomb_surplus"
+
+
+def coulomb_atoms_ini(n, cells_per_side, system_length=1.0, beta=2.0, alpha=3.45, fourier_cutoff=6,
+                      position_cutoff=2, prefactor=1.0, bounding_prefactor=1.5837, estimator_prefactor=1.0,
+                      points_per_side=10, chain_time=0.78965, end_of_run_time=1.0e9, charge_values="1",
+                      nearby_handlers=27, surplus_handlers=16, neighbor_layers=1):
+    """C3 of SURVEY.md 8(d): the structure of config_files/2018_JCP_149_064113/coulomb_atoms/cell_veto.ini."""
+    tags = _INTERACTION_TAGS_COULOMB
+    cps = ", ".join(str(c) for c in cells_per_side)
+    return f"""
+[Run]
+mediator = single_process_mediator
+setting = hypercubic_setting
+
+[HypercubicSetting]
+system_length = {system_length!r}
+beta = {beta!r}
+dimension = 3
+
+[SingleProcessMediator]
+state_handler = tree_state_handler
+scheduler = heap_scheduler
+activator = tag_activator
+input_output_handler = input_output_handler
+
+[TagActivator]
+taggers =
+    coulomb_cell_veto (cell_veto_tagger),
+    coulomb_nearby (excluded_cells_tagger),
+    cell_boundary (cell_boundary_tagger),
+    coulomb_surplus (surplus_cells_tagger),
+    end_of_chain (active_global_state_in_state_tagger),
+    end_of_run (no_in_state_tagger),
+    start_of_run (no_in_state_tagger)
+internal_states = single_active_cell_occupancy
+
+[CoulombCellVeto]
+create = {tags}
+trash = {tags}
+event_handler = leaf_unit_cell_veto_event_handler
+internal_state_label = single_active_cell_occupancy
+
+[LeafUnitCellVetoEventHandler]
+estimator = inner_point_estimator
+charge = electric_charge
+
+[InnerPointEstimator]
+potential = merged_image_coulomb_potential
+prefactor = {estimator_prefactor!r}
+target_charge = 1.0
+points_per_side = {points_per_side}
+
+[MergedImageCoulombPotential]
+alpha = {alpha!r}
+fourier_cutoff = {fourier_cutoff}
+position_cutoff = {position_cutoff}
+prefactor = {prefactor!r}
+
+[InversePowerCoulombBoundingPotential]
+prefactor = {bounding_prefactor!r}
+
+[CoulombNearby]
+create = {tags}
+trash = {tags}
+internal_state_label = single_active_cell_occupancy
+event_handler = two_leaf_unit_bounding_potential_event_handler
+number_event_handlers = {nearby_handlers}
+
+[TwoLeafUnitBoundingPotentialEventHandler]
+potential = merged_image_coulomb_potential
+bounding_potential = inverse_power_coulomb_bounding_potential
+charge = electric_charge
+
+[CoulombSurplus]
+create = {tags}
+trash = {tags}
+internal_state_label = single_active_cell_occupancy
+event_handler = two_leaf_unit_bounding_potential_event_handler
+number_event_handlers = {surplus_handlers}
+
+[CellBoundary]
+create = {tags}
+trash = {tags}
+internal_state_label = single_active_cell_occupancy
+event_handler = cell_boundary_event_handler
+
+[SingleActiveCellOccupancy]
+cells = cuboid_periodic_cells
+cell_level = 1
+
+[CuboidPeriodicCells]
+cells_per_side = {cps}
+neighbor_layers = {neighbor_layers}
+
+[EndOfChain]
+create = end_of_chain, {tags}
+trash = end_of_chain, {tags}
+event_handler = single_independent_active_periodic_direction_end_of_chain_event_handler
+
+[SingleIndependentActivePeriodicDirectionEndOfChainEventHandler]
+chain_time = {chain_time!r}
+
+[EndOfRun]
+create = end_of_run
+trash = end_of_chain, {tags}, end_of_run
+event_handler = final_time_end_of_run_event_handler
+
+[FinalTimeEndOfRunEventHandler]
+end_of_run_time = {end_of_run_time!r}
+
+[StartOfRun]
+trash = start_of_run
+create = end_of_chain, {tags}, end_of_run
+event_handler = initial_chain_start_of_run_event_handler
+
+[InitialChainStartOfRunEventHandler]
+initial_direction_of_motion = 0
+speed = 1.0
+initial_active_identifier = 0
+
+[TreeStateHandler]
+physical_state = tree_physical_state
+lifting_state = tree_lifting_state
+
+[InputOutputHandler]
+input_handler = random_input_handler
+
+[RandomInputHandler]
+random_node_creator = atom_random_node_creator
+number_of_root_nodes = {n}
+
+[AtomRandomNodeCreator]
+charge_values = electric_charge_values (charge_values)
+
+[ElectricChargeValues]
+charge_name = electric_charge
+charge_values = {charge_values}
+"""
+
+
+def lattice_start(n, system_length, cells_per_side, jitter=0.05, seed=1000):
+    """Start configuration of C2/C5: particle i sits in cell i (flat cell order, x fastest) at
+    the cell centre plus a uniform jitter in (-jitter, jitter)^3, numpy PCG64(seed)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    h = system_length / cells_per_side
+    idx = np.arange(n)
+    ids = np.stack([idx % cells_per_side, (idx // cells_per_side) % cells_per_side,
+                    idx // (cells_per_side * cells_per_side)], axis=1)
+    assert ids[:, 2].max() < cells_per_side
+    return (ids + 0.5) * h + rng.uniform(-jitter, jitter, size=(n, 3))
+
+
+def uniform_start(n, system_length, dimension=3, seed=1000):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.uniform(0.0, system_length, size=(n, dimension))
