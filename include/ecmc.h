@@ -153,6 +153,10 @@ typedef struct EcmcChainState {
     int32_t reserved;
     double pending_q, pending_r;
     double pending_rate;      /* bounding event rate stored by the handler for the confirmation step */
+    /* The kept handler computes its out-state from the in-state it was given BEFORE the control event
+     * time-sliced the active particle: coordinate along the direction of motion and time stamp at that moment. */
+    double pending_position;
+    double pending_stamp_q, pending_stamp_r;
 } EcmcChainState;
 
 enum EcmcEventKind {
@@ -240,14 +244,17 @@ double ecmc_kernel_seconds(EcmcHandle *h);
 uint64_t ecmc_kernel_launches(EcmcHandle *h);
 
 /* ---- batched potential arithmetic on the device -------------------------------------------------------
- * Back the host-side Potential classes (derivative / displacement of jellyfysh/potential/potential.py:154-301)
- * and the init-time estimators. separations: [n][dimension]; charges: [n][2] or NULL; out: [n].
- * direction is the direction of motion, speed the (positive) velocity component. */
-int ecmc_potential_derivative(const EcmcPotential *potential, int dimension, double system_length, int direction,
-                              double speed, size_t n, const double *separations, const double *charges,
+ * Back the host-side Potential classes -- derivative(velocity, separation, charges) and
+ * displacement(velocity, separation, charges, potential_change) of jellyfysh/potential/potential.py:154-301 --
+ * and the init-time estimators. velocity: [dimension]; standard-velocity potentials need exactly one positive
+ * component (jellyfysh/potential/abstracts.py:105-140), the hard potentials take any velocity.
+ * separations: [n][dimension]; charges: [n][2] or NULL (1.0); potential_changes: [n] or NULL; out: [n] (seconds
+ * for displacement, as in the reference). */
+int ecmc_potential_derivative(const EcmcPotential *potential, int dimension, double system_length,
+                              const double *velocity, size_t n, const double *separations, const double *charges,
                               double *out, int device);
-int ecmc_potential_displacement(const EcmcPotential *potential, int dimension, double system_length, int direction,
-                                double speed, size_t n, const double *separations, const double *charges,
+int ecmc_potential_displacement(const EcmcPotential *potential, int dimension, double system_length,
+                                const double *velocity, size_t n, const double *separations, const double *charges,
                                 const double *potential_changes, double *out, int device);
 /* Draws of the counter-based random stream, for host-side reproduction: out[n] uniform doubles in [0,1)
  * of (seed, stream, event, slot), starting at draw index `first`. Pure host function (no device needed). */

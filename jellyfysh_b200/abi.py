@@ -92,7 +92,8 @@ class EcmcChainState(C.Structure):
                 ("event_counter", C.c_uint64),
                 ("stream", C.c_uint32), ("pending_kind", C.c_int32),
                 ("pending_target", C.c_int32), ("reserved", C.c_int32),
-                ("pending_q", C.c_double), ("pending_r", C.c_double), ("pending_rate", C.c_double)]
+                ("pending_q", C.c_double), ("pending_r", C.c_double), ("pending_rate", C.c_double),
+                ("pending_position", C.c_double), ("pending_stamp_q", C.c_double), ("pending_stamp_r", C.c_double)]
 
 
 class EcmcEventRecord(C.Structure):
@@ -127,8 +128,9 @@ def chain_state_dtype():
                      ("eoc_q", "<f8"), ("eoc_r", "<f8"), ("eoc_next_active", "<i4"), ("active_cell", "<i4"),
                      ("event_counter", "<u8"), ("stream", "<u4"), ("pending_kind", "<i4"),
                      ("pending_target", "<i4"), ("reserved", "<i4"),
-                     ("pending_q", "<f8"), ("pending_r", "<f8"), ("pending_rate", "<f8")])
+                     ("pending_q", "<f8"), ("pending_r", "<f8"), ("pending_rate", "<f8"),
+                     ("pending_position", "<f8"), ("pending_stamp_q", "<f8"), ("pending_stamp_r", "<f8")])
 
 
 assert C.sizeof(EcmcEventRecord) == 72
-assert C.sizeof(EcmcChainState) == 96
+assert C.sizeof(EcmcChainState) == 120

@@ -434,7 +434,8 @@ static double hd_displacement(double min_sep, double max_sep, const double *velo
 /* ================================================================================================== */
 typedef struct {
     int fourier_cutoff, fourier_cutoff_sq, position_cutoff, position_cutoff_sq;
-    double alpha_over_length, two_alpha_over_length_root_pi, system_length, two_pi_over_length;
+    double alpha_over_length, alpha_over_length_sq, two_alpha_over_length_root_pi, system_length,
+        two_pi_over_length;
     double prefactor;
     double *fourier_array; /* [(fc+1)^3], index (i*(fc+1)+j)*(fc+1)+k */
 } mic_potential;
@@ -462,6 +463,7 @@ static int mic_make(mic_potential *p, double prefactor, double alpha, int fourie
     p->position_cutoff = position_cutoff;
     p->position_cutoff_sq = position_cutoff * position_cutoff;
     p->alpha_over_length = alpha / system_length;
+    p->alpha_over_length_sq = alpha * alpha / (system_length * system_length);
     p->two_alpha_over_length_root_pi = 2.0 * alpha / (system_length * sqrt(M_PI));
     p->system_length = system_length;
     p->two_pi_over_length = 2.0 * M_PI / system_length;
@@ -486,6 +488,7 @@ static double mic_c_derivative(const mic_potential *p, double sx, double sy, dou
                 vector_sq = vector_x * vector_x + vector_y_sq + vector_z_sq;
                 vector_norm = sqrt(vector_sq);
                 derivative += vector_x * (p->two_alpha_over_length_root_pi
+                                          * exp(-p->alpha_over_length_sq * vector_sq)
                                           + erfc(p->alpha_over_length * vector_norm) / vector_norm) / vector_sq;
             }
         }
@@ -674,53 +677,55 @@ static int pot_needs_potential_change(int kind) {
     return !(kind == ECMC_POT_HARD_SPHERE || kind == ECMC_POT_HARD_DIPOLE);
 }
 
-/* Scalar entry points for the known-answer tests. sep has `dimension` entries and may be modified. */
-ORC_API double orc_potential_derivative(const EcmcPotential *p, int dimension, double L, int dir, double speed,
-                                        const double *sep, double c1, double c2) {
-    opotential o;
-    if (pot_make(&o, p, L)) return NAN;
-    double r = pot_derivative(&o, dir, speed, sep, dimension, c1, c2);
-    pot_free(&o);
-    return r;
+/* StandardVelocityPotential._analyse_velocity, abstracts.py:105-140: exactly one non-zero component, which is
+ * positive. Returns the direction or -1. */
+static int analyse_velocity(const double *velocity, int D, double *speed) {
+    int dir = -1;
+    for (int d = 0; d < D; d++)
+        if (velocity[d] != 0.0) {
+            if (dir >= 0) return -1;
+            dir = d;
+        }
+    if (dir < 0 || !(velocity[dir] > 0.0)) return -1;
+    *speed = velocity[dir];
+    return dir;
 }
-ORC_API double orc_potential_displacement(const EcmcPotential *p, int dimension, double L, int dir, double speed,
-                                          const double *sep, double c1, double c2, double dU) {
-    opotential o;
-    double s[ECMC_MAX_DIM] = {0, 0, 0};
-    if (pot_make(&o, p, L)) return NAN;
-    memcpy(s, sep, sizeof(double) * dimension);
-    double r = pot_displacement(&o, dir, speed, s, dimension, c1, c2, dU);
-    pot_free(&o);
-    return r;
-}
-/* general-velocity hard potentials (hard-disk configs use non-axis velocities in the no-cell variant) */
-ORC_API double orc_hard_sphere_displacement(double radius, int dimension, const double *velocity, const double *sep) {
-    return hs_displacement(radius, velocity, sep, dimension);
-}
-ORC_API double orc_hard_dipole_displacement(double min_sep, double max_sep, int dimension, const double *velocity,
-                                            const double *sep) {
-    return hd_displacement(min_sep, max_sep, velocity, sep, dimension);
-}
-ORC_API void orc_potential_derivative_batch(const EcmcPotential *p, int dimension, double L, int dir, double speed,
+static int pot_is_hard(int kind) { return kind == ECMC_POT_HARD_SPHERE || kind == ECMC_POT_HARD_DIPOLE; }
+
+/* Entry points with the reference's signatures: derivative(velocity, separation, charges) and
+ * displacement(velocity, separation, charges, potential_change) (potential.py:154-301). */
+ORC_API void orc_potential_derivative_batch(const EcmcPotential *p, int dimension, double L, const double *velocity,
                                             size_t n, const double *seps, const double *charges, double *out) {
     opotential o;
-    if (pot_make(&o, p, L)) return;
+    double speed = 0.0;
+    int dir = analyse_velocity(velocity, dimension, &speed);
+    if (pot_make(&o, p, L) || dir < 0) {
+        for (size_t i = 0; i < n; i++) out[i] = NAN;
+        return;
+    }
     for (size_t i = 0; i < n; i++) {
         double c1 = charges ? charges[2 * i] : 1.0, c2 = charges ? charges[2 * i + 1] : 1.0;
         out[i] = pot_derivative(&o, dir, speed, seps + i * dimension, dimension, c1, c2);
     }
     pot_free(&o);
 }
-ORC_API void orc_potential_displacement_batch(const EcmcPotential *p, int dimension, double L, int dir, double speed,
+ORC_API void orc_potential_displacement_batch(const EcmcPotential *p, int dimension, double L, const double *velocity,
                                               size_t n, const double *seps, const double *charges, const double *dUs,
                                               double *out) {
     opotential o;
-    if (pot_make(&o, p, L)) return;
+    double speed = 0.0;
+    int dir = analyse_velocity(velocity, dimension, &speed);
+    if (pot_make(&o, p, L) || (dir < 0 && !pot_is_hard(p->kind))) {
+        for (size_t i = 0; i < n; i++) out[i] = NAN;
+        return;
+    }
     for (size_t i = 0; i < n; i++) {
         double s[ECMC_MAX_DIM] = {0, 0, 0};
         memcpy(s, seps + i * dimension, sizeof(double) * dimension);
         double c1 = charges ? charges[2 * i] : 1.0, c2 = charges ? charges[2 * i + 1] : 1.0;
-        out[i] = pot_displacement(&o, dir, speed, s, dimension, c1, c2, dUs ? dUs[i] : 0.0);
+        if (p->kind == ECMC_POT_HARD_SPHERE) out[i] = hs_displacement(o.p0, velocity, s, dimension);
+        else if (p->kind == ECMC_POT_HARD_DIPOLE) out[i] = hd_displacement(o.p0, o.p1, velocity, s, dimension);
+        else out[i] = pot_displacement(&o, dir, speed, s, dimension, c1, c2, dUs ? dUs[i] : 0.0);
     }
     pot_free(&o);
 }
@@ -1221,7 +1226,8 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
     double boundary_position = 0.0;
     best.kind = ECMC_EVENT_NONE; best.t.q = ORC_INF; best.t.r = ORC_INF; best.target = -1; best.target_cell = -1;
     best.rate = 0.0;
-    if (c->st.pending_kind != ECMC_EVENT_NONE) {
+    int was_pending = c->st.pending_kind != ECMC_EVENT_NONE;
+    if (was_pending) {
         /* a candidate that survived a host control event: nothing is recomputed, no draws are consumed */
         best.kind = c->st.pending_kind;
         best.t.q = c->st.pending_q; best.t.r = c->st.pending_r;
@@ -1286,10 +1292,24 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
             c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
             c->st.pending_rate = interaction.rate;
             c->st.pending_target = interaction.kind == ECMC_EVENT_PAIR ? interaction.target : interaction.target_cell;
+            if (!was_pending) {
+                /* the kept handlers hold copies of the in-state made before the control event time-slices
+                 * the global state (single_process_mediator.py:105-109): their out-state starts from here */
+                c->st.pending_position = c->pos[c->st.active * c->D + c->st.direction];
+                c->st.pending_stamp_q = c->st.time_q;
+                c->st.pending_stamp_r = c->st.time_r;
+            }
             return 0;
         }
     }
     c->st.pending_kind = ECMC_EVENT_NONE;
+    if (was_pending && best.kind != ECMC_EVENT_END_OF_CHAIN) {
+        /* the kept handler's stored in-state predates the control event's time slice; the end-of-chain
+         * handler instead receives the current global state (mediator/mediator.py:233-249) */
+        c->pos[c->st.active * c->D + c->st.direction] = c->st.pending_position;
+        c->st.time_q = c->st.pending_stamp_q;
+        c->st.time_r = c->st.pending_stamp_r;
+    }
 
     int old_active = c->st.active;
     int new_active = old_active;

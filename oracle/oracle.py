@@ -48,16 +48,8 @@ def lib() -> C.CDLL:
     L.orc_correct_position_entry.restype = d
     L.orc_correct_separation_entry.argtypes = [d, d]
     L.orc_correct_separation_entry.restype = d
-    L.orc_potential_derivative.argtypes = [pot, i, d, i, d, dp, d, d]
-    L.orc_potential_derivative.restype = d
-    L.orc_potential_displacement.argtypes = [pot, i, d, i, d, dp, d, d, d]
-    L.orc_potential_displacement.restype = d
-    L.orc_hard_sphere_displacement.argtypes = [d, i, dp, dp]
-    L.orc_hard_sphere_displacement.restype = d
-    L.orc_hard_dipole_displacement.argtypes = [d, d, i, dp, dp]
-    L.orc_hard_dipole_displacement.restype = d
-    L.orc_potential_derivative_batch.argtypes = [pot, i, d, i, d, sz, p, p, p]
-    L.orc_potential_displacement_batch.argtypes = [pot, i, d, i, d, sz, p, p, p, p]
+    L.orc_potential_derivative_batch.argtypes = [pot, i, d, dp, sz, p, p, p]
+    L.orc_potential_displacement_batch.argtypes = [pot, i, d, dp, sz, p, p, p, p]
     L.orc_random_doubles.argtypes = [u32, u32, u64, u32, u32, sz, p]
     L.orc_random_words.argtypes = [u32, u32, u64, u32, u32, sz, p]
     L.orc_cells_geometry.argtypes = [i, ip, d, p, p]
@@ -108,44 +100,45 @@ def time_from_float(t):
     return oq.value, orr.value
 
 
-def potential_derivative(pot, dimension, system_length, direction, speed, separation, c1=1.0, c2=1.0):
-    return lib().orc_potential_derivative(C.byref(pot), dimension, system_length, direction, speed,
-                                          _vec(separation), c1, c2)
+def _velocity(direction_or_velocity, dimension, speed=1.0):
+    if np.isscalar(direction_or_velocity):
+        velocity = [0.0] * dimension
+        velocity[int(direction_or_velocity)] = float(speed)
+        return _vec(velocity)
+    return _vec(direction_or_velocity)
 
 
-def potential_displacement(pot, dimension, system_length, direction, speed, separation, c1=1.0, c2=1.0,
-                           potential_change=0.0):
-    return lib().orc_potential_displacement(C.byref(pot), dimension, system_length, direction, speed,
-                                            _vec(separation), c1, c2, potential_change)
-
-
-def hard_sphere_displacement(radius, velocity, separation):
-    return lib().orc_hard_sphere_displacement(radius, len(velocity), _vec(velocity), _vec(separation))
-
-
-def hard_dipole_displacement(min_sep, max_sep, velocity, separation):
-    return lib().orc_hard_dipole_displacement(min_sep, max_sep, len(velocity), _vec(velocity), _vec(separation))
-
-
-def potential_derivative_batch(pot, dimension, system_length, direction, speed, separations, charges=None):
+def potential_derivative_batch(pot, dimension, system_length, velocity, separations, charges=None):
+    """derivative(velocity, separation, charges) of the reference for n separations. velocity: vector or direction."""
     seps = np.ascontiguousarray(separations, dtype=np.float64).reshape(-1, dimension)
     out = np.empty(len(seps), dtype=np.float64)
     ch = None if charges is None else np.ascontiguousarray(charges, dtype=np.float64)
-    lib().orc_potential_derivative_batch(C.byref(pot), dimension, system_length, direction, speed, len(seps),
-                                         seps.ctypes.data, None if ch is None else ch.ctypes.data, out.ctypes.data)
+    lib().orc_potential_derivative_batch(C.byref(pot), dimension, system_length, _velocity(velocity, dimension),
+                                         len(seps), seps.ctypes.data, None if ch is None else ch.ctypes.data,
+                                         out.ctypes.data)
     return out
 
 
-def potential_displacement_batch(pot, dimension, system_length, direction, speed, separations, charges=None,
+def potential_displacement_batch(pot, dimension, system_length, velocity, separations, charges=None,
                                  potential_changes=None):
+    """displacement(velocity, separation, charges, potential_change) of the reference (a time) for n inputs."""
     seps = np.ascontiguousarray(separations, dtype=np.float64).reshape(-1, dimension)
     out = np.empty(len(seps), dtype=np.float64)
     ch = None if charges is None else np.ascontiguousarray(charges, dtype=np.float64)
     du = None if potential_changes is None else np.ascontiguousarray(potential_changes, dtype=np.float64)
-    lib().orc_potential_displacement_batch(C.byref(pot), dimension, system_length, direction, speed, len(seps),
-                                           seps.ctypes.data, None if ch is None else ch.ctypes.data,
+    lib().orc_potential_displacement_batch(C.byref(pot), dimension, system_length, _velocity(velocity, dimension),
+                                           len(seps), seps.ctypes.data, None if ch is None else ch.ctypes.data,
                                            None if du is None else du.ctypes.data, out.ctypes.data)
     return out
+
+
+def potential_derivative(pot, dimension, system_length, velocity, separation, c1=1.0, c2=1.0):
+    return float(potential_derivative_batch(pot, dimension, system_length, velocity, [separation], [[c1, c2]])[0])
+
+
+def potential_displacement(pot, dimension, system_length, velocity, separation, c1=1.0, c2=1.0, potential_change=0.0):
+    return float(potential_displacement_batch(pot, dimension, system_length, velocity, [separation], [[c1, c2]],
+                                              [potential_change])[0])
 
 
 def random_doubles(seed, stream, event, slot, first, n):
@@ -224,7 +217,7 @@ def inner_point_derivative_bounds(pot, system_length, per_side, neighbor_layers,
         # correct_separation, hypercubic_setting.py:172 (np.mod has Python's sign convention)
         seps = np.mod(seps + half, system_length) - half
         for direction in range(dimension):
-            der = potential_derivative_batch(pot, dimension, system_length, direction, 1.0, seps, charges)
+            der = potential_derivative_batch(pot, dimension, system_length, direction, seps, charges)
             upper_bound = -float("inf")
             lower_bound = float("inf")
             for value in der:  # max/min accumulate exactly like the reference's loop

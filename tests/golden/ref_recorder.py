@@ -145,6 +145,7 @@ class ReferenceRun:
         self.events = 0  # committed device events
         self.records = []
         self.iterations = []  # (winner class name, event time float)
+        self.host_times = []  # (committed device events so far, quotient, remainder) of sampling events
         self._instrument()
 
     # -- random -------------------------------------------------------------------------------------
@@ -277,6 +278,9 @@ class ReferenceRun:
         if kind == HOST_EVENT:
             self._current = None
             self.iterations.append((name, None))
+            t = getattr(winner, "_event_time", None)
+            if t is not None and "Sampling" in name:
+                self.host_times.append((self.events, t.quotient, t.remainder))
             return
         n_interaction = sum(1 for _, h in pushed if self._kind_of(h) not in (HOST_EVENT, EVENT_END_OF_CHAIN))
         rec = np.zeros((), dtype=RECORD_DTYPE)

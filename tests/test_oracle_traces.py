@@ -1,0 +1,116 @@
+"""Whole-chain parity of the CPU oracle with the running reference.
+
+tests/golden/trace_*.npz hold, event by event, what the unmodified reference did when its `random` module read
+the slot-keyed Philox stream (tests/golden/ref_recorder.py). The oracle, started from the same configuration
+and reading the same stream, must reproduce every event: winner kind, target, acceptance, new active particle
+bit-exact -- and, because it follows the reference operation by operation with the same libm, also the event
+times and positions bit-exact. Snapshots pin positions, cell occupancy and surplus lists along the way."""
+import numpy as np
+import pytest
+
+import trace_util as tu
+
+
+def _init_tables(oracle, g):
+    """Init-time tables rebuilt by the oracle's restatement of estimator + Walker."""
+    handler, pot, bound, veto, use_charge = tu.potentials_of(g)
+    cps = [int(c) for c in g["meta_cells_per_side"]]
+    prefactor, points = float(g["meta_estimator"][0]), int(g["meta_estimator"][1])
+    bounds, far = oracle.inner_point_derivative_bounds(veto, float(g["meta_system_length"]), cps, 1,
+                                                       prefactor=prefactor, points_per_side=points,
+                                                       target_charge=1.0 if use_charge else None,
+                                                       uses_charges=use_charge)
+    return oracle.veto_tables(bounds, far)
+
+
+@pytest.mark.parametrize("name", tu.TRACES)
+def test_init_tables_bit_exact(oracle, name):
+    g = tu.load_trace(name)
+    ours, ref = _init_tables(oracle, g), tu.reference_tables(g)
+    assert np.array_equal(ours["bounds"], ref["bounds"], equal_nan=True)
+    for kind in ("upper", "lower"):
+        for d in range(3):
+            for key in ("cell_a", "cell_b", "rate_a"):
+                assert np.array_equal(ours[kind][d][key], ref[kind][d][key]), (kind, d, key)
+            assert ours[kind][d]["total_rate"] == ref[kind][d]["total_rate"]
+            assert ours[kind][d]["mean_rate"] == ref[kind][d]["mean_rate"]
+
+
+@pytest.mark.parametrize("name", tu.TRACES)
+def test_chain_replay_bit_exact(oracle, name):
+    g = tu.load_trace(name)
+    records = g["records"]
+    chain = oracle.OracleChain(tu.builder_of(g, oracle.ProgramBuilder, tables=_init_tables(oracle, g)))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        assert tu.records_equal_discrete(rec, ref)
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            occ, surplus = chain.cells()
+            assert np.array_equal(occ, g["snap_occupants"][k])
+            ns = int(g["snap_n_surplus"][k])
+            assert sorted(surplus.tolist()) == sorted(g["snap_surplus"][k][:ns].tolist())
+            st = chain.state()
+            assert (st.active, st.direction) == (int(g["snap_active"][k]), int(g["snap_direction"][k]))
+            assert (st.time_q, st.time_r) == tuple(g["snap_time"][k])
+    assert np.array_equal(chain.positions(), g["final_positions"])
+    assert chain.stats()["capacity_errors"] == 0
+
+
+def test_time_limit_keeps_candidates(oracle):
+    """Stopping at host control times (sampling) keeps the interaction winner: the event sequence is the same
+    whether the chain runs in one go or is interrupted, up to the rounding of the extra time slices."""
+    g = tu.load_trace("trace_lj_small")
+    pb = tu.builder_of(g, oracle.ProgramBuilder)
+    free = oracle.OracleChain(pb)
+    free.set_positions(g["positions0"])
+    free.start(stream=3)
+    n_free, rec_free = free.run(until=(2.0, 0.5), record=20000)
+    stepped = oracle.OracleChain(pb)
+    stepped.set_positions(g["positions0"])
+    stepped.start(stream=3)
+    parts = []
+    for k in range(1, 26):
+        t = oracle.time_from_float(0.1 * k)
+        _, rec = stepped.run(until=t, record=20000)
+        parts.append(rec)
+        st = stepped.state()
+        assert (st.time_q, st.time_r) == t
+    rec_stepped = np.concatenate(parts)
+    assert len(rec_stepped) == n_free
+    for f in ("kind", "target", "accepted", "new_active"):
+        assert np.array_equal(rec_stepped[f], rec_free[f]), f
+    assert tu.max_time_error(rec_stepped, rec_free) < 1e-12
+
+
+def test_sampling_interleaved_replay_bit_exact(oracle):
+    """The reference trace with FixedIntervalSamplingEventHandler events in between: running the oracle up to
+    each recorded sampling time reproduces the reference bit for bit (time slices at the sampling times, kept
+    candidates, no extra draws)."""
+    g = tu.load_trace("trace_lj_sampling")
+    records, host = g["records"], g["host_times"]
+    chain = oracle.OracleChain(tu.builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"])
+    chain.start(stream=int(g["seed"][1]))
+    parts, done = [], 0
+    assert len(host) > 20
+    for events_before, q, r in host:
+        n, rec = chain.run(until=(q, r), record=10000)
+        parts.append(rec)
+        done += n
+        assert done == int(events_before)
+    n, rec = chain.run(max_events=len(records) - done, record=10000)
+    parts.append(rec)
+    ours = np.concatenate(parts)
+    assert tu.records_equal_discrete(ours, records)
+    assert np.array_equal(ours["time_q"], records["time_q"]) and np.array_equal(ours["time_r"], records["time_r"])
+    assert np.array_equal(ours["active_pos"], records["active_pos"])

@@ -1,0 +1,59 @@
+"""Build programs / oracle chains from the committed reference traces (tests/golden/trace_*.npz)."""
+import numpy as np
+
+import kat_replay as kr
+from jellyfysh_b200 import abi
+
+TRACES = ["trace_lj_small", "trace_lj_surplus", "trace_coulomb_small", "trace_coulomb_surplus"]
+DISCRETE_FIELDS = ("kind", "target", "target_cell", "accepted", "n_candidates", "new_active", "new_direction")
+
+
+def reference_tables(g, dimension=3):
+    """Walker tables and bounds exactly as the reference built them (stored in the trace fixture)."""
+    tables = {"upper": [], "lower": [], "bounds": g["bounds"]}
+    for name in ("upper", "lower"):
+        for d in range(dimension):
+            tables[name].append({"cell_a": g[f"{name}{d}_cell_a"], "cell_b": g[f"{name}{d}_cell_b"],
+                                 "rate_a": g[f"{name}{d}_rate_a"], "total_rate": float(g[f"{name}{d}_rates"][0]),
+                                 "mean_rate": float(g[f"{name}{d}_rates"][1])})
+    return tables
+
+
+def potentials_of(g):
+    """(pair_handler, pair potential, bounding potential or None, veto potential, use_charge)."""
+    if "meta_lj" in g:
+        lj = abi.EcmcPotential.make(abi.POT_LENNARD_JONES, *g["meta_lj"])
+        return abi.PAIR_TWO_LEAF_UNIT, lj, None, lj, False
+    mic = abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"])
+    ipcb = abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, *g["meta_ipcb"])
+    return abi.PAIR_TWO_LEAF_UNIT_BOUNDING, mic, ipcb, mic, True
+
+
+def builder_of(g, builder_cls, tables=None, max_surplus=128):
+    handler, pot, bound, veto, use_charge = potentials_of(g)
+    cps = [int(c) for c in g["meta_cells_per_side"]]
+    pb = builder_cls(3, int(g["meta_n"]), float(g["meta_system_length"]), float(g["meta_beta"]), cps, 1,
+                     max_occupants=1, max_surplus=max_surplus, chain_time=float(g["meta_chain_time"]),
+                     seed=int(g["seed"][0]))
+    pb.set_pair(handler, pot, bound, use_charge=use_charge)
+    pb.set_veto(veto, tables if tables is not None else reference_tables(g), use_charge=use_charge, target_charge=1.0)
+    return pb
+
+
+def charges_of(g):
+    return g["charges"] if "charges" in g else None
+
+
+def load_trace(name):
+    return kr.load_npz(name)
+
+
+def records_equal_discrete(a, b):
+    return all(np.array_equal(a[f], b[f]) for f in DISCRETE_FIELDS)
+
+
+def max_time_error(a, b):
+    """Largest |t_a - t_b| / max(1, |t|) with t = quotient + remainder evaluated without cancellation."""
+    diff = (a["time_q"] - b["time_q"]) + (a["time_r"] - b["time_r"])
+    scale = np.maximum(1.0, np.abs(a["time_q"] + a["time_r"]))
+    return float(np.max(np.abs(diff) / scale))
