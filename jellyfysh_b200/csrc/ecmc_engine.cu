@@ -1,0 +1,745 @@
+// ecmc_engine.cu -- libecmc_b200.so: the C ABI of include/ecmc.h over the sm_100a kernels of ecmc_kernels.cuh.
+// Host side: turns an EcmcProgram into the device program (cell geometry, nearby-cell list, translate tables,
+// Walker tables, Ewald term lists), owns the HBM state of the chains and launches the kernels on one stream.
+// There is no CPU implementation of the hot path in this library.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ecmc_kernels.cuh"
+
+using namespace ecmc;
+
+#define ECMC_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kWarpsPerBlock = 4;
+
+struct EventPair {
+    cudaEvent_t start, stop;
+};
+
+}  // namespace
+
+struct EcmcHandle {
+    int device = 0;
+    int n_chains = 0;
+    EcmcProgram program{};
+    DeviceProgram dprog{};
+    DeviceState state{};
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocations;
+    EcmcStats *d_stats = nullptr;
+    EcmcStats *h_stats = nullptr;     // pinned
+    double *d_staging = nullptr;      // [n_chains][n_particles][dimension] + charges
+    double *d_staging_charges = nullptr;
+    uint32_t *d_streams = nullptr;
+    std::vector<EventPair> timed;     // launches not yet accounted
+    std::vector<EventPair> free_events;
+    double kernel_seconds = 0.0;
+    uint64_t kernel_launches = 0;
+    bool started = false;
+    std::string error;
+};
+
+namespace {
+
+int fail(EcmcHandle *h, int code, const std::string &message) {
+    if (h) h->error = message; else g_create_error = message;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                                      \
+    do {                                                                                                       \
+        cudaError_t err_ = (expr);                                                                             \
+        if (err_ != cudaSuccess)                                                                               \
+            return fail(h, ECMC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err_));               \
+    } while (0)
+
+template <typename T>
+int device_alloc(EcmcHandle *h, T **out, size_t count) {
+    void *p = nullptr;
+    CUDA_TRY(h, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    h->allocations.push_back(p);
+    *out = static_cast<T *>(p);
+    return ECMC_OK;
+}
+template <typename T>
+int device_upload(EcmcHandle *h, const T **out, const std::vector<T> &host) {
+    T *p = nullptr;
+    int rc = device_alloc(h, &p, host.size());
+    if (rc) return rc;
+    if (!host.empty()) CUDA_TRY(h, cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = p;
+    return ECMC_OK;
+}
+
+// Python's float % for a positive divisor (setting/hypercubic_setting.py:117)
+double host_py_mod(double x, double L) {
+    double m = std::fmod(x, L);
+    if (m != 0.0) { if (m < 0.0) m += L; } else m = 0.0;
+    return m;
+}
+
+// CuboidCells geometry per axis (cuboid_cells.py:98-146): cell `id` covers exactly the doubles x with
+// int(x / side) == id; cell_min / cell_max are the smallest / largest of them.
+void axis_geometry(int n, double side, std::vector<double> &cell_min, std::vector<double> &cell_max) {
+    cell_min.assign(n, 0.0);
+    cell_max.assign(n, 0.0);
+    const double inf = INFINITY;
+    for (int id = 0; id < n; id++) {
+        double lo = id * side, hi = (id + 1) * side;
+        if (lo > 0.0) {
+            while ((int)(lo / side) >= id) lo = std::nextafter(lo, -inf);
+            while ((int)(lo / side) < id) lo = std::nextafter(lo, inf);
+        }
+        while ((int)(hi / side) <= id) hi = std::nextafter(hi, inf);
+        while ((int)(hi / side) > id) hi = std::nextafter(hi, -inf);
+        cell_min[id] = lo;
+        cell_max[id] = hi;
+    }
+}
+
+int bit_length(uint32_t n) {
+    int bits = 0;
+    while ((n >> bits) != 0) bits++;
+    return bits;
+}
+
+int make_potential(EcmcHandle *h, const EcmcPotential &in, double L, PotentialParams *out) {
+    PotentialParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.kind = in.kind;
+    switch (in.kind) {
+    case ECMC_POT_NONE: break;
+    case ECMC_POT_INVERSE_POWER:
+        p.ip = make_inverse_power(in.params[0], in.params[1]);
+        if (!(p.ip.power > 0.0)) return fail(h, ECMC_ERR_INVALID, "inverse power potential: power must be > 0");
+        break;
+    case ECMC_POT_LENNARD_JONES:
+        if (!(in.params[0] > 0.0) || !(in.params[1] > 0.0))
+            return fail(h, ECMC_ERR_INVALID, "Lennard-Jones potential: prefactor and characteristic_length must be > 0");
+        p.lj = make_lennard_jones(in.params[0], in.params[1]);
+        break;
+    case ECMC_POT_DISPLACED_EVEN_POWER:
+        p.dep.k = in.params[0];
+        p.dep.r0 = in.params[1];
+        p.dep.power = in.params[2];
+        if (!(p.dep.k > 0.0) || !(p.dep.power > 0.0) || std::fmod(p.dep.power, 2.0) != 0.0)
+            return fail(h, ECMC_ERR_INVALID, "displaced even power potential: prefactor > 0 and an even power required");
+        break;
+    case ECMC_POT_HARD_SPHERE: p.p0 = in.params[0]; break;
+    case ECMC_POT_HARD_DIPOLE: p.p0 = in.params[0]; p.p1 = in.params[1]; break;
+    case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING: p.p0 = in.params[0]; break;
+    case ECMC_POT_MERGED_IMAGE_COULOMB: {
+        // constants and Fourier coefficients of merged_image_coulomb_potential.c:77-119; the loops of
+        // derivative() (:205-274) become flat term lists
+        const double prefactor = in.params[0], alpha = in.params[1];
+        const int fc = (int)in.params[2], pc = (int)in.params[3];
+        if (fc < 0 || fc > kMaxFourierCutoff || pc < 0 || pc > 100 || !(alpha > 0.0))
+            return fail(h, ECMC_ERR_INVALID, "merged image Coulomb potential: cutoffs / alpha out of range");
+        p.mic.prefactor = prefactor;
+        p.mic.alpha_over_length = alpha / L;
+        p.mic.alpha_over_length_sq = alpha * alpha / (L * L);
+        p.mic.two_alpha_root_pi = 2.0 * alpha / (L * std::sqrt(M_PI));
+        p.mic.length = L;
+        p.mic.two_pi_over_length = 2.0 * M_PI / L;
+        p.mic.fourier_cutoff = fc;
+        std::vector<int> images, modes;
+        std::vector<double> coefficients;
+        for (int k = -pc; k <= pc; k++) {
+            const int cy = (int)std::sqrt((double)(pc * pc - k * k));
+            for (int j = -cy; j <= cy; j++) {
+                const int cx = (int)std::sqrt((double)(pc * pc - j * j - k * k));
+                for (int i = -cx; i <= cx; i++) images.push_back((i & 0xff) | ((j & 0xff) << 8) | ((k & 0xff) << 16));
+            }
+        }
+        for (int i = 1; i <= fc; i++) {
+            const int cy = (int)std::sqrt((double)(fc * fc - i * i));
+            for (int j = 0; j <= cy; j++) {
+                const int cz = (int)std::sqrt((double)(fc * fc - i * i - j * j));
+                for (int k = 0; k <= cz; k++) {
+                    const double multiplicity = (j == 0 && k == 0) ? 1.0 : ((j == 0 || k == 0) ? 2.0 : 4.0);
+                    const double norm_sq = (double)(i * i + j * j + k * k);
+                    modes.push_back(i | (j << 8) | (k << 16));
+                    coefficients.push_back(4.0 * i * multiplicity / (norm_sq * L * L) * std::exp(-M_PI * M_PI * norm_sq / (alpha * alpha)));
+                }
+            }
+        }
+        p.mic.n_images = (int)images.size();
+        p.mic.n_modes = (int)modes.size();
+        int rc = device_upload(h, &p.mic.images, images);
+        if (!rc) rc = device_upload(h, &p.mic.modes, modes);
+        if (!rc) rc = device_upload(h, &p.mic.coefficients, coefficients);
+        if (rc) return rc;
+        break;
+    }
+    default: return fail(h, ECMC_ERR_INVALID, "unknown potential kind " + std::to_string(in.kind));
+    }
+    *out = p;
+    return ECMC_OK;
+}
+
+bool is_invertible(int kind) {
+    return kind == ECMC_POT_INVERSE_POWER || kind == ECMC_POT_LENNARD_JONES || kind == ECMC_POT_DISPLACED_EVEN_POWER ||
+           kind == ECMC_POT_HARD_SPHERE || kind == ECMC_POT_HARD_DIPOLE || kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING;
+}
+bool has_derivative(int kind) {
+    return kind == ECMC_POT_INVERSE_POWER || kind == ECMC_POT_LENNARD_JONES || kind == ECMC_POT_DISPLACED_EVEN_POWER ||
+           kind == ECMC_POT_MERGED_IMAGE_COULOMB || kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING;
+}
+
+int upload_walker(EcmcHandle *h, const EcmcWalkerTable &in, DeviceWalker *out, int n_cells) {
+    std::memset(out, 0, sizeof(*out));
+    if (in.n_entries <= 0) return ECMC_OK;
+    if (!in.cell_a || !in.cell_b || !in.rate_a) return fail(h, ECMC_ERR_INVALID, "Walker table with null arrays");
+    std::vector<WalkerEntry> entries(in.n_entries);
+    for (int e = 0; e < in.n_entries; e++) {
+        if (in.cell_a[e] < 0 || in.cell_a[e] >= n_cells || in.cell_b[e] >= n_cells)
+            return fail(h, ECMC_ERR_INVALID, "Walker table entry refers to a cell outside the cell system");
+        entries[e].cell_a = in.cell_a[e];
+        entries[e].cell_b = in.cell_b[e];
+        entries[e].rate_a = in.rate_a[e];
+    }
+    out->n_entries = in.n_entries;
+    out->bits = bit_length((uint32_t)in.n_entries);
+    out->total_rate = in.total_rate;
+    out->mean_rate = in.mean_rate;
+    return device_upload(h, &out->entries, entries);
+}
+
+int build_device_program(EcmcHandle *h) {
+    const EcmcProgram &p = h->program;
+    DeviceProgram &d = h->dprog;
+    std::memset(&d, 0, sizeof(d));
+    if (p.abi_version != ECMC_ABI_VERSION) return fail(h, ECMC_ERR_INVALID, "ABI version mismatch");
+    if (p.dimension < 1 || p.dimension > 3) return fail(h, ECMC_ERR_INVALID, "dimension must be 1, 2 or 3");
+    if (p.n_particles < 1 || p.n_particles >= (1 << 24))
+        return fail(h, ECMC_ERR_INVALID, "n_particles must be in [1, 2^24)");
+    if (!(p.system_length > 0.0) || !(p.beta > 0.0) || !(p.speed > 0.0) || !(p.chain_time > 0.0))
+        return fail(h, ECMC_ERR_INVALID, "system_length, beta, speed and chain_time must be > 0");
+    if (p.max_occupants < 1 || p.max_surplus < 0 || p.neighbor_layers < 0 || p.neighbor_layers > 3)
+        return fail(h, ECMC_ERR_INVALID, "max_occupants >= 1, max_surplus >= 0, 0 <= neighbor_layers <= 3 required");
+    if (p.initial_active < 0 || p.initial_active >= p.n_particles || p.initial_direction < 0 ||
+        p.initial_direction >= p.dimension)
+        return fail(h, ECMC_ERR_INVALID, "initial_active / initial_direction out of range");
+    d.dimension = p.dimension;
+    d.n_particles = p.n_particles;
+    d.n_cells = 1;
+    d.max_per_side = 1;
+    for (int k = 0; k < 3; k++) {
+        const int n = k < p.dimension ? p.cells_per_side[k] : 1;
+        if (n < 1 || n > 1023) return fail(h, ECMC_ERR_INVALID, "cells_per_side must be in [1, 1023]");
+        d.per_side[k] = n;
+        d.cumulative[k] = d.n_cells;
+        d.n_cells *= n;
+        d.side_length[k] = p.system_length / n;
+        d.max_per_side = std::max(d.max_per_side, n);
+    }
+    d.max_occupants = p.max_occupants;
+    d.max_surplus = std::max(p.max_surplus, 1);
+    d.pair_handler = p.pair_handler;
+    d.pair_use_charge = p.pair_use_charge;
+    d.veto_enabled = p.veto_enabled;
+    d.veto_use_charge = p.veto_use_charge;
+    d.seed = p.seed;
+    d.length = p.system_length;
+    d.half_length = p.system_length / 2.0;
+    d.beta = p.beta;
+    d.speed = p.speed;
+    d.chain_time = p.chain_time;
+    d.veto_target_charge = p.veto_target_charge;
+
+    // potentials
+    int rc;
+    if (p.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT) {
+        if (!is_invertible(p.pair_potential.kind)) return fail(h, ECMC_ERR_INVALID, "pair potential is not invertible");
+        if ((rc = make_potential(h, p.pair_potential, p.system_length, &d.cand_potential))) return rc;
+    } else if (p.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING) {
+        if (!is_invertible(p.pair_bounding_potential.kind) || !has_derivative(p.pair_bounding_potential.kind))
+            return fail(h, ECMC_ERR_INVALID, "pair bounding potential must be invertible with a derivative");
+        if (!has_derivative(p.pair_potential.kind)) return fail(h, ECMC_ERR_INVALID, "pair potential has no derivative");
+        if ((rc = make_potential(h, p.pair_bounding_potential, p.system_length, &d.cand_potential))) return rc;
+        if ((rc = make_potential(h, p.pair_potential, p.system_length, &d.real_potential))) return rc;
+    } else if (p.pair_handler != ECMC_PAIR_NONE) {
+        return fail(h, ECMC_ERR_INVALID, "unknown pair handler kind");
+    }
+    if ((d.cand_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB || d.real_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB ||
+         d.cand_potential.kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING) && p.dimension != 3)
+        return fail(h, ECMC_ERR_INVALID, "Coulomb potentials need dimension 3");
+
+    // nearby cells of cell zero, duplicates removed, in the order of cuboid_periodic_cells.py:74-100
+    {
+        std::vector<int> nearby;
+        const int nl = p.neighbor_layers, w = 2 * nl + 1;
+        int total = 1;
+        for (int k = 0; k < p.dimension; k++) total *= w;
+        for (int t = 0; t < total; t++) {
+            int rem = t, id[3] = {0, 0, 0};
+            for (int k = 0; k < p.dimension; k++) {
+                const int off = rem % w - nl;
+                rem /= w;
+                id[k] = ((off % d.per_side[k]) + d.per_side[k]) % d.per_side[k];
+            }
+            const int code = id[0] | (id[1] << 10) | (id[2] << 20);
+            bool dup = false;
+            for (int c : nearby) dup = dup || c == code;
+            if (!dup) nearby.push_back(code);
+        }
+        d.n_nearby = (int)nearby.size();
+        if ((rc = device_upload(h, &d.nearby, nearby))) return rc;
+    }
+    // cell boundaries and the translate table, per axis
+    {
+        const int mps = d.max_per_side;
+        std::vector<double> cmin_all(3 * mps, 0.0);
+        std::vector<int> translate(3 * mps * mps, 0);
+        for (int k = 0; k < 3; k++) {
+            std::vector<double> cmin, cmax;
+            axis_geometry(d.per_side[k], d.side_length[k], cmin, cmax);
+            for (int a = 0; a < d.per_side[k]; a++) {
+                cmin_all[k * mps + a] = cmin[a];
+                for (int r = 0; r < d.per_side[k]; r++) {
+                    const double x = host_py_mod((cmax[a] + cmin[a]) / 2.0 + cmin[r], p.system_length);
+                    translate[(k * mps + a) * mps + r] = (int)(x / d.side_length[k]);
+                }
+            }
+        }
+        if ((rc = device_upload(h, &d.cell_min_axis, cmin_all))) return rc;
+        if ((rc = device_upload(h, &d.translate_axis, translate))) return rc;
+    }
+    // cell veto
+    if (p.veto_enabled) {
+        if (!p.veto_tables || !p.veto_tables->bounds) return fail(h, ECMC_ERR_INVALID, "veto enabled without tables");
+        if (!has_derivative(p.veto_potential.kind)) return fail(h, ECMC_ERR_INVALID, "veto potential has no derivative");
+        if (p.veto_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB && p.dimension != 3)
+            return fail(h, ECMC_ERR_INVALID, "Coulomb potentials need dimension 3");
+        if (p.veto_use_charge && !(p.veto_target_charge != 0.0))
+            return fail(h, ECMC_ERR_INVALID, "veto_target_charge must not be 0");
+        if ((rc = make_potential(h, p.veto_potential, p.system_length, &d.veto_potential))) return rc;
+        for (int k = 0; k < p.dimension; k++) {
+            if ((rc = upload_walker(h, p.veto_tables->upper[k], &d.upper[k], d.n_cells))) return rc;
+            if ((rc = upload_walker(h, p.veto_tables->lower[k], &d.lower[k], d.n_cells))) return rc;
+            if (d.upper[k].n_entries <= 0 && d.lower[k].n_entries <= 0)
+                return fail(h, ECMC_ERR_INVALID, "veto enabled but a direction has no Walker table");
+        }
+        std::vector<double> bounds(p.veto_tables->bounds, p.veto_tables->bounds + (size_t)d.n_cells * p.dimension * 2);
+        if ((rc = device_upload(h, &d.bounds, bounds))) return rc;
+    }
+    return ECMC_OK;
+}
+
+// ---- kernel dispatch: specialised instantiations for the named configurations, one generic fallback ----------
+typedef void (*EventKernel)(const DeviceProgram, const DeviceState, const RunArgs);
+
+template <int CAND, int REAL, int VETO>
+EventKernel pick_record(bool record) {
+    return record ? event_kernel<CAND, REAL, VETO, true, kWarpsPerBlock> : event_kernel<CAND, REAL, VETO, false, kWarpsPerBlock>;
+}
+
+EventKernel pick_kernel(const DeviceProgram &d, bool record) {
+    const int cand = d.pair_handler == ECMC_PAIR_NONE ? 0 : d.cand_potential.kind;
+    const int real = d.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING ? d.real_potential.kind : 0;
+    const int veto = d.veto_enabled ? d.veto_potential.kind : 0;
+    const int LJ = ECMC_POT_LENNARD_JONES, HS = ECMC_POT_HARD_SPHERE, MIC = ECMC_POT_MERGED_IMAGE_COULOMB,
+              IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING;
+    if (cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record);
+    if (cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record);
+    if (cand == HS && real == 0 && veto == 0) return pick_record<ECMC_POT_HARD_SPHERE, 0, 0>(record);
+    if (cand == IPCB && real == MIC && veto == MIC)
+        return pick_record<ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, ECMC_POT_MERGED_IMAGE_COULOMB, ECMC_POT_MERGED_IMAGE_COULOMB>(record);
+    return pick_record<-1, -1, -1>(record);
+}
+
+int acquire_events(EcmcHandle *h, EventPair *out) {
+    if (!h->free_events.empty()) {
+        *out = h->free_events.back();
+        h->free_events.pop_back();
+        return ECMC_OK;
+    }
+    CUDA_TRY(h, cudaEventCreate(&out->start));
+    CUDA_TRY(h, cudaEventCreate(&out->stop));
+    return ECMC_OK;
+}
+
+int collect_timings(EcmcHandle *h) {
+    for (EventPair &e : h->timed) {
+        float ms = 0.0f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, e.start, e.stop));
+        h->kernel_seconds += 1.0e-3 * ms;
+        h->free_events.push_back(e);
+    }
+    h->timed.clear();
+    return ECMC_OK;
+}
+
+int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_events, EcmcEventRecord *d_records,
+                  int records_per_chain) {
+    if (!h->started) return fail(h, ECMC_ERR_STATE, "ecmc_run before ecmc_start / ecmc_upload_chain_states");
+    if (std::isnan(until_q) || std::isnan(until_r)) return fail(h, ECMC_ERR_INVALID, "until time is NaN");
+    if (max_events <= 0 && std::isinf(until_q))
+        return fail(h, ECMC_ERR_INVALID, "neither a time limit nor an event limit: the run would not end");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    RunArgs args;
+    args.until_q = until_q;
+    args.until_r = until_r;
+    args.max_events = max_events;
+    args.records = d_records;
+    args.records_per_chain = records_per_chain;
+    args.stats = h->d_stats;
+    EventPair ev;
+    int rc = acquire_events(h, &ev);
+    if (rc) return rc;
+    const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
+    const int blocks = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    CUDA_TRY(h, cudaEventRecord(ev.start, h->stream));
+    kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(ev.stop, h->stream));
+    h->timed.push_back(ev);
+    h->kernel_launches++;
+    return ECMC_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================================
+// lifecycle
+// ==========================================================================================================
+ECMC_API int ecmc_abi_version(void) { return ECMC_ABI_VERSION; }
+
+ECMC_API const char *ecmc_last_error(const EcmcHandle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+ECMC_API void ecmc_destroy(EcmcHandle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (EventPair &e : h->timed) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+    for (EventPair &e : h->free_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+    for (void *p : h->allocations) cudaFree(p);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+ECMC_API int ecmc_create(const EcmcProgram *program, int device, int n_chains, EcmcHandle **out) {
+    if (!out) return fail(nullptr, ECMC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!program) return fail(nullptr, ECMC_ERR_INVALID, "program is NULL");
+    if (n_chains < 1) return fail(nullptr, ECMC_ERR_INVALID, "n_chains must be >= 1");
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail(nullptr, ECMC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(err) +
+                                                " (libecmc_b200 has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(nullptr, ECMC_ERR_INVALID, "device index out of range");
+    EcmcHandle *h = new (std::nothrow) EcmcHandle();
+    if (!h) return fail(nullptr, ECMC_ERR_INVALID, "out of host memory");
+    h->device = device;
+    h->n_chains = n_chains;
+    h->program = *program;
+    int rc = ECMC_OK;
+    do {
+        if ((err = cudaSetDevice(device)) != cudaSuccess) { rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
+        if ((err = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err));
+            break;
+        }
+        if ((rc = build_device_program(h))) break;
+        const DeviceProgram &d = h->dprog;
+        const size_t n = (size_t)n_chains * d.n_particles;
+        h->state.n_chains = n_chains;
+        if ((rc = device_alloc(h, &h->state.particles, n))) break;
+        if ((rc = device_alloc(h, &h->state.occupants, (size_t)n_chains * d.n_cells * d.max_occupants))) break;
+        if ((rc = device_alloc(h, &h->state.surplus, (size_t)n_chains * d.max_surplus))) break;
+        if ((rc = device_alloc(h, &h->state.n_surplus, (size_t)n_chains))) break;
+        if ((rc = device_alloc(h, &h->state.chains, (size_t)n_chains))) break;
+        if ((rc = device_alloc(h, &h->d_stats, 1))) break;
+        if ((rc = device_alloc(h, &h->d_staging, n * d.dimension))) break;
+        if ((rc = device_alloc(h, &h->d_staging_charges, n))) break;
+        if ((rc = device_alloc(h, &h->d_streams, (size_t)n_chains))) break;
+        if ((err = cudaMallocHost(&h->h_stats, sizeof(EcmcStats))) != cudaSuccess) {
+            rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err));
+            break;
+        }
+        if ((err = cudaMemsetAsync(h->d_stats, 0, sizeof(EcmcStats), h->stream)) != cudaSuccess ||
+            (err = cudaMemsetAsync(h->state.n_surplus, 0, sizeof(int) * n_chains, h->stream)) != cudaSuccess ||
+            (err = cudaStreamSynchronize(h->stream)) != cudaSuccess) {
+            rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err));
+            break;
+        }
+    } while (0);
+    if (rc) {
+        g_create_error = h->error;
+        ecmc_destroy(h);
+        return rc;
+    }
+    h->program.veto_tables = nullptr;  // copied; the caller's arrays are not referenced after create
+    *out = h;
+    return ECMC_OK;
+}
+
+// ==========================================================================================================
+// state
+// ==========================================================================================================
+ECMC_API int ecmc_upload_positions(EcmcHandle *h, const double *positions, const double *charges) {
+    if (!h || !positions) return fail(h, ECMC_ERR_INVALID, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_chains * h->dprog.n_particles;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_staging, positions, n * h->dprog.dimension * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (charges)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_staging_charges, charges, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    pack_particles_kernel<<<blocks, 256, 0, h->stream>>>(h->d_staging, charges ? h->d_staging_charges : nullptr,
+                                                         h->state.particles, n, h->dprog.dimension);
+    CUDA_TRY(h, cudaGetLastError());
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_download_positions(EcmcHandle *h, double *positions) {
+    if (!h || !positions) return fail(h, ECMC_ERR_INVALID, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_chains * h->dprog.n_particles;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    unpack_particles_kernel<<<blocks, 256, 0, h->stream>>>(h->state.particles, h->d_staging, n, h->dprog.dimension);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(positions, h->d_staging, n * h->dprog.dimension * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return collect_timings(h);
+}
+
+ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_stream) {
+    if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (streams)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_streams, streams, sizeof(uint32_t) * h->n_chains, cudaMemcpyHostToDevice, h->stream));
+    const int blocks = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
+        h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
+        h->program.initial_direction, h->d_stats);
+    CUDA_TRY(h, cudaGetLastError());
+    h->started = true;
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_upload_chain_states(EcmcHandle *h, const EcmcChainState *states) {
+    if (!h || !states) return fail(h, ECMC_ERR_INVALID, "null argument");
+    for (int c = 0; c < h->n_chains; c++) {
+        const EcmcChainState &s = states[c];
+        if (s.active < 0 || s.active >= h->dprog.n_particles || s.direction < 0 || s.direction >= h->dprog.dimension ||
+            s.active_cell < 0 || s.active_cell >= h->dprog.n_cells || s.eoc_next_active < 0 ||
+            s.eoc_next_active >= h->dprog.n_particles)
+            return fail(h, ECMC_ERR_INVALID, "chain state " + std::to_string(c) + " out of range");
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->state.chains, states, sizeof(EcmcChainState) * h->n_chains, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->started = true;
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_download_chain_states(EcmcHandle *h, EcmcChainState *states) {
+    if (!h || !states) return fail(h, ECMC_ERR_INVALID, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(states, h->state.chains, sizeof(EcmcChainState) * h->n_chains, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return collect_timings(h);
+}
+
+ECMC_API int ecmc_upload_cells(EcmcHandle *h, const int32_t *occupants, const int32_t *surplus, const int32_t *n_surplus) {
+    if (!h || !occupants || !surplus || !n_surplus) return fail(h, ECMC_ERR_INVALID, "null argument");
+    const DeviceProgram &d = h->dprog;
+    for (int c = 0; c < h->n_chains; c++)
+        if (n_surplus[c] < 0 || n_surplus[c] > d.max_surplus) return fail(h, ECMC_ERR_INVALID, "n_surplus out of range");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->state.occupants, occupants, sizeof(int) * (size_t)h->n_chains * d.n_cells * d.max_occupants,
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->state.surplus, surplus, sizeof(int) * (size_t)h->n_chains * d.max_surplus,
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->state.n_surplus, n_surplus, sizeof(int) * (size_t)h->n_chains, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_download_cells(EcmcHandle *h, int32_t *occupants, int32_t *surplus, int32_t *n_surplus) {
+    if (!h || !occupants || !surplus || !n_surplus) return fail(h, ECMC_ERR_INVALID, "null argument");
+    const DeviceProgram &d = h->dprog;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(occupants, h->state.occupants, sizeof(int) * (size_t)h->n_chains * d.n_cells * d.max_occupants,
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(surplus, h->state.surplus, sizeof(int) * (size_t)h->n_chains * d.max_surplus,
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(n_surplus, h->state.n_surplus, sizeof(int) * (size_t)h->n_chains, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return collect_timings(h);
+}
+
+// ==========================================================================================================
+// the hot path
+// ==========================================================================================================
+ECMC_API int ecmc_run(EcmcHandle *h, double until_q, double until_r, int64_t max_events_per_chain) {
+    if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
+    return launch_events(h, until_q, until_r, max_events_per_chain, nullptr, 0);
+}
+
+ECMC_API int ecmc_sync(EcmcHandle *h, EcmcStats *stats) {
+    if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(EcmcStats), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, sizeof(EcmcStats), h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (stats) *stats = *h->h_stats;
+    int rc = collect_timings(h);
+    if (rc) return rc;
+    if (h->h_stats->capacity_errors)
+        return fail(h, ECMC_ERR_CAPACITY, "surplus list / occupant capacity overflowed in " +
+                                              std::to_string(h->h_stats->capacity_errors) + " place(s): raise max_surplus");
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_run_recorded(EcmcHandle *h, double until_q, double until_r, int64_t max_events_per_chain,
+                               EcmcEventRecord *records, int32_t records_per_chain, EcmcStats *stats) {
+    if (!h || !records || records_per_chain < 1) return fail(h, ECMC_ERR_INVALID, "null / empty record buffer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_chains * records_per_chain;
+    EcmcEventRecord *d_records = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_records, n * sizeof(EcmcEventRecord)));
+    cudaMemsetAsync(d_records, 0, n * sizeof(EcmcEventRecord), h->stream);
+    int rc = launch_events(h, until_q, until_r, max_events_per_chain, d_records, records_per_chain);
+    if (!rc) {
+        cudaError_t err = cudaMemcpyAsync(records, d_records, n * sizeof(EcmcEventRecord), cudaMemcpyDeviceToHost, h->stream);
+        if (err != cudaSuccess) rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err));
+    }
+    const int rc_sync = ecmc_sync(h, stats);
+    cudaFree(d_records);
+    return rc ? rc : rc_sync;
+}
+
+ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
+                                double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
+                                EcmcStats *stats) {
+    int rc = ecmc_upload_positions(h, positions_in, charges);
+    if (!rc) rc = ecmc_start(h, nullptr, first_stream);
+    if (!rc) rc = ecmc_run(h, until_q, until_r, max_events_per_chain);
+    if (!rc && positions_out) rc = ecmc_download_positions(h, positions_out);
+    const int rc_sync = h ? ecmc_sync(h, stats) : ECMC_ERR_INVALID;
+    return rc ? rc : rc_sync;
+}
+
+ECMC_API void *ecmc_stream(EcmcHandle *h) { return h ? (void *)h->stream : nullptr; }
+ECMC_API double ecmc_kernel_seconds(EcmcHandle *h) { return h ? h->kernel_seconds : 0.0; }
+ECMC_API uint64_t ecmc_kernel_launches(EcmcHandle *h) { return h ? h->kernel_launches : 0; }
+
+// ==========================================================================================================
+// batched potential arithmetic
+// ==========================================================================================================
+namespace {
+
+int potential_batch(bool displacement, const EcmcPotential *potential, int dimension, double system_length,
+                    const double *velocity, size_t n, const double *separations, const double *charges,
+                    const double *potential_changes, double *out, int device) {
+    if (!potential || !velocity || !out || (n && !separations)) return fail(nullptr, ECMC_ERR_INVALID, "null argument");
+    if (dimension < 1 || dimension > 3) return fail(nullptr, ECMC_ERR_INVALID, "dimension must be 1, 2 or 3");
+    const bool hard = potential->kind == ECMC_POT_HARD_SPHERE || potential->kind == ECMC_POT_HARD_DIPOLE;
+    if (displacement ? !is_invertible(potential->kind) : !has_derivative(potential->kind))
+        return fail(nullptr, ECMC_ERR_INVALID, displacement ? "potential is not invertible" : "potential has no derivative");
+    if ((potential->kind == ECMC_POT_MERGED_IMAGE_COULOMB || potential->kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING) &&
+        dimension != 3)
+        return fail(nullptr, ECMC_ERR_INVALID, "Coulomb potentials need dimension 3");
+    // StandardVelocityPotential._analyse_velocity (potential/abstracts.py:105-140)
+    int dir = -1;
+    bool standard = true;
+    for (int k = 0; k < dimension; k++)
+        if (velocity[k] != 0.0) {
+            if (dir >= 0) standard = false;
+            dir = k;
+        }
+    if (dir < 0 || !(velocity[dir] > 0.0)) standard = false;
+    if (!standard && !(hard && displacement))
+        return fail(nullptr, ECMC_ERR_INVALID, "velocity must have exactly one non-zero, positive component");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(nullptr, ECMC_ERR_CUDA, "no CUDA device (libecmc_b200 has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(nullptr, ECMC_ERR_INVALID, "device index out of range");
+    if (n == 0) return ECMC_OK;
+    EcmcHandle scratch;  // owns the temporary device allocations
+    scratch.device = device;
+    int rc = ECMC_OK;
+    cudaError_t err;
+    do {
+        if ((err = cudaSetDevice(device)) != cudaSuccess) { rc = fail(nullptr, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
+        PotentialParams params;
+        if ((rc = make_potential(&scratch, *potential, system_length, &params))) { g_create_error = scratch.error; break; }
+        BatchArgs b;
+        std::memset(&b, 0, sizeof(b));
+        b.dimension = dimension;
+        b.dir = standard ? dir : 0;
+        b.speed = standard ? velocity[dir] : 1.0;
+        b.length = system_length;
+        for (int k = 0; k < 3; k++) b.velocity[k] = k < dimension ? velocity[k] : 0.0;
+        b.n = n;
+        double *d_sep = nullptr, *d_charges = nullptr, *d_du = nullptr, *d_out = nullptr;
+        if ((rc = device_alloc(&scratch, &d_sep, n * dimension)) || (rc = device_alloc(&scratch, &d_out, n))) break;
+        if (charges && (rc = device_alloc(&scratch, &d_charges, 2 * n))) break;
+        if (potential_changes && displacement && (rc = device_alloc(&scratch, &d_du, n))) break;
+        err = cudaMemcpy(d_sep, separations, n * dimension * sizeof(double), cudaMemcpyHostToDevice);
+        if (err == cudaSuccess && d_charges) err = cudaMemcpy(d_charges, charges, 2 * n * sizeof(double), cudaMemcpyHostToDevice);
+        if (err == cudaSuccess && d_du) err = cudaMemcpy(d_du, potential_changes, n * sizeof(double), cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) { rc = fail(nullptr, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
+        b.separations = d_sep;
+        b.charges = d_charges;
+        b.potential_changes = d_du;
+        b.out = d_out;
+        if (displacement) {
+            const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+            displacement_batch_kernel<<<blocks, 256>>>(params, b);
+        } else {
+            const size_t work = params.kind == ECMC_POT_MERGED_IMAGE_COULOMB ? (n + 7) / 8 : (n + 255) / 256;
+            const int blocks = (int)std::min<size_t>(work, 148 * 8);
+            derivative_batch_kernel<<<blocks, 256>>>(params, b);
+        }
+        if ((err = cudaGetLastError()) != cudaSuccess || (err = cudaDeviceSynchronize()) != cudaSuccess ||
+            (err = cudaMemcpy(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            rc = fail(nullptr, ECMC_ERR_CUDA, cudaGetErrorString(err));
+            break;
+        }
+    } while (0);
+    for (void *p : scratch.allocations) cudaFree(p);
+    return rc;
+}
+
+}  // namespace
+
+ECMC_API int ecmc_potential_derivative(const EcmcPotential *potential, int dimension, double system_length,
+                                       const double *velocity, size_t n, const double *separations,
+                                       const double *charges, double *out, int device) {
+    return potential_batch(false, potential, dimension, system_length, velocity, n, separations, charges, nullptr, out, device);
+}
+
+ECMC_API int ecmc_potential_displacement(const EcmcPotential *potential, int dimension, double system_length,
+                                         const double *velocity, size_t n, const double *separations,
+                                         const double *charges, const double *potential_changes, double *out, int device) {
+    return potential_batch(true, potential, dimension, system_length, velocity, n, separations, charges, potential_changes,
+                           out, device);
+}
+
+// ==========================================================================================================
+// the random stream on the host (same functions the kernels use)
+// ==========================================================================================================
+ECMC_API void ecmc_random_doubles(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t first, size_t n,
+                                  double *out) {
+    const StreamKey key = {seed, stream, event};
+    for (size_t i = 0; i < n; i++) out[i] = stream_double(key, slot, first + (uint32_t)i);
+}
+
+ECMC_API void ecmc_random_words(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t first, size_t n,
+                                uint32_t *out) {
+    const StreamKey key = {seed, stream, event};
+    for (size_t i = 0; i < n; i++) out[i] = stream_word(key, slot, first + (uint32_t)i);
+}

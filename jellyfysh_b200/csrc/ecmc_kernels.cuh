@@ -1,0 +1,644 @@
+// ecmc_kernels.cuh -- the event kernel: one warp advances one Markov chain, event after event.
+//
+// Per event (= one iteration of the reference's mediator loop, jellyfysh/mediator/single_process_mediator.py:91-156):
+//   lanes  <- candidate targets: occupants of the nearby cells of the active cell (ExcludedCellsTagger,
+//             excluded_cells_tagger.py:129-132), then the surplus list (SurplusCellsTagger, :129-131);
+//             more than 32 candidates are taken in passes
+//   lane 0 <- the cell-veto candidate (CellVetoEventHandler.send_event_time, cell_veto_event_handler.py:200-238)
+//   lane 1 <- the cell-boundary candidate (CellBoundaryEventHandler.send_event_time, :122-156)
+//   argmin over (quotient, remainder, sequence) by warp shuffles  == HeapScheduler.get_succeeding_event
+//   the end-of-chain candidate persists in the chain state and is compared last
+//   out-state (lifting) + commit + occupancy update, all lanes redundantly, lane 0 writes.
+// Chain-level state lives in registers between events; positions / occupancy stay in HBM (L2) and are
+// gathered with one 32-byte load per target.
+#pragma once
+
+#include "ecmc_program.cuh"
+
+namespace ecmc {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSeqNone = 0x7fffffff;
+
+template <int KIND>
+ECMC_D int resolve_kind(int runtime_kind) { return KIND >= 0 ? KIND : runtime_kind; }
+
+ECMC_D bool needs_potential_change(int kind) { return !(kind == ECMC_POT_HARD_SPHERE || kind == ECMC_POT_HARD_DIPOLE); }
+
+// component along the direction of motion and squared norm of the others
+ECMC_D void split_separation(int dir, double sx, double sy, double sz, double &sd, double &perp2) {
+    if (dir == 0) { sd = sx; perp2 = fma(sy, sy, sz * sz); }
+    else if (dir == 1) { sd = sy; perp2 = fma(sx, sx, sz * sz); }
+    else { sd = sz; perp2 = fma(sx, sx, sy * sy); }
+}
+
+// InvertiblePotential.displacement(velocity, separation, charges, potential_change): a TIME
+// (jellyfysh/potential/potential.py:218-301, potential/abstracts.py:212-243)
+template <int KIND>
+ECMC_D double displacement_time(const PotentialParams &p, int dir, double speed, double length, double sx, double sy,
+                                double sz, double c1, double c2, double du) {
+    double sd, perp2;
+    split_separation(dir, sx, sy, sz, sd, perp2);
+    switch (resolve_kind<KIND>(p.kind)) {
+    case ECMC_POT_LENNARD_JONES: return lj_displacement(p.lj, sd, perp2, du) / speed;
+    case ECMC_POT_INVERSE_POWER: {
+        double r2, p2;
+        ip_squares(dir, sx, sy, sz, r2, p2);
+        return ip_displacement(p.ip, sd, p2, r2, c1, c2, du) / speed;
+    }
+    case ECMC_POT_DISPLACED_EVEN_POWER: return dep_displacement(p.dep, sd, perp2, du) / speed;
+    case ECMC_POT_HARD_SPHERE:
+        return hard_sphere_time(p.p0, __dmul_rn(speed, speed), __dmul_rn(speed, sd), dot3(sx, sy, sz, sx, sy, sz));
+    case ECMC_POT_HARD_DIPOLE:
+        return hard_dipole_time(p.p0, p.p1, __dmul_rn(speed, speed), __dmul_rn(speed, sd), dot3(sx, sy, sz, sx, sy, sz));
+    case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING:
+        return ipcb_displacement(p.p0 * c1 * c2, sd, perp2, du, length) / speed;
+    default: return NAN;
+    }
+}
+
+// Potential.derivative(velocity, separation, charges) (potential/abstracts.py:80-103). Warp-collective: all 32
+// lanes call it with identical arguments (the merged-image Coulomb sum is spread over the lanes).
+template <int KIND>
+ECMC_D double derivative_warp(const PotentialParams &p, int dir, double speed, double sx, double sy, double sz,
+                              double c1, double c2, double *trig, int lane) {
+    double sd, perp2;
+    split_separation(dir, sx, sy, sz, sd, perp2);
+    switch (resolve_kind<KIND>(p.kind)) {
+    case ECMC_POT_LENNARD_JONES: return lj_derivative(p.lj, sd, perp2) * speed;
+    case ECMC_POT_INVERSE_POWER: {
+        double r2, p2;
+        ip_squares(dir, sx, sy, sz, r2, p2);
+        return ip_derivative(p.ip, sd, r2, c1, c2) * speed;
+    }
+    case ECMC_POT_DISPLACED_EVEN_POWER: return dep_derivative(p.dep, sd, perp2) * speed;
+    case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING: return ipcb_derivative(p.p0 * c1 * c2, sd, perp2) * speed;
+    case ECMC_POT_MERGED_IMAGE_COULOMB: {
+        // permutation_3d (base/vectors.py:217-239): x is the direction of motion
+        const double px = sd;
+        const double py = dir == 0 ? sy : (dir == 1 ? sz : sx);
+        const double pz = dir == 0 ? sz : (dir == 1 ? sx : sy);
+        return p.mic.prefactor * c1 * c2 * mic_derivative_warp(p.mic, px, py, pz, trig, lane) * speed;
+    }
+    default: return NAN;
+    }
+}
+
+template <int REAL, int VETO>
+struct UsesMic {
+    static constexpr bool value = REAL < 0 || VETO < 0 || REAL == ECMC_POT_MERGED_IMAGE_COULOMB ||
+                                  VETO == ECMC_POT_MERGED_IMAGE_COULOMB;
+};
+
+// position -> per-axis cell identifiers, int(x / cell side) (cuboid_cells.py:190-211)
+ECMC_D void cell_identifier_of(const DeviceProgram &P, const Particle &a, int id[3]) {
+    id[0] = (int)(a.x / P.side_length[0]);
+    id[1] = P.dimension > 1 ? (int)(a.y / P.side_length[1]) : 0;
+    id[2] = P.dimension > 2 ? (int)(a.z / P.side_length[2]) : 0;
+}
+ECMC_D int flat_cell(const DeviceProgram &P, const int id[3]) {
+    return id[0] * P.cumulative[0] + id[1] * P.cumulative[1] + id[2] * P.cumulative[2];
+}
+ECMC_D double component(const Particle &a, int dir) { return dir == 0 ? a.x : (dir == 1 ? a.y : a.z); }
+ECMC_D void set_component(Particle &a, int dir, double v) {
+    if (dir == 0) a.x = v; else if (dir == 1) a.y = v; else a.z = v;
+}
+
+// SingleActiveCellOccupancy: append to the occupants of a cell, or to the surplus when the cell is full
+// (single_active_cell_occupancy.py:117-121, :176-180). Serial, called by one lane. Returns the change of
+// n_surplus, or 2 on overflow of the surplus capacity.
+ECMC_D int occupancy_insert(int *occ, int *sur, int n_surplus, int m, int max_surplus, int cell, int id) {
+    for (int s = 0; s < m; s++)
+        if (occ[cell * m + s] < 0) { occ[cell * m + s] = id; return 0; }
+    if (n_surplus >= max_surplus) return 2;
+    sur[n_surplus] = id;
+    return 1;
+}
+// Remove from the occupants (list.remove keeps the order of the rest; the surplus is not promoted, see
+// single_active_cell_occupancy.py:186-193) or else from the surplus. Returns the change of n_surplus, 2 if absent.
+ECMC_D int occupancy_remove(int *occ, int *sur, int n_surplus, int m, int cell, int id) {
+    for (int s = 0; s < m; s++)
+        if (occ[cell * m + s] == id) {
+            for (int t = s; t + 1 < m; t++) occ[cell * m + t] = occ[cell * m + t + 1];
+            occ[cell * m + m - 1] = -1;
+            return 0;
+        }
+    for (int s = 0; s < n_surplus; s++)
+        if (sur[s] == id) {
+            for (int t = s; t + 1 < n_surplus; t++) sur[t] = sur[t + 1];
+            return -1;
+        }
+    return 2;
+}
+
+template <int CAND, int REAL, int VETO, bool RECORD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
+    __shared__ double trig_all[UsesMic<REAL, VETO>::value ? WARPS * kTrigDoubles : 1];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chain = blockIdx.x * WARPS + warp;
+    if (chain >= S.n_chains) return;
+    double *trig = UsesMic<REAL, VETO>::value ? trig_all + warp * kTrigDoubles : trig_all;
+
+    Particle *part = S.particles + (size_t)chain * P.n_particles;
+    const int m = P.max_occupants;
+    int *occ = S.occupants + (size_t)chain * P.n_cells * m;
+    int *sur = S.surplus + (size_t)chain * P.max_surplus;
+    EcmcChainState *stp = S.chains + chain;
+
+    // chain state -> registers (uniform over the warp)
+    int active = stp->active, dir = stp->direction;
+    Time now = {stp->time_q, stp->time_r};
+    Time eoc = {stp->eoc_q, stp->eoc_r};
+    int eoc_next = stp->eoc_next_active;
+    int active_cell = stp->active_cell;
+    unsigned long long ev = stp->event_counter;
+    const uint32_t stream = stp->stream;
+    int pending_kind = stp->pending_kind, pending_target = stp->pending_target;
+    Time pending_t = {stp->pending_q, stp->pending_r};
+    double pending_rate = stp->pending_rate, pending_position = stp->pending_position;
+    Time pending_stamp = {stp->pending_stamp_q, stp->pending_stamp_r};
+    int n_surplus = S.n_surplus[chain];
+    Particle a = part[active];
+    int cid[3];
+    cid[0] = (active_cell / P.cumulative[0]) % P.per_side[0];
+    cid[1] = (active_cell / P.cumulative[1]) % P.per_side[1];
+    cid[2] = (active_cell / P.cumulative[2]) % P.per_side[2];
+
+    const Time until = {A.until_q, A.until_r};
+    const double L = P.length, half = P.half_length, speed = P.speed;
+    const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
+
+    unsigned long long n_events = 0, n_pair = 0, n_veto = 0, n_veto_acc = 0, n_boundary = 0, n_eoc = 0, n_candidates = 0,
+                       n_violations = 0, n_capacity = 0;
+    bool stopped_by_time = false;
+
+    while (A.max_events <= 0 || (long long)n_events < A.max_events) {
+        const StreamKey key = {P.seed, stream, ev};
+        // the interaction winner: (time, kind, target particle, target cell, bounding rate)
+        Time bt = time_inf();
+        int bkind = ECMC_EVENT_NONE, btarget = -1, bcell = -1;
+        double brate = 0.0;
+        int n_cand = 0;
+        const bool was_pending = pending_kind != ECMC_EVENT_NONE;
+        if (was_pending) {
+            // a candidate that survived a host control event: nothing is recomputed, no draws are consumed
+            bkind = pending_kind;
+            bt = pending_t;
+            brate = pending_rate;
+            if (bkind == ECMC_EVENT_PAIR) btarget = pending_target; else bcell = pending_target;
+        } else {
+            int wseq = kSeqNone;  // per-lane best
+            const int nearby_slots = P.pair_handler != ECMC_PAIR_NONE ? P.n_nearby * m : 0;
+            const int n_slots = P.pair_handler != ECMC_PAIR_NONE ? nearby_slots + n_surplus : 0;
+            const double c_active = P.pair_use_charge ? a.charge : 1.0;
+            for (int base = 0; base < n_slots; base += 32) {
+                const int s = base + lane;
+                int target = -1;
+                if (s < nearby_slots) {
+                    const int ci = m == 1 ? s : s / m;
+                    const int code = __ldg(P.nearby + ci);
+                    int x = cid[0] + (code & 1023), y = cid[1] + ((code >> 10) & 1023), z = cid[2] + (code >> 20);
+                    if (x >= P.per_side[0]) x -= P.per_side[0];
+                    if (y >= P.per_side[1]) y -= P.per_side[1];
+                    if (z >= P.per_side[2]) z -= P.per_side[2];
+                    const int cell = x * P.cumulative[0] + y * P.cumulative[1] + z * P.cumulative[2];
+                    target = occ[cell * m + (s - ci * m)];
+                } else if (s < n_slots) {
+                    target = sur[s - nearby_slots];
+                }
+                Time t = time_inf();
+                if (target >= 0) {
+                    const Particle tp = part[target];
+                    const double sx = correct_separation_entry(tp.x - a.x, L, half);
+                    const double sy = correct_separation_entry(tp.y - a.y, L, half);
+                    const double sz = correct_separation_entry(tp.z - a.z, L, half);
+                    double du = 0.0;
+                    if (cand_needs_du)
+                        du = expovariate(stream_double(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target), 0), P.beta);
+                    const double dt = displacement_time<CAND>(P.cand_potential, dir, speed, L, sx, sy, sz, c_active,
+                                                              P.pair_use_charge ? tp.charge : 1.0, du);
+                    t = time_add(now, dt);
+                }
+                const bool finite = target >= 0 && isfinite(t.q);  // heap_scheduler.py:139: only finite times
+                n_cand += __popc(__ballot_sync(kFull, finite));
+                if (finite && time_lt(t, bt)) {
+                    bt = t; wseq = s; bkind = ECMC_EVENT_PAIR; btarget = target;
+                }
+            }
+            // cell veto (lane 0) and cell boundary (lane 1)
+            bool veto_finite = false;
+            if (lane == 0 && P.veto_enabled) {
+                double charge_factor = 1.0;
+                if (P.veto_use_charge) charge_factor = a.charge * 1.0 / P.veto_target_charge;
+                int rate_index = 0;
+                const DeviceWalker *w = &P.upper[dir];
+                if (!(charge_factor > 0.0)) { charge_factor *= -1.0; w = &P.lower[dir]; rate_index = 1; }
+                const double total_rate = w->total_rate * charge_factor;
+                // random.choice(table): _randbelow(n) by rejection on the top bits of successive words
+                uint32_t e = 0;
+                for (uint32_t index = 0;; index += 4) {
+                    const Philox4 b = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0), index >> 2);
+                    bool found = false;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t r = b.w[j] >> (32 - w->bits);
+                        if (!found && r < (uint32_t)w->n_entries) { e = r; found = true; }
+                    }
+                    if (found) break;
+                }
+                const Philox4 b = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0), 0);
+                const double u0 = words_to_double(b.w[0], b.w[1]), u1 = words_to_double(b.w[2], b.w[3]);
+                const WalkerEntry entry = w->entries[e];
+                const int relative_cell = (0.0 + (w->mean_rate - 0.0) * u0 <= entry.rate_a) ? entry.cell_a : entry.cell_b;
+                const double rate = __ldg(P.bounds + (relative_cell * P.dimension + dir) * 2 + rate_index) * charge_factor;
+                // translate(active cell, relative cell), per axis (cuboid_periodic_cells.py:182-207)
+                const int mps = P.max_per_side;
+                const int rx = (relative_cell / P.cumulative[0]) % P.per_side[0];
+                const int ry = (relative_cell / P.cumulative[1]) % P.per_side[1];
+                const int rz = (relative_cell / P.cumulative[2]) % P.per_side[2];
+                const int tx = __ldg(P.translate_axis + (0 * mps + cid[0]) * mps + rx);
+                const int ty = __ldg(P.translate_axis + (1 * mps + cid[1]) * mps + ry);
+                const int tz = __ldg(P.translate_axis + (2 * mps + cid[2]) * mps + rz);
+                const double dt = expovariate(u1, P.beta) / (total_rate * speed);
+                const Time t = time_add(now, dt);
+                veto_finite = isfinite(t.q);
+                if (veto_finite && time_lt(t, bt)) {
+                    bt = t; wseq = n_slots; bkind = ECMC_EVENT_CELL_VETO; btarget = -1;
+                    bcell = tx * P.cumulative[0] + ty * P.cumulative[1] + tz * P.cumulative[2];
+                    brate = rate;
+                }
+            }
+            if (lane == 1) {
+                // neighbor cell in the positive direction and its lower boundary
+                int nid = cid[dir] + 1;
+                if (nid >= P.per_side[dir]) nid = 0;
+                const double neighbor_boundary = __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
+                double separation = neighbor_boundary - component(a, dir);
+                if (separation < 0.0) separation = separation + L;  // next_image, hypercubic_setting.py:191
+                const Time t = time_add(now, separation / speed);
+                if (time_lt(t, bt)) {
+                    bt = t; wseq = n_slots + 1; bkind = ECMC_EVENT_CELL_BOUNDARY; btarget = -1;
+                    bcell = active_cell + (nid - cid[dir]) * P.cumulative[dir];
+                }
+            }
+            n_cand += __popc(__ballot_sync(kFull, veto_finite)) + 1;
+            // argmin over the warp: lexicographic (quotient, remainder, sequence)
+            double rq = bt.q, rr = bt.r;
+            int rseq = wseq;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oq = __shfl_xor_sync(kFull, rq, o), orr = __shfl_xor_sync(kFull, rr, o);
+                const int os = __shfl_xor_sync(kFull, rseq, o);
+                const bool take = oq < rq || (oq == rq && (orr < rr || (orr == rr && os < rseq)));
+                if (take) { rq = oq; rr = orr; rseq = os; }
+            }
+            const unsigned owners = __ballot_sync(kFull, wseq == rseq && rseq != kSeqNone);
+            const int owner = owners ? __ffs(owners) - 1 : 0;
+            bt.q = rq; bt.r = rr;
+            bkind = __shfl_sync(kFull, bkind, owner);
+            btarget = __shfl_sync(kFull, btarget, owner);
+            bcell = __shfl_sync(kFull, bcell, owner);
+            brate = __shfl_sync(kFull, brate, owner);
+            if (!owners) bkind = ECMC_EVENT_NONE;
+        }
+
+        // the end-of-chain candidate lives in the scheduler since the chain started
+        n_cand++;
+        const bool eoc_first = time_lt(eoc, bt);
+        const Time event_time = eoc_first ? eoc : bt;
+        const int kind = eoc_first ? ECMC_EVENT_END_OF_CHAIN : bkind;
+        if (!time_lt(event_time, until)) {
+            // a host control event comes first: the interaction winner stays scheduled
+            pending_kind = bkind;
+            pending_t = bt;
+            pending_rate = brate;
+            pending_target = bkind == ECMC_EVENT_PAIR ? btarget : bcell;
+            if (!was_pending) {
+                pending_position = component(a, dir);
+                pending_stamp = now;
+            }
+            stopped_by_time = true;
+            break;
+        }
+        pending_kind = ECMC_EVENT_NONE;
+        if (was_pending && kind != ECMC_EVENT_END_OF_CHAIN) {
+            // the kept handler's in-state predates the control event's time slice
+            set_component(a, dir, pending_position);
+            now = pending_stamp;
+        }
+
+        // ---- out-state: time slice of the active particle (event_handler/abstracts/abstracts.py:82-95)
+        {
+            const double dt = time_sub(event_time, now);
+            set_component(a, dir, correct_position_entry(__dadd_rn(component(a, dir), __dmul_rn(speed, dt)), L));
+            now = event_time;
+        }
+        int new_active = active, accepted = 0, rec_target = -1;
+        switch (kind) {
+        case ECMC_EVENT_PAIR: {
+            rec_target = btarget;
+            if (P.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT) {
+                accepted = 1;  // two_leaf_unit_event_handler.py:140-154
+            } else {
+                // two_leaf_unit_bounding_potential_event_handler.py:148-168 +
+                // event_handler_with_bounding_potential.py:75-101
+                const Particle tp = part[btarget];
+                const double sx = correct_separation_entry(tp.x - a.x, L, half);
+                const double sy = correct_separation_entry(tp.y - a.y, L, half);
+                const double sz = correct_separation_entry(tp.z - a.z, L, half);
+                const double c1 = P.pair_use_charge ? a.charge : 1.0, c2 = P.pair_use_charge ? tp.charge : 1.0;
+                const double bounding_rate = derivative_warp<CAND>(P.cand_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
+                const double real = derivative_warp<REAL>(P.real_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
+                if (real > 0.0) {
+                    if (bounding_rate < real) n_violations++;
+                    const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+                    if (0.0 + (bounding_rate - 0.0) * u < real) accepted = 1;
+                }
+            }
+            if (accepted) new_active = btarget;
+            n_pair++;
+            break;
+        }
+        case ECMC_EVENT_CELL_VETO: {
+            // mediator.py:265-292 + leaf_unit_cell_veto_event_handler.py:117-149
+            const int t = occ[bcell * m];
+            rec_target = t;
+            if (t >= 0) {
+                const Particle tp = part[t];
+                const double sx = correct_separation_entry(tp.x - a.x, L, half);
+                const double sy = correct_separation_entry(tp.y - a.y, L, half);
+                const double sz = correct_separation_entry(tp.z - a.z, L, half);
+                const double c1 = P.veto_use_charge ? a.charge : 1.0, c2 = P.veto_use_charge ? tp.charge : 1.0;
+                const double real = derivative_warp<VETO>(P.veto_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
+                if (real > 0.0) {
+                    if (brate < real) n_violations++;
+                    const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+                    if (0.0 + (brate - 0.0) * u < real) { accepted = 1; new_active = t; }
+                }
+            }
+            n_veto++;
+            n_veto_acc += accepted;
+            break;
+        }
+        case ECMC_EVENT_CELL_BOUNDARY: {
+            // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
+            const int nid = (bcell / P.cumulative[dir]) % P.per_side[dir];
+            set_component(a, dir, __ldg(P.cell_min_axis + dir * P.max_per_side + nid));
+            n_boundary++;
+            break;
+        }
+        case ECMC_EVENT_END_OF_CHAIN:
+            // abstracts/end_of_chain_event_handler.py:107-187, new direction = (d + 1) mod D
+            new_active = eoc_next;
+            rec_target = new_active;
+            accepted = 1;
+            n_eoc++;
+            break;
+        default: break;
+        }
+        if (RECORD && lane == 0 && (long long)n_events < A.records_per_chain) {
+            EcmcEventRecord rec;
+            rec.kind = kind; rec.target = rec_target; rec.target_cell = kind == ECMC_EVENT_END_OF_CHAIN ? -1 : bcell;
+            rec.accepted = accepted; rec.n_candidates = n_cand;
+            rec.new_active = new_active;
+            rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % P.dimension : dir;
+            rec.reserved = 0;
+            rec.time_q = event_time.q; rec.time_r = event_time.r;
+            rec.active_pos[0] = a.x; rec.active_pos[1] = a.y; rec.active_pos[2] = a.z;
+            A.records[(size_t)chain * A.records_per_chain + n_events] = rec;
+        }
+        ev++;
+        n_events++;
+        n_candidates += (unsigned long long)n_cand;
+        if (kind == ECMC_EVENT_END_OF_CHAIN) dir = (dir + 1) % P.dimension;
+
+        // ---- SingleActiveCellOccupancy.update (single_active_cell_occupancy.py:149-203)
+        if (new_active != active) {
+            int delta = 0;
+            if (lane == 0) {
+                part[active] = a;
+                delta = occupancy_insert(occ, sur, n_surplus, m, P.max_surplus, active_cell, active);
+            }
+            delta = __shfl_sync(kFull, delta, 0);
+            if (delta == 2) n_capacity++; else n_surplus += delta;
+            __syncwarp();
+            active = new_active;
+            a = part[active];
+            cell_identifier_of(P, a, cid);
+            active_cell = flat_cell(P, cid);
+            delta = 0;
+            if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, m, active_cell, active);
+            delta = __shfl_sync(kFull, delta, 0);
+            if (delta == 2) n_capacity++; else n_surplus += delta;
+            __syncwarp();
+        } else {
+            cell_identifier_of(P, a, cid);
+            active_cell = flat_cell(P, cid);
+        }
+        if (kind == ECMC_EVENT_END_OF_CHAIN) {
+            // the next end-of-chain candidate: chain_time after this one, new active by randint
+            // (single_independent_active_periodic_direction_end_of_chain_event_handler.py:203-237)
+            eoc = time_add(now, time_sub(now, now) + P.chain_time);
+            const StreamKey next_key = {P.seed, stream, ev};
+            eoc_next = (int)stream_randbelow(next_key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.n_particles);
+        }
+    }
+
+    if (stopped_by_time) {
+        // the sampling / end-of-run handler time-slices the active unit (fixed_interval_sampling_event_handler.py:96-109)
+        const double dt = time_sub(until, now);
+        set_component(a, dir, correct_position_entry(__dadd_rn(component(a, dir), __dmul_rn(speed, dt)), L));
+        now = until;
+    }
+    if (lane == 0) {
+        part[active] = a;
+        stp->active = active; stp->direction = dir;
+        stp->time_q = now.q; stp->time_r = now.r;
+        stp->eoc_q = eoc.q; stp->eoc_r = eoc.r;
+        stp->eoc_next_active = eoc_next; stp->active_cell = active_cell;
+        stp->event_counter = ev;
+        stp->pending_kind = pending_kind; stp->pending_target = pending_target;
+        stp->pending_q = pending_t.q; stp->pending_r = pending_t.r;
+        stp->pending_rate = pending_rate; stp->pending_position = pending_position;
+        stp->pending_stamp_q = pending_stamp.q; stp->pending_stamp_r = pending_stamp.r;
+        S.n_surplus[chain] = n_surplus;
+        if (A.stats) {
+            unsigned long long *st = reinterpret_cast<unsigned long long *>(A.stats);
+            if (n_events) atomicAdd(st + 0, n_events);
+            if (n_pair) atomicAdd(st + 1, n_pair);
+            if (n_veto) atomicAdd(st + 2, n_veto);
+            if (n_veto_acc) atomicAdd(st + 3, n_veto_acc);
+            if (n_boundary) atomicAdd(st + 4, n_boundary);
+            if (n_eoc) atomicAdd(st + 5, n_eoc);
+            if (n_candidates) atomicAdd(st + 6, n_candidates);
+            if (n_violations) atomicAdd(st + 7, n_violations);
+            if (n_capacity) atomicAdd(st + 8, n_capacity);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// start of run: SingleActiveCellOccupancy.initialize (single_active_cell_occupancy.py:95-121) +
+// InitialChainStartOfRunEventHandler (initial_chain_start_of_run_event_handler.py:92-131). One warp per chain.
+// Particles enter in identifier order: the first max_occupants of a cell become occupants, the rest surplus.
+// ---------------------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams, uint32_t first_stream,
+             int initial_active, int initial_direction, EcmcStats *stats) {
+    const int lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (chain >= S.n_chains) return;
+    Particle *part = S.particles + (size_t)chain * P.n_particles;
+    const int m = P.max_occupants;
+    int *occ = S.occupants + (size_t)chain * P.n_cells * m;
+    int *sur = S.surplus + (size_t)chain * P.max_surplus;
+    for (int i = lane; i < P.n_cells * m; i += 32) occ[i] = -1;
+    __syncwarp();
+    int n_surplus = 0, overflow = 0;
+    if (m == 1) {
+        // lowest identifier wins the cell; everyone else goes to the surplus in identifier order
+        for (int i = lane; i < P.n_particles; i += 32) {
+            int id[3];
+            const Particle p = part[i];
+            cell_identifier_of(P, p, id);
+            atomicMin(reinterpret_cast<unsigned int *>(occ + flat_cell(P, id)), (unsigned int)i);
+        }
+        __syncwarp();
+        for (int base = 0; base < P.n_particles; base += 32) {
+            const int i = base + lane;
+            bool extra = false;
+            if (i < P.n_particles) {
+                int id[3];
+                const Particle p = part[i];
+                cell_identifier_of(P, p, id);
+                extra = occ[flat_cell(P, id)] != i;
+            }
+            const unsigned mask = __ballot_sync(kFull, extra);
+            if (extra) {
+                const int slot = n_surplus + __popc(mask & ((1u << lane) - 1u));
+                if (slot < P.max_surplus) sur[slot] = i;
+            }
+            n_surplus += __popc(mask);
+        }
+        if (n_surplus > P.max_surplus) { overflow = n_surplus - P.max_surplus; n_surplus = P.max_surplus; }
+    } else {
+        if (lane == 0) {
+            for (int i = 0; i < P.n_particles; i++) {
+                int id[3];
+                const Particle p = part[i];
+                cell_identifier_of(P, p, id);
+                const int delta = occupancy_insert(occ, sur, n_surplus, m, P.max_surplus, flat_cell(P, id), i);
+                if (delta == 2) overflow++; else n_surplus += delta;
+            }
+        }
+        n_surplus = __shfl_sync(kFull, n_surplus, 0);
+        overflow = __shfl_sync(kFull, overflow, 0);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        EcmcChainState st;
+        st.active = initial_active; st.direction = initial_direction;
+        st.time_q = 0.0; st.time_r = 0.0;
+        st.event_counter = 0;
+        st.stream = streams ? streams[chain] : first_stream + (uint32_t)chain;
+        int id[3];
+        const Particle a = part[initial_active];
+        cell_identifier_of(P, a, id);
+        st.active_cell = flat_cell(P, id);
+        const int delta = occupancy_remove(occ, sur, n_surplus, m, st.active_cell, initial_active);
+        if (delta == 2) overflow++; else n_surplus += delta;
+        const Time now = {0.0, 0.0};
+        const Time eoc = time_add(now, time_sub(now, now) + P.chain_time);
+        st.eoc_q = eoc.q; st.eoc_r = eoc.r;
+        const StreamKey key = {P.seed, st.stream, 0ull};
+        st.eoc_next_active = (int)stream_randbelow(key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.n_particles);
+        st.pending_kind = ECMC_EVENT_NONE; st.pending_target = 0; st.reserved = 0;
+        st.pending_q = 0.0; st.pending_r = 0.0; st.pending_rate = 0.0; st.pending_position = 0.0;
+        st.pending_stamp_q = 0.0; st.pending_stamp_r = 0.0;
+        S.chains[chain] = st;
+        S.n_surplus[chain] = n_surplus;
+        if (overflow && stats) atomicAdd(reinterpret_cast<unsigned long long *>(stats) + 8, (unsigned long long)overflow);
+    }
+}
+
+// host layout [n_chains][n_particles][dimension] (+ charges [n_chains][n_particles]) <-> 32-byte particle records
+__global__ void pack_particles_kernel(const double *positions, const double *charges, Particle *out, size_t n, int dimension) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        Particle p;
+        p.x = positions[i * dimension];
+        p.y = dimension > 1 ? positions[i * dimension + 1] : 0.0;
+        p.z = dimension > 2 ? positions[i * dimension + 2] : 0.0;
+        p.charge = charges ? charges[i] : 1.0;
+        out[i] = p;
+    }
+}
+__global__ void unpack_particles_kernel(const Particle *in, double *positions, size_t n, int dimension) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const Particle p = in[i];
+        positions[i * dimension] = p.x;
+        if (dimension > 1) positions[i * dimension + 1] = p.y;
+        if (dimension > 2) positions[i * dimension + 2] = p.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched potential arithmetic (ecmc_potential_derivative / ecmc_potential_displacement): one warp per element
+// for the merged-image Coulomb sum, one thread per element otherwise.
+// ---------------------------------------------------------------------------------------------------------
+struct BatchArgs {
+    int dimension, dir;
+    double speed, length;
+    double velocity[3];
+    size_t n;
+    const double *separations, *charges, *potential_changes;
+    double *out;
+};
+
+__global__ void __launch_bounds__(256)
+derivative_batch_kernel(const __grid_constant__ PotentialParams p, const BatchArgs b) {
+    __shared__ double trig_all[8 * kTrigDoubles];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *trig = trig_all + warp * kTrigDoubles;
+    if (p.kind == ECMC_POT_MERGED_IMAGE_COULOMB) {
+        for (size_t i = blockIdx.x * 8ull + warp; i < b.n; i += (size_t)gridDim.x * 8ull) {
+            const double *s = b.separations + i * b.dimension;
+            const double c1 = b.charges ? b.charges[2 * i] : 1.0, c2 = b.charges ? b.charges[2 * i + 1] : 1.0;
+            const double v = derivative_warp<-1>(p, b.dir, b.speed, s[0], s[1], b.dimension > 2 ? s[2] : 0.0, c1, c2, trig, lane);
+            if (lane == 0) b.out[i] = v;
+        }
+    } else {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < b.n; i += (size_t)gridDim.x * blockDim.x) {
+            const double *s = b.separations + i * b.dimension;
+            const double c1 = b.charges ? b.charges[2 * i] : 1.0, c2 = b.charges ? b.charges[2 * i + 1] : 1.0;
+            b.out[i] = derivative_warp<-1>(p, b.dir, b.speed, s[0], b.dimension > 1 ? s[1] : 0.0,
+                                           b.dimension > 2 ? s[2] : 0.0, c1, c2, trig, lane);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+displacement_batch_kernel(const __grid_constant__ PotentialParams p, const BatchArgs b) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < b.n; i += (size_t)gridDim.x * blockDim.x) {
+        const double *s = b.separations + i * b.dimension;
+        const double sx = s[0], sy = b.dimension > 1 ? s[1] : 0.0, sz = b.dimension > 2 ? s[2] : 0.0;
+        const double c1 = b.charges ? b.charges[2 * i] : 1.0, c2 = b.charges ? b.charges[2 * i + 1] : 1.0;
+        const double du = b.potential_changes ? b.potential_changes[i] : 0.0;
+        double out;
+        if (p.kind == ECMC_POT_HARD_SPHERE || p.kind == ECMC_POT_HARD_DIPOLE) {
+            // general velocity (hard_sphere_potential.py:65-99, hard_dipole_potential.py:75-114)
+            const double vx = b.velocity[0], vy = b.velocity[1], vz = b.velocity[2];
+            const double vv = dot3(vx, vy, vz, vx, vy, vz);
+            const double vs = dot3(vx, vy, vz, sx, sy, sz);
+            const double ss = dot3(sx, sy, sz, sx, sy, sz);
+            out = p.kind == ECMC_POT_HARD_SPHERE ? hard_sphere_time(p.p0, vv, vs, ss) : hard_dipole_time(p.p0, p.p1, vv, vs, ss);
+        } else {
+            out = displacement_time<-1>(p, b.dir, b.speed, b.length, sx, sy, sz, c1, c2, du);
+        }
+        b.out[i] = out;
+    }
+}
+
+}  // namespace ecmc

@@ -1,0 +1,87 @@
+// ecmc_program.cuh -- the device-side description of one ECMC configuration ("program") and of the state
+// of the chains in HBM. Plain data, passed to the kernels by value (__grid_constant__).
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   particles  [n_chains][n_particles]   32-byte records (x, y, z, charge): a gather of one target particle
+//                                        costs exactly one 32-byte DRAM sector and one vector load
+//   occupants  [n_chains][n_cells][max_occupants] int32, -1 = empty (SingleActiveCellOccupancy._occupied_cells)
+//   surplus    [n_chains][max_surplus] int32 + n_surplus[n_chains]   (SingleActiveCellOccupancy._surplus)
+//   chains     [n_chains] EcmcChainState (include/ecmc.h), read once / written once per launch
+// Tables shared by all chains (cell geometry, nearby offsets, Walker tables, Ewald term lists) are read-only.
+#pragma once
+
+#include "ecmc_math.cuh"
+
+namespace ecmc {
+
+struct __align__(32) Particle {
+    double x, y, z, charge;
+};
+
+// Walker alias-table entry (jellyfysh/event_handler/walker.py:69-103): cell_a with rate_a, else cell_b
+struct __align__(16) WalkerEntry {
+    int cell_a, cell_b;
+    double rate_a;
+};
+
+struct DeviceWalker {
+    const WalkerEntry *entries;
+    int n_entries;
+    int bits;  // n_entries.bit_length(), for CPython's _randbelow
+    double total_rate, mean_rate;
+};
+
+struct PotentialParams {
+    int kind;  // EcmcPotentialKind
+    LennardJones lj;
+    InversePower ip;
+    DisplacedEvenPower dep;
+    double p0, p1;  // hard sphere radius | hard dipole min, max | Coulomb bound prefactor
+    MergedImageCoulomb mic;
+};
+
+constexpr int kMaxFourierCutoff = 15;
+constexpr int kTrigDoubles = 3 * 2 * (kMaxFourierCutoff + 1);
+constexpr int kMaxNearby = 343;  // (2 * 3 + 1)^3
+
+struct DeviceProgram {
+    int dimension, n_particles, n_cells, n_nearby;
+    int per_side[3], cumulative[3];
+    int max_occupants, max_surplus;
+    int pair_handler, pair_use_charge;
+    int veto_enabled, veto_use_charge;
+    uint32_t seed;
+    int pad;
+    double length, half_length, beta, speed, chain_time, veto_target_charge;
+    double side_length[3];
+    // cand: the invertible potential the pair candidates are drawn from (the pair potential of a
+    // TwoLeafUnitEventHandler, the bounding potential of a TwoLeafUnitBoundingPotentialEventHandler);
+    // real: the potential a bounded pair event is confirmed against; veto: the cell-veto potential
+    PotentialParams cand_potential, real_potential, veto_potential;
+    // tables
+    const int *nearby;            // [n_nearby] relative cell identifiers packed x | y << 10 | z << 20 (cuboid_periodic_cells.py:74-100)
+    const double *cell_min_axis;  // [3][max_per_side] lower cell boundary per axis index (cuboid_cells.py:119-131)
+    const int *translate_axis;    // [3][max_per_side][max_per_side] (cuboid_periodic_cells.py:182-207)
+    int max_per_side, pad2;
+    DeviceWalker upper[3], lower[3];
+    const double *bounds;         // [n_cells][dimension][2]
+};
+
+struct DeviceState {
+    Particle *particles;
+    int *occupants;
+    int *surplus;
+    int *n_surplus;
+    EcmcChainState *chains;
+    int n_chains;
+};
+
+struct RunArgs {
+    double until_q, until_r;
+    long long max_events;   // <= 0: unlimited
+    EcmcEventRecord *records;
+    int records_per_chain;
+    EcmcStats *stats;
+};
+
+}  // namespace ecmc

@@ -280,74 +280,8 @@ def veto_tables(bounds, far_cells, dimension=3):
     return {"upper": upper, "lower": lower, "bounds": np.ascontiguousarray(bounds, dtype=np.float64)}
 
 
-class ProgramBuilder:
-    """Assembles an EcmcProgram and keeps every array it points to alive."""
-
-    def __init__(self, dimension, n_particles, system_length, beta, cells_per_side, neighbor_layers=1,
-                 max_occupants=1, max_surplus=64, chain_time=1.0, speed=1.0, initial_direction=0,
-                 initial_active=0, seed=0):
-        self.program = abi.EcmcProgram()
-        p = self.program
-        p.abi_version = abi.ECMC_ABI_VERSION
-        p.dimension = dimension
-        p.n_particles = n_particles
-        p.system_length = system_length
-        p.beta = beta
-        cps = list(cells_per_side) + [1] * (3 - len(cells_per_side))
-        for d in range(3):
-            p.cells_per_side[d] = cps[d] if d < dimension else 1
-        p.neighbor_layers = neighbor_layers
-        p.max_occupants = max_occupants
-        p.max_surplus = max_surplus
-        p.chain_time = chain_time
-        p.speed = speed
-        p.initial_direction = initial_direction
-        p.initial_active = initial_active
-        p.seed = seed
-        self._keep = []
-        self.tables = None
-
-    @property
-    def n_cells(self):
-        p = self.program
-        return int(np.prod([p.cells_per_side[d] for d in range(p.dimension)]))
-
-    def set_pair(self, handler, potential, bounding=None, use_charge=False):
-        p = self.program
-        p.pair_handler = handler
-        p.pair_potential = potential
-        if bounding is not None:
-            p.pair_bounding_potential = bounding
-        p.pair_use_charge = int(use_charge)
-        return self
-
-    def set_veto(self, potential, tables, use_charge=False, target_charge=1.0):
-        p = self.program
-        p.veto_enabled = 1
-        p.veto_potential = potential
-        p.veto_use_charge = int(use_charge)
-        p.veto_target_charge = target_charge
-        vt = abi.EcmcVetoTables()
-        for name, dst in (("upper", vt.upper), ("lower", vt.lower)):
-            for d in range(p.dimension):
-                t = tables[name][d]
-                a = np.ascontiguousarray(t["cell_a"], dtype=np.int32)
-                b = np.ascontiguousarray(t["cell_b"], dtype=np.int32)
-                r = np.ascontiguousarray(t["rate_a"], dtype=np.float64)
-                self._keep += [a, b, r]
-                dst[d].n_entries = len(a)
-                dst[d].cell_a = a.ctypes.data_as(C.POINTER(C.c_int32))
-                dst[d].cell_b = b.ctypes.data_as(C.POINTER(C.c_int32))
-                dst[d].rate_a = r.ctypes.data_as(C.POINTER(C.c_double))
-                dst[d].total_rate = t["total_rate"]
-                dst[d].mean_rate = t["mean_rate"]
-        bounds = np.ascontiguousarray(np.nan_to_num(tables["bounds"], nan=0.0), dtype=np.float64)
-        self._keep.append(bounds)
-        vt.bounds = bounds.ctypes.data_as(C.POINTER(C.c_double))
-        self._keep.append(vt)
-        p.veto_tables = C.pointer(vt)
-        self.tables = tables
-        return self
+# the program assembly is plain data and shared with the product package
+from jellyfysh_b200.program import ProgramBuilder  # noqa: E402,F401
 
 
 class OracleChain:

