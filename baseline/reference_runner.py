@@ -1,0 +1,105 @@
+"""Time the UNMODIFIED reference (JeLLyFysh, installed copy under baseline/_ref) on a bench workload.
+
+bench.py's `--impl reference` arm and its `cpu_baseline` leg call this: one OS process per host core, every
+process builds the reference's object graph from INI text with the reference's own factory
+(jellyfysh/run.py:161-200 does the same), runs `mediator.run()` -- the reference's stock single-process event loop --
+for a fixed wall-clock budget and counts the iterations whose winner is an interaction / cell / end-of-chain
+handler (SURVEY.md 8d "unit of work") by wrapping `Scheduler.get_succeeding_event`, exactly like the survey probe.
+Nothing of jellyfysh_b200 or of the oracle is on this path.
+
+Start configuration: the reference's RandomInputHandler asks `setting.random_position()` for every particle; the
+runner answers with the bench's jittered-lattice start so that both arms simulate the same system (uniform random
+positions at density 0.5 would overlap Lennard-Jones cores). That is the only patch.
+"""
+import configparser
+import contextlib
+import io
+import multiprocessing
+import os
+import random
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = os.path.join(HERE, "_ref")
+INTERACTION_HANDLERS = ("TwoLeafUnit", "CellVeto", "CellBoundary", "EndOfChain")
+
+
+def available():
+    return os.path.exists(os.path.join(REF_ROOT, "jellyfysh", "run.py"))
+
+
+class _Stop(Exception):
+    pass
+
+
+def _run_one(args):
+    ini_text, positions, seed, warmup_seconds, budget_seconds = args
+    sys.path.insert(0, REF_ROOT)
+    import warnings
+    warnings.filterwarnings("ignore")
+    from jellyfysh.base import factory
+    from jellyfysh.base.strings import to_camel_case
+    import jellyfysh.setting as setting
+    random.seed(seed)
+    config = configparser.ConfigParser()
+    config.read_string(ini_text)
+    t_init = time.perf_counter()
+    factory.build_from_config(config, to_camel_case(config.get("Run", "setting")), "jellyfysh.setting")
+    if positions is not None:
+        iterator = iter([list(map(float, p)) for p in positions])
+        setting.random_position = lambda: next(iterator)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mediator = factory.build_from_config(config, to_camel_case(config.get("Run", "mediator")), "jellyfysh.mediator")
+    init_seconds = time.perf_counter() - t_init
+    scheduler = mediator._scheduler
+    original = scheduler.get_succeeding_event
+    state = {"events": 0, "t0": None, "counted_from": None, "deadline": None}
+    started = time.perf_counter()
+
+    def get_succeeding_event():
+        winner = original()
+        now = time.perf_counter()
+        if state["t0"] is None and now - started >= warmup_seconds:
+            state["t0"] = now
+            state["deadline"] = now + budget_seconds
+            state["events"] = 0
+        if any(tag in type(winner).__name__ for tag in INTERACTION_HANDLERS):
+            state["events"] += 1
+        if state["deadline"] is not None and now >= state["deadline"]:
+            state["elapsed"] = now - state["t0"]
+            raise _Stop()
+        return winner
+
+    scheduler.get_succeeding_event = get_succeeding_event
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mediator.run()
+    except _Stop:
+        pass
+    return state["events"], state["elapsed"], init_seconds
+
+
+def run(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0):
+    """Run one chain per entry of positions_per_process in parallel processes.
+    Returns (events per second summed over processes, processes, events, mean init seconds)."""
+    jobs = [(ini_text, positions, 1000 + k, warmup_seconds, budget_seconds)
+            for k, positions in enumerate(positions_per_process)]
+    context = multiprocessing.get_context("spawn")
+    with context.Pool(len(jobs)) as pool:
+        results = pool.map(_run_one, jobs)
+    rate = sum(events / elapsed for events, elapsed, _ in results)
+    return rate, len(jobs), sum(r[0] for r in results), sum(r[2] for r in results) / len(results)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, os.path.join(HERE, "..", "tests", "golden"))
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import configs
+    from jellyfysh_b200 import workloads
+    n, cells = 1024, 12
+    length = float((n / 0.5) ** (1.0 / 3.0))
+    ini = configs.lennard_jones_ini(n, length, cells, chain_time=10.0)
+    procs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    positions = workloads.lattice_start(procs, n, cells, length)
+    print(run(ini, list(positions), 1.0, float(sys.argv[2]) if len(sys.argv) > 2 else 5.0))

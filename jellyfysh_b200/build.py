@@ -30,13 +30,14 @@ def is_stale() -> bool:
     return any(os.path.getmtime(path) > built for path in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if it is missing or older than its sources; returns its path."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, output: str = None, defines=()) -> str:
+    """Compile the library if it is missing or older than its sources; returns its path.
+    `output` / `defines` build a tuning variant next to the default library."""
+    if output is None and not force and not is_stale():
         return LIBRARY
     command = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
                "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-cudart", "shared",
-               "-o", LIBRARY] + SOURCES
+               "-o", output or LIBRARY] + ["-D" + d for d in defines] + SOURCES
     if verbose:
         command.insert(1, "-Xptxas=-v")
     result = subprocess.run(command, capture_output=True, text=True)
@@ -44,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(result.stdout + result.stderr)
     if result.returncode != 0:
         raise RuntimeError("nvcc failed building libecmc_b200.so")
-    return LIBRARY
+    return output or LIBRARY
 
 
 if __name__ == "__main__":

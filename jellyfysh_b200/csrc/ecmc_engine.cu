@@ -195,17 +195,25 @@ bool has_derivative(int kind) {
            kind == ECMC_POT_MERGED_IMAGE_COULOMB || kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING;
 }
 
-int upload_walker(EcmcHandle *h, const EcmcWalkerTable &in, DeviceWalker *out, int n_cells) {
+int upload_walker(EcmcHandle *h, const EcmcWalkerTable &in, DeviceWalker *out, const DeviceProgram &d, const double *bounds,
+                  int direction, int rate_index) {
     std::memset(out, 0, sizeof(*out));
     if (in.n_entries <= 0) return ECMC_OK;
     if (!in.cell_a || !in.cell_b || !in.rate_a) return fail(h, ECMC_ERR_INVALID, "Walker table with null arrays");
     std::vector<WalkerEntry> entries(in.n_entries);
+    auto pack = [&d](int cell) {
+        return ((cell / d.cumulative[0]) % d.per_side[0]) | (((cell / d.cumulative[1]) % d.per_side[1]) << 10) |
+               (((cell / d.cumulative[2]) % d.per_side[2]) << 20);
+    };
+    auto bound = [&](int cell) { return bounds[((size_t)cell * d.dimension + direction) * 2 + rate_index]; };
     for (int e = 0; e < in.n_entries; e++) {
-        if (in.cell_a[e] < 0 || in.cell_a[e] >= n_cells || in.cell_b[e] >= n_cells)
+        if (in.cell_a[e] < 0 || in.cell_a[e] >= d.n_cells || in.cell_b[e] >= d.n_cells)
             return fail(h, ECMC_ERR_INVALID, "Walker table entry refers to a cell outside the cell system");
-        entries[e].cell_a = in.cell_a[e];
-        entries[e].cell_b = in.cell_b[e];
         entries[e].rate_a = in.rate_a[e];
+        entries[e].cell_a = pack(in.cell_a[e]);
+        entries[e].bound_a = bound(in.cell_a[e]);
+        entries[e].cell_b = in.cell_b[e] >= 0 ? pack(in.cell_b[e]) : -1;
+        entries[e].bound_b = in.cell_b[e] >= 0 ? bound(in.cell_b[e]) : 0.0;
     }
     out->n_entries = in.n_entries;
     out->bits = bit_length((uint32_t)in.n_entries);
@@ -255,6 +263,8 @@ int build_device_program(EcmcHandle *h) {
     d.speed = p.speed;
     d.chain_time = p.chain_time;
     d.veto_target_charge = p.veto_target_charge;
+    d.inv_beta = 1.0 / p.beta;
+    d.inv_speed = 1.0 / p.speed;
 
     // potentials
     int rc;
@@ -300,6 +310,7 @@ int build_device_program(EcmcHandle *h) {
         const int mps = d.max_per_side;
         std::vector<double> cmin_all(3 * mps, 0.0);
         std::vector<int> translate(3 * mps * mps, 0);
+        d.translate_modular = 1;
         for (int k = 0; k < 3; k++) {
             std::vector<double> cmin, cmax;
             axis_geometry(d.per_side[k], d.side_length[k], cmin, cmax);
@@ -308,6 +319,7 @@ int build_device_program(EcmcHandle *h) {
                 for (int r = 0; r < d.per_side[k]; r++) {
                     const double x = host_py_mod((cmax[a] + cmin[a]) / 2.0 + cmin[r], p.system_length);
                     translate[(k * mps + a) * mps + r] = (int)(x / d.side_length[k]);
+                    if (translate[(k * mps + a) * mps + r] != (a + r) % d.per_side[k]) d.translate_modular = 0;
                 }
             }
         }
@@ -324,13 +336,11 @@ int build_device_program(EcmcHandle *h) {
             return fail(h, ECMC_ERR_INVALID, "veto_target_charge must not be 0");
         if ((rc = make_potential(h, p.veto_potential, p.system_length, &d.veto_potential))) return rc;
         for (int k = 0; k < p.dimension; k++) {
-            if ((rc = upload_walker(h, p.veto_tables->upper[k], &d.upper[k], d.n_cells))) return rc;
-            if ((rc = upload_walker(h, p.veto_tables->lower[k], &d.lower[k], d.n_cells))) return rc;
+            if ((rc = upload_walker(h, p.veto_tables->upper[k], &d.upper[k], d, p.veto_tables->bounds, k, 0))) return rc;
+            if ((rc = upload_walker(h, p.veto_tables->lower[k], &d.lower[k], d, p.veto_tables->bounds, k, 1))) return rc;
             if (d.upper[k].n_entries <= 0 && d.lower[k].n_entries <= 0)
                 return fail(h, ECMC_ERR_INVALID, "veto enabled but a direction has no Walker table");
         }
-        std::vector<double> bounds(p.veto_tables->bounds, p.veto_tables->bounds + (size_t)d.n_cells * p.dimension * 2);
-        if ((rc = device_upload(h, &d.bounds, bounds))) return rc;
     }
     return ECMC_OK;
 }

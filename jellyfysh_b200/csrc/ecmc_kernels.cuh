@@ -18,6 +18,10 @@
 namespace ecmc {
 
 constexpr unsigned kFull = 0xffffffffu;
+// resident warps (= chains) per SM the event kernel is compiled for: sets the register budget (65536 / 32 / warps)
+#ifndef ECMC_RESIDENT_WARPS
+#define ECMC_RESIDENT_WARPS 28
+#endif
 constexpr int kSeqNone = 0x7fffffff;
 
 template <int KIND>
@@ -34,25 +38,30 @@ ECMC_D void split_separation(int dir, double sx, double sy, double sz, double &s
 
 // InvertiblePotential.displacement(velocity, separation, charges, potential_change): a TIME
 // (jellyfysh/potential/potential.py:218-301, potential/abstracts.py:212-243)
+// `inv_speed` = 1 / speed; the hard potentials take the velocity itself.
 template <int KIND>
-ECMC_D double displacement_time(const PotentialParams &p, int dir, double speed, double length, double sx, double sy,
+ECMC_D double displacement_time(const PotentialParams &p, int dir, double inv_speed, double length, double sx, double sy,
                                 double sz, double c1, double c2, double du) {
     double sd, perp2;
     split_separation(dir, sx, sy, sz, sd, perp2);
     switch (resolve_kind<KIND>(p.kind)) {
-    case ECMC_POT_LENNARD_JONES: return lj_displacement(p.lj, sd, perp2, du) / speed;
+    case ECMC_POT_LENNARD_JONES: return lj_displacement(p.lj, sd, perp2, du) * inv_speed;
     case ECMC_POT_INVERSE_POWER: {
         double r2, p2;
         ip_squares(dir, sx, sy, sz, r2, p2);
-        return ip_displacement(p.ip, sd, p2, r2, c1, c2, du) / speed;
+        return ip_displacement(p.ip, sd, p2, r2, c1, c2, du) * inv_speed;
     }
-    case ECMC_POT_DISPLACED_EVEN_POWER: return dep_displacement(p.dep, sd, perp2, du) / speed;
-    case ECMC_POT_HARD_SPHERE:
+    case ECMC_POT_DISPLACED_EVEN_POWER: return dep_displacement(p.dep, sd, perp2, du) * inv_speed;
+    case ECMC_POT_HARD_SPHERE: {
+        const double speed = 1.0 / inv_speed;
         return hard_sphere_time(p.p0, __dmul_rn(speed, speed), __dmul_rn(speed, sd), dot3(sx, sy, sz, sx, sy, sz));
-    case ECMC_POT_HARD_DIPOLE:
+    }
+    case ECMC_POT_HARD_DIPOLE: {
+        const double speed = 1.0 / inv_speed;
         return hard_dipole_time(p.p0, p.p1, __dmul_rn(speed, speed), __dmul_rn(speed, sd), dot3(sx, sy, sz, sx, sy, sz));
+    }
     case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING:
-        return ipcb_displacement(p.p0 * c1 * c2, sd, perp2, du, length) / speed;
+        return ipcb_displacement(p.p0 * c1 * c2, sd, perp2, du, length) * inv_speed;
     default: return NAN;
     }
 }
@@ -131,8 +140,31 @@ ECMC_D int occupancy_remove(int *occ, int *sur, int n_surplus, int m, int cell, 
     return 2;
 }
 
+// Order-preserving 64-bit key of a candidate time. All candidates of one event are `now + dt` with the same
+// `now`, and Time.__add__ splits x = now.remainder + dt exactly into floor(x) and x - floor(x) (base/time.py:129-133),
+// so the lexicographic comparison of (quotient, remainder) (heap.c:176-178) is the comparison of the doubles x,
+// and for x >= 0 that is the comparison of their bit patterns as unsigned integers.
+ECMC_D unsigned long long time_key(double x) {
+    return x >= 0.0 ? (unsigned long long)__double_as_longlong(x) : (x < 0.0 ? 0ull : 0x7ff0000000000000ull);
+}
+// argmin over the warp of (key, sequence): the lane that owns the minimum, by two 32-bit REDUX.MIN steps on the key
+// and one on the sequence number (ties in time are broken like the oracle's scan: lowest sequence first)
+ECMC_D int warp_argmin(unsigned long long key, int seq, int lane) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned min_hi = __reduce_min_sync(kFull, hi);
+    const unsigned min_lo = __reduce_min_sync(kFull, hi == min_hi ? lo : 0xffffffffu);
+    const bool tied = hi == min_hi && lo == min_lo;
+    const int min_seq = __reduce_min_sync(kFull, tied ? seq : kSeqNone);
+    return __ffs(__ballot_sync(kFull, tied && seq == min_seq)) - 1;
+}
+
+struct Counters {
+    unsigned events, pair, veto, veto_accepted, boundary, end_of_chain, violations, capacity;
+    unsigned long long candidates;
+};
+
 template <int CAND, int REAL, int VETO, bool RECORD, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     __shared__ double trig_all[UsesMic<REAL, VETO>::value ? WARPS * kTrigDoubles : 1];
     const int lane = threadIdx.x & 31;
@@ -155,10 +187,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     int active_cell = stp->active_cell;
     unsigned long long ev = stp->event_counter;
     const uint32_t stream = stp->stream;
-    int pending_kind = stp->pending_kind, pending_target = stp->pending_target;
-    Time pending_t = {stp->pending_q, stp->pending_r};
-    double pending_rate = stp->pending_rate, pending_position = stp->pending_position;
-    Time pending_stamp = {stp->pending_stamp_q, stp->pending_stamp_r};
+    bool was_pending = stp->pending_kind != ECMC_EVENT_NONE;  // only the first iteration can start from a kept candidate
     int n_surplus = S.n_surplus[chain];
     Particle a = part[active];
     int cid[3];
@@ -168,35 +197,46 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
 
     const Time until = {A.until_q, A.until_r};
     const double L = P.length, half = P.half_length, speed = P.speed;
+    const bool has_pairs = P.pair_handler != ECMC_PAIR_NONE;
     const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
+    const bool has_veto = VETO != 0 && P.veto_enabled;
+    const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
 
-    unsigned long long n_events = 0, n_pair = 0, n_veto = 0, n_veto_acc = 0, n_boundary = 0, n_eoc = 0, n_candidates = 0,
-                       n_violations = 0, n_capacity = 0;
+    Counters n = {0, 0, 0, 0, 0, 0, 0, 0, 0ull};
     bool stopped_by_time = false;
 
-    while (A.max_events <= 0 || (long long)n_events < A.max_events) {
+    while (n.events < max_events) {
         const StreamKey key = {P.seed, stream, ev};
         // the interaction winner: (time, kind, target particle, target cell, bounding rate)
         Time bt = time_inf();
         int bkind = ECMC_EVENT_NONE, btarget = -1, bcell = -1;
         double brate = 0.0;
         int n_cand = 0;
-        const bool was_pending = pending_kind != ECMC_EVENT_NONE;
+        double kept_position = 0.0;
+        Time kept_stamp = now;
         if (was_pending) {
             // a candidate that survived a host control event: nothing is recomputed, no draws are consumed
-            bkind = pending_kind;
-            bt = pending_t;
-            brate = pending_rate;
-            if (bkind == ECMC_EVENT_PAIR) btarget = pending_target; else bcell = pending_target;
+            bkind = stp->pending_kind;
+            bt.q = stp->pending_q; bt.r = stp->pending_r;
+            brate = stp->pending_rate;
+            if (bkind == ECMC_EVENT_PAIR) btarget = stp->pending_target; else bcell = stp->pending_target;
+            kept_position = stp->pending_position;
+            kept_stamp.q = stp->pending_stamp_q; kept_stamp.r = stp->pending_stamp_r;
         } else {
-            int wseq = kSeqNone;  // per-lane best
-            const int nearby_slots = P.pair_handler != ECMC_PAIR_NONE ? P.n_nearby * m : 0;
-            const int n_slots = P.pair_handler != ECMC_PAIR_NONE ? nearby_slots + n_surplus : 0;
+            // Slot layout of one event: slot 0 = cell veto, slot 1 = cell boundary, slots 2.. = pair candidates (nearby
+            // cells x occupant slots, then the surplus list). Lanes take slots in passes of 32; pass 0 does the two
+            // special candidates next to 30 pair slots, which covers a 3^3 neighbourhood plus 3 surplus particles.
+            // The sequence number that breaks ties follows the oracle's scan: pairs, veto, boundary.
+            const int nearby_slots = has_pairs ? P.n_nearby * m : 0;
+            const int n_pair_slots = has_pairs ? nearby_slots + n_surplus : 0;
             const double c_active = P.pair_use_charge ? a.charge : 1.0;
-            for (int base = 0; base < n_slots; base += 32) {
-                const int s = base + lane;
+            unsigned long long wkey = 0x7ff0000000000000ull;  // per-lane best
+            double wx = INFINITY;
+            int wseq = kSeqNone;
+            for (int base = 0; base < n_pair_slots + 2; base += 32) {
+                const int s = base + lane - 2;  // pair slot index; -2 = veto, -1 = boundary
                 int target = -1;
-                if (s < nearby_slots) {
+                if (s >= 0 && s < nearby_slots) {
                     const int ci = m == 1 ? s : s / m;
                     const int code = __ldg(P.nearby + ci);
                     int x = cid[0] + (code & 1023), y = cid[1] + ((code >> 10) & 1023), z = cid[2] + (code >> 20);
@@ -205,103 +245,118 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     if (z >= P.per_side[2]) z -= P.per_side[2];
                     const int cell = x * P.cumulative[0] + y * P.cumulative[1] + z * P.cumulative[2];
                     target = occ[cell * m + (s - ci * m)];
-                } else if (s < n_slots) {
+                } else if (s >= nearby_slots && s < n_pair_slots) {
                     target = sur[s - nearby_slots];
                 }
-                Time t = time_inf();
-                if (target >= 0) {
-                    const Particle tp = part[target];
-                    const double sx = correct_separation_entry(tp.x - a.x, L, half);
-                    const double sy = correct_separation_entry(tp.y - a.y, L, half);
-                    const double sz = correct_separation_entry(tp.z - a.z, L, half);
-                    double du = 0.0;
-                    if (cand_needs_du)
-                        du = expovariate(stream_double(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target), 0), P.beta);
-                    const double dt = displacement_time<CAND>(P.cand_potential, dir, speed, L, sx, sy, sz, c_active,
-                                                              P.pair_use_charge ? tp.charge : 1.0, du);
-                    t = time_add(now, dt);
-                }
-                const bool finite = target >= 0 && isfinite(t.q);  // heap_scheduler.py:139: only finite times
-                n_cand += __popc(__ballot_sync(kFull, finite));
-                if (finite && time_lt(t, bt)) {
-                    bt = t; wseq = s; bkind = ECMC_EVENT_PAIR; btarget = target;
-                }
-            }
-            // cell veto (lane 0) and cell boundary (lane 1)
-            bool veto_finite = false;
-            if (lane == 0 && P.veto_enabled) {
-                double charge_factor = 1.0;
-                if (P.veto_use_charge) charge_factor = a.charge * 1.0 / P.veto_target_charge;
-                int rate_index = 0;
-                const DeviceWalker *w = &P.upper[dir];
-                if (!(charge_factor > 0.0)) { charge_factor *= -1.0; w = &P.lower[dir]; rate_index = 1; }
-                const double total_rate = w->total_rate * charge_factor;
-                // random.choice(table): _randbelow(n) by rejection on the top bits of successive words
-                uint32_t e = 0;
-                for (uint32_t index = 0;; index += 4) {
-                    const Philox4 b = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0), index >> 2);
+                const bool is_pair = target >= 0;
+                const bool is_veto = s == -2 && has_veto;
+                const bool is_boundary = s == -1;
+                Particle tp;
+                if (is_pair) tp = part[target];
+                // One Philox block per lane, all lanes together: pair lanes draw their potential change (slot keyed
+                // by the target), the veto lane its (Walker uniform, time) pair, and the boundary lane -- which needs
+                // no random number -- computes the veto lane's table-index words.
+                const uint32_t slot = is_pair ? ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target)
+                                              : (is_boundary ? ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0) : ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0));
+                Philox4 b = stream_block(key, slot, 0);
+                const double u_first = words_to_double(b.w[0], b.w[1]), u_second = words_to_double(b.w[2], b.w[3]);
+                // random.expovariate(beta): pair lanes use their first double, the veto lane its second
+                const double exponential = -log(1.0 - (is_veto ? u_second : u_first)) * P.inv_beta;
+                // the table-index words travel from the boundary lane (lane 1 of pass 0) to the veto lane (lane 0)
+                uint32_t choice[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) choice[j] = __shfl_down_sync(kFull, b.w[j], 1);
+                double dt = INFINITY;
+                int kind = ECMC_EVENT_NONE, cell = -1, seq = kSeqNone;
+                double rate = 0.0;
+                if (is_pair) {
+                    const double sx = correct_separation_in_box(tp.x - a.x, L, half);
+                    const double sy = correct_separation_in_box(tp.y - a.y, L, half);
+                    const double sz = correct_separation_in_box(tp.z - a.z, L, half);
+                    dt = displacement_time<CAND>(P.cand_potential, dir, P.inv_speed, L, sx, sy, sz, c_active,
+                                                 P.pair_use_charge ? tp.charge : 1.0, cand_needs_du ? exponential : 0.0);
+                    kind = ECMC_EVENT_PAIR;
+                    seq = s;
+                } else if (is_veto) {
+                    // CellVetoEventHandler.send_event_time (cell_veto_event_handler.py:200-238)
+                    double charge_factor = 1.0;
+                    if (P.veto_use_charge) charge_factor = a.charge * 1.0 / P.veto_target_charge;
+                    const DeviceWalker *w = &P.upper[dir];
+                    if (!(charge_factor > 0.0)) { charge_factor *= -1.0; w = &P.lower[dir]; }
+                    const double total_rate = w->total_rate * charge_factor;
+                    // random.choice(table) = table[_randbelow(n)]: rejection on the top bits of successive words
+                    uint32_t e = 0;
                     bool found = false;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint32_t r = b.w[j] >> (32 - w->bits);
+                        const uint32_t r = choice[j] >> (32 - w->bits);
                         if (!found && r < (uint32_t)w->n_entries) { e = r; found = true; }
                     }
-                    if (found) break;
-                }
-                const Philox4 b = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0), 0);
-                const double u0 = words_to_double(b.w[0], b.w[1]), u1 = words_to_double(b.w[2], b.w[3]);
-                const WalkerEntry entry = w->entries[e];
-                const int relative_cell = (0.0 + (w->mean_rate - 0.0) * u0 <= entry.rate_a) ? entry.cell_a : entry.cell_b;
-                const double rate = __ldg(P.bounds + (relative_cell * P.dimension + dir) * 2 + rate_index) * charge_factor;
-                // translate(active cell, relative cell), per axis (cuboid_periodic_cells.py:182-207)
-                const int mps = P.max_per_side;
-                const int rx = (relative_cell / P.cumulative[0]) % P.per_side[0];
-                const int ry = (relative_cell / P.cumulative[1]) % P.per_side[1];
-                const int rz = (relative_cell / P.cumulative[2]) % P.per_side[2];
-                const int tx = __ldg(P.translate_axis + (0 * mps + cid[0]) * mps + rx);
-                const int ty = __ldg(P.translate_axis + (1 * mps + cid[1]) * mps + ry);
-                const int tz = __ldg(P.translate_axis + (2 * mps + cid[2]) * mps + rz);
-                const double dt = expovariate(u1, P.beta) / (total_rate * speed);
-                const Time t = time_add(now, dt);
-                veto_finite = isfinite(t.q);
-                if (veto_finite && time_lt(t, bt)) {
-                    bt = t; wseq = n_slots; bkind = ECMC_EVENT_CELL_VETO; btarget = -1;
-                    bcell = tx * P.cumulative[0] + ty * P.cumulative[1] + tz * P.cumulative[2];
-                    brate = rate;
-                }
-            }
-            if (lane == 1) {
-                // neighbor cell in the positive direction and its lower boundary
-                int nid = cid[dir] + 1;
-                if (nid >= P.per_side[dir]) nid = 0;
-                const double neighbor_boundary = __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
-                double separation = neighbor_boundary - component(a, dir);
-                if (separation < 0.0) separation = separation + L;  // next_image, hypercubic_setting.py:191
-                const Time t = time_add(now, separation / speed);
-                if (time_lt(t, bt)) {
-                    bt = t; wseq = n_slots + 1; bkind = ECMC_EVENT_CELL_BOUNDARY; btarget = -1;
-                    bcell = active_cell + (nid - cid[dir]) * P.cumulative[dir];
-                }
-            }
-            n_cand += __popc(__ballot_sync(kFull, veto_finite)) + 1;
-            // argmin over the warp: lexicographic (quotient, remainder, sequence)
-            double rq = bt.q, rr = bt.r;
-            int rseq = wseq;
+                    for (uint32_t block = 1; !found; block++) {
+                        const Philox4 more = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0), block);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double oq = __shfl_xor_sync(kFull, rq, o), orr = __shfl_xor_sync(kFull, rr, o);
-                const int os = __shfl_xor_sync(kFull, rseq, o);
-                const bool take = oq < rq || (oq == rq && (orr < rr || (orr == rr && os < rseq)));
-                if (take) { rq = oq; rr = orr; rseq = os; }
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t r = more.w[j] >> (32 - w->bits);
+                            if (!found && r < (uint32_t)w->n_entries) { e = r; found = true; }
+                        }
+                    }
+                    const WalkerEntry entry = w->entries[e];
+                    // Walker.sample_cell (walker.py:114-118): random.uniform(0.0, mean) <= rate
+                    const bool first = 0.0 + (w->mean_rate - 0.0) * u_first <= entry.rate_a;
+                    const int relative = first ? entry.cell_a : entry.cell_b;
+                    rate = (first ? entry.bound_a : entry.bound_b) * charge_factor;
+                    // translate(active cell, relative cell), per axis (cuboid_periodic_cells.py:182-207)
+                    int tx, ty, tz;
+                    const int rx = relative & 1023, ry = (relative >> 10) & 1023, rz = relative >> 20;
+                    if (P.translate_modular) {
+                        tx = cid[0] + rx; ty = cid[1] + ry; tz = cid[2] + rz;
+                        if (tx >= P.per_side[0]) tx -= P.per_side[0];
+                        if (ty >= P.per_side[1]) ty -= P.per_side[1];
+                        if (tz >= P.per_side[2]) tz -= P.per_side[2];
+                    } else {
+                        const int mps = P.max_per_side;
+                        tx = __ldg(P.translate_axis + (0 * mps + cid[0]) * mps + rx);
+                        ty = __ldg(P.translate_axis + (1 * mps + cid[1]) * mps + ry);
+                        tz = __ldg(P.translate_axis + (2 * mps + cid[2]) * mps + rz);
+                    }
+                    cell = tx * P.cumulative[0] + ty * P.cumulative[1] + tz * P.cumulative[2];
+                    dt = exponential / (total_rate * speed);
+                    kind = ECMC_EVENT_CELL_VETO;
+                    seq = n_pair_slots;
+                } else if (is_boundary) {
+                    // CellBoundaryEventHandler.send_event_time (cell_boundary_event_handler.py:122-156): the lower
+                    // boundary of the neighbour cell in the direction of motion
+                    int nid = cid[dir] + 1;
+                    if (nid >= P.per_side[dir]) nid = 0;
+                    const double neighbor_boundary = __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
+                    double separation = neighbor_boundary - component(a, dir);
+                    if (separation < 0.0) separation = separation + L;  // next_image, hypercubic_setting.py:191
+                    dt = separation * P.inv_speed;
+                    cell = active_cell + (nid - cid[dir]) * P.cumulative[dir];
+                    kind = ECMC_EVENT_CELL_BOUNDARY;
+                    seq = n_pair_slots + 1;
+                }
+                // Time.__add__: event time = now + dt; x orders the candidates (see time_key)
+                const double x = now.r + dt;
+                const bool finite = kind != ECMC_EVENT_NONE && isfinite(x);  // heap_scheduler.py:139: only finite times
+                n_cand += __popc(__ballot_sync(kFull, finite));
+                const unsigned long long k64 = finite ? time_key(x) : 0x7ff0000000000000ull;
+                if (k64 < wkey) {
+                    wkey = k64; wx = x; wseq = seq; bkind = kind; btarget = target; bcell = cell; brate = rate;
+                }
             }
-            const unsigned owners = __ballot_sync(kFull, wseq == rseq && rseq != kSeqNone);
-            const int owner = owners ? __ffs(owners) - 1 : 0;
-            bt.q = rq; bt.r = rr;
-            bkind = __shfl_sync(kFull, bkind, owner);
-            btarget = __shfl_sync(kFull, btarget, owner);
-            bcell = __shfl_sync(kFull, bcell, owner);
-            brate = __shfl_sync(kFull, brate, owner);
-            if (!owners) bkind = ECMC_EVENT_NONE;
+            const int owner = warp_argmin(wkey, wseq, lane);
+            if (owner >= 0) {
+                const double x = __shfl_sync(kFull, wx, owner);
+                const double fl = floor(x);
+                bt.q = now.q + fl; bt.r = x - fl;
+                bkind = __shfl_sync(kFull, bkind, owner);
+                btarget = __shfl_sync(kFull, btarget, owner);
+                bcell = __shfl_sync(kFull, bcell, owner);
+                brate = __shfl_sync(kFull, brate, owner);
+            } else {
+                bkind = ECMC_EVENT_NONE;
+            }
         }
 
         // the end-of-chain candidate lives in the scheduler since the chain started
@@ -311,22 +366,27 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         const int kind = eoc_first ? ECMC_EVENT_END_OF_CHAIN : bkind;
         if (!time_lt(event_time, until)) {
             // a host control event comes first: the interaction winner stays scheduled
-            pending_kind = bkind;
-            pending_t = bt;
-            pending_rate = brate;
-            pending_target = bkind == ECMC_EVENT_PAIR ? btarget : bcell;
-            if (!was_pending) {
-                pending_position = component(a, dir);
-                pending_stamp = now;
+            if (lane == 0) {
+                stp->pending_kind = bkind;
+                stp->pending_q = bt.q; stp->pending_r = bt.r;
+                stp->pending_rate = brate;
+                stp->pending_target = bkind == ECMC_EVENT_PAIR ? btarget : bcell;
+                if (!was_pending) {
+                    stp->pending_position = component(a, dir);
+                    stp->pending_stamp_q = now.q; stp->pending_stamp_r = now.r;
+                }
             }
             stopped_by_time = true;
             break;
         }
-        pending_kind = ECMC_EVENT_NONE;
-        if (was_pending && kind != ECMC_EVENT_END_OF_CHAIN) {
-            // the kept handler's in-state predates the control event's time slice
-            set_component(a, dir, pending_position);
-            now = pending_stamp;
+        if (was_pending) {
+            if (lane == 0) stp->pending_kind = ECMC_EVENT_NONE;
+            if (kind != ECMC_EVENT_END_OF_CHAIN) {
+                // the kept handler's in-state predates the control event's time slice
+                set_component(a, dir, kept_position);
+                now = kept_stamp;
+            }
+            was_pending = false;
         }
 
         // ---- out-state: time slice of the active particle (event_handler/abstracts/abstracts.py:82-95)
@@ -345,20 +405,20 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 // two_leaf_unit_bounding_potential_event_handler.py:148-168 +
                 // event_handler_with_bounding_potential.py:75-101
                 const Particle tp = part[btarget];
-                const double sx = correct_separation_entry(tp.x - a.x, L, half);
-                const double sy = correct_separation_entry(tp.y - a.y, L, half);
-                const double sz = correct_separation_entry(tp.z - a.z, L, half);
+                const double sx = correct_separation_in_box(tp.x - a.x, L, half);
+                const double sy = correct_separation_in_box(tp.y - a.y, L, half);
+                const double sz = correct_separation_in_box(tp.z - a.z, L, half);
                 const double c1 = P.pair_use_charge ? a.charge : 1.0, c2 = P.pair_use_charge ? tp.charge : 1.0;
                 const double bounding_rate = derivative_warp<CAND>(P.cand_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
                 const double real = derivative_warp<REAL>(P.real_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
-                    if (bounding_rate < real) n_violations++;
+                    if (bounding_rate < real) n.violations++;
                     const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
                     if (0.0 + (bounding_rate - 0.0) * u < real) accepted = 1;
                 }
             }
             if (accepted) new_active = btarget;
-            n_pair++;
+            n.pair++;
             break;
         }
         case ECMC_EVENT_CELL_VETO: {
@@ -367,26 +427,28 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             rec_target = t;
             if (t >= 0) {
                 const Particle tp = part[t];
-                const double sx = correct_separation_entry(tp.x - a.x, L, half);
-                const double sy = correct_separation_entry(tp.y - a.y, L, half);
-                const double sz = correct_separation_entry(tp.z - a.z, L, half);
+                const double sx = correct_separation_in_box(tp.x - a.x, L, half);
+                const double sy = correct_separation_in_box(tp.y - a.y, L, half);
+                const double sz = correct_separation_in_box(tp.z - a.z, L, half);
                 const double c1 = P.veto_use_charge ? a.charge : 1.0, c2 = P.veto_use_charge ? tp.charge : 1.0;
                 const double real = derivative_warp<VETO>(P.veto_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
-                    if (brate < real) n_violations++;
+                    if (brate < real) n.violations++;
                     const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
                     if (0.0 + (brate - 0.0) * u < real) { accepted = 1; new_active = t; }
                 }
             }
-            n_veto++;
-            n_veto_acc += accepted;
+            n.veto++;
+            n.veto_accepted += accepted;
             break;
         }
         case ECMC_EVENT_CELL_BOUNDARY: {
             // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
-            const int nid = (bcell / P.cumulative[dir]) % P.per_side[dir];
+            int nid = cid[dir] + 1;
+            if (nid >= P.per_side[dir]) nid = 0;
+            if (bcell != active_cell + (nid - cid[dir]) * P.cumulative[dir]) nid = (bcell / P.cumulative[dir]) % P.per_side[dir];
             set_component(a, dir, __ldg(P.cell_min_axis + dir * P.max_per_side + nid));
-            n_boundary++;
+            n.boundary++;
             break;
         }
         case ECMC_EVENT_END_OF_CHAIN:
@@ -394,11 +456,11 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             new_active = eoc_next;
             rec_target = new_active;
             accepted = 1;
-            n_eoc++;
+            n.end_of_chain++;
             break;
         default: break;
         }
-        if (RECORD && lane == 0 && (long long)n_events < A.records_per_chain) {
+        if (RECORD && lane == 0 && (int)n.events < A.records_per_chain) {
             EcmcEventRecord rec;
             rec.kind = kind; rec.target = rec_target; rec.target_cell = kind == ECMC_EVENT_END_OF_CHAIN ? -1 : bcell;
             rec.accepted = accepted; rec.n_candidates = n_cand;
@@ -407,12 +469,12 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             rec.reserved = 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
             rec.active_pos[0] = a.x; rec.active_pos[1] = a.y; rec.active_pos[2] = a.z;
-            A.records[(size_t)chain * A.records_per_chain + n_events] = rec;
+            A.records[(size_t)chain * A.records_per_chain + n.events] = rec;
         }
         ev++;
-        n_events++;
-        n_candidates += (unsigned long long)n_cand;
-        if (kind == ECMC_EVENT_END_OF_CHAIN) dir = (dir + 1) % P.dimension;
+        n.events++;
+        n.candidates += (unsigned long long)n_cand;
+        if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir + 1 == P.dimension ? 0 : dir + 1;
 
         // ---- SingleActiveCellOccupancy.update (single_active_cell_occupancy.py:149-203)
         if (new_active != active) {
@@ -422,7 +484,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 delta = occupancy_insert(occ, sur, n_surplus, m, P.max_surplus, active_cell, active);
             }
             delta = __shfl_sync(kFull, delta, 0);
-            if (delta == 2) n_capacity++; else n_surplus += delta;
+            if (delta == 2) n.capacity++; else n_surplus += delta;
             __syncwarp();
             active = new_active;
             a = part[active];
@@ -431,11 +493,20 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             delta = 0;
             if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, m, active_cell, active);
             delta = __shfl_sync(kFull, delta, 0);
-            if (delta == 2) n_capacity++; else n_surplus += delta;
+            if (delta == 2) n.capacity++; else n_surplus += delta;
             __syncwarp();
         } else {
-            cell_identifier_of(P, a, cid);
-            active_cell = flat_cell(P, cid);
+            // The oracle recomputes the cell from the position after every event. Cell `id` holds exactly the doubles
+            // in [cell_min[id], cell_min[id + 1]) (see axis_geometry), and only the coordinate along the direction of
+            // motion moved, so two comparisons tell whether the three divisions are needed at all.
+            const double *cell_min = P.cell_min_axis + dir * P.max_per_side;
+            const int id = cid[dir];
+            const double x = component(a, dir);
+            const bool same = x >= __ldg(cell_min + id) && (id + 1 == P.per_side[dir] ? x < L : x < __ldg(cell_min + id + 1));
+            if (!same) {
+                cell_identifier_of(P, a, cid);
+                active_cell = flat_cell(P, cid);
+            }
         }
         if (kind == ECMC_EVENT_END_OF_CHAIN) {
             // the next end-of-chain candidate: chain_time after this one, new active by randint
@@ -459,22 +530,18 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         stp->eoc_q = eoc.q; stp->eoc_r = eoc.r;
         stp->eoc_next_active = eoc_next; stp->active_cell = active_cell;
         stp->event_counter = ev;
-        stp->pending_kind = pending_kind; stp->pending_target = pending_target;
-        stp->pending_q = pending_t.q; stp->pending_r = pending_t.r;
-        stp->pending_rate = pending_rate; stp->pending_position = pending_position;
-        stp->pending_stamp_q = pending_stamp.q; stp->pending_stamp_r = pending_stamp.r;
         S.n_surplus[chain] = n_surplus;
         if (A.stats) {
             unsigned long long *st = reinterpret_cast<unsigned long long *>(A.stats);
-            if (n_events) atomicAdd(st + 0, n_events);
-            if (n_pair) atomicAdd(st + 1, n_pair);
-            if (n_veto) atomicAdd(st + 2, n_veto);
-            if (n_veto_acc) atomicAdd(st + 3, n_veto_acc);
-            if (n_boundary) atomicAdd(st + 4, n_boundary);
-            if (n_eoc) atomicAdd(st + 5, n_eoc);
-            if (n_candidates) atomicAdd(st + 6, n_candidates);
-            if (n_violations) atomicAdd(st + 7, n_violations);
-            if (n_capacity) atomicAdd(st + 8, n_capacity);
+            if (n.events) atomicAdd(st + 0, (unsigned long long)n.events);
+            if (n.pair) atomicAdd(st + 1, (unsigned long long)n.pair);
+            if (n.veto) atomicAdd(st + 2, (unsigned long long)n.veto);
+            if (n.veto_accepted) atomicAdd(st + 3, (unsigned long long)n.veto_accepted);
+            if (n.boundary) atomicAdd(st + 4, (unsigned long long)n.boundary);
+            if (n.end_of_chain) atomicAdd(st + 5, (unsigned long long)n.end_of_chain);
+            if (n.candidates) atomicAdd(st + 6, n.candidates);
+            if (n.violations) atomicAdd(st + 7, (unsigned long long)n.violations);
+            if (n.capacity) atomicAdd(st + 8, (unsigned long long)n.capacity);
         }
     }
 }
@@ -635,7 +702,7 @@ displacement_batch_kernel(const __grid_constant__ PotentialParams p, const Batch
             const double ss = dot3(sx, sy, sz, sx, sy, sz);
             out = p.kind == ECMC_POT_HARD_SPHERE ? hard_sphere_time(p.p0, vv, vs, ss) : hard_dipole_time(p.p0, p.p1, vv, vs, ss);
         } else {
-            out = displacement_time<-1>(p, b.dir, b.speed, b.length, sx, sy, sz, c1, c2, du);
+            out = displacement_time<-1>(p, b.dir, 1.0 / b.speed, b.length, sx, sy, sz, c1, c2, du);
         }
         b.out[i] = out;
     }

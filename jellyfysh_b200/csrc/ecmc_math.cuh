@@ -143,6 +143,12 @@ ECMC_HD double py_mod(double x, double L) {
     return m;
 }
 ECMC_HD double correct_separation_entry(double s, double L, double half) { return py_mod(s + half, L) - half; }
+// the same for two positions inside the box, |s| < L: s + L/2 lies in (-L/2, 3L/2) and the modulo is one select
+ECMC_HD double correct_separation_in_box(double s, double L, double half) {
+    const double x = s + half;
+    const double m = x < 0.0 ? x + L : (x >= L ? x - L : x);
+    return m - half;
+}
 ECMC_HD double correct_position_entry(double x, double L) { return py_mod(x, L); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -196,31 +202,34 @@ ECMC_D double lj_derivative(const LennardJones &p, double sd, double perp2) {
 //   (1) inside the sphere while approaching (sd from min(sd, h) down to 0), if the line hits the sphere;
 //   (2) outside the sphere while receding (sd from -h, or from min(sd, 0) if the sphere is missed, to -inf).
 // h = sqrt(r0^2 - perp2) is the half chord. Energies at sphere points are the exact minimum -k/4.
+// Written without divergent branches -- the lanes of a warp hold different targets, so every branch any lane takes
+// costs the whole warp: both energies come from ONE division, the case analysis is a chain of selects, and every
+// lane runs the same sqrt -> rcbrt -> sqrt sequence once.
 ECMC_D double lj_displacement(const LennardJones &p, double sd, double perp2, double du) {
     const double r2 = fma(sd, sd, perp2);
+    const double pc = fmax(perp2, 1.0e-150);     // head-on approach: the barrier is infinite
+    const double inv = 1.0 / (r2 * pc);
+    const double xr = p.sigma2 * (inv * pc), xp = p.sigma2 * (inv * r2);
+    const double xr3 = xr * xr * xr, xp3 = xp * xp * xp;
+    const double e_r = p.k * xr3 * (xr3 - 1.0);  // U at the current separation
+    const double e_p = p.k * xp3 * (xp3 - 1.0);  // U at the closest approach of the straight line
+    const bool approaching = sd > 0.0;
     const bool hits = perp2 < p.r0sq;            // the line of motion crosses the minimum sphere
     const bool inside = r2 < p.r0sq;
-    double u_start;                              // energy at the start of stretch (2)
-    if (sd > 0.0 && hits) {
-        // stretch (1): from the entry point (or the current point if already inside) up to sd = 0
-        const double u1 = inside ? lj_energy(p, r2) : p.u_min;
-        const double u_max = lj_energy(p, perp2);
-        const double barrier = u_max - u1;
-        if (du < barrier) {
-            const double rn2 = lj_radius_sq(p, u1 + du, true);
-            return sd - sqrt(rn2 - perp2);
-        }
-        du -= barrier;
-        u_start = p.u_min;                       // leaves through the sphere at sd = -h
-    } else if (sd > 0.0) {
-        u_start = lj_energy(p, perp2);           // misses the sphere: downhill to the closest approach
-    } else {
-        u_start = inside ? p.u_min : lj_energy(p, r2);
-    }
-    const double u_end = u_start + du;
-    if (u_end >= 0.0) return INFINITY;           // escapes the attractive tail
-    const double rn2 = lj_radius_sq(p, u_end, false);
-    return sd + sqrt(rn2 - perp2);
+    const bool climbs = approaching && hits;     // stretch (1) exists
+    const double u1 = inside ? e_r : p.u_min;    // energy where stretch (1) starts
+    const double barrier = e_p - u1;
+    const bool inner = climbs && du < barrier;   // the event happens on stretch (1)
+    // energy at which the event happens: on stretch (1), or on stretch (2) started at the sphere / the closest
+    // approach / the current point
+    const double u_start = climbs ? p.u_min : (approaching ? e_p : (inside ? p.u_min : e_r));
+    const double u_event = inner ? u1 + du : u_start + (climbs ? du - barrier : du);
+    const double root = sqrt(fmax(fma(u_event, p.four_over_k, 1.0), 0.0));
+    const double x3 = 0.5 * (inner ? 1.0 + root : 1.0 - root);
+    const double rn2 = p.sigma2 * rcbrt(x3);
+    const double s = sqrt(rn2 - perp2);
+    if (!inner && u_event >= 0.0) return INFINITY;  // escapes the attractive tail
+    return inner ? sd - s : sd + s;
 }
 
 // ---- hard sphere / hard dipole, general velocity (hard_sphere_potential.py:65-99, hard_dipole_potential.py:75-114)

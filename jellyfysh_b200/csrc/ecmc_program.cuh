@@ -18,10 +18,14 @@ struct __align__(32) Particle {
     double x, y, z, charge;
 };
 
-// Walker alias-table entry (jellyfysh/event_handler/walker.py:69-103): cell_a with rate_a, else cell_b
-struct __align__(16) WalkerEntry {
-    int cell_a, cell_b;
+// Walker alias-table entry (jellyfysh/event_handler/walker.py:69-103): cell_a if uniform(0, mean) <= rate_a, else
+// cell_b. One 32-byte record per entry = one sector per cell-veto draw: the relative cells come as packed per-axis
+// identifiers (x | y << 10 | z << 20, no divisions on the device) together with the derivative bound of each cell
+// for this direction and sign (CellVetoEventHandler._derivative_bounds), which the confirmation step needs.
+struct __align__(32) WalkerEntry {
     double rate_a;
+    int cell_a, cell_b;
+    double bound_a, bound_b;
 };
 
 struct DeviceWalker {
@@ -62,9 +66,10 @@ struct DeviceProgram {
     const int *nearby;            // [n_nearby] relative cell identifiers packed x | y << 10 | z << 20 (cuboid_periodic_cells.py:74-100)
     const double *cell_min_axis;  // [3][max_per_side] lower cell boundary per axis index (cuboid_cells.py:119-131)
     const int *translate_axis;    // [3][max_per_side][max_per_side] (cuboid_periodic_cells.py:182-207)
-    int max_per_side, pad2;
+    int max_per_side;
+    int translate_modular;        // 1 if translate_axis[d][a][r] == (a + r) mod cells_per_side[d] everywhere
     DeviceWalker upper[3], lower[3];
-    const double *bounds;         // [n_cells][dimension][2]
+    double inv_beta, inv_speed;
 };
 
 struct DeviceState {

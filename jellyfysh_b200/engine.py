@@ -12,7 +12,8 @@ import numpy as np
 from jellyfysh_b200 import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, "libecmc_b200.so")
+# JELLYFYSH_B200_LIBRARY selects another build of the same library (kernel tuning experiments)
+LIBRARY_PATH = os.environ.get("JELLYFYSH_B200_LIBRARY", os.path.join(_HERE, "libecmc_b200.so"))
 _LIB = None
 
 INF = float("inf")
