@@ -219,6 +219,7 @@ int upload_walker(EcmcHandle *h, const EcmcWalkerTable &in, DeviceWalker *out, c
     out->bits = bit_length((uint32_t)in.n_entries);
     out->total_rate = in.total_rate;
     out->mean_rate = in.mean_rate;
+    out->inv_total_rate_speed = 1.0 / (in.total_rate * d.speed);
     return device_upload(h, &out->entries, entries);
 }
 

@@ -105,6 +105,11 @@ ECMC_D void cell_identifier_of(const DeviceProgram &P, const Particle &a, int id
     id[1] = P.dimension > 1 ? (int)(a.y / P.side_length[1]) : 0;
     id[2] = P.dimension > 2 ? (int)(a.z / P.side_length[2]) : 0;
 }
+ECMC_D void cell_identifier_of(const DeviceProgram &P, const Particle &a, int &id0, int &id1, int &id2) {
+    id0 = (int)(a.x / P.side_length[0]);
+    id1 = P.dimension > 1 ? (int)(a.y / P.side_length[1]) : 0;
+    id2 = P.dimension > 2 ? (int)(a.z / P.side_length[2]) : 0;
+}
 ECMC_D int flat_cell(const DeviceProgram &P, const int id[3]) {
     return id[0] * P.cumulative[0] + id[1] * P.cumulative[1] + id[2] * P.cumulative[2];
 }
@@ -158,10 +163,15 @@ ECMC_D int warp_argmin(unsigned long long key, int seq, int lane) {
     return __ffs(__ballot_sync(kFull, tied && seq == min_seq)) - 1;
 }
 
+// Per-launch event counters of one chain, kept in registers; the rare ones (accepted vetoes, bound violations,
+// capacity overflows) go straight to the global statistics, the boundary count is what remains of `events`.
 struct Counters {
-    unsigned events, pair, veto, veto_accepted, boundary, end_of_chain, violations, capacity;
+    unsigned events, pair, veto, end_of_chain;
     unsigned long long candidates;
 };
+ECMC_D void count_rare(const RunArgs &A, int lane, int index) {
+    if (lane == 0 && A.stats) atomicAdd(reinterpret_cast<unsigned long long *>(A.stats) + index, 1ull);
+}
 
 template <int CAND, int REAL, int VETO, bool RECORD, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
@@ -190,10 +200,11 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     bool was_pending = stp->pending_kind != ECMC_EVENT_NONE;  // only the first iteration can start from a kept candidate
     int n_surplus = S.n_surplus[chain];
     Particle a = part[active];
-    int cid[3];
-    cid[0] = (active_cell / P.cumulative[0]) % P.per_side[0];
-    cid[1] = (active_cell / P.cumulative[1]) % P.per_side[1];
-    cid[2] = (active_cell / P.cumulative[2]) % P.per_side[2];
+    // per-axis identifiers of the active cell: scalars, never indexed by a runtime direction (that would put them
+    // into local memory)
+    int cid0 = (active_cell / P.cumulative[0]) % P.per_side[0];
+    int cid1 = (active_cell / P.cumulative[1]) % P.per_side[1];
+    int cid2 = (active_cell / P.cumulative[2]) % P.per_side[2];
 
     const Time until = {A.until_q, A.until_r};
     const double L = P.length, half = P.half_length, speed = P.speed;
@@ -202,7 +213,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     const bool has_veto = VETO != 0 && P.veto_enabled;
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
 
-    Counters n = {0, 0, 0, 0, 0, 0, 0, 0, 0ull};
+    Counters n = {0, 0, 0, 0, 0ull};
     bool stopped_by_time = false;
 
     while (n.events < max_events) {
@@ -230,16 +241,16 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             const int nearby_slots = has_pairs ? P.n_nearby * m : 0;
             const int n_pair_slots = has_pairs ? nearby_slots + n_surplus : 0;
             const double c_active = P.pair_use_charge ? a.charge : 1.0;
-            unsigned long long wkey = 0x7ff0000000000000ull;  // per-lane best
-            double wx = INFINITY;
-            int wseq = kSeqNone;
+            unsigned long long best_key = 0x7ff0000000000000ull;  // best of the passes so far (uniform)
+            double best_x = INFINITY;
+            int best_seq = kSeqNone;
             for (int base = 0; base < n_pair_slots + 2; base += 32) {
                 const int s = base + lane - 2;  // pair slot index; -2 = veto, -1 = boundary
                 int target = -1;
                 if (s >= 0 && s < nearby_slots) {
                     const int ci = m == 1 ? s : s / m;
                     const int code = __ldg(P.nearby + ci);
-                    int x = cid[0] + (code & 1023), y = cid[1] + ((code >> 10) & 1023), z = cid[2] + (code >> 20);
+                    int x = cid0 + (code & 1023), y = cid1 + ((code >> 10) & 1023), z = cid2 + (code >> 20);
                     if (x >= P.per_side[0]) x -= P.per_side[0];
                     if (y >= P.per_side[1]) y -= P.per_side[1];
                     if (z >= P.per_side[2]) z -= P.per_side[2];
@@ -279,11 +290,14 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     seq = s;
                 } else if (is_veto) {
                     // CellVetoEventHandler.send_event_time (cell_veto_event_handler.py:200-238)
+                    // InnerPointEstimator.charge_correction_factor (inner_point_estimator.py:165-192)
                     double charge_factor = 1.0;
-                    if (P.veto_use_charge) charge_factor = a.charge * 1.0 / P.veto_target_charge;
+                    if (P.veto_use_charge) {
+                        charge_factor = a.charge * 1.0;
+                        if (P.veto_target_charge != 1.0) charge_factor = charge_factor / P.veto_target_charge;
+                    }
                     const DeviceWalker *w = &P.upper[dir];
                     if (!(charge_factor > 0.0)) { charge_factor *= -1.0; w = &P.lower[dir]; }
-                    const double total_rate = w->total_rate * charge_factor;
                     // random.choice(table) = table[_randbelow(n)]: rejection on the top bits of successive words
                     uint32_t e = 0;
                     bool found = false;
@@ -309,30 +323,33 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     int tx, ty, tz;
                     const int rx = relative & 1023, ry = (relative >> 10) & 1023, rz = relative >> 20;
                     if (P.translate_modular) {
-                        tx = cid[0] + rx; ty = cid[1] + ry; tz = cid[2] + rz;
+                        tx = cid0 + rx; ty = cid1 + ry; tz = cid2 + rz;
                         if (tx >= P.per_side[0]) tx -= P.per_side[0];
                         if (ty >= P.per_side[1]) ty -= P.per_side[1];
                         if (tz >= P.per_side[2]) tz -= P.per_side[2];
                     } else {
                         const int mps = P.max_per_side;
-                        tx = __ldg(P.translate_axis + (0 * mps + cid[0]) * mps + rx);
-                        ty = __ldg(P.translate_axis + (1 * mps + cid[1]) * mps + ry);
-                        tz = __ldg(P.translate_axis + (2 * mps + cid[2]) * mps + rz);
+                        tx = __ldg(P.translate_axis + (0 * mps + cid0) * mps + rx);
+                        ty = __ldg(P.translate_axis + (1 * mps + cid1) * mps + ry);
+                        tz = __ldg(P.translate_axis + (2 * mps + cid2) * mps + rz);
                     }
                     cell = tx * P.cumulative[0] + ty * P.cumulative[1] + tz * P.cumulative[2];
-                    dt = exponential / (total_rate * speed);
+                    // expovariate(beta) / (total rate * charge factor * speed): the reciprocal of the table's part is
+                    // precomputed, chargeless handlers never divide
+                    dt = exponential * w->inv_total_rate_speed;
+                    if (P.veto_use_charge) dt = exponential / (w->total_rate * charge_factor * speed);
                     kind = ECMC_EVENT_CELL_VETO;
                     seq = n_pair_slots;
                 } else if (is_boundary) {
                     // CellBoundaryEventHandler.send_event_time (cell_boundary_event_handler.py:122-156): the lower
                     // boundary of the neighbour cell in the direction of motion
-                    int nid = cid[dir] + 1;
+                    int nid = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2)) + 1;
                     if (nid >= P.per_side[dir]) nid = 0;
                     const double neighbor_boundary = __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
                     double separation = neighbor_boundary - component(a, dir);
                     if (separation < 0.0) separation = separation + L;  // next_image, hypercubic_setting.py:191
                     dt = separation * P.inv_speed;
-                    cell = active_cell + (nid - cid[dir]) * P.cumulative[dir];
+                    cell = active_cell + (nid - (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2))) * P.cumulative[dir];
                     kind = ECMC_EVENT_CELL_BOUNDARY;
                     seq = n_pair_slots + 1;
                 }
@@ -341,19 +358,22 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const bool finite = kind != ECMC_EVENT_NONE && isfinite(x);  // heap_scheduler.py:139: only finite times
                 n_cand += __popc(__ballot_sync(kFull, finite));
                 const unsigned long long k64 = finite ? time_key(x) : 0x7ff0000000000000ull;
-                if (k64 < wkey) {
-                    wkey = k64; wx = x; wseq = seq; bkind = kind; btarget = target; bcell = cell; brate = rate;
+                // argmin of this pass, then against the earlier passes (usually there is one pass)
+                const int owner = warp_argmin(k64, finite ? seq : kSeqNone, lane);
+                const unsigned long long pass_key = __shfl_sync(kFull, k64, owner);
+                const int pass_seq = __shfl_sync(kFull, finite ? seq : kSeqNone, owner);
+                if (pass_key < best_key || (pass_key == best_key && pass_seq < best_seq)) {
+                    best_key = pass_key; best_seq = pass_seq;
+                    best_x = __shfl_sync(kFull, x, owner);
+                    bkind = __shfl_sync(kFull, kind, owner);
+                    btarget = __shfl_sync(kFull, target, owner);
+                    bcell = __shfl_sync(kFull, cell, owner);
+                    brate = __shfl_sync(kFull, rate, owner);
                 }
             }
-            const int owner = warp_argmin(wkey, wseq, lane);
-            if (owner >= 0) {
-                const double x = __shfl_sync(kFull, wx, owner);
-                const double fl = floor(x);
-                bt.q = now.q + fl; bt.r = x - fl;
-                bkind = __shfl_sync(kFull, bkind, owner);
-                btarget = __shfl_sync(kFull, btarget, owner);
-                bcell = __shfl_sync(kFull, bcell, owner);
-                brate = __shfl_sync(kFull, brate, owner);
+            if (best_seq != kSeqNone) {
+                const double fl = floor(best_x);
+                bt.q = now.q + fl; bt.r = best_x - fl;
             } else {
                 bkind = ECMC_EVENT_NONE;
             }
@@ -412,7 +432,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const double bounding_rate = derivative_warp<CAND>(P.cand_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
                 const double real = derivative_warp<REAL>(P.real_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
-                    if (bounding_rate < real) n.violations++;
+                    if (bounding_rate < real) count_rare(A, lane, 7);
                     const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
                     if (0.0 + (bounding_rate - 0.0) * u < real) accepted = 1;
                 }
@@ -433,22 +453,21 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const double c1 = P.veto_use_charge ? a.charge : 1.0, c2 = P.veto_use_charge ? tp.charge : 1.0;
                 const double real = derivative_warp<VETO>(P.veto_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
-                    if (brate < real) n.violations++;
+                    if (brate < real) count_rare(A, lane, 7);
                     const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
                     if (0.0 + (brate - 0.0) * u < real) { accepted = 1; new_active = t; }
                 }
             }
             n.veto++;
-            n.veto_accepted += accepted;
+            if (accepted) count_rare(A, lane, 3);
             break;
         }
         case ECMC_EVENT_CELL_BOUNDARY: {
             // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
-            int nid = cid[dir] + 1;
+            int nid = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2)) + 1;
             if (nid >= P.per_side[dir]) nid = 0;
-            if (bcell != active_cell + (nid - cid[dir]) * P.cumulative[dir]) nid = (bcell / P.cumulative[dir]) % P.per_side[dir];
+            if (bcell != active_cell + (nid - (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2))) * P.cumulative[dir]) nid = (bcell / P.cumulative[dir]) % P.per_side[dir];
             set_component(a, dir, __ldg(P.cell_min_axis + dir * P.max_per_side + nid));
-            n.boundary++;
             break;
         }
         case ECMC_EVENT_END_OF_CHAIN:
@@ -484,28 +503,28 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 delta = occupancy_insert(occ, sur, n_surplus, m, P.max_surplus, active_cell, active);
             }
             delta = __shfl_sync(kFull, delta, 0);
-            if (delta == 2) n.capacity++; else n_surplus += delta;
+            if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
             __syncwarp();
             active = new_active;
             a = part[active];
-            cell_identifier_of(P, a, cid);
-            active_cell = flat_cell(P, cid);
+            cell_identifier_of(P, a, cid0, cid1, cid2);
+            active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
             delta = 0;
             if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, m, active_cell, active);
             delta = __shfl_sync(kFull, delta, 0);
-            if (delta == 2) n.capacity++; else n_surplus += delta;
+            if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
             __syncwarp();
         } else {
             // The oracle recomputes the cell from the position after every event. Cell `id` holds exactly the doubles
             // in [cell_min[id], cell_min[id + 1]) (see axis_geometry), and only the coordinate along the direction of
             // motion moved, so two comparisons tell whether the three divisions are needed at all.
             const double *cell_min = P.cell_min_axis + dir * P.max_per_side;
-            const int id = cid[dir];
+            const int id = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2));
             const double x = component(a, dir);
             const bool same = x >= __ldg(cell_min + id) && (id + 1 == P.per_side[dir] ? x < L : x < __ldg(cell_min + id + 1));
             if (!same) {
-                cell_identifier_of(P, a, cid);
-                active_cell = flat_cell(P, cid);
+                cell_identifier_of(P, a, cid0, cid1, cid2);
+                active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
             }
         }
         if (kind == ECMC_EVENT_END_OF_CHAIN) {
@@ -536,12 +555,10 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             if (n.events) atomicAdd(st + 0, (unsigned long long)n.events);
             if (n.pair) atomicAdd(st + 1, (unsigned long long)n.pair);
             if (n.veto) atomicAdd(st + 2, (unsigned long long)n.veto);
-            if (n.veto_accepted) atomicAdd(st + 3, (unsigned long long)n.veto_accepted);
-            if (n.boundary) atomicAdd(st + 4, (unsigned long long)n.boundary);
+            const unsigned boundary = n.events - n.pair - n.veto - n.end_of_chain;
+            if (boundary) atomicAdd(st + 4, (unsigned long long)boundary);
             if (n.end_of_chain) atomicAdd(st + 5, (unsigned long long)n.end_of_chain);
             if (n.candidates) atomicAdd(st + 6, n.candidates);
-            if (n.violations) atomicAdd(st + 7, (unsigned long long)n.violations);
-            if (n.capacity) atomicAdd(st + 8, (unsigned long long)n.capacity);
         }
     }
 }

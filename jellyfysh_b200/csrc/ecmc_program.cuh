@@ -33,6 +33,7 @@ struct DeviceWalker {
     int n_entries;
     int bits;  // n_entries.bit_length(), for CPython's _randbelow
     double total_rate, mean_rate;
+    double inv_total_rate_speed;  // 1 / (total_rate * speed)
 };
 
 struct PotentialParams {
