@@ -350,8 +350,12 @@ int build_device_program(EcmcHandle *h) {
 typedef void (*EventKernel)(const DeviceProgram, const DeviceState, const RunArgs);
 
 template <int CAND, int REAL, int VETO>
-EventKernel pick_record(bool record) {
-    return record ? event_kernel<CAND, REAL, VETO, true, kWarpsPerBlock> : event_kernel<CAND, REAL, VETO, false, kWarpsPerBlock>;
+EventKernel pick_record(bool record, bool single) {
+    if (single)
+        return record ? event_kernel<CAND, REAL, VETO, true, true, kWarpsPerBlock>
+                      : event_kernel<CAND, REAL, VETO, true, false, kWarpsPerBlock>;
+    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock>
+                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock>;
 }
 
 EventKernel pick_kernel(const DeviceProgram &d, bool record) {
@@ -360,12 +364,13 @@ EventKernel pick_kernel(const DeviceProgram &d, bool record) {
     const int veto = d.veto_enabled ? d.veto_potential.kind : 0;
     const int LJ = ECMC_POT_LENNARD_JONES, HS = ECMC_POT_HARD_SPHERE, MIC = ECMC_POT_MERGED_IMAGE_COULOMB,
               IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING;
-    if (cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record);
-    if (cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record);
-    if (cand == HS && real == 0 && veto == 0) return pick_record<ECMC_POT_HARD_SPHERE, 0, 0>(record);
+    const bool single = d.max_occupants == 1;
+    if (cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record, single);
+    if (cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record, single);
+    if (cand == HS && real == 0 && veto == 0) return pick_record<ECMC_POT_HARD_SPHERE, 0, 0>(record, false);
     if (cand == IPCB && real == MIC && veto == MIC)
-        return pick_record<ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, ECMC_POT_MERGED_IMAGE_COULOMB, ECMC_POT_MERGED_IMAGE_COULOMB>(record);
-    return pick_record<-1, -1, -1>(record);
+        return pick_record<ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, ECMC_POT_MERGED_IMAGE_COULOMB, ECMC_POT_MERGED_IMAGE_COULOMB>(record, single);
+    return pick_record<-1, -1, -1>(record, false);
 }
 
 int acquire_events(EcmcHandle *h, EventPair *out) {

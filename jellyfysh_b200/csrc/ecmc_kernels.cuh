@@ -149,8 +149,8 @@ ECMC_D int occupancy_remove(int *occ, int *sur, int n_surplus, int m, int cell, 
 // `now`, and Time.__add__ splits x = now.remainder + dt exactly into floor(x) and x - floor(x) (base/time.py:129-133),
 // so the lexicographic comparison of (quotient, remainder) (heap.c:176-178) is the comparison of the doubles x,
 // and for x >= 0 that is the comparison of their bit patterns as unsigned integers.
-ECMC_D unsigned long long time_key(double x) {
-    return x >= 0.0 ? (unsigned long long)__double_as_longlong(x) : (x < 0.0 ? 0ull : 0x7ff0000000000000ull);
+ECMC_D unsigned long long time_key(double x) {  // x finite; a (rounding-) negative x sorts first
+    return x > 0.0 ? (unsigned long long)__double_as_longlong(x) : 0ull;
 }
 // argmin over the warp of (key, sequence): the lane that owns the minimum, by two 32-bit REDUX.MIN steps on the key
 // and one on the sequence number (ties in time are broken like the oracle's scan: lowest sequence first)
@@ -173,7 +173,9 @@ ECMC_D void count_rare(const RunArgs &A, int lane, int index) {
     if (lane == 0 && A.stats) atomicAdd(reinterpret_cast<unsigned long long *>(A.stats) + index, 1ull);
 }
 
-template <int CAND, int REAL, int VETO, bool RECORD, int WARPS>
+// SINGLE: the program stores one occupant per cell (the reference's default maximum_number_occupants = 1), which
+// removes the slot arithmetic from the candidate gather.
+template <int CAND, int REAL, int VETO, bool SINGLE, bool RECORD, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     __shared__ double trig_all[UsesMic<REAL, VETO>::value ? WARPS * kTrigDoubles : 1];
@@ -184,7 +186,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     double *trig = UsesMic<REAL, VETO>::value ? trig_all + warp * kTrigDoubles : trig_all;
 
     Particle *part = S.particles + (size_t)chain * P.n_particles;
-    const int m = P.max_occupants;
+    const int m = SINGLE ? 1 : P.max_occupants;
     int *occ = S.occupants + (size_t)chain * P.n_cells * m;
     int *sur = S.surplus + (size_t)chain * P.max_surplus;
     EcmcChainState *stp = S.chains + chain;
@@ -205,6 +207,15 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     int cid0 = (active_cell / P.cumulative[0]) % P.per_side[0];
     int cid1 = (active_cell / P.cumulative[1]) % P.per_side[1];
     int cid2 = (active_cell / P.cumulative[2]) % P.per_side[2];
+
+    // lower boundary of the next cell in the direction of motion (cell_boundary_event_handler.py:135-156); 0.0 when
+    // the active cell is the last one of its row. Reloaded whenever the active cell or the direction changes.
+    auto next_boundary = [&]() {
+        int nid = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2)) + 1;
+        if (nid >= P.per_side[dir]) nid = 0;
+        return __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
+    };
+    double boundary = next_boundary();
 
     const Time until = {A.until_q, A.until_r};
     const double L = P.length, half = P.half_length, speed = P.speed;
@@ -341,21 +352,18 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     kind = ECMC_EVENT_CELL_VETO;
                     seq = n_pair_slots;
                 } else if (is_boundary) {
-                    // CellBoundaryEventHandler.send_event_time (cell_boundary_event_handler.py:122-156): the lower
-                    // boundary of the neighbour cell in the direction of motion
-                    int nid = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2)) + 1;
-                    if (nid >= P.per_side[dir]) nid = 0;
-                    const double neighbor_boundary = __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
-                    double separation = neighbor_boundary - component(a, dir);
+                    // CellBoundaryEventHandler.send_event_time (cell_boundary_event_handler.py:122-156)
+                    double separation = boundary - component(a, dir);
                     if (separation < 0.0) separation = separation + L;  // next_image, hypercubic_setting.py:191
                     dt = separation * P.inv_speed;
-                    cell = active_cell + (nid - (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2))) * P.cumulative[dir];
+                    const int id = dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2);
+                    cell = active_cell + ((id + 1 == P.per_side[dir] ? 0 : id + 1) - id) * P.cumulative[dir];
                     kind = ECMC_EVENT_CELL_BOUNDARY;
                     seq = n_pair_slots + 1;
                 }
                 // Time.__add__: event time = now + dt; x orders the candidates (see time_key)
                 const double x = now.r + dt;
-                const bool finite = kind != ECMC_EVENT_NONE && isfinite(x);  // heap_scheduler.py:139: only finite times
+                const bool finite = kind != ECMC_EVENT_NONE && x < INFINITY;  // heap_scheduler.py:139; NaN never wins
                 n_cand += __popc(__ballot_sync(kFull, finite));
                 const unsigned long long k64 = finite ? time_key(x) : 0x7ff0000000000000ull;
                 // argmin of this pass, then against the earlier passes (usually there is one pass)
@@ -410,11 +418,15 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         }
 
         // ---- out-state: time slice of the active particle (event_handler/abstracts/abstracts.py:82-95)
+        const double x_before = component(a, dir);
         {
             const double dt = time_sub(event_time, now);
-            set_component(a, dir, correct_position_entry(__dadd_rn(component(a, dir), __dmul_rn(speed, dt)), L));
+            set_component(a, dir, correct_position_entry(__dadd_rn(x_before, __dmul_rn(speed, dt)), L));
             now = event_time;
         }
+        // Did the time slice itself carry the particle out of its cell (without a boundary event)? Cell `id` holds
+        // exactly the doubles in [cell_min[id], cell_min[id + 1]) and the particle only moves forward.
+        const bool left_cell = boundary == 0.0 ? component(a, dir) < x_before : component(a, dir) >= boundary;
         int new_active = active, accepted = 0, rec_target = -1;
         switch (kind) {
         case ECMC_EVENT_PAIR: {
@@ -464,10 +476,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         }
         case ECMC_EVENT_CELL_BOUNDARY: {
             // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
-            int nid = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2)) + 1;
-            if (nid >= P.per_side[dir]) nid = 0;
-            if (bcell != active_cell + (nid - (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2))) * P.cumulative[dir]) nid = (bcell / P.cumulative[dir]) % P.per_side[dir];
-            set_component(a, dir, __ldg(P.cell_min_axis + dir * P.max_per_side + nid));
+            set_component(a, dir, boundary);
             break;
         }
         case ECMC_EVENT_END_OF_CHAIN:
@@ -514,18 +523,12 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             delta = __shfl_sync(kFull, delta, 0);
             if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
             __syncwarp();
-        } else {
-            // The oracle recomputes the cell from the position after every event. Cell `id` holds exactly the doubles
-            // in [cell_min[id], cell_min[id + 1]) (see axis_geometry), and only the coordinate along the direction of
-            // motion moved, so two comparisons tell whether the three divisions are needed at all.
-            const double *cell_min = P.cell_min_axis + dir * P.max_per_side;
-            const int id = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2));
-            const double x = component(a, dir);
-            const bool same = x >= __ldg(cell_min + id) && (id + 1 == P.per_side[dir] ? x < L : x < __ldg(cell_min + id + 1));
-            if (!same) {
-                cell_identifier_of(P, a, cid0, cid1, cid2);
-                active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
-            }
+            boundary = next_boundary();
+        } else if (kind == ECMC_EVENT_CELL_BOUNDARY || kind == ECMC_EVENT_END_OF_CHAIN || left_cell) {
+            // the oracle recomputes the cell from the position after every event; only these can change it
+            cell_identifier_of(P, a, cid0, cid1, cid2);
+            active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
+            boundary = next_boundary();
         }
         if (kind == ECMC_EVENT_END_OF_CHAIN) {
             // the next end-of-chain candidate: chain_time after this one, new active by randint
