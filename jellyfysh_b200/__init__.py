@@ -1,0 +1,20 @@
+"""jellyfysh_b200 -- B200-native batched event-chain Monte Carlo engine behind JeLLyFysh's plugin surface.
+
+engine      ctypes binding of libecmc_b200.so (include/ecmc.h), the CUDA library of the hot path
+program     EcmcProgram assembly, tables: init-time cell-veto tables on the device, workloads: synthetic configs
+compiler    JeLLyFysh object graph (factory-built from INI) -> EcmcProgram
+mediator    CudaBatchedMediator, the drop-in for jellyfysh.mediator.single_process_mediator
+"""
+import importlib
+import sys
+
+
+def install():
+    """Make `[Run] mediator = cuda_batched_mediator` resolvable by the reference's factory
+    (jellyfysh/base/factory.py:111-122 imports jellyfysh.mediator.<snake_case_name>) without copying a file into
+    the jellyfysh tree: the module is registered under that name. Needs `jellyfysh` importable."""
+    module = importlib.import_module("jellyfysh_b200.mediator.cuda_batched_mediator")
+    sys.modules["jellyfysh.mediator.cuda_batched_mediator"] = module
+    import jellyfysh.mediator
+    jellyfysh.mediator.cuda_batched_mediator = module
+    return module

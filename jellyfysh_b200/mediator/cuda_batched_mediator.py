@@ -1,0 +1,143 @@
+"""CudaBatchedMediator -- the reference's mediator contract over the B200 event-chain engine.
+
+Drop-in for jellyfysh/mediator/single_process_mediator.py:57-156: same constructor arguments (input-output handler,
+state handler, scheduler, activator -- all built by the reference's factory from an unchanged INI file), same `run()`
+/ `post_run()` protocol (run.py:183-200), raises base.exceptions.EndOfRun like mediator.py:375. Selected with
+
+    [Run]
+    mediator = cuda_batched_mediator
+
+    [CudaBatchedMediator]
+    state_handler = tree_state_handler
+    scheduler = heap_scheduler
+    activator = tag_activator
+    input_output_handler = input_output_handler
+    number_of_chains = 4096        ; independent Markov chains advanced at once (default 1)
+    device = 0
+    seed = 0
+
+(see INTEGRATION.md for how the module becomes `jellyfysh.mediator.cuda_batched_mediator`).
+
+What moves to the device: every iteration of the reference loop whose winner is an interaction, cell-veto,
+cell-boundary or end-of-chain handler. What stays on the host: sampling and end-of-run handlers, which the reference
+calls at their own event times -- here between `ecmc_run(until = their time)` launches, with the chain states downloaded
+into the reference's state handler so that the reference's output handlers see exactly what they expect.
+The scheduler object is kept for the host control events only (the device argmin replaces it for interaction events).
+Chain 0 starts from the state the input handler produced; chains c > 0 from further reads of the same input handler.
+"""
+import logging
+
+import numpy as np
+
+from jellyfysh.activator import Activator
+from jellyfysh.base.exceptions import EndOfRun
+from jellyfysh.base.time import Time
+from jellyfysh.input_output_handler import InputOutputHandler
+from jellyfysh.mediator.mediator import Mediator
+from jellyfysh.scheduler import Scheduler
+from jellyfysh.state_handler import StateHandler
+
+from jellyfysh_b200 import compiler, engine
+
+
+class CudaBatchedMediator(Mediator):
+    """Mediator that advances `number_of_chains` independent chains on one CUDA device."""
+
+    def __init__(self, input_output_handler: InputOutputHandler, state_handler: StateHandler, scheduler: Scheduler,
+                 activator: Activator, number_of_chains: int = 1, device: int = 0, seed: int = 0,
+                 first_random_stream: int = 0, maximum_surplus: int = 0) -> None:
+        """
+        Parameters follow SingleProcessMediator (single_process_mediator.py:57-72); in addition:
+
+        number_of_chains : independent Markov chains on the device.
+        device : CUDA device index.
+        seed, first_random_stream : chain c reads the counter-based random stream (seed, first_random_stream + c).
+        maximum_surplus : capacity of the per-chain surplus list (0: one slot per particle).
+        """
+        self._logger = logging.getLogger(__name__)
+        if number_of_chains < 1:
+            raise compiler._configuration_error("number_of_chains must be at least 1")
+        state_handler.initialize(input_output_handler.read())
+        super().__init__(input_output_handler, state_handler, scheduler, activator)
+        template = state_handler.extract_global_state()
+        self._compiled = compiler.compile_program(activator, template, seed=seed,
+                                                  max_surplus=maximum_surplus if maximum_surplus > 0 else None)
+        self._number_of_chains = number_of_chains
+        positions, charges = compiler.positions_and_charges(template, self._compiled.charge_name)
+        all_positions = np.empty((number_of_chains,) + positions.shape)
+        all_charges = None if charges is None else np.empty((number_of_chains,) + charges.shape)
+        all_positions[0] = positions
+        if charges is not None:
+            all_charges[0] = charges
+        for chain in range(1, number_of_chains):
+            nodes = input_output_handler.read()
+            all_positions[chain] = [node.value.position for node in nodes]
+            if charges is not None:
+                all_charges[chain] = [node.value.charge[self._compiled.charge_name] for node in nodes]
+        self._engine = engine.Engine(self._compiled.builder, n_chains=number_of_chains, device=device)
+        self._engine.upload_positions(all_positions, all_charges)
+        self._engine.start(first_stream=first_random_stream)
+        self._statistics = {}
+        self._control_times = {}
+
+    # ---- state hand-over to the reference's state handler ------------------------------------------------------
+    def _load_chain_into_state_handler(self, chain, positions, states):
+        """Write one chain's device state through the public state-handler contract
+        (state_handler.py:63-165): positions of all units, velocity / time stamp of the active one."""
+        speed = self._compiled.builder.program.speed
+        dimension = self._compiled.builder.program.dimension
+        cnodes = self._state_handler.extract_global_state()
+        state = states[chain]
+        for index, cnode in enumerate(cnodes):
+            unit = cnode.value
+            unit.position = [float(x) for x in positions[chain, index]]
+            if index == int(state["active"]):
+                unit.velocity = [speed if d == int(state["direction"]) else 0.0 for d in range(dimension)]
+                unit.time_stamp = Time(float(state["time_q"]), float(state["time_r"]))
+            else:
+                unit.velocity, unit.time_stamp = None, None
+        self._state_handler.insert_into_global_state(cnodes)
+
+    def _write_output(self, handler):
+        if handler.output_handler is None:
+            return
+        positions = self._engine.download_positions()
+        states = self._engine.chain_states()
+        for chain in range(self._number_of_chains):
+            self._load_chain_into_state_handler(chain, positions, states)
+            self._input_output_handler.write(handler.output_handler, self._state_handler.extract_global_state())
+
+    # ---- the loop ------------------------------------------------------------------------------------------------
+    def run(self) -> None:
+        """Advance all chains from control event to control event until the end-of-run handler fires."""
+        controls = self._compiled.control_handlers
+        for handler in controls:
+            if handler not in self._control_times:
+                self._control_times[handler] = handler.send_event_time()
+        while True:
+            handler = min(controls, key=lambda h: self._control_times[h])
+            event_time = self._control_times[handler]
+            self._engine.run(until=(event_time.quotient, event_time.remainder))
+            for key, value in self._engine.sync().items():
+                self._statistics[key] = self._statistics.get(key, 0) + value
+            self._event_handler_with_shortest_event_time = handler
+            names = {cls.__name__ for cls in type(handler).__mro__}
+            if "EndOfRunEventHandler" in names:
+                self._write_output(handler)
+                positions = self._engine.download_positions()
+                self._load_chain_into_state_handler(0, positions, self._engine.chain_states())
+                raise EndOfRun
+            self._write_output(handler)
+            self._control_times[handler] = handler.send_event_time()
+
+    @property
+    def statistics(self):
+        """Event counters of all chains so far (EcmcStats of include/ecmc.h)."""
+        return dict(self._statistics)
+
+    @property
+    def engine(self):
+        return self._engine
+
+    def update_logging(self) -> None:
+        self._logger = logging.getLogger(__name__)

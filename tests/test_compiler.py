@@ -1,0 +1,123 @@
+"""The host layer: compile a JeLLyFysh object graph, built by the reference's own factory from INI text, into an
+EcmcProgram. Needs the installed reference copy under baseline/_ref (git-ignored, travels to the GPU box); skipped
+without it. No GPU needed: the compiled program is run by the CPU oracle and compared with the reference trace."""
+import configparser
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import configs
+import trace_util as tu
+
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "jellyfysh", "run.py")),
+                                reason="baseline/_ref (installed reference) not present")
+
+
+def build_reference_graph(ini_text, positions=None):
+    """The reference's run.py:182-183 on INI text; returns (mediator, setting module)."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+    warnings.filterwarnings("ignore")
+    from jellyfysh.base import factory
+    from jellyfysh.base.strings import to_camel_case
+    import jellyfysh.setting as setting
+    from jellyfysh.activator.tagger.factor_type_maps import FactorTypeMaps
+    setting.reset()
+    FactorTypeMaps._instance = None
+    factory.used_sections.clear()
+    config = configparser.ConfigParser()
+    config.read_string(ini_text)
+    factory.build_from_config(config, to_camel_case(config.get("Run", "setting")), "jellyfysh.setting")
+    if positions is not None:
+        iterator = iter([list(map(float, p)) for p in positions])
+        setting.random_position = lambda: next(iterator)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mediator = factory.build_from_config(config, to_camel_case(config.get("Run", "mediator")), "jellyfysh.mediator")
+    return mediator, setting
+
+
+@pytest.fixture
+def lj_graph():
+    g = tu.load_trace("trace_lj_small")
+    ini = configs.lennard_jones_ini(int(g["meta_n"]), float(g["meta_system_length"]), int(g["meta_cells_per_side"][0]),
+                                    chain_time=float(g["meta_chain_time"]), points_per_side=int(g["meta_estimator"][1]),
+                                    estimator_prefactor=float(g["meta_estimator"][0]), end_of_run_time=50.0)
+    mediator, setting = build_reference_graph(ini, g["positions0"])
+    yield g, mediator
+    setting.reset()
+
+
+def test_compiled_program_matches_reference_tables(lj_graph):
+    from jellyfysh_b200 import abi, compiler
+    g, mediator = lj_graph
+    compiled = compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state(),
+                                        seed=int(g["seed"][0]))
+    p = compiled.builder.program
+    assert (p.dimension, p.n_particles, p.neighbor_layers, p.max_occupants) == (3, int(g["meta_n"]), 1, 1)
+    assert [p.cells_per_side[d] for d in range(3)] == [int(c) for c in g["meta_cells_per_side"]]
+    assert (p.system_length, p.beta, p.chain_time, p.speed) == (float(g["meta_system_length"]), 1.0,
+                                                                float(g["meta_chain_time"]), 1.0)
+    assert p.pair_handler == abi.PAIR_TWO_LEAF_UNIT and p.pair_potential.kind == abi.POT_LENNARD_JONES
+    assert list(p.pair_potential.params)[:2] == list(g["meta_lj"])
+    assert p.veto_enabled == 1 and p.veto_use_charge == 0 and compiled.charge_name is None
+    ref = tu.reference_tables(g)
+    ours = compiled.builder.tables
+    assert np.array_equal(ours["bounds"], np.nan_to_num(ref["bounds"], nan=0.0))
+    for kind in ("upper", "lower"):
+        for d in range(3):
+            for key in ("cell_a", "cell_b", "rate_a"):
+                assert np.array_equal(ours[kind][d][key], ref[kind][d][key])
+            assert ours[kind][d]["total_rate"] == ref[kind][d]["total_rate"]
+    assert len(compiled.control_handlers) == 1  # end of run
+
+
+def test_compiled_program_replays_reference_trace(oracle, lj_graph):
+    """INI -> reference factory -> compiler -> oracle chain reproduces the recorded reference run bit for bit."""
+    from jellyfysh_b200 import compiler
+    g, mediator = lj_graph
+    template = mediator._state_handler.extract_global_state()
+    compiled = compiler.compile_program(mediator._activator, template, seed=int(g["seed"][0]))
+    positions, charges = compiler.positions_and_charges(template, compiled.charge_name)
+    assert np.array_equal(positions, g["positions0"]) and charges is None
+    chain = oracle.OracleChain(compiled.builder)
+    chain.set_positions(positions)
+    chain.start(stream=int(g["seed"][1]))
+    n, rec = chain.run(max_events=2000, record=2000)
+    assert n == 2000 and tu.records_equal_discrete(rec, g["records"][:2000])
+    assert np.array_equal(rec["time_r"], g["records"]["time_r"][:2000])
+
+
+def test_coulomb_graph_compiles_with_charges():
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_coulomb_small")
+    ini = configs.coulomb_atoms_ini(int(g["meta_n"]), [int(c) for c in g["meta_cells_per_side"]],
+                                    points_per_side=int(g["meta_estimator"][1]), end_of_run_time=5.0)
+    mediator, setting = build_reference_graph(ini, g["positions0"])
+    try:
+        compiled = compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())
+        p = compiled.builder.program
+        assert p.pair_handler == abi.PAIR_TWO_LEAF_UNIT_BOUNDING
+        assert p.pair_potential.kind == abi.POT_MERGED_IMAGE_COULOMB
+        assert p.pair_bounding_potential.kind == abi.POT_INVERSE_POWER_COULOMB_BOUNDING
+        assert list(p.pair_potential.params)[:4] == list(g["meta_mic"])
+        assert p.pair_use_charge == 1 and p.veto_use_charge == 1 and compiled.charge_name == "electric_charge"
+        assert [p.cells_per_side[d] for d in range(3)] == [int(c) for c in g["meta_cells_per_side"]]
+    finally:
+        setting.reset()
+
+
+def test_unsupported_graphs_are_rejected(lj_graph):
+    """A dumping handler or an unbounded occupancy is refused, never approximated."""
+    from jellyfysh.base.exceptions import ConfigurationError
+    from jellyfysh_b200 import compiler
+    g, mediator = lj_graph
+    occupancy = mediator._activator._internal_states[0]
+    occupancy._maximum_number_occupants = 0
+    with pytest.raises(ConfigurationError):
+        compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())

@@ -1,0 +1,103 @@
+"""The drop-in: an INI file of the reference grammar with `[Run] mediator = cuda_batched_mediator` runs through the
+reference's own factory, input handler, state handler and output handlers, with the event loop on the GPU.
+Needs the installed reference copy (baseline/_ref) next to a CUDA device."""
+import os
+
+import numpy as np
+import pytest
+
+import configs
+import trace_util as tu
+from test_compiler import REF, build_reference_graph
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(os.path.join(REF, "jellyfysh", "run.py")),
+                                 reason="baseline/_ref (installed reference) not present")]
+
+
+def _device_ini(g, tmp_path, chains, end_of_run_time, sampling_interval):
+    ini = configs.lennard_jones_ini(int(g["meta_n"]), float(g["meta_system_length"]), int(g["meta_cells_per_side"][0]),
+                                    chain_time=float(g["meta_chain_time"]), points_per_side=int(g["meta_estimator"][1]),
+                                    estimator_prefactor=float(g["meta_estimator"][0]), end_of_run_time=end_of_run_time,
+                                    sampling_interval=sampling_interval)
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = %d\n"
+                                                 "first_random_stream = %d" % (chains, int(g["seed"][0]), int(g["seed"][1])))
+    return ini.replace("/tmp/jf_b200_golden_separation.dat", str(tmp_path / "separation.dat"))
+
+
+def test_ini_runs_on_the_device(oracle, tmp_path):
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import jellyfysh_b200
+    from jellyfysh_b200 import engine
+    from jellyfysh_b200.program import ProgramBuilder
+    jellyfysh_b200.install()
+    from jellyfysh.base.exceptions import EndOfRun
+
+    g = tu.load_trace("trace_lj_small")
+    end, interval = 2.5, 0.4
+    mediator, setting = build_reference_graph(_device_ini(g, tmp_path, 1, end, interval), g["positions0"])
+    try:
+        assert type(mediator).__mro__[1].__name__ == "Mediator" or "CudaBatchedMediator" in type(mediator).__name__
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        final = np.array([node.value.position for node in mediator._state_handler.extract_global_state()])
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["events"] > 1000 and stats["capacity_errors"] == 0
+    # the same program driven directly, interrupted at the same control times
+    times = [oracle.time_from_float(interval * k) for k in range(1, int(end / interval) + 1)] + [oracle.time_from_float(end)]
+    with engine.Engine(tu.builder_of(g, ProgramBuilder), n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        events = 0
+        for t in times:
+            eng.run(until=t)
+            events += eng.sync()["events"]
+        direct = eng.download_positions()[0]
+    assert events == stats["events"]
+    assert np.array_equal(final, direct)
+    # and the oracle agrees with both
+    chain = oracle.OracleChain(tu.builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"])
+    chain.start(stream=int(g["seed"][1]))
+    n_oracle = sum(chain.run(until=t)[0] for t in times)
+    assert n_oracle == events
+    assert np.max(np.abs(chain.positions() - final)) < 1e-12 * float(g["meta_system_length"])
+    # the reference's own output handler wrote the samples of every sampling event
+    lines = (tmp_path / "separation.dat").read_text().strip().splitlines()
+    n = int(g["meta_n"])
+    assert len(lines) == int(end / interval) * n * (n - 1) // 2
+
+
+def test_many_chains_from_the_input_handler(tmp_path):
+    """number_of_chains > 1: further start configurations come from the reference's input handler."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    from jellyfysh.base.exceptions import EndOfRun
+    g = tu.load_trace("trace_lj_small")
+    rng = np.random.default_rng(3)
+    side = 4
+    grid = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)[:int(g["meta_n"])]
+    length = float(g["meta_system_length"])
+    chains = 6
+    positions = np.concatenate([(grid + 0.5) * (length / side) + rng.uniform(-0.1, 0.1, size=grid.shape)
+                                for _ in range(chains)])
+    mediator, setting = build_reference_graph(_device_ini(g, tmp_path, chains, 1.0, None), positions)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        stats = mediator.statistics
+        states = mediator.engine.chain_states()
+    finally:
+        setting.reset()
+    assert stats["events"] > chains * 100
+    assert np.all(states["time_q"] == 1.0) and np.all(states["time_r"] == 0.0)
+    assert len(set(states["event_counter"].tolist())) > 1  # the chains are different

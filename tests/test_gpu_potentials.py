@@ -192,12 +192,3 @@ def test_lennard_jones_against_oracle_large(oracle):
         der = engine.potential_derivative(pot, 3, 12.7, d, sep)
         ref_der = oracle.potential_derivative_batch(pot, 3, 12.7, d, sep)
         assert close(der, ref_der, scale=lj_derivative_scale(4.0, 1.0, sep, d))
-
-
-def test_random_stream_device_library_matches_oracle(oracle):
-    for seed, stream, event, slot in [(0, 0, 0, 0), (7, 3, 12345, abi.slot(abi.SLOT_PAIR_TIME, 77)),
-                                      (0xdeadbeef, 4095, (1 << 40) + 17, abi.slot(abi.SLOT_VETO_CHOICE))]:
-        assert np.array_equal(engine.random_words(seed, stream, event, slot, 0, 13),
-                              oracle.random_words(seed, stream, event, slot, 0, 13))
-        assert np.array_equal(engine.random_doubles(seed, stream, event, slot, 0, 9),
-                              oracle.random_doubles(seed, stream, event, slot, 0, 9))
