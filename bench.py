@@ -36,7 +36,7 @@ UNIT = "events/s"
 def parse_args():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=10)
+    parser.add_argument("--steps", type=int, default=40)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--chains", type=int, default=4096, help="independent chains per GPU")
@@ -66,14 +66,21 @@ class ClockSampler:
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
-        self.samples = []
+        self.samples = []  # (arrival time, fields)
         self.process = None
         self.device_index = device_index
+        self.window = [None, None]
+
+    def open_window(self):
+        self.window[0] = time.perf_counter()
+
+    def close_window(self):
+        self.window[1] = time.perf_counter()
 
     def __enter__(self):
         try:
             self.process = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.FIELDS,
-                                             "--format=csv,noheader,nounits", "-lms", "100"],
+                                             "--format=csv,noheader,nounits", "-lms", "20"],
                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -85,7 +92,7 @@ class ClockSampler:
         for line in self.process.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 6 and parts[0].isdigit():
-                self.samples.append(parts)
+                self.samples.append((time.perf_counter(), parts))
 
     def __exit__(self, *exc):
         if self.process is not None:
@@ -96,16 +103,20 @@ class ClockSampler:
                 self.process.kill()
 
     def summary(self):
-        if not self.samples:
+        begin, end = self.window
+        inside = [fields for stamp, fields in self.samples if begin is not None and begin <= stamp <= (end or stamp)]
+        # nvidia-smi reports with a delay: if the timed region was shorter than its period, take the nearest samples
+        samples = inside or [fields for _, fields in self.samples[-3:]]
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        clocks = sorted(int(s[0]) for s in self.samples)
+        clocks = sorted(int(s[0]) for s in samples)
         reasons = set()
-        for s in self.samples:
+        for s in samples:
             for name, value in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
                 if value.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": int(self.samples[0][1]), "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+        return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": int(samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(samples), "samples_inside_timed_region": len(inside)}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -237,13 +248,13 @@ def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from jellyfysh_b200 import engine, workloads
+    from jellyfysh_b200 import engine, sharding, workloads
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     builder, length = workloads.lennard_jones(n_particles=args.particles, cells_per_side=args.cells, device=local_rank)
-    first_chain = rank * args.chains
+    first_chain, _ = sharding.chain_shard(rank, world, args.chains)
     positions = workloads.lattice_start(args.chains, args.particles, args.cells, length, first_chain=first_chain)
     eng = engine.Engine(builder, n_chains=args.chains, device=local_rank)
     eng.upload_positions(positions)
@@ -255,20 +266,23 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        eng.run(max_events=args.events)
-    eng.sync()
-    launches_before = eng.kernel_launches
-    kernel_seconds_before = eng.kernel_seconds
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:  # nvidia-smi needs ~0.1 s to start: it runs through the warm-up
+        for _ in range(args.warmup):
+            eng.run(max_events=args.events)
+        eng.sync()
+        launches_before = eng.kernel_launches
+        kernel_seconds_before = eng.kernel_seconds
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        clocks.open_window()
         start.record(stream)
         for _ in range(args.steps):
             eng.run(max_events=args.events)
         stop.record(stream)
         stop.synchronize()
         barrier()
+        clocks.close_window()
+        time.sleep(0.05)
     stats = eng.sync()
     elapsed_ms = start.elapsed_time(stop)
     launches = eng.kernel_launches - launches_before
@@ -291,15 +305,12 @@ def run_ours(args, rank, local_rank, world):
     e2e_launches = 4 * args.e2e_steps  # pack, start, events, unpack per call
     assert eng.kernel_launches - e2e_launches_before == args.e2e_steps + 1
 
-    # ---- reduce over ranks: total events, max time
-    totals = torch.tensor([float(stats["events"]), float(e2e_events), float(stats["candidates"])], dtype=torch.float64,
-                          device="cuda")
-    times = torch.tensor([elapsed_ms, e2e_seconds, kernel_seconds], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(totals, op=dist.ReduceOp.SUM)
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_events, total_e2e_events, total_candidates = totals.tolist()
-    max_ms, max_e2e_seconds, max_kernel_seconds = times.tolist()
+    # ---- reduce over ranks (NCCL): event counters are summed, times are the slowest rank's
+    device = torch.device("cuda", local_rank)
+    all_stats = sharding.reduce_counters(stats, device=device)
+    total_e2e_events = int(sharding.reduce_histogram([e2e_events], device=device)[0])
+    max_ms, max_e2e_seconds, _ = sharding.reduce_max([elapsed_ms, e2e_seconds, kernel_seconds], device=device).tolist()
+    total_events = all_stats["events"]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,7 +336,9 @@ def run_ours(args, rank, local_rank, world):
                 "kernel": "ecmc::event_kernel<LJ, 0, LJ>", "algorithmic_bytes_per_event": bytes_per_event,
                 "events_per_launch": events_per_launch, "launch_ms": 1e3 * launch_seconds,
                 "pair_candidates_per_event": pair_candidates,
-                "note": "the kernel is bound by the fp64 pipe, not by HBM: see fp64"}
+                "note": "the chain state is L2-resident and the kernel is bound by instruction issue (a dependent chain of "
+                        "~1000 warp instructions per event, a quarter of them fp64), not by HBM: see fp64 and "
+                        "profiles/"}
     dfma = dfma_peak(local_rank)
     flops_per_event = algorithmic_flops_per_event(pair_candidates)
     achieved_tflops = events_per_launch * flops_per_event / launch_seconds * 1e-12
@@ -333,6 +346,8 @@ def run_ours(args, rank, local_rank, world):
             "frac_algorithmic": None if not dfma else achieved_tflops / dfma,
             "algorithmic_flops_per_event": flops_per_event,
             "ncu_fp64_pipe_utilisation_pct": ncu.get("fp64_pipe_pct"),
+            "ncu_issue_slot_utilisation_pct": ncu.get("issue_active_pct"),
+            "ncu_warp_instructions_per_event": ncu.get("warp_instructions_per_event"),
             "peak_source": "tools/fp64_peak.cu measured in this run (2 flop per DFMA)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -343,8 +358,8 @@ def run_ours(args, rank, local_rank, world):
                     "steps": args.e2e_steps, "call": "ecmc_run_from_host (pinned host buffers; upload, start, run, download)"},
             "gpu_launches": int(launches + e2e_launches),
             "roofline": roofline, "fp64": fp64,
-            "event_mix": {k: stats[k] for k in ("pair_events", "veto_events", "veto_accepted", "boundary_events",
-                                                "end_of_chain_events", "bound_violations")}}
+            "event_mix": {k: all_stats[k] for k in ("pair_events", "veto_events", "veto_accepted", "boundary_events",
+                                                    "end_of_chain_events", "bound_violations")}}
     if world == 1 and not args.no_cpu_baseline:
         baseline = reference_sample(args, args.cpu_seconds)
         if baseline is None:
