@@ -23,6 +23,7 @@ constexpr unsigned kFull = 0xffffffffu;
 #define ECMC_RESIDENT_WARPS 28
 #endif
 constexpr int kSeqNone = 0x7fffffff;
+constexpr int kListCapacity = 128;  // per-warp compact candidate list (targets + sequence numbers: 1 KB)
 
 template <int KIND>
 ECMC_D int resolve_kind(int runtime_kind) { return KIND >= 0 ? KIND : runtime_kind; }
@@ -175,15 +176,41 @@ ECMC_D void count_rare(const RunArgs &A, int lane, int index) {
 
 // SINGLE: the program stores one occupant per cell (the reference's default maximum_number_occupants = 1), which
 // removes the slot arithmetic from the candidate gather.
+// The active particle in the frame of its motion: p0 is the coordinate along the direction of motion, p1 and p2 the
+// following ones cyclically (the order of permutation_3d, base/vectors.py:217-239). Targets are rotated into the same
+// frame once per candidate; everything downstream is free of direction selects.
+struct Moving {
+    double p0, p1, p2, charge;
+};
+ECMC_D Moving rotate_in(const Particle &q, int dir) {
+    Moving m;
+    m.p0 = dir == 0 ? q.x : (dir == 1 ? q.y : q.z);
+    m.p1 = dir == 0 ? q.y : (dir == 1 ? q.z : q.x);
+    m.p2 = dir == 0 ? q.z : (dir == 1 ? q.x : q.y);
+    m.charge = q.charge;
+    return m;
+}
+ECMC_D Particle rotate_out(const Moving &m, int dir) {
+    Particle q;
+    q.x = dir == 0 ? m.p0 : (dir == 1 ? m.p2 : m.p1);
+    q.y = dir == 0 ? m.p1 : (dir == 1 ? m.p0 : m.p2);
+    q.z = dir == 0 ? m.p2 : (dir == 1 ? m.p1 : m.p0);
+    q.charge = m.charge;
+    return q;
+}
+
 template <int CAND, int REAL, int VETO, bool SINGLE, bool RECORD, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     __shared__ double trig_all[UsesMic<REAL, VETO>::value ? WARPS * kTrigDoubles : 1];
+    __shared__ int list_all[WARPS * 2 * kListCapacity];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chain = blockIdx.x * WARPS + warp;
     if (chain >= S.n_chains) return;
     double *trig = UsesMic<REAL, VETO>::value ? trig_all + warp * kTrigDoubles : trig_all;
+    int *list_target = list_all + warp * 2 * kListCapacity;  // compacted candidates of the current event
+    int *list_seq = list_target + kListCapacity;
 
     Particle *part = S.particles + (size_t)chain * P.n_particles;
     const int m = SINGLE ? 1 : P.max_occupants;
@@ -201,7 +228,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     const uint32_t stream = stp->stream;
     bool was_pending = stp->pending_kind != ECMC_EVENT_NONE;  // only the first iteration can start from a kept candidate
     int n_surplus = S.n_surplus[chain];
-    Particle a = part[active];
+    Moving a = rotate_in(part[active], dir);
     // per-axis identifiers of the active cell: scalars, never indexed by a runtime direction (that would put them
     // into local memory)
     int cid0 = (active_cell / P.cumulative[0]) % P.per_side[0];
@@ -210,9 +237,11 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
 
     // lower boundary of the next cell in the direction of motion (cell_boundary_event_handler.py:135-156); 0.0 when
     // the active cell is the last one of its row. Reloaded whenever the active cell or the direction changes.
+    int next_cell = 0;  // flat index of that cell
     auto next_boundary = [&]() {
-        int nid = (dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2)) + 1;
-        if (nid >= P.per_side[dir]) nid = 0;
+        const int id = dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2);
+        const int nid = id + 1 == P.per_side[dir] ? 0 : id + 1;
+        next_cell = active_cell + (nid - id) * P.cumulative[dir];
         return __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
     };
     double boundary = next_boundary();
@@ -245,20 +274,26 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             kept_position = stp->pending_position;
             kept_stamp.q = stp->pending_stamp_q; kept_stamp.r = stp->pending_stamp_r;
         } else {
-            // Slot layout of one event: slot 0 = cell veto, slot 1 = cell boundary, slots 2.. = pair candidates (nearby
-            // cells x occupant slots, then the surplus list). Lanes take slots in passes of 32; pass 0 does the two
-            // special candidates next to 30 pair slots, which covers a 3^3 neighbourhood plus 3 surplus particles.
-            // The sequence number that breaks ties follows the oracle's scan: pairs, veto, boundary.
+            // Candidate gather: the occupant slots of the nearby cells, then the surplus list, are scanned 32 at a time
+            // and the occupied ones are compacted (ballot + popc) into a per-warp list in shared memory. The list is
+            // then worked off in passes of 32 lanes; the first pass also carries the two special candidates (lane 0
+            // cell veto, lane 1 cell boundary), so 30 real pair candidates -- the ~16 occupied nearby cells of a dense
+            // liquid plus ~14 surplus particles -- cost one pass. The sequence number that breaks ties follows the
+            // oracle's scan: pair slots in scan order, veto, boundary.
             const int nearby_slots = has_pairs ? P.n_nearby * m : 0;
             const int n_pair_slots = has_pairs ? nearby_slots + n_surplus : 0;
             const double c_active = P.pair_use_charge ? a.charge : 1.0;
             unsigned long long best_key = 0x7ff0000000000000ull;  // best of the passes so far (uniform)
             double best_x = INFINITY;
             int best_seq = kSeqNone;
-            for (int base = 0; base < n_pair_slots + 2; base += 32) {
-                const int s = base + lane - 2;  // pair slot index; -2 = veto, -1 = boundary
-                int target = -1;
-                if (s >= 0 && s < nearby_slots) {
+            int cursor = 0;      // next slot to scan
+            bool first = true;   // the special candidates have not been processed yet
+            while (first || cursor < n_pair_slots) {
+              int count = 0;  // entries in the compact list
+              while (cursor < n_pair_slots && count <= kListCapacity - 32) {
+                const int s = cursor + lane;
+                int found = -1;
+                if (s < nearby_slots) {
                     const int ci = m == 1 ? s : s / m;
                     const int code = __ldg(P.nearby + ci);
                     int x = cid0 + (code & 1023), y = cid1 + ((code >> 10) & 1023), z = cid2 + (code >> 20);
@@ -266,15 +301,30 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     if (y >= P.per_side[1]) y -= P.per_side[1];
                     if (z >= P.per_side[2]) z -= P.per_side[2];
                     const int cell = x * P.cumulative[0] + y * P.cumulative[1] + z * P.cumulative[2];
-                    target = occ[cell * m + (s - ci * m)];
-                } else if (s >= nearby_slots && s < n_pair_slots) {
-                    target = sur[s - nearby_slots];
+                    found = occ[cell * m + (s - ci * m)];
+                } else if (s < n_pair_slots) {
+                    found = sur[s - nearby_slots];
                 }
+                const unsigned occupied = __ballot_sync(kFull, found >= 0);
+                if (found >= 0) {
+                    const int rank = count + __popc(occupied & ((1u << lane) - 1u));
+                    list_target[rank] = found;
+                    list_seq[rank] = s;
+                }
+                count += __popc(occupied);
+                cursor += 32;
+              }
+              __syncwarp();
+              const int shift = first ? 2 : 0;
+              for (int base = 0; base < count + shift; base += 32) {
+                const int entry = base + lane - shift;  // -2 = veto, -1 = boundary
+                int target = -1, s = -1;
+                if (entry >= 0 && entry < count) { target = list_target[entry]; s = list_seq[entry]; }
                 const bool is_pair = target >= 0;
-                const bool is_veto = s == -2 && has_veto;
-                const bool is_boundary = s == -1;
-                Particle tp;
-                if (is_pair) tp = part[target];
+                const bool is_veto = entry == -2 && has_veto;
+                const bool is_boundary = entry == -1;
+                Moving tp;
+                if (is_pair) tp = rotate_in(part[target], dir);
                 // One Philox block per lane, all lanes together: pair lanes draw their potential change (slot keyed
                 // by the target), the veto lane its (Walker uniform, time) pair, and the boundary lane -- which needs
                 // no random number -- computes the veto lane's table-index words.
@@ -292,10 +342,10 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 int kind = ECMC_EVENT_NONE, cell = -1, seq = kSeqNone;
                 double rate = 0.0;
                 if (is_pair) {
-                    const double sx = correct_separation_in_box(tp.x - a.x, L, half);
-                    const double sy = correct_separation_in_box(tp.y - a.y, L, half);
-                    const double sz = correct_separation_in_box(tp.z - a.z, L, half);
-                    dt = displacement_time<CAND>(P.cand_potential, dir, P.inv_speed, L, sx, sy, sz, c_active,
+                    const double s0 = correct_separation_in_box(tp.p0 - a.p0, L, half);
+                    const double s1 = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                    const double s2 = correct_separation_in_box(tp.p2 - a.p2, L, half);
+                    dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c_active,
                                                  P.pair_use_charge ? tp.charge : 1.0, cand_needs_du ? exponential : 0.0);
                     kind = ECMC_EVENT_PAIR;
                     seq = s;
@@ -353,11 +403,10 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     seq = n_pair_slots;
                 } else if (is_boundary) {
                     // CellBoundaryEventHandler.send_event_time (cell_boundary_event_handler.py:122-156)
-                    double separation = boundary - component(a, dir);
+                    double separation = boundary - a.p0;
                     if (separation < 0.0) separation = separation + L;  // next_image, hypercubic_setting.py:191
                     dt = separation * P.inv_speed;
-                    const int id = dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2);
-                    cell = active_cell + ((id + 1 == P.per_side[dir] ? 0 : id + 1) - id) * P.cumulative[dir];
+                    cell = next_cell;
                     kind = ECMC_EVENT_CELL_BOUNDARY;
                     seq = n_pair_slots + 1;
                 }
@@ -378,6 +427,9 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     bcell = __shfl_sync(kFull, cell, owner);
                     brate = __shfl_sync(kFull, rate, owner);
                 }
+              }
+              first = false;
+              __syncwarp();
             }
             if (best_seq != kSeqNone) {
                 const double fl = floor(best_x);
@@ -400,7 +452,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 stp->pending_rate = brate;
                 stp->pending_target = bkind == ECMC_EVENT_PAIR ? btarget : bcell;
                 if (!was_pending) {
-                    stp->pending_position = component(a, dir);
+                    stp->pending_position = a.p0;
                     stp->pending_stamp_q = now.q; stp->pending_stamp_r = now.r;
                 }
             }
@@ -411,22 +463,22 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             if (lane == 0) stp->pending_kind = ECMC_EVENT_NONE;
             if (kind != ECMC_EVENT_END_OF_CHAIN) {
                 // the kept handler's in-state predates the control event's time slice
-                set_component(a, dir, kept_position);
+                a.p0 = kept_position;
                 now = kept_stamp;
             }
             was_pending = false;
         }
 
         // ---- out-state: time slice of the active particle (event_handler/abstracts/abstracts.py:82-95)
-        const double x_before = component(a, dir);
+        const double x_before = a.p0;
         {
             const double dt = time_sub(event_time, now);
-            set_component(a, dir, correct_position_entry(__dadd_rn(x_before, __dmul_rn(speed, dt)), L));
+            a.p0 = correct_position_entry(__dadd_rn(x_before, __dmul_rn(speed, dt)), L);
             now = event_time;
         }
         // Did the time slice itself carry the particle out of its cell (without a boundary event)? Cell `id` holds
         // exactly the doubles in [cell_min[id], cell_min[id + 1]) and the particle only moves forward.
-        const bool left_cell = boundary == 0.0 ? component(a, dir) < x_before : component(a, dir) >= boundary;
+        const bool left_cell = boundary == 0.0 ? a.p0 < x_before : a.p0 >= boundary;
         int new_active = active, accepted = 0, rec_target = -1;
         switch (kind) {
         case ECMC_EVENT_PAIR: {
@@ -436,13 +488,13 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             } else {
                 // two_leaf_unit_bounding_potential_event_handler.py:148-168 +
                 // event_handler_with_bounding_potential.py:75-101
-                const Particle tp = part[btarget];
-                const double sx = correct_separation_in_box(tp.x - a.x, L, half);
-                const double sy = correct_separation_in_box(tp.y - a.y, L, half);
-                const double sz = correct_separation_in_box(tp.z - a.z, L, half);
+                const Moving tp = rotate_in(part[btarget], dir);
+                const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
+                const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
                 const double c1 = P.pair_use_charge ? a.charge : 1.0, c2 = P.pair_use_charge ? tp.charge : 1.0;
-                const double bounding_rate = derivative_warp<CAND>(P.cand_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
-                const double real = derivative_warp<REAL>(P.real_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
+                const double bounding_rate = derivative_warp<CAND>(P.cand_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
+                const double real = derivative_warp<REAL>(P.real_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
                     if (bounding_rate < real) count_rare(A, lane, 7);
                     const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
@@ -458,12 +510,12 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             const int t = occ[bcell * m];
             rec_target = t;
             if (t >= 0) {
-                const Particle tp = part[t];
-                const double sx = correct_separation_in_box(tp.x - a.x, L, half);
-                const double sy = correct_separation_in_box(tp.y - a.y, L, half);
-                const double sz = correct_separation_in_box(tp.z - a.z, L, half);
+                const Moving tp = rotate_in(part[t], dir);
+                const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
+                const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
                 const double c1 = P.veto_use_charge ? a.charge : 1.0, c2 = P.veto_use_charge ? tp.charge : 1.0;
-                const double real = derivative_warp<VETO>(P.veto_potential, dir, speed, sx, sy, sz, c1, c2, trig, lane);
+                const double real = derivative_warp<VETO>(P.veto_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
                     if (brate < real) count_rare(A, lane, 7);
                     const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
@@ -476,7 +528,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         }
         case ECMC_EVENT_CELL_BOUNDARY: {
             // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
-            set_component(a, dir, boundary);
+            a.p0 = boundary;
             break;
         }
         case ECMC_EVENT_END_OF_CHAIN:
@@ -496,27 +548,33 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % P.dimension : dir;
             rec.reserved = 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
-            rec.active_pos[0] = a.x; rec.active_pos[1] = a.y; rec.active_pos[2] = a.z;
+            const Particle lab = rotate_out(a, dir);
+            rec.active_pos[0] = lab.x; rec.active_pos[1] = lab.y; rec.active_pos[2] = lab.z;
             A.records[(size_t)chain * A.records_per_chain + n.events] = rec;
         }
         ev++;
         n.events++;
         n.candidates += (unsigned long long)n_cand;
+        Particle lab;  // the old active particle in the lab frame, where the rare paths below need it
+        const bool needs_lab = new_active != active || kind == ECMC_EVENT_CELL_BOUNDARY ||
+                               kind == ECMC_EVENT_END_OF_CHAIN || left_cell;
+        if (needs_lab) lab = rotate_out(a, dir);
         if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir + 1 == P.dimension ? 0 : dir + 1;
 
         // ---- SingleActiveCellOccupancy.update (single_active_cell_occupancy.py:149-203)
         if (new_active != active) {
             int delta = 0;
             if (lane == 0) {
-                part[active] = a;
+                part[active] = lab;
                 delta = occupancy_insert(occ, sur, n_surplus, m, P.max_surplus, active_cell, active);
             }
             delta = __shfl_sync(kFull, delta, 0);
             if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
             __syncwarp();
             active = new_active;
-            a = part[active];
-            cell_identifier_of(P, a, cid0, cid1, cid2);
+            lab = part[active];
+            a = rotate_in(lab, dir);
+            cell_identifier_of(P, lab, cid0, cid1, cid2);
             active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
             delta = 0;
             if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, m, active_cell, active);
@@ -526,7 +584,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             boundary = next_boundary();
         } else if (kind == ECMC_EVENT_CELL_BOUNDARY || kind == ECMC_EVENT_END_OF_CHAIN || left_cell) {
             // the oracle recomputes the cell from the position after every event; only these can change it
-            cell_identifier_of(P, a, cid0, cid1, cid2);
+            a = rotate_in(lab, dir);
+            cell_identifier_of(P, lab, cid0, cid1, cid2);
             active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
             boundary = next_boundary();
         }
@@ -542,11 +601,11 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     if (stopped_by_time) {
         // the sampling / end-of-run handler time-slices the active unit (fixed_interval_sampling_event_handler.py:96-109)
         const double dt = time_sub(until, now);
-        set_component(a, dir, correct_position_entry(__dadd_rn(component(a, dir), __dmul_rn(speed, dt)), L));
+        a.p0 = correct_position_entry(__dadd_rn(a.p0, __dmul_rn(speed, dt)), L);
         now = until;
     }
     if (lane == 0) {
-        part[active] = a;
+        part[active] = rotate_out(a, dir);
         stp->active = active; stp->direction = dir;
         stp->time_q = now.q; stp->time_r = now.r;
         stp->eoc_q = eoc.q; stp->eoc_r = eoc.r;

@@ -146,8 +146,8 @@ ECMC_HD double correct_separation_entry(double s, double L, double half) { retur
 // the same for two positions inside the box, |s| < L: s + L/2 lies in (-L/2, 3L/2) and the modulo is one select
 ECMC_HD double correct_separation_in_box(double s, double L, double half) {
     const double x = s + half;
-    const double m = x < 0.0 ? x + L : (x >= L ? x - L : x);
-    return m - half;
+    const double shift = x < 0.0 ? L : (x >= L ? -L : 0.0);
+    return (x + shift) - half;
 }
 ECMC_HD double correct_position_entry(double x, double L) { return py_mod(x, L); }
 
