@@ -67,6 +67,18 @@ ECMC_D double displacement_time(const PotentialParams &p, int dir, double inv_sp
     }
 }
 
+// Can this pair candidate fire at all? `du_lower` = u / beta is a lower bound of the potential change the candidate
+// will draw (-log(1 - u) >= u). True only if the displacement is certainly infinite -- then the candidate never enters
+// the scheduler (heap_scheduler.py:139) and its logarithm and inversion need not be computed. Separation in the frame
+// of motion (s0 along the direction).
+template <int KIND>
+ECMC_D bool certainly_dead(const PotentialParams &p, double s0, double s1, double s2, double du_lower) {
+    switch (resolve_kind<KIND>(p.kind)) {
+    case ECMC_POT_LENNARD_JONES: return lj_certainly_dead(p.lj, s0, fma(s1, s1, s2 * s2), du_lower);
+    default: return false;
+    }
+}
+
 // Potential.derivative(velocity, separation, charges) (potential/abstracts.py:80-103). Warp-collective: all 32
 // lanes call it with identical arguments (the merged-image Coulomb sum is spread over the lanes).
 template <int KIND>
@@ -332,6 +344,20 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                                               : (is_boundary ? ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0) : ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0));
                 Philox4 b = stream_block(key, slot, 0);
                 const double u_first = words_to_double(b.w[0], b.w[1]), u_second = words_to_double(b.w[2], b.w[3]);
+                // Passes after the first hold surplus particles only, scattered over the whole box: most of them
+                // cannot fire (their potential change exceeds the depth of the attractive tail), which one division
+                // decides. If that holds for every lane the pass ends here, without logarithm and inversion.
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                if (is_pair) {
+                    s0 = correct_separation_in_box(tp.p0 - a.p0, L, half);
+                    s1 = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                    s2 = correct_separation_in_box(tp.p2 - a.p2, L, half);
+                }
+                if (base > 0 || !first) {
+                    const bool alive = is_pair && !certainly_dead<CAND>(P.cand_potential, s0, s1, s2,
+                                                                        cand_needs_du ? u_first * P.inv_beta : 0.0);
+                    if (!__any_sync(kFull, alive)) continue;
+                }
                 // random.expovariate(beta): pair lanes use their first double, the veto lane its second
                 const double exponential = -log(1.0 - (is_veto ? u_second : u_first)) * P.inv_beta;
                 // the table-index words travel from the boundary lane (lane 1 of pass 0) to the veto lane (lane 0)
@@ -342,9 +368,6 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 int kind = ECMC_EVENT_NONE, cell = -1, seq = kSeqNone;
                 double rate = 0.0;
                 if (is_pair) {
-                    const double s0 = correct_separation_in_box(tp.p0 - a.p0, L, half);
-                    const double s1 = correct_separation_in_box(tp.p1 - a.p1, L, half);
-                    const double s2 = correct_separation_in_box(tp.p2 - a.p2, L, half);
                     dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c_active,
                                                  P.pair_use_charge ? tp.charge : 1.0, cand_needs_du ? exponential : 0.0);
                     kind = ECMC_EVENT_PAIR;

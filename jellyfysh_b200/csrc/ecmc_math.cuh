@@ -232,6 +232,21 @@ ECMC_D double lj_displacement(const LennardJones &p, double sd, double perp2, do
     return inner ? sd - s : sd + s;
 }
 
+// Cheap exclusion test for lj_displacement: a candidate that does not climb the repulsive core (stretch (1)) starts
+// stretch (2) at an energy u_start < 0 and escapes to infinity if its potential change exceeds -u_start. With a lower
+// bound of that potential change this needs one division and no logarithm / root. The margin keeps the test
+// strictly on the safe side of rounding: anything close to the threshold goes through the full computation.
+ECMC_D bool lj_certainly_dead(const LennardJones &p, double sd, double perp2, double du_lower) {
+    const bool approaching = sd > 0.0;
+    if (approaching && perp2 < p.r0sq) return false;  // hits the minimum sphere: climbs the core
+    const double r2 = approaching ? perp2 : fma(sd, sd, perp2);  // where stretch (2) starts
+    if (r2 < p.r0sq) return du_lower > -p.u_min * (1.0 + 1.0e-9);
+    const double x = p.sigma2 / r2;
+    const double x3 = x * x * x;
+    const double u_start = p.k * x3 * (x3 - 1.0);
+    return du_lower > -u_start * (1.0 + 1.0e-9);
+}
+
 // ---- hard sphere / hard dipole, general velocity (hard_sphere_potential.py:65-99, hard_dipole_potential.py:75-114)
 // Grazing collisions make the square-root term cancel to ~0, where one ulp of its inputs decides between a hit
 // and a miss. These few operations therefore follow the reference operation by operation: products and sums
