@@ -34,7 +34,7 @@ class _Stop(Exception):
 
 
 def _run_one(args):
-    ini_text, positions, seed, warmup_seconds, budget_seconds = args
+    ini_text, positions, seed, warmup_seconds, budget_seconds, segments = args
     sys.path.insert(0, REF_ROOT)
     import warnings
     warnings.filterwarnings("ignore")
@@ -54,7 +54,7 @@ def _run_one(args):
     init_seconds = time.perf_counter() - t_init
     scheduler = mediator._scheduler
     original = scheduler.get_succeeding_event
-    state = {"events": 0, "t0": None, "counted_from": None, "deadline": None}
+    state = {"events": 0, "t0": None, "deadline": None, "done": []}
     started = time.perf_counter()
 
     def get_succeeding_event():
@@ -67,8 +67,10 @@ def _run_one(args):
         if any(tag in type(winner).__name__ for tag in INTERACTION_HANDLERS):
             state["events"] += 1
         if state["deadline"] is not None and now >= state["deadline"]:
-            state["elapsed"] = now - state["t0"]
-            raise _Stop()
+            state["done"].append((state["events"], now - state["t0"]))  # one timed segment
+            if len(state["done"]) >= segments:
+                raise _Stop()
+            state["t0"], state["deadline"], state["events"] = now, now + budget_seconds, 0
         return winner
 
     scheduler.get_succeeding_event = get_succeeding_event
@@ -77,19 +79,28 @@ def _run_one(args):
             mediator.run()
     except _Stop:
         pass
-    return state["events"], state["elapsed"], init_seconds
+    return state["done"], init_seconds
 
 
-def run(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0):
-    """Run one chain per entry of positions_per_process in parallel processes.
-    Returns (events per second summed over processes, processes, events, mean init seconds)."""
-    jobs = [(ini_text, positions, 1000 + k, warmup_seconds, budget_seconds)
+def run_segments(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0, segments=1):
+    """One chain per entry of positions_per_process in parallel processes, `segments` consecutive timed segments of
+    budget_seconds each after the warm-up. Returns ([events/s summed over processes per segment], processes,
+    total events, mean init seconds)."""
+    jobs = [(ini_text, positions, 1000 + k, warmup_seconds, budget_seconds, segments)
             for k, positions in enumerate(positions_per_process)]
     context = multiprocessing.get_context("spawn")
     with context.Pool(len(jobs)) as pool:
         results = pool.map(_run_one, jobs)
-    rate = sum(events / elapsed for events, elapsed, _ in results)
-    return rate, len(jobs), sum(r[0] for r in results), sum(r[2] for r in results) / len(results)
+    rates = [sum(done[k][0] / done[k][1] for done, _ in results) for k in range(segments)]
+    events = sum(events for done, _ in results for events, _ in done)
+    return rates, len(jobs), events, sum(init for _, init in results) / len(results)
+
+
+def run(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0):
+    """Single timed segment: (events per second summed over processes, processes, events, mean init seconds)."""
+    rates, processes, events, init_seconds = run_segments(ini_text, positions_per_process, warmup_seconds,
+                                                          budget_seconds, 1)
+    return rates[0], processes, events, init_seconds
 
 
 if __name__ == "__main__":

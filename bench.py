@@ -178,25 +178,36 @@ def port_sample(args, builder, length, seconds):
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the CPU reference on the host cores, rank 0 only. One pool of processes (one chain per core)
+    runs the warm-up steps and the K timed steps back to back; a step is a bounded wall-clock segment."""
     if rank != 0:
         return
-    seconds = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
-    values = []
-    sample = None
-    for step in range(args.warmup + args.steps):
-        sample = reference_sample(args, seconds)
-        if sample is None:
-            break
-        if step >= args.warmup:
-            values.append(sample["value"])
-    if sample is None:
-        # no installed reference on this box: fall back to the C port of its algorithm
-        from jellyfysh_b200 import workloads
+    steps = args.warmup + args.steps
+    seconds = max(0.5, min(20.0, 60.0 / steps))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import configs
+    import reference_runner
+    from jellyfysh_b200 import workloads
+    cores = os.cpu_count() or 1
+    length = float((args.particles / 0.5) ** (1.0 / 3.0))
+    if reference_runner.available():
+        ini = configs.lennard_jones_ini(args.particles, length, args.cells, chain_time=10.0)
+        positions = workloads.lattice_start(cores, args.particles, args.cells, length)
+        rates, processes, events, init_seconds = reference_runner.run_segments(
+            ini, list(positions), warmup_seconds=0.0, budget_seconds=seconds, segments=steps)
+        value = sum(rates[args.warmup:]) / args.steps
+        sample = {"value": value, "unit": UNIT, "cores": processes, "kind": "reference",
+                  "sample": "unmodified JeLLyFysh 1.1 (baseline/_ref, CPython %d.%d) single_process_mediator, one chain "
+                            "of the same workload per core, %d warm-up + %d timed segments of %.1f s: %d events; init "
+                            "%.1f s per process not counted"
+                            % (sys.version_info[0], sys.version_info[1], args.warmup, args.steps, seconds, events,
+                               init_seconds)}
+    else:
+        # no installed reference on this box: the C port of its algorithm (oracle) instead
         builder, length = workloads.lennard_jones(n_particles=args.particles, cells_per_side=args.cells)
         sample = port_sample(args, builder, length, seconds)
-        values = [sample["value"]]
-    value = sum(values) / len(values)
-    sample["value"] = value
+        value = sample["value"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * seconds, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
