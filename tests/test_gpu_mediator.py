@@ -101,3 +101,48 @@ def test_many_chains_from_the_input_handler(tmp_path):
     assert stats["events"] > chains * 100
     assert np.all(states["time_q"] == 1.0) and np.all(states["time_r"] == 0.0)
     assert len(set(states["event_counter"].tolist())) > 1  # the chains are different
+
+
+def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path):
+    """The statistical check of the reference (README.md:169-189): the shipped coulomb_atoms/cell_veto.ini, run
+    unchanged except for the mediator line, the output file and the run length, must reproduce the cumulative
+    histogram of the pair separation that the reference ships (ReferenceDataCoulombAtoms.dat, reversible Monte Carlo;
+    fixture tests/golden/reference_cdfs.npz). 2048 chains in parallel give ~10^5 samples in a few seconds."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import kat_replay as kr
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    from jellyfysh.base.exceptions import EndOfRun
+    path = os.path.join(REF, "jellyfysh", "config_files", "2018_JCP_149_064113", "coulomb_atoms", "cell_veto.ini")
+    ini = open(path).read()
+    chains = 2048
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 11" % chains)
+    ini = ini.replace("end_of_run_time = 100000", "end_of_run_time = 40")
+    ini = ini.replace("output/2018_JCP_149_064113/coulomb_atoms/SamplesOfSeparation_CellVeto.dat",
+                      str(tmp_path / "separation.dat"))
+    assert "cuda_batched_mediator" in ini and str(tmp_path) in ini
+    mediator, setting = build_reference_graph(ini)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["bound_violations"] == 0 and stats["capacity_errors"] == 0
+    samples = np.loadtxt(tmp_path / "separation.dat", comments="#")
+    per_chain = int(40 / 0.56789)
+    assert len(samples) == chains * per_chain
+    samples = samples.reshape(per_chain, chains)[10:].ravel()  # drop the first samples of every chain (random start)
+    g = kr.load_npz("reference_cdfs")
+    x, cdf = g["coulomb_atoms_x"], g["coulomb_atoms_cdf"]
+    edges = x + 0.5 * (x[1] - x[0])  # the fixture tabulates the cumulative histogram at bin centres
+    ours = np.searchsorted(np.sort(samples), edges, side="right") / len(samples)
+    distance = np.max(np.abs(ours - cdf))
+    # Kolmogorov-Smirnov: 1.95 / sqrt(n) at the 0.1 % level for n independent samples; consecutive samples of a chain are
+    # correlated, so n is taken as the number of chains times a conservative 10 independent samples each
+    assert distance < 1.95 / np.sqrt(chains * 10) + 1.0e-3, distance
+    assert 0.2 < np.median(samples) < 0.8
