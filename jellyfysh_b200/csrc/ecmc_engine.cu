@@ -20,7 +20,10 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef ECMC_WARPS_PER_BLOCK
+#define ECMC_WARPS_PER_BLOCK 4
+#endif
+constexpr int kWarpsPerBlock = ECMC_WARPS_PER_BLOCK;
 
 struct EventPair {
     cudaEvent_t start, stop;
@@ -35,6 +38,7 @@ struct EcmcHandle {
     DeviceProgram dprog{};
     DeviceState state{};
     cudaStream_t stream = nullptr;
+    std::vector<cudaStream_t> slice_streams;  // ecmc_run_from_host pipelines chain slices over these
     std::vector<void *> allocations;
     EcmcStats *d_stats = nullptr;
     EcmcStats *h_stats = nullptr;     // pinned
@@ -440,6 +444,7 @@ ECMC_API void ecmc_destroy(EcmcHandle *h) {
     for (EventPair &e : h->free_events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
     for (void *p : h->allocations) cudaFree(p);
     if (h->h_stats) cudaFreeHost(h->h_stats);
+    for (cudaStream_t s : h->slice_streams) cudaStreamDestroy(s);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -471,6 +476,7 @@ ECMC_API int ecmc_create(const EcmcProgram *program, int device, int n_chains, E
         const DeviceProgram &d = h->dprog;
         const size_t n = (size_t)n_chains * d.n_particles;
         h->state.n_chains = n_chains;
+        h->state.first_chain = 0;
         if ((rc = device_alloc(h, &h->state.particles, n))) break;
         if ((rc = device_alloc(h, &h->state.occupants, (size_t)n_chains * d.n_cells * d.max_occupants))) break;
         if ((rc = device_alloc(h, &h->state.surplus, (size_t)n_chains * d.max_surplus))) break;
@@ -637,15 +643,71 @@ ECMC_API int ecmc_run_recorded(EcmcHandle *h, double until_q, double until_r, in
     return rc ? rc : rc_sync;
 }
 
+// Host buffers in, host buffers out. The chains are cut into slices; every slice runs its own
+// H2D -> pack -> start -> events -> unpack -> D2H sequence on its own stream, so the copies of one slice overlap the
+// event kernels of the others (the kernels of different slices run concurrently: a slice fills only part of the GPU).
 ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
                                 double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
                                 EcmcStats *stats) {
-    int rc = ecmc_upload_positions(h, positions_in, charges);
-    if (!rc) rc = ecmc_start(h, nullptr, first_stream);
-    if (!rc) rc = ecmc_run(h, until_q, until_r, max_events_per_chain);
-    if (!rc && positions_out) rc = ecmc_download_positions(h, positions_out);
-    const int rc_sync = h ? ecmc_sync(h, stats) : ECMC_ERR_INVALID;
-    return rc ? rc : rc_sync;
+    if (!h || !positions_in) return fail(h, ECMC_ERR_INVALID, "null argument");
+    if (std::isnan(until_q) || std::isnan(until_r)) return fail(h, ECMC_ERR_INVALID, "until time is NaN");
+    if (max_events_per_chain <= 0 && std::isinf(until_q))
+        return fail(h, ECMC_ERR_INVALID, "neither a time limit nor an event limit: the run would not end");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const DeviceProgram &d = h->dprog;
+    int max_slices = 4;
+    if (const char *env = std::getenv("ECMC_HOST_SLICES")) max_slices = std::max(1, std::atoi(env));
+    const int slices = std::max(1, std::min(max_slices, h->n_chains / 256));
+    while ((int)h->slice_streams.size() < slices) {
+        cudaStream_t s;
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        h->slice_streams.push_back(s);
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // earlier work on the handle's stream comes first
+    RunArgs args;
+    args.until_q = until_q;
+    args.until_r = until_r;
+    args.max_events = max_events_per_chain;
+    args.records = nullptr;
+    args.records_per_chain = 0;
+    args.stats = h->d_stats;
+    const EventKernel kernel = pick_kernel(d, false);
+    const size_t per_chain = (size_t)d.n_particles;
+    const int base = h->n_chains / slices, extra = h->n_chains % slices;
+    int first = 0;
+    for (int k = 0; k < slices; k++) {
+        const int count = base + (k < extra ? 1 : 0);
+        cudaStream_t s = h->slice_streams[k];
+        const size_t offset = (size_t)first * per_chain, n = (size_t)count * per_chain;
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_staging + offset * d.dimension, positions_in + offset * d.dimension,
+                                    n * d.dimension * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (charges)
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_staging_charges + offset, charges + offset, n * sizeof(double),
+                                        cudaMemcpyHostToDevice, s));
+        const int copy_blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 4);
+        pack_particles_kernel<<<copy_blocks, 256, 0, s>>>(h->d_staging + offset * d.dimension,
+                                                          charges ? h->d_staging_charges + offset : nullptr,
+                                                          h->state.particles + offset, n, d.dimension);
+        DeviceState slice = h->state;
+        slice.first_chain = first;
+        slice.n_chains = count;
+        const int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, s>>>(
+            d, slice, nullptr, first_stream, h->program.initial_active, h->program.initial_direction, h->d_stats);
+        kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(d, slice, args);
+        CUDA_TRY(h, cudaGetLastError());
+        h->kernel_launches++;
+        if (positions_out) {
+            unpack_particles_kernel<<<copy_blocks, 256, 0, s>>>(h->state.particles + offset,
+                                                                h->d_staging + offset * d.dimension, n, d.dimension);
+            CUDA_TRY(h, cudaMemcpyAsync(positions_out + offset * d.dimension, h->d_staging + offset * d.dimension,
+                                        n * d.dimension * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        first += count;
+    }
+    for (int k = 0; k < slices; k++) CUDA_TRY(h, cudaStreamSynchronize(h->slice_streams[k]));
+    h->started = true;
+    return ecmc_sync(h, stats);
 }
 
 ECMC_API void *ecmc_stream(EcmcHandle *h) { return h ? (void *)h->stream : nullptr; }

@@ -218,8 +218,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     __shared__ int list_all[WARPS * 2 * kListCapacity];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int chain = blockIdx.x * WARPS + warp;
-    if (chain >= S.n_chains) return;
+    const int chain = S.first_chain + blockIdx.x * WARPS + warp;
+    if (chain >= S.first_chain + S.n_chains) return;
     double *trig = UsesMic<REAL, VETO>::value ? trig_all + warp * kTrigDoubles : trig_all;
     int *list_target = list_all + warp * 2 * kListCapacity;  // compacted candidates of the current event
     int *list_seq = list_target + kListCapacity;
@@ -275,6 +275,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         int bkind = ECMC_EVENT_NONE, btarget = -1, bcell = -1;
         double brate = 0.0;
         int n_cand = 0;
+        bool have_confirmation = false;  // the confirmation draw of this event is already known
+        double u_confirmation = 0.0;
         double kept_position = 0.0;
         Time kept_stamp = now;
         if (was_pending) {
@@ -340,10 +342,19 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 // One Philox block per lane, all lanes together: pair lanes draw their potential change (slot keyed
                 // by the target), the veto lane its (Walker uniform, time) pair, and the boundary lane -- which needs
                 // no random number -- computes the veto lane's table-index words.
+                // If the last lane of the first pass is idle it draws the confirmation number of the out-state ahead
+                // of time (slot CONFIRM): a third of all events need it, and here it costs nothing.
+                const bool draws_confirmation = first && base == 0 && lane == 31 && !is_pair;
                 const uint32_t slot = is_pair ? ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target)
-                                              : (is_boundary ? ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0) : ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0));
+                                              : (is_boundary ? ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0)
+                                                             : (draws_confirmation ? ECMC_SLOT(ECMC_SLOT_CONFIRM, 0)
+                                                                                   : ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0)));
                 Philox4 b = stream_block(key, slot, 0);
                 const double u_first = words_to_double(b.w[0], b.w[1]), u_second = words_to_double(b.w[2], b.w[3]);
+                if (first && base == 0) {
+                    have_confirmation = __shfl_sync(kFull, (int)draws_confirmation, 31) != 0;
+                    u_confirmation = __shfl_sync(kFull, u_first, 31);
+                }
                 // Passes after the first hold surplus particles only, scattered over the whole box: most of them
                 // cannot fire (their potential change exceeds the depth of the attractive tail), which one division
                 // decides. If that holds for every lane the pass ends here, without logarithm and inversion.
@@ -359,7 +370,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     if (!__any_sync(kFull, alive)) continue;
                 }
                 // random.expovariate(beta): pair lanes use their first double, the veto lane its second
-                const double exponential = -log(1.0 - (is_veto ? u_second : u_first)) * P.inv_beta;
+                const double exponential = -log_unit_interval(1.0 - (is_veto ? u_second : u_first)) * P.inv_beta;
                 // the table-index words travel from the boundary lane (lane 1 of pass 0) to the veto lane (lane 0)
                 uint32_t choice[4];
 #pragma unroll
@@ -520,7 +531,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const double real = derivative_warp<REAL>(P.real_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
                     if (bounding_rate < real) count_rare(A, lane, 7);
-                    const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+                    const double u = have_confirmation ? u_confirmation : stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
                     if (0.0 + (bounding_rate - 0.0) * u < real) accepted = 1;
                 }
             }
@@ -541,7 +552,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const double real = derivative_warp<VETO>(P.veto_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
                     if (brate < real) count_rare(A, lane, 7);
-                    const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+                    const double u = have_confirmation ? u_confirmation : stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
                     if (0.0 + (brate - 0.0) * u < real) { accepted = 1; new_active = t; }
                 }
             }
@@ -658,8 +669,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams, uint32_t first_stream,
              int initial_active, int initial_direction, EcmcStats *stats) {
     const int lane = threadIdx.x & 31;
-    const int chain = blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (chain >= S.n_chains) return;
+    const int chain = S.first_chain + blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (chain >= S.first_chain + S.n_chains) return;
     Particle *part = S.particles + (size_t)chain * P.n_particles;
     const int m = P.max_occupants;
     int *occ = S.occupants + (size_t)chain * P.n_cells * m;

@@ -91,6 +91,31 @@ ECMC_HD uint32_t stream_randbelow(const StreamKey &k, uint32_t slot, uint32_t n)
 // random.expovariate(beta) = -log(1 - u) / beta
 ECMC_D double expovariate(double u, double beta) { return -log(1.0 - u) / beta; }
 
+// Natural logarithm for the argument range of expovariate, x = 1 - u in [2^-53, 1]: normal, positive, finite, so the
+// special-case handling of the library routine (zero, negative, denormal, infinity, NaN) is dropped. Classic
+// argument reduction x = 2^k m with m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(s) with s = (m - 1) / (m + 1) as an odd
+// polynomial in s (Remez coefficients of FreeBSD's e_log.c, error < 1 ulp), k ln 2 added in two parts.
+ECMC_D double log_unit_interval(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int carry = (hi + 0x95f64) & 0x100000;  // mantissa above sqrt(2): halve it, bump the exponent
+    k += carry >> 20;
+    const double m = __hiloint2double(hi | (carry ^ 0x3ff00000), lo);
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
+                                     2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double r = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + r, dk * 1.90821492927058770002e-10)) - f);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Time as (quotient, remainder), jellyfysh/base/time.py. Time displacements here are >= 0.
 // ---------------------------------------------------------------------------------------------------------

@@ -79,7 +79,8 @@ struct DeviceState {
     int *surplus;
     int *n_surplus;
     EcmcChainState *chains;
-    int n_chains;
+    int n_chains;      // chains of this launch ...
+    int first_chain;   // ... starting at this one (launches on chain slices overlap copies with compute)
 };
 
 struct RunArgs {
