@@ -34,6 +34,16 @@ class _Stop(Exception):
 
 
 def _run_one(args):
+    """Worker: never lets a reference exception travel through the pool (the parent could not unpickle it and
+    multiprocessing would wait forever); errors come back as text."""
+    try:
+        return _run_one_unguarded(args)
+    except BaseException as error:  # noqa: BLE001 - reported to the parent
+        import traceback
+        return ("error", "".join(traceback.format_exception_only(type(error), error)).strip())
+
+
+def _run_one_unguarded(args):
     ini_text, positions, seed, warmup_seconds, budget_seconds, segments = args
     sys.path.insert(0, REF_ROOT)
     import warnings
@@ -91,6 +101,9 @@ def run_segments(ini_text, positions_per_process, warmup_seconds=2.0, budget_sec
     context = multiprocessing.get_context("spawn")
     with context.Pool(len(jobs)) as pool:
         results = pool.map(_run_one, jobs)
+    failures = [r[1] for r in results if r[0] == "error"]
+    if failures:
+        raise RuntimeError("the reference failed in %d of %d processes: %s" % (len(failures), len(jobs), failures[0]))
     rates = [sum(done[k][0] / done[k][1] for done, _ in results) for k in range(segments)]
     events = sum(events for done, _ in results for events, _ in done)
     return rates, len(jobs), events, sum(init for _, init in results) / len(results)

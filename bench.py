@@ -133,7 +133,8 @@ def reference_sample(args, seconds):
         return None
     cores = os.cpu_count() or 1
     length = float((args.particles / 0.5) ** (1.0 / 3.0))
-    ini = configs.lennard_jones_ini(args.particles, length, args.cells, chain_time=10.0)
+    # one handler instance per possible surplus particle: the reference raises when the list outgrows its pool
+    ini = configs.lennard_jones_ini(args.particles, length, args.cells, chain_time=10.0, surplus_handlers=400)
     positions = workloads.lattice_start(cores, args.particles, args.cells, length)
     rate, processes, events, init_seconds = reference_runner.run(ini, list(positions), warmup_seconds=2.0,
                                                                   budget_seconds=seconds)
@@ -192,7 +193,8 @@ def run_reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     length = float((args.particles / 0.5) ** (1.0 / 3.0))
     if reference_runner.available():
-        ini = configs.lennard_jones_ini(args.particles, length, args.cells, chain_time=10.0)
+        # one handler instance per possible surplus particle: the reference raises when the list outgrows its pool
+        ini = configs.lennard_jones_ini(args.particles, length, args.cells, chain_time=10.0, surplus_handlers=400)
         positions = workloads.lattice_start(cores, args.particles, args.cells, length)
         rates, processes, events, init_seconds = reference_runner.run_segments(
             ini, list(positions), warmup_seconds=0.0, budget_seconds=seconds, segments=steps)
@@ -317,6 +319,11 @@ def run_ours(args, rank, local_rank, world):
     # per chain slice: pack, start, events, unpack (ecmc_kernel_launches counts the event kernels)
     e2e_launches = 4 * (eng.kernel_launches - e2e_launches_before)
 
+    # ---- an observable reduced over ranks: pair-separation histogram of all chains, one NCCL all-reduce
+    import numpy as _np
+    local_histogram = eng.separation_histogram(256, 0.0, length * 3 ** 0.5 / 2.0)
+    histogram = sharding.reduce_histogram(local_histogram.astype(_np.int64), device=torch.device("cuda", local_rank))
+
     # ---- reduce over ranks (NCCL): event counters are summed, times are the slowest rank's
     device = torch.device("cuda", local_rank)
     all_stats = sharding.reduce_counters(stats, device=device)
@@ -371,6 +378,9 @@ def run_ours(args, rank, local_rank, world):
                             "chain slices on separate streams"},
             "gpu_launches": int(launches + e2e_launches),
             "roofline": roofline, "fp64": fp64,
+            "observable": {"kind": "pair-separation histogram of all chains (ecmc_separation_histogram), summed over "
+                                   "ranks by one all-reduce", "bins": 256, "pairs_counted": int(histogram.sum()),
+                           "expected_pairs": world * args.chains * args.particles * (args.particles - 1) // 2},
             "event_mix": {k: all_stats[k] for k in ("pair_events", "veto_events", "veto_accepted", "boundary_events",
                                                     "end_of_chain_events", "bound_violations")}}
     if world == 1 and not args.no_cpu_baseline:

@@ -237,6 +237,15 @@ int ecmc_run_recorded(EcmcHandle *h, double until_q, double until_r, int64_t max
 int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
                        double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
                        EcmcStats *stats);
+/* ---- observables --------------------------------------------------------------------------------------------
+ * Histogram of the shortest pair separations |r_ij| (all pairs i < j of every chain) into n_bins equal bins on
+ * [r_min, r_max]: what SeparationOutputHandler.write prints sample by sample
+ * (jellyfysh/input_output_handler/output_handler/separation_output_handler.py:75-97) and
+ * jellyfysh/output/plotting_functions.py histograms afterwards, accumulated on the device over all chains at once.
+ * Counts are ADDED to histogram[n_bins] (host buffer), so successive sampling times accumulate; separations outside
+ * the range are not counted. Ranks of a multi-GPU run sum their histograms with one all-reduce (sharding.py). */
+int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_min, double r_max, uint64_t *histogram);
+
 /* The CUDA stream the handle launches on (a cudaStream_t), so callers can time with events on it. */
 void *ecmc_stream(EcmcHandle *h);
 /* Seconds of device time (CUDA events on the handle's stream) spent in event kernels since create. */

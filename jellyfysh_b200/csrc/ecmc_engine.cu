@@ -710,6 +710,35 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
     return ecmc_sync(h, stats);
 }
 
+ECMC_API int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_min, double r_max, uint64_t *histogram) {
+    if (!h || !histogram) return fail(h, ECMC_ERR_INVALID, "null argument");
+    if (n_bins < 1 || n_bins > kHistogramMaxBins || !(r_max > r_min) || r_min < 0.0)
+        return fail(h, ECMC_ERR_INVALID, "histogram needs 1 <= n_bins <= 4096 and 0 <= r_min < r_max");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    unsigned long long *d_histogram = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_histogram, sizeof(unsigned long long) * n_bins));
+    int rc = ECMC_OK;
+    do {
+        cudaError_t err = cudaMemsetAsync(d_histogram, 0, sizeof(unsigned long long) * n_bins, h->stream);
+        if (err != cudaSuccess) { rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
+        const int n_tiles = (h->dprog.n_particles + kHistogramTile - 1) / kHistogramTile;
+        separation_histogram_kernel<<<h->n_chains * n_tiles, 256, 0, h->stream>>>(
+            h->state.particles, h->dprog.n_particles, n_tiles, h->dprog.length, n_bins, r_min,
+            (double)n_bins / (r_max - r_min), d_histogram);
+        std::vector<unsigned long long> counts(n_bins);
+        if ((err = cudaGetLastError()) != cudaSuccess ||
+            (err = cudaMemcpyAsync(counts.data(), d_histogram, sizeof(unsigned long long) * n_bins, cudaMemcpyDeviceToHost,
+                                   h->stream)) != cudaSuccess ||
+            (err = cudaStreamSynchronize(h->stream)) != cudaSuccess) {
+            rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err));
+            break;
+        }
+        for (int b = 0; b < n_bins; b++) histogram[b] += counts[b];
+    } while (0);
+    cudaFree(d_histogram);
+    return rc;
+}
+
 ECMC_API void *ecmc_stream(EcmcHandle *h) { return h ? (void *)h->stream : nullptr; }
 ECMC_API double ecmc_kernel_seconds(EcmcHandle *h) { return h ? h->kernel_seconds : 0.0; }
 ECMC_API uint64_t ecmc_kernel_launches(EcmcHandle *h) { return h ? h->kernel_launches : 0; }

@@ -765,6 +765,49 @@ __global__ void unpack_particles_kernel(const Particle *in, double *positions, s
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Pair-separation histogram (SeparationOutputHandler, separation_output_handler.py:75-97): one block per
+// (chain, tile of 1024 particles j). The tile is staged in shared memory, every thread walks over particles i and
+// bins |r_ij| for the j > i of the tile into a shared-memory histogram, flushed to the global one at the end.
+// Streaming, coalesced: each position is read once per tile from L2/HBM; the histogram never leaves the SM.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kHistogramTile = 1024;
+constexpr int kHistogramMaxBins = 4096;
+
+__global__ void __launch_bounds__(256)
+separation_histogram_kernel(const Particle *particles, int n_particles, int n_tiles, double length, int n_bins,
+                            double r_min, double inv_bin_width, unsigned long long *histogram) {
+    __shared__ double tile_x[kHistogramTile], tile_y[kHistogramTile], tile_z[kHistogramTile];
+    __shared__ unsigned int bins[kHistogramMaxBins];
+    const int chain = blockIdx.x / n_tiles, tile = blockIdx.x % n_tiles;
+    const Particle *part = particles + (size_t)chain * n_particles;
+    const int j0 = tile * kHistogramTile, j1 = min(n_particles, j0 + kHistogramTile);
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) bins[b] = 0;
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+        const Particle p = part[j];
+        tile_x[j - j0] = p.x; tile_y[j - j0] = p.y; tile_z[j - j0] = p.z;
+    }
+    __syncthreads();
+    const double half = 0.5 * length;
+    for (int i = threadIdx.x; i < j1 - 1; i += blockDim.x) {
+        const Particle p = part[i];
+        for (int j = max(i + 1, j0); j < j1; j++) {
+            const double sx = correct_separation_in_box(tile_x[j - j0] - p.x, length, half);
+            const double sy = correct_separation_in_box(tile_y[j - j0] - p.y, length, half);
+            const double sz = correct_separation_in_box(tile_z[j - j0] - p.z, length, half);
+            const double r = sqrt(fma(sx, sx, fma(sy, sy, sz * sz)));
+            const double scaled = (r - r_min) * inv_bin_width;
+            if (scaled >= 0.0 && scaled <= (double)n_bins) {
+                const int bin = min((int)scaled, n_bins - 1);  // r == r_max belongs to the last bin (numpy.histogram)
+                atomicAdd(&bins[bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x)
+        if (bins[b]) atomicAdd(histogram + b, (unsigned long long)bins[b]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // batched potential arithmetic (ecmc_potential_derivative / ecmc_potential_displacement): one warp per element
 // for the merged-image Coulomb sum, one thread per element otherwise.
 // ---------------------------------------------------------------------------------------------------------

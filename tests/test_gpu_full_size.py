@@ -138,3 +138,36 @@ def test_device_tables_for_c2_match_oracle_tables(oracle):
     for d in range(3):
         same = np.mean(reference_tables["upper"][d]["cell_a"] == builder.tables["upper"][d]["cell_a"])
         assert same > 0.99  # the alias pairing only differs where two bounds are equal to the last bit
+
+
+def test_separation_histogram_matches_numpy():
+    """ecmc_separation_histogram against numpy on the downloaded positions: all pairs of every chain."""
+    n_chains, n, cells = 24, 200, 6
+    builder, length = workloads.lennard_jones(n_particles=n, cells_per_side=cells, points_per_side=2)
+    positions = workloads.lattice_start(n_chains, n, cells, length, jitter=0.2)
+    with engine.Engine(builder, n_chains=n_chains) as eng:
+        eng.upload_positions(positions)
+        eng.start()
+        eng.run(max_events=500)
+        eng.sync()
+        r_max = length * np.sqrt(3.0) / 2.0
+        ours = eng.separation_histogram(1000, 0.0, r_max)
+        eng.separation_histogram(1000, 0.0, r_max, out=ours)  # accumulates
+        current = eng.download_positions()
+    expected = np.zeros(1000, dtype=np.int64)
+    half = length / 2.0
+    iu = np.triu_indices(n, k=1)
+    for c in range(n_chains):
+        sep = current[c][iu[1]] - current[c][iu[0]]
+        sep = np.mod(sep + half, length) - half
+        expected += np.histogram(np.sqrt(np.sum(sep * sep, axis=1)), bins=1000, range=(0.0, r_max))[0]
+    assert ours.sum() == 2 * n_chains * n * (n - 1) // 2
+    # a separation within one ulp of a bin edge may fall on either side (fma vs numpy's rounding): a handful at most
+    assert np.abs(ours.astype(np.int64) - 2 * expected).sum() <= 8
+    # N > tile size exercises the tiling: 1500 particles, one chain
+    builder, length = workloads.lennard_jones(n_particles=1500, cells_per_side=12, points_per_side=2, veto=False)
+    positions = workloads.lattice_start(1, 1500, 12, length)
+    with engine.Engine(builder, n_chains=1) as eng:
+        eng.upload_positions(positions)
+        counts = eng.separation_histogram(64, 0.0, length)
+    assert counts.sum() == 1500 * 1499 // 2
