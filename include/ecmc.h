@@ -78,6 +78,17 @@ enum EcmcPairHandlerKind {
     ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING = 2
 };
 
+/* ---- far-field handlers ---------------------------------------------------------------------------------------- */
+enum EcmcFarFieldKind {
+    ECMC_FAR_NONE = 0,
+    /* CellVetoTagger + LeafUnitCellVetoEventHandler, jellyfysh/event_handler/leaf_unit_cell_veto_event_handler.py:117-149 */
+    ECMC_FAR_CELL_VETO = 1,
+    /* CellBoundingPotentialTagger (jellyfysh/activator/tagger/cell_bounding_potential_tagger.py:127-155) +
+     * TwoLeafUnitCellBoundingPotentialEventHandler (two_leaf_unit_cell_bounding_potential_event_handler.py:137-211) with
+     * CellBoundingPotential (jellyfysh/potential/cell_bounding_potential.py:155-238) */
+    ECMC_FAR_CELL_BOUNDING = 2
+};
+
 /* ---- cell-veto tables -------------------------------------------------------------------------------
  * Walker alias table for one direction of motion and one sign, as built by the reference at init
  * (jellyfysh/event_handler/walker.py:69-103; jellyfysh/event_handler/abstracts/cell_veto_event_handler.py:134-159).
@@ -119,7 +130,10 @@ typedef struct EcmcProgram {
     int32_t pair_use_charge;  /* 1: potentials get (charge_active, charge_target); 0: (1.0, 1.0) / none */
     EcmcPotential pair_potential;
     EcmcPotential pair_bounding_potential; /* only for ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING */
-    /* LeafUnitCellVetoEventHandler for all non-nearby cells */
+    /* The far field, all non-nearby cells: EcmcFarFieldKind. ECMC_FAR_CELL_VETO = LeafUnitCellVetoEventHandler (one
+     * candidate per event from the Walker tables); ECMC_FAR_CELL_BOUNDING = TwoLeafUnitCellBoundingPotentialEventHandler
+     * (one candidate per occupied non-nearby cell from the constant bound of its relative cell; needs
+     * max_occupants == 1 like the reference, uses only veto_tables->bounds). Both confirm against veto_potential. */
     int32_t veto_enabled;
     int32_t veto_use_charge;
     EcmcPotential veto_potential;
@@ -164,14 +178,15 @@ enum EcmcEventKind {
     ECMC_EVENT_PAIR = 1,          /* nearby-cell or surplus pair factor */
     ECMC_EVENT_CELL_VETO = 2,
     ECMC_EVENT_CELL_BOUNDARY = 3,
-    ECMC_EVENT_END_OF_CHAIN = 4
+    ECMC_EVENT_END_OF_CHAIN = 4,
+    ECMC_EVENT_CELL_BOUNDING = 5  /* pair factor of a non-nearby cell, found through the cell-bounding potential */
 };
 
 /* One committed event, as the scheduler + winning handler of the reference would report it. */
 typedef struct EcmcEventRecord {
     int32_t kind;             /* EcmcEventKind of the winner (argmin) */
-    int32_t target;           /* pair / accepted or rejected veto: target particle (-1: empty veto cell) */
-    int32_t target_cell;      /* veto: sampled target cell; boundary: new cell; else -1 */
+    int32_t target;           /* pair / cell bounding / accepted or rejected veto: target particle (-1: empty veto cell) */
+    int32_t target_cell;      /* veto: sampled target cell; boundary: new cell; cell bounding: relative cell; else -1 */
     int32_t accepted;         /* 1 if the velocity was handed over (lifting happened) */
     int32_t n_candidates;     /* finite candidate times that entered the argmin */
     int32_t new_active;       /* active particle after the event */
@@ -183,7 +198,7 @@ typedef struct EcmcEventRecord {
 
 typedef struct EcmcStats {
     uint64_t events;            /* events committed by this call, all chains */
-    uint64_t pair_events;
+    uint64_t pair_events;       /* nearby / surplus pair events and cell-bounding pair events */
     uint64_t veto_events;
     uint64_t veto_accepted;
     uint64_t boundary_events;

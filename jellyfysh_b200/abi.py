@@ -28,8 +28,14 @@ EVENT_PAIR = 1
 EVENT_CELL_VETO = 2
 EVENT_CELL_BOUNDARY = 3
 EVENT_END_OF_CHAIN = 4
+EVENT_CELL_BOUNDING = 5
+
+FAR_NONE = 0
+FAR_CELL_VETO = 1
+FAR_CELL_BOUNDING = 2
 EVENT_NAMES = {EVENT_NONE: "none", EVENT_PAIR: "pair", EVENT_CELL_VETO: "cell_veto",
-               EVENT_CELL_BOUNDARY: "cell_boundary", EVENT_END_OF_CHAIN: "end_of_chain"}
+               EVENT_CELL_BOUNDARY: "cell_boundary", EVENT_END_OF_CHAIN: "end_of_chain",
+               EVENT_CELL_BOUNDING: "cell_bounding"}
 
 SLOT_PAIR_TIME = 1
 SLOT_VETO_TIME = 2

@@ -131,9 +131,12 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None)
 
     # ---- handlers by kind
     pair_handlers, veto_handlers, boundary_handlers, eoc_handlers, start_handlers, control = [], [], [], [], [], []
+    bounding_handlers = []
     for handler in activator.get_event_handlers():
         names = _class_names(handler)
-        if "TwoLeafUnitBoundingPotentialEventHandler" in names or "TwoLeafUnitEventHandler" in names:
+        if "TwoLeafUnitCellBoundingPotentialEventHandler" in names:
+            bounding_handlers.append(handler)
+        elif "TwoLeafUnitBoundingPotentialEventHandler" in names or "TwoLeafUnitEventHandler" in names:
             pair_handlers.append(handler)
         elif "LeafUnitCellVetoEventHandler" in names:
             veto_handlers.append(handler)
@@ -216,6 +219,32 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None)
                          target_charge=1.0 if target_charge is None else target_charge)
         if veto_charge is not None:
             charge_names.add(veto_charge)
+    # ---- cell bounding: one TwoLeafUnitCellBoundingPotentialEventHandler per possible far target, all alike
+    # (two_leaf_unit_cell_bounding_potential_event_handler.py:65-110); the bounds were built by
+    # CellBoundingPotential.initialize (cell_bounding_potential.py:96-153) as (upper dict, lower dict or None)
+    if bounding_handlers:
+        if veto_handlers:
+            raise _configuration_error("cell-veto and cell-bounding handlers for the same far field")
+        first = bounding_handlers[0]
+        potential = potential_descriptor(first._potential)
+        charge = first._charge
+        for handler in bounding_handlers[1:]:
+            if not _same_potential(potential, potential_descriptor(handler._potential)) or handler._charge != charge:
+                raise _configuration_error("cell-bounding handlers must share potential and charge")
+        index_of = {cell: index for index, cell in enumerate(cell_objects)}
+        bounds = np.zeros((len(cell_objects), dimension, 2))
+        stored = first._bounding_potential._derivative_bounds  # a bare dict when no lower bounds were asked for
+        upper, lower = (stored, None) if isinstance(stored, dict) else stored
+        for cell, per_direction in upper.items():
+            for d in range(dimension):
+                bounds[index_of[cell], d, 0] = per_direction[d]
+                if lower is not None:
+                    bounds[index_of[cell], d, 1] = -lower[cell][d]
+        target_charge = getattr(first._bounding_potential._estimator, "_target_charge", None)
+        builder.set_cell_bounding(potential, bounds, use_charge=charge is not None,
+                                  target_charge=1.0 if target_charge is None else target_charge)
+        if charge is not None:
+            charge_names.add(charge)
     if len(charge_names) > 1:
         raise _configuration_error("pair and cell-veto handlers use different charges: {0}".format(sorted(charge_names)))
     return CompiledProgram(builder, charge_names.pop() if charge_names else None, control, n_particles)

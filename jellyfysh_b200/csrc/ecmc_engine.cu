@@ -273,6 +273,7 @@ int build_device_program(EcmcHandle *h) {
 
     // potentials
     int rc;
+    bool relative_modular = true;
     if (p.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT) {
         if (!is_invertible(p.pair_potential.kind)) return fail(h, ECMC_ERR_INVALID, "pair potential is not invertible");
         if ((rc = make_potential(h, p.pair_potential, p.system_length, &d.cand_potential))) return rc;
@@ -316,6 +317,7 @@ int build_device_program(EcmcHandle *h) {
         std::vector<double> cmin_all(3 * mps, 0.0);
         std::vector<int> translate(3 * mps * mps, 0);
         d.translate_modular = 1;
+        relative_modular = true;
         for (int k = 0; k < 3; k++) {
             std::vector<double> cmin, cmax;
             axis_geometry(d.per_side[k], d.side_length[k], cmin, cmax);
@@ -325,27 +327,42 @@ int build_device_program(EcmcHandle *h) {
                     const double x = host_py_mod((cmax[a] + cmin[a]) / 2.0 + cmin[r], p.system_length);
                     translate[(k * mps + a) * mps + r] = (int)(x / d.side_length[k]);
                     if (translate[(k * mps + a) * mps + r] != (a + r) % d.per_side[k]) d.translate_modular = 0;
+                    // relative_cell(cell a, reference r), cuboid_periodic_cells.py:155-180
+                    const double y = host_py_mod((cmax[a] + cmin[a]) / 2.0 - cmin[r], p.system_length);
+                    if ((int)(y / d.side_length[k]) != ((a - r) % d.per_side[k] + d.per_side[k]) % d.per_side[k])
+                        relative_modular = false;
                 }
             }
         }
         if ((rc = device_upload(h, &d.cell_min_axis, cmin_all))) return rc;
         if ((rc = device_upload(h, &d.translate_axis, translate))) return rc;
     }
-    // cell veto
+    // far field: cell veto (Walker tables) or cell bounding (one candidate per occupied far cell)
+    d.neighbor_layers = p.neighbor_layers;
+    if (p.veto_enabled != ECMC_FAR_NONE && p.veto_enabled != ECMC_FAR_CELL_VETO && p.veto_enabled != ECMC_FAR_CELL_BOUNDING)
+        return fail(h, ECMC_ERR_INVALID, "unknown far-field kind");
     if (p.veto_enabled) {
-        if (!p.veto_tables || !p.veto_tables->bounds) return fail(h, ECMC_ERR_INVALID, "veto enabled without tables");
-        if (!has_derivative(p.veto_potential.kind)) return fail(h, ECMC_ERR_INVALID, "veto potential has no derivative");
+        if (!p.veto_tables || !p.veto_tables->bounds) return fail(h, ECMC_ERR_INVALID, "far field enabled without tables");
+        if (!has_derivative(p.veto_potential.kind)) return fail(h, ECMC_ERR_INVALID, "far-field potential has no derivative");
         if (p.veto_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB && p.dimension != 3)
             return fail(h, ECMC_ERR_INVALID, "Coulomb potentials need dimension 3");
         if (p.veto_use_charge && !(p.veto_target_charge != 0.0))
             return fail(h, ECMC_ERR_INVALID, "veto_target_charge must not be 0");
         if ((rc = make_potential(h, p.veto_potential, p.system_length, &d.veto_potential))) return rc;
+    }
+    if (p.veto_enabled == ECMC_FAR_CELL_VETO) {
         for (int k = 0; k < p.dimension; k++) {
             if ((rc = upload_walker(h, p.veto_tables->upper[k], &d.upper[k], d, p.veto_tables->bounds, k, 0))) return rc;
             if ((rc = upload_walker(h, p.veto_tables->lower[k], &d.lower[k], d, p.veto_tables->bounds, k, 1))) return rc;
             if (d.upper[k].n_entries <= 0 && d.lower[k].n_entries <= 0)
                 return fail(h, ECMC_ERR_INVALID, "veto enabled but a direction has no Walker table");
         }
+    } else if (p.veto_enabled == ECMC_FAR_CELL_BOUNDING) {
+        // the reference's handler takes exactly two units (two_leaf_unit_cell_bounding_potential_event_handler.py:158)
+        if (p.max_occupants != 1) return fail(h, ECMC_ERR_INVALID, "cell bounding needs max_occupants == 1");
+        if (!relative_modular) return fail(h, ECMC_ERR_INVALID, "cell geometry with non-modular relative cells");
+        std::vector<double> bounds(p.veto_tables->bounds, p.veto_tables->bounds + (size_t)d.n_cells * p.dimension * 2);
+        if ((rc = device_upload(h, &d.bounds, bounds))) return rc;
     }
     return ECMC_OK;
 }

@@ -131,6 +131,35 @@ ECMC_D void set_component(Particle &a, int dir, double v) {
     if (dir == 0) a.x = v; else if (dir == 1) a.y = v; else a.z = v;
 }
 
+// Is `cell` (flat index) one of the nearby cells of the cell with identifiers (c0, c1, c2)? Per axis the periodic
+// distance must be within the neighbour layers (cuboid_periodic_cells.py:74-100).
+ECMC_D bool cell_is_nearby(const DeviceProgram &P, int cell, int c0, int c1, int c2) {
+    const int ids[3] = {(cell / P.cumulative[0]) % P.per_side[0], (cell / P.cumulative[1]) % P.per_side[1],
+                        (cell / P.cumulative[2]) % P.per_side[2]};
+    const int ref[3] = {c0, c1, c2};
+    bool nearby = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int delta = ids[k] - ref[k];
+        if (delta < 0) delta += P.per_side[k];
+        nearby = nearby && (delta <= P.neighbor_layers || delta >= P.per_side[k] - P.neighbor_layers);
+    }
+    return nearby;
+}
+// relative_cell(cell, active cell) as a flat index (cuboid_periodic_cells.py:155-180; modular per axis, checked on
+// the host)
+ECMC_D int relative_cell_of(const DeviceProgram &P, int cell, int c0, int c1, int c2) {
+    const int ref[3] = {c0, c1, c2};
+    int relative = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int delta = (cell / P.cumulative[k]) % P.per_side[k] - ref[k];
+        if (delta < 0) delta += P.per_side[k];
+        relative += delta * P.cumulative[k];
+    }
+    return relative;
+}
+
 // SingleActiveCellOccupancy: append to the occupants of a cell, or to the surplus when the cell is full
 // (single_active_cell_occupancy.py:117-121, :176-180). Serial, called by one lane. Returns the change of
 // n_surplus, or 2 on overflow of the surplus capacity.
@@ -262,7 +291,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     const double L = P.length, half = P.half_length, speed = P.speed;
     const bool has_pairs = P.pair_handler != ECMC_PAIR_NONE;
     const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
-    const bool has_veto = VETO != 0 && P.veto_enabled;
+    const bool has_veto = VETO != 0 && P.veto_enabled == ECMC_FAR_CELL_VETO;
+    const bool has_far_pairs = VETO != 0 && P.veto_enabled == ECMC_FAR_CELL_BOUNDING;
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
 
     Counters n = {0, 0, 0, 0, 0ull};
@@ -284,7 +314,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             bkind = stp->pending_kind;
             bt.q = stp->pending_q; bt.r = stp->pending_r;
             brate = stp->pending_rate;
-            if (bkind == ECMC_EVENT_PAIR) btarget = stp->pending_target; else bcell = stp->pending_target;
+            if (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING) btarget = stp->pending_target;
+            else bcell = stp->pending_target;
             kept_position = stp->pending_position;
             kept_stamp.q = stp->pending_stamp_q; kept_stamp.r = stp->pending_stamp_r;
         } else {
@@ -296,15 +327,19 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             // oracle's scan: pair slots in scan order, veto, boundary.
             const int nearby_slots = has_pairs ? P.n_nearby * m : 0;
             const int n_pair_slots = has_pairs ? nearby_slots + n_surplus : 0;
+            // with a cell-bounding far field every occupied cell that is not nearby is one more candidate
+            // (cell_bounding_potential_tagger.py:150-155); these slots follow the pair slots, one per cell
+            const int n_scan_slots = n_pair_slots + (has_far_pairs ? P.n_cells : 0);
+            const int special_seq = n_pair_slots + P.n_cells;
             const double c_active = P.pair_use_charge ? a.charge : 1.0;
             unsigned long long best_key = 0x7ff0000000000000ull;  // best of the passes so far (uniform)
             double best_x = INFINITY;
             int best_seq = kSeqNone;
             int cursor = 0;      // next slot to scan
             bool first = true;   // the special candidates have not been processed yet
-            while (first || cursor < n_pair_slots) {
+            while (first || cursor < n_scan_slots) {
               int count = 0;  // entries in the compact list
-              while (cursor < n_pair_slots && count <= kListCapacity - 32) {
+              while (cursor < n_scan_slots && count <= kListCapacity - 32) {
                 const int s = cursor + lane;
                 int found = -1;
                 if (s < nearby_slots) {
@@ -318,6 +353,9 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     found = occ[cell * m + (s - ci * m)];
                 } else if (s < n_pair_slots) {
                     found = sur[s - nearby_slots];
+                } else if (s < n_scan_slots) {
+                    const int cell = s - n_pair_slots;
+                    if (!cell_is_nearby(P, cell, cid0, cid1, cid2)) found = occ[cell];
                 }
                 const unsigned occupied = __ballot_sync(kFull, found >= 0);
                 if (found >= 0) {
@@ -365,8 +403,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     s2 = correct_separation_in_box(tp.p2 - a.p2, L, half);
                 }
                 if (base > 0 || !first) {
-                    const bool alive = is_pair && !certainly_dead<CAND>(P.cand_potential, s0, s1, s2,
-                                                                        cand_needs_du ? u_first * P.inv_beta : 0.0);
+                    const bool alive = is_pair && (s >= n_pair_slots || !certainly_dead<CAND>(P.cand_potential, s0, s1, s2,
+                                                                        cand_needs_du ? u_first * P.inv_beta : 0.0));
                     if (!__any_sync(kFull, alive)) continue;
                 }
                 // random.expovariate(beta): pair lanes use their first double, the veto lane its second
@@ -378,7 +416,20 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 double dt = INFINITY;
                 int kind = ECMC_EVENT_NONE, cell = -1, seq = kSeqNone;
                 double rate = 0.0;
-                if (is_pair) {
+                const bool is_far = is_pair && s >= n_pair_slots;  // cell-bounding candidate
+                if (is_far) {
+                    // TwoLeafUnitCellBoundingPotentialEventHandler.send_event_time (:137-177): constant event rate =
+                    // bound of the relative cell x charge correction factor (cell_bounding_potential.py:155-238)
+                    const int relative = relative_cell_of(P, s - n_pair_slots, cid0, cid1, cid2);
+                    double charge_product = 1.0;
+                    if (P.veto_use_charge) charge_product = a.charge * tp.charge / P.veto_target_charge;
+                    const double *bound = P.bounds + (relative * P.dimension + dir) * 2;
+                    rate = charge_product > 0.0 ? __ldg(bound) * charge_product : -__ldg(bound + 1) * charge_product;
+                    dt = rate > 0.0 ? exponential / rate * P.inv_speed : INFINITY;
+                    cell = relative;
+                    kind = ECMC_EVENT_CELL_BOUNDING;
+                    seq = s;
+                } else if (is_pair) {
                     dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c_active,
                                                  P.pair_use_charge ? tp.charge : 1.0, cand_needs_du ? exponential : 0.0);
                     kind = ECMC_EVENT_PAIR;
@@ -434,7 +485,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     dt = exponential * w->inv_total_rate_speed;
                     if (P.veto_use_charge) dt = exponential / (w->total_rate * charge_factor * speed);
                     kind = ECMC_EVENT_CELL_VETO;
-                    seq = n_pair_slots;
+                    seq = special_seq;
                 } else if (is_boundary) {
                     // CellBoundaryEventHandler.send_event_time (cell_boundary_event_handler.py:122-156)
                     double separation = boundary - a.p0;
@@ -442,7 +493,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     dt = separation * P.inv_speed;
                     cell = next_cell;
                     kind = ECMC_EVENT_CELL_BOUNDARY;
-                    seq = n_pair_slots + 1;
+                    seq = special_seq + 1;
                 }
                 // Time.__add__: event time = now + dt; x orders the candidates (see time_key)
                 const double x = now.r + dt;
@@ -484,7 +535,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 stp->pending_kind = bkind;
                 stp->pending_q = bt.q; stp->pending_r = bt.r;
                 stp->pending_rate = brate;
-                stp->pending_target = bkind == ECMC_EVENT_PAIR ? btarget : bcell;
+                stp->pending_target = (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING) ? btarget : bcell;
                 if (!was_pending) {
                     stp->pending_position = a.p0;
                     stp->pending_stamp_q = now.q; stp->pending_stamp_r = now.r;
@@ -558,6 +609,26 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             }
             n.veto++;
             if (accepted) count_rare(A, lane, 3);
+            break;
+        }
+        case ECMC_EVENT_CELL_BOUNDING: {
+            // TwoLeafUnitCellBoundingPotentialEventHandler.send_out_state (:179-211): the stored bounding rate (times the
+            // speed) against the real derivative, event_handler_with_bounding_potential.py:75-101
+            rec_target = btarget;
+            const Moving tp = rotate_in(part[btarget], dir);
+            const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
+            const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
+            const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
+            const double c1 = P.veto_use_charge ? a.charge : 1.0, c2 = P.veto_use_charge ? tp.charge : 1.0;
+            const double bounding_rate = brate * speed;
+            const double real = derivative_warp<VETO>(P.veto_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
+            if (real > 0.0) {
+                if (bounding_rate < real) count_rare(A, lane, 7);
+                const double u = have_confirmation ? u_confirmation : stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+                if (0.0 + (bounding_rate - 0.0) * u < real) accepted = 1;
+            }
+            if (accepted) new_active = btarget;
+            n.pair++;
             break;
         }
         case ECMC_EVENT_CELL_BOUNDARY: {

@@ -70,6 +70,8 @@ struct DeviceProgram {
     int max_per_side;
     int translate_modular;        // 1 if translate_axis[d][a][r] == (a + r) mod cells_per_side[d] everywhere
     DeviceWalker upper[3], lower[3];
+    const double *bounds;         // [n_cells][dimension][2] (upper, -lower) per relative cell: ECMC_FAR_CELL_BOUNDING only
+    int neighbor_layers, pad3;
     double inv_beta, inv_speed;
 };
 

@@ -48,6 +48,22 @@ class ProgramBuilder:
         p.pair_use_charge = int(use_charge)
         return self
 
+    def set_cell_bounding(self, potential, bounds, use_charge=False, target_charge=1.0):
+        """Far field through TwoLeafUnitCellBoundingPotentialEventHandler: bounds[n_cells][dimension][2] holds
+        (upper bound, -lower bound) of the derivative per relative cell (CellBoundingPotential._derivative_bounds)."""
+        p = self.program
+        p.veto_enabled = abi.FAR_CELL_BOUNDING
+        p.veto_potential = potential
+        p.veto_use_charge = int(use_charge)
+        p.veto_target_charge = target_charge
+        vt = abi.EcmcVetoTables()
+        array = np.ascontiguousarray(np.nan_to_num(bounds, nan=0.0), dtype=np.float64)
+        self._keep += [array, vt]
+        vt.bounds = array.ctypes.data_as(C.POINTER(C.c_double))
+        p.veto_tables = C.pointer(vt)
+        self.tables = {"bounds": array}
+        return self
+
     def set_veto(self, potential, tables, use_charge=False, target_charge=1.0):
         p = self.program
         p.veto_enabled = 1

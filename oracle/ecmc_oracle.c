@@ -1004,7 +1004,7 @@ ORC_API OrcChain *orc_chain_create(const EcmcProgram *prog) {
     }
     if (prog->veto_enabled) {
         if (!prog->veto_tables) goto fail;
-        for (int d = 0; d < c->D; d++) {
+        for (int d = 0; d < c->D && prog->veto_enabled == ECMC_FAR_CELL_VETO; d++) {
             if (copy_walker(&c->upper[d], &prog->veto_tables->upper[d])) goto fail;
             if (copy_walker(&c->lower[d], &prog->veto_tables->lower[d])) goto fail;
         }
@@ -1172,6 +1172,32 @@ static candidate veto_candidate(OrcChain *c) {
     return cand;
 }
 
+/* TwoLeafUnitCellBoundingPotentialEventHandler.send_event_time (two_leaf_unit_cell_bounding_potential_event_handler.py:
+ * 137-177) with CellBoundingPotential.standard_velocity_displacement (cell_bounding_potential.py:155-238): the cells of
+ * both units are recomputed from their positions, the bound of the relative cell times the charge correction factor
+ * (inner_point_estimator.py:165-192) is a constant event rate. target_cell carries the relative cell. */
+static candidate cell_bounding_candidate(OrcChain *c, int target) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_CELL_BOUNDING; cand.target = target;
+    int dir = c->st.direction;
+    int active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
+    int target_cell = position_to_cell(&c->cells, c->pos + target * c->D);
+    int relative_cell = cells_relative(&c->cells, target_cell, active_cell);
+    cand.target_cell = relative_cell;
+    double c1 = c->prog.veto_use_charge ? c->charge[c->st.active] : 1.0;
+    double c2 = c->prog.veto_use_charge ? c->charge[target] : 1.0;
+    double charge_product = c->prog.veto_use_charge ? c1 * c2 / c->prog.veto_target_charge : 1.0;
+    /* bounds holds (upper, -lower): lower_bound * charge_product for a negative product */
+    if (charge_product > 0.0) cand.rate = c->bounds[(relative_cell * c->D + dir) * 2 + 0] * charge_product;
+    else cand.rate = -c->bounds[(relative_cell * c->D + dir) * 2 + 1] * charge_product;
+    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target), 0);
+    double dU = rng_expovariate(u, c->prog.beta);
+    double displacement = cand.rate > 0 ? dU / cand.rate : ORC_INF;
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, displacement / c->prog.speed);
+    return cand;
+}
+
 /* CellBoundaryEventHandler.send_event_time, cell_boundary_event_handler.py:122-156 (positive velocity) */
 static candidate boundary_candidate(OrcChain *c, double *boundary_out) {
     candidate cand;
@@ -1232,7 +1258,7 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         best.kind = c->st.pending_kind;
         best.t.q = c->st.pending_q; best.t.r = c->st.pending_r;
         best.rate = c->st.pending_rate;
-        if (best.kind == ECMC_EVENT_PAIR) best.target = c->st.pending_target;
+        if (best.kind == ECMC_EVENT_PAIR || best.kind == ECMC_EVENT_CELL_BOUNDING) best.target = c->st.pending_target;
         else best.target_cell = c->st.pending_target;
         if (best.kind == ECMC_EVENT_CELL_BOUNDARY)
             boundary_position = c->cells.cell_min[best.target_cell * c->D + c->st.direction];
@@ -1267,7 +1293,19 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
                 }
             }
         }
-        if (c->prog.veto_enabled) {
+        if (c->prog.veto_enabled == ECMC_FAR_CELL_BOUNDING) {
+            /* CellBoundingPotentialTagger, cell_bounding_potential_tagger.py:150-155: every non-empty cell that is
+             * not nearby the active cell */
+            for (int cell = 0; cell < c->cells.n_cells; cell++) {
+                int t = c->occ[cell * m];
+                if (t < 0) continue;
+                int is_near = 0;
+                for (int i = 0; i < nn; i++) if (nearby[i] == cell) { is_near = 1; break; }
+                if (is_near) continue;
+                candidate cand = cell_bounding_candidate(c, t);
+                if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
+            }
+        } else if (c->prog.veto_enabled) {
             candidate cand = veto_candidate(c);
             if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
         }
@@ -1291,7 +1329,8 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
             c->st.pending_kind = interaction.kind;
             c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
             c->st.pending_rate = interaction.rate;
-            c->st.pending_target = interaction.kind == ECMC_EVENT_PAIR ? interaction.target : interaction.target_cell;
+            c->st.pending_target = (interaction.kind == ECMC_EVENT_PAIR || interaction.kind == ECMC_EVENT_CELL_BOUNDING)
+                                       ? interaction.target : interaction.target_cell;
             if (!was_pending) {
                 /* the kept handlers hold copies of the in-state made before the control event time-slices
                  * the global state (single_process_mediator.py:105-109): their out-state starts from here */
@@ -1361,6 +1400,26 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         }
         c->stats.veto_events++;
         if (accepted) c->stats.veto_accepted++;
+        break;
+    }
+    case ECMC_EVENT_CELL_BOUNDING: {
+        /* TwoLeafUnitCellBoundingPotentialEventHandler.send_out_state (:179-211): the bounding event rate is the one
+         * stored by send_event_time (times the speed, StandardVelocityPotential.derivative), confirmed against the
+         * real potential like any bounded pair (event_handler_with_bounding_potential.py:75-101) */
+        rec_target = best.target;
+        double sep[ECMC_MAX_DIM] = {0, 0, 0};
+        separation_vector(c->pos + old_active * c->D, c->pos + best.target * c->D, c->D, c->L, sep);
+        double c1 = c->prog.veto_use_charge ? c_act : 1.0;
+        double c2 = c->prog.veto_use_charge ? c->charge[best.target] : 1.0;
+        double bounding_rate = best.rate * c->prog.speed;
+        double real = pot_derivative(&c->veto_pot, c->st.direction, c->prog.speed, sep, c->D, c1, c2);
+        if (real > 0) {
+            if (bounding_rate < real) c->stats.bound_violations++;
+            double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+            if (0 + (bounding_rate - 0) * u < real) accepted = 1;
+        }
+        if (accepted) new_active = best.target;
+        c->stats.pair_events++;
         break;
     }
     case ECMC_EVENT_CELL_BOUNDARY:

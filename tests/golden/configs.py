@@ -156,10 +156,32 @@ _INTERACTION_TAGS_COULOMB = "coulomb_nearby, coulomb_cell_veto, cell_boundary, c
 def coulomb_atoms_ini(n, cells_per_side, system_length=1.0, beta=2.0, alpha=3.45, fourier_cutoff=6,
                       position_cutoff=2, prefactor=1.0, bounding_prefactor=1.5837, estimator_prefactor=1.0,
                       points_per_side=10, chain_time=0.78965, end_of_run_time=1.0e9, charge_values="1",
-                      nearby_handlers=27, surplus_handlers=16, neighbor_layers=1):
-    """C3 of SURVEY.md 8(d): the structure of config_files/2018_JCP_149_064113/coulomb_atoms/cell_veto.ini."""
+                      nearby_handlers=27, surplus_handlers=16, neighbor_layers=1, far_field="cell_veto"):
+    """C3 of SURVEY.md 8(d): the structure of config_files/2018_JCP_149_064113/coulomb_atoms/cell_veto.ini, or with
+    far_field="cell_bounding" of coulomb_atoms/cell_bounded.ini (TwoLeafUnitCellBoundingPotentialEventHandler)."""
     tags = _INTERACTION_TAGS_COULOMB
     cps = ", ".join(str(c) for c in cells_per_side)
+    text = _coulomb_atoms_text(n, cps, system_length, beta, alpha, fourier_cutoff, position_cutoff, prefactor,
+                               bounding_prefactor, estimator_prefactor, points_per_side, chain_time, end_of_run_time,
+                               charge_values, nearby_handlers, surplus_handlers, neighbor_layers, tags)
+    if far_field == "cell_bounding":
+        text = text.replace("coulomb_cell_veto (cell_veto_tagger)", "coulomb_cell_veto (cell_bounding_potential_tagger)")
+        text = text.replace("event_handler = leaf_unit_cell_veto_event_handler",
+                            "event_handler = two_leaf_unit_cell_bounding_potential_event_handler\n"
+                            f"number_event_handlers = {n}")
+        text = text.replace("[LeafUnitCellVetoEventHandler]\nestimator = inner_point_estimator\n",
+                            "[TwoLeafUnitCellBoundingPotentialEventHandler]\npotential = merged_image_coulomb_potential\n"
+                            "bounding_potential = cell_bounding_potential\n")
+        text = text.replace("[InnerPointEstimator]", "[CellBoundingPotential]\nestimator = inner_point_estimator\n\n"
+                                                     "[InnerPointEstimator]")
+    elif far_field != "cell_veto":
+        raise ValueError(far_field)
+    return text
+
+
+def _coulomb_atoms_text(n, cps, system_length, beta, alpha, fourier_cutoff, position_cutoff, prefactor,
+                        bounding_prefactor, estimator_prefactor, points_per_side, chain_time, end_of_run_time,
+                        charge_values, nearby_handlers, surplus_handlers, neighbor_layers, tags):
     return f"""
 [Run]
 mediator = single_process_mediator

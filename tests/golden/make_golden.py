@@ -237,11 +237,22 @@ def base_vectors():
 # whole-chain traces
 # ------------------------------------------------------------------------------------------------------
 def _tables_of(run):
-    veto = [h for h in run.mediator._activator.get_event_handlers() if "CellVeto" in type(h).__name__][0]
     dim = run.setting.dimension
     n_cells = len(list(run._cells().yield_cells()))
     out = {}
     bounds = np.full((n_cells, dim, 2), np.nan)
+    vetoes = [h for h in run.mediator._activator.get_event_handlers() if "CellVeto" in type(h).__name__]
+    if not vetoes:
+        # cell-bounding configuration: CellBoundingPotential._derivative_bounds = (upper dict, lower dict)
+        handler = [h for h in run.mediator._activator.get_event_handlers() if "CellBounding" in type(h).__name__][0]
+        upper, lower = handler._bounding_potential._derivative_bounds
+        for cell, per_direction in upper.items():
+            for d in range(dim):
+                bounds[run._cell_index(cell), d, 0] = per_direction[d]
+                bounds[run._cell_index(cell), d, 1] = -lower[cell][d]
+        out["bounds"] = bounds
+        return out
+    veto = vetoes[0]
     for cell, b in veto._derivative_bounds.items():
         for d in range(dim):
             bounds[run._cell_index(cell), d, 0] = b[d][0]
@@ -287,8 +298,8 @@ def chain_trace(name, ini, positions, seed, stream, n_events, snapshot_every, me
     finally:
         run.close()
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    kinds = np.bincount(records["kind"], minlength=5)
-    print(f"{name}.npz: {len(records)} events, kinds pair/veto/boundary/eoc = {kinds[1:].tolist()}, "
+    kinds = np.bincount(records["kind"], minlength=6)
+    print(f"{name}.npz: {len(records)} events, kinds pair/veto/boundary/eoc/cell-bounding = {kinds[1:].tolist()}, "
           f"accepted = {int(records['accepted'].sum())}, snapshots = {len(run.snapshots)}, "
           f"max surplus = {int(out['snap_n_surplus'].max())}")
 
@@ -330,8 +341,24 @@ def chain_traces():
                           ipcb=[1.5837], estimator=[1.0, 4], chain_time=0.78965))
 
 
+def cell_bounding_traces():
+    # Coulomb atoms with the far field through TwoLeafUnitCellBoundingPotentialEventHandler (shipped
+    # coulomb_atoms/cell_bounded.ini shape)
+    n, cps, length = 10, [4, 5, 4], 1.0
+    pos = configs.uniform_start(n, length, seed=9)
+    charges = np.ones(n)
+    chain_trace("trace_coulomb_cell_bounded",
+                configs.coulomb_atoms_ini(n, cps, points_per_side=4, far_field="cell_bounding",
+                                          estimator_prefactor=1.5, surplus_handlers=n),
+                pos, seed=13, stream=6, n_events=5000, snapshot_every=250, charges=charges,
+                meta=dict(n=n, cells_per_side=cps, system_length=length, beta=2.0, mic=[1.0, 3.45, 6, 2],
+                          ipcb=[1.5837], estimator=[1.5, 4], chain_time=0.78965, far_field=2))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["potentials", "base", "traces"]
+    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding"]
+    if "cell_bounding" in which:
+        cell_bounding_traces()
     if "potentials" in which:
         potential_vectors()
     if "base" in which:

@@ -97,7 +97,7 @@ class SlotRandom(random.Random):
         return None
 
 
-EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDARY, EVENT_END_OF_CHAIN = 1, 2, 3, 4
+EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDARY, EVENT_END_OF_CHAIN, EVENT_CELL_BOUNDING = 1, 2, 3, 4, 5
 HOST_EVENT = 0
 
 RECORD_DTYPE = np.dtype([("kind", "<i4"), ("target", "<i4"), ("target_cell", "<i4"), ("accepted", "<i4"),
@@ -170,6 +170,8 @@ class ReferenceRun:
         names = {cls.__name__ for cls in type(handler).__mro__}
         if "CellVetoEventHandler" in names:
             return EVENT_CELL_VETO
+        if "TwoLeafUnitCellBoundingPotentialEventHandler" in names:
+            return EVENT_CELL_BOUNDING
         if "CellBoundaryEventHandler" in names:
             return EVENT_CELL_BOUNDARY
         if "EndOfChainEventHandler" in names:
@@ -195,7 +197,7 @@ class ReferenceRun:
             orig_time, orig_out = h.send_event_time, h.send_out_state
 
             def send_event_time(*args, _h=h, _kind=kind, _orig=orig_time):
-                if _kind == EVENT_PAIR:
+                if _kind in (EVENT_PAIR, EVENT_CELL_BOUNDING):
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_of_pair(args[0])))
                 elif _kind == EVENT_CELL_VETO:
                     run.rng.set_context(run.events, make_slot(SLOT_VETO_TIME), make_slot(SLOT_VETO_CHOICE))
@@ -209,7 +211,7 @@ class ReferenceRun:
                     run.rng.clear_context()
 
             def send_out_state(*args, _h=h, _kind=kind, _orig=orig_out):
-                if _kind in (EVENT_PAIR, EVENT_CELL_VETO):
+                if _kind in (EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDING):
                     run.rng.set_context(run.events, make_slot(SLOT_CONFIRM))
                 else:
                     run.rng.clear_context()
@@ -293,6 +295,9 @@ class ReferenceRun:
         old_active = self._active()[0] if kind != EVENT_END_OF_CHAIN or self.events >= 0 else -1
         if kind == EVENT_PAIR:
             rec["target"] = [u.identifier[0] for u in winner._leaf_units if u.velocity is None][0]
+        elif kind == EVENT_CELL_BOUNDING:
+            rec["target"] = [u.identifier[0] for u in winner._leaf_units if u.velocity is None][0]
+            rec["target_cell"] = self._cell_index(winner._relative_cell)
         elif kind == EVENT_CELL_VETO:
             cell = self.mediator._out_state_arguments[winner][0]
             rec["target_cell"] = self._cell_index(cell)

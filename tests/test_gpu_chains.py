@@ -29,7 +29,7 @@ def assert_records_match(ours, ref, length, tag=""):
     assert np.max(np.abs(ours["active_pos"] - ref["active_pos"])) < RTOL * max(1.0, length), tag
 
 
-@pytest.mark.parametrize("name", tu.TRACES)
+@pytest.mark.parametrize("name", tu.TRACES + tu.CELL_BOUNDING_TRACES)
 def test_reference_trace_replay(name):
     g = tu.load_trace(name)
     records = g["records"]
@@ -183,6 +183,26 @@ def test_coulomb_batch_against_oracle(oracle):
     charges[0] = 1.0
     stats = _compare_batch_with_oracle(oracle, pb, positions, charges, 1200, 7, "coulomb")
     assert stats["pair_events"] > 100 and stats["veto_events"] > 1000
+
+
+def test_coulomb_cell_bounding_batch_against_oracle(oracle):
+    """Far field through TwoLeafUnitCellBoundingPotentialEventHandler: one candidate per occupied non-nearby cell
+    (coulomb_atoms/cell_bounded.ini shape), charges of both signs, more occupied far cells than one pass holds."""
+    n, cells, length = 60, [5, 4, 5], 1.0
+    mic = abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, 1.0, 3.45, 6, 2)
+    ipcb = abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, 1.5837)
+    bounds, _ = oracle.inner_point_derivative_bounds(mic, length, cells, 1, prefactor=1.5, points_per_side=3,
+                                                     target_charge=1.0, uses_charges=True)
+    pb = ProgramBuilder(3, n, length, 2.0, cells, 1, max_occupants=1, max_surplus=n, chain_time=0.78965, seed=33)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT_BOUNDING, mic, ipcb, use_charge=True)
+    pb.set_cell_bounding(mic, bounds, use_charge=True, target_charge=1.0)
+    rng = np.random.default_rng(78)
+    n_chains = 7
+    positions = rng.uniform(0.0, length, size=(n_chains, n, 3))
+    charges = np.where(rng.random((n_chains, n)) < 0.5, 1.0, -1.0)
+    charges[0] = 1.0
+    stats = _compare_batch_with_oracle(oracle, pb, positions, charges, 900, 3, "coulomb cell bounding")
+    assert stats["pair_events"] > 500 and stats["veto_events"] == 0
 
 
 def test_hard_disks_2d_against_oracle(oracle):

@@ -103,8 +103,11 @@ def test_many_chains_from_the_input_handler(tmp_path):
     assert len(set(states["event_counter"].tolist())) > 1  # the chains are different
 
 
-def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path):
-    """The statistical check of the reference (README.md:169-189): the shipped coulomb_atoms/cell_veto.ini, run
+@pytest.mark.parametrize("config,output", [("cell_veto.ini", "SamplesOfSeparation_CellVeto.dat"),
+                                           ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat")])
+def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path, config, output):
+    """The statistical check of the reference (README.md:169-189): the shipped coulomb_atoms/cell_veto.ini (far field
+    through the cell-veto handler) and cell_bounded.ini (through the cell-bounding potential handlers), run
     unchanged except for the mediator line, the output file and the run length, must reproduce the cumulative
     histogram of the pair separation that the reference ships (ReferenceDataCoulombAtoms.dat, reversible Monte Carlo;
     fixture tests/golden/reference_cdfs.npz). 2048 chains in parallel give ~10^5 samples in a few seconds."""
@@ -115,14 +118,13 @@ def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path):
     import jellyfysh_b200
     jellyfysh_b200.install()
     from jellyfysh.base.exceptions import EndOfRun
-    path = os.path.join(REF, "jellyfysh", "config_files", "2018_JCP_149_064113", "coulomb_atoms", "cell_veto.ini")
+    path = os.path.join(REF, "jellyfysh", "config_files", "2018_JCP_149_064113", "coulomb_atoms", config)
     ini = open(path).read()
     chains = 2048
     ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
     ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 11" % chains)
     ini = ini.replace("end_of_run_time = 100000", "end_of_run_time = 40")
-    ini = ini.replace("output/2018_JCP_149_064113/coulomb_atoms/SamplesOfSeparation_CellVeto.dat",
-                      str(tmp_path / "separation.dat"))
+    ini = ini.replace("output/2018_JCP_149_064113/coulomb_atoms/" + output, str(tmp_path / "separation.dat"))
     assert "cuda_batched_mediator" in ini and str(tmp_path) in ini
     mediator, setting = build_reference_graph(ini)
     try:

@@ -66,6 +66,31 @@ def test_chain_replay_bit_exact(oracle, name):
     assert chain.stats()["capacity_errors"] == 0
 
 
+@pytest.mark.parametrize("name", tu.CELL_BOUNDING_TRACES)
+def test_cell_bounding_chain_replay_bit_exact(oracle, name):
+    """Far field through TwoLeafUnitCellBoundingPotentialEventHandler (coulomb_atoms/cell_bounded.ini shape)."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    # the bounds are those of the inner point estimator, rebuilt by the oracle's restatement
+    _, _, _, veto, use_charge = tu.potentials_of(g)
+    cps = [int(c) for c in g["meta_cells_per_side"]]
+    bounds, _ = oracle.inner_point_derivative_bounds(veto, float(g["meta_system_length"]), cps, 1,
+                                                     prefactor=float(g["meta_estimator"][0]),
+                                                     points_per_side=int(g["meta_estimator"][1]), target_charge=1.0,
+                                                     uses_charges=use_charge)
+    assert np.array_equal(bounds, g["bounds"], equal_nan=True)
+    chain = oracle.OracleChain(tu.builder_of(g, oracle.ProgramBuilder, tables={"bounds": bounds}))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.start(stream=int(g["seed"][1]))
+    n, rec = chain.run(max_events=len(records), record=len(records))
+    assert n == len(records)
+    assert (rec["kind"] == 5).sum() > 1000
+    assert tu.records_equal_discrete(rec, records)
+    assert np.array_equal(rec["time_q"], records["time_q"]) and np.array_equal(rec["time_r"], records["time_r"])
+    assert np.array_equal(rec["active_pos"], records["active_pos"])
+    assert np.array_equal(chain.positions(), g["final_positions"])
+
+
 def test_time_limit_keeps_candidates(oracle):
     """Stopping at host control times (sampling) keeps the interaction winner: the event sequence is the same
     whether the chain runs in one go or is interrupted, up to the rounding of the extra time slices."""

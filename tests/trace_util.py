@@ -5,6 +5,7 @@ import kat_replay as kr
 from jellyfysh_b200 import abi
 
 TRACES = ["trace_lj_small", "trace_lj_surplus", "trace_coulomb_small", "trace_coulomb_surplus"]
+CELL_BOUNDING_TRACES = ["trace_coulomb_cell_bounded"]
 DISCRETE_FIELDS = ("kind", "target", "target_cell", "accepted", "n_candidates", "new_active", "new_direction")
 
 
@@ -36,7 +37,12 @@ def builder_of(g, builder_cls, tables=None, max_surplus=128):
                      max_occupants=1, max_surplus=max_surplus, chain_time=float(g["meta_chain_time"]),
                      seed=int(g["seed"][0]))
     pb.set_pair(handler, pot, bound, use_charge=use_charge)
-    pb.set_veto(veto, tables if tables is not None else reference_tables(g), use_charge=use_charge, target_charge=1.0)
+    if "meta_far_field" in g and int(g["meta_far_field"]) == abi.FAR_CELL_BOUNDING:
+        pb.set_cell_bounding(veto, g["bounds"] if tables is None else tables["bounds"], use_charge=use_charge,
+                             target_charge=1.0)
+    else:
+        pb.set_veto(veto, tables if tables is not None else reference_tables(g), use_charge=use_charge,
+                    target_charge=1.0)
     return pb
 
 
