@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-#define ECMC_ABI_VERSION 1
+#define ECMC_ABI_VERSION 2
+#define ECMC_MAX_BONDS 4
 #define ECMC_MAX_DIM 3
 
 /* ---- status codes ---------------------------------------------------------------------------------- */
@@ -148,6 +149,20 @@ typedef struct EcmcProgram {
     /* counter-based random stream, see DESIGN.md "Random stream" */
     uint32_t seed;
     uint32_t reserved1;
+    /* ---- composite point objects (dipoles, molecules): TreeStateHandler with two node levels,
+     * jellyfysh/state_handler/tree_state_handler.py:104-230. The n_particles leaf units are grouped into
+     * n_particles / nodes_per_root root units; leaf (root r, child k) has the flat identifier r * nodes_per_root + k.
+     * The root unit of the active leaf moves with velocity * weight, weight = 1 / nodes_per_root
+     * (event_handler/abstracts/abstracts.py:165-227), its position is kept alongside (ecmc_upload_roots).
+     * nodes_per_root <= 1: point masses only (single node level). Cells hold leaf identifiers (cell_level = 2). */
+    int32_t nodes_per_root;
+    /* Intramolecular two-leaf factors from a factor type map (FactorTypeMapInStateTagger,
+     * jellyfysh/activator/tagger/factor_type_map_in_state_tagger.py:83-107, e.g. "[0, 1], Dipole" of
+     * config_files/factor_set_files/factor_set_hard_disk_dipoles.txt): pairs of child indices (a, b) of the same root,
+     * each handled by a TwoLeafUnitEventHandler with bond_potential (hard dipole tether, harmonic bond). */
+    int32_t n_bonds;
+    int32_t bonds[ECMC_MAX_BONDS][2];
+    EcmcPotential bond_potential;
 } EcmcProgram;
 
 /* ---- per-chain lifting state ("who is active, where is the clock") ------------------------------------
@@ -158,12 +173,13 @@ typedef struct EcmcChainState {
     int32_t direction;        /* direction of motion */
     double time_q, time_r;    /* time stamp of the active particle as (quotient, remainder), base/time.py */
     double eoc_q, eoc_r;      /* scheduled end-of-chain event time */
-    int32_t eoc_next_active;  /* particle drawn (randint) when the end-of-chain candidate was created */
+    int32_t eoc_next_active;  /* leaf drawn (randint; root then child for composite objects) when the end-of-chain
+                               * candidate was created */
     int32_t active_cell;      /* flat cell index the occupancy system attributes to the active particle */
     uint64_t event_counter;   /* events committed so far: the random-stream event index */
     uint32_t stream;          /* random-stream id of this chain (Philox key word 0) */
     int32_t pending_kind;     /* EcmcEventKind of a candidate kept across a host control event, or 0 */
-    int32_t pending_target;   /* pair: target id; veto: target cell */
+    int32_t pending_target;   /* pair / bond: target id; veto, boundary: target cell */
     int32_t reserved;
     double pending_q, pending_r;
     double pending_rate;      /* bounding event rate stored by the handler for the confirmation step */
@@ -171,6 +187,7 @@ typedef struct EcmcChainState {
      * time-sliced the active particle: coordinate along the direction of motion and time stamp at that moment. */
     double pending_position;
     double pending_stamp_q, pending_stamp_r;
+    double pending_root_position; /* the same for the root unit of the active leaf (composite objects) */
 } EcmcChainState;
 
 enum EcmcEventKind {
@@ -179,7 +196,8 @@ enum EcmcEventKind {
     ECMC_EVENT_CELL_VETO = 2,
     ECMC_EVENT_CELL_BOUNDARY = 3,
     ECMC_EVENT_END_OF_CHAIN = 4,
-    ECMC_EVENT_CELL_BOUNDING = 5  /* pair factor of a non-nearby cell, found through the cell-bounding potential */
+    ECMC_EVENT_CELL_BOUNDING = 5, /* pair factor of a non-nearby cell, found through the cell-bounding potential */
+    ECMC_EVENT_BOND = 6           /* intramolecular two-leaf factor of the factor type map (EcmcProgram.bonds) */
 };
 
 /* One committed event, as the scheduler + winning handler of the reference would report it. */
@@ -206,7 +224,8 @@ typedef struct EcmcStats {
     uint64_t candidates;        /* finite candidates that entered an argmin */
     uint64_t bound_violations;  /* real derivative exceeded its bound (reference: bounding_potential_warning) */
     uint64_t capacity_errors;   /* surplus / occupant overflow (fatal: results invalid) */
-    uint64_t reserved[3];
+    uint64_t bond_events;       /* events of the intramolecular factor-type-map factors */
+    uint64_t reserved[2];
 } EcmcStats;
 
 typedef struct EcmcHandle EcmcHandle;
@@ -222,6 +241,10 @@ int ecmc_abi_version(void);
 /* positions: [n_chains][n_particles][dimension] doubles; charges: [n_chains][n_particles] or NULL (all 1.0). */
 int ecmc_upload_positions(EcmcHandle *h, const double *positions, const double *charges);
 int ecmc_download_positions(EcmcHandle *h, double *positions);
+/* Root-unit positions of composite objects, [n_chains][n_particles / nodes_per_root][dimension] (programs with
+ * nodes_per_root > 1 only; ECMC_ERR_INVALID otherwise). Must be uploaded before ecmc_start. */
+int ecmc_upload_roots(EcmcHandle *h, const double *roots);
+int ecmc_download_roots(EcmcHandle *h, double *roots);
 /* InitialChainStartOfRunEventHandler (initial_chain_start_of_run_event_handler.py:92-131) +
  * SingleActiveCellOccupancy.initialize (single_active_cell_occupancy.py:95-121): bins all particles,
  * activates program.initial_active at time 0 and schedules the first end-of-chain event.
@@ -294,6 +317,7 @@ void ecmc_random_words(uint32_t seed, uint32_t stream, uint64_t event, uint32_t 
 #define ECMC_SLOT_CONFIRM 4u         /* double 0 -> uniform(0, bounding rate) in the out-state */
 #define ECMC_SLOT_END_OF_CHAIN 5u    /* words -> randint(0, n_particles - 1) (rejection loop) */
 #define ECMC_SLOT_LIFTING 6u         /* doubles -> Lifting.insert / RatioLifting draws */
+#define ECMC_SLOT_FACTOR_TIME 7u     /* index = target leaf; factor-type-map pair factors: double 0 -> expovariate(beta) */
 #define ECMC_SLOT(kind, index) (((uint32_t)(kind) << 24) | ((uint32_t)(index) & 0xFFFFFFu))
 
 #ifdef __cplusplus

@@ -1,8 +1,9 @@
 """ctypes mirror of include/ecmc.h (the C ABI of libecmc_b200.so). Plain data only, no computation."""
 import ctypes as C
 
-ECMC_ABI_VERSION = 1
+ECMC_ABI_VERSION = 2
 ECMC_MAX_DIM = 3
+ECMC_MAX_BONDS = 4
 
 ECMC_OK = 0
 ECMC_ERR_INVALID = -1
@@ -29,13 +30,14 @@ EVENT_CELL_VETO = 2
 EVENT_CELL_BOUNDARY = 3
 EVENT_END_OF_CHAIN = 4
 EVENT_CELL_BOUNDING = 5
+EVENT_BOND = 6
 
 FAR_NONE = 0
 FAR_CELL_VETO = 1
 FAR_CELL_BOUNDING = 2
 EVENT_NAMES = {EVENT_NONE: "none", EVENT_PAIR: "pair", EVENT_CELL_VETO: "cell_veto",
                EVENT_CELL_BOUNDARY: "cell_boundary", EVENT_END_OF_CHAIN: "end_of_chain",
-               EVENT_CELL_BOUNDING: "cell_bounding"}
+               EVENT_CELL_BOUNDING: "cell_bounding", EVENT_BOND: "bond"}
 
 SLOT_PAIR_TIME = 1
 SLOT_VETO_TIME = 2
@@ -43,6 +45,7 @@ SLOT_VETO_CHOICE = 3
 SLOT_CONFIRM = 4
 SLOT_END_OF_CHAIN = 5
 SLOT_LIFTING = 6
+SLOT_FACTOR_TIME = 7
 
 
 def slot(kind: int, index: int = 0) -> int:
@@ -87,7 +90,9 @@ class EcmcProgram(C.Structure):
                 ("veto_tables", C.POINTER(EcmcVetoTables)),
                 ("chain_time", C.c_double), ("speed", C.c_double),
                 ("initial_direction", C.c_int32), ("initial_active", C.c_int32),
-                ("seed", C.c_uint32), ("reserved1", C.c_uint32)]
+                ("seed", C.c_uint32), ("reserved1", C.c_uint32),
+                ("nodes_per_root", C.c_int32), ("n_bonds", C.c_int32),
+                ("bonds", (C.c_int32 * 2) * ECMC_MAX_BONDS), ("bond_potential", EcmcPotential)]
 
 
 class EcmcChainState(C.Structure):
@@ -99,7 +104,8 @@ class EcmcChainState(C.Structure):
                 ("stream", C.c_uint32), ("pending_kind", C.c_int32),
                 ("pending_target", C.c_int32), ("reserved", C.c_int32),
                 ("pending_q", C.c_double), ("pending_r", C.c_double), ("pending_rate", C.c_double),
-                ("pending_position", C.c_double), ("pending_stamp_q", C.c_double), ("pending_stamp_r", C.c_double)]
+                ("pending_position", C.c_double), ("pending_stamp_q", C.c_double), ("pending_stamp_r", C.c_double),
+                ("pending_root_position", C.c_double)]
 
 
 class EcmcEventRecord(C.Structure):
@@ -114,7 +120,7 @@ class EcmcStats(C.Structure):
                 ("veto_accepted", C.c_uint64), ("boundary_events", C.c_uint64),
                 ("end_of_chain_events", C.c_uint64), ("candidates", C.c_uint64),
                 ("bound_violations", C.c_uint64), ("capacity_errors", C.c_uint64),
-                ("reserved", C.c_uint64 * 3)]
+                ("bond_events", C.c_uint64), ("reserved", C.c_uint64 * 2)]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
@@ -135,8 +141,9 @@ def chain_state_dtype():
                      ("event_counter", "<u8"), ("stream", "<u4"), ("pending_kind", "<i4"),
                      ("pending_target", "<i4"), ("reserved", "<i4"),
                      ("pending_q", "<f8"), ("pending_r", "<f8"), ("pending_rate", "<f8"),
-                     ("pending_position", "<f8"), ("pending_stamp_q", "<f8"), ("pending_stamp_r", "<f8")])
+                     ("pending_position", "<f8"), ("pending_stamp_q", "<f8"), ("pending_stamp_r", "<f8"),
+                     ("pending_root_position", "<f8")])
 
 
 assert C.sizeof(EcmcEventRecord) == 72
-assert C.sizeof(EcmcChainState) == 120
+assert C.sizeof(EcmcChainState) == 128

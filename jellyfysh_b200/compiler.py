@@ -59,6 +59,17 @@ def _charge_name(charges_function):
     return names.pop() if names else None
 
 
+def _root_with_exact_square(square, scale=1.0):
+    """x with scale * x * x == square in floating point (the reference stores only the squares, e.g.
+    hard_sphere_potential.py:63 `4.0 * radius * radius`; the device recomputes them the same way from x)."""
+    import math
+    x = math.sqrt(square / scale)
+    for candidate in (x, math.nextafter(x, 0.0), math.nextafter(x, math.inf)):
+        if scale * candidate * candidate == square:
+            return candidate
+    raise _configuration_error("cannot recover a length from its stored square {0!r}".format(square))
+
+
 def potential_descriptor(potential):
     """EcmcPotential of a reference potential object (jellyfysh/potential/*)."""
     names = _class_names(potential)
@@ -71,7 +82,11 @@ def potential_descriptor(potential):
         return abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, potential._prefactor,
                                       potential._equilibrium_separation, potential._power)
     if "HardSpherePotential" in names:
-        return abi.EcmcPotential.make(abi.POT_HARD_SPHERE, (potential._diameter_squared / 4.0) ** 0.5)
+        return abi.EcmcPotential.make(abi.POT_HARD_SPHERE, _root_with_exact_square(potential._diameter_squared, 4.0))
+    if "HardDipolePotential" in names:
+        # hard_dipole_potential.py:72-73
+        return abi.EcmcPotential.make(abi.POT_HARD_DIPOLE, _root_with_exact_square(potential._minimum_separation_squared),
+                                      _root_with_exact_square(potential._maximum_separation_squared))
     if "MergedImageCoulombPotential" in names:
         # merged_image_coulomb_potential.py:111-118
         return abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, potential._prefactor, potential._alpha,
@@ -88,29 +103,34 @@ def _same_potential(a, b):
 class CompiledProgram:
     """The result: a ProgramBuilder plus what the mediator needs around it."""
 
-    def __init__(self, builder, charge_name, control_handlers, n_particles):
+    def __init__(self, builder, charge_name, control_handlers, n_particles, nodes_per_root=1):
         self.builder = builder
         self.charge_name = charge_name
         self.control_handlers = control_handlers  # sampling / end-of-run handlers, run on the host
-        self.n_particles = n_particles
+        self.n_particles = n_particles            # leaf units
+        self.nodes_per_root = nodes_per_root      # 1: point masses; > 1: composite point objects
 
 
-def compile_program(activator, extracted_global_state, seed=0, max_surplus=None):
+def compile_program(activator, extracted_global_state, seed=0, max_surplus=None, occupant_capacity=8):
     """Walk the initialized activator and return a CompiledProgram.
 
-    extracted_global_state: state_handler.extract_global_state() (root cnodes), used for N and the node structure."""
+    extracted_global_state: state_handler.extract_global_state() (root cnodes), used for N and the node structure.
+    occupant_capacity: occupants stored per cell on the device when the reference's occupancy is unbounded
+    (maximum_number_occupants = -1); an overflow is reported as a capacity error, never silently dropped."""
     import jellyfysh.setting as setting
     from jellyfysh.setting import hypercubic_setting
 
-    if setting.number_of_node_levels != 1:
-        raise _configuration_error("only point-mass (single level) systems run on the device in this version; composite "
-                                   "objects (dipoles, water) need the composite-object handlers")
+    levels = setting.number_of_node_levels
+    if levels not in (1, 2):
+        raise _configuration_error("only trees with one or two node levels are supported")
+    nodes_per_root = setting.number_of_nodes_per_root_node if levels == 2 else 1
     for cnode in extracted_global_state:
-        if cnode.children:
-            raise _configuration_error("root nodes with children are not supported")
+        if len(cnode.children) != (nodes_per_root if levels == 2 else 0):
+            raise _configuration_error("every root node must have the same number of leaf nodes")
     if not hypercubic_setting.initialized():
         raise _configuration_error("a hypercubic setting is required")
-    dimension, length, n_particles = setting.dimension, hypercubic_setting.system_length, len(extracted_global_state)
+    dimension, length = setting.dimension, hypercubic_setting.system_length
+    n_particles = len(extracted_global_state) * nodes_per_root
 
     # ---- cell occupancy (tag_activator.py:82-135 keeps the internal states in _internal_states)
     internal_states = list(activator._internal_states)
@@ -120,21 +140,37 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None)
     cells = occupancy.cells
     if "CuboidPeriodicCells" not in _class_names(cells):
         raise _configuration_error("cells must be CuboidPeriodicCells")
-    if occupancy.cell_level != 1:
-        raise _configuration_error("cell_level must be 1")
+    if occupancy.cell_level != levels:
+        raise _configuration_error("the cells must hold leaf units (cell_level = number of node levels); composite "
+                                   "objects in root-level cells (water, dipoles of 2018_JCP_149_064113) need the "
+                                   "composite-object handlers")
     max_occupants = occupancy._maximum_number_occupants  # cell_occupancy.py:70-72
-    if max_occupants <= 0:
-        raise _configuration_error("an unbounded number of occupants per cell is not supported: set maximum_number_occupants")
+    unbounded = max_occupants <= 0
+    if unbounded:
+        # the reference keeps plain lists per cell and never uses the surplus; the device keeps `occupant_capacity`
+        # slots per cell and no surplus, so that an overflow surfaces as a capacity error
+        max_occupants, max_surplus = occupant_capacity, 0
     cells_per_side = list(cells._cells_per_side)
     neighbor_layers = cells._neighbor_layers
     cell_objects = list(cells.yield_cells())  # flat index order (cuboid_cells.py:144-146)
 
     # ---- handlers by kind
     pair_handlers, veto_handlers, boundary_handlers, eoc_handlers, start_handlers, control = [], [], [], [], [], []
-    bounding_handlers = []
+    bounding_handlers, bond_handlers = [], []
+    # handlers fed by a factor type map are intramolecular factors (factor_type_map_in_state_tagger.py:83-107)
+    factor_tagger_of = {}
+    for tagger in activator._taggers:
+        if "FactorTypeMapInStateTagger" in _class_names(tagger):
+            for handler in tagger.get_event_handlers():
+                factor_tagger_of[id(handler)] = tagger
     for handler in activator.get_event_handlers():
         names = _class_names(handler)
-        if "TwoLeafUnitCellBoundingPotentialEventHandler" in names:
+        if id(handler) in factor_tagger_of:
+            if "TwoLeafUnitEventHandler" not in names:
+                raise _configuration_error("factor-type-map handler {0} has no device implementation"
+                                           .format(type(handler).__name__))
+            bond_handlers.append(handler)
+        elif "TwoLeafUnitCellBoundingPotentialEventHandler" in names:
             bounding_handlers.append(handler)
         elif "TwoLeafUnitBoundingPotentialEventHandler" in names or "TwoLeafUnitEventHandler" in names:
             pair_handlers.append(handler)
@@ -161,8 +197,9 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None)
     if len(moving) != 1 or velocity[moving[0]] <= 0.0:
         raise _configuration_error("the initial velocity must be along one positive axis")
     initial_active = tuple(start._initial_active_identifier)
-    if len(initial_active) != 1:
-        raise _configuration_error("the initial active identifier must name a root node")
+    if len(initial_active) != levels:
+        raise _configuration_error("the initial active identifier must name a leaf unit")
+    initial_leaf = initial_active[0] if levels == 1 else initial_active[0] * nodes_per_root + initial_active[1]
     if not any("EndOfRunEventHandler" in _class_names(h) for h in control):
         raise _configuration_error("an end-of-run handler is required")
 
@@ -170,7 +207,30 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None)
                              max_occupants=max_occupants,
                              max_surplus=n_particles if max_surplus is None else max_surplus,
                              chain_time=eoc._chain_time, speed=velocity[moving[0]], initial_direction=moving[0],
-                             initial_active=initial_active[0], seed=seed)
+                             initial_active=initial_leaf, seed=seed)
+
+    # ---- composite point objects: intramolecular pair factors of the factor type map
+    if levels == 2:
+        bonds, bond_potential = [], None
+        for handler in bond_handlers:
+            factor_map = factor_tagger_of[id(handler)]._factor_type_map
+            if not getattr(factor_map, "_local", False):
+                raise _configuration_error("only local (intramolecular) factor type maps are supported")
+            if _charge_name(handler._charges) is not None:
+                raise _configuration_error("intramolecular factors with charges are not supported")
+            potential = potential_descriptor(handler._potential)
+            if bond_potential is not None and not _same_potential(bond_potential, potential):
+                raise _configuration_error("all intramolecular pair factors must share one potential")
+            bond_potential = potential
+            for entries in factor_map.map.values():
+                for indices in entries:
+                    if len(indices) != 2:
+                        raise _configuration_error("only two-unit intramolecular factors are supported")
+                    if tuple(sorted(indices)) not in bonds:
+                        bonds.append(tuple(sorted(indices)))
+        builder.set_composite(nodes_per_root, bonds, bond_potential)
+    elif bond_handlers:
+        raise _configuration_error("factor type maps need composite point objects")
 
     # ---- pair factor
     charge_names = set()
@@ -247,13 +307,18 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None)
             charge_names.add(charge)
     if len(charge_names) > 1:
         raise _configuration_error("pair and cell-veto handlers use different charges: {0}".format(sorted(charge_names)))
-    return CompiledProgram(builder, charge_names.pop() if charge_names else None, control, n_particles)
+    return CompiledProgram(builder, charge_names.pop() if charge_names else None, control, n_particles, nodes_per_root)
 
 
 def positions_and_charges(extracted_global_state, charge_name):
-    """(positions[N][D], charges[N] or None) of root cnodes (tree_state_handler.py:213-230)."""
-    positions = np.array([cnode.value.position for cnode in extracted_global_state], dtype=np.float64)
+    """(positions[N][D] of the leaf units, charges[N] or None, roots[N_root][D] or None) of root cnodes
+    (tree_state_handler.py:213-230); leaves in flat order root * nodes_per_root + child."""
+    composite = bool(extracted_global_state[0].children)
+    leaves = ([child for cnode in extracted_global_state for child in cnode.children] if composite
+              else list(extracted_global_state))
+    positions = np.array([leaf.value.position for leaf in leaves], dtype=np.float64)
     charges = None
     if charge_name is not None:
-        charges = np.array([cnode.value.charge[charge_name] for cnode in extracted_global_state], dtype=np.float64)
-    return positions, charges
+        charges = np.array([leaf.value.charge[charge_name] for leaf in leaves], dtype=np.float64)
+    roots = np.array([cnode.value.position for cnode in extracted_global_state], dtype=np.float64) if composite else None
+    return positions, charges, roots

@@ -42,6 +42,7 @@ struct EcmcHandle {
     std::vector<void *> allocations;
     EcmcStats *d_stats = nullptr;
     EcmcStats *h_stats = nullptr;     // pinned
+    bool roots_uploaded = false;
     double *d_staging = nullptr;      // [n_chains][n_particles][dimension] + charges
     double *d_staging_charges = nullptr;
     uint32_t *d_streams = nullptr;
@@ -270,10 +271,27 @@ int build_device_program(EcmcHandle *h) {
     d.veto_target_charge = p.veto_target_charge;
     d.inv_beta = 1.0 / p.beta;
     d.inv_speed = 1.0 / p.speed;
+    // composite point objects
+    d.nodes_per_root = p.nodes_per_root > 1 ? p.nodes_per_root : 1;
+    if (p.n_particles % d.nodes_per_root) return fail(h, ECMC_ERR_INVALID, "n_particles must be a multiple of nodes_per_root");
+    if (p.n_bonds < 0 || p.n_bonds > ECMC_MAX_BONDS || (p.n_bonds > 0 && d.nodes_per_root == 1))
+        return fail(h, ECMC_ERR_INVALID, "bonds need composite objects and n_bonds <= ECMC_MAX_BONDS");
+    d.n_bonds = p.n_bonds;
+    for (int b = 0; b < p.n_bonds; b++)
+        for (int k = 0; k < 2; k++) {
+            if (p.bonds[b][k] < 0 || p.bonds[b][k] >= d.nodes_per_root || p.bonds[b][0] == p.bonds[b][1])
+                return fail(h, ECMC_ERR_INVALID, "bond child indices out of range");
+            d.bonds[b][k] = p.bonds[b][k];
+        }
+    d.root_speed = p.speed * (1.0 / d.nodes_per_root);  // velocity component * weight (abstracts.py:181)
 
     // potentials
     int rc;
     bool relative_modular = true;
+    if (p.n_bonds > 0) {
+        if (!is_invertible(p.bond_potential.kind)) return fail(h, ECMC_ERR_INVALID, "bond potential is not invertible");
+        if ((rc = make_potential(h, p.bond_potential, p.system_length, &d.bond_potential))) return rc;
+    }
     if (p.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT) {
         if (!is_invertible(p.pair_potential.kind)) return fail(h, ECMC_ERR_INVALID, "pair potential is not invertible");
         if ((rc = make_potential(h, p.pair_potential, p.system_length, &d.cand_potential))) return rc;
@@ -373,10 +391,15 @@ typedef void (*EventKernel)(const DeviceProgram, const DeviceState, const RunArg
 template <int CAND, int REAL, int VETO>
 EventKernel pick_record(bool record, bool single) {
     if (single)
-        return record ? event_kernel<CAND, REAL, VETO, true, true, kWarpsPerBlock>
-                      : event_kernel<CAND, REAL, VETO, true, false, kWarpsPerBlock>;
-    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock>
-                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock>;
+        return record ? event_kernel<CAND, REAL, VETO, true, true, kWarpsPerBlock, false>
+                      : event_kernel<CAND, REAL, VETO, true, false, kWarpsPerBlock, false>;
+    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock, false>
+                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock, false>;
+}
+template <int CAND, int REAL, int VETO>
+EventKernel pick_composite(bool record) {
+    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock, true>
+                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock, true>;
 }
 
 EventKernel pick_kernel(const DeviceProgram &d, bool record) {
@@ -386,6 +409,11 @@ EventKernel pick_kernel(const DeviceProgram &d, bool record) {
     const int LJ = ECMC_POT_LENNARD_JONES, HS = ECMC_POT_HARD_SPHERE, MIC = ECMC_POT_MERGED_IMAGE_COULOMB,
               IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING;
     const bool single = d.max_occupants == 1;
+    if (d.nodes_per_root > 1) {
+        // composite point objects: hard disks / spheres tethered into dipoles (C1), anything else generic
+        if (cand == HS && real == 0 && veto == 0) return pick_composite<ECMC_POT_HARD_SPHERE, 0, 0>(record);
+        return pick_composite<-1, -1, -1>(record);
+    }
     if (cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record, single);
     if (cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record, single);
     if (cand == HS && real == 0 && veto == 0) return pick_record<ECMC_POT_HARD_SPHERE, 0, 0>(record, false);
@@ -495,6 +523,7 @@ ECMC_API int ecmc_create(const EcmcProgram *program, int device, int n_chains, E
         h->state.n_chains = n_chains;
         h->state.first_chain = 0;
         if ((rc = device_alloc(h, &h->state.particles, n))) break;
+        if (d.nodes_per_root > 1 && (rc = device_alloc(h, &h->state.roots, n / d.nodes_per_root))) break;
         if ((rc = device_alloc(h, &h->state.occupants, (size_t)n_chains * d.n_cells * d.max_occupants))) break;
         if ((rc = device_alloc(h, &h->state.surplus, (size_t)n_chains * d.max_surplus))) break;
         if ((rc = device_alloc(h, &h->state.n_surplus, (size_t)n_chains))) break;
@@ -553,8 +582,37 @@ ECMC_API int ecmc_download_positions(EcmcHandle *h, double *positions) {
     return collect_timings(h);
 }
 
+ECMC_API int ecmc_upload_roots(EcmcHandle *h, const double *roots) {
+    if (!h || !roots) return fail(h, ECMC_ERR_INVALID, "null argument");
+    if (h->dprog.nodes_per_root <= 1) return fail(h, ECMC_ERR_INVALID, "the program has no composite objects");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_chains * (h->dprog.n_particles / h->dprog.nodes_per_root);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_staging, roots, n * h->dprog.dimension * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    pack_particles_kernel<<<blocks, 256, 0, h->stream>>>(h->d_staging, nullptr, h->state.roots, n, h->dprog.dimension);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->roots_uploaded = true;
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_download_roots(EcmcHandle *h, double *roots) {
+    if (!h || !roots) return fail(h, ECMC_ERR_INVALID, "null argument");
+    if (h->dprog.nodes_per_root <= 1) return fail(h, ECMC_ERR_INVALID, "the program has no composite objects");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_chains * (h->dprog.n_particles / h->dprog.nodes_per_root);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    unpack_particles_kernel<<<blocks, 256, 0, h->stream>>>(h->state.roots, h->d_staging, n, h->dprog.dimension);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(roots, h->d_staging, n * h->dprog.dimension * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ECMC_OK;
+}
+
 ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_stream) {
     if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
+    if (h->dprog.nodes_per_root > 1 && !h->roots_uploaded)
+        return fail(h, ECMC_ERR_STATE, "composite objects: ecmc_upload_roots before ecmc_start");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (streams)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_streams, streams, sizeof(uint32_t) * h->n_chains, cudaMemcpyHostToDevice, h->stream));
@@ -667,6 +725,8 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
                                 double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
                                 EcmcStats *stats) {
     if (!h || !positions_in) return fail(h, ECMC_ERR_INVALID, "null argument");
+    if (h->dprog.nodes_per_root > 1 && !h->roots_uploaded)
+        return fail(h, ECMC_ERR_STATE, "composite objects: ecmc_upload_roots before ecmc_run_from_host");
     if (std::isnan(until_q) || std::isnan(until_r)) return fail(h, ECMC_ERR_INVALID, "until time is NaN");
     if (max_events_per_chain <= 0 && std::isinf(until_q))
         return fail(h, ECMC_ERR_INVALID, "neither a time limit nor an event limit: the run would not end");

@@ -240,7 +240,23 @@ ECMC_D Particle rotate_out(const Moving &m, int dir) {
     return q;
 }
 
-template <int CAND, int REAL, int VETO, bool SINGLE, bool RECORD, int WARPS>
+// The unit that becomes active at the next end of chain: randint over the point masses, or for composite objects
+// (randint over the roots, randint over the children), continuing in the same word stream
+// (single_independent_active_periodic_direction_end_of_chain_event_handler.py:203-237).
+ECMC_D int draw_end_of_chain_active(const DeviceProgram &P, const StreamKey &key) {
+    if (P.nodes_per_root <= 1)
+        return (int)stream_randbelow(key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.n_particles);
+    uint32_t index = 0;
+    const uint32_t root = stream_randbelow_from(key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0),
+                                                (uint32_t)(P.n_particles / P.nodes_per_root), index);
+    const uint32_t child = stream_randbelow_from(key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.nodes_per_root, index);
+    return (int)(root * (uint32_t)P.nodes_per_root + child);
+}
+
+// COMPOSITE: the point masses are leaves of composite point objects (EcmcProgram.nodes_per_root > 1): the root unit of
+// the active leaf is time-sliced with it, and the factor-type-map pair factors inside the active leaf's object
+// (EcmcProgram.bonds) are extra candidates.
+template <int CAND, int REAL, int VETO, bool SINGLE, bool RECORD, int WARPS, bool COMPOSITE>
 __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     __shared__ double trig_all[UsesMic<REAL, VETO>::value ? WARPS * kTrigDoubles : 1];
@@ -270,6 +286,10 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     bool was_pending = stp->pending_kind != ECMC_EVENT_NONE;  // only the first iteration can start from a kept candidate
     int n_surplus = S.n_surplus[chain];
     Moving a = rotate_in(part[active], dir);
+    // composite objects: the root unit of the active leaf, coordinate along the direction of motion
+    Particle *roots = COMPOSITE ? S.roots + (size_t)chain * (P.n_particles / P.nodes_per_root) : nullptr;
+    double root_p0 = 0.0;
+    if (COMPOSITE) root_p0 = component(roots[active / P.nodes_per_root], dir);
     // per-axis identifiers of the active cell: scalars, never indexed by a runtime direction (that would put them
     // into local memory)
     int cid0 = (active_cell / P.cumulative[0]) % P.per_side[0];
@@ -296,6 +316,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
 
     Counters n = {0, 0, 0, 0, 0ull};
+    unsigned n_bond_events = 0;
     bool stopped_by_time = false;
 
     while (n.events < max_events) {
@@ -307,16 +328,18 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         int n_cand = 0;
         bool have_confirmation = false;  // the confirmation draw of this event is already known
         double u_confirmation = 0.0;
-        double kept_position = 0.0;
+        double kept_position = 0.0, kept_root_position = 0.0;
         Time kept_stamp = now;
         if (was_pending) {
             // a candidate that survived a host control event: nothing is recomputed, no draws are consumed
             bkind = stp->pending_kind;
             bt.q = stp->pending_q; bt.r = stp->pending_r;
             brate = stp->pending_rate;
-            if (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING) btarget = stp->pending_target;
+            if (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING || bkind == ECMC_EVENT_BOND)
+                btarget = stp->pending_target;
             else bcell = stp->pending_target;
             kept_position = stp->pending_position;
+            if (COMPOSITE) kept_root_position = stp->pending_root_position;
             kept_stamp.q = stp->pending_stamp_q; kept_stamp.r = stp->pending_stamp_r;
         } else {
             // Candidate gather: the occupant slots of the nearby cells, then the surplus list, are scanned 32 at a time
@@ -329,8 +352,11 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             const int n_pair_slots = has_pairs ? nearby_slots + n_surplus : 0;
             // with a cell-bounding far field every occupied cell that is not nearby is one more candidate
             // (cell_bounding_potential_tagger.py:150-155); these slots follow the pair slots, one per cell
-            const int n_scan_slots = n_pair_slots + (has_far_pairs ? P.n_cells : 0);
-            const int special_seq = n_pair_slots + P.n_cells;
+            // composite objects: the factor-type-map factors of the active leaf's object come after the pair slots
+            const int n_bond_slots = COMPOSITE ? P.n_bonds : 0;
+            const int far_base = n_pair_slots + n_bond_slots;
+            const int n_scan_slots = far_base + (has_far_pairs ? P.n_cells : 0);
+            const int special_seq = far_base + P.n_cells;
             const double c_active = P.pair_use_charge ? a.charge : 1.0;
             unsigned long long best_key = 0x7ff0000000000000ull;  // best of the passes so far (uniform)
             double best_x = INFINITY;
@@ -353,8 +379,13 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     found = occ[cell * m + (s - ci * m)];
                 } else if (s < n_pair_slots) {
                     found = sur[s - nearby_slots];
+                } else if (COMPOSITE && s < far_base) {
+                    const int b = s - n_pair_slots;
+                    const int root = active / P.nodes_per_root, child = active - root * P.nodes_per_root;
+                    const int partner = P.bonds[b][0] == child ? P.bonds[b][1] : (P.bonds[b][1] == child ? P.bonds[b][0] : -1);
+                    if (partner >= 0) found = root * P.nodes_per_root + partner;
                 } else if (s < n_scan_slots) {
-                    const int cell = s - n_pair_slots;
+                    const int cell = s - far_base;
                     if (!cell_is_nearby(P, cell, cid0, cid1, cid2)) found = occ[cell];
                 }
                 const unsigned occupied = __ballot_sync(kFull, found >= 0);
@@ -383,7 +414,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 // If the last lane of the first pass is idle it draws the confirmation number of the out-state ahead
                 // of time (slot CONFIRM): a third of all events need it, and here it costs nothing.
                 const bool draws_confirmation = first && base == 0 && lane == 31 && !is_pair;
-                const uint32_t slot = is_pair ? ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target)
+                const bool is_bond = COMPOSITE && is_pair && s >= n_pair_slots && s < far_base;
+                const uint32_t slot = is_pair ? ECMC_SLOT(is_bond ? ECMC_SLOT_FACTOR_TIME : ECMC_SLOT_PAIR_TIME, target)
                                               : (is_boundary ? ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0)
                                                              : (draws_confirmation ? ECMC_SLOT(ECMC_SLOT_CONFIRM, 0)
                                                                                    : ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0)));
@@ -416,11 +448,17 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 double dt = INFINITY;
                 int kind = ECMC_EVENT_NONE, cell = -1, seq = kSeqNone;
                 double rate = 0.0;
-                const bool is_far = is_pair && s >= n_pair_slots;  // cell-bounding candidate
-                if (is_far) {
+                const bool is_far = is_pair && s >= far_base;  // cell-bounding candidate
+                if (is_bond) {
+                    // TwoLeafUnitEventHandler.send_event_time with the factor's own potential
+                    dt = displacement_time<-1>(P.bond_potential, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
+                                               needs_potential_change(P.bond_potential.kind) ? exponential : 0.0);
+                    kind = ECMC_EVENT_BOND;
+                    seq = s;
+                } else if (is_far) {
                     // TwoLeafUnitCellBoundingPotentialEventHandler.send_event_time (:137-177): constant event rate =
                     // bound of the relative cell x charge correction factor (cell_bounding_potential.py:155-238)
-                    const int relative = relative_cell_of(P, s - n_pair_slots, cid0, cid1, cid2);
+                    const int relative = relative_cell_of(P, s - far_base, cid0, cid1, cid2);
                     double charge_product = 1.0;
                     if (P.veto_use_charge) charge_product = a.charge * tp.charge / P.veto_target_charge;
                     const double *bound = P.bounds + (relative * P.dimension + dir) * 2;
@@ -535,9 +573,11 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 stp->pending_kind = bkind;
                 stp->pending_q = bt.q; stp->pending_r = bt.r;
                 stp->pending_rate = brate;
-                stp->pending_target = (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING) ? btarget : bcell;
+                stp->pending_target = (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING ||
+                                       bkind == ECMC_EVENT_BOND) ? btarget : bcell;
                 if (!was_pending) {
                     stp->pending_position = a.p0;
+                    if (COMPOSITE) stp->pending_root_position = root_p0;
                     stp->pending_stamp_q = now.q; stp->pending_stamp_r = now.r;
                 }
             }
@@ -549,6 +589,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             if (kind != ECMC_EVENT_END_OF_CHAIN) {
                 // the kept handler's in-state predates the control event's time slice
                 a.p0 = kept_position;
+                if (COMPOSITE) root_p0 = kept_root_position;
                 now = kept_stamp;
             }
             was_pending = false;
@@ -559,6 +600,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         {
             const double dt = time_sub(event_time, now);
             a.p0 = correct_position_entry(__dadd_rn(x_before, __dmul_rn(speed, dt)), L);
+            // the root unit moves with velocity * weight and carries the same time stamp (abstracts.py:82-101,165-190)
+            if (COMPOSITE) root_p0 = correct_position_entry(__dadd_rn(root_p0, __dmul_rn(P.root_speed, dt)), L);
             now = event_time;
         }
         // Did the time slice itself carry the particle out of its cell (without a boundary event)? Cell `id` holds
@@ -631,6 +674,14 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             n.pair++;
             break;
         }
+        case ECMC_EVENT_BOND: {
+            // TwoLeafUnitEventHandler.send_out_state (two_leaf_unit_event_handler.py:140-154)
+            rec_target = btarget;
+            accepted = 1;
+            new_active = btarget;
+            n_bond_events++;
+            break;
+        }
         case ECMC_EVENT_CELL_BOUNDARY: {
             // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
             a.p0 = boundary;
@@ -664,7 +715,14 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         const bool needs_lab = new_active != active || kind == ECMC_EVENT_CELL_BOUNDARY ||
                                kind == ECMC_EVENT_END_OF_CHAIN || left_cell;
         if (needs_lab) lab = rotate_out(a, dir);
+        if (COMPOSITE && (new_active != active || kind == ECMC_EVENT_END_OF_CHAIN)) {
+            // the root of the old active leaf stops here (or turns with the chain); the new one is picked up below
+            if (lane == 0) set_component(roots[active / P.nodes_per_root], dir, root_p0);
+            __syncwarp();
+        }
         if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir + 1 == P.dimension ? 0 : dir + 1;
+        if (COMPOSITE && (new_active != active || kind == ECMC_EVENT_END_OF_CHAIN))
+            root_p0 = component(roots[new_active / P.nodes_per_root], dir);
 
         // ---- SingleActiveCellOccupancy.update (single_active_cell_occupancy.py:149-203)
         if (new_active != active) {
@@ -699,7 +757,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             // (single_independent_active_periodic_direction_end_of_chain_event_handler.py:203-237)
             eoc = time_add(now, time_sub(now, now) + P.chain_time);
             const StreamKey next_key = {P.seed, stream, ev};
-            eoc_next = (int)stream_randbelow(next_key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.n_particles);
+            eoc_next = draw_end_of_chain_active(P, next_key);
         }
     }
 
@@ -707,10 +765,12 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         // the sampling / end-of-run handler time-slices the active unit (fixed_interval_sampling_event_handler.py:96-109)
         const double dt = time_sub(until, now);
         a.p0 = correct_position_entry(__dadd_rn(a.p0, __dmul_rn(speed, dt)), L);
+        if (COMPOSITE) root_p0 = correct_position_entry(__dadd_rn(root_p0, __dmul_rn(P.root_speed, dt)), L);
         now = until;
     }
     if (lane == 0) {
         part[active] = rotate_out(a, dir);
+        if (COMPOSITE) set_component(roots[active / P.nodes_per_root], dir, root_p0);
         stp->active = active; stp->direction = dir;
         stp->time_q = now.q; stp->time_r = now.r;
         stp->eoc_q = eoc.q; stp->eoc_r = eoc.r;
@@ -722,8 +782,9 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             if (n.events) atomicAdd(st + 0, (unsigned long long)n.events);
             if (n.pair) atomicAdd(st + 1, (unsigned long long)n.pair);
             if (n.veto) atomicAdd(st + 2, (unsigned long long)n.veto);
-            const unsigned boundary = n.events - n.pair - n.veto - n.end_of_chain;
+            const unsigned boundary = n.events - n.pair - n.veto - n.end_of_chain - n_bond_events;
             if (boundary) atomicAdd(st + 4, (unsigned long long)boundary);
+            if (n_bond_events) atomicAdd(st + 9, (unsigned long long)n_bond_events);
             if (n.end_of_chain) atomicAdd(st + 5, (unsigned long long)n.end_of_chain);
             if (n.candidates) atomicAdd(st + 6, n.candidates);
         }
@@ -805,9 +866,10 @@ start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         const Time eoc = time_add(now, time_sub(now, now) + P.chain_time);
         st.eoc_q = eoc.q; st.eoc_r = eoc.r;
         const StreamKey key = {P.seed, st.stream, 0ull};
-        st.eoc_next_active = (int)stream_randbelow(key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.n_particles);
+        st.eoc_next_active = draw_end_of_chain_active(P, key);
         st.pending_kind = ECMC_EVENT_NONE; st.pending_target = 0; st.reserved = 0;
         st.pending_q = 0.0; st.pending_r = 0.0; st.pending_rate = 0.0; st.pending_position = 0.0;
+        st.pending_root_position = 0.0;
         st.pending_stamp_q = 0.0; st.pending_stamp_r = 0.0;
         S.chains[chain] = st;
         S.n_surplus[chain] = n_surplus;

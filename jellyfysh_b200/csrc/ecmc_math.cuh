@@ -88,6 +88,15 @@ ECMC_HD uint32_t stream_randbelow(const StreamKey &k, uint32_t slot, uint32_t n)
         index += 4;
     }
 }
+// the same, continuing in the word stream of the slot at `index` (successive randint calls of one handler)
+ECMC_HD uint32_t stream_randbelow_from(const StreamKey &k, uint32_t slot, uint32_t n, uint32_t &index) {
+    int bits = 0;
+    while ((n >> bits) != 0) bits++;
+    for (;;) {
+        const uint32_t r = stream_word(k, slot, index++) >> (32 - bits);
+        if (r < n) return r;
+    }
+}
 // random.expovariate(beta) = -log(1 - u) / beta
 ECMC_D double expovariate(double u, double beta) { return -log(1.0 - u) / beta; }
 

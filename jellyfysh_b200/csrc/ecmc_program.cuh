@@ -73,10 +73,16 @@ struct DeviceProgram {
     const double *bounds;         // [n_cells][dimension][2] (upper, -lower) per relative cell: ECMC_FAR_CELL_BOUNDING only
     int neighbor_layers, pad3;
     double inv_beta, inv_speed;
+    // composite point objects: leaves grouped into roots (EcmcProgram.nodes_per_root), intramolecular pair factors
+    int nodes_per_root, n_bonds;
+    int bonds[ECMC_MAX_BONDS][2];
+    double root_speed;            // speed * weight, weight = 1 / nodes_per_root
+    PotentialParams bond_potential;
 };
 
 struct DeviceState {
     Particle *particles;
+    Particle *roots;   // [n_chains][n_particles / nodes_per_root] root-unit positions (composite objects only)
     int *occupants;
     int *surplus;
     int *n_surplus;

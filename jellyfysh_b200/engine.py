@@ -47,6 +47,8 @@ def library() -> C.CDLL:
     lib.ecmc_last_error.restype = C.c_char_p
     lib.ecmc_upload_positions.argtypes = [vp, vp, vp]
     lib.ecmc_download_positions.argtypes = [vp, vp]
+    lib.ecmc_upload_roots.argtypes = [vp, vp]
+    lib.ecmc_download_roots.argtypes = [vp, vp]
     lib.ecmc_start.argtypes = [vp, vp, u32]
     lib.ecmc_upload_chain_states.argtypes = [vp, vp]
     lib.ecmc_download_chain_states.argtypes = [vp, vp]
@@ -96,6 +98,7 @@ class Engine:
         self.n_cells = int(np.prod([program.cells_per_side[d] for d in range(self.dimension)]))
         self.max_occupants = int(program.max_occupants)
         self.max_surplus = max(int(program.max_surplus), 1)
+        self.nodes_per_root = max(int(program.nodes_per_root), 1)
         self.n_chains = int(n_chains)
         self.device = int(device)
         handle = C.c_void_p()
@@ -132,6 +135,16 @@ class Engine:
     def download_positions(self):
         out = np.empty((self.n_chains, self.n_particles, self.dimension), dtype=np.float64)
         self._check(self._lib.ecmc_download_positions(self._h, _ptr(out)))
+        return out
+
+    def upload_roots(self, roots):
+        """Root-unit positions of composite objects, [n_chains][n_particles / nodes_per_root][dimension]."""
+        arr = _f64(roots, (self.n_chains, self.n_particles // self.nodes_per_root, self.dimension))
+        self._check(self._lib.ecmc_upload_roots(self._h, _ptr(arr)))
+
+    def download_roots(self):
+        out = np.empty((self.n_chains, self.n_particles // self.nodes_per_root, self.dimension), dtype=np.float64)
+        self._check(self._lib.ecmc_download_roots(self._h, _ptr(out)))
         return out
 
     def start(self, streams=None, first_stream=0):

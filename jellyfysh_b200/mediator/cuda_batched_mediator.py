@@ -45,7 +45,7 @@ class CudaBatchedMediator(Mediator):
 
     def __init__(self, input_output_handler: InputOutputHandler, state_handler: StateHandler, scheduler: Scheduler,
                  activator: Activator, number_of_chains: int = 1, device: int = 0, seed: int = 0,
-                 first_random_stream: int = 0, maximum_surplus: int = 0) -> None:
+                 first_random_stream: int = 0, maximum_surplus: int = 0, occupant_capacity: int = 8) -> None:
         """
         Parameters follow SingleProcessMediator (single_process_mediator.py:57-72); in addition:
 
@@ -53,6 +53,7 @@ class CudaBatchedMediator(Mediator):
         device : CUDA device index.
         seed, first_random_stream : chain c reads the counter-based random stream (seed, first_random_stream + c).
         maximum_surplus : capacity of the per-chain surplus list (0: one slot per particle).
+        occupant_capacity : occupants per cell kept on the device when the reference's cell occupancy is unbounded.
         """
         self._logger = logging.getLogger(__name__)
         if number_of_chains < 1:
@@ -61,50 +62,71 @@ class CudaBatchedMediator(Mediator):
         super().__init__(input_output_handler, state_handler, scheduler, activator)
         template = state_handler.extract_global_state()
         self._compiled = compiler.compile_program(activator, template, seed=seed,
-                                                  max_surplus=maximum_surplus if maximum_surplus > 0 else None)
+                                                  max_surplus=maximum_surplus if maximum_surplus > 0 else None,
+                                                  occupant_capacity=occupant_capacity)
         self._number_of_chains = number_of_chains
-        positions, charges = compiler.positions_and_charges(template, self._compiled.charge_name)
+        positions, charges, roots = compiler.positions_and_charges(template, self._compiled.charge_name)
         all_positions = np.empty((number_of_chains,) + positions.shape)
         all_charges = None if charges is None else np.empty((number_of_chains,) + charges.shape)
-        all_positions[0] = positions
-        if charges is not None:
-            all_charges[0] = charges
-        for chain in range(1, number_of_chains):
-            nodes = input_output_handler.read()
-            all_positions[chain] = [node.value.position for node in nodes]
+        all_roots = None if roots is None else np.empty((number_of_chains,) + roots.shape)
+        for chain in range(number_of_chains):
+            if chain > 0:
+                positions, charges, roots = compiler.positions_and_charges(input_output_handler.read(),
+                                                                           self._compiled.charge_name)
+            all_positions[chain] = positions
             if charges is not None:
-                all_charges[chain] = [node.value.charge[self._compiled.charge_name] for node in nodes]
+                all_charges[chain] = charges
+            if roots is not None:
+                all_roots[chain] = roots
         self._engine = engine.Engine(self._compiled.builder, n_chains=number_of_chains, device=device)
         self._engine.upload_positions(all_positions, all_charges)
+        if all_roots is not None:
+            self._engine.upload_roots(all_roots)
         self._engine.start(first_stream=first_random_stream)
         self._statistics = {}
         self._control_times = {}
 
     # ---- state hand-over to the reference's state handler ------------------------------------------------------
-    def _load_chain_into_state_handler(self, chain, positions, states):
+    def _load_chain_into_state_handler(self, chain, positions, states, roots=None):
         """Write one chain's device state through the public state-handler contract
-        (state_handler.py:63-165): positions of all units, velocity / time stamp of the active one."""
+        (state_handler.py:63-165): positions of all units, velocity / time stamp of the active leaf unit and, for
+        composite point objects, of its root unit (velocity * weight, event_handler/abstracts/abstracts.py:165-190)."""
         speed = self._compiled.builder.program.speed
         dimension = self._compiled.builder.program.dimension
+        npr = self._compiled.nodes_per_root
         cnodes = self._state_handler.extract_global_state()
         state = states[chain]
-        for index, cnode in enumerate(cnodes):
-            unit = cnode.value
-            unit.position = [float(x) for x in positions[chain, index]]
-            if index == int(state["active"]):
-                unit.velocity = [speed if d == int(state["direction"]) else 0.0 for d in range(dimension)]
-                unit.time_stamp = Time(float(state["time_q"]), float(state["time_r"]))
-            else:
+        active, direction = int(state["active"]), int(state["direction"])
+
+        def fill(unit, position, unit_speed):
+            unit.position = [float(x) for x in position]
+            if unit_speed is None:
                 unit.velocity, unit.time_stamp = None, None
+            else:
+                unit.velocity = [unit_speed if d == direction else 0.0 for d in range(dimension)]
+                unit.time_stamp = Time(float(state["time_q"]), float(state["time_r"]))
+
+        for index, cnode in enumerate(cnodes):
+            if roots is None:
+                fill(cnode.value, positions[chain, index], speed if index == active else None)
+                continue
+            is_active_root = index == active // npr
+            fill(cnode.value, roots[chain, index], speed * cnode.children[0].weight if is_active_root else None)
+            for k, child in enumerate(cnode.children):
+                fill(child.value, positions[chain, index * npr + k], speed if index * npr + k == active else None)
         self._state_handler.insert_into_global_state(cnodes)
+
+    def _download(self):
+        positions = self._engine.download_positions()
+        roots = self._engine.download_roots() if self._compiled.nodes_per_root > 1 else None
+        return positions, roots, self._engine.chain_states()
 
     def _write_output(self, handler):
         if handler.output_handler is None:
             return
-        positions = self._engine.download_positions()
-        states = self._engine.chain_states()
+        positions, roots, states = self._download()
         for chain in range(self._number_of_chains):
-            self._load_chain_into_state_handler(chain, positions, states)
+            self._load_chain_into_state_handler(chain, positions, states, roots)
             self._input_output_handler.write(handler.output_handler, self._state_handler.extract_global_state())
 
     # ---- the loop ------------------------------------------------------------------------------------------------
@@ -124,8 +146,8 @@ class CudaBatchedMediator(Mediator):
             names = {cls.__name__ for cls in type(handler).__mro__}
             if "EndOfRunEventHandler" in names:
                 self._write_output(handler)
-                positions = self._engine.download_positions()
-                self._load_chain_into_state_handler(0, positions, self._engine.chain_states())
+                positions, roots, states = self._download()
+                self._load_chain_into_state_handler(0, positions, states, roots)
                 raise EndOfRun
             self._write_output(handler)
             self._control_times[handler] = handler.send_event_time()

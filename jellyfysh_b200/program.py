@@ -48,6 +48,22 @@ class ProgramBuilder:
         p.pair_use_charge = int(use_charge)
         return self
 
+    def set_composite(self, nodes_per_root, bonds=(), bond_potential=None):
+        """Composite point objects: n_particles leaves in groups of nodes_per_root; `bonds` = pairs of child indices
+        handled by a TwoLeafUnitEventHandler with bond_potential (factor type map, e.g. "[0, 1], Dipole")."""
+        p = self.program
+        if p.n_particles % nodes_per_root:
+            raise ValueError("n_particles must be a multiple of nodes_per_root")
+        if len(bonds) > abi.ECMC_MAX_BONDS:
+            raise ValueError("too many bonds")
+        p.nodes_per_root = nodes_per_root
+        p.n_bonds = len(bonds)
+        for i, (a, b) in enumerate(bonds):
+            p.bonds[i][0], p.bonds[i][1] = a, b
+        if bond_potential is not None:
+            p.bond_potential = bond_potential
+        return self
+
     def set_cell_bounding(self, potential, bounds, use_charge=False, target_charge=1.0):
         """Far field through TwoLeafUnitCellBoundingPotentialEventHandler: bounds[n_cells][dimension][2] holds
         (upper bound, -lower bound) of the derivative per relative cell (CellBoundingPotential._derivative_bounds)."""

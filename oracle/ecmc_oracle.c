@@ -781,6 +781,17 @@ static uint32_t rng_randbelow(uint32_t seed, uint32_t stream, uint64_t event, ui
     }
 }
 
+/* the same, continuing in the word stream at *index (successive randint calls of one handler) */
+static uint32_t rng_randbelow_from(uint32_t seed, uint32_t stream, uint64_t event, uint32_t slot, uint32_t n,
+                                   uint32_t *index) {
+    int k = 0;
+    while ((n >> k) != 0) k++;
+    for (;;) {
+        uint32_t r = rng_word(seed, stream, event, slot, (*index)++) >> (32 - k);
+        if (r < n) return r;
+    }
+}
+
 /* ================================================================================================== */
 /* activator/internal_state/cell_occupancy/cells: CuboidPeriodicCells                                 */
 /* ================================================================================================== */
@@ -941,7 +952,9 @@ typedef struct OrcChain {
     int D, N;
     double L;
     ocells cells;
-    opotential pair_pot, pair_bound, veto_pot;
+    opotential pair_pot, pair_bound, veto_pot, bond_pot;
+    int npr;          /* nodes per root (1: point masses) */
+    double *root_pos; /* [N / npr][D] root-unit positions of composite objects */
     /* copied veto tables */
     EcmcWalkerTable upper[ECMC_MAX_DIM], lower[ECMC_MAX_DIM];
     double *bounds;
@@ -979,9 +992,9 @@ ORC_API void orc_chain_destroy(OrcChain *c) {
         free((void *)c->lower[d].cell_a); free((void *)c->lower[d].cell_b); free((void *)c->lower[d].rate_a);
     }
     free(c->bounds); free(c->nearby_offsets); free(c->is_nearby_of_zero);
-    free(c->pos); free(c->charge); free(c->occ); free(c->surplus);
+    free(c->pos); free(c->charge); free(c->occ); free(c->surplus); free(c->root_pos);
     cells_free(&c->cells);
-    pot_free(&c->pair_pot); pot_free(&c->pair_bound); pot_free(&c->veto_pot);
+    pot_free(&c->pair_pot); pot_free(&c->pair_bound); pot_free(&c->veto_pot); pot_free(&c->bond_pot);
     free(c);
 }
 
@@ -995,6 +1008,12 @@ ORC_API OrcChain *orc_chain_create(const EcmcProgram *prog) {
     if (pot_make(&c->pair_pot, &prog->pair_potential, c->L)) goto fail;
     if (pot_make(&c->pair_bound, &prog->pair_bounding_potential, c->L)) goto fail;
     if (pot_make(&c->veto_pot, &prog->veto_potential, c->L)) goto fail;
+    if (pot_make(&c->bond_pot, &prog->bond_potential, c->L)) goto fail;
+    c->npr = prog->nodes_per_root > 1 ? prog->nodes_per_root : 1;
+    if (c->N % c->npr || prog->n_bonds < 0 || prog->n_bonds > ECMC_MAX_BONDS) goto fail;
+    if (prog->n_bonds > 0 && c->npr == 1) goto fail;
+    c->root_pos = (double *)calloc((size_t)(c->N / c->npr) * c->D, sizeof(double));
+    if (!c->root_pos) goto fail;
     c->is_nearby_of_zero = (unsigned char *)calloc(c->cells.n_cells, 1);
     c->nearby_offsets = (int *)malloc(sizeof(int) * c->cells.n_cells);
     if (!c->is_nearby_of_zero || !c->nearby_offsets) goto fail;
@@ -1032,6 +1051,12 @@ ORC_API void orc_chain_set_positions(OrcChain *c, const double *pos, const doubl
 }
 ORC_API void orc_chain_get_positions(const OrcChain *c, double *pos) {
     memcpy(pos, c->pos, sizeof(double) * c->N * c->D);
+}
+ORC_API void orc_chain_set_roots(OrcChain *c, const double *roots) {
+    memcpy(c->root_pos, roots, sizeof(double) * (c->N / c->npr) * c->D);
+}
+ORC_API void orc_chain_get_roots(const OrcChain *c, double *roots) {
+    memcpy(roots, c->root_pos, sizeof(double) * (c->N / c->npr) * c->D);
 }
 ORC_API void orc_chain_get_state(const OrcChain *c, EcmcChainState *st) { *st = c->st; }
 ORC_API void orc_chain_set_state(OrcChain *c, const EcmcChainState *st) { c->st = *st; c->started = 1; }
@@ -1091,8 +1116,20 @@ static void schedule_end_of_chain(OrcChain *c) {
     double new_chain_time = time_sub(now, now) + c->prog.chain_time;
     otime t = time_add(now, new_chain_time);
     c->st.eoc_q = t.q; c->st.eoc_r = t.r;
-    c->st.eoc_next_active = (int)rng_randbelow(c->prog.seed, c->st.stream, c->st.event_counter,
-                                               ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)c->N);
+    if (c->npr == 1) {
+        c->st.eoc_next_active = (int)rng_randbelow(c->prog.seed, c->st.stream, c->st.event_counter,
+                                                   ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)c->N);
+    } else {
+        /* a leaf unit was active: (randint(0, number_of_root_nodes - 1), randint(0, number_of_nodes_per_root_node - 1)),
+         * single_independent_active_periodic_direction_end_of_chain_event_handler.py:231-237; the second randint
+         * continues in the word stream where the first one stopped */
+        uint32_t index = 0;
+        uint32_t root = rng_randbelow_from(c->prog.seed, c->st.stream, c->st.event_counter,
+                                           ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)(c->N / c->npr), &index);
+        uint32_t child = rng_randbelow_from(c->prog.seed, c->st.stream, c->st.event_counter,
+                                            ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)c->npr, &index);
+        c->st.eoc_next_active = (int)(root * (uint32_t)c->npr + child);
+    }
 }
 
 /* Start of run: SingleActiveCellOccupancy.initialize (:95-121), InitialChainStartOfRunEventHandler
@@ -1198,6 +1235,27 @@ static candidate cell_bounding_candidate(OrcChain *c, int target) {
     return cand;
 }
 
+/* A factor-type-map pair factor inside the active leaf's composite object (FactorTypeMapInStateTagger,
+ * factor_type_map_in_state_tagger.py:83-107) handled by a TwoLeafUnitEventHandler (two_leaf_unit_event_handler.py:
+ * 105-138) with the bond potential. */
+static candidate bond_candidate(OrcChain *c, int target) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_BOND; cand.target = target; cand.target_cell = -1; cand.rate = 0.0;
+    const double *pa = c->pos + c->st.active * c->D, *pt = c->pos + target * c->D;
+    double sep[ECMC_MAX_DIM] = {0, 0, 0};
+    separation_vector(pa, pt, c->D, c->L, sep);
+    double dU = 0.0;
+    if (pot_needs_potential_change(c->bond_pot.kind)) {
+        double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter,
+                              ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
+        dU = rng_expovariate(u, c->prog.beta);
+    }
+    double dt = pot_displacement(&c->bond_pot, c->st.direction, c->prog.speed, sep, c->D, 1.0, 1.0, dU);
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, dt);
+    return cand;
+}
+
 /* CellBoundaryEventHandler.send_event_time, cell_boundary_event_handler.py:122-156 (positive velocity) */
 static candidate boundary_candidate(OrcChain *c, double *boundary_out) {
     candidate cand;
@@ -1225,6 +1283,17 @@ static void time_slice_active(OrcChain *c, otime event_time) {
     for (int d = 0; d < c->D; d++) {
         double v = d == c->st.direction ? c->prog.speed : 0.0;
         pa[d] = correct_position_entry(pa[d] + v * dt, c->L);
+    }
+    if (c->npr > 1) {
+        /* the root unit of the active leaf moves with velocity * weight, weight = 1 / number of children
+         * (_register_velocity_change_leaf_cnode, abstracts.py:165-190); it carries the same time stamp as the leaf and
+         * is time-sliced with it (_time_slice_all_units_in_state, :97-101) */
+        double *pr = c->root_pos + (c->st.active / c->npr) * c->D;
+        double weight = 1.0 / c->npr;
+        for (int d = 0; d < c->D; d++) {
+            double v = (d == c->st.direction ? c->prog.speed : 0.0) * weight;
+            pr[d] = correct_position_entry(pr[d] + v * dt, c->L);
+        }
     }
     c->st.time_q = event_time.q; c->st.time_r = event_time.r;
 }
@@ -1258,7 +1327,8 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         best.kind = c->st.pending_kind;
         best.t.q = c->st.pending_q; best.t.r = c->st.pending_r;
         best.rate = c->st.pending_rate;
-        if (best.kind == ECMC_EVENT_PAIR || best.kind == ECMC_EVENT_CELL_BOUNDING) best.target = c->st.pending_target;
+        if (best.kind == ECMC_EVENT_PAIR || best.kind == ECMC_EVENT_CELL_BOUNDING || best.kind == ECMC_EVENT_BOND)
+            best.target = c->st.pending_target;
         else best.target_cell = c->st.pending_target;
         if (best.kind == ECMC_EVENT_CELL_BOUNDARY)
             boundary_position = c->cells.cell_min[best.target_cell * c->D + c->st.direction];
@@ -1292,6 +1362,16 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
                     if (lt_candidate(&cand, &best)) best = cand;
                 }
             }
+        }
+        /* factor-type-map factors that contain the active leaf */
+        for (int b = 0; b < c->prog.n_bonds; b++) {
+            int child = c->st.active % c->npr, root = c->st.active / c->npr;
+            int partner = -1;
+            if (c->prog.bonds[b][0] == child) partner = c->prog.bonds[b][1];
+            else if (c->prog.bonds[b][1] == child) partner = c->prog.bonds[b][0];
+            if (partner < 0) continue;
+            candidate cand = bond_candidate(c, root * c->npr + partner);
+            if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
         }
         if (c->prog.veto_enabled == ECMC_FAR_CELL_BOUNDING) {
             /* CellBoundingPotentialTagger, cell_bounding_potential_tagger.py:150-155: every non-empty cell that is
@@ -1329,12 +1409,14 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
             c->st.pending_kind = interaction.kind;
             c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
             c->st.pending_rate = interaction.rate;
-            c->st.pending_target = (interaction.kind == ECMC_EVENT_PAIR || interaction.kind == ECMC_EVENT_CELL_BOUNDING)
-                                       ? interaction.target : interaction.target_cell;
+            c->st.pending_target = (interaction.kind == ECMC_EVENT_PAIR || interaction.kind == ECMC_EVENT_CELL_BOUNDING ||
+                                    interaction.kind == ECMC_EVENT_BOND) ? interaction.target : interaction.target_cell;
             if (!was_pending) {
                 /* the kept handlers hold copies of the in-state made before the control event time-slices
                  * the global state (single_process_mediator.py:105-109): their out-state starts from here */
                 c->st.pending_position = c->pos[c->st.active * c->D + c->st.direction];
+                if (c->npr > 1)
+                    c->st.pending_root_position = c->root_pos[(c->st.active / c->npr) * c->D + c->st.direction];
                 c->st.pending_stamp_q = c->st.time_q;
                 c->st.pending_stamp_r = c->st.time_r;
             }
@@ -1346,6 +1428,7 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         /* the kept handler's stored in-state predates the control event's time slice; the end-of-chain
          * handler instead receives the current global state (mediator/mediator.py:233-249) */
         c->pos[c->st.active * c->D + c->st.direction] = c->st.pending_position;
+        if (c->npr > 1) c->root_pos[(c->st.active / c->npr) * c->D + c->st.direction] = c->st.pending_root_position;
         c->st.time_q = c->st.pending_stamp_q;
         c->st.time_r = c->st.pending_stamp_r;
     }
@@ -1422,6 +1505,13 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         c->stats.pair_events++;
         break;
     }
+    case ECMC_EVENT_BOND:
+        /* TwoLeafUnitEventHandler.send_out_state, two_leaf_unit_event_handler.py:140-154 */
+        rec_target = best.target;
+        accepted = 1;
+        new_active = best.target;
+        c->stats.bond_events++;
+        break;
     case ECMC_EVENT_CELL_BOUNDARY:
         /* CellBoundaryEventHandler.send_out_state, cell_boundary_event_handler.py:158-173 */
         c->pos[old_active * c->D + c->st.direction] = boundary_position;

@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
     L.orc_chain_destroy.argtypes = [p]
     L.orc_chain_set_positions.argtypes = [p, p, p]
     L.orc_chain_get_positions.argtypes = [p, p]
+    L.orc_chain_set_roots.argtypes = [p, p]
+    L.orc_chain_get_roots.argtypes = [p, p]
     L.orc_chain_get_state.argtypes = [p, C.POINTER(abi.EcmcChainState)]
     L.orc_chain_set_state.argtypes = [p, C.POINTER(abi.EcmcChainState)]
     L.orc_chain_get_cells.argtypes = [p, p, p, C.POINTER(C.c_int32)]
@@ -310,6 +312,17 @@ class OracleChain:
     def positions(self):
         out = np.empty((self.n, self.dimension))
         self._lib.orc_chain_get_positions(self._h, out.ctypes.data)
+        return out
+
+    def set_roots(self, roots):
+        npr = max(int(self._builder.program.nodes_per_root), 1)
+        arr = np.ascontiguousarray(roots, dtype=np.float64).reshape(self.n // npr, self.dimension)
+        self._lib.orc_chain_set_roots(self._h, arr.ctypes.data)
+
+    def roots(self):
+        npr = max(int(self._builder.program.nodes_per_root), 1)
+        out = np.empty((self.n // npr, self.dimension))
+        self._lib.orc_chain_get_roots(self._h, out.ctypes.data)
         return out
 
     def start(self, stream=0):

@@ -328,3 +328,103 @@ def lattice_start(n, system_length, cells_per_side, jitter=0.05, seed=1000):
 def uniform_start(n, system_length, dimension=3, seed=1000):
     rng = np.random.Generator(np.random.PCG64(seed))
     return rng.uniform(0.0, system_length, size=(n, dimension))
+
+
+# ------------------------------------------------------------------------------------------------------
+# C1 of SURVEY.md 8(d): the shipped hard-disk dipole configuration, unchanged except for where the start
+# configuration comes from and where the output goes
+# ------------------------------------------------------------------------------------------------------
+def shipped_ini(ref_root, *relative):
+    import os
+    with open(os.path.join(ref_root, "jellyfysh", "config_files", *relative)) as file:
+        return file.read()
+
+
+def hard_disk_dipoles_cells_ini(ref_root, n_dipoles=81, end_of_run_time=1.0e9, sampling=False, output="/dev/null"):
+    import os
+    """config_files/hard_disk_dipoles/hard_disk_dipoles_cells.ini with the PDB input handler (MDAnalysis is not
+    installed here) replaced by the random input handler, whose node creator the recorder feeds with the PDB's
+    coordinates (ReferenceRun(composites=...)); everything that touches the hot path is the shipped text."""
+    text = shipped_ini(ref_root, "hard_disk_dipoles", "hard_disk_dipoles_cells.ini")
+    head, tail = text.split("[PdbInputHandler]")
+    tail = tail.split("[ElectricChargeValues]", 1)[1]
+    text = (head.replace("input_handler = pdb_input_handler", "input_handler = random_input_handler") +
+            "[RandomInputHandler]\nrandom_node_creator = dipole_random_node_creator\n"
+            f"number_of_root_nodes = {n_dipoles}\n\n"
+            "[DipoleRandomNodeCreator]\ncharge_values = electric_charge_values (charge_values)\n"
+            "min_initial_dipole_separation = 0.96\nmax_initial_dipole_separation = 1.04\n\n"
+            "[ElectricChargeValues]" + tail)
+    text = text.replace("filename = config_files/", "filename = " + os.path.join(ref_root, "jellyfysh", "config_files") + "/")
+    text = text.replace("end_of_run_time = 15015000", f"end_of_run_time = {end_of_run_time!r}")
+    text = text.replace("output/hard_disk_dipoles/Polarization_81Dipoles_Cells.dat", output)
+    if not sampling:
+        text = text.replace("    polarization_sampling (no_in_state_tagger),\n", "")
+        text = text.replace(", polarization_sampling", "")
+        start, rest = text.split("[PolarizationSampling]")
+        rest = rest.split("[EndOfChain]", 1)[1]
+        text = start + "[EndOfChain]" + rest
+        text = text.replace("output_handlers = polarization_output_handler\n", "")
+        start, rest = text.split("[PolarizationOutputHandler]")
+        text = start
+    return text
+
+
+def read_pdb_dipoles(ref_root, system_length=12.836):
+    """(roots[81][2], leaves[81][2][2]) of the shipped PDB start configuration as PdbInputHandler.read builds them
+    (pdb_input_handler.py:146-190): MDAnalysis keeps coordinates as float32; the root is the barycentre over the
+    shortest separations."""
+    import os
+    import numpy as np
+    path = os.path.join(ref_root, "jellyfysh", "config_files", "hard_disk_dipoles",
+                        "81dipoles_min0.952380952380952_max1.047619047619048.pdb")
+    atoms = []
+    for line in open(path):
+        if line.startswith("ATOM"):
+            atoms.append((int(line[22:26]), float(np.float32(line[30:38])), float(np.float32(line[38:46]))))
+    n = max(a[0] for a in atoms)
+    leaves = np.zeros((n, 2, 2))
+    count = [0] * n
+    for resid, x, y in atoms:
+        leaves[resid - 1, count[resid - 1]] = [x % system_length, y % system_length]
+        count[resid - 1] += 1
+    roots = np.zeros((n, 2))
+    half = system_length / 2.0
+    for r in range(n):
+        first, other = leaves[r, 0], leaves[r, 1]
+        for d in range(2):
+            shortest = (float(other[d]) - float(first[d]) + half) % system_length - half
+            closest = float(first[d]) + shortest
+            center = float(first[d]) * 0.5 + closest * 0.5
+            roots[r, d] = center % system_length
+    return roots, leaves
+
+
+def patch_composite_start(composites):
+    """Make the reference's random node creators return the given composite point objects instead of drawing them:
+    composites = (roots[n_roots][D], leaves[n_roots][nodes_per_root][D]); successive reads of the input handler cycle
+    through roots / leaves in blocks of number_of_root_nodes. Charges are assigned by the creator as usual. Returns a
+    function that restores the reference's methods. Needs `jellyfysh` importable."""
+    import itertools
+    from jellyfysh.base.node import Node
+    from jellyfysh.base.particle import Particle
+    from jellyfysh.input_output_handler.input_handler.random_node_creator import (dipole_random_node_creator,
+                                                                                  water_random_node_creator)
+    roots, leaves = composites
+    counter = itertools.cycle(range(len(roots)))
+
+    def fill_root_node(creator, node):
+        r = next(counter)
+        for k, position in enumerate(leaves[r]):
+            node.add_child(Node(Particle([float(x) for x in position],
+                                         {cv.charge_name: cv[k] for cv in creator._charge_values})))
+        node.value = Particle(position=[float(x) for x in roots[r]])
+
+    saved = []
+    for cls in (dipole_random_node_creator.DipoleRandomNodeCreator, water_random_node_creator.WaterRandomNodeCreator):
+        saved.append((cls, cls.fill_root_node))
+        cls.fill_root_node = fill_root_node
+
+    def restore():
+        for cls, original in saved:
+            cls.fill_root_node = original
+    return restore

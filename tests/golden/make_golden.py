@@ -283,23 +283,31 @@ def _pack_snapshots(run):
             "snap_time": np.array([[s["time_q"], s["time_r"]] for s in snaps])}
 
 
-def chain_trace(name, ini, positions, seed, stream, n_events, snapshot_every, meta, charges=None, max_occupants=1):
-    run = rr.ReferenceRun(REF, ini, seed=seed, stream=stream, positions=positions)
+def chain_trace(name, ini, positions, seed, stream, n_events, snapshot_every, meta, charges=None, max_occupants=1,
+                composites=None):
+    run = rr.ReferenceRun(REF, ini, seed=seed, stream=stream, positions=positions, composites=composites)
     try:
+        if composites is not None:
+            positions = np.asarray(composites[1], dtype=np.float64).reshape(-1, np.shape(composites[1])[-1])
         records = run.run(max_events=n_events, snapshot_every=snapshot_every, max_occupants=max_occupants)
         out = {"records": records, "positions0": np.asarray(positions, dtype=np.float64),
                "final_positions": run.positions(), "seed": np.array([seed, stream], dtype=np.int64)}
+        if composites is not None:
+            out["roots0"] = np.asarray(composites[0], dtype=np.float64)
+            out["final_roots"] = run.roots()
+            out["snap_roots"] = np.array([s["roots"] for s in run.snapshots])
         out.update({"meta_" + k: np.asarray(v) for k, v in meta.items()})
         if charges is not None:
             out["charges"] = np.asarray(charges, dtype=np.float64)
-        out.update(_tables_of(run))
+        if meta.get("far_field", 1):
+            out.update(_tables_of(run))
         out.update(_pack_snapshots(run))
         out["host_times"] = np.array(run.host_times, dtype=np.float64).reshape(-1, 3)
     finally:
         run.close()
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    kinds = np.bincount(records["kind"], minlength=6)
-    print(f"{name}.npz: {len(records)} events, kinds pair/veto/boundary/eoc/cell-bounding = {kinds[1:].tolist()}, "
+    kinds = np.bincount(records["kind"], minlength=7)
+    print(f"{name}.npz: {len(records)} events, kinds pair/veto/boundary/eoc/cell-bounding/bond = {kinds[1:].tolist()}, "
           f"accepted = {int(records['accepted'].sum())}, snapshots = {len(run.snapshots)}, "
           f"max surplus = {int(out['snap_n_surplus'].max())}")
 
@@ -355,8 +363,21 @@ def cell_bounding_traces():
                           ipcb=[1.5837], estimator=[1.5, 4], chain_time=0.78965, far_field=2))
 
 
+def dipole_traces():
+    # C1: the shipped hard_disk_dipoles_cells.ini from the shipped PDB start configuration (81 dipoles = 162 disks,
+    # 13^2 leaf-level cells, unbounded occupancy, hard-sphere pairs + hard-dipole tether, root units follow)
+    roots, leaves = configs.read_pdb_dipoles(REF)
+    chain_trace("trace_hard_disk_dipoles", configs.hard_disk_dipoles_cells_ini(REF), None, seed=17, stream=9,
+                n_events=6000, snapshot_every=500, max_occupants=6, composites=(roots, leaves),
+                meta=dict(n=162, cells_per_side=[13, 13], system_length=12.836, beta=1.0, chain_time=1.0, far_field=0,
+                          nodes_per_root=2, hard_sphere=[0.476190476190476],
+                          hard_dipole=[0.952380952380952, 1.047619047619048], max_occupants=6))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding"]
+    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles"]
+    if "dipoles" in which:
+        dipole_traces()
     if "cell_bounding" in which:
         cell_bounding_traces()
     if "potentials" in which:

@@ -8,7 +8,10 @@ import numpy as np
 
 ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 out = {}
-for key, path in {"coulomb_atoms": "jellyfysh/output/2018_JCP_149_064113/coulomb_atoms/ReferenceDataCoulombAtoms.dat"}.items():
+for key, path in {"coulomb_atoms": "jellyfysh/output/2018_JCP_149_064113/coulomb_atoms/ReferenceDataCoulombAtoms.dat",
+                  "dipoles_px": "jellyfysh/output/hard_disk_dipoles/ReferenceDataPx_81Dipoles_NewtonianECMC.dat",
+                  "dipoles_py": "jellyfysh/output/hard_disk_dipoles/ReferenceDataPy_81Dipoles_NewtonianECMC.dat",
+                  "water_oo": "jellyfysh/output/2018_JCP_149_064113/water/ReferenceOOSeparation.dat"}.items():
     data = np.loadtxt(os.path.join(ref, path))
     out[key + "_x"], out[key + "_cdf"] = data[:, 0], data[:, 1]
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cdfs.npz"), **out)

@@ -53,6 +53,7 @@ def stream_double(seed, stream, event, slot, index):
 
 
 SLOT_PAIR_TIME, SLOT_VETO_TIME, SLOT_VETO_CHOICE, SLOT_CONFIRM, SLOT_END_OF_CHAIN, SLOT_LIFTING = 1, 2, 3, 4, 5, 6
+SLOT_FACTOR_TIME = 7
 SLOT_INIT = 15  # initial random positions (host side only)
 
 
@@ -98,6 +99,7 @@ class SlotRandom(random.Random):
 
 
 EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDARY, EVENT_END_OF_CHAIN, EVENT_CELL_BOUNDING = 1, 2, 3, 4, 5
+EVENT_BOND = 6
 HOST_EVENT = 0
 
 RECORD_DTYPE = np.dtype([("kind", "<i4"), ("target", "<i4"), ("target_cell", "<i4"), ("accepted", "<i4"),
@@ -117,7 +119,11 @@ def import_reference(ref_root):
 class ReferenceRun:
     """Build the reference object graph from INI text and run it with full instrumentation."""
 
-    def __init__(self, ref_root, ini_text, seed=0, stream=0, positions=None):
+    def __init__(self, ref_root, ini_text, seed=0, stream=0, positions=None, composites=None):
+        """positions: start configuration of point masses, fed through setting.random_position. composites: start
+        configuration of composite point objects as (roots[n_roots][D], leaves[n_roots][nodes_per_root][D]), fed
+        through the fill_root_node method of the INI's random node creator (the only patched reference method: it
+        replaces the random draw of a molecule by the given one, charges as the creator assigns them)."""
         import_reference(ref_root)
         from jellyfysh.base import factory
         from jellyfysh.base.strings import to_camel_case
@@ -136,6 +142,9 @@ class ReferenceRun:
         if positions is not None:
             pos_iter = iter([list(map(float, p)) for p in positions])
             setting.random_position = lambda: next(pos_iter)
+        self._unpatch_creators = []
+        if composites is not None:
+            self._patch_node_creators(composites)
         # initial positions of RandomInputHandler come from setting.random_position() -> random.uniform
         self.rng.set_context(0, make_slot(SLOT_INIT))
         with contextlib.redirect_stdout(io.StringIO()):
@@ -147,6 +156,16 @@ class ReferenceRun:
         self.iterations = []  # (winner class name, event time float)
         self.host_times = []  # (committed device events so far, quotient, remainder) of sampling events
         self._instrument()
+
+    def _patch_node_creators(self, composites):
+        import configs
+        self._unpatch_creators.append(configs.patch_composite_start(composites))
+
+    def leaf_id(self, identifier):
+        """Flat leaf identifier root * nodes_per_root + child (the root identifier for point masses)."""
+        if len(identifier) == 1:
+            return identifier[0]
+        return identifier[0] * self.setting.number_of_nodes_per_root_node + identifier[1]
 
     # -- random -------------------------------------------------------------------------------------
     def _patch_random(self):
@@ -163,6 +182,8 @@ class ReferenceRun:
         for name, fn in self._saved.items():
             setattr(random, name, fn)
         self._eoc_module.randint = self._saved_eoc_randint
+        for restore in self._unpatch_creators:
+            restore()
         self.setting.reset()
 
     # -- instrumentation ------------------------------------------------------------------------------
@@ -177,14 +198,24 @@ class ReferenceRun:
         if "EndOfChainEventHandler" in names:
             return EVENT_END_OF_CHAIN
         if names & {"TwoLeafUnitEventHandler", "TwoLeafUnitBoundingPotentialEventHandler"}:
-            return EVENT_PAIR
+            return EVENT_BOND if id(handler) in self._factor_map_handlers() else EVENT_PAIR
         return HOST_EVENT
 
-    @staticmethod
-    def _target_of_pair(in_state):
+    def _factor_map_handlers(self):
+        """ids of the handlers that belong to a FactorTypeMapInStateTagger (intramolecular factors)."""
+        if getattr(self, "_factor_ids", None) is None:
+            self._factor_ids = set()
+            for tagger in self.mediator._activator._taggers:
+                if "FactorTypeMapInStateTagger" in {cls.__name__ for cls in type(tagger).__mro__}:
+                    self._factor_ids |= {id(h) for h in tagger.get_event_handlers()}
+        return self._factor_ids
+
+    def _target_of_pair(self, in_state):
+        from jellyfysh.base.node import yield_leaf_nodes
         for cnode in in_state:
-            if cnode.value.velocity is None:
-                return cnode.value.identifier[0]
+            for leaf in yield_leaf_nodes(cnode):
+                if leaf.value.velocity is None:
+                    return self.leaf_id(leaf.value.identifier)
         raise RuntimeError("pair in-state without target")
 
     def _instrument(self):
@@ -199,6 +230,8 @@ class ReferenceRun:
             def send_event_time(*args, _h=h, _kind=kind, _orig=orig_time):
                 if _kind in (EVENT_PAIR, EVENT_CELL_BOUNDING):
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_of_pair(args[0])))
+                elif _kind == EVENT_BOND:
+                    run.rng.set_context(run.events, make_slot(SLOT_FACTOR_TIME, run._target_of_pair(args[0])))
                 elif _kind == EVENT_CELL_VETO:
                     run.rng.set_context(run.events, make_slot(SLOT_VETO_TIME), make_slot(SLOT_VETO_CHOICE))
                 elif _kind == EVENT_END_OF_CHAIN:
@@ -257,12 +290,13 @@ class ReferenceRun:
 
     def _active(self):
         sh = self.mediator._state_handler
-        ids = list(sh._lifting_state._lifting_dictionary.keys())
-        assert len(ids) == 1
-        velocity, stamp = sh._lifting_state.get(ids[0])
-        pos = sh._physical_state.get(ids[0]).value.position
+        ids = sorted(sh._lifting_state._lifting_dictionary.keys(), key=len)
+        assert len(ids) == self.setting.number_of_node_levels  # the active leaf and its ancestors
+        leaf = ids[-1]
+        velocity, stamp = sh._lifting_state.get(leaf)
+        pos = sh._physical_state.get(leaf).value.position
         direction = [i for i, v in enumerate(velocity) if v != 0.0][0]
-        return ids[0][0], direction, list(pos), stamp
+        return self.leaf_id(leaf), direction, list(pos), stamp
 
     def _cell_index(self, cell):
         cells = self._cells()
@@ -293,8 +327,8 @@ class ReferenceRun:
         rec["time_q"] = winner._event_time.quotient
         rec["time_r"] = winner._event_time.remainder
         old_active = self._active()[0] if kind != EVENT_END_OF_CHAIN or self.events >= 0 else -1
-        if kind == EVENT_PAIR:
-            rec["target"] = [u.identifier[0] for u in winner._leaf_units if u.velocity is None][0]
+        if kind in (EVENT_PAIR, EVENT_BOND):
+            rec["target"] = [self.leaf_id(u.identifier) for u in winner._leaf_units if u.velocity is None][0]
         elif kind == EVENT_CELL_BOUNDING:
             rec["target"] = [u.identifier[0] for u in winner._leaf_units if u.velocity is None][0]
             rec["target_cell"] = self._cell_index(winner._relative_cell)
@@ -304,7 +338,7 @@ class ReferenceRun:
             occ = self.mediator._activator.get_info_internal_state(winner, cell)
             rec["target"] = occ[0][0] if occ else -1
         elif kind == EVENT_END_OF_CHAIN:
-            rec["target"] = self.mediator._out_state_arguments[winner][0][0][0]
+            rec["target"] = self.leaf_id(self.mediator._out_state_arguments[winner][0][0])
         self._current = (rec, old_active, kind)
         self.iterations.append((name, float(rec["time_q"] + rec["time_r"])))
 
@@ -313,7 +347,7 @@ class ReferenceRun:
         self._current = None
         new_active, direction, _, _ = self._active()
         sh = self.mediator._state_handler
-        pos = sh._physical_state.get((old_active,)).value.position
+        pos = sh._physical_state.get(self._identifier_of(old_active)).value.position
         rec["new_active"] = new_active
         rec["new_direction"] = direction
         rec["accepted"] = int(new_active != old_active or kind == EVENT_END_OF_CHAIN)
@@ -325,8 +359,24 @@ class ReferenceRun:
         self.records.append(rec.copy())
         self.events += 1
 
+    def _identifier_of(self, leaf):
+        if self.setting.number_of_node_levels == 1:
+            return (leaf,)
+        npr = self.setting.number_of_nodes_per_root_node
+        return (leaf // npr, leaf % npr)
+
     # -- state snapshots -------------------------------------------------------------------------------
     def positions(self):
+        """Leaf positions in flat leaf order."""
+        sh = self.mediator._state_handler
+        n = self.setting.number_of_root_nodes
+        if self.setting.number_of_node_levels == 1:
+            return np.array([sh._physical_state.get((i,)).value.position for i in range(n)], dtype=np.float64)
+        npr = self.setting.number_of_nodes_per_root_node
+        return np.array([sh._physical_state.get((i, k)).value.position for i in range(n) for k in range(npr)],
+                        dtype=np.float64)
+
+    def roots(self):
         sh = self.mediator._state_handler
         n = self.setting.number_of_root_nodes
         return np.array([sh._physical_state.get((i,)).value.position for i in range(n)], dtype=np.float64)
@@ -345,8 +395,8 @@ class ReferenceRun:
         occ = np.full((len(cells), max_occupants), -1, dtype=np.int32)
         for index, cell in enumerate(cells):
             for s, identifier in enumerate(ist._occupants[cell]):
-                occ[index, s] = identifier[0]
-        surplus = [identifier[0] for identifier in ist.yield_surplus()]
+                occ[index, s] = self.leaf_id(identifier)
+        surplus = [self.leaf_id(identifier) for identifier in ist.yield_surplus()]
         return occ, np.array(surplus, dtype=np.int32)
 
     def run(self, max_events=None, snapshot_every=None, max_occupants=1):
@@ -389,7 +439,8 @@ class ReferenceRun:
     def _snapshot(self, max_occupants):
         occ, surplus = self.occupancy(max_occupants)
         active, direction, _, stamp = self._active()
-        self.snapshots.append({"event": self.events, "positions": self.positions(), "occupants": occ,
+        self.snapshots.append({"event": self.events, "positions": self.positions(), "roots": self.roots(),
+                               "occupants": occ,
                                "surplus": surplus, "active": active, "direction": direction,
                                "time_q": stamp.quotient, "time_r": stamp.remainder})
 

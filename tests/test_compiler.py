@@ -18,8 +18,9 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "jellyfysh"
                                 reason="baseline/_ref (installed reference) not present")
 
 
-def build_reference_graph(ini_text, positions=None):
-    """The reference's run.py:182-183 on INI text; returns (mediator, setting module)."""
+def build_reference_graph(ini_text, positions=None, composites=None):
+    """The reference's run.py:182-183 on INI text; returns (mediator, setting module). positions / composites: the
+    start configuration fed to the reference's random input handler (configs.patch_composite_start)."""
     if REF not in sys.path:
         sys.path.insert(0, REF)
     import warnings
@@ -37,8 +38,13 @@ def build_reference_graph(ini_text, positions=None):
     if positions is not None:
         iterator = iter([list(map(float, p)) for p in positions])
         setting.random_position = lambda: next(iterator)
-    with contextlib.redirect_stdout(io.StringIO()):
-        mediator = factory.build_from_config(config, to_camel_case(config.get("Run", "mediator")), "jellyfysh.mediator")
+    restore = configs.patch_composite_start(composites) if composites is not None else (lambda: None)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mediator = factory.build_from_config(config, to_camel_case(config.get("Run", "mediator")),
+                                                 "jellyfysh.mediator")
+    finally:
+        restore()
     return mediator, setting
 
 
@@ -83,8 +89,8 @@ def test_compiled_program_replays_reference_trace(oracle, lj_graph):
     g, mediator = lj_graph
     template = mediator._state_handler.extract_global_state()
     compiled = compiler.compile_program(mediator._activator, template, seed=int(g["seed"][0]))
-    positions, charges = compiler.positions_and_charges(template, compiled.charge_name)
-    assert np.array_equal(positions, g["positions0"]) and charges is None
+    positions, charges, roots = compiler.positions_and_charges(template, compiled.charge_name)
+    assert np.array_equal(positions, g["positions0"]) and charges is None and roots is None
     chain = oracle.OracleChain(compiled.builder)
     chain.set_positions(positions)
     chain.start(stream=int(g["seed"][1]))
@@ -112,12 +118,46 @@ def test_coulomb_graph_compiles_with_charges():
         setting.reset()
 
 
+def test_hard_disk_dipole_graph_compiles_and_replays(oracle):
+    """C1: the shipped hard_disk_dipoles_cells.ini (composite point objects, leaf-level cells, unbounded occupancy,
+    hard-sphere pairs + hard-dipole tether from the factor type map) -> compiler -> oracle chain reproduces the
+    reference's recorded run bit for bit."""
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_hard_disk_dipoles")
+    n_roots = len(g["roots0"])
+    composites = (g["roots0"], g["positions0"].reshape(n_roots, 2, -1))
+    mediator, setting = build_reference_graph(configs.hard_disk_dipoles_cells_ini(REF, end_of_run_time=50.0),
+                                              composites=composites)
+    try:
+        template = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, template, seed=int(g["seed"][0]), occupant_capacity=6)
+        p = compiled.builder.program
+        assert (p.dimension, p.n_particles, p.nodes_per_root, p.n_bonds) == (2, 162, 2, 1)
+        assert (p.bonds[0][0], p.bonds[0][1]) == (0, 1) and p.bond_potential.kind == abi.POT_HARD_DIPOLE
+        assert p.pair_handler == abi.PAIR_TWO_LEAF_UNIT and p.pair_potential.kind == abi.POT_HARD_SPHERE
+        assert p.veto_enabled == 0 and p.max_occupants == 6 and p.max_surplus == 0 and p.initial_active == 0
+        # the lengths recovered from the stored squares reproduce them exactly
+        assert 4.0 * p.pair_potential.params[0] * p.pair_potential.params[0] == 4.0 * 0.476190476190476 * 0.476190476190476
+        assert p.bond_potential.params[0] * p.bond_potential.params[0] == 0.952380952380952 * 0.952380952380952
+        positions, charges, roots = compiler.positions_and_charges(template, compiled.charge_name)
+        assert np.array_equal(positions, g["positions0"]) and np.array_equal(roots, g["roots0"]) and charges is None
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions)
+        chain.set_roots(roots)
+        chain.start(stream=int(g["seed"][1]))
+        n, rec = chain.run(max_events=3000, record=3000)
+        assert n == 3000 and tu.records_equal_discrete(rec, g["records"][:3000])
+        assert np.array_equal(rec["time_r"], g["records"]["time_r"][:3000])
+    finally:
+        setting.reset()
+
+
 def test_unsupported_graphs_are_rejected(lj_graph):
-    """A dumping handler or an unbounded occupancy is refused, never approximated."""
+    """A graph the device cannot run faithfully is refused, never approximated."""
     from jellyfysh.base.exceptions import ConfigurationError
     from jellyfysh_b200 import compiler
     g, mediator = lj_graph
     occupancy = mediator._activator._internal_states[0]
-    occupancy._maximum_number_occupants = 0
+    occupancy._cell_level = 2
     with pytest.raises(ConfigurationError):
         compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())

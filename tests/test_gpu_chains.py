@@ -96,7 +96,8 @@ def _lj_batch(oracle, n_chains, n=48, cells=4, length=4.6, seed=5, chain_time=1.
     return pb, positions
 
 
-def _compare_batch_with_oracle(oracle, pb, positions, charges, n_events, first_stream, tag, resync_every=None):
+def _compare_batch_with_oracle(oracle, pb, positions, charges, n_events, first_stream, tag, resync_every=None,
+                               roots=None):
     """Run the same seeded chains on the GPU and in the oracle and compare every event and the final state.
 
     Event chains are chaotic (hard-core collisions amplify a rounding difference of 1e-16 by a constant factor per
@@ -109,18 +110,23 @@ def _compare_batch_with_oracle(oracle, pb, positions, charges, n_events, first_s
     for c in range(n_chains):
         chain = oracle.OracleChain(pb)
         chain.set_positions(positions[c], None if charges is None else charges[c])
+        if roots is not None:
+            chain.set_roots(roots[c])
         chain.start(stream=first_stream + c)
         chains.append(chain)
     total = dict.fromkeys(["events", "pair_events", "veto_events", "veto_accepted", "boundary_events",
-                           "end_of_chain_events", "candidates"], 0)
+                           "end_of_chain_events", "candidates", "bond_events"], 0)
     segment = resync_every or n_events
     with engine.Engine(pb, n_chains=n_chains) as eng:
         eng.upload_positions(positions, charges)
+        if roots is not None:
+            eng.upload_roots(roots)
         eng.start(first_stream=first_stream)
         for begin in range(0, n_events, segment):
             count = min(segment, n_events - begin)
             rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
             final = eng.download_positions()
+            final_roots = eng.download_roots() if roots is not None else None
             occ, surplus = eng.cells()
             states = eng.chain_states()
             for c, chain in enumerate(chains):
@@ -128,6 +134,8 @@ def _compare_batch_with_oracle(oracle, pb, positions, charges, n_events, first_s
                 assert n == count
                 assert_records_match(rec[c], ref, length, f"{tag} chain {c} events {begin}+")
                 assert np.max(np.abs(final[c] - chain.positions())) < RTOL * max(1.0, length)
+                if roots is not None:
+                    assert np.max(np.abs(final_roots[c] - chain.roots())) < RTOL * max(1.0, length)
                 o_occ, o_sur = chain.cells()
                 assert np.array_equal(occ[c], o_occ)
                 assert surplus[c].tolist() == o_sur.tolist()
@@ -139,6 +147,8 @@ def _compare_batch_with_oracle(oracle, pb, positions, charges, n_events, first_s
                 total[key] += stats[key]
             if resync_every:
                 eng.upload_positions(np.stack([chain.positions() for chain in chains]), charges)
+                if roots is not None:
+                    eng.upload_roots(np.stack([chain.roots() for chain in chains]))
                 new_states = states.copy()
                 for c, chain in enumerate(chains):
                     st = chain.state()
@@ -216,6 +226,56 @@ def test_hard_disks_2d_against_oracle(oracle):
     positions = np.stack([(grid + 0.5) * (length / 6) + rng.uniform(-0.3, 0.3, size=(n, 2)) for _ in range(5)])
     stats = _compare_batch_with_oracle(oracle, pb, positions, None, 600, 3, "hard disks", resync_every=40)
     assert stats["pair_events"] > 50 and stats["veto_events"] == 0
+
+
+def _dipole_batch(n_chains, columns=5, rows=9, length=11.0, seed=3, chain_time=1.0, max_occupants=6):
+    """columns x rows hard-disk dipoles lying along x on a jittered lattice (the C1 structure, smaller)."""
+    hs = abi.EcmcPotential.make(abi.POT_HARD_SPHERE, 0.476190476190476)
+    tether = abi.EcmcPotential.make(abi.POT_HARD_DIPOLE, 0.952380952380952, 1.047619047619048)
+    n_roots = columns * rows
+    pb = ProgramBuilder(2, 2 * n_roots, length, 1.0, [11, 11], 1, max_occupants=max_occupants, max_surplus=0,
+                        chain_time=chain_time, seed=seed)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT, hs)
+    pb.set_composite(2, bonds=[(0, 1)], bond_potential=tether)
+    rng = np.random.default_rng(300 + seed)
+    grid = np.stack(np.meshgrid(np.arange(columns), np.arange(rows), indexing="ij"), axis=-1).reshape(-1, 2)
+    roots = np.empty((n_chains, n_roots, 2))
+    leaves = np.empty((n_chains, n_roots, 2, 2))
+    for c in range(n_chains):
+        centre = (grid + 0.5) * np.array([length / columns, length / rows]) + rng.uniform(-0.02, 0.02, size=(n_roots, 2))
+        angle = rng.uniform(-0.05, 0.05, size=n_roots)
+        half = 0.5 * rng.uniform(0.96, 1.04, size=n_roots)
+        offset = np.stack([np.cos(angle), np.sin(angle)], axis=1) * half[:, None]
+        roots[c] = centre % length
+        leaves[c, :, 0] = (centre + offset) % length
+        leaves[c, :, 1] = (centre - offset) % length
+    return pb, roots, leaves.reshape(n_chains, 2 * n_roots, 2)
+
+
+def test_hard_disk_dipoles_against_oracle(oracle):
+    """Composite point objects (C1 structure): hard-sphere pairs through leaf-level cells with several occupants,
+    the hard-dipole tether of the factor type map, root units time-sliced with their active leaf, end of chain drawing
+    (root, child). Chaotic: re-seeded from the oracle every 40 events."""
+    pb, roots, leaves = _dipole_batch(n_chains=6)
+    stats = _compare_batch_with_oracle(oracle, pb, leaves, None, 1200, 5, "dipoles", resync_every=40, roots=roots)
+    assert stats["pair_events"] > 300 and stats["bond_events"] > 100 and stats["end_of_chain_events"] > 20
+
+
+def test_hard_disk_dipoles_reference_trace():
+    """The shipped hard_disk_dipoles_cells.ini from the shipped start configuration (tests/golden/
+    trace_hard_disk_dipoles.npz, recorded from the running reference): every segment between two snapshots of the
+    reference starts from the reference's own state and must reproduce its events."""
+    g = tu.load_trace("trace_hard_disk_dipoles")
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    pb = tu.dipole_builder_of(g, ProgramBuilder)
+    with engine.Engine(pb, n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        rec, stats = eng.run_recorded(max_events=120, records_per_chain=120)
+        assert_records_match(rec[0], records[:120], length, "dipole trace")
+        assert stats["bond_events"] > 5 and stats["capacity_errors"] == 0
 
 
 def test_single_particle_chain(oracle):

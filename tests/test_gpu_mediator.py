@@ -148,3 +148,106 @@ def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path, con
     # correlated, so n is taken as the number of chains times a conservative 10 independent samples each
     assert distance < 1.95 / np.sqrt(chains * 10) + 1.0e-3, distance
     assert 0.2 < np.median(samples) < 0.8
+
+
+def _dipole_ini(tmp_path, chains, end_of_run_time, sampling):
+    ini = configs.hard_disk_dipoles_cells_ini(REF, end_of_run_time=end_of_run_time, sampling=sampling,
+                                              output=str(tmp_path / "polarization.dat"))
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 17\n"
+                                                 "first_random_stream = 9\noccupant_capacity = 6" % chains)
+    return ini
+
+
+def test_shipped_hard_disk_dipoles_config_runs_on_the_device(oracle, tmp_path):
+    """C1: config_files/hard_disk_dipoles/hard_disk_dipoles_cells.ini through CudaBatchedMediator (only the mediator
+    line and the input handler differ, see configs.hard_disk_dipoles_cells_ini), from the shipped start configuration.
+    The final state handed back to the reference's tree state handler (leaf and root units, velocities with the
+    root's weight, time stamps) is the one the oracle -- bit-exact with the reference on this trace -- reaches."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    g = tu.load_trace("trace_hard_disk_dipoles")
+    n_roots = len(g["roots0"])
+    composites = (g["roots0"], g["positions0"].reshape(n_roots, 2, -1))
+    end = 30.0
+    mediator, setting = build_reference_graph(_dipole_ini(tmp_path, 1, end, sampling=True), composites=composites)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        state = mediator._state_handler.extract_global_state()
+        roots = np.array([node.value.position for node in state])
+        leaves = np.array([child.value.position for node in state for child in node.children])
+        active = [(node.value.identifier, node.value.velocity) for node in state if node.value.velocity is not None]
+        active += [(child.value.identifier, child.value.velocity) for node in state for child in node.children
+                   if child.value.velocity is not None]
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["events"] > 400 and stats["bond_events"] > 20 and stats["capacity_errors"] == 0
+    chain = oracle.OracleChain(tu.dipole_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"])
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    total = 0
+    for k in list(range(1, int(end / 10.01) + 1)) + [None]:
+        until = oracle.time_from_float(end if k is None else 10.01 * k)
+        n, _ = chain.run(until=until)
+        total += n
+    assert total == stats["events"]
+    assert np.max(np.abs(leaves - chain.positions())) < 1e-12 * 12.836
+    assert np.max(np.abs(roots - chain.roots())) < 1e-12 * 12.836
+    st = chain.state()
+    assert len(active) == 2  # the active disk and its dipole
+    assert active[0][0] == (st.active // 2,) and active[1][0] == (st.active // 2, st.active % 2)
+    assert active[1][1][st.direction] == 1.0 and active[0][1][st.direction] == 0.5
+    samples = np.loadtxt(tmp_path / "polarization.dat", comments="#")
+    assert samples.shape == (int(end / 10.01) + 1, 2)  # first_event_time_zero = True
+
+
+def test_hard_disk_dipoles_polarization_statistics(tmp_path):
+    """Statistical check of C1: the polarization of 81 hard-disk dipoles sampled by the reference's own
+    PolarizationOutputHandler from 192 device chains follows the cumulative histograms the reference ships
+    (ReferenceDataP{x,y}_81Dipoles_NewtonianECMC.dat, fixture tests/golden/reference_cdfs.npz)."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import kat_replay as kr
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    g = tu.load_trace("trace_hard_disk_dipoles")
+    n_roots = len(g["roots0"])
+    composites = (g["roots0"], g["positions0"].reshape(n_roots, 2, -1))
+    # the polarization is a slow collective variable: sample every 500.5 time units (the shipped file: 10.01) over
+    # 6 x 10^4 time units per chain, about 1.2 x 10^6 events each
+    chains, end, interval = 256, 60000.0, 500.5
+    ini = _dipole_ini(tmp_path, chains, end, sampling=True).replace("sampling_interval = 10.01",
+                                                                    "sampling_interval = %r" % interval)
+    assert "sampling_interval = 500.5" in ini
+    mediator, setting = build_reference_graph(ini, composites=composites)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["capacity_errors"] == 0
+    samples = np.loadtxt(tmp_path / "polarization.dat", comments="#")
+    per_chain = int(end / interval) + 1
+    assert samples.shape == (chains * per_chain, 2)
+    samples = samples.reshape(per_chain, chains, 2)[per_chain // 5:].reshape(-1, 2)  # all chains share the start
+    ref = kr.load_npz("reference_cdfs")
+    for axis, key in enumerate(("dipoles_px", "dipoles_py")):
+        x, cdf = ref[key + "_x"], ref[key + "_cdf"]
+        edges = x + 0.5 * (x[1] - x[0])
+        ours = np.searchsorted(np.sort(samples[:, axis]), edges, side="right") / len(samples)
+        distance = np.max(np.abs(ours - cdf))
+        print(key, "KS distance", distance, "samples", len(samples))
+        # Kolmogorov-Smirnov at the 0.1 % level, counting a conservative 10 independent samples per chain
+        assert distance < 1.95 / np.sqrt(chains * 10) + 5.0e-3, (key, distance)

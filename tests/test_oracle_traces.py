@@ -91,6 +91,39 @@ def test_cell_bounding_chain_replay_bit_exact(oracle, name):
     assert np.array_equal(chain.positions(), g["final_positions"])
 
 
+@pytest.mark.parametrize("name", tu.DIPOLE_TRACES)
+def test_composite_chain_replay_bit_exact(oracle, name):
+    """C1, the shipped hard_disk_dipoles_cells.ini from the shipped start configuration: composite point objects
+    (root units follow their active leaf), leaf-level cells with several occupants, hard-sphere pair events,
+    hard-dipole tether events of the factor type map, end of chain drawing (root, child)."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    chain = oracle.OracleChain(tu.dipole_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"])
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        for f in tu.DISCRETE_FIELDS:
+            assert np.array_equal(rec[f], ref[f]), (f, done + int(np.nonzero(rec[f] != ref[f])[0][0]))
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            assert np.array_equal(chain.roots(), g["snap_roots"][k])
+            occ, surplus = chain.cells()
+            assert np.array_equal(occ, g["snap_occupants"][k]) and len(surplus) == 0
+    assert np.array_equal(chain.positions(), g["final_positions"])
+    assert np.array_equal(chain.roots(), g["final_roots"])
+    stats = chain.stats()
+    assert stats["capacity_errors"] == 0 and stats["bond_events"] > 500 and stats["pair_events"] > 4000
+
+
 def test_time_limit_keeps_candidates(oracle):
     """Stopping at host control times (sampling) keeps the interaction winner: the event sequence is the same
     whether the chain runs in one go or is interrupted, up to the rounding of the extra time slices."""

@@ -6,6 +6,7 @@ from jellyfysh_b200 import abi
 
 TRACES = ["trace_lj_small", "trace_lj_surplus", "trace_coulomb_small", "trace_coulomb_surplus"]
 CELL_BOUNDING_TRACES = ["trace_coulomb_cell_bounded"]
+DIPOLE_TRACES = ["trace_hard_disk_dipoles"]
 DISCRETE_FIELDS = ("kind", "target", "target_cell", "accepted", "n_candidates", "new_active", "new_direction")
 
 
@@ -43,6 +44,18 @@ def builder_of(g, builder_cls, tables=None, max_surplus=128):
     else:
         pb.set_veto(veto, tables if tables is not None else reference_tables(g), use_charge=use_charge,
                     target_charge=1.0)
+    return pb
+
+
+def dipole_builder_of(g, builder_cls):
+    """C1: hard-disk dipoles (two disks per root, leaf-level cells, hard-sphere pairs, hard-dipole tether)."""
+    dimension = len(g["meta_cells_per_side"])
+    pb = builder_cls(dimension, int(g["meta_n"]), float(g["meta_system_length"]), float(g["meta_beta"]),
+                     [int(c) for c in g["meta_cells_per_side"]], 1, max_occupants=int(g["meta_max_occupants"]),
+                     max_surplus=0, chain_time=float(g["meta_chain_time"]), seed=int(g["seed"][0]))
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT, abi.EcmcPotential.make(abi.POT_HARD_SPHERE, *g["meta_hard_sphere"]))
+    pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1)],
+                     bond_potential=abi.EcmcPotential.make(abi.POT_HARD_DIPOLE, *g["meta_hard_dipole"]))
     return pb
 
 
