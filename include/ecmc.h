@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ECMC_ABI_VERSION 2
+#define ECMC_ABI_VERSION 3
 #define ECMC_MAX_BONDS 4
 #define ECMC_MAX_DIM 3
 
@@ -49,6 +49,8 @@ extern "C" {
  *                              jellyfysh/potential/merged_image_coulomb_potential/merged_image_coulomb_potential.c:77-274
  *  INVERSE_POWER_COULOMB_BOUNDING [0]=prefactor
  *                jellyfysh/potential/inverse_power_coulomb_bounding_potential/inverse_power_coulomb_bounding_potential.c:53-139
+ *  BENDING                  [0]=prefactor [1]=equilibrium_angle (three-unit potential, derivative only)
+ *                                                            jellyfysh/potential/bending_potential.py:60-138
  */
 enum EcmcPotentialKind {
     ECMC_POT_NONE = 0,
@@ -58,7 +60,8 @@ enum EcmcPotentialKind {
     ECMC_POT_HARD_SPHERE = 4,
     ECMC_POT_HARD_DIPOLE = 5,
     ECMC_POT_MERGED_IMAGE_COULOMB = 6,
-    ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING = 7
+    ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING = 7,
+    ECMC_POT_BENDING = 8
 };
 
 typedef struct EcmcPotential {
@@ -76,8 +79,24 @@ enum EcmcPairHandlerKind {
     /* TwoLeafUnitBoundingPotentialEventHandler: candidate from an invertible bounding potential, confirmed
      * against the real potential's derivative.
      * jellyfysh/event_handler/two_leaf_unit_bounding_potential_event_handler.py:112-168 */
-    ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING = 2
+    ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING = 2,
+    /* TwoCompositeObjectSummedBoundingPotentialEventHandler: the active leaf against every leaf of a composite object
+     * in a nearby cell / the surplus; candidate = minimum over the target leaves of the bounding potential's
+     * displacement, confirmed against the summed derivative, new active leaf from the lifting scheme.
+     * jellyfysh/event_handler/two_composite_object_summed_bounding_potential_event_handler.py:119-202.
+     * Needs cell_level = 1 (cells hold root units). With it the far field ECMC_FAR_CELL_VETO is the
+     * CompositeObjectCellVetoEventHandler (composite_object_cell_veto_event_handler.py:110-162). */
+    ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING = 3
 };
+
+/* ---- lifting schemes (jellyfysh/lifting/{inside_first,outside_first,ratio}_lifting.py) ---------------------------- */
+enum EcmcLiftingKind {
+    ECMC_LIFTING_NONE = 0,
+    ECMC_LIFTING_INSIDE_FIRST = 1,
+    ECMC_LIFTING_OUTSIDE_FIRST = 2,
+    ECMC_LIFTING_RATIO = 3
+};
+#define ECMC_MAX_INTER_FACTORS 4
 
 /* ---- far-field handlers ---------------------------------------------------------------------------------------- */
 enum EcmcFarFieldKind {
@@ -163,6 +182,31 @@ typedef struct EcmcProgram {
     int32_t n_bonds;
     int32_t bonds[ECMC_MAX_BONDS][2];
     EcmcPotential bond_potential;
+    /* ---- molecules in root-level cells (water, C4) ------------------------------------------------------------
+     * cell_level: 1 = the cells hold root units (SingleActiveCellOccupancy cell_level = 1 with two node levels: the
+     * cell-boundary handler follows the root unit, which moves with speed / nodes_per_root), 0 or 2 = leaf units. */
+    int32_t cell_level;
+    int32_t composite_lifting;   /* EcmcLiftingKind of the composite-object handlers (pair + cell veto) */
+    /* Two-leaf factors between DIFFERENT composite objects from a non-local factor type map entry, e.g.
+     * "[1, 4], LennardJones" of factor_set_water.txt: the active leaf with child index a against child b of every
+     * other object (factor_type_maps.py:333-347), each by a TwoLeafUnitEventHandler with inter_potential. */
+    int32_t n_inter_factors;
+    int32_t inter_factors[ECMC_MAX_INTER_FACTORS][2];
+    EcmcPotential inter_potential;
+    /* Three-leaf bending factor inside an object (FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential,
+     * jellyfysh/event_handler/fixed_separations_event_handler_with_piecewise_constant_bounding_potential.py:113-187):
+     * children bending_children[0..2] in factor order, separations r[s[1]] - r[s[0]] and r[s[3]] - r[s[2]] (indices into
+     * the three units), bounding rate = max(derivative now, derivative after max_displacement) + offset. */
+    int32_t bending_enabled;
+    int32_t bending_lifting;     /* EcmcLiftingKind */
+    int32_t bending_children[3];
+    int32_t bending_separations[4];
+    /* 1: a cell-boundary event of the root unit does not trash the leaf-level factor handlers (bonds, inter-object
+     * factors, bending), which then keep their candidates -- the tag lists of the shipped water configurations */
+    int32_t boundary_keeps_factors;
+    EcmcPotential bending_potential;
+    double bending_offset;
+    double bending_max_displacement;
 } EcmcProgram;
 
 /* ---- per-chain lifting state ("who is active, where is the clock") ------------------------------------
@@ -188,6 +232,17 @@ typedef struct EcmcChainState {
     double pending_position;
     double pending_stamp_q, pending_stamp_r;
     double pending_root_position; /* the same for the root unit of the active leaf (composite objects) */
+    /* Molecules (cell_level = 1) with EcmcProgram.boundary_keeps_factors: the earliest candidate of the leaf-level
+     * factors (bonds, inter-object factors, bending) when a cell-boundary event of the root unit left them running
+     * -- their handlers are not trashed by that event (e.g. [MoleculeCellBoundary] of the shipped water
+     * configurations), so they keep their event times and in-states, and consume no new draws. kept_kind = 0: nothing
+     * kept (all factors are recomputed); -1: kept, but no factor candidate was finite. */
+    int32_t kept_kind;
+    int32_t kept_target;
+    double kept_q, kept_r;
+    double kept_rate;
+    double kept_position, kept_root_position;
+    double kept_stamp_q, kept_stamp_r;
 } EcmcChainState;
 
 enum EcmcEventKind {
@@ -197,13 +252,16 @@ enum EcmcEventKind {
     ECMC_EVENT_CELL_BOUNDARY = 3,
     ECMC_EVENT_END_OF_CHAIN = 4,
     ECMC_EVENT_CELL_BOUNDING = 5, /* pair factor of a non-nearby cell, found through the cell-bounding potential */
-    ECMC_EVENT_BOND = 6           /* intramolecular two-leaf factor of the factor type map (EcmcProgram.bonds) */
+    ECMC_EVENT_BOND = 6,          /* intramolecular two-leaf factor of the factor type map (EcmcProgram.bonds) */
+    ECMC_EVENT_FACTOR_PAIR = 7,   /* two-leaf factor between different objects (EcmcProgram.inter_factors) */
+    ECMC_EVENT_BENDING = 8        /* three-leaf bending factor */
 };
 
 /* One committed event, as the scheduler + winning handler of the reference would report it. */
 typedef struct EcmcEventRecord {
     int32_t kind;             /* EcmcEventKind of the winner (argmin) */
-    int32_t target;           /* pair / cell bounding / accepted or rejected veto: target particle (-1: empty veto cell) */
+    int32_t target;           /* pair / cell bounding / accepted or rejected veto: target particle (-1: empty veto cell);
+                               * composite-object pair and veto: the target ROOT unit */
     int32_t target_cell;      /* veto: sampled target cell; boundary: new cell; cell bounding: relative cell; else -1 */
     int32_t accepted;         /* 1 if the velocity was handed over (lifting happened) */
     int32_t n_candidates;     /* finite candidate times that entered the argmin */
@@ -224,8 +282,9 @@ typedef struct EcmcStats {
     uint64_t candidates;        /* finite candidates that entered an argmin */
     uint64_t bound_violations;  /* real derivative exceeded its bound (reference: bounding_potential_warning) */
     uint64_t capacity_errors;   /* surplus / occupant overflow (fatal: results invalid) */
-    uint64_t bond_events;       /* events of the intramolecular factor-type-map factors */
-    uint64_t reserved[2];
+    uint64_t bond_events;       /* events of the intramolecular factor-type-map factors (bonds + bending) */
+    uint64_t factor_pair_events; /* events of the inter-object two-leaf factors */
+    uint64_t reserved[1];
 } EcmcStats;
 
 typedef struct EcmcHandle EcmcHandle;
@@ -318,6 +377,10 @@ void ecmc_random_words(uint32_t seed, uint32_t stream, uint64_t event, uint32_t 
 #define ECMC_SLOT_END_OF_CHAIN 5u    /* words -> randint(0, n_particles - 1) (rejection loop) */
 #define ECMC_SLOT_LIFTING 6u         /* doubles -> Lifting.insert / RatioLifting draws */
 #define ECMC_SLOT_FACTOR_TIME 7u     /* index = target leaf; factor-type-map pair factors: double 0 -> expovariate(beta) */
+#define ECMC_SLOT_BENDING_TIME 8u    /* double 0 -> expovariate(beta) of the bending factor */
+/* Composite-object pair candidates draw double k of (ECMC_SLOT_PAIR_TIME, target root) for target leaf k. All draws of an
+ * out-state come from ECMC_SLOT_CONFIRM in call order: 0 = confirmation, 1 = Lifting.insert of the active unit,
+ * 2 = RatioLifting.get_active_identifier. */
 #define ECMC_SLOT(kind, index) (((uint32_t)(kind) << 24) | ((uint32_t)(index) & 0xFFFFFFu))
 
 #ifdef __cplusplus

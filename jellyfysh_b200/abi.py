@@ -1,9 +1,10 @@
 """ctypes mirror of include/ecmc.h (the C ABI of libecmc_b200.so). Plain data only, no computation."""
 import ctypes as C
 
-ECMC_ABI_VERSION = 2
+ECMC_ABI_VERSION = 3
 ECMC_MAX_DIM = 3
 ECMC_MAX_BONDS = 4
+ECMC_MAX_INTER_FACTORS = 4
 
 ECMC_OK = 0
 ECMC_ERR_INVALID = -1
@@ -19,10 +20,17 @@ POT_HARD_SPHERE = 4
 POT_HARD_DIPOLE = 5
 POT_MERGED_IMAGE_COULOMB = 6
 POT_INVERSE_POWER_COULOMB_BOUNDING = 7
+POT_BENDING = 8
 
 PAIR_NONE = 0
 PAIR_TWO_LEAF_UNIT = 1
 PAIR_TWO_LEAF_UNIT_BOUNDING = 2
+PAIR_TWO_COMPOSITE_SUMMED_BOUNDING = 3
+
+LIFTING_NONE = 0
+LIFTING_INSIDE_FIRST = 1
+LIFTING_OUTSIDE_FIRST = 2
+LIFTING_RATIO = 3
 
 EVENT_NONE = 0
 EVENT_PAIR = 1
@@ -31,13 +39,16 @@ EVENT_CELL_BOUNDARY = 3
 EVENT_END_OF_CHAIN = 4
 EVENT_CELL_BOUNDING = 5
 EVENT_BOND = 6
+EVENT_FACTOR_PAIR = 7
+EVENT_BENDING = 8
 
 FAR_NONE = 0
 FAR_CELL_VETO = 1
 FAR_CELL_BOUNDING = 2
 EVENT_NAMES = {EVENT_NONE: "none", EVENT_PAIR: "pair", EVENT_CELL_VETO: "cell_veto",
                EVENT_CELL_BOUNDARY: "cell_boundary", EVENT_END_OF_CHAIN: "end_of_chain",
-               EVENT_CELL_BOUNDING: "cell_bounding", EVENT_BOND: "bond"}
+               EVENT_CELL_BOUNDING: "cell_bounding", EVENT_BOND: "bond", EVENT_FACTOR_PAIR: "factor_pair",
+               EVENT_BENDING: "bending"}
 
 SLOT_PAIR_TIME = 1
 SLOT_VETO_TIME = 2
@@ -46,6 +57,7 @@ SLOT_CONFIRM = 4
 SLOT_END_OF_CHAIN = 5
 SLOT_LIFTING = 6
 SLOT_FACTOR_TIME = 7
+SLOT_BENDING_TIME = 8
 
 
 def slot(kind: int, index: int = 0) -> int:
@@ -92,7 +104,14 @@ class EcmcProgram(C.Structure):
                 ("initial_direction", C.c_int32), ("initial_active", C.c_int32),
                 ("seed", C.c_uint32), ("reserved1", C.c_uint32),
                 ("nodes_per_root", C.c_int32), ("n_bonds", C.c_int32),
-                ("bonds", (C.c_int32 * 2) * ECMC_MAX_BONDS), ("bond_potential", EcmcPotential)]
+                ("bonds", (C.c_int32 * 2) * ECMC_MAX_BONDS), ("bond_potential", EcmcPotential),
+                ("cell_level", C.c_int32), ("composite_lifting", C.c_int32),
+                ("n_inter_factors", C.c_int32), ("inter_factors", (C.c_int32 * 2) * ECMC_MAX_INTER_FACTORS),
+                ("inter_potential", EcmcPotential),
+                ("bending_enabled", C.c_int32), ("bending_lifting", C.c_int32),
+                ("bending_children", C.c_int32 * 3), ("bending_separations", C.c_int32 * 4), ("boundary_keeps_factors", C.c_int32),
+                ("bending_potential", EcmcPotential), ("bending_offset", C.c_double),
+                ("bending_max_displacement", C.c_double)]
 
 
 class EcmcChainState(C.Structure):
@@ -105,7 +124,10 @@ class EcmcChainState(C.Structure):
                 ("pending_target", C.c_int32), ("reserved", C.c_int32),
                 ("pending_q", C.c_double), ("pending_r", C.c_double), ("pending_rate", C.c_double),
                 ("pending_position", C.c_double), ("pending_stamp_q", C.c_double), ("pending_stamp_r", C.c_double),
-                ("pending_root_position", C.c_double)]
+                ("pending_root_position", C.c_double),
+                ("kept_kind", C.c_int32), ("kept_target", C.c_int32), ("kept_q", C.c_double), ("kept_r", C.c_double),
+                ("kept_rate", C.c_double), ("kept_position", C.c_double), ("kept_root_position", C.c_double),
+                ("kept_stamp_q", C.c_double), ("kept_stamp_r", C.c_double)]
 
 
 class EcmcEventRecord(C.Structure):
@@ -120,7 +142,7 @@ class EcmcStats(C.Structure):
                 ("veto_accepted", C.c_uint64), ("boundary_events", C.c_uint64),
                 ("end_of_chain_events", C.c_uint64), ("candidates", C.c_uint64),
                 ("bound_violations", C.c_uint64), ("capacity_errors", C.c_uint64),
-                ("bond_events", C.c_uint64), ("reserved", C.c_uint64 * 2)]
+                ("bond_events", C.c_uint64), ("factor_pair_events", C.c_uint64), ("reserved", C.c_uint64 * 1)]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
@@ -142,8 +164,11 @@ def chain_state_dtype():
                      ("pending_target", "<i4"), ("reserved", "<i4"),
                      ("pending_q", "<f8"), ("pending_r", "<f8"), ("pending_rate", "<f8"),
                      ("pending_position", "<f8"), ("pending_stamp_q", "<f8"), ("pending_stamp_r", "<f8"),
-                     ("pending_root_position", "<f8")])
+                     ("pending_root_position", "<f8"),
+                     ("kept_kind", "<i4"), ("kept_target", "<i4"), ("kept_q", "<f8"), ("kept_r", "<f8"),
+                     ("kept_rate", "<f8"), ("kept_position", "<f8"), ("kept_root_position", "<f8"),
+                     ("kept_stamp_q", "<f8"), ("kept_stamp_r", "<f8")])
 
 
 assert C.sizeof(EcmcEventRecord) == 72
-assert C.sizeof(EcmcChainState) == 128
+assert C.sizeof(EcmcChainState) == 192

@@ -64,6 +64,34 @@ class ProgramBuilder:
             p.bond_potential = bond_potential
         return self
 
+    def set_molecules(self, lifting, inter_factors=(), inter_potential=None, bending=None, boundary_keeps_factors=True):
+        """Composite objects in root-level cells (water): the pair handler set by set_pair(PAIR_TWO_COMPOSITE_...)
+        and the cell veto act on whole objects with the given lifting scheme; inter_factors = (child a, child b) leaf
+        factors between different objects with inter_potential; bending = dict(children, separations, potential,
+        offset, max_displacement, lifting)."""
+        p = self.program
+        p.cell_level = 1
+        p.composite_lifting = lifting
+        p.boundary_keeps_factors = int(boundary_keeps_factors)
+        if len(inter_factors) > abi.ECMC_MAX_INTER_FACTORS:
+            raise ValueError("too many inter-object factors")
+        p.n_inter_factors = len(inter_factors)
+        for i, (a, b) in enumerate(inter_factors):
+            p.inter_factors[i][0], p.inter_factors[i][1] = a, b
+        if inter_potential is not None:
+            p.inter_potential = inter_potential
+        if bending is not None:
+            p.bending_enabled = 1
+            p.bending_lifting = bending["lifting"]
+            for i, child in enumerate(bending["children"]):
+                p.bending_children[i] = child
+            for i, index in enumerate(bending["separations"]):
+                p.bending_separations[i] = index
+            p.bending_potential = bending["potential"]
+            p.bending_offset = bending["offset"]
+            p.bending_max_displacement = bending["max_displacement"]
+        return self
+
     def set_cell_bounding(self, potential, bounds, use_charge=False, target_charge=1.0):
         """Far field through TwoLeafUnitCellBoundingPotentialEventHandler: bounds[n_cells][dimension][2] holds
         (upper bound, -lower bound) of the derivative per relative cell (CellBoundingPotential._derivative_bounds)."""

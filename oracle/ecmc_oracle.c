@@ -636,6 +636,7 @@ static int pot_make(opotential *o, const EcmcPotential *p, double L) {
     case ECMC_POT_MERGED_IMAGE_COULOMB:
         return mic_make(&o->mic, p->params[0], p->params[1], (int)p->params[2], (int)p->params[3], L);
     case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING: o->p0 = p->params[0]; return 0;
+    case ECMC_POT_BENDING: o->p0 = p->params[0]; o->p1 = p->params[1]; return 0;
     default: return -1;
     }
 }
@@ -656,6 +657,27 @@ static double pot_derivative(const opotential *o, int dir, double speed, const d
     default: return NAN;
     }
 }
+/* BendingPotential.derivative (bending_potential.py:60-138): time derivatives with respect to the units i, j, k for
+ * separation_one = r_i - r_j, separation_two = r_k - r_j. vectors.norm = sqrt(sum of squares), sum() compensated. */
+static void bending_derivative(double prefactor, double equilibrium_angle, int dir, double speed, const double *s1,
+                               const double *s2, int D, double out[3]) {
+    double n1 = v_norm(s1, D), n2 = v_norm(s2, D);
+    pysum dot;
+    pysum_init(&dot);
+    for (int i = 0; i < D; i++) pysum_add(&dot, s1[i] * s2[i]);
+    double cosine = pysum_result(&dot) / n1 / n2;
+    double angle = acos(cosine);
+    double du_dangle = prefactor * (angle - equilibrium_angle);
+    double dangle_dcos = -1.0 / sin(angle);
+    double dcos_ds1 = s2[dir] / n1 / n2 - cosine * s1[dir] / pow(n1, 2.0);
+    double dcos_ds2 = s1[dir] / n1 / n2 - cosine * s2[dir] / pow(n2, 2.0);
+    double du_ds1 = du_dangle * dangle_dcos * dcos_ds1;
+    double du_ds2 = du_dangle * dangle_dcos * dcos_ds2;
+    out[0] = du_ds1 * speed;
+    out[1] = (-du_ds1 - du_ds2) * speed;
+    out[2] = du_ds2 * speed;
+}
+
 /* InvertiblePotential.displacement: time displacement. For standard-velocity potentials
  * standard_velocity_displacement(...) / speed (abstracts.py:212-243); hard potentials take the velocity. */
 static double pot_displacement(const opotential *o, int dir, double speed, double *sep, int D, double c1, double c2,
@@ -952,7 +974,8 @@ typedef struct OrcChain {
     int D, N;
     double L;
     ocells cells;
-    opotential pair_pot, pair_bound, veto_pot, bond_pot;
+    opotential pair_pot, pair_bound, veto_pot, bond_pot, inter_pot, bending_pot;
+    int molecules; /* composite objects in root-level cells (cell_level = 1 with two node levels) */
     int npr;          /* nodes per root (1: point masses) */
     double *root_pos; /* [N / npr][D] root-unit positions of composite objects */
     /* copied veto tables */
@@ -995,6 +1018,7 @@ ORC_API void orc_chain_destroy(OrcChain *c) {
     free(c->pos); free(c->charge); free(c->occ); free(c->surplus); free(c->root_pos);
     cells_free(&c->cells);
     pot_free(&c->pair_pot); pot_free(&c->pair_bound); pot_free(&c->veto_pot); pot_free(&c->bond_pot);
+    pot_free(&c->inter_pot); pot_free(&c->bending_pot);
     free(c);
 }
 
@@ -1009,7 +1033,13 @@ ORC_API OrcChain *orc_chain_create(const EcmcProgram *prog) {
     if (pot_make(&c->pair_bound, &prog->pair_bounding_potential, c->L)) goto fail;
     if (pot_make(&c->veto_pot, &prog->veto_potential, c->L)) goto fail;
     if (pot_make(&c->bond_pot, &prog->bond_potential, c->L)) goto fail;
+    if (pot_make(&c->inter_pot, &prog->inter_potential, c->L)) goto fail;
+    if (pot_make(&c->bending_pot, &prog->bending_potential, c->L)) goto fail;
     c->npr = prog->nodes_per_root > 1 ? prog->nodes_per_root : 1;
+    c->molecules = prog->cell_level == 1 && c->npr > 1;
+    if ((prog->pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || prog->n_inter_factors > 0 ||
+         prog->bending_enabled) && !c->molecules) goto fail;
+    if (c->molecules && (c->D != 3 || c->npr > 4 || prog->max_occupants != 1)) goto fail;
     if (c->N % c->npr || prog->n_bonds < 0 || prog->n_bonds > ECMC_MAX_BONDS) goto fail;
     if (prog->n_bonds > 0 && c->npr == 1) goto fail;
     c->root_pos = (double *)calloc((size_t)(c->N / c->npr) * c->D, sizeof(double));
@@ -1138,15 +1168,25 @@ ORC_API void orc_chain_start(OrcChain *c, uint32_t stream) {
     int m = c->prog.max_occupants;
     for (int i = 0; i < c->cells.n_cells * m; i++) c->occ[i] = -1;
     c->n_surplus = 0;
-    for (int i = 0; i < c->N; i++) occ_insert(c, position_to_cell(&c->cells, c->pos + i * c->D), i);
+    if (c->molecules) {
+        /* cell_level = 1: the cells hold the root units (single_active_cell_occupancy.py:95-121) */
+        for (int r = 0; r < c->N / c->npr; r++) occ_insert(c, position_to_cell(&c->cells, c->root_pos + r * c->D), r);
+    } else {
+        for (int i = 0; i < c->N; i++) occ_insert(c, position_to_cell(&c->cells, c->pos + i * c->D), i);
+    }
     memset(&c->st, 0, sizeof(c->st));
     c->st.stream = stream;
     c->st.active = c->prog.initial_active;
     c->st.direction = c->prog.initial_direction;
     c->st.time_q = 0.0; c->st.time_r = 0.0;
     c->st.event_counter = 0;
-    c->st.active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
-    occ_remove(c, c->st.active_cell, c->st.active);
+    if (c->molecules) {
+        c->st.active_cell = position_to_cell(&c->cells, c->root_pos + (c->st.active / c->npr) * c->D);
+        occ_remove(c, c->st.active_cell, c->st.active / c->npr);
+    } else {
+        c->st.active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
+        occ_remove(c, c->st.active_cell, c->st.active);
+    }
     schedule_end_of_chain(c);
     c->st.pending_kind = ECMC_EVENT_NONE;
     c->started = 1;
@@ -1201,7 +1241,8 @@ static candidate veto_candidate(OrcChain *c) {
     int relative_cell = (0.0 + (w->mean_rate - 0.0) * u0 <= w->rate_a[e]) ? w->cell_a[e] : w->cell_b[e];
     cand.rate = c->bounds[(relative_cell * c->D + dir) * 2 + rate_index] * charge_factor;
     /* the active cell is recomputed from the position, cell_veto_event_handler.py:216 */
-    int active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
+    int active_cell = c->molecules ? position_to_cell(&c->cells, c->root_pos + (c->st.active / c->npr) * c->D)
+                                   : position_to_cell(&c->cells, c->pos + c->st.active * c->D);
     cand.target_cell = cells_translate(&c->cells, active_cell, relative_cell);
     double dt = rng_expovariate(u1, c->prog.beta) / (total_rate * c->prog.speed);
     otime now = {c->st.time_q, c->st.time_r};
@@ -1313,9 +1354,461 @@ static void occupancy_update(OrcChain *c, int new_active) {
 
 static int lt_candidate(const candidate *a, const candidate *b) { return time_lt(a->t, b->t); }
 
+/* ================================================================================================== */
+/* Molecules: composite objects in root-level cells (water, C4 of SURVEY.md 8d)                        */
+/* ================================================================================================== */
+/* Lifting.insert + get_active_identifier of the three schemes (lifting/lifting.py:49-91, inside_first_lifting.py:
+ * 39-54, outside_first_lifting.py:39-55, ratio_lifting.py:40-56). Draws come from the out-state's slot in call order. */
+typedef struct {
+    double negative[8];
+    int ids[8];
+    int n_negative;
+    double random_position, sum_positive;
+    int active_recorded;
+} olifting;
+static void lifting_reset(olifting *l) { memset(l, 0, sizeof(*l)); }
+static void lifting_insert(olifting *l, double rate, int id, int is_active, OrcChain *c, uint32_t *draw) {
+    if (rate > 0.0) {
+        l->sum_positive += rate;
+        if (is_active) {
+            l->active_recorded = 1;
+            double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), (*draw)++);
+            l->random_position += 0.0 + (rate - 0.0) * u; /* random.uniform(0.0, lifting_rate) */
+        } else if (!l->active_recorded) {
+            l->random_position += rate;
+        }
+    } else {
+        l->negative[l->n_negative] = -rate;
+        l->ids[l->n_negative++] = id;
+    }
+}
+static int lifting_get(olifting *l, int kind, OrcChain *c, uint32_t *draw) {
+    double position = l->random_position;
+    if (kind == ECMC_LIFTING_OUTSIDE_FIRST || kind == ECMC_LIFTING_RATIO) {
+        pysum total;
+        pysum_init(&total);
+        for (int i = 0; i < l->n_negative; i++) pysum_add(&total, l->negative[i]);
+        double sum_negative = l->n_negative ? pysum_result(&total) : 0.0;
+        if (kind == ECMC_LIFTING_OUTSIDE_FIRST) {
+            position = sum_negative - l->random_position;
+        } else {
+            double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), (*draw)++);
+            position = 0.0 + (sum_negative - 0.0) * u;
+        }
+    }
+    double summed = 0.0;
+    for (int i = 0; i < l->n_negative; i++) {
+        summed += l->negative[i];
+        if (position <= summed) return l->ids[i];
+    }
+    return l->n_negative ? l->ids[l->n_negative - 1] : -1;
+}
+
+/* TwoCompositeObjectSummedBoundingPotentialEventHandler.send_event_time
+ * (two_composite_object_summed_bounding_potential_event_handler.py:119-156): minimum over the target leaf units (sorted
+ * by identifier, abstracts/composite_objects.py:63-83) of the bounding potential's displacement, one expovariate each */
+static candidate composite_pair_candidate(OrcChain *c, int target_root) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_PAIR; cand.target = target_root; cand.target_cell = -1; cand.rate = 0.0;
+    const double *pa = c->pos + c->st.active * c->D;
+    double best = ORC_INF;
+    for (int k = 0; k < c->npr; k++) {
+        int t = target_root * c->npr + k;
+        double sep[ECMC_MAX_DIM] = {0, 0, 0};
+        separation_vector(pa, c->pos + t * c->D, c->D, c->L, sep);
+        double c1 = c->prog.pair_use_charge ? c->charge[c->st.active] : 1.0;
+        double c2 = c->prog.pair_use_charge ? c->charge[t] : 1.0;
+        double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter,
+                              ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target_root), (uint32_t)k);
+        double dt = pot_displacement(&c->pair_bound, c->st.direction, c->prog.speed, sep, c->D, c1, c2,
+                                     rng_expovariate(u, c->prog.beta));
+        if (dt < best) best = dt; /* min() keeps the first of equal values */
+    }
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, best);
+    return cand;
+}
+
+/* A two-leaf factor between the active leaf and a leaf of another object (non-local factor type map entry), handled by
+ * a TwoLeafUnitEventHandler (two_leaf_unit_event_handler.py:105-138) */
+static candidate factor_pair_candidate(OrcChain *c, int target) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_FACTOR_PAIR; cand.target = target; cand.target_cell = -1; cand.rate = 0.0;
+    double sep[ECMC_MAX_DIM] = {0, 0, 0};
+    separation_vector(c->pos + c->st.active * c->D, c->pos + target * c->D, c->D, c->L, sep);
+    double dU = 0.0;
+    if (pot_needs_potential_change(c->inter_pot.kind)) {
+        double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
+        dU = rng_expovariate(u, c->prog.beta);
+    }
+    double dt = pot_displacement(&c->inter_pot, c->st.direction, c->prog.speed, sep, c->D, 1.0, 1.0, dU);
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, dt);
+    return cand;
+}
+
+/* the derivative triple of the bending factor for the three units of the active object, the active leaf optionally
+ * displaced (event_handler_with_bounding_potential.py:282-332; _get_separations of
+ * fixed_separations_event_handler_with_piecewise_constant_bounding_potential.py:189-210) */
+static void bending_triple(OrcChain *c, double advance, double out[3]) {
+    int root = c->st.active / c->npr;
+    double positions[3][ECMC_MAX_DIM];
+    for (int i = 0; i < 3; i++) {
+        int leaf = root * c->npr + c->prog.bending_children[i];
+        for (int d = 0; d < c->D; d++) positions[i][d] = c->pos[leaf * c->D + d];
+        if (leaf == c->st.active && advance != 0.0)
+            for (int d = 0; d < c->D; d++) {
+                double v = d == c->st.direction ? c->prog.speed : 0.0;
+                positions[i][d] = correct_position_entry(positions[i][d] + v * advance, c->L);
+            }
+    }
+    const int32_t *s = c->prog.bending_separations;
+    double s1[ECMC_MAX_DIM] = {0, 0, 0}, s2[ECMC_MAX_DIM] = {0, 0, 0};
+    separation_vector(positions[s[0]], positions[s[1]], c->D, c->L, s1);
+    separation_vector(positions[s[2]], positions[s[3]], c->D, c->L, s2);
+    bending_derivative(c->bending_pot.p0, c->bending_pot.p1, c->st.direction, c->prog.speed, s1, s2, c->D, out);
+}
+static int bending_active_index(const OrcChain *c) {
+    int child = c->st.active % c->npr;
+    for (int i = 0; i < 3; i++) if (c->prog.bending_children[i] == child) return i;
+    return -1;
+}
+/* FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential.send_event_time (:113-141): cand.rate carries the
+ * bounding event rate, or a negative number for None */
+static candidate bending_candidate(OrcChain *c) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_BENDING; cand.target = -1; cand.target_cell = -1;
+    int index = bending_active_index(c);
+    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_BENDING_TIME, 0), 0);
+    double potential_change = rng_expovariate(u, c->prog.beta);
+    double one[3], two[3];
+    bending_triple(c, 0.0, one);
+    bending_triple(c, c->prog.bending_max_displacement, two);
+    double constant = (one[index] > two[index] ? one[index] : two[index]) + c->prog.bending_offset; /* max(a, b) */
+    double dt;
+    if (constant <= 0.0) { cand.rate = -1.0; dt = c->prog.bending_max_displacement; }
+    else if (potential_change / constant < c->prog.bending_max_displacement) { cand.rate = constant; dt = potential_change / constant; }
+    else { cand.rate = -1.0; dt = c->prog.bending_max_displacement; }
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, dt);
+    return cand;
+}
+
+/* CellBoundaryEventHandler.send_event_time for the root unit (cell_level = 1): it moves with velocity * weight */
+static candidate root_boundary_candidate(OrcChain *c, double *boundary_out) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_CELL_BOUNDARY; cand.target = -1; cand.rate = 0.0;
+    int dir = c->st.direction;
+    const double *pr = c->root_pos + (c->st.active / c->npr) * c->D;
+    int cell = position_to_cell(&c->cells, pr);
+    int neighbor = neighbor_cell_positive(&c->cells, cell, dir);
+    double neighbor_boundary = c->cells.cell_min[neighbor * c->D + dir];
+    double separation = neighbor_boundary - pr[dir];
+    if (separation < 0.0) separation = separation + c->L;
+    double velocity = c->prog.speed * (1.0 / c->npr);
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, separation / velocity);
+    cand.target_cell = neighbor;
+    *boundary_out = neighbor_boundary;
+    return cand;
+}
+
+/* EventHandlerWithBoundingPotential._fill_lifting (event_handler_with_bounding_potential.py:170-220) followed by the
+ * lifting scheme: returns the new active leaf. target_derivatives holds -derivative(active, target_k) on entry. */
+static int composite_lifting(OrcChain *c, int target_root, double active_derivative, double *target_derivatives,
+                             uint32_t *draw) {
+    int local_root = c->st.active / c->npr;
+    double local_derivatives[4] = {0, 0, 0, 0};
+    for (int i = 0; i < c->npr; i++) {
+        int local = local_root * c->npr + i;
+        if (local == c->st.active) { local_derivatives[i] = active_derivative; continue; }
+        for (int j = 0; j < c->npr; j++) {
+            int target = target_root * c->npr + j;
+            double sep[ECMC_MAX_DIM] = {0, 0, 0};
+            separation_vector(c->pos + local * c->D, c->pos + target * c->D, c->D, c->L, sep);
+            double c1 = c->prog.pair_use_charge ? c->charge[local] : 1.0;
+            double c2 = c->prog.pair_use_charge ? c->charge[target] : 1.0;
+            double pairwise = pot_derivative(&c->pair_pot, c->st.direction, c->prog.speed, sep, c->D, c1, c2);
+            local_derivatives[i] += pairwise;
+            target_derivatives[j] -= pairwise;
+        }
+    }
+    olifting lift;
+    lifting_reset(&lift);
+    for (int pass = 0; pass < 2; pass++) {
+        int local_now = (local_root < target_root) == (pass == 0);
+        for (int i = 0; i < c->npr; i++) {
+            if (local_now)
+                lifting_insert(&lift, local_derivatives[i], local_root * c->npr + i, local_root * c->npr + i == c->st.active, c, draw);
+            else
+                lifting_insert(&lift, target_derivatives[i], target_root * c->npr + i, 0, c, draw);
+        }
+    }
+    return lifting_get(&lift, c->prog.composite_lifting, c, draw);
+}
+
+/* SingleActiveCellOccupancy.update for cell_level = 1: the active unit on the cell level is the root */
+static void molecule_occupancy_update(OrcChain *c, int new_active) {
+    int old_root = c->st.active / c->npr, new_root = new_active / c->npr;
+    if (new_root != old_root) {
+        occ_insert(c, c->st.active_cell, old_root);
+        c->st.active_cell = position_to_cell(&c->cells, c->root_pos + new_root * c->D);
+        occ_remove(c, c->st.active_cell, new_root);
+    } else {
+        c->st.active_cell = position_to_cell(&c->cells, c->root_pos + new_root * c->D);
+    }
+    c->st.active = new_active;
+}
+
+static int is_leaf_kind(int kind) {
+    return kind == ECMC_EVENT_PAIR || kind == ECMC_EVENT_CELL_BOUNDING || kind == ECMC_EVENT_BOND ||
+           kind == ECMC_EVENT_FACTOR_PAIR;
+}
+
+static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
+    candidate best;
+    int n_cand = 0;
+    double boundary_position = 0.0;
+    best.kind = ECMC_EVENT_NONE; best.t.q = ORC_INF; best.t.r = ORC_INF; best.target = -1; best.target_cell = -1;
+    best.rate = 0.0;
+    int was_pending = c->st.pending_kind != ECMC_EVENT_NONE;
+    int npr = c->npr, D = c->D, dir = c->st.direction;
+    int active_root = c->st.active / npr, active_child = c->st.active % npr;
+    candidate factor_best; /* the earliest leaf-level factor candidate of this iteration (computed or kept) */
+    int factor_from_kept = 0, best_from_kept = 0;
+    factor_best.kind = ECMC_EVENT_NONE; factor_best.t.q = ORC_INF; factor_best.t.r = ORC_INF; factor_best.target = -1;
+    factor_best.target_cell = -1; factor_best.rate = 0.0;
+    if (was_pending) {
+        best.kind = c->st.pending_kind;
+        best.t.q = c->st.pending_q; best.t.r = c->st.pending_r;
+        best.rate = c->st.pending_rate;
+        if (is_leaf_kind(best.kind)) best.target = c->st.pending_target; else best.target_cell = c->st.pending_target;
+        if (best.kind == ECMC_EVENT_CELL_BOUNDARY) boundary_position = c->cells.cell_min[best.target_cell * D + dir];
+    } else {
+#define CONSIDER(cand) do { if (!isinf((cand).t.q)) { n_cand++; if (lt_candidate(&(cand), &best)) { best = (cand); best_from_kept = 0; } } } while (0)
+        int nearby[343];
+        int nn = nearby_cells(&c->cells, c->st.active_cell, nearby);
+        if (c->prog.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING) {
+            for (int i = 0; i < nn; i++) {
+                int t = c->occ[nearby[i]];
+                if (t < 0) continue;
+                candidate cand = composite_pair_candidate(c, t);
+                CONSIDER(cand);
+            }
+            for (int s = 0; s < c->n_surplus; s++) {
+                candidate cand = composite_pair_candidate(c, c->surplus[s]);
+                CONSIDER(cand);
+            }
+        }
+        /* the leaf-level factors: recomputed, unless a cell-boundary event left their handlers running */
+        if (c->st.kept_kind != ECMC_EVENT_NONE) {
+            if (c->st.kept_kind > 0) {
+                factor_best.kind = c->st.kept_kind;
+                factor_best.t.q = c->st.kept_q; factor_best.t.r = c->st.kept_r;
+                factor_best.rate = c->st.kept_rate;
+                factor_best.target = c->st.kept_target;
+                factor_from_kept = 1;
+            }
+        } else {
+#define CONSIDER_FACTOR(cand) do { if (!isinf((cand).t.q)) { n_cand++; if (lt_candidate(&(cand), &factor_best)) factor_best = (cand); } } while (0)
+            for (int b = 0; b < c->prog.n_bonds; b++) {
+                int partner = -1;
+                if (c->prog.bonds[b][0] == active_child) partner = c->prog.bonds[b][1];
+                else if (c->prog.bonds[b][1] == active_child) partner = c->prog.bonds[b][0];
+                if (partner < 0) continue;
+                candidate cand = bond_candidate(c, active_root * npr + partner);
+                CONSIDER_FACTOR(cand);
+            }
+            for (int f = 0; f < c->prog.n_inter_factors; f++) {
+                if (c->prog.inter_factors[f][0] != active_child) continue;
+                for (int r = 0; r < c->N / npr; r++) {
+                    if (r == active_root) continue;
+                    candidate cand = factor_pair_candidate(c, r * npr + c->prog.inter_factors[f][1]);
+                    CONSIDER_FACTOR(cand);
+                }
+            }
+            if (c->prog.bending_enabled && bending_active_index(c) >= 0) {
+                candidate cand = bending_candidate(c);
+                CONSIDER_FACTOR(cand);
+            }
+#undef CONSIDER_FACTOR
+        }
+        if (lt_candidate(&factor_best, &best)) { best = factor_best; best_from_kept = factor_from_kept; }
+        if (c->prog.veto_enabled == ECMC_FAR_CELL_VETO) {
+            candidate cand = veto_candidate(c);
+            CONSIDER(cand);
+        }
+        {
+            candidate cand = root_boundary_candidate(c, &boundary_position);
+            n_cand++;
+            if (lt_candidate(&cand, &best)) { best = cand; best_from_kept = 0; }
+        }
+#undef CONSIDER
+    }
+    {
+        candidate interaction = best;
+        candidate cand;
+        cand.kind = ECMC_EVENT_END_OF_CHAIN; cand.target = c->st.eoc_next_active; cand.target_cell = -1; cand.rate = 0.0;
+        cand.t.q = c->st.eoc_q; cand.t.r = c->st.eoc_r;
+        n_cand++;
+        if (lt_candidate(&cand, &best)) best = cand;
+        if (!time_lt(best.t, until)) {
+            c->st.pending_kind = interaction.kind;
+            c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
+            c->st.pending_rate = interaction.rate;
+            c->st.pending_target = is_leaf_kind(interaction.kind) ? interaction.target : interaction.target_cell;
+            if (!was_pending) {
+                c->st.pending_position = c->pos[c->st.active * D + dir];
+                c->st.pending_root_position = c->root_pos[active_root * D + dir];
+                c->st.pending_stamp_q = c->st.time_q;
+                c->st.pending_stamp_r = c->st.time_r;
+                if (best_from_kept) { /* the kept factor handler's in-state is older still */
+                    c->st.pending_position = c->st.kept_position;
+                    c->st.pending_root_position = c->st.kept_root_position;
+                    c->st.pending_stamp_q = c->st.kept_stamp_q;
+                    c->st.pending_stamp_r = c->st.kept_stamp_r;
+                }
+            }
+            return 0;
+        }
+    }
+    c->st.pending_kind = ECMC_EVENT_NONE;
+    if (was_pending && best.kind != ECMC_EVENT_END_OF_CHAIN) {
+        c->pos[c->st.active * D + dir] = c->st.pending_position;
+        c->root_pos[active_root * D + dir] = c->st.pending_root_position;
+        c->st.time_q = c->st.pending_stamp_q;
+        c->st.time_r = c->st.pending_stamp_r;
+    } else if (best_from_kept && best.kind != ECMC_EVENT_END_OF_CHAIN) {
+        /* the kept handler computes its out-state from the in-state it received before the cell-boundary event(s) */
+        c->pos[c->st.active * D + dir] = c->st.kept_position;
+        c->root_pos[active_root * D + dir] = c->st.kept_root_position;
+        c->st.time_q = c->st.kept_stamp_q;
+        c->st.time_r = c->st.kept_stamp_r;
+    }
+    /* which handlers survive this event: a cell-boundary event leaves the leaf-level factors running */
+    if (best.kind == ECMC_EVENT_CELL_BOUNDARY && c->prog.boundary_keeps_factors) {
+        if (c->st.kept_kind == ECMC_EVENT_NONE && !was_pending) {
+            c->st.kept_kind = factor_best.kind == ECMC_EVENT_NONE ? -1 : factor_best.kind;
+            c->st.kept_target = factor_best.target;
+            c->st.kept_q = factor_best.t.q; c->st.kept_r = factor_best.t.r;
+            c->st.kept_rate = factor_best.rate;
+            c->st.kept_position = c->pos[c->st.active * D + dir];
+            c->st.kept_root_position = c->root_pos[active_root * D + dir];
+            c->st.kept_stamp_q = c->st.time_q; c->st.kept_stamp_r = c->st.time_r;
+        }
+    } else {
+        c->st.kept_kind = ECMC_EVENT_NONE;
+    }
+
+    int old_active = c->st.active, new_active = old_active, accepted = 0, rec_target = -1;
+    uint32_t draw = 0;
+    time_slice_active(c, best.t);
+    const double *pa = c->pos + old_active * D;
+    switch (best.kind) {
+    case ECMC_EVENT_PAIR:
+    case ECMC_EVENT_CELL_VETO: {
+        /* two_composite_object_summed_bounding_potential_event_handler.py:158-202 /
+         * composite_object_cell_veto_event_handler.py:110-162 (+ mediator.py:265-292 for the occupant of the cell) */
+        int veto = best.kind == ECMC_EVENT_CELL_VETO;
+        int target_root = veto ? c->occ[best.target_cell] : best.target;
+        rec_target = target_root;
+        if (veto) c->stats.veto_events++; else c->stats.pair_events++;
+        if (target_root < 0) break;
+        double bounding_rate = veto ? best.rate : 0.0;
+        double factor_derivative = 0.0;
+        double target_derivatives[4] = {0, 0, 0, 0};
+        const opotential *real = veto ? &c->veto_pot : &c->pair_pot;
+        int use_charge = veto ? c->prog.veto_use_charge : c->prog.pair_use_charge;
+        for (int k = 0; k < npr; k++) {
+            int t = target_root * npr + k;
+            double sep[ECMC_MAX_DIM] = {0, 0, 0};
+            separation_vector(pa, c->pos + t * D, D, c->L, sep);
+            double c1 = use_charge ? c->charge[old_active] : 1.0, c2 = use_charge ? c->charge[t] : 1.0;
+            if (!veto) {
+                double b = pot_derivative(&c->pair_bound, dir, c->prog.speed, sep, D, c1, c2);
+                bounding_rate += b > 0.0 ? b : 0.0; /* max(0.0, b) */
+            }
+            double pairwise = pot_derivative(real, dir, c->prog.speed, sep, D, c1, c2);
+            factor_derivative += pairwise;
+            target_derivatives[k] -= pairwise;
+        }
+        double event_rate = factor_derivative > 0.0 ? factor_derivative : 0.0; /* max(0.0, factor_derivative) */
+        if (bounding_rate < event_rate) c->stats.bound_violations++;
+        double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+        if (event_rate <= 0.0 + (bounding_rate - 0.0) * u) break;
+        /* the summed-bounding handler passes the clipped event rate, the cell-veto handler the factor derivative */
+        new_active = composite_lifting(c, target_root, veto ? factor_derivative : event_rate, target_derivatives, &draw);
+        accepted = 1;
+        if (veto) c->stats.veto_accepted++;
+        break;
+    }
+    case ECMC_EVENT_BOND:
+    case ECMC_EVENT_FACTOR_PAIR:
+        rec_target = best.target;
+        accepted = 1;
+        new_active = best.target;
+        if (best.kind == ECMC_EVENT_BOND) c->stats.bond_events++; else c->stats.factor_pair_events++;
+        break;
+    case ECMC_EVENT_BENDING: {
+        /* fixed_separations_event_handler_with_piecewise_constant_bounding_potential.py:143-187 */
+        c->stats.bond_events++;
+        if (best.rate < 0.0) break; /* bounding event rate None */
+        double derivatives[3];
+        bending_triple(c, 0.0, derivatives);
+        int index = bending_active_index(c);
+        if (derivatives[index] > 0) {
+            if (best.rate < derivatives[index]) c->stats.bound_violations++;
+            double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+            if (0.0 + (best.rate - 0.0) * u < derivatives[index]) {
+                olifting lift;
+                lifting_reset(&lift);
+                for (int i = 0; i < 3; i++)
+                    lifting_insert(&lift, derivatives[i], active_root * npr + c->prog.bending_children[i], i == index, c, &draw);
+                new_active = lifting_get(&lift, c->prog.bending_lifting, c, &draw);
+                accepted = 1;
+            }
+        }
+        break;
+    }
+    case ECMC_EVENT_CELL_BOUNDARY:
+        c->root_pos[active_root * D + dir] = boundary_position;
+        c->stats.boundary_events++;
+        break;
+    case ECMC_EVENT_END_OF_CHAIN:
+        new_active = c->st.eoc_next_active;
+        rec_target = new_active;
+        accepted = 1;
+        c->stats.end_of_chain_events++;
+        break;
+    default: break;
+    }
+    if (new_active < 0) { c->stats.capacity_errors++; new_active = old_active; }
+    if (rec) {
+        memset(rec, 0, sizeof(*rec));
+        rec->kind = best.kind;
+        rec->target = rec_target;
+        rec->target_cell = best.target_cell;
+        rec->accepted = best.kind == ECMC_EVENT_END_OF_CHAIN ? 1 : (new_active != old_active);
+        rec->n_candidates = n_cand;
+        rec->time_q = best.t.q; rec->time_r = best.t.r;
+        for (int d = 0; d < D; d++) rec->active_pos[d] = c->pos[old_active * D + d];
+    }
+    (void)accepted;
+    c->st.event_counter++;
+    c->stats.events++;
+    c->stats.candidates += (uint64_t)n_cand;
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN) c->st.direction = (c->st.direction + 1) % D;
+    molecule_occupancy_update(c, new_active);
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN) schedule_end_of_chain(c);
+    if (rec) { rec->new_active = c->st.active; rec->new_direction = c->st.direction; }
+    return 1;
+}
+
+
 /* One iteration of SingleProcessMediator.run (single_process_mediator.py:91-156) restricted to device
  * events. Returns 0 if the next event time is not < until (nothing committed, candidate kept pending). */
 static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
+    if (c->molecules) return molecule_step(c, until, rec);
     candidate best;
     int n_cand = 0;
     double boundary_position = 0.0;

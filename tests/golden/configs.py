@@ -428,3 +428,70 @@ def patch_composite_start(composites):
         for cls, original in saved:
             cls.fill_root_node = original
     return restore
+
+
+# ------------------------------------------------------------------------------------------------------
+# C4 of SURVEY.md 8(d): SPC/Fw-like water, config_files/2018_JCP_149_064113/water/coulomb_cell_veto_lj_inverted.ini
+# ------------------------------------------------------------------------------------------------------
+def water_ini(ref_root, n_molecules=32, end_of_run_time=1.0e9, number_trials=1000, sampling_interval=None,
+              output="/dev/null", cells_per_side=None, neighbor_layers=None, system_length=None):
+    """The shipped water configuration (Coulomb through composite-object handlers with cell veto, Lennard-Jones
+    inverted, harmonic bonds, bending with ratio lifting) for n_molecules molecules; only the size of the system,
+    the run length, the number of estimator trials and the output change."""
+    import os
+    text = shipped_ini(ref_root, "2018_JCP_149_064113", "water", "coulomb_cell_veto_lj_inverted.ini")
+    text = text.replace("filename = config_files/", "filename = " + os.path.join(ref_root, "jellyfysh", "config_files") + "/")
+    text = text.replace("number_of_root_nodes = 2", f"number_of_root_nodes = {n_molecules}")
+    # the shipped file is sized for two molecules: one handler per possible partner molecule
+    for section in ("[CoulombNearby]", "[CoulombSurplus]", "[LennardJones]"):
+        head, tail = text.split(section)
+        tail = tail.replace("number_event_handlers = 1", f"number_event_handlers = {max(n_molecules - 1, 1)}", 1)
+        text = head + section + tail
+    text = text.replace("end_of_run_time = 500000", f"end_of_run_time = {end_of_run_time!r}")
+    text = text.replace("number_trials = 1000", f"number_trials = {number_trials}")
+    text = text.replace("output/2018_JCP_149_064113/water/SamplesOfOOSeparation_CoulombCellVeto_LJInverted.dat", output)
+    if cells_per_side is not None:
+        text = text.replace("cells_per_side = 6, 6, 6", "cells_per_side = " + ", ".join(str(c) for c in cells_per_side))
+    if neighbor_layers is not None:
+        text = text.replace("neighbor_layers = 2", f"neighbor_layers = {neighbor_layers}")
+    if system_length is not None:
+        text = text.replace("system_length = 10", f"system_length = {system_length!r}")
+    if sampling_interval is None:
+        text = text.replace("    sampling (no_in_state_tagger),\n", "")
+        text = text.replace(", sampling", "")
+        start, rest = text.split("[Sampling]")
+        rest = rest.split("[EndOfChain]", 1)[1]
+        text = start + "[EndOfChain]" + rest
+        text = text.replace("output_handlers = oxygen_oxygen_separation_output_handler\n", "")
+        text = text.split("[OxygenOxygenSeparationOutputHandler]")[0]
+    else:
+        text = text.replace("sampling_interval = 2.6789", f"sampling_interval = {sampling_interval!r}")
+    return text
+
+
+def water_start(n_molecules, system_length, seed=1000, bond_length=1.012, bond_angle=1.9764, jitter=0.3):
+    """(roots[n][3], leaves[n][3][3]) of water molecules (H, O, H; the root is the geometric centre, as
+    WaterRandomNodeCreator builds them, water_random_node_creator.py:69-118) on a jittered cubic lattice with random
+    orientations, so that no two molecules start on top of each other."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(n_molecules ** (1.0 / 3.0)))
+    grid = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)
+    grid = grid[rng.permutation(len(grid))[:n_molecules]]
+    roots = np.empty((n_molecules, 3))
+    leaves = np.empty((n_molecules, 3, 3))
+    for m in range(n_molecules):
+        centre = (grid[m] + 0.5) * (system_length / side) + rng.uniform(-jitter, jitter, size=3)
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        other = rng.normal(size=3)
+        other -= other.dot(axis) * axis
+        other /= np.linalg.norm(other)
+        oh_one = bond_length * (np.cos(bond_angle / 2) * axis + np.sin(bond_angle / 2) * other)
+        oh_two = bond_length * (np.cos(bond_angle / 2) * axis - np.sin(bond_angle / 2) * other)
+        oxygen = centre - (oh_one + oh_two) / 3.0
+        roots[m] = centre % system_length
+        leaves[m, 0] = (oxygen + oh_one) % system_length
+        leaves[m, 1] = oxygen % system_length
+        leaves[m, 2] = (oxygen + oh_two) % system_length
+    return roots, leaves

@@ -306,8 +306,9 @@ def chain_trace(name, ini, positions, seed, stream, n_events, snapshot_every, me
     finally:
         run.close()
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    kinds = np.bincount(records["kind"], minlength=7)
-    print(f"{name}.npz: {len(records)} events, kinds pair/veto/boundary/eoc/cell-bounding/bond = {kinds[1:].tolist()}, "
+    kinds = np.bincount(records["kind"], minlength=9)
+    print(f"{name}.npz: {len(records)} events, kinds pair/veto/boundary/eoc/cell-bounding/bond/factor-pair/bending = "
+          f"{kinds[1:].tolist()}, "
           f"accepted = {int(records['accepted'].sum())}, snapshots = {len(run.snapshots)}, "
           f"max surplus = {int(out['snap_n_surplus'].max())}")
 
@@ -374,8 +375,40 @@ def dipole_traces():
                           hard_dipole=[0.952380952380952, 1.047619047619048], max_occupants=6))
 
 
+def _composite_veto_tables(run):
+    """Tables of the CompositeObjectCellVetoEventHandler (same layout as the leaf-unit handler's)."""
+    return _tables_of(run)
+
+
+def water_traces():
+    # C4: the shipped water/coulomb_cell_veto_lj_inverted.ini with 32 molecules (SURVEY 8d), 200 estimator trials
+    n = 32
+    roots, leaves = configs.water_start(n, 10.0, seed=4)
+    chain_trace("trace_water", configs.water_ini(REF, n_molecules=n, number_trials=200), None, seed=23, stream=7,
+                n_events=4000, snapshot_every=500, max_occupants=1, composites=(roots, leaves),
+                charges=np.tile([0.41, -0.82, 0.41], n),
+                meta=dict(n=3 * n, cells_per_side=[6, 6, 6], neighbor_layers=2, system_length=10.0, beta=1.679,
+                          chain_time=2.12345, nodes_per_root=3, mic=[332.0, 3.45, 6, 2], ipcb=[531.2],
+                          lj=[0.6217012, 3.165492], harmonic=[529.581, 1.012, 2.0], bending=[75.9, 1.9764],
+                          bending_offset=10.0, bending_max_displacement=0.112321434, initial_active=1))
+    # dense and small: 12 molecules in a box of 6 with 4^3 cells and one neighbour layer -> composite pair events,
+    # surplus molecules, accepted cell vetoes with lifting into either molecule
+    n = 12
+    roots, leaves = configs.water_start(n, 6.0, seed=5, jitter=0.2)
+    chain_trace("trace_water_dense", configs.water_ini(REF, n_molecules=n, number_trials=200, system_length=6.0,
+                                                       cells_per_side=[4, 4, 4], neighbor_layers=1), None,
+                seed=24, stream=8, n_events=4000, snapshot_every=500, max_occupants=1, composites=(roots, leaves),
+                charges=np.tile([0.41, -0.82, 0.41], n),
+                meta=dict(n=3 * n, cells_per_side=[4, 4, 4], neighbor_layers=1, system_length=6.0, beta=1.679,
+                          chain_time=2.12345, nodes_per_root=3, mic=[332.0, 3.45, 6, 2], ipcb=[531.2],
+                          lj=[0.6217012, 3.165492], harmonic=[529.581, 1.012, 2.0], bending=[75.9, 1.9764],
+                          bending_offset=10.0, bending_max_displacement=0.112321434, initial_active=1))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles"]
+    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "water"]
+    if "water" in which:
+        water_traces()
     if "dipoles" in which:
         dipole_traces()
     if "cell_bounding" in which:

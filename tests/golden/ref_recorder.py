@@ -53,7 +53,7 @@ def stream_double(seed, stream, event, slot, index):
 
 
 SLOT_PAIR_TIME, SLOT_VETO_TIME, SLOT_VETO_CHOICE, SLOT_CONFIRM, SLOT_END_OF_CHAIN, SLOT_LIFTING = 1, 2, 3, 4, 5, 6
-SLOT_FACTOR_TIME = 7
+SLOT_FACTOR_TIME, SLOT_BENDING_TIME = 7, 8
 SLOT_INIT = 15  # initial random positions (host side only)
 
 
@@ -99,7 +99,7 @@ class SlotRandom(random.Random):
 
 
 EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDARY, EVENT_END_OF_CHAIN, EVENT_CELL_BOUNDING = 1, 2, 3, 4, 5
-EVENT_BOND = 6
+EVENT_BOND, EVENT_FACTOR_PAIR, EVENT_BENDING = 6, 7, 8
 HOST_EVENT = 0
 
 RECORD_DTYPE = np.dtype([("kind", "<i4"), ("target", "<i4"), ("target_cell", "<i4"), ("accepted", "<i4"),
@@ -197,18 +197,36 @@ class ReferenceRun:
             return EVENT_CELL_BOUNDARY
         if "EndOfChainEventHandler" in names:
             return EVENT_END_OF_CHAIN
+        if "FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential" in names:
+            return EVENT_BENDING
+        if "TwoCompositeObjectSummedBoundingPotentialEventHandler" in names:
+            return EVENT_PAIR
         if names & {"TwoLeafUnitEventHandler", "TwoLeafUnitBoundingPotentialEventHandler"}:
-            return EVENT_BOND if id(handler) in self._factor_map_handlers() else EVENT_PAIR
+            local = self._factor_map_handlers().get(id(handler))
+            return EVENT_PAIR if local is None else (EVENT_BOND if local else EVENT_FACTOR_PAIR)
         return HOST_EVENT
 
     def _factor_map_handlers(self):
-        """ids of the handlers that belong to a FactorTypeMapInStateTagger (intramolecular factors)."""
+        """id -> is the factor local (intramolecular)? for the handlers of every FactorTypeMapInStateTagger."""
         if getattr(self, "_factor_ids", None) is None:
-            self._factor_ids = set()
+            self._factor_ids = {}
             for tagger in self.mediator._activator._taggers:
                 if "FactorTypeMapInStateTagger" in {cls.__name__ for cls in type(tagger).__mro__}:
-                    self._factor_ids |= {id(h) for h in tagger.get_event_handlers()}
+                    local = bool(getattr(tagger._factor_type_map, "_local", False))
+                    self._factor_ids.update({id(h): local for h in tagger.get_event_handlers()})
         return self._factor_ids
+
+    def _target_root_of(self, in_state):
+        """The root of the composite object in the in-state that holds no active leaf unit."""
+        from jellyfysh.base.node import yield_leaf_nodes
+        for cnode in in_state:
+            if all(leaf.value.velocity is None for leaf in yield_leaf_nodes(cnode)):
+                return cnode.value.identifier[0]
+        raise RuntimeError("composite in-state without target")
+
+    @staticmethod
+    def _is_composite_pair(handler):
+        return "TwoCompositeObjectSummedBoundingPotentialEventHandler" in {c.__name__ for c in type(handler).__mro__}
 
     def _target_of_pair(self, in_state):
         from jellyfysh.base.node import yield_leaf_nodes
@@ -228,10 +246,14 @@ class ReferenceRun:
             orig_time, orig_out = h.send_event_time, h.send_out_state
 
             def send_event_time(*args, _h=h, _kind=kind, _orig=orig_time):
-                if _kind in (EVENT_PAIR, EVENT_CELL_BOUNDING):
+                if _kind == EVENT_PAIR and run._is_composite_pair(_h):
+                    run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_root_of(args[0])))
+                elif _kind in (EVENT_PAIR, EVENT_CELL_BOUNDING):
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_of_pair(args[0])))
-                elif _kind == EVENT_BOND:
+                elif _kind in (EVENT_BOND, EVENT_FACTOR_PAIR):
                     run.rng.set_context(run.events, make_slot(SLOT_FACTOR_TIME, run._target_of_pair(args[0])))
+                elif _kind == EVENT_BENDING:
+                    run.rng.set_context(run.events, make_slot(SLOT_BENDING_TIME))
                 elif _kind == EVENT_CELL_VETO:
                     run.rng.set_context(run.events, make_slot(SLOT_VETO_TIME), make_slot(SLOT_VETO_CHOICE))
                 elif _kind == EVENT_END_OF_CHAIN:
@@ -244,7 +266,8 @@ class ReferenceRun:
                     run.rng.clear_context()
 
             def send_out_state(*args, _h=h, _kind=kind, _orig=orig_out):
-                if _kind in (EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDING):
+                if _kind in (EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDING, EVENT_BENDING):
+                    # confirmation, then the draws of the lifting scheme, in call order
                     run.rng.set_context(run.events, make_slot(SLOT_CONFIRM))
                 else:
                     run.rng.clear_context()
@@ -327,7 +350,9 @@ class ReferenceRun:
         rec["time_q"] = winner._event_time.quotient
         rec["time_r"] = winner._event_time.remainder
         old_active = self._active()[0] if kind != EVENT_END_OF_CHAIN or self.events >= 0 else -1
-        if kind in (EVENT_PAIR, EVENT_BOND):
+        if kind == EVENT_PAIR and self._is_composite_pair(winner):
+            rec["target"] = winner._target_leaf_units[0].identifier[0]  # the target composite object (root)
+        elif kind in (EVENT_PAIR, EVENT_BOND, EVENT_FACTOR_PAIR):
             rec["target"] = [self.leaf_id(u.identifier) for u in winner._leaf_units if u.velocity is None][0]
         elif kind == EVENT_CELL_BOUNDING:
             rec["target"] = [u.identifier[0] for u in winner._leaf_units if u.velocity is None][0]
@@ -353,7 +378,9 @@ class ReferenceRun:
         rec["accepted"] = int(new_active != old_active or kind == EVENT_END_OF_CHAIN)
         if kind == EVENT_CELL_BOUNDARY:
             cells = self._cells()
-            rec["target_cell"] = self._cell_index(cells.position_to_cell(pos))
+            cell_level = self.mediator._activator._internal_states[0].cell_level
+            on_cell_level = sh._physical_state.get(self._identifier_of(old_active)[:cell_level]).value.position
+            rec["target_cell"] = self._cell_index(cells.position_to_cell(on_cell_level))
         for d in range(self.setting.dimension):
             rec["active_pos"][d] = pos[d]
         self.records.append(rec.copy())

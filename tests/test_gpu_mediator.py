@@ -223,12 +223,13 @@ def test_hard_disk_dipoles_polarization_statistics(tmp_path):
     g = tu.load_trace("trace_hard_disk_dipoles")
     n_roots = len(g["roots0"])
     composites = (g["roots0"], g["positions0"].reshape(n_roots, 2, -1))
-    # the polarization is a slow collective variable: sample every 500.5 time units (the shipped file: 10.01) over
-    # 6 x 10^4 time units per chain, about 1.2 x 10^6 events each
-    chains, end, interval = 256, 60000.0, 500.5
+    # the polarization is a slow collective variable (relaxation time ~3 x 10^4 time units measured here: the distance
+    # to the reference histogram falls from 0.46 over 1.5 x 10^3 time units to 0.10 over 6 x 10^4): sample every 3003
+    # time units (the shipped file: 10.01) over 3 x 10^5 time units per chain, about 6 x 10^6 events each
+    chains, end, interval = 256, 300300.0, 3003.0
     ini = _dipole_ini(tmp_path, chains, end, sampling=True).replace("sampling_interval = 10.01",
                                                                     "sampling_interval = %r" % interval)
-    assert "sampling_interval = 500.5" in ini
+    assert "sampling_interval = 3003.0" in ini
     mediator, setting = build_reference_graph(ini, composites=composites)
     try:
         with pytest.raises(EndOfRun):

@@ -124,6 +124,40 @@ def test_composite_chain_replay_bit_exact(oracle, name):
     assert stats["capacity_errors"] == 0 and stats["bond_events"] > 500 and stats["pair_events"] > 4000
 
 
+@pytest.mark.parametrize("name", tu.WATER_TRACES)
+def test_water_chain_replay_bit_exact(oracle, name):
+    """C4, the shipped water/coulomb_cell_veto_lj_inverted.ini: composite-object Coulomb pair and cell-veto events with
+    inside-first lifting over the six leaf units, Lennard-Jones between the oxygens, harmonic bonds, the bending
+    factor with its piecewise constant bounding potential and ratio lifting, root units in root-level cells."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    chain = oracle.OracleChain(tu.water_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], g["charges"])
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        for f in tu.DISCRETE_FIELDS:
+            assert np.array_equal(rec[f], ref[f]), (f, done + int(np.nonzero(rec[f] != ref[f])[0][0]))
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            assert np.array_equal(chain.roots(), g["snap_roots"][k])
+            occ, surplus = chain.cells()
+            assert np.array_equal(occ, g["snap_occupants"][k])
+            ns = int(g["snap_n_surplus"][k])
+            assert sorted(surplus.tolist()) == sorted(g["snap_surplus"][k][:ns].tolist())
+    assert np.array_equal(chain.positions(), g["final_positions"])
+    assert np.array_equal(chain.roots(), g["final_roots"])
+    assert chain.stats()["capacity_errors"] == 0
+
+
 def test_time_limit_keeps_candidates(oracle):
     """Stopping at host control times (sampling) keeps the interaction winner: the event sequence is the same
     whether the chain runs in one go or is interrupted, up to the rounding of the extra time slices."""

@@ -7,6 +7,7 @@ from jellyfysh_b200 import abi
 TRACES = ["trace_lj_small", "trace_lj_surplus", "trace_coulomb_small", "trace_coulomb_surplus"]
 CELL_BOUNDING_TRACES = ["trace_coulomb_cell_bounded"]
 DIPOLE_TRACES = ["trace_hard_disk_dipoles"]
+WATER_TRACES = ["trace_water", "trace_water_dense"]
 DISCRETE_FIELDS = ("kind", "target", "target_cell", "accepted", "n_candidates", "new_active", "new_direction")
 
 
@@ -56,6 +57,29 @@ def dipole_builder_of(g, builder_cls):
     pb.set_pair(abi.PAIR_TWO_LEAF_UNIT, abi.EcmcPotential.make(abi.POT_HARD_SPHERE, *g["meta_hard_sphere"]))
     pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1)],
                      bond_potential=abi.EcmcPotential.make(abi.POT_HARD_DIPOLE, *g["meta_hard_dipole"]))
+    return pb
+
+
+def water_builder_of(g, builder_cls, max_surplus=None):
+    """C4: SPC/Fw-like water (water/coulomb_cell_veto_lj_inverted.ini): composite-object Coulomb handlers with
+    inside-first lifting on root-level cells, Lennard-Jones between the oxygens, harmonic bonds, bending."""
+    n = int(g["meta_n"])
+    pb = builder_cls(3, n, float(g["meta_system_length"]), float(g["meta_beta"]),
+                     [int(c) for c in g["meta_cells_per_side"]], int(g["meta_neighbor_layers"]), max_occupants=1,
+                     max_surplus=n // 3 if max_surplus is None else max_surplus, chain_time=float(g["meta_chain_time"]),
+                     initial_active=int(g["meta_initial_active"]), seed=int(g["seed"][0]))
+    mic = abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"])
+    pb.set_pair(abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, mic,
+                abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, *g["meta_ipcb"]), use_charge=True)
+    pb.set_veto(mic, reference_tables(g), use_charge=True, target_charge=1.0)
+    pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1), (1, 2)],
+                     bond_potential=abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, *g["meta_harmonic"]))
+    pb.set_molecules(abi.LIFTING_INSIDE_FIRST, inter_factors=[(1, 1)],
+                     inter_potential=abi.EcmcPotential.make(abi.POT_LENNARD_JONES, *g["meta_lj"]),
+                     bending=dict(children=[0, 1, 2], separations=[1, 0, 1, 2], lifting=abi.LIFTING_RATIO,
+                                  potential=abi.EcmcPotential.make(abi.POT_BENDING, *g["meta_bending"]),
+                                  offset=float(g["meta_bending_offset"]),
+                                  max_displacement=float(g["meta_bending_max_displacement"])))
     return pb
 
 
