@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ecmc_kernels.cuh"
+#include "ecmc_molecules.cuh"
 
 using namespace ecmc;
 
@@ -43,6 +44,8 @@ struct EcmcHandle {
     EcmcStats *d_stats = nullptr;
     EcmcStats *h_stats = nullptr;     // pinned
     bool roots_uploaded = false;
+    bool molecules = false;           // composite objects in root-level cells: molecule_kernel
+    MoleculeProgram mprog;
     double *d_staging = nullptr;      // [n_chains][n_particles][dimension] + charges
     double *d_staging_charges = nullptr;
     uint32_t *d_streams = nullptr;
@@ -284,6 +287,57 @@ int build_device_program(EcmcHandle *h) {
             d.bonds[b][k] = p.bonds[b][k];
         }
     d.root_speed = p.speed * (1.0 / d.nodes_per_root);  // velocity component * weight (abstracts.py:181)
+    // molecules: composite objects in root-level cells (water)
+    h->molecules = p.cell_level == 1 && d.nodes_per_root > 1;
+    std::memset(&h->mprog, 0, sizeof(h->mprog));
+    if ((p.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || p.n_inter_factors > 0 || p.bending_enabled) && !h->molecules)
+        return fail(h, ECMC_ERR_INVALID, "composite-object handlers need cell_level = 1 and nodes_per_root > 1");
+    if (h->molecules) {
+        MoleculeProgram &m = h->mprog;
+        if (p.dimension != 3 || d.nodes_per_root > 3 || p.max_occupants != 1)
+            return fail(h, ECMC_ERR_INVALID, "molecules need dimension 3, nodes_per_root <= 3 and max_occupants = 1");
+        if (p.pair_handler != ECMC_PAIR_NONE && p.pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING)
+            return fail(h, ECMC_ERR_INVALID, "molecules need the composite-object pair handler");
+        if (p.veto_enabled != ECMC_FAR_NONE && p.veto_enabled != ECMC_FAR_CELL_VETO)
+            return fail(h, ECMC_ERR_INVALID, "molecules support the cell-veto far field only");
+        if (p.composite_lifting < ECMC_LIFTING_INSIDE_FIRST || p.composite_lifting > ECMC_LIFTING_RATIO)
+            return fail(h, ECMC_ERR_INVALID, "unknown lifting scheme");
+        if (p.n_inter_factors < 0 || p.n_inter_factors > ECMC_MAX_INTER_FACTORS)
+            return fail(h, ECMC_ERR_INVALID, "n_inter_factors out of range");
+        m.composite_lifting = p.composite_lifting;
+        m.n_inter = p.n_inter_factors;
+        for (int f = 0; f < p.n_inter_factors; f++)
+            for (int k = 0; k < 2; k++) {
+                if (p.inter_factors[f][k] < 0 || p.inter_factors[f][k] >= d.nodes_per_root)
+                    return fail(h, ECMC_ERR_INVALID, "inter-object factor child index out of range");
+                m.inter[f][k] = p.inter_factors[f][k];
+            }
+        if (p.n_inter_factors > 0) {
+            if (!is_invertible(p.inter_potential.kind)) return fail(h, ECMC_ERR_INVALID, "inter-object potential is not invertible");
+            int rc_inter = make_potential(h, p.inter_potential, p.system_length, &m.inter_potential);
+            if (rc_inter) return rc_inter;
+        }
+        m.bending_enabled = p.bending_enabled ? 1 : 0;
+        m.boundary_keeps_factors = p.boundary_keeps_factors ? 1 : 0;
+        if (p.bending_enabled) {
+            if (p.bending_potential.kind != ECMC_POT_BENDING || d.nodes_per_root != 3 || !(p.bending_max_displacement > 0.0) ||
+                p.bending_lifting < ECMC_LIFTING_INSIDE_FIRST || p.bending_lifting > ECMC_LIFTING_RATIO)
+                return fail(h, ECMC_ERR_INVALID, "bending needs three leaves per object, a bending potential, a lifting scheme and max_displacement > 0");
+            m.bending_lifting = p.bending_lifting;
+            for (int i = 0; i < 3; i++) {
+                if (p.bending_children[i] < 0 || p.bending_children[i] >= 3) return fail(h, ECMC_ERR_INVALID, "bending child out of range");
+                m.bending_children[i] = p.bending_children[i];
+            }
+            for (int i = 0; i < 4; i++) {
+                if (p.bending_separations[i] < 0 || p.bending_separations[i] >= 3) return fail(h, ECMC_ERR_INVALID, "bending separation index out of range");
+                m.bending_separations[i] = p.bending_separations[i];
+            }
+            m.bending_prefactor = p.bending_potential.params[0];
+            m.bending_angle = p.bending_potential.params[1];
+            m.bending_offset = p.bending_offset;
+            m.bending_max_displacement = p.bending_max_displacement;
+        }
+    }
 
     // potentials
     int rc;
@@ -295,7 +349,7 @@ int build_device_program(EcmcHandle *h) {
     if (p.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT) {
         if (!is_invertible(p.pair_potential.kind)) return fail(h, ECMC_ERR_INVALID, "pair potential is not invertible");
         if ((rc = make_potential(h, p.pair_potential, p.system_length, &d.cand_potential))) return rc;
-    } else if (p.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING) {
+    } else if (p.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING || p.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING) {
         if (!is_invertible(p.pair_bounding_potential.kind) || !has_derivative(p.pair_bounding_potential.kind))
             return fail(h, ECMC_ERR_INVALID, "pair bounding potential must be invertible with a derivative");
         if (!has_derivative(p.pair_potential.kind)) return fail(h, ECMC_ERR_INVALID, "pair potential has no derivative");
@@ -461,10 +515,17 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
     EventPair ev;
     int rc = acquire_events(h, &ev);
     if (rc) return rc;
-    const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
     const int blocks = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
     CUDA_TRY(h, cudaEventRecord(ev.start, h->stream));
-    kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
+    if (h->molecules) {
+        if (d_records)
+            molecule_kernel<true, kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
+        else
+            molecule_kernel<false, kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
+    } else {
+        const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
+        kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
+    }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(ev.stop, h->stream));
     h->timed.push_back(ev);
@@ -617,9 +678,14 @@ ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_s
     if (streams)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_streams, streams, sizeof(uint32_t) * h->n_chains, cudaMemcpyHostToDevice, h->stream));
     const int blocks = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
-        h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
-        h->program.initial_direction, h->d_stats);
+    if (h->molecules)
+        molecule_start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
+            h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
+            h->program.initial_direction, h->d_stats);
+    else
+        start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
+            h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
+            h->program.initial_direction, h->d_stats);
     CUDA_TRY(h, cudaGetLastError());
     h->started = true;
     return ECMC_OK;
@@ -727,6 +793,7 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
     if (!h || !positions_in) return fail(h, ECMC_ERR_INVALID, "null argument");
     if (h->dprog.nodes_per_root > 1 && !h->roots_uploaded)
         return fail(h, ECMC_ERR_STATE, "composite objects: ecmc_upload_roots before ecmc_run_from_host");
+    if (h->molecules) return fail(h, ECMC_ERR_INVALID, "molecules: use ecmc_upload_positions / _roots, ecmc_start, ecmc_run");
     if (std::isnan(until_q) || std::isnan(until_r)) return fail(h, ECMC_ERR_INVALID, "until time is NaN");
     if (max_events_per_chain <= 0 && std::isinf(until_q))
         return fail(h, ECMC_ERR_INVALID, "neither a time limit nor an event limit: the run would not end");

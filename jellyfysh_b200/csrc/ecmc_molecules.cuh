@@ -1,0 +1,781 @@
+// ecmc_molecules.cuh -- the event kernel for composite point objects in root-level cells (water).
+//
+// One warp advances one Markov chain, like ecmc::event_kernel, but the factors are those of the shipped water
+// configurations (jellyfysh/config_files/2018_JCP_149_064113/water/coulomb_cell_veto_lj_inverted.ini):
+//   * composite-object Coulomb pairs with every object in a nearby cell / the surplus
+//     (TwoCompositeObjectSummedBoundingPotentialEventHandler, two_composite_object_summed_bounding_potential_event_handler.py:
+//     119-202): one LANE per (target object, target leaf) -- the handler's minimum over the target leaves is part of the
+//     warp argmin;
+//   * the composite-object cell veto for all other cells (CompositeObjectCellVetoEventHandler,
+//     composite_object_cell_veto_event_handler.py:110-162 on abstracts/cell_veto_event_handler.py:200-238);
+//   * two-leaf factors between objects (Lennard-Jones between the oxygens, "[1, 4], LennardJones"): one lane per object;
+//   * intramolecular two-leaf factors (harmonic bonds) and the three-leaf bending factor with its piecewise constant
+//     bounding potential (event_handler_with_bounding_potential.py:282-332);
+//   * the cell boundary of the ROOT unit, which moves with speed / nodes_per_root (cell_boundary_event_handler.py:98-173);
+//   * lifting schemes over the six leaf units (event_handler_with_bounding_potential.py:170-220, lifting/*.py).
+// The work of one event is a list of items in shared memory (type, target, sequence number), worked off 32 at a time.
+#pragma once
+
+#include "ecmc_kernels.cuh"
+
+namespace ecmc {
+
+struct MoleculeProgram {
+    int composite_lifting, bending_lifting;
+    int n_inter, bending_enabled;
+    int inter[ECMC_MAX_INTER_FACTORS][2];
+    int bending_children[3];
+    int bending_separations[4];
+    int boundary_keeps_factors;
+    double bending_prefactor, bending_angle, bending_offset, bending_max_displacement;
+    PotentialParams inter_potential;
+};
+
+constexpr int kItemCapacity = 192;  // work items per chunk (two ints each: 1.5 KB per warp)
+enum ItemType { ITEM_PAIR_LEAF = 0, ITEM_INTER = 1, ITEM_BOND = 2, ITEM_BENDING = 3, ITEM_VETO = 4, ITEM_BOUNDARY = 5 };
+
+struct Vec3 {
+    double x, y, z;
+};
+ECMC_D double vcomp(const Vec3 &v, int d) { return d == 0 ? v.x : (d == 1 ? v.y : v.z); }
+ECMC_D Vec3 lab_position(const Particle &p) {
+    Vec3 v;
+    v.x = p.x; v.y = p.y; v.z = p.z;
+    return v;
+}
+ECMC_D Vec3 separation_lab(const Vec3 &from, const Vec3 &to, double L, double half) {
+    Vec3 s;
+    s.x = correct_separation_in_box(to.x - from.x, L, half);
+    s.y = correct_separation_in_box(to.y - from.y, L, half);
+    s.z = correct_separation_in_box(to.z - from.z, L, half);
+    return s;
+}
+
+// BendingPotential.derivative (bending_potential.py:60-138): time derivatives with respect to the units i, j, k for
+// s1 = r_i - r_j, s2 = r_k - r_j along direction `dir`
+ECMC_D void bending_derivative(double prefactor, double equilibrium_angle, int dir, double speed, const Vec3 &s1,
+                               const Vec3 &s2, double out[3]) {
+    const double n1 = sqrt(fma(s1.x, s1.x, fma(s1.y, s1.y, s1.z * s1.z)));
+    const double n2 = sqrt(fma(s2.x, s2.x, fma(s2.y, s2.y, s2.z * s2.z)));
+    const double inv1 = 1.0 / n1, inv2 = 1.0 / n2;
+    const double cosine = fma(s1.x, s2.x, fma(s1.y, s2.y, s1.z * s2.z)) * inv1 * inv2;
+    const double angle = acos(cosine);
+    const double du_dangle = prefactor * (angle - equilibrium_angle);
+    const double dangle_dcos = -1.0 / sin(angle);
+    const double a1 = vcomp(s1, dir), a2 = vcomp(s2, dir);
+    const double dcos_ds1 = a2 * inv1 * inv2 - cosine * a1 * inv1 * inv1;
+    const double dcos_ds2 = a1 * inv1 * inv2 - cosine * a2 * inv2 * inv2;
+    const double du_ds1 = du_dangle * dangle_dcos * dcos_ds1;
+    const double du_ds2 = du_dangle * dangle_dcos * dcos_ds2;
+    out[0] = du_ds1 * speed;
+    out[1] = (-du_ds1 - du_ds2) * speed;
+    out[2] = du_ds2 * speed;
+}
+
+// Lifting.insert / get_active_identifier (lifting/lifting.py:49-91 and the three schemes), at most eight units.
+// Draws come from the out-state's slot (ECMC_SLOT_CONFIRM) in call order.
+struct Lifting {
+    double negative[6];
+    int ids[6];
+    int n_negative;
+    double random_position;
+    bool active_recorded;
+};
+ECMC_D void lifting_reset(Lifting &l) {
+    l.n_negative = 0;
+    l.random_position = 0.0;
+    l.active_recorded = false;
+}
+ECMC_D void lifting_insert(Lifting &l, double rate, int id, bool is_active, const StreamKey &key, uint32_t &draw) {
+    if (rate > 0.0) {
+        if (is_active) {
+            l.active_recorded = true;
+            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+            l.random_position += 0.0 + (rate - 0.0) * u;
+        } else if (!l.active_recorded) {
+            l.random_position += rate;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if (i == l.n_negative) { l.negative[i] = -rate; l.ids[i] = id; }
+        l.n_negative++;
+    }
+}
+// Python's sum() over floats is Neumaier-compensated since CPython 3.12
+ECMC_D double pysum_n(const double *v, int n) {
+    double f = 0.0, comp = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (i < n) {
+            const double x = v[i];
+            const double t = __dadd_rn(f, x);
+            comp = __dadd_rn(comp, fabs(f) >= fabs(x) ? __dadd_rn(__dsub_rn(f, t), x) : __dadd_rn(__dsub_rn(x, t), f));
+            f = t;
+        }
+    if (comp != 0.0 && isfinite(comp)) f = __dadd_rn(f, comp);
+    return f;
+}
+ECMC_D int lifting_get(const Lifting &l, int kind, const StreamKey &key, uint32_t &draw) {
+    double position = l.random_position;
+    if (kind == ECMC_LIFTING_OUTSIDE_FIRST) {
+        position = pysum_n(l.negative, l.n_negative) - l.random_position;
+    } else if (kind == ECMC_LIFTING_RATIO) {
+        const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+        position = 0.0 + (pysum_n(l.negative, l.n_negative) - 0.0) * u;
+    }
+    double summed = 0.0;
+    int chosen = -1;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (i < l.n_negative) {
+            summed += l.negative[i];
+            if (chosen < 0 && position <= summed) chosen = l.ids[i];
+            if (i == l.n_negative - 1 && chosen < 0) chosen = l.ids[i];
+        }
+    return chosen;
+}
+
+// derivative of a pair potential between two leaves in the lab frame (all lanes, identical arguments)
+template <int KIND>
+ECMC_D double pair_derivative_lab(const PotentialParams &p, int dir, double speed, const Vec3 &from, const Vec3 &to,
+                                  double c1, double c2, double L, double half, double *trig, int lane) {
+    const Vec3 s = separation_lab(from, to, L, half);
+    return derivative_warp<KIND>(p, dir, speed, s.x, s.y, s.z, c1, c2, trig, lane);
+}
+
+template <bool RECORD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ MoleculeProgram M, const DeviceState S,
+                const RunArgs A) {
+    __shared__ double trig_all[WARPS * kTrigDoubles];
+    __shared__ int items_all[WARPS * 2 * kItemCapacity];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chain = S.first_chain + blockIdx.x * WARPS + warp;
+    if (chain >= S.first_chain + S.n_chains) return;
+    double *trig = trig_all + warp * kTrigDoubles;
+    int *item_code = items_all + warp * 2 * kItemCapacity;  // type | sequence << 4
+    int *item_target = item_code + kItemCapacity;
+
+    const int npr = P.nodes_per_root;
+    const int n_roots = P.n_particles / npr;
+    Particle *part = S.particles + (size_t)chain * P.n_particles;
+    Particle *roots = S.roots + (size_t)chain * n_roots;
+    int *occ = S.occupants + (size_t)chain * P.n_cells;
+    int *sur = S.surplus + (size_t)chain * P.max_surplus;
+    EcmcChainState *stp = S.chains + chain;
+
+    int active = stp->active, dir = stp->direction;
+    Time now = {stp->time_q, stp->time_r};
+    Time eoc = {stp->eoc_q, stp->eoc_r};
+    int eoc_next = stp->eoc_next_active;
+    int active_cell = stp->active_cell;
+    unsigned long long ev = stp->event_counter;
+    const uint32_t stream = stp->stream;
+    bool was_pending = stp->pending_kind != ECMC_EVENT_NONE;
+    int n_surplus = S.n_surplus[chain];
+    // candidates of the leaf-level factors kept across a cell-boundary event of the root (EcmcChainState.kept_*)
+    int kept_kind = stp->kept_kind, kept_target = stp->kept_target;
+    Time kept_time = {stp->kept_q, stp->kept_r};
+    double kept_rate = stp->kept_rate, kept_pos = stp->kept_position, kept_root = stp->kept_root_position;
+    Time kept_stamp = {stp->kept_stamp_q, stp->kept_stamp_r};
+
+    Vec3 apos = lab_position(part[active]);     // the active leaf
+    double acharge = part[active].charge;
+    Vec3 rpos = lab_position(roots[active / npr]);  // its root unit
+    int cid0 = (active_cell / P.cumulative[0]) % P.per_side[0];
+    int cid1 = (active_cell / P.cumulative[1]) % P.per_side[1];
+    int cid2 = (active_cell / P.cumulative[2]) % P.per_side[2];
+
+    const Time until = {A.until_q, A.until_r};
+    const double L = P.length, half = P.half_length, speed = P.speed;
+    const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
+    unsigned n_events = 0, n_pair = 0, n_veto = 0, n_eoc = 0, n_bond = 0, n_factor = 0, n_boundary = 0;
+    unsigned long long n_candidates = 0;
+    bool stopped_by_time = false;
+
+    auto set_dir = [&](Vec3 &v, double value) { if (dir == 0) v.x = value; else if (dir == 1) v.y = value; else v.z = value; };
+
+    while (n_events < max_events) {
+        const StreamKey key = {P.seed, stream, ev};
+        const int active_root = active / npr, active_child = active - active_root * npr;
+        Time bt = time_inf();
+        int bkind = ECMC_EVENT_NONE, btarget = -1, bcell = -1;
+        double brate = 0.0;
+        int n_cand = 0;
+        bool best_from_kept = false;
+        // the earliest factor candidate of this iteration (what a cell-boundary event would leave running)
+        Time ft = time_inf();
+        int fkind = ECMC_EVENT_NONE, ftarget = -1;
+        double frate = 0.0;
+        double restore_pos = 0.0, restore_root = 0.0;
+        Time restore_stamp = now;
+        bool restore = false;
+        // lower boundary of the next cell of the ROOT unit along the direction of motion
+        const int id_dir = dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2);
+        const int nid = id_dir + 1 == P.per_side[dir] ? 0 : id_dir + 1;
+        const int next_cell = active_cell + (nid - id_dir) * P.cumulative[dir];
+        const double boundary = __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
+
+        if (was_pending) {
+            bkind = stp->pending_kind;
+            bt.q = stp->pending_q; bt.r = stp->pending_r;
+            brate = stp->pending_rate;
+            if (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_BOND || bkind == ECMC_EVENT_FACTOR_PAIR)
+                btarget = stp->pending_target;
+            else bcell = stp->pending_target;
+            restore = true;
+            restore_pos = stp->pending_position; restore_root = stp->pending_root_position;
+            restore_stamp.q = stp->pending_stamp_q; restore_stamp.r = stp->pending_stamp_r;
+        } else {
+            const bool factors_kept = kept_kind != ECMC_EVENT_NONE;
+            const int nearby_slots = P.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING ? P.n_nearby : 0;
+            const int n_pair_slots = nearby_slots ? nearby_slots + n_surplus : 0;
+            // scan positions: [0, n_pair_slots) objects, then bonds, inter-object factors (one per object and factor),
+            // bending, veto, boundary
+            const int bond_base = n_pair_slots;
+            const int inter_base = bond_base + (factors_kept ? 0 : P.n_bonds);
+            const int bending_base = inter_base + (factors_kept ? 0 : M.n_inter * n_roots);
+            const int veto_base = bending_base + ((!factors_kept && M.bending_enabled) ? 1 : 0);
+            const int boundary_base = veto_base + (P.veto_enabled == ECMC_FAR_CELL_VETO ? 1 : 0);
+            const int n_scan = boundary_base + 1;
+            unsigned long long best_key = 0x7ff0000000000000ull;
+            double best_x = INFINITY;
+            int best_seq = kSeqNone;
+            unsigned long long fbest_key = 0x7ff0000000000000ull;
+            int fbest_seq = kSeqNone;
+            double fbest_x = INFINITY;
+            int cursor = 0;
+            while (cursor < n_scan) {
+                int count = 0;
+                while (cursor < n_scan && count <= kItemCapacity - 96) {
+                    const int s = cursor + lane;
+                    int type = -1, target = -1, copies = 0;
+                    if (s < nearby_slots) {
+                        const int code = __ldg(P.nearby + s);
+                        int x = cid0 + (code & 1023), y = cid1 + ((code >> 10) & 1023), z = cid2 + (code >> 20);
+                        if (x >= P.per_side[0]) x -= P.per_side[0];
+                        if (y >= P.per_side[1]) y -= P.per_side[1];
+                        if (z >= P.per_side[2]) z -= P.per_side[2];
+                        target = occ[x * P.cumulative[0] + y * P.cumulative[1] + z * P.cumulative[2]];
+                        if (target >= 0) { type = ITEM_PAIR_LEAF; copies = npr; }
+                    } else if (s < n_pair_slots) {
+                        target = sur[s - nearby_slots];
+                        type = ITEM_PAIR_LEAF; copies = npr;
+                    } else if (s < inter_base) {
+                        const int b = s - bond_base;
+                        const int partner = P.bonds[b][0] == active_child ? P.bonds[b][1]
+                                                                          : (P.bonds[b][1] == active_child ? P.bonds[b][0] : -1);
+                        if (partner >= 0) { type = ITEM_BOND; target = active_root * npr + partner; copies = 1; }
+                    } else if (s < bending_base) {
+                        const int f = (s - inter_base) / n_roots, r = (s - inter_base) - f * n_roots;
+                        if (M.inter[f][0] == active_child && r != active_root) {
+                            type = ITEM_INTER; target = r * npr + M.inter[f][1]; copies = 1;
+                        }
+                    } else if (s < veto_base) {
+                        bool member = false;
+                        for (int i = 0; i < 3; i++) member = member || M.bending_children[i] == active_child;
+                        if (member) { type = ITEM_BENDING; target = 0; copies = 1; }
+                    } else if (s < boundary_base) {
+                        type = ITEM_VETO; target = 0; copies = 1;
+                    } else if (s < n_scan) {
+                        type = ITEM_BOUNDARY; target = 0; copies = 1;
+                    }
+                    // exclusive prefix sum of `copies` over the lanes: where this lane's items go
+                    int offset = copies;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(kFull, offset, o);
+                        if (lane >= o) offset += v;
+                    }
+                    const int total = __shfl_sync(kFull, offset, 31);
+                    offset -= copies;
+                    for (int k = 0; k < copies; k++) {
+                        item_code[count + offset + k] = type | ((s * 4 + k) << 4);
+                        item_target[count + offset + k] = type == ITEM_PAIR_LEAF ? target * npr + k : target;
+                    }
+                    count += total;
+                    cursor += 32;
+                }
+                __syncwarp();
+                for (int base = 0; base < count; base += 32) {
+                    const int entry = base + lane;
+                    int type = -1, target = -1, seq = kSeqNone;
+                    if (entry < count) {
+                        const int code = item_code[entry];
+                        type = code & 15; seq = code >> 4;
+                        target = item_target[entry];
+                    }
+                    double dt = INFINITY, rate = 0.0;
+                    int kind = ECMC_EVENT_NONE, cell = -1, rec_target = -1;
+                    bool is_factor = false;
+                    if (type == ITEM_PAIR_LEAF || type == ITEM_INTER || type == ITEM_BOND) {
+                        const Particle tp = part[target];
+                        const Vec3 s3 = separation_lab(apos, lab_position(tp), L, half);
+                        const double s0 = vcomp(s3, dir);
+                        const double s1 = dir == 0 ? s3.y : (dir == 1 ? s3.z : s3.x);
+                        const double s2 = dir == 0 ? s3.z : (dir == 1 ? s3.x : s3.y);
+                        if (type == ITEM_PAIR_LEAF) {
+                            // double k of (PAIR_TIME, target object) for target leaf k
+                            const int root = target / npr, k = target - root * npr;
+                            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, root), (uint32_t)k);
+                            const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                            const double c1 = P.pair_use_charge ? acharge : 1.0, c2 = P.pair_use_charge ? tp.charge : 1.0;
+                            dt = displacement_time<-1>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c1, c2, du);
+                            kind = ECMC_EVENT_PAIR;
+                            rec_target = root;
+                        } else {
+                            const PotentialParams &pot = type == ITEM_BOND ? P.bond_potential : M.inter_potential;
+                            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
+                            const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                            dt = displacement_time<-1>(pot, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
+                                                       needs_potential_change(pot.kind) ? du : 0.0);
+                            kind = type == ITEM_BOND ? ECMC_EVENT_BOND : ECMC_EVENT_FACTOR_PAIR;
+                            rec_target = target;
+                            is_factor = true;
+                        }
+                    } else if (type == ITEM_BENDING) {
+                        // _displacement_from_piecewise_constant_bounding_potential
+                        // (event_handler_with_bounding_potential.py:282-332)
+                        int index = 0;
+                        Vec3 unit[3], moved[3];
+                        for (int i = 0; i < 3; i++) {
+                            const int leaf = active_root * npr + M.bending_children[i];
+                            unit[i] = leaf == active ? apos : lab_position(part[leaf]);
+                            moved[i] = unit[i];
+                            if (leaf == active) {
+                                index = i;
+                                const double x = correct_position_entry(
+                                    __dadd_rn(vcomp(apos, dir), __dmul_rn(speed, M.bending_max_displacement)), L);
+                                set_dir(moved[i], x);
+                            }
+                        }
+                        const int *sp = M.bending_separations;
+                        double one[3], two[3];
+                        bending_derivative(M.bending_prefactor, M.bending_angle, dir, speed,
+                                           separation_lab(unit[sp[0]], unit[sp[1]], L, half),
+                                           separation_lab(unit[sp[2]], unit[sp[3]], L, half), one);
+                        bending_derivative(M.bending_prefactor, M.bending_angle, dir, speed,
+                                           separation_lab(moved[sp[0]], moved[sp[1]], L, half),
+                                           separation_lab(moved[sp[2]], moved[sp[3]], L, half), two);
+                        const double a = index == 0 ? one[0] : (index == 1 ? one[1] : one[2]);
+                        const double b = index == 0 ? two[0] : (index == 1 ? two[1] : two[2]);
+                        const double constant = (a > b ? a : b) + M.bending_offset;
+                        const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_BENDING_TIME, 0), 0);
+                        const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                        rate = -1.0;  // bounding event rate None
+                        dt = M.bending_max_displacement;
+                        if (constant > 0.0 && du / constant < M.bending_max_displacement) { rate = constant; dt = du / constant; }
+                        kind = ECMC_EVENT_BENDING;
+                        is_factor = true;
+                    } else if (type == ITEM_VETO) {
+                        // CellVetoEventHandler.send_event_time (cell_veto_event_handler.py:200-238) for the active leaf
+                        // of a composite object; DipoleMonteCarloEstimator.charge_correction_factor = the active charge
+                        double charge_factor = 1.0;
+                        if (P.veto_use_charge) {
+                            charge_factor = acharge * 1.0;
+                            if (P.veto_target_charge != 1.0) charge_factor = charge_factor / P.veto_target_charge;
+                        }
+                        const DeviceWalker *w = &P.upper[dir];
+                        if (!(charge_factor > 0.0)) { charge_factor *= -1.0; w = &P.lower[dir]; }
+                        uint32_t index = 0;
+                        const uint32_t e = stream_randbelow_from(key, ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0),
+                                                                 (uint32_t)w->n_entries, index);
+                        const WalkerEntry entry = w->entries[e];
+                        const double u0 = stream_double(key, ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0), 0);
+                        const double u1 = stream_double(key, ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0), 1);
+                        const bool first = 0.0 + (w->mean_rate - 0.0) * u0 <= entry.rate_a;
+                        const int relative = first ? entry.cell_a : entry.cell_b;
+                        rate = (first ? entry.bound_a : entry.bound_b) * charge_factor;
+                        int tx, ty, tz;
+                        const int rx = relative & 1023, ry = (relative >> 10) & 1023, rz = relative >> 20;
+                        if (P.translate_modular) {
+                            tx = cid0 + rx; ty = cid1 + ry; tz = cid2 + rz;
+                            if (tx >= P.per_side[0]) tx -= P.per_side[0];
+                            if (ty >= P.per_side[1]) ty -= P.per_side[1];
+                            if (tz >= P.per_side[2]) tz -= P.per_side[2];
+                        } else {
+                            const int mps = P.max_per_side;
+                            tx = __ldg(P.translate_axis + (0 * mps + cid0) * mps + rx);
+                            ty = __ldg(P.translate_axis + (1 * mps + cid1) * mps + ry);
+                            tz = __ldg(P.translate_axis + (2 * mps + cid2) * mps + rz);
+                        }
+                        cell = tx * P.cumulative[0] + ty * P.cumulative[1] + tz * P.cumulative[2];
+                        const double exponential = -log_unit_interval(1.0 - u1) * P.inv_beta;
+                        dt = exponential / (w->total_rate * charge_factor * speed);
+                        kind = ECMC_EVENT_CELL_VETO;
+                    } else if (type == ITEM_BOUNDARY) {
+                        double separation = boundary - vcomp(rpos, dir);
+                        if (separation < 0.0) separation = separation + L;
+                        dt = separation / P.root_speed;
+                        cell = next_cell;
+                        kind = ECMC_EVENT_CELL_BOUNDARY;
+                    }
+                    const double x = now.r + dt;
+                    const bool finite = kind != ECMC_EVENT_NONE && x < INFINITY;
+                    // the reference counts one candidate per handler: the first leaf of an object stands for the pair
+                    n_cand += __popc(__ballot_sync(kFull, finite && !(type == ITEM_PAIR_LEAF && (seq & 3) != 0)));
+                    const unsigned long long k64 = finite ? time_key(x) : 0x7ff0000000000000ull;
+                    const int owner = warp_argmin(k64, finite ? seq : kSeqNone, lane);
+                    const unsigned long long pass_key = __shfl_sync(kFull, k64, owner);
+                    const int pass_seq = __shfl_sync(kFull, finite ? seq : kSeqNone, owner);
+                    if (pass_key < best_key || (pass_key == best_key && pass_seq < best_seq)) {
+                        best_key = pass_key; best_seq = pass_seq;
+                        best_x = __shfl_sync(kFull, x, owner);
+                        bkind = __shfl_sync(kFull, kind, owner);
+                        btarget = __shfl_sync(kFull, rec_target, owner);
+                        bcell = __shfl_sync(kFull, cell, owner);
+                        brate = __shfl_sync(kFull, rate, owner);
+                    }
+                    // the earliest of the leaf-level factors, separately (kept if a cell-boundary event wins)
+                    const bool ffinite = finite && is_factor;
+                    if (__any_sync(kFull, ffinite)) {
+                        const unsigned long long f64 = ffinite ? k64 : 0x7ff0000000000000ull;
+                        const int fowner = warp_argmin(f64, ffinite ? seq : kSeqNone, lane);
+                        const unsigned long long fkey = __shfl_sync(kFull, f64, fowner);
+                        const int fseq = __shfl_sync(kFull, ffinite ? seq : kSeqNone, fowner);
+                        if (fkey < fbest_key || (fkey == fbest_key && fseq < fbest_seq)) {
+                            fbest_key = fkey; fbest_seq = fseq;
+                            fbest_x = __shfl_sync(kFull, x, fowner);
+                            fkind = __shfl_sync(kFull, kind, fowner);
+                            ftarget = __shfl_sync(kFull, rec_target, fowner);
+                            frate = __shfl_sync(kFull, rate, fowner);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (best_seq != kSeqNone) {
+                const double fl = floor(best_x);
+                bt.q = now.q + fl; bt.r = best_x - fl;
+            } else {
+                bkind = ECMC_EVENT_NONE;
+            }
+            if (fbest_seq != kSeqNone) {
+                const double fl = floor(fbest_x);
+                ft.q = now.q + fl; ft.r = fbest_x - fl;
+            }
+            if (kept_kind > 0 && time_lt(kept_time, bt)) {
+                // a factor handler that a cell-boundary event left running fires first: its in-state is the old one
+                bt = kept_time; bkind = kept_kind; btarget = kept_target; bcell = -1; brate = kept_rate;
+                best_from_kept = true;
+            }
+        }
+
+        n_cand++;
+        const bool eoc_first = time_lt(eoc, bt);
+        const Time event_time = eoc_first ? eoc : bt;
+        const int kind = eoc_first ? ECMC_EVENT_END_OF_CHAIN : bkind;
+        if (!time_lt(event_time, until)) {
+            if (lane == 0) {
+                stp->pending_kind = bkind;
+                stp->pending_q = bt.q; stp->pending_r = bt.r;
+                stp->pending_rate = brate;
+                stp->pending_target = (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_BOND || bkind == ECMC_EVENT_FACTOR_PAIR)
+                                          ? btarget : bcell;
+                if (!was_pending) {
+                    stp->pending_position = best_from_kept ? kept_pos : vcomp(apos, dir);
+                    stp->pending_root_position = best_from_kept ? kept_root : vcomp(rpos, dir);
+                    stp->pending_stamp_q = best_from_kept ? kept_stamp.q : now.q;
+                    stp->pending_stamp_r = best_from_kept ? kept_stamp.r : now.r;
+                }
+            }
+            stopped_by_time = true;
+            break;
+        }
+        if (was_pending) {
+            if (lane == 0) stp->pending_kind = ECMC_EVENT_NONE;
+        } else if (best_from_kept) {
+            restore = true;
+            restore_pos = kept_pos; restore_root = kept_root; restore_stamp = kept_stamp;
+        }
+        if (restore && kind != ECMC_EVENT_END_OF_CHAIN) {
+            set_dir(apos, restore_pos);
+            set_dir(rpos, restore_root);
+            now = restore_stamp;
+        }
+        // which handlers survive this event: a cell-boundary event of the root leaves the leaf-level factors running
+        if (kind == ECMC_EVENT_CELL_BOUNDARY && M.boundary_keeps_factors) {
+            if (kept_kind == ECMC_EVENT_NONE && !was_pending) {
+                kept_kind = fkind == ECMC_EVENT_NONE ? -1 : fkind;
+                kept_target = ftarget; kept_time = ft; kept_rate = frate;
+                kept_pos = vcomp(apos, dir); kept_root = vcomp(rpos, dir); kept_stamp = now;
+            }
+        } else {
+            kept_kind = ECMC_EVENT_NONE;
+        }
+        was_pending = false;
+
+        // ---- out-state: time slice of the active leaf and its root (abstracts.py:82-101)
+        {
+            const double dt = time_sub(event_time, now);
+            set_dir(apos, correct_position_entry(__dadd_rn(vcomp(apos, dir), __dmul_rn(speed, dt)), L));
+            set_dir(rpos, correct_position_entry(__dadd_rn(vcomp(rpos, dir), __dmul_rn(P.root_speed, dt)), L));
+            now = event_time;
+        }
+        int new_active = active, rec_target = -1;
+        uint32_t draw = 0;
+        switch (kind) {
+        case ECMC_EVENT_PAIR:
+        case ECMC_EVENT_CELL_VETO: {
+            const bool veto = kind == ECMC_EVENT_CELL_VETO;
+            const int target_root = veto ? occ[bcell] : btarget;
+            rec_target = target_root;
+            if (veto) n_veto++; else n_pair++;
+            if (target_root < 0) break;
+            const bool use_charge = veto ? P.veto_use_charge : P.pair_use_charge;
+            double bounding_rate = veto ? brate : 0.0;
+            double factor_derivative = 0.0;
+            double target_derivatives[4] = {0.0, 0.0, 0.0, 0.0};
+            Vec3 tpos[4];
+            double tcharge[4];
+            for (int k = 0; k < npr; k++) {
+                const Particle tp = part[target_root * npr + k];
+                tpos[k] = lab_position(tp);
+                tcharge[k] = tp.charge;
+                const double c1 = use_charge ? acharge : 1.0, c2 = use_charge ? tp.charge : 1.0;
+                if (!veto) {
+                    const double b = pair_derivative_lab<-1>(P.cand_potential, dir, speed, apos, tpos[k], c1, c2, L, half, trig, lane);
+                    bounding_rate += b > 0.0 ? b : 0.0;
+                }
+                const double pairwise = pair_derivative_lab<-1>(veto ? P.veto_potential : P.real_potential, dir, speed, apos,
+                                                                tpos[k], c1, c2, L, half, trig, lane);
+                factor_derivative += pairwise;
+                target_derivatives[k] -= pairwise;
+            }
+            const double event_rate = factor_derivative > 0.0 ? factor_derivative : 0.0;
+            if (bounding_rate < event_rate) count_rare(A, lane, 7);
+            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+            if (event_rate <= 0.0 + (bounding_rate - 0.0) * u) break;
+            // _fill_lifting (event_handler_with_bounding_potential.py:170-220)
+            double local_derivatives[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = 0; i < npr; i++) {
+                const int local = active_root * npr + i;
+                if (local == active) { local_derivatives[i] = veto ? factor_derivative : event_rate; continue; }
+                const Particle lp = part[local];
+                for (int j = 0; j < npr; j++) {
+                    const double c1 = use_charge ? lp.charge : 1.0, c2 = use_charge ? tcharge[j] : 1.0;
+                    const double pairwise = pair_derivative_lab<-1>(veto ? P.veto_potential : P.real_potential, dir, speed,
+                                                                    lab_position(lp), tpos[j], c1, c2, L, half, trig, lane);
+                    local_derivatives[i] += pairwise;
+                    target_derivatives[j] -= pairwise;
+                }
+            }
+            Lifting lift;
+            lifting_reset(lift);
+            for (int pass = 0; pass < 2; pass++) {
+                const bool local_now = (active_root < target_root) == (pass == 0);
+                for (int i = 0; i < npr; i++) {
+                    if (local_now)
+                        lifting_insert(lift, local_derivatives[i], active_root * npr + i, active_root * npr + i == active, key, draw);
+                    else
+                        lifting_insert(lift, target_derivatives[i], target_root * npr + i, false, key, draw);
+                }
+            }
+            new_active = lifting_get(lift, M.composite_lifting, key, draw);
+            if (veto) count_rare(A, lane, 3);
+            break;
+        }
+        case ECMC_EVENT_BOND:
+        case ECMC_EVENT_FACTOR_PAIR:
+            rec_target = btarget;
+            new_active = btarget;
+            if (kind == ECMC_EVENT_BOND) n_bond++; else n_factor++;
+            break;
+        case ECMC_EVENT_BENDING: {
+            n_bond++;
+            if (brate < 0.0) break;
+            int index = 0;
+            Vec3 unit[3];
+            for (int i = 0; i < 3; i++) {
+                const int leaf = active_root * npr + M.bending_children[i];
+                unit[i] = leaf == active ? apos : lab_position(part[leaf]);
+                if (leaf == active) index = i;
+            }
+            const int *sp = M.bending_separations;
+            double derivatives[3];
+            bending_derivative(M.bending_prefactor, M.bending_angle, dir, speed,
+                               separation_lab(unit[sp[0]], unit[sp[1]], L, half),
+                               separation_lab(unit[sp[2]], unit[sp[3]], L, half), derivatives);
+            const double own = index == 0 ? derivatives[0] : (index == 1 ? derivatives[1] : derivatives[2]);
+            if (own > 0.0) {
+                if (brate < own) count_rare(A, lane, 7);
+                const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+                if (0.0 + (brate - 0.0) * u < own) {
+                    Lifting lift;
+                    lifting_reset(lift);
+                    for (int i = 0; i < 3; i++)
+                        lifting_insert(lift, derivatives[i], active_root * npr + M.bending_children[i], i == index, key, draw);
+                    new_active = lifting_get(lift, M.bending_lifting, key, draw);
+                }
+            }
+            break;
+        }
+        case ECMC_EVENT_CELL_BOUNDARY:
+            // the root lands exactly on the lower boundary of its new cell (cell_boundary_event_handler.py:158-173)
+            set_dir(rpos, __ldg(P.cell_min_axis + dir * P.max_per_side + (bcell / P.cumulative[dir]) % P.per_side[dir]));
+            n_boundary++;
+            break;
+        case ECMC_EVENT_END_OF_CHAIN:
+            new_active = eoc_next;
+            rec_target = new_active;
+            n_eoc++;
+            break;
+        default: break;
+        }
+        if (new_active < 0) { count_rare(A, lane, 8); new_active = active; }
+        if (RECORD && lane == 0 && (int)n_events < A.records_per_chain) {
+            EcmcEventRecord rec;
+            rec.kind = kind; rec.target = rec_target; rec.target_cell = kind == ECMC_EVENT_END_OF_CHAIN ? -1 : bcell;
+            rec.accepted = kind == ECMC_EVENT_END_OF_CHAIN ? 1 : (new_active != active);
+            rec.n_candidates = n_cand;
+            rec.new_active = new_active;
+            rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % P.dimension : dir;
+            rec.reserved = 0;
+            rec.time_q = event_time.q; rec.time_r = event_time.r;
+            rec.active_pos[0] = apos.x; rec.active_pos[1] = apos.y; rec.active_pos[2] = apos.z;
+            A.records[(size_t)chain * A.records_per_chain + n_events] = rec;
+        }
+        ev++;
+        n_events++;
+        n_candidates += (unsigned long long)n_cand;
+        if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir + 1 == P.dimension ? 0 : dir + 1;
+
+        // ---- commit + SingleActiveCellOccupancy.update on the cell level of the roots
+        const int new_root = new_active / npr;
+        if (new_active != active) {
+            if (lane == 0) {
+                Particle p = part[active];
+                p.x = apos.x; p.y = apos.y; p.z = apos.z;
+                part[active] = p;
+            }
+            __syncwarp();
+            const Particle np = part[new_active];
+            apos = lab_position(np);
+            acharge = np.charge;
+        }
+        if (new_root != active_root) {
+            int delta = 0;
+            if (lane == 0) {
+                Particle r = roots[active_root];
+                r.x = rpos.x; r.y = rpos.y; r.z = rpos.z;
+                roots[active_root] = r;
+                delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, active_cell, active_root);
+            }
+            delta = __shfl_sync(kFull, delta, 0);
+            if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+            __syncwarp();
+            rpos = lab_position(roots[new_root]);
+        }
+        active = new_active;
+        {
+            // the cell of the root is recomputed from its position after every event, like the oracle does
+            const int old_cell = active_cell;
+            cid0 = (int)(rpos.x / P.side_length[0]);
+            cid1 = (int)(rpos.y / P.side_length[1]);
+            cid2 = (int)(rpos.z / P.side_length[2]);
+            active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
+            (void)old_cell;
+        }
+        if (new_root != active_root) {
+            int delta = 0;
+            if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, 1, active_cell, new_root);
+            delta = __shfl_sync(kFull, delta, 0);
+            if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+            __syncwarp();
+        }
+        if (kind == ECMC_EVENT_END_OF_CHAIN) {
+            eoc = time_add(now, time_sub(now, now) + P.chain_time);
+            const StreamKey next_key = {P.seed, stream, ev};
+            eoc_next = draw_end_of_chain_active(P, next_key);
+        }
+    }
+
+    if (stopped_by_time) {
+        const double dt = time_sub(until, now);
+        set_dir(apos, correct_position_entry(__dadd_rn(vcomp(apos, dir), __dmul_rn(speed, dt)), L));
+        set_dir(rpos, correct_position_entry(__dadd_rn(vcomp(rpos, dir), __dmul_rn(P.root_speed, dt)), L));
+        now = until;
+    }
+    if (lane == 0) {
+        Particle p = part[active];
+        p.x = apos.x; p.y = apos.y; p.z = apos.z;
+        part[active] = p;
+        Particle r = roots[active / npr];
+        r.x = rpos.x; r.y = rpos.y; r.z = rpos.z;
+        roots[active / npr] = r;
+        stp->active = active; stp->direction = dir;
+        stp->time_q = now.q; stp->time_r = now.r;
+        stp->eoc_q = eoc.q; stp->eoc_r = eoc.r;
+        stp->eoc_next_active = eoc_next; stp->active_cell = active_cell;
+        stp->event_counter = ev;
+        stp->kept_kind = kept_kind; stp->kept_target = kept_target;
+        stp->kept_q = kept_time.q; stp->kept_r = kept_time.r;
+        stp->kept_rate = kept_rate; stp->kept_position = kept_pos; stp->kept_root_position = kept_root;
+        stp->kept_stamp_q = kept_stamp.q; stp->kept_stamp_r = kept_stamp.r;
+        S.n_surplus[chain] = n_surplus;
+        if (A.stats) {
+            unsigned long long *st = reinterpret_cast<unsigned long long *>(A.stats);
+            if (n_events) atomicAdd(st + 0, (unsigned long long)n_events);
+            if (n_pair) atomicAdd(st + 1, (unsigned long long)n_pair);
+            if (n_veto) atomicAdd(st + 2, (unsigned long long)n_veto);
+            if (n_boundary) atomicAdd(st + 4, (unsigned long long)n_boundary);
+            if (n_eoc) atomicAdd(st + 5, (unsigned long long)n_eoc);
+            if (n_candidates) atomicAdd(st + 6, n_candidates);
+            if (n_bond) atomicAdd(st + 9, (unsigned long long)n_bond);
+            if (n_factor) atomicAdd(st + 10, (unsigned long long)n_factor);
+        }
+    }
+}
+
+// start of run for molecules: the cells hold the ROOT units (SingleActiveCellOccupancy.initialize with cell_level = 1,
+// single_active_cell_occupancy.py:95-121), the active unit on the cell level is the root of the initial active leaf
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams,
+                      uint32_t first_stream, int initial_active, int initial_direction, EcmcStats *stats) {
+    const int lane = threadIdx.x & 31;
+    const int chain = S.first_chain + blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (chain >= S.first_chain + S.n_chains) return;
+    const int npr = P.nodes_per_root, n_roots = P.n_particles / npr;
+    const Particle *roots = S.roots + (size_t)chain * n_roots;
+    int *occ = S.occupants + (size_t)chain * P.n_cells;
+    int *sur = S.surplus + (size_t)chain * P.max_surplus;
+    for (int i = lane; i < P.n_cells; i += 32) occ[i] = -1;
+    __syncwarp();
+    if (lane == 0) {
+        int n_surplus = 0, overflow = 0;
+        for (int r = 0; r < n_roots; r++) {
+            int id[3];
+            cell_identifier_of(P, roots[r], id);
+            const int delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, flat_cell(P, id), r);
+            if (delta == 2) overflow++; else n_surplus += delta;
+        }
+        EcmcChainState st;
+        st.active = initial_active; st.direction = initial_direction;
+        st.time_q = 0.0; st.time_r = 0.0;
+        st.event_counter = 0;
+        st.stream = streams ? streams[chain] : first_stream + (uint32_t)chain;
+        int id[3];
+        cell_identifier_of(P, roots[initial_active / npr], id);
+        st.active_cell = flat_cell(P, id);
+        const int delta = occupancy_remove(occ, sur, n_surplus, 1, st.active_cell, initial_active / npr);
+        if (delta == 2) overflow++; else n_surplus += delta;
+        const Time now = {0.0, 0.0};
+        const Time eoc = time_add(now, time_sub(now, now) + P.chain_time);
+        st.eoc_q = eoc.q; st.eoc_r = eoc.r;
+        const StreamKey key = {P.seed, st.stream, 0ull};
+        st.eoc_next_active = draw_end_of_chain_active(P, key);
+        st.pending_kind = ECMC_EVENT_NONE; st.pending_target = 0; st.reserved = 0;
+        st.pending_q = 0.0; st.pending_r = 0.0; st.pending_rate = 0.0; st.pending_position = 0.0;
+        st.pending_stamp_q = 0.0; st.pending_stamp_r = 0.0; st.pending_root_position = 0.0;
+        st.kept_kind = ECMC_EVENT_NONE; st.kept_target = 0; st.kept_q = 0.0; st.kept_r = 0.0; st.kept_rate = 0.0;
+        st.kept_position = 0.0; st.kept_root_position = 0.0; st.kept_stamp_q = 0.0; st.kept_stamp_r = 0.0;
+        S.chains[chain] = st;
+        S.n_surplus[chain] = n_surplus;
+        if (overflow && stats) atomicAdd(reinterpret_cast<unsigned long long *>(stats) + 8, (unsigned long long)overflow);
+    }
+}
+
+}  // namespace ecmc

@@ -115,7 +115,7 @@ def _compare_batch_with_oracle(oracle, pb, positions, charges, n_events, first_s
         chain.start(stream=first_stream + c)
         chains.append(chain)
     total = dict.fromkeys(["events", "pair_events", "veto_events", "veto_accepted", "boundary_events",
-                           "end_of_chain_events", "candidates", "bond_events"], 0)
+                           "end_of_chain_events", "candidates", "bond_events", "factor_pair_events"], 0)
     segment = resync_every or n_events
     with engine.Engine(pb, n_chains=n_chains) as eng:
         eng.upload_positions(positions, charges)
@@ -276,6 +276,57 @@ def test_hard_disk_dipoles_reference_trace():
         rec, stats = eng.run_recorded(max_events=120, records_per_chain=120)
         assert_records_match(rec[0], records[:120], length, "dipole trace")
         assert stats["bond_events"] > 5 and stats["capacity_errors"] == 0
+
+
+@pytest.mark.parametrize("name", tu.WATER_TRACES)
+def test_water_reference_trace_replay(name):
+    """C4: the shipped water/coulomb_cell_veto_lj_inverted.ini recorded from the running reference (composite-object
+    Coulomb pair and cell-veto events with inside-first lifting, Lennard-Jones between the oxygens, harmonic bonds,
+    bending with ratio lifting, root-level cells, factors kept across root cell-boundary events): every event of the
+    trace and the reference's snapshots of leaves, roots and cell occupancy."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    with engine.Engine(tu.water_builder_of(g, ProgramBuilder), n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None], g["charges"][None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        done = 0
+        snaps = list(g["snap_event"])
+        for k, event in enumerate(snaps + [len(records)]):
+            count = int(event) - done
+            if count:
+                rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+                assert stats["events"] == count and stats["capacity_errors"] == 0
+                assert_records_match(rec[0], records[done:event], length, f"{name}[{done}:{event}]")
+            done = int(event)
+            if k < len(snaps):
+                assert np.max(np.abs(eng.download_positions()[0] - g["snap_positions"][k])) < RTOL * length
+                assert np.max(np.abs(eng.download_roots()[0] - g["snap_roots"][k])) < RTOL * length
+                occ, surplus = eng.cells()
+                assert np.array_equal(occ[0], g["snap_occupants"][k])
+        assert np.max(np.abs(eng.download_positions()[0] - g["final_positions"])) < RTOL * length
+        assert np.max(np.abs(eng.download_roots()[0] - g["final_roots"])) < RTOL * length
+
+
+def test_water_batch_against_oracle(oracle):
+    """Seeded water chains (12 molecules, the dense geometry of trace_water_dense with the reference's own cell-veto
+    tables) against the oracle, event by event, including surplus molecules (more molecules than a cell holds)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import configs
+    g = tu.load_trace("trace_water_dense")
+    pb = tu.water_builder_of(g, ProgramBuilder)
+    n_chains, n_roots = 5, int(g["meta_n"]) // 3
+    roots = np.empty((n_chains, n_roots, 3))
+    leaves = np.empty((n_chains, 3 * n_roots, 3))
+    for c in range(n_chains):
+        r, l = configs.water_start(n_roots, float(g["meta_system_length"]), seed=40 + c, jitter=0.2 + 0.1 * c)
+        roots[c], leaves[c] = r, l.reshape(-1, 3)
+    charges = np.tile(g["charges"], (n_chains, 1))
+    stats = _compare_batch_with_oracle(oracle, pb, leaves, charges, 1500, 60, "water", roots=roots)
+    assert stats["pair_events"] > 300 and stats["veto_events"] > 2000 and stats["bond_events"] > 100
+    assert stats["factor_pair_events"] > 100
 
 
 def test_single_particle_chain(oracle):
