@@ -93,7 +93,18 @@ def potential_descriptor(potential):
                                       potential._fourier_cutoff, potential._position_cutoff)
     if "InversePowerCoulombBoundingPotential" in names:
         return abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, potential._prefactor)
+    if "BendingPotential" in names:
+        return abi.EcmcPotential.make(abi.POT_BENDING, potential._prefactor, potential._equilibrium_angle)
     raise _configuration_error("potential {0} has no device implementation".format(type(potential).__name__))
+
+
+def _lifting_kind(lifting):
+    names = _class_names(lifting)
+    for name, kind in (("InsideFirstLifting", abi.LIFTING_INSIDE_FIRST), ("OutsideFirstLifting", abi.LIFTING_OUTSIDE_FIRST),
+                       ("RatioLifting", abi.LIFTING_RATIO)):
+        if name in names:
+            return kind
+    raise _configuration_error("lifting scheme {0} has no device implementation".format(type(lifting).__name__))
 
 
 def _same_potential(a, b):
@@ -140,10 +151,9 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
     cells = occupancy.cells
     if "CuboidPeriodicCells" not in _class_names(cells):
         raise _configuration_error("cells must be CuboidPeriodicCells")
-    if occupancy.cell_level != levels:
-        raise _configuration_error("the cells must hold leaf units (cell_level = number of node levels); composite "
-                                   "objects in root-level cells (water, dipoles of 2018_JCP_149_064113) need the "
-                                   "composite-object handlers")
+    molecules = levels == 2 and occupancy.cell_level == 1  # composite objects in root-level cells (water)
+    if occupancy.cell_level != levels and not molecules:
+        raise _configuration_error("cell_level must be 1 or the number of node levels")
     max_occupants = occupancy._maximum_number_occupants  # cell_occupancy.py:70-72
     unbounded = max_occupants <= 0
     if unbounded:
@@ -156,7 +166,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
 
     # ---- handlers by kind
     pair_handlers, veto_handlers, boundary_handlers, eoc_handlers, start_handlers, control = [], [], [], [], [], []
-    bounding_handlers, bond_handlers = [], []
+    bounding_handlers, bond_handlers, bending_handlers = [], [], []
     # handlers fed by a factor type map are intramolecular factors (factor_type_map_in_state_tagger.py:83-107)
     factor_tagger_of = {}
     for tagger in activator._taggers:
@@ -166,15 +176,20 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
     for handler in activator.get_event_handlers():
         names = _class_names(handler)
         if id(handler) in factor_tagger_of:
-            if "TwoLeafUnitEventHandler" not in names:
+            if "FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential" in names:
+                bending_handlers.append(handler)
+            elif "TwoLeafUnitEventHandler" in names:
+                bond_handlers.append(handler)
+            else:
                 raise _configuration_error("factor-type-map handler {0} has no device implementation"
                                            .format(type(handler).__name__))
-            bond_handlers.append(handler)
+        elif "TwoCompositeObjectSummedBoundingPotentialEventHandler" in names:
+            pair_handlers.append(handler)
         elif "TwoLeafUnitCellBoundingPotentialEventHandler" in names:
             bounding_handlers.append(handler)
         elif "TwoLeafUnitBoundingPotentialEventHandler" in names or "TwoLeafUnitEventHandler" in names:
             pair_handlers.append(handler)
-        elif "LeafUnitCellVetoEventHandler" in names:
+        elif "LeafUnitCellVetoEventHandler" in names or "CompositeObjectCellVetoEventHandler" in names:
             veto_handlers.append(handler)
         elif "CellBoundaryEventHandler" in names:
             boundary_handlers.append(handler)
@@ -209,32 +224,85 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                              chain_time=eoc._chain_time, speed=velocity[moving[0]], initial_direction=moving[0],
                              initial_active=initial_leaf, seed=seed)
 
-    # ---- composite point objects: intramolecular pair factors of the factor type map
+    # ---- composite point objects: factors of the factor type map
+    inter_factors, inter_potential, bending = [], None, None
     if levels == 2:
         bonds, bond_potential = [], None
         for handler in bond_handlers:
             factor_map = factor_tagger_of[id(handler)]._factor_type_map
-            if not getattr(factor_map, "_local", False):
-                raise _configuration_error("only local (intramolecular) factor type maps are supported")
             if _charge_name(handler._charges) is not None:
-                raise _configuration_error("intramolecular factors with charges are not supported")
+                raise _configuration_error("factor-type-map pair factors with charges are not supported")
             potential = potential_descriptor(handler._potential)
-            if bond_potential is not None and not _same_potential(bond_potential, potential):
-                raise _configuration_error("all intramolecular pair factors must share one potential")
-            bond_potential = potential
-            for entries in factor_map.map.values():
+            local = getattr(factor_map, "_local", None)
+            if local is None:
+                raise _configuration_error("a factor type map without entries in the factor set file is not supported")
+            if local:
+                if bond_potential is not None and not _same_potential(bond_potential, potential):
+                    raise _configuration_error("all intramolecular pair factors must share one potential")
+                bond_potential = potential
+            else:
+                if not molecules:
+                    raise _configuration_error("factors between composite objects need root-level cells")
+                if inter_potential is not None and not _same_potential(inter_potential, potential):
+                    raise _configuration_error("all pair factors between composite objects must share one potential")
+                inter_potential = potential
+            for child, entries in factor_map.map.items():
                 for indices in entries:
                     if len(indices) != 2:
-                        raise _configuration_error("only two-unit intramolecular factors are supported")
-                    if tuple(sorted(indices)) not in bonds:
-                        bonds.append(tuple(sorted(indices)))
+                        raise _configuration_error("only two-unit factors are supported by the pair handlers")
+                    if local:
+                        if tuple(sorted(indices)) not in bonds:
+                            bonds.append(tuple(sorted(indices)))
+                    else:
+                        # "[1, 4]": the active child `child` against child (other - nodes_per_root) of every other object
+                        other = [index for index in indices if index >= nodes_per_root]
+                        own = [index for index in indices if index < nodes_per_root]
+                        if len(other) != 1 or own != [child]:
+                            raise _configuration_error("unsupported factor between composite objects: {0}".format(indices))
+                        pair = (child, other[0] - nodes_per_root)
+                        if pair not in inter_factors:
+                            inter_factors.append(pair)
         builder.set_composite(nodes_per_root, bonds, bond_potential)
-    elif bond_handlers:
+        if bending_handlers:
+            first = bending_handlers[0]
+            factor_map = factor_tagger_of[id(first)]._factor_type_map
+            entries = {tuple(indices) for lists in factor_map.map.values() for indices in lists}
+            if len(entries) != 1 or len(next(iter(entries))) != 3 or not getattr(factor_map, "_local", False):
+                raise _configuration_error("exactly one local three-unit (bending) factor is supported")
+            bending = dict(children=list(next(iter(entries))), separations=list(first._separations),
+                           potential=potential_descriptor(first._potential), offset=first._offset,
+                           max_displacement=first._max_displacement, lifting=_lifting_kind(first._lifting))
+            if bending["potential"].kind != abi.POT_BENDING or not molecules:
+                raise _configuration_error("the three-unit factor must be a bending potential in root-level cells")
+    elif bond_handlers or bending_handlers:
         raise _configuration_error("factor type maps need composite point objects")
 
     # ---- pair factor
     charge_names = set()
-    if pair_handlers:
+    composite_lifting = None
+    if pair_handlers and "TwoCompositeObjectSummedBoundingPotentialEventHandler" in _class_names(pair_handlers[0]):
+        # two_composite_object_summed_bounding_potential_event_handler.py:65-117
+        if not molecules:
+            raise _configuration_error("composite-object pair handlers need root-level cells")
+        first = pair_handlers[0]
+        potential = potential_descriptor(first._potential)
+        bounding = potential_descriptor(first._bounding_potential)
+        charge = _charge_name(first._potential_charges)
+        composite_lifting = _lifting_kind(first._lifting)
+        for handler in pair_handlers[1:]:
+            if "TwoCompositeObjectSummedBoundingPotentialEventHandler" not in _class_names(handler) or \
+                    not _same_potential(potential, potential_descriptor(handler._potential)) or \
+                    not _same_potential(bounding, potential_descriptor(handler._bounding_potential)) or \
+                    _charge_name(handler._potential_charges) != charge or \
+                    _charge_name(handler._bounding_potential_charges) != charge or \
+                    _lifting_kind(handler._lifting) != composite_lifting:
+                raise _configuration_error("nearby and surplus composite-object handlers must be alike")
+        builder.set_pair(abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, potential, bounding, use_charge=charge is not None)
+        if charge is not None:
+            charge_names.add(charge)
+    elif pair_handlers:
+        if molecules:
+            raise _configuration_error("leaf-unit pair handlers in root-level cells are not supported")
         first = pair_handlers[0]
         bounded = "TwoLeafUnitBoundingPotentialEventHandler" in _class_names(first)
         potential = potential_descriptor(first._potential)
@@ -305,6 +373,29 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                                   target_charge=1.0 if target_charge is None else target_charge)
         if charge is not None:
             charge_names.add(charge)
+    # ---- molecules: lifting scheme of the composite-object handlers, factors between objects, bending
+    if molecules:
+        if bounding_handlers:
+            raise _configuration_error("cell-bounding handlers for composite objects are not supported")
+        if veto_handlers:
+            if "CompositeObjectCellVetoEventHandler" not in _class_names(veto_handlers[0]):
+                raise _configuration_error("root-level cells need the composite-object cell-veto handler")
+            veto_lifting = _lifting_kind(veto_handlers[0]._lifting)
+            if composite_lifting is not None and veto_lifting != composite_lifting:
+                raise _configuration_error("the composite-object handlers must share one lifting scheme")
+            composite_lifting = veto_lifting
+        # Does a cell-boundary event of the root trash the leaf-level factor handlers? (tag lists, tagger.py:163-200)
+        boundary_tagger = [tagger for tagger in activator._taggers
+                           if any(handler is boundary_handlers[0] for handler in tagger.get_event_handlers())][0]
+        factor_tags = {tagger.tag for tagger in factor_tagger_of.values()}
+        trashed = set(boundary_tagger.trashes)
+        if factor_tags and factor_tags & trashed and not factor_tags <= trashed:
+            raise _configuration_error("a cell-boundary event must trash all or none of the factor-type-map handlers")
+        builder.set_molecules(composite_lifting if composite_lifting is not None else abi.LIFTING_INSIDE_FIRST,
+                              inter_factors=inter_factors, inter_potential=inter_potential, bending=bending,
+                              boundary_keeps_factors=not (factor_tags and factor_tags <= trashed))
+    elif veto_handlers and "CompositeObjectCellVetoEventHandler" in _class_names(veto_handlers[0]):
+        raise _configuration_error("the composite-object cell-veto handler needs root-level cells")
     if len(charge_names) > 1:
         raise _configuration_error("pair and cell-veto handlers use different charges: {0}".format(sorted(charge_names)))
     return CompiledProgram(builder, charge_names.pop() if charge_names else None, control, n_particles, nodes_per_root)

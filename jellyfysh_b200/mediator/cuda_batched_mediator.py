@@ -45,7 +45,8 @@ class CudaBatchedMediator(Mediator):
 
     def __init__(self, input_output_handler: InputOutputHandler, state_handler: StateHandler, scheduler: Scheduler,
                  activator: Activator, number_of_chains: int = 1, device: int = 0, seed: int = 0,
-                 first_random_stream: int = 0, maximum_surplus: int = 0, occupant_capacity: int = 8) -> None:
+                 first_random_stream: int = 0, maximum_surplus: int = 0, occupant_capacity: int = 8,
+                 events_per_launch: int = 4000000) -> None:
         """
         Parameters follow SingleProcessMediator (single_process_mediator.py:57-72); in addition:
 
@@ -54,6 +55,9 @@ class CudaBatchedMediator(Mediator):
         seed, first_random_stream : chain c reads the counter-based random stream (seed, first_random_stream + c).
         maximum_surplus : capacity of the per-chain surplus list (0: one slot per particle).
         occupant_capacity : occupants per cell kept on the device when the reference's cell occupancy is unbounded.
+        events_per_launch : upper limit of events per chain and kernel launch; a chain that needs more to reach the
+            next control time is continued by further launches, and one that stops advancing in time (a collapsing
+            configuration, e.g. overlapping molecules with unbounded attraction) raises an error instead of hanging.
         """
         self._logger = logging.getLogger(__name__)
         if number_of_chains < 1:
@@ -85,6 +89,7 @@ class CudaBatchedMediator(Mediator):
         self._engine.start(first_stream=first_random_stream)
         self._statistics = {}
         self._control_times = {}
+        self._events_per_launch = max(int(events_per_launch), 1)
 
     # ---- state hand-over to the reference's state handler ------------------------------------------------------
     def _load_chain_into_state_handler(self, chain, positions, states, roots=None):
@@ -139,9 +144,7 @@ class CudaBatchedMediator(Mediator):
         while True:
             handler = min(controls, key=lambda h: self._control_times[h])
             event_time = self._control_times[handler]
-            self._engine.run(until=(event_time.quotient, event_time.remainder))
-            for key, value in self._engine.sync().items():
-                self._statistics[key] = self._statistics.get(key, 0) + value
+            self._advance_to(event_time)
             self._event_handler_with_shortest_event_time = handler
             names = {cls.__name__ for cls in type(handler).__mro__}
             if "EndOfRunEventHandler" in names:
@@ -151,6 +154,27 @@ class CudaBatchedMediator(Mediator):
                 raise EndOfRun
             self._write_output(handler)
             self._control_times[handler] = handler.send_event_time()
+
+    def _advance_to(self, event_time):
+        """ecmc_run(until = event_time), in launches of at most events_per_launch events per chain."""
+        until = (event_time.quotient, event_time.remainder)
+        stalled = 0
+        while True:
+            before = self._engine.chain_states()
+            self._engine.run(until=until, max_events=self._events_per_launch)
+            stats = self._engine.sync()
+            for key, value in stats.items():
+                self._statistics[key] = self._statistics.get(key, 0) + value
+            after = self._engine.chain_states()
+            behind = (after["time_q"] != until[0]) | (after["time_r"] != until[1])
+            if not behind.any():
+                return
+            advanced = (after["time_q"] - before["time_q"]) + (after["time_r"] - before["time_r"])
+            stalled = stalled + 1 if float(np.min(advanced[behind])) < 1.0e-9 else 0
+            if stalled >= 3:
+                chain = int(np.nonzero(behind)[0][0])
+                raise RuntimeError("chain {0} does not advance in time any more ({1} events per launch): "
+                                   "collapsing configuration?".format(chain, self._events_per_launch))
 
     @property
     def statistics(self):

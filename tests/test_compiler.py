@@ -152,6 +152,50 @@ def test_hard_disk_dipole_graph_compiles_and_replays(oracle):
         setting.reset()
 
 
+def test_water_graph_compiles_and_replays(oracle):
+    """C4: the shipped water/coulomb_cell_veto_lj_inverted.ini -> compiler -> oracle chain reproduces the reference's
+    recorded run bit for bit (the cell-veto tables are those the reference built, from the fixture: the dipole Monte
+    Carlo estimator draws random numbers)."""
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_water")
+    n_roots = len(g["roots0"])
+    composites = (g["roots0"], g["positions0"].reshape(n_roots, 3, 3))
+    mediator, setting = build_reference_graph(configs.water_ini(REF, n_molecules=n_roots, number_trials=2,
+                                                                end_of_run_time=50.0), composites=composites)
+    try:
+        template = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, template, seed=int(g["seed"][0]))
+        p = compiled.builder.program
+        assert (p.dimension, p.n_particles, p.nodes_per_root, p.cell_level, p.neighbor_layers) == (3, 96, 3, 1, 2)
+        assert p.pair_handler == abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING and p.composite_lifting == abi.LIFTING_INSIDE_FIRST
+        assert p.pair_potential.kind == abi.POT_MERGED_IMAGE_COULOMB and p.pair_potential.params[0] == 332.0
+        assert p.pair_bounding_potential.kind == abi.POT_INVERSE_POWER_COULOMB_BOUNDING
+        assert p.veto_enabled == abi.FAR_CELL_VETO and p.veto_use_charge == 1 and compiled.charge_name == "electric_charge"
+        assert p.n_bonds == 2 and sorted((p.bonds[i][0], p.bonds[i][1]) for i in range(2)) == [(0, 1), (1, 2)]
+        assert p.bond_potential.kind == abi.POT_DISPLACED_EVEN_POWER
+        assert p.n_inter_factors == 1 and (p.inter_factors[0][0], p.inter_factors[0][1]) == (1, 1)
+        assert p.inter_potential.kind == abi.POT_LENNARD_JONES
+        assert p.bending_enabled == 1 and p.bending_lifting == abi.LIFTING_RATIO
+        assert list(p.bending_children) == [0, 1, 2] and list(p.bending_separations) == [1, 0, 1, 2]
+        assert (p.bending_offset, p.bending_max_displacement) == (10.0, 0.112321434)
+        assert p.boundary_keeps_factors == 1 and p.initial_active == 1
+        positions, charges, roots = compiler.positions_and_charges(template, compiled.charge_name)
+        assert np.array_equal(positions, g["positions0"]) and np.array_equal(roots, g["roots0"])
+        assert np.array_equal(charges, g["charges"])
+        # the fixture's tables (1000 -> 200 trials there, 2 here) replace the freshly estimated ones
+        compiled.builder.set_veto(compiled.builder.program.veto_potential, tu.reference_tables(g), use_charge=True,
+                                  target_charge=1.0)
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions, charges)
+        chain.set_roots(roots)
+        chain.start(stream=int(g["seed"][1]))
+        n, rec = chain.run(max_events=2000, record=2000)
+        assert n == 2000 and tu.records_equal_discrete(rec, g["records"][:2000])
+        assert np.array_equal(rec["time_r"], g["records"]["time_r"][:2000])
+    finally:
+        setting.reset()
+
+
 def test_unsupported_graphs_are_rejected(lj_graph):
     """A graph the device cannot run faithfully is refused, never approximated."""
     from jellyfysh.base.exceptions import ConfigurationError

@@ -252,3 +252,48 @@ def test_hard_disk_dipoles_polarization_statistics(tmp_path):
         print(key, "KS distance", distance, "samples", len(samples))
         # Kolmogorov-Smirnov at the 0.1 % level, counting a conservative 10 independent samples per chain
         assert distance < 1.95 / np.sqrt(chains * 10) + 5.0e-3, (key, distance)
+
+
+def test_shipped_water_config_matches_reference_statistics(tmp_path):
+    """C4 statistical check: the shipped water/coulomb_cell_veto_lj_inverted.ini (two SPC/Fw molecules),
+    unchanged except for the mediator line, the run length, the sampling interval and the output file, run as many
+    independent device chains, reproduces the cumulative histogram of the oxygen-oxygen separation the reference ships
+    (ReferenceOOSeparation.dat; fixture tests/golden/reference_cdfs.npz)."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import kat_replay as kr
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    chains, end, interval = 1024, 2000.0, 20.0
+    ini = configs.water_ini(REF, n_molecules=2, end_of_run_time=end, sampling_interval=interval,
+                            output=str(tmp_path / "oo_separation.dat"))
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 29" % chains)
+    assert "number_trials = 1000" in ini and "number_of_root_nodes = 2" in ini
+    # Every chain starts from its own pair of well separated molecules: the random input handler of the shipped file
+    # can put a hydrogen next to the other oxygen, which has no repulsive core for it -- such a chain collapses (event
+    # rate -> infinity) in the reference as well.
+    starts = [configs.water_start(2, 10.0, seed=500 + c) for c in range(chains)]
+    composites = (np.concatenate([r for r, _ in starts]), np.concatenate([l for _, l in starts]))
+    mediator, setting = build_reference_graph(ini, composites=composites)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["capacity_errors"] == 0 and stats["bond_events"] > 0 and stats["veto_events"] > 0
+    samples = np.loadtxt(tmp_path / "oo_separation.dat", comments="#")
+    per_chain = int(end / interval)
+    assert len(samples) == chains * per_chain
+    samples = samples.reshape(per_chain, chains)[per_chain // 2:].ravel()  # random starts: let the pairs find each other
+    ref = kr.load_npz("reference_cdfs")
+    x, cdf = ref["water_oo_x"], ref["water_oo_cdf"]
+    edges = x + 0.5 * (x[1] - x[0])
+    ours = np.searchsorted(np.sort(samples), edges, side="right") / len(samples)
+    distance = np.max(np.abs(ours - cdf))
+    print("water O-O KS distance", distance, "samples", len(samples), "median", np.median(samples), stats)
+    assert distance < 1.95 / np.sqrt(chains * 5) + 5.0e-3, distance
