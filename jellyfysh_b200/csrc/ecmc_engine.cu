@@ -445,15 +445,21 @@ typedef void (*EventKernel)(const DeviceProgram, const DeviceState, const RunArg
 template <int CAND, int REAL, int VETO>
 EventKernel pick_record(bool record, bool single) {
     if (single)
-        return record ? event_kernel<CAND, REAL, VETO, true, true, kWarpsPerBlock, false>
-                      : event_kernel<CAND, REAL, VETO, true, false, kWarpsPerBlock, false>;
-    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock, false>
-                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock, false>;
+        return record ? event_kernel<CAND, REAL, VETO, true, true, kWarpsPerBlock, false, false>
+                      : event_kernel<CAND, REAL, VETO, true, false, kWarpsPerBlock, false, false>;
+    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock, false, false>
+                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock, false, false>;
 }
 template <int CAND, int REAL, int VETO>
 EventKernel pick_composite(bool record) {
-    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock, true>
-                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock, true>;
+    return record ? event_kernel<CAND, REAL, VETO, false, true, kWarpsPerBlock, true, false>
+                  : event_kernel<CAND, REAL, VETO, false, false, kWarpsPerBlock, true, false>;
+}
+// cell-bounding far field: the reference's handler needs one occupant per cell (SINGLE)
+template <int CAND, int REAL, int VETO>
+EventKernel pick_far_pairs(bool record) {
+    return record ? event_kernel<CAND, REAL, VETO, true, true, kWarpsPerBlock, false, true>
+                  : event_kernel<CAND, REAL, VETO, true, false, kWarpsPerBlock, false, true>;
 }
 
 EventKernel pick_kernel(const DeviceProgram &d, bool record) {
@@ -467,6 +473,11 @@ EventKernel pick_kernel(const DeviceProgram &d, bool record) {
         // composite point objects: hard disks / spheres tethered into dipoles (C1), anything else generic
         if (cand == HS && real == 0 && veto == 0) return pick_composite<ECMC_POT_HARD_SPHERE, 0, 0>(record);
         return pick_composite<-1, -1, -1>(record);
+    }
+    if (d.veto_enabled == ECMC_FAR_CELL_BOUNDING) {
+        if (cand == IPCB && real == MIC && veto == MIC)
+            return pick_far_pairs<ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, ECMC_POT_MERGED_IMAGE_COULOMB, ECMC_POT_MERGED_IMAGE_COULOMB>(record);
+        return pick_far_pairs<-1, -1, -1>(record);
     }
     if (cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record, single);
     if (cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record, single);

@@ -256,7 +256,9 @@ ECMC_D int draw_end_of_chain_active(const DeviceProgram &P, const StreamKey &key
 // COMPOSITE: the point masses are leaves of composite point objects (EcmcProgram.nodes_per_root > 1): the root unit of
 // the active leaf is time-sliced with it, and the factor-type-map pair factors inside the active leaf's object
 // (EcmcProgram.bonds) are extra candidates.
-template <int CAND, int REAL, int VETO, bool SINGLE, bool RECORD, int WARPS, bool COMPOSITE>
+// FAR_PAIRS: the far field is ECMC_FAR_CELL_BOUNDING (one candidate per occupied non-nearby cell) instead of the
+// cell veto. Both switches are compile-time so that the Lennard-Jones / cell-veto kernel carries none of their code.
+template <int CAND, int REAL, int VETO, bool SINGLE, bool RECORD, int WARPS, bool COMPOSITE, bool FAR_PAIRS>
 __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     __shared__ double trig_all[UsesMic<REAL, VETO>::value ? WARPS * kTrigDoubles : 1];
@@ -311,8 +313,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     const double L = P.length, half = P.half_length, speed = P.speed;
     const bool has_pairs = P.pair_handler != ECMC_PAIR_NONE;
     const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
-    const bool has_veto = VETO != 0 && P.veto_enabled == ECMC_FAR_CELL_VETO;
-    const bool has_far_pairs = VETO != 0 && P.veto_enabled == ECMC_FAR_CELL_BOUNDING;
+    const bool has_veto = VETO != 0 && !FAR_PAIRS && P.veto_enabled == ECMC_FAR_CELL_VETO;
+    const bool has_far_pairs = VETO != 0 && FAR_PAIRS;
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
 
     Counters n = {0, 0, 0, 0, 0ull};
@@ -335,7 +337,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             bkind = stp->pending_kind;
             bt.q = stp->pending_q; bt.r = stp->pending_r;
             brate = stp->pending_rate;
-            if (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING || bkind == ECMC_EVENT_BOND)
+            if (bkind == ECMC_EVENT_PAIR || (FAR_PAIRS && bkind == ECMC_EVENT_CELL_BOUNDING) ||
+                (COMPOSITE && bkind == ECMC_EVENT_BOND))
                 btarget = stp->pending_target;
             else bcell = stp->pending_target;
             kept_position = stp->pending_position;
@@ -356,7 +359,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             const int n_bond_slots = COMPOSITE ? P.n_bonds : 0;
             const int far_base = n_pair_slots + n_bond_slots;
             const int n_scan_slots = far_base + (has_far_pairs ? P.n_cells : 0);
-            const int special_seq = far_base + P.n_cells;
+            const int special_seq = FAR_PAIRS ? far_base + P.n_cells : far_base;
             const double c_active = P.pair_use_charge ? a.charge : 1.0;
             unsigned long long best_key = 0x7ff0000000000000ull;  // best of the passes so far (uniform)
             double best_x = INFINITY;
@@ -384,7 +387,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     const int root = active / P.nodes_per_root, child = active - root * P.nodes_per_root;
                     const int partner = P.bonds[b][0] == child ? P.bonds[b][1] : (P.bonds[b][1] == child ? P.bonds[b][0] : -1);
                     if (partner >= 0) found = root * P.nodes_per_root + partner;
-                } else if (s < n_scan_slots) {
+                } else if (FAR_PAIRS && s < n_scan_slots) {
                     const int cell = s - far_base;
                     if (!cell_is_nearby(P, cell, cid0, cid1, cid2)) found = occ[cell];
                 }
@@ -435,7 +438,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     s2 = correct_separation_in_box(tp.p2 - a.p2, L, half);
                 }
                 if (base > 0 || !first) {
-                    const bool alive = is_pair && (s >= n_pair_slots || !certainly_dead<CAND>(P.cand_potential, s0, s1, s2,
+                    const bool alive = is_pair && (((COMPOSITE || FAR_PAIRS) && s >= n_pair_slots) || !certainly_dead<CAND>(P.cand_potential, s0, s1, s2,
                                                                         cand_needs_du ? u_first * P.inv_beta : 0.0));
                     if (!__any_sync(kFull, alive)) continue;
                 }
@@ -448,7 +451,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 double dt = INFINITY;
                 int kind = ECMC_EVENT_NONE, cell = -1, seq = kSeqNone;
                 double rate = 0.0;
-                const bool is_far = is_pair && s >= far_base;  // cell-bounding candidate
+                const bool is_far = FAR_PAIRS && is_pair && s >= far_base;  // cell-bounding candidate
                 if (is_bond) {
                     // TwoLeafUnitEventHandler.send_event_time with the factor's own potential
                     dt = displacement_time<-1>(P.bond_potential, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
@@ -573,8 +576,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 stp->pending_kind = bkind;
                 stp->pending_q = bt.q; stp->pending_r = bt.r;
                 stp->pending_rate = brate;
-                stp->pending_target = (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_CELL_BOUNDING ||
-                                       bkind == ECMC_EVENT_BOND) ? btarget : bcell;
+                stp->pending_target = (bkind == ECMC_EVENT_PAIR || (FAR_PAIRS && bkind == ECMC_EVENT_CELL_BOUNDING) ||
+                                       (COMPOSITE && bkind == ECMC_EVENT_BOND)) ? btarget : bcell;
                 if (!was_pending) {
                     stp->pending_position = a.p0;
                     if (COMPOSITE) stp->pending_root_position = root_p0;
@@ -657,6 +660,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         case ECMC_EVENT_CELL_BOUNDING: {
             // TwoLeafUnitCellBoundingPotentialEventHandler.send_out_state (:179-211): the stored bounding rate (times the
             // speed) against the real derivative, event_handler_with_bounding_potential.py:75-101
+            if (!FAR_PAIRS) break;
             rec_target = btarget;
             const Moving tp = rotate_in(part[btarget], dir);
             const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
@@ -676,6 +680,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         }
         case ECMC_EVENT_BOND: {
             // TwoLeafUnitEventHandler.send_out_state (two_leaf_unit_event_handler.py:140-154)
+            if (!COMPOSITE) break;
             rec_target = btarget;
             accepted = 1;
             new_active = btarget;
@@ -757,7 +762,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             // (single_independent_active_periodic_direction_end_of_chain_event_handler.py:203-237)
             eoc = time_add(now, time_sub(now, now) + P.chain_time);
             const StreamKey next_key = {P.seed, stream, ev};
-            eoc_next = draw_end_of_chain_active(P, next_key);
+            eoc_next = COMPOSITE ? draw_end_of_chain_active(P, next_key)
+                                 : (int)stream_randbelow(next_key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.n_particles);
         }
     }
 
@@ -782,9 +788,9 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             if (n.events) atomicAdd(st + 0, (unsigned long long)n.events);
             if (n.pair) atomicAdd(st + 1, (unsigned long long)n.pair);
             if (n.veto) atomicAdd(st + 2, (unsigned long long)n.veto);
-            const unsigned boundary = n.events - n.pair - n.veto - n.end_of_chain - n_bond_events;
+            const unsigned boundary = n.events - n.pair - n.veto - n.end_of_chain - (COMPOSITE ? n_bond_events : 0u);
             if (boundary) atomicAdd(st + 4, (unsigned long long)boundary);
-            if (n_bond_events) atomicAdd(st + 9, (unsigned long long)n_bond_events);
+            if (COMPOSITE && n_bond_events) atomicAdd(st + 9, (unsigned long long)n_bond_events);
             if (n.end_of_chain) atomicAdd(st + 5, (unsigned long long)n.end_of_chain);
             if (n.candidates) atomicAdd(st + 6, n.candidates);
         }
