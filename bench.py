@@ -246,7 +246,8 @@ def algorithmic_bytes_per_event(stats, args):
     """active position 8D + occupancy of the K nearby cells 4K + one 32-byte particle record per pair
     candidate + cell-veto target slot and record (4 + 32 when the cell is occupied; counted always) + write-back of the
     active position and time 8D + 16 + two occupancy updates 8."""
-    pair_candidates = stats["candidates"] / stats["events"] - 3.0  # minus veto, boundary, end-of-chain
+    # pair candidates = the targets gathered from the nearby cells and the surplus: the handler calls the reference makes
+    pair_candidates = stats["pair_targets"] / stats["events"]
     return 24.0 + 4.0 * 27 + 32.0 * pair_candidates + 36.0 + 40.0 + 8.0, pair_candidates
 
 

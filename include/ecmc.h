@@ -284,7 +284,8 @@ typedef struct EcmcStats {
     uint64_t capacity_errors;   /* surplus / occupant overflow (fatal: results invalid) */
     uint64_t bond_events;       /* events of the intramolecular factor-type-map factors (bonds + bending) */
     uint64_t factor_pair_events; /* events of the inter-object two-leaf factors */
-    uint64_t reserved[1];
+    uint64_t pair_targets;      /* pair targets gathered from nearby cells / surplus / far cells (event_kernel): the
+                                 * handler calls the reference would make, finite or not */
 } EcmcStats;
 
 typedef struct EcmcHandle EcmcHandle;

@@ -142,7 +142,7 @@ class EcmcStats(C.Structure):
                 ("veto_accepted", C.c_uint64), ("boundary_events", C.c_uint64),
                 ("end_of_chain_events", C.c_uint64), ("candidates", C.c_uint64),
                 ("bound_violations", C.c_uint64), ("capacity_errors", C.c_uint64),
-                ("bond_events", C.c_uint64), ("factor_pair_events", C.c_uint64), ("reserved", C.c_uint64 * 1)]
+                ("bond_events", C.c_uint64), ("factor_pair_events", C.c_uint64), ("pair_targets", C.c_uint64)]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}

@@ -209,7 +209,7 @@ ECMC_D int warp_argmin(unsigned long long key, int seq, int lane) {
 // capacity overflows) go straight to the global statistics, the boundary count is what remains of `events`.
 struct Counters {
     unsigned events, pair, veto, end_of_chain;
-    unsigned long long candidates;
+    unsigned long long candidates, targets;
 };
 ECMC_D void count_rare(const RunArgs &A, int lane, int index) {
     if (lane == 0 && A.stats) atomicAdd(reinterpret_cast<unsigned long long *>(A.stats) + index, 1ull);
@@ -263,10 +263,17 @@ __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     __shared__ double trig_all[UsesMic<REAL, VETO>::value ? WARPS * kTrigDoubles : 1];
     __shared__ int list_all[WARPS * 2 * kListCapacity];
+    // Most events change nothing but the position of the active particle (a rejected cell veto: nine out of ten for
+    // C2). The candidate list of such an event is the previous one, and so are the positions of its targets: the list
+    // stays in shared memory and the (rotated) positions of the first pass are cached next to it, so that an unchanged
+    // event costs neither the gather of the 27 nearby cells nor the two dependent L2 round trips behind it.
+    __shared__ double cache_all[WARPS * 4 * 32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chain = S.first_chain + blockIdx.x * WARPS + warp;
     if (chain >= S.first_chain + S.n_chains) return;
+    double *cache_p0 = cache_all + warp * 128, *cache_p1 = cache_p0 + 32, *cache_p2 = cache_p0 + 64, *cache_charge = cache_p0 + 96;
+    int cached_count = -1;  // >= 0: entries of the still valid list of the previous event
     double *trig = UsesMic<REAL, VETO>::value ? trig_all + warp * kTrigDoubles : trig_all;
     int *list_target = list_all + warp * 2 * kListCapacity;  // compacted candidates of the current event
     int *list_seq = list_target + kListCapacity;
@@ -311,13 +318,21 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
 
     const Time until = {A.until_q, A.until_r};
     const double L = P.length, half = P.half_length, speed = P.speed;
+    // Measured on B200 (C2): the two-phase pass makes the kernel SLOWER (4.6e8 vs 6.0e8 events/s): the special lanes'
+    // logarithm is no longer shared with the pair lanes and ptxas spills 770 instead of 470 bytes at 72 registers.
+    // Kept behind ECMC_PRUNE for the next round (profiles/README.md); the default build does not contain it.
+#ifdef ECMC_PRUNE
+    constexpr bool PRUNE = !RECORD && !COMPOSITE && !FAR_PAIRS && CAND == ECMC_POT_LENNARD_JONES;
+#else
+    constexpr bool PRUNE = false;
+#endif
     const bool has_pairs = P.pair_handler != ECMC_PAIR_NONE;
     const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
     const bool has_veto = VETO != 0 && !FAR_PAIRS && P.veto_enabled == ECMC_FAR_CELL_VETO;
     const bool has_far_pairs = VETO != 0 && FAR_PAIRS;
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
 
-    Counters n = {0, 0, 0, 0, 0ull};
+    Counters n = {0, 0, 0, 0, 0ull, 0ull};
     unsigned n_bond_events = 0;
     bool stopped_by_time = false;
 
@@ -366,8 +381,11 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             int best_seq = kSeqNone;
             int cursor = 0;      // next slot to scan
             bool first = true;   // the special candidates have not been processed yet
+            double d_star = INFINITY;  // PRUNE: no candidate beyond this displacement can win the event
             while (first || cursor < n_scan_slots) {
               int count = 0;  // entries in the compact list
+              const bool from_cache = first && cached_count >= 0;
+              if (from_cache) { count = cached_count; cursor = n_scan_slots; }
               while (cursor < n_scan_slots && count <= kListCapacity - 32) {
                 const int s = cursor + lane;
                 int found = -1;
@@ -401,6 +419,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 cursor += 32;
               }
               __syncwarp();
+              if (first) cached_count = cursor >= n_scan_slots ? count : -1;  // reusable if it is the whole list
+              n.targets += (unsigned long long)count;
               const int shift = first ? 2 : 0;
               for (int base = 0; base < count + shift; base += 32) {
                 const int entry = base + lane - shift;  // -2 = veto, -1 = boundary
@@ -410,7 +430,16 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const bool is_veto = entry == -2 && has_veto;
                 const bool is_boundary = entry == -1;
                 Moving tp;
-                if (is_pair) tp = rotate_in(part[target], dir);
+                if (is_pair) {
+                    if (from_cache && base == 0) {
+                        tp.p0 = cache_p0[lane]; tp.p1 = cache_p1[lane]; tp.p2 = cache_p2[lane]; tp.charge = cache_charge[lane];
+                    } else {
+                        tp = rotate_in(part[target], dir);
+                        if (first && base == 0) {
+                            cache_p0[lane] = tp.p0; cache_p1[lane] = tp.p1; cache_p2[lane] = tp.p2; cache_charge[lane] = tp.charge;
+                        }
+                    }
+                }
                 // One Philox block per lane, all lanes together: pair lanes draw their potential change (slot keyed
                 // by the target), the veto lane its (Walker uniform, time) pair, and the boundary lane -- which needs
                 // no random number -- computes the veto lane's table-index words.
@@ -437,13 +466,21 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     s1 = correct_separation_in_box(tp.p1 - a.p1, L, half);
                     s2 = correct_separation_in_box(tp.p2 - a.p2, L, half);
                 }
+                // PRUNE (Lennard-Jones, no event records): the first pass runs in two phases. Phase 0 evaluates the
+                // special lanes only; their earliest time, and the end of chain, bound how far the active particle can
+                // move in this event. Phase 1 evaluates the pair lanes -- but only if one of them may fire within that
+                // displacement (lj_may_fire_within: one division, no logarithm). In nine events out of ten none can,
+                // and the event costs neither the pair lanes' logarithm nor their inversion. The winner is unchanged;
+                // only the count of finite candidates (EcmcStats.candidates) then covers the evaluated lanes only.
+                const bool prune_first = PRUNE && first && base == 0;
+                bool alive = true;
                 if (base > 0 || !first) {
-                    const bool alive = is_pair && (((COMPOSITE || FAR_PAIRS) && s >= n_pair_slots) || !certainly_dead<CAND>(P.cand_potential, s0, s1, s2,
+                    alive = is_pair && (((COMPOSITE || FAR_PAIRS) && s >= n_pair_slots) || !certainly_dead<CAND>(P.cand_potential, s0, s1, s2,
                                                                         cand_needs_du ? u_first * P.inv_beta : 0.0));
+                    if (PRUNE)
+                        alive = alive && lj_may_fire_within(P.cand_potential.lj, s0, fma(s1, s1, s2 * s2), d_star, u_first * P.inv_beta);
                     if (!__any_sync(kFull, alive)) continue;
                 }
-                // random.expovariate(beta): pair lanes use their first double, the veto lane its second
-                const double exponential = -log_unit_interval(1.0 - (is_veto ? u_second : u_first)) * P.inv_beta;
                 // the table-index words travel from the boundary lane (lane 1 of pass 0) to the veto lane (lane 0)
                 uint32_t choice[4];
 #pragma unroll
@@ -452,6 +489,23 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 int kind = ECMC_EVENT_NONE, cell = -1, seq = kSeqNone;
                 double rate = 0.0;
                 const bool is_far = FAR_PAIRS && is_pair && s >= far_base;  // cell-bounding candidate
+                for (int phase = 0; phase < (prune_first ? 2 : 1); phase++) {
+                bool on = !PRUNE || alive;
+                if (prune_first) {
+                    if (phase == 0) {
+                        on = !is_pair;
+                    } else {
+                        const double x0 = __shfl_sync(kFull, now.r + dt, 0), x1 = __shfl_sync(kFull, now.r + dt, 1);
+                        const double eoc_x = (eoc.q - now.q) + eoc.r;
+                        const double t_rel = fmin(fmin(x0, x1), eoc_x) - now.r;
+                        d_star = fma(speed * t_rel, 1.0 + 1.0e-9, 1.0e-12);
+                        on = is_pair && lj_may_fire_within(P.cand_potential.lj, s0, fma(s1, s1, s2 * s2), d_star, u_first * P.inv_beta);
+                        if (!__any_sync(kFull, on)) break;
+                    }
+                }
+                if (!on) continue;
+                // random.expovariate(beta): pair lanes use their first double, the veto lane its second
+                const double exponential = -log_unit_interval(1.0 - (is_veto ? u_second : u_first)) * P.inv_beta;
                 if (is_bond) {
                     // TwoLeafUnitEventHandler.send_event_time with the factor's own potential
                     dt = displacement_time<-1>(P.bond_potential, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
@@ -535,6 +589,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     cell = next_cell;
                     kind = ECMC_EVENT_CELL_BOUNDARY;
                     seq = special_seq + 1;
+                }
                 }
                 // Time.__add__: event time = now + dt; x orders the candidates (see time_key)
                 const double x = now.r + dt;
@@ -731,6 +786,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
 
         // ---- SingleActiveCellOccupancy.update (single_active_cell_occupancy.py:149-203)
         if (new_active != active) {
+            cached_count = -1;
             int delta = 0;
             if (lane == 0) {
                 part[active] = lab;
@@ -751,6 +807,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             __syncwarp();
             boundary = next_boundary();
         } else if (kind == ECMC_EVENT_CELL_BOUNDARY || kind == ECMC_EVENT_END_OF_CHAIN || left_cell) {
+            cached_count = -1;
             // the oracle recomputes the cell from the position after every event; only these can change it
             a = rotate_in(lab, dir);
             cell_identifier_of(P, lab, cid0, cid1, cid2);
@@ -793,6 +850,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             if (COMPOSITE && n_bond_events) atomicAdd(st + 9, (unsigned long long)n_bond_events);
             if (n.end_of_chain) atomicAdd(st + 5, (unsigned long long)n.end_of_chain);
             if (n.candidates) atomicAdd(st + 6, n.candidates);
+            if (n.targets) atomicAdd(st + 11, n.targets);
         }
     }
 }

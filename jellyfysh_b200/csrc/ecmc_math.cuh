@@ -281,6 +281,23 @@ ECMC_D bool lj_certainly_dead(const LennardJones &p, double sd, double perp2, do
     return du_lower > -u_start * (1.0 + 1.0e-9);
 }
 
+// Can the Lennard-Jones candidate fire within the next `d` of displacement? `du_lower` <= the potential change it will
+// draw. False only if it certainly cannot: the stretch [0, d] holds neither the closest approach nor a crossing of the
+// minimum sphere, so the energy is monotonic along it and rises by U(end) - U(now), which one division gives; anything
+// else, and anything within the rounding margin, is left to the full computation.
+ECMC_D bool lj_may_fire_within(const LennardJones &p, double sd, double perp2, double d, double du_lower) {
+    if (!(d < INFINITY)) return true;
+    if (sd > 0.0 && !(d < sd)) return true;          // the closest approach lies inside the stretch
+    const double e = sd - d;
+    const double r2_now = fma(sd, sd, perp2), r2_end = fma(e, e, perp2);
+    if ((r2_now < p.r0sq) != (r2_end < p.r0sq)) return true;  // crosses the minimum sphere
+    const double inv = 1.0 / (r2_now * r2_end);
+    const double x_now = p.sigma2 * (inv * r2_end), x_end = p.sigma2 * (inv * r2_now);
+    const double x3_now = x_now * x_now * x_now, x3_end = x_end * x_end * x_end;
+    const double rise = p.k * (x3_end * (x3_end - 1.0) - x3_now * (x3_now - 1.0));
+    return !(rise + 1.0e-12 < du_lower * (1.0 - 1.0e-9));
+}
+
 // ---- hard sphere / hard dipole, general velocity (hard_sphere_potential.py:65-99, hard_dipole_potential.py:75-114)
 // Grazing collisions make the square-root term cancel to ~0, where one ulp of its inputs decides between a hit
 // and a miss. These few operations therefore follow the reference operation by operation: products and sums

@@ -7,7 +7,7 @@ are sum-reductions of event counters / sample histograms and the max-reduction o
 import numpy as np
 
 COUNTER_KEYS = ("events", "pair_events", "veto_events", "veto_accepted", "boundary_events", "end_of_chain_events",
-                "candidates", "bound_violations", "capacity_errors")
+                "candidates", "bound_violations", "capacity_errors", "bond_events", "factor_pair_events", "pair_targets")
 
 
 def chain_shard(rank, world_size, chains_per_rank):

@@ -390,6 +390,30 @@ def test_split_launches_equal_one_launch(oracle):
         assert two.kernel_launches == 3 and two.kernel_seconds > 0.0
 
 
+def test_pruned_launches_reach_the_same_state(oracle):
+    """The kernel instantiations with and without event records must commit the same events: identical positions, cells
+    and chain states bit for bit, the same event counts. (A build with -DECMC_PRUNE skips pair candidates that provably
+    cannot win in launches without records; then only the count of finite candidates may differ.)"""
+    pb, positions = _lj_batch(oracle, n_chains=64, n=100, cells=4, length=5.2, seed=14)
+    with engine.Engine(pb, n_chains=64) as pruned, engine.Engine(pb, n_chains=64) as exact:
+        for eng in (pruned, exact):
+            eng.upload_positions(positions)
+            eng.start(first_stream=7)
+        pruned.run(max_events=4000)
+        s1 = pruned.sync()
+        _, s2 = exact.run_recorded(max_events=4000, records_per_chain=1)
+        assert np.array_equal(pruned.download_positions(), exact.download_positions())
+        assert np.array_equal(pruned.chain_states(), exact.chain_states())
+        occ1, sur1 = pruned.cells()
+        occ2, sur2 = exact.cells()
+        assert np.array_equal(occ1, occ2) and all(a.tolist() == b.tolist() for a, b in zip(sur1, sur2))
+        for key in ("events", "pair_events", "veto_events", "veto_accepted", "boundary_events", "end_of_chain_events",
+                    "pair_targets"):
+            assert s1[key] == s2[key], key
+        assert 0 < s1["candidates"] <= s2["candidates"]  # equal unless the library was built with -DECMC_PRUNE
+        assert s1["pair_events"] > 10000 and s1["veto_accepted"] > 100
+
+
 def test_surplus_overflow_is_reported(oracle):
     pb, positions = _lj_batch(oracle, n_chains=2, n=100, cells=4, length=5.2, seed=9)
     pb.program.max_surplus = 4  # 100 particles in 64 cells need at least 36 surplus slots
