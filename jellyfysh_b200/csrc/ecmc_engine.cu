@@ -479,8 +479,10 @@ EventKernel pick_kernel(const DeviceProgram &d, bool record) {
             return pick_far_pairs<ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, ECMC_POT_MERGED_IMAGE_COULOMB, ECMC_POT_MERGED_IMAGE_COULOMB>(record);
         return pick_far_pairs<-1, -1, -1>(record);
     }
-    if (cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record, single);
-    if (cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record, single);
+    // the Lennard-Jones kernels assume chargeless handlers and modular cell translations (FAST in event_kernel)
+    const bool fast = !d.pair_use_charge && !d.veto_use_charge && d.translate_modular;
+    if (fast && cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record, single);
+    if (fast && cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record, single);
     if (cand == HS && real == 0 && veto == 0) return pick_record<ECMC_POT_HARD_SPHERE, 0, 0>(record, false);
     if (cand == IPCB && real == MIC && veto == MIC)
         return pick_record<ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, ECMC_POT_MERGED_IMAGE_COULOMB, ECMC_POT_MERGED_IMAGE_COULOMB>(record, single);

@@ -326,7 +326,13 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
 #else
     constexpr bool PRUNE = false;
 #endif
-    const bool has_pairs = P.pair_handler != ECMC_PAIR_NONE;
+    // The Lennard-Jones instantiations are picked only for chargeless handlers on modular cell translations
+    // (pick_kernel): those configuration tests are compile-time constants there.
+    constexpr bool FAST = CAND == ECMC_POT_LENNARD_JONES && REAL == 0 && (VETO == ECMC_POT_LENNARD_JONES || VETO == 0);
+    const bool pair_use_charge = FAST ? false : P.pair_use_charge != 0;
+    const bool veto_use_charge = FAST ? false : P.veto_use_charge != 0;
+    const bool translate_modular = FAST ? true : P.translate_modular != 0;
+    const bool has_pairs = FAST ? true : P.pair_handler != ECMC_PAIR_NONE;
     const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
     const bool has_veto = VETO != 0 && !FAR_PAIRS && P.veto_enabled == ECMC_FAR_CELL_VETO;
     const bool has_far_pairs = VETO != 0 && FAR_PAIRS;
@@ -375,7 +381,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             const int far_base = n_pair_slots + n_bond_slots;
             const int n_scan_slots = far_base + (has_far_pairs ? P.n_cells : 0);
             const int special_seq = FAR_PAIRS ? far_base + P.n_cells : far_base;
-            const double c_active = P.pair_use_charge ? a.charge : 1.0;
+            const double c_active = pair_use_charge ? a.charge : 1.0;
             unsigned long long best_key = 0x7ff0000000000000ull;  // best of the passes so far (uniform)
             double best_x = INFINITY;
             int best_seq = kSeqNone;
@@ -517,7 +523,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     // bound of the relative cell x charge correction factor (cell_bounding_potential.py:155-238)
                     const int relative = relative_cell_of(P, s - far_base, cid0, cid1, cid2);
                     double charge_product = 1.0;
-                    if (P.veto_use_charge) charge_product = a.charge * tp.charge / P.veto_target_charge;
+                    if (veto_use_charge) charge_product = a.charge * tp.charge / P.veto_target_charge;
                     const double *bound = P.bounds + (relative * P.dimension + dir) * 2;
                     rate = charge_product > 0.0 ? __ldg(bound) * charge_product : -__ldg(bound + 1) * charge_product;
                     dt = rate > 0.0 ? exponential / rate * P.inv_speed : INFINITY;
@@ -526,14 +532,14 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     seq = s;
                 } else if (is_pair) {
                     dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c_active,
-                                                 P.pair_use_charge ? tp.charge : 1.0, cand_needs_du ? exponential : 0.0);
+                                                 pair_use_charge ? tp.charge : 1.0, cand_needs_du ? exponential : 0.0);
                     kind = ECMC_EVENT_PAIR;
                     seq = s;
                 } else if (is_veto) {
                     // CellVetoEventHandler.send_event_time (cell_veto_event_handler.py:200-238)
                     // InnerPointEstimator.charge_correction_factor (inner_point_estimator.py:165-192)
                     double charge_factor = 1.0;
-                    if (P.veto_use_charge) {
+                    if (veto_use_charge) {
                         charge_factor = a.charge * 1.0;
                         if (P.veto_target_charge != 1.0) charge_factor = charge_factor / P.veto_target_charge;
                     }
@@ -563,7 +569,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     // translate(active cell, relative cell), per axis (cuboid_periodic_cells.py:182-207)
                     int tx, ty, tz;
                     const int rx = relative & 1023, ry = (relative >> 10) & 1023, rz = relative >> 20;
-                    if (P.translate_modular) {
+                    if (translate_modular) {
                         tx = cid0 + rx; ty = cid1 + ry; tz = cid2 + rz;
                         if (tx >= P.per_side[0]) tx -= P.per_side[0];
                         if (ty >= P.per_side[1]) ty -= P.per_side[1];
@@ -578,7 +584,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     // expovariate(beta) / (total rate * charge factor * speed): the reciprocal of the table's part is
                     // precomputed, chargeless handlers never divide
                     dt = exponential * w->inv_total_rate_speed;
-                    if (P.veto_use_charge) dt = exponential / (w->total_rate * charge_factor * speed);
+                    if (veto_use_charge) dt = exponential / (w->total_rate * charge_factor * speed);
                     kind = ECMC_EVENT_CELL_VETO;
                     seq = special_seq;
                 } else if (is_boundary) {
@@ -678,7 +684,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
                 const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
                 const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
-                const double c1 = P.pair_use_charge ? a.charge : 1.0, c2 = P.pair_use_charge ? tp.charge : 1.0;
+                const double c1 = pair_use_charge ? a.charge : 1.0, c2 = pair_use_charge ? tp.charge : 1.0;
                 const double bounding_rate = derivative_warp<CAND>(P.cand_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
                 const double real = derivative_warp<REAL>(P.real_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
@@ -700,7 +706,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
                 const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
                 const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
-                const double c1 = P.veto_use_charge ? a.charge : 1.0, c2 = P.veto_use_charge ? tp.charge : 1.0;
+                const double c1 = veto_use_charge ? a.charge : 1.0, c2 = veto_use_charge ? tp.charge : 1.0;
                 const double real = derivative_warp<VETO>(P.veto_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
                 if (real > 0.0) {
                     if (brate < real) count_rare(A, lane, 7);
@@ -721,7 +727,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
             const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
             const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
-            const double c1 = P.veto_use_charge ? a.charge : 1.0, c2 = P.veto_use_charge ? tp.charge : 1.0;
+            const double c1 = veto_use_charge ? a.charge : 1.0, c2 = veto_use_charge ? tp.charge : 1.0;
             const double bounding_rate = brate * speed;
             const double real = derivative_warp<VETO>(P.veto_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
             if (real > 0.0) {
