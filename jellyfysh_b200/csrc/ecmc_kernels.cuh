@@ -208,7 +208,7 @@ ECMC_D int warp_argmin(unsigned long long key, int seq, int lane) {
 // Per-launch event counters of one chain, kept in registers; the rare ones (accepted vetoes, bound violations,
 // capacity overflows) go straight to the global statistics, the boundary count is what remains of `events`.
 struct Counters {
-    unsigned events, pair, veto, end_of_chain;
+    unsigned events, veto;
     unsigned long long candidates, targets;
 };
 ECMC_D void count_rare(const RunArgs &A, int lane, int index) {
@@ -230,6 +230,10 @@ ECMC_D Moving rotate_in(const Particle &q, int dir) {
     m.p2 = dir == 0 ? q.z : (dir == 1 ? q.x : q.y);
     m.charge = q.charge;
     return m;
+}
+// write the coordinates of a particle back; its charge never changes
+ECMC_D void store_position(Particle *slot, const Particle &lab) {
+    slot->x = lab.x; slot->y = lab.y; slot->z = lab.z;
 }
 ECMC_D Particle rotate_out(const Moving &m, int dir) {
     Particle q;
@@ -333,12 +337,13 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     const bool veto_use_charge = FAST ? false : P.veto_use_charge != 0;
     const bool translate_modular = FAST ? true : P.translate_modular != 0;
     const bool has_pairs = FAST ? true : P.pair_handler != ECMC_PAIR_NONE;
+    const int dimension = FAST ? 3 : P.dimension;
     const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
     const bool has_veto = VETO != 0 && !FAR_PAIRS && P.veto_enabled == ECMC_FAR_CELL_VETO;
     const bool has_far_pairs = VETO != 0 && FAR_PAIRS;
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
 
-    Counters n = {0, 0, 0, 0, 0ull, 0ull};
+    Counters n = {0, 0, 0ull, 0ull};
     unsigned n_bond_events = 0;
     bool stopped_by_time = false;
 
@@ -694,7 +699,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 }
             }
             if (accepted) new_active = btarget;
-            n.pair++;
+            count_rare(A, lane, 1);
             break;
         }
         case ECMC_EVENT_CELL_VETO: {
@@ -736,7 +741,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 if (0.0 + (bounding_rate - 0.0) * u < real) accepted = 1;
             }
             if (accepted) new_active = btarget;
-            n.pair++;
+            count_rare(A, lane, 1);
             break;
         }
         case ECMC_EVENT_BOND: {
@@ -750,6 +755,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         }
         case ECMC_EVENT_CELL_BOUNDARY: {
             // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
+            count_rare(A, lane, 4);
             a.p0 = boundary;
             break;
         }
@@ -758,7 +764,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             new_active = eoc_next;
             rec_target = new_active;
             accepted = 1;
-            n.end_of_chain++;
+            count_rare(A, lane, 5);
             break;
         default: break;
         }
@@ -767,7 +773,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             rec.kind = kind; rec.target = rec_target; rec.target_cell = kind == ECMC_EVENT_END_OF_CHAIN ? -1 : bcell;
             rec.accepted = accepted; rec.n_candidates = n_cand;
             rec.new_active = new_active;
-            rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % P.dimension : dir;
+            rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % dimension : dir;
             rec.reserved = 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
             const Particle lab = rotate_out(a, dir);
@@ -786,7 +792,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             if (lane == 0) set_component(roots[active / P.nodes_per_root], dir, root_p0);
             __syncwarp();
         }
-        if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir + 1 == P.dimension ? 0 : dir + 1;
+        if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir + 1 == dimension ? 0 : dir + 1;
         if (COMPOSITE && (new_active != active || kind == ECMC_EVENT_END_OF_CHAIN))
             root_p0 = component(roots[new_active / P.nodes_per_root], dir);
 
@@ -795,7 +801,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             cached_count = -1;
             int delta = 0;
             if (lane == 0) {
-                part[active] = lab;
+                store_position(part + active, lab);
                 delta = occupancy_insert(occ, sur, n_surplus, m, P.max_surplus, active_cell, active);
             }
             delta = __shfl_sync(kFull, delta, 0);
@@ -838,7 +844,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         now = until;
     }
     if (lane == 0) {
-        part[active] = rotate_out(a, dir);
+        store_position(part + active, rotate_out(a, dir));
         if (COMPOSITE) set_component(roots[active / P.nodes_per_root], dir, root_p0);
         stp->active = active; stp->direction = dir;
         stp->time_q = now.q; stp->time_r = now.r;
@@ -849,12 +855,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         if (A.stats) {
             unsigned long long *st = reinterpret_cast<unsigned long long *>(A.stats);
             if (n.events) atomicAdd(st + 0, (unsigned long long)n.events);
-            if (n.pair) atomicAdd(st + 1, (unsigned long long)n.pair);
             if (n.veto) atomicAdd(st + 2, (unsigned long long)n.veto);
-            const unsigned boundary = n.events - n.pair - n.veto - n.end_of_chain - (COMPOSITE ? n_bond_events : 0u);
-            if (boundary) atomicAdd(st + 4, (unsigned long long)boundary);
             if (COMPOSITE && n_bond_events) atomicAdd(st + 9, (unsigned long long)n_bond_events);
-            if (n.end_of_chain) atomicAdd(st + 5, (unsigned long long)n.end_of_chain);
             if (n.candidates) atomicAdd(st + 6, n.candidates);
             if (n.targets) atomicAdd(st + 11, n.targets);
         }
