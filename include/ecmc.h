@@ -343,6 +343,12 @@ int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *
  * Counts are ADDED to histogram[n_bins] (host buffer), so successive sampling times accumulate; separations outside
  * the range are not counted. Ranks of a multi-GPU run sum their histograms with one all-reduce (sharding.py). */
 int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_min, double r_max, uint64_t *histogram);
+/* The same over the particles first, first + stride, first + 2 stride, ... only: with stride = nodes_per_root and
+ * first = a child index, the separations between one kind of leaf of every composite object -- the oxygen-oxygen
+ * separations of water that OxygenOxygenSeparationOutputHandler samples
+ * (jellyfysh/input_output_handler/output_handler/oxygen_oxygen_separation_output_handler.py). */
+int ecmc_separation_histogram_subset(EcmcHandle *h, int32_t first, int32_t stride, int32_t n_bins, double r_min,
+                                     double r_max, uint64_t *histogram);
 
 /* The CUDA stream the handle launches on (a cudaStream_t), so callers can time with events on it. */
 void *ecmc_stream(EcmcHandle *h);

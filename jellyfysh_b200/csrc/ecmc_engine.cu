@@ -531,10 +531,23 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
     const int blocks = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
     CUDA_TRY(h, cudaEventRecord(ev.start, h->stream));
     if (h->molecules) {
-        if (d_records)
-            molecule_kernel<true, kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
-        else
-            molecule_kernel<false, kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
+        // the shipped water configurations: Coulomb bound / merged-image Coulomb / harmonic bonds / Lennard-Jones
+        const DeviceProgram &d = h->dprog;
+        const bool water = d.cand_potential.kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING &&
+                           d.real_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB &&
+                           (!d.veto_enabled || d.veto_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB) &&
+                           (d.n_bonds == 0 || (d.bond_potential.kind == ECMC_POT_DISPLACED_EVEN_POWER &&
+                                               d.bond_potential.dep.power == 2.0)) &&
+                           (h->mprog.n_inter == 0 || h->mprog.inter_potential.kind == ECMC_POT_LENNARD_JONES);
+        typedef void (*MoleculeKernel)(const DeviceProgram, const MoleculeProgram, const DeviceState, const RunArgs);
+        const int IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, MIC = ECMC_POT_MERGED_IMAGE_COULOMB,
+                  DEP = kPotHarmonic, LJ = ECMC_POT_LENNARD_JONES;
+        MoleculeKernel kernel;
+        if (water) kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kWarpsPerBlock>
+                                      : molecule_kernel<IPCB, MIC, DEP, LJ, false, kWarpsPerBlock>;
+        else kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kWarpsPerBlock>
+                                : molecule_kernel<-1, -1, -1, -1, false, kWarpsPerBlock>;
+        kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
     } else {
         const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
         kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
@@ -868,7 +881,14 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
 }
 
 ECMC_API int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_min, double r_max, uint64_t *histogram) {
+    return ecmc_separation_histogram_subset(h, 0, 1, n_bins, r_min, r_max, histogram);
+}
+
+ECMC_API int ecmc_separation_histogram_subset(EcmcHandle *h, int32_t first, int32_t stride, int32_t n_bins, double r_min,
+                                              double r_max, uint64_t *histogram) {
     if (!h || !histogram) return fail(h, ECMC_ERR_INVALID, "null argument");
+    if (stride < 1 || first < 0 || first >= stride || first >= h->dprog.n_particles)
+        return fail(h, ECMC_ERR_INVALID, "histogram subset needs 0 <= first < stride and first < n_particles");
     if (n_bins < 1 || n_bins > kHistogramMaxBins || !(r_max > r_min) || r_min < 0.0)
         return fail(h, ECMC_ERR_INVALID, "histogram needs 1 <= n_bins <= 4096 and 0 <= r_min < r_max");
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -878,10 +898,11 @@ ECMC_API int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_m
     do {
         cudaError_t err = cudaMemsetAsync(d_histogram, 0, sizeof(unsigned long long) * n_bins, h->stream);
         if (err != cudaSuccess) { rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
-        const int n_tiles = (h->dprog.n_particles + kHistogramTile - 1) / kHistogramTile;
+        const int n_subset = (h->dprog.n_particles - first + stride - 1) / stride;
+        const int n_tiles = (n_subset + kHistogramTile - 1) / kHistogramTile;
         separation_histogram_kernel<<<h->n_chains * n_tiles, 256, 0, h->stream>>>(
-            h->state.particles, h->dprog.n_particles, n_tiles, h->dprog.length, n_bins, r_min,
-            (double)n_bins / (r_max - r_min), d_histogram);
+            h->state.particles, n_subset, n_tiles, h->dprog.length, n_bins, r_min,
+            (double)n_bins / (r_max - r_min), d_histogram, first, stride, h->dprog.n_particles);
         std::vector<unsigned long long> counts(n_bins);
         if ((err = cudaGetLastError()) != cudaSuccess ||
             (err = cudaMemcpyAsync(counts.data(), d_histogram, sizeof(unsigned long long) * n_bins, cudaMemcpyDeviceToHost,

@@ -18,6 +18,9 @@
 namespace ecmc {
 
 constexpr unsigned kFull = 0xffffffffu;
+// compile-time kind of a displaced even power potential whose power is known to be 2 (harmonic bond): never appears in
+// an EcmcPotential, only as a template argument chosen by the engine
+constexpr int kPotHarmonic = 103;
 // resident warps (= chains) per SM the event kernel is compiled for: sets the register budget (65536 / 32 / warps)
 #ifndef ECMC_RESIDENT_WARPS
 #define ECMC_RESIDENT_WARPS 28
@@ -52,7 +55,8 @@ ECMC_D double displacement_time(const PotentialParams &p, int dir, double inv_sp
         ip_squares(dir, sx, sy, sz, r2, p2);
         return ip_displacement(p.ip, sd, p2, r2, c1, c2, du) * inv_speed;
     }
-    case ECMC_POT_DISPLACED_EVEN_POWER: return dep_displacement(p.dep, sd, perp2, du) * inv_speed;
+    case ECMC_POT_DISPLACED_EVEN_POWER: return dep_displacement<false>(p.dep, sd, perp2, du) * inv_speed;
+    case kPotHarmonic: return dep_displacement<true>(p.dep, sd, perp2, du) * inv_speed;
     case ECMC_POT_HARD_SPHERE: {
         const double speed = 1.0 / inv_speed;
         return hard_sphere_time(p.p0, __dmul_rn(speed, speed), __dmul_rn(speed, sd), dot3(sx, sy, sz, sx, sy, sz));
@@ -978,23 +982,27 @@ __global__ void unpack_particles_kernel(const Particle *in, double *positions, s
 constexpr int kHistogramTile = 1024;
 constexpr int kHistogramMaxBins = 4096;
 
+// `first`, `stride`: only the particles first, first + stride, ... take part (n_particles counts those): stride =
+// nodes_per_root and first = child index select one leaf of every composite object, e.g. the oxygens of water
+// (OxygenOxygenSeparationOutputHandler, oxygen_oxygen_separation_output_handler.py).
 __global__ void __launch_bounds__(256)
 separation_histogram_kernel(const Particle *particles, int n_particles, int n_tiles, double length, int n_bins,
-                            double r_min, double inv_bin_width, unsigned long long *histogram) {
+                            double r_min, double inv_bin_width, unsigned long long *histogram, int first, int stride,
+                            int particles_per_chain) {
     __shared__ double tile_x[kHistogramTile], tile_y[kHistogramTile], tile_z[kHistogramTile];
     __shared__ unsigned int bins[kHistogramMaxBins];
     const int chain = blockIdx.x / n_tiles, tile = blockIdx.x % n_tiles;
-    const Particle *part = particles + (size_t)chain * n_particles;
+    const Particle *part = particles + (size_t)chain * particles_per_chain + first;
     const int j0 = tile * kHistogramTile, j1 = min(n_particles, j0 + kHistogramTile);
     for (int b = threadIdx.x; b < n_bins; b += blockDim.x) bins[b] = 0;
     for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-        const Particle p = part[j];
+        const Particle p = part[(size_t)j * stride];
         tile_x[j - j0] = p.x; tile_y[j - j0] = p.y; tile_z[j - j0] = p.z;
     }
     __syncthreads();
     const double half = 0.5 * length;
     for (int i = threadIdx.x; i < j1 - 1; i += blockDim.x) {
-        const Particle p = part[i];
+        const Particle p = part[(size_t)i * stride];
         for (int j = max(i + 1, j0); j < j1; j++) {
             const double sx = correct_separation_in_box(tile_x[j - j0] - p.x, length, half);
             const double sy = correct_separation_in_box(tile_y[j - j0] - p.y, length, half);

@@ -158,6 +158,17 @@ ECMC_HD bool time_lt(Time a, Time b) { return a.q < b.q || (a.q == b.q && a.r < 
 // Periodic boundaries of the hypercubic box, jellyfysh/setting/hypercubic_setting.py:117,172.
 // Python's float % has the sign of the divisor.
 // ---------------------------------------------------------------------------------------------------------
+// the general case of Python's float %, out of line: the hot paths only ever see arguments in [-L, 2L), and an
+// inlined fmod is a hundred instructions at every call site
+__host__ __device__ __noinline__ inline double py_mod_general(double x, double L) {
+    double m = fmod(x, L);
+    if (m != 0.0) {
+        if (m < 0.0) m += L;
+    } else {
+        m = 0.0;
+    }
+    return m;
+}
 ECMC_HD double py_mod(double x, double L) {
     // x % L of Python for L > 0. In [-L, 2L) -- every case on the hot path -- fmod reduces to at most one exact
     // subtraction / one rounded addition, identical to CPython's float_rem; fmod itself is a long loop on the GPU.
@@ -168,13 +179,7 @@ ECMC_HD double py_mod(double x, double L) {
         const double m = x + L;      // fmod(x, L) = x, then += L
         return m;
     }
-    double m = fmod(x, L);
-    if (m != 0.0) {
-        if (m < 0.0) m += L;
-    } else {
-        m = 0.0;
-    }
-    return m;
+    return py_mod_general(x, L);
 }
 ECMC_HD double correct_separation_entry(double s, double L, double half) { return py_mod(s + half, L) - half; }
 // the same for two positions inside the box, |s| < L: s + L/2 lies in (-L/2, 3L/2) and the modulo is one select
@@ -419,12 +424,25 @@ ECMC_D double ip_displacement(const InversePower &p, double sd, double perp2, do
 struct DisplacedEvenPower {
     double k, r0, power;
 };
-ECMC_D double dep_energy(const DisplacedEvenPower &p, double r2) { return p.k * pow(sqrt(r2) - p.r0, p.power); }
+// x^power and x^(1/power); SQUARE: the harmonic bond (power = 2, every shipped configuration), known at compile time,
+// needs no generic pow (a few hundred instructions per call site)
+template <bool SQUARE>
+ECMC_D double dep_pow(const DisplacedEvenPower &p, double x) { return (SQUARE || p.power == 2.0) ? x * x : pow(x, p.power); }
+template <>
+ECMC_D double dep_pow<true>(const DisplacedEvenPower &, double x) { return x * x; }
+template <bool SQUARE>
+ECMC_D double dep_root(const DisplacedEvenPower &p, double x) { return p.power == 2.0 ? sqrt(x) : pow(x, 1.0 / p.power); }
+template <>
+ECMC_D double dep_root<true>(const DisplacedEvenPower &, double x) { return sqrt(x); }
+template <bool SQUARE = false>
+ECMC_D double dep_energy(const DisplacedEvenPower &p, double r2) { return p.k * dep_pow<SQUARE>(p, sqrt(r2) - p.r0); }
 ECMC_D double dep_derivative(const DisplacedEvenPower &p, double sd, double perp2) {
     const double r = sqrt(fma(sd, sd, perp2));
-    return -p.power * p.k * pow(r - p.r0, p.power - 1.0) * sd / r;
+    const double d = r - p.r0;
+    return -p.power * p.k * (p.power == 2.0 ? d : pow(d, p.power - 1.0)) * sd / r;
 }
 // same two-stretch structure as lj_displacement; the outside branch never escapes (U -> +inf)
+template <bool SQUARE = false>
 ECMC_D double dep_displacement(const DisplacedEvenPower &p, double sd, double perp2, double du) {
     const double r0sq = p.r0 * p.r0;
     const double r2 = fma(sd, sd, perp2);
@@ -432,21 +450,21 @@ ECMC_D double dep_displacement(const DisplacedEvenPower &p, double sd, double pe
     const bool inside = r2 < r0sq;
     double u_start;
     if (sd > 0.0 && hits) {
-        const double u1 = inside ? dep_energy(p, r2) : 0.0;
-        const double u_max = dep_energy(p, perp2);
+        const double u1 = inside ? dep_energy<SQUARE>(p, r2) : 0.0;
+        const double u_max = dep_energy<SQUARE>(p, perp2);
         const double barrier = u_max - u1;
         if (du < barrier) {
-            const double rn = p.r0 - pow((u1 + du) / p.k, 1.0 / p.power);
+            const double rn = p.r0 - dep_root<SQUARE>(p, (u1 + du) / p.k);
             return sd - sqrt(rn * rn - perp2);
         }
         du -= barrier;
         u_start = 0.0;
     } else if (sd > 0.0) {
-        u_start = dep_energy(p, perp2);
+        u_start = dep_energy<SQUARE>(p, perp2);
     } else {
-        u_start = inside ? 0.0 : dep_energy(p, r2);
+        u_start = inside ? 0.0 : dep_energy<SQUARE>(p, r2);
     }
-    const double rn = p.r0 + pow((u_start + du) / p.k, 1.0 / p.power);
+    const double rn = p.r0 + dep_root<SQUARE>(p, (u_start + du) / p.k);
     return sd + sqrt(rn * rn - perp2);
 }
 

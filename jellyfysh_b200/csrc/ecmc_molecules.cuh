@@ -53,15 +53,16 @@ ECMC_D Vec3 separation_lab(const Vec3 &from, const Vec3 &to, double L, double ha
 
 // BendingPotential.derivative (bending_potential.py:60-138): time derivatives with respect to the units i, j, k for
 // s1 = r_i - r_j, s2 = r_k - r_j along direction `dir`
-ECMC_D void bending_derivative(double prefactor, double equilibrium_angle, int dir, double speed, const Vec3 &s1,
-                               const Vec3 &s2, double out[3]) {
+__device__ __noinline__ void bending_derivative(double prefactor, double equilibrium_angle, int dir, double speed,
+                                                const Vec3 &s1, const Vec3 &s2, double out[3]) {
     const double n1 = sqrt(fma(s1.x, s1.x, fma(s1.y, s1.y, s1.z * s1.z)));
     const double n2 = sqrt(fma(s2.x, s2.x, fma(s2.y, s2.y, s2.z * s2.z)));
     const double inv1 = 1.0 / n1, inv2 = 1.0 / n2;
     const double cosine = fma(s1.x, s2.x, fma(s1.y, s2.y, s1.z * s2.z)) * inv1 * inv2;
     const double angle = acos(cosine);
     const double du_dangle = prefactor * (angle - equilibrium_angle);
-    const double dangle_dcos = -1.0 / sin(angle);
+    // sin(angle) for an angle in [0, pi] without the sine: sqrt((1 - cos)(1 + cos))
+    const double dangle_dcos = -rsqrt((1.0 - cosine) * (1.0 + cosine));
     const double a1 = vcomp(s1, dir), a2 = vcomp(s2, dir);
     const double dcos_ds1 = a2 * inv1 * inv2 - cosine * a1 * inv1 * inv1;
     const double dcos_ds2 = a1 * inv1 * inv2 - cosine * a2 * inv2 * inv2;
@@ -74,6 +75,13 @@ ECMC_D void bending_derivative(double prefactor, double equilibrium_angle, int d
 
 // Lifting.insert / get_active_identifier (lifting/lifting.py:49-91 and the three schemes), at most eight units.
 // Draws come from the out-state's slot (ECMC_SLOT_CONFIRM) in call order.
+// The draws of an out-state (confirmation, lifting) come from many call sites, each event uses one or two of them: one
+// out-of-line Philox instead of a dozen inlined copies keeps the kernel's instruction footprint down.
+__device__ __noinline__ double confirm_draw(uint32_t seed, uint32_t stream, unsigned long long event, uint32_t index) {
+    const StreamKey key = {seed, stream, event};
+    return stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), index);
+}
+
 struct Lifting {
     double negative[6];
     int ids[6];
@@ -90,7 +98,7 @@ ECMC_D void lifting_insert(Lifting &l, double rate, int id, bool is_active, cons
     if (rate > 0.0) {
         if (is_active) {
             l.active_recorded = true;
-            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+            const double u = confirm_draw(key.seed, key.stream, key.event, draw++);
             l.random_position += 0.0 + (rate - 0.0) * u;
         } else if (!l.active_recorded) {
             l.random_position += rate;
@@ -121,7 +129,7 @@ ECMC_D int lifting_get(const Lifting &l, int kind, const StreamKey &key, uint32_
     if (kind == ECMC_LIFTING_OUTSIDE_FIRST) {
         position = pysum_n(l.negative, l.n_negative) - l.random_position;
     } else if (kind == ECMC_LIFTING_RATIO) {
-        const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+        const double u = confirm_draw(key.seed, key.stream, key.event, draw++);
         position = 0.0 + (pysum_n(l.negative, l.n_negative) - 0.0) * u;
     }
     double summed = 0.0;
@@ -144,7 +152,10 @@ ECMC_D double pair_derivative_lab(const PotentialParams &p, int dir, double spee
     return derivative_warp<KIND>(p, dir, speed, s.x, s.y, s.z, c1, c2, trig, lane);
 }
 
-template <bool RECORD, int WARPS>
+// CAND / REAL / BOND / INTER: compile-time kinds of the bounding potential of the composite pairs, of the potential the
+// composite events are confirmed against (pair and cell veto), of the intramolecular pair factors and of the factors
+// between objects; -1 = decided at run time (the generic instantiation is four times the code).
+template <int CAND, int REAL, int BOND, int INTER, bool RECORD, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ MoleculeProgram M, const DeviceState S,
                 const RunArgs A) {
@@ -322,15 +333,18 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                             const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, root), (uint32_t)k);
                             const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
                             const double c1 = P.pair_use_charge ? acharge : 1.0, c2 = P.pair_use_charge ? tp.charge : 1.0;
-                            dt = displacement_time<-1>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c1, c2, du);
+                            dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c1, c2, du);
                             kind = ECMC_EVENT_PAIR;
                             rec_target = root;
                         } else {
-                            const PotentialParams &pot = type == ITEM_BOND ? P.bond_potential : M.inter_potential;
                             const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
                             const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
-                            dt = displacement_time<-1>(pot, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
-                                                       needs_potential_change(pot.kind) ? du : 0.0);
+                            if (type == ITEM_BOND)
+                                dt = displacement_time<BOND>(P.bond_potential, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
+                                                             needs_potential_change(resolve_kind<BOND>(P.bond_potential.kind)) ? du : 0.0);
+                            else
+                                dt = displacement_time<INTER>(M.inter_potential, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
+                                                              needs_potential_change(resolve_kind<INTER>(M.inter_potential.kind)) ? du : 0.0);
                             kind = type == ITEM_BOND ? ECMC_EVENT_BOND : ECMC_EVENT_FACTOR_PAIR;
                             rec_target = target;
                             is_factor = true;
@@ -530,38 +544,47 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             double target_derivatives[4] = {0.0, 0.0, 0.0, 0.0};
             Vec3 tpos[4];
             double tcharge[4];
+            const PotentialParams &real_potential = veto ? P.veto_potential : P.real_potential;
             for (int k = 0; k < npr; k++) {
                 const Particle tp = part[target_root * npr + k];
                 tpos[k] = lab_position(tp);
                 tcharge[k] = tp.charge;
-                const double c1 = use_charge ? acharge : 1.0, c2 = use_charge ? tp.charge : 1.0;
                 if (!veto) {
-                    const double b = pair_derivative_lab<-1>(P.cand_potential, dir, speed, apos, tpos[k], c1, c2, L, half, trig, lane);
+                    const double c1 = use_charge ? acharge : 1.0, c2 = use_charge ? tp.charge : 1.0;
+                    const double b = pair_derivative_lab<CAND>(P.cand_potential, dir, speed, apos, tpos[k], c1, c2, L, half, trig, lane);
                     bounding_rate += b > 0.0 ? b : 0.0;
                 }
-                const double pairwise = pair_derivative_lab<-1>(veto ? P.veto_potential : P.real_potential, dir, speed, apos,
-                                                                tpos[k], c1, c2, L, half, trig, lane);
-                factor_derivative += pairwise;
-                target_derivatives[k] -= pairwise;
             }
-            const double event_rate = factor_derivative > 0.0 ? factor_derivative : 0.0;
-            if (bounding_rate < event_rate) count_rare(A, lane, 7);
-            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
-            if (event_rate <= 0.0 + (bounding_rate - 0.0) * u) break;
-            // _fill_lifting (event_handler_with_bounding_potential.py:170-220)
+            // The derivatives of the real potential, all through ONE call site (the merged-image Coulomb sum is a
+            // thousand instructions): first the active leaf against the target leaves (confirmation), then -- only if
+            // the event is confirmed -- the other local leaves against the target leaves (_fill_lifting,
+            // event_handler_with_bounding_potential.py:170-220)
             double local_derivatives[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int i = 0; i < npr; i++) {
-                const int local = active_root * npr + i;
-                if (local == active) { local_derivatives[i] = veto ? factor_derivative : event_rate; continue; }
+            bool confirmed = false;
+            for (int i = -1; i < npr; i++) {
+                const int local = i < 0 ? active : active_root * npr + i;
+                if (i >= 0 && local == active) continue;
+                if (i == 0 || (i == 1 && active == active_root * npr)) {
+                    // between the two stages: confirm the event with the summed derivative of the active leaf
+                    const double event_rate = factor_derivative > 0.0 ? factor_derivative : 0.0;
+                    if (bounding_rate < event_rate) count_rare(A, lane, 7);
+                    const double u = confirm_draw(key.seed, key.stream, key.event, draw++);
+                    if (event_rate <= 0.0 + (bounding_rate - 0.0) * u) break;
+                    confirmed = true;
+                    local_derivatives[active - active_root * npr] = veto ? factor_derivative : event_rate;
+                }
                 const Particle lp = part[local];
+                const Vec3 lpos = i < 0 ? apos : lab_position(lp);
+                const double lcharge = i < 0 ? acharge : lp.charge;
                 for (int j = 0; j < npr; j++) {
-                    const double c1 = use_charge ? lp.charge : 1.0, c2 = use_charge ? tcharge[j] : 1.0;
-                    const double pairwise = pair_derivative_lab<-1>(veto ? P.veto_potential : P.real_potential, dir, speed,
-                                                                    lab_position(lp), tpos[j], c1, c2, L, half, trig, lane);
-                    local_derivatives[i] += pairwise;
+                    const double c1 = use_charge ? lcharge : 1.0, c2 = use_charge ? tcharge[j] : 1.0;
+                    const double pairwise = pair_derivative_lab<REAL>(real_potential, dir, speed, lpos, tpos[j], c1, c2, L,
+                                                                      half, trig, lane);
+                    if (i < 0) factor_derivative += pairwise; else local_derivatives[i] += pairwise;
                     target_derivatives[j] -= pairwise;
                 }
             }
+            if (!confirmed) break;
             Lifting lift;
             lifting_reset(lift);
             for (int pass = 0; pass < 2; pass++) {
@@ -601,7 +624,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             const double own = index == 0 ? derivatives[0] : (index == 1 ? derivatives[1] : derivatives[2]);
             if (own > 0.0) {
                 if (brate < own) count_rare(A, lane, 7);
-                const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+                const double u = confirm_draw(key.seed, key.stream, key.event, draw++);
                 if (0.0 + (brate - 0.0) * u < own) {
                     Lifting lift;
                     lifting_reset(lift);

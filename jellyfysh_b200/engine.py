@@ -59,6 +59,7 @@ def library() -> C.CDLL:
     lib.ecmc_run_recorded.argtypes = [vp, d, d, i64, vp, i32, stats]
     lib.ecmc_run_from_host.argtypes = [vp, vp, vp, u32, d, d, i64, vp, stats]
     lib.ecmc_separation_histogram.argtypes = [vp, i32, d, d, vp]
+    lib.ecmc_separation_histogram_subset.argtypes = [vp, i32, i32, i32, d, d, vp]
     lib.ecmc_stream.argtypes = [vp]
     lib.ecmc_stream.restype = vp
     lib.ecmc_kernel_seconds.argtypes = [vp]
@@ -207,11 +208,13 @@ class Engine:
                                                  float(until[1]), int(max_events), _ptr(out), C.byref(stats)))
         return out, stats.as_dict()
 
-    def separation_histogram(self, n_bins, r_min, r_max, out=None):
-        """Add the pair-separation counts of the current configuration of all chains to `out` (uint64[n_bins])."""
+    def separation_histogram(self, n_bins, r_min, r_max, out=None, first=0, stride=1):
+        """Add the pair-separation counts of the current configuration of all chains to `out` (uint64[n_bins]);
+        first / stride select every stride-th particle (e.g. the oxygens of water: first=1, stride=3)."""
         if out is None:
             out = np.zeros(n_bins, dtype=np.uint64)
-        self._check(self._lib.ecmc_separation_histogram(self._h, int(n_bins), float(r_min), float(r_max), _ptr(out)))
+        self._check(self._lib.ecmc_separation_histogram_subset(self._h, int(first), int(stride), int(n_bins),
+                                                               float(r_min), float(r_max), _ptr(out)))
         return out
 
     @property

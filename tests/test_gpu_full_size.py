@@ -171,3 +171,25 @@ def test_separation_histogram_matches_numpy():
         eng.upload_positions(positions)
         counts = eng.separation_histogram(64, 0.0, length)
     assert counts.sum() == 1500 * 1499 // 2
+
+
+def test_subset_separation_histogram_matches_numpy():
+    """ecmc_separation_histogram_subset: every third particle starting at 1 (the oxygens of water molecules stored as
+    H, O, H) against numpy."""
+    n_chains, n, cells = 7, 201, 6
+    builder, length = workloads.lennard_jones(n_particles=n, cells_per_side=cells, points_per_side=2, veto=False)
+    positions = workloads.lattice_start(n_chains, n, cells, length, jitter=0.2)
+    with engine.Engine(builder, n_chains=n_chains) as eng:
+        eng.upload_positions(positions)
+        r_max = length * np.sqrt(3.0) / 2.0
+        ours = eng.separation_histogram(500, 0.0, r_max, first=1, stride=3)
+    subset = positions[:, 1::3]
+    m = subset.shape[1]
+    iu = np.triu_indices(m, k=1)
+    half = length / 2.0
+    expected = np.zeros(500, dtype=np.int64)
+    for c in range(n_chains):
+        sep = np.mod(subset[c][iu[1]] - subset[c][iu[0]] + half, length) - half
+        expected += np.histogram(np.sqrt(np.sum(sep * sep, axis=1)), bins=500, range=(0.0, r_max))[0]
+    assert ours.sum() == n_chains * m * (m - 1) // 2
+    assert np.abs(ours.astype(np.int64) - expected).sum() <= 4
