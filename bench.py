@@ -216,7 +216,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": sample,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -389,13 +389,31 @@ def run_ours(args, rank, local_rank, world):
         if baseline is None:
             baseline = port_sample(args, builder, length, args.cpu_seconds)
         line["cpu_baseline"] = baseline
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else a library prints there (NCCL's
+    version banner, for instance) was diverted to stderr by main()."""
+    text = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)  # file-descriptor level: also catches what native libraries print
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
