@@ -217,6 +217,39 @@ class Engine:
                                                                float(r_min), float(r_max), _ptr(out)))
         return out
 
+    # ---- checkpoint / resume (the role of DumpingOutputHandler + resume.py, jellyfysh/resume.py) ----
+    def save_checkpoint(self, path):
+        """Everything that defines the future of all chains -- leaf (and root) positions, cell occupancy, surplus lists,
+        lifting state incl. the random-stream counters and kept candidates -- as one .npz file. A run resumed from it
+        commits bit for bit the events the uninterrupted run commits."""
+        self._check(self._lib.ecmc_sync(self._h, None))
+        occupants, surplus = self.cells()
+        n_surplus = np.array([len(items) for items in surplus], dtype=np.int32)
+        padded = np.full((self.n_chains, self.max_surplus), -1, dtype=np.int32)
+        for chain, items in enumerate(surplus):
+            padded[chain, :len(items)] = items
+        arrays = {"positions": self.download_positions(), "chain_states": self.chain_states(), "occupants": occupants,
+                  "surplus": padded, "n_surplus": n_surplus,
+                  "layout": np.array([self.n_chains, self.n_particles, self.dimension, self.n_cells, self.max_occupants,
+                                      self.max_surplus, self.nodes_per_root], dtype=np.int64)}
+        if self.nodes_per_root > 1:
+            arrays["roots"] = self.download_roots()
+        np.savez_compressed(path, **arrays)
+
+    def load_checkpoint(self, path, charges=None):
+        """Restore a state written by save_checkpoint into an engine of the same program and number of chains
+        (charges are part of the start configuration, not of the checkpoint: pass them again if the program uses them)."""
+        with np.load(path) as data:
+            layout = [self.n_chains, self.n_particles, self.dimension, self.n_cells, self.max_occupants, self.max_surplus,
+                      self.nodes_per_root]
+            if data["layout"].tolist() != layout:
+                raise ValueError("checkpoint layout {0} does not match this engine {1}".format(data["layout"].tolist(), layout))
+            self.upload_positions(data["positions"], charges)
+            if self.nodes_per_root > 1:
+                self.upload_roots(data["roots"])
+            self.set_cells(data["occupants"], [row[:n] for row, n in zip(data["surplus"], data["n_surplus"])])
+            self.set_chain_states(data["chain_states"])
+
     @property
     def cuda_stream(self):
         return self._lib.ecmc_stream(self._h)

@@ -414,6 +414,55 @@ def test_pruned_launches_reach_the_same_state(oracle):
         assert s1["pair_events"] > 10000 and s1["veto_accepted"] > 100
 
 
+def test_checkpoint_resume_is_bit_exact(oracle, tmp_path):
+    """save_checkpoint / load_checkpoint (the role of the reference's dumping handler + resume.py): a run resumed in a
+    fresh engine commits exactly the events of the uninterrupted run -- Lennard-Jones with surplus particles, and water
+    with root units and kept factor candidates."""
+    pb, positions = _lj_batch(oracle, n_chains=12, n=100, cells=4, length=5.2, seed=21)
+    with engine.Engine(pb, n_chains=12) as straight, engine.Engine(pb, n_chains=12) as first:
+        for eng in (straight, first):
+            eng.upload_positions(positions)
+            eng.start(first_stream=3)
+        straight.run(max_events=1500)
+        straight.sync()
+        first.run(max_events=700)
+        first.save_checkpoint(tmp_path / "lj.npz")
+    with engine.Engine(pb, n_chains=12) as resumed, engine.Engine(pb, n_chains=12) as reference:
+        resumed.load_checkpoint(tmp_path / "lj.npz")
+        resumed.run(max_events=800)
+        resumed.sync()
+        reference.upload_positions(positions)
+        reference.start(first_stream=3)
+        reference.run(max_events=1500)
+        reference.sync()
+        assert np.array_equal(resumed.download_positions(), reference.download_positions())
+        assert np.array_equal(resumed.chain_states(), reference.chain_states())
+        assert np.array_equal(resumed.cells()[0], reference.cells()[0])
+    g = tu.load_trace("trace_water_dense")
+    wb = tu.water_builder_of(g, ProgramBuilder)
+    charges = g["charges"][None]
+
+    def started():
+        eng = engine.Engine(wb, n_chains=1)
+        eng.upload_positions(g["positions0"][None], charges)
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        return eng
+
+    with started() as straight, started() as first:
+        straight.run(max_events=1200)
+        straight.sync()
+        first.run(max_events=500)
+        first.save_checkpoint(tmp_path / "water.npz")
+        with engine.Engine(wb, n_chains=1) as resumed:
+            resumed.load_checkpoint(tmp_path / "water.npz", charges=charges)
+            resumed.run(max_events=700)
+            resumed.sync()
+            assert np.array_equal(resumed.download_positions(), straight.download_positions())
+            assert np.array_equal(resumed.download_roots(), straight.download_roots())
+            assert np.array_equal(resumed.chain_states(), straight.chain_states())
+
+
 def test_surplus_overflow_is_reported(oracle):
     pb, positions = _lj_batch(oracle, n_chains=2, n=100, cells=4, length=5.2, seed=9)
     pb.program.max_surplus = 4  # 100 particles in 64 cells need at least 36 surplus slots
