@@ -1367,12 +1367,19 @@ typedef struct {
     int active_recorded;
 } olifting;
 static void lifting_reset(olifting *l) { memset(l, 0, sizeof(*l)); }
+/* the uniform draws of a lifting scheme: from the chain's out-state slot, or (c == NULL, tests of the schemes alone)
+ * from a caller-supplied list */
+static const double *g_lifting_test_uniforms = NULL;
+static double lifting_uniform(OrcChain *c, uint32_t *draw) {
+    if (!c) return g_lifting_test_uniforms[(*draw)++];
+    return rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), (*draw)++);
+}
 static void lifting_insert(olifting *l, double rate, int id, int is_active, OrcChain *c, uint32_t *draw) {
     if (rate > 0.0) {
         l->sum_positive += rate;
         if (is_active) {
             l->active_recorded = 1;
-            double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), (*draw)++);
+            double u = lifting_uniform(c, draw);
             l->random_position += 0.0 + (rate - 0.0) * u; /* random.uniform(0.0, lifting_rate) */
         } else if (!l->active_recorded) {
             l->random_position += rate;
@@ -1392,7 +1399,7 @@ static int lifting_get(olifting *l, int kind, OrcChain *c, uint32_t *draw) {
         if (kind == ECMC_LIFTING_OUTSIDE_FIRST) {
             position = sum_negative - l->random_position;
         } else {
-            double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), (*draw)++);
+            double u = lifting_uniform(c, draw);
             position = 0.0 + (sum_negative - 0.0) * u;
         }
     }
@@ -1402,6 +1409,25 @@ static int lifting_get(olifting *l, int kind, OrcChain *c, uint32_t *draw) {
         if (position <= summed) return l->ids[i];
     }
     return l->n_negative ? l->ids[l->n_negative - 1] : -1;
+}
+
+/* The lifting schemes alone (unittests/test_lifting/test_{inside_first,outside_first,ratio}_lifting.py): insert n units
+ * (rate, identifier = index, active flag) in order, then ask for the next active identifier. uniforms: the values of
+ * random() behind the scheme's random.uniform calls, in call order. Returns the chosen index, -1 if no unit has a
+ * negative rate, -2 if the active unit was not recorded (LiftingSchemeError). */
+ORC_API int orc_lifting_choose(int kind, int n, const double *rates, int active_index, const double *uniforms) {
+    if (n > 8) return -3;
+    olifting lift;
+    uint32_t draw = 0;
+    lifting_reset(&lift);
+    g_lifting_test_uniforms = uniforms;
+    for (int i = 0; i < n; i++) lifting_insert(&lift, rates[i], i, i == active_index, NULL, &draw);
+    if (!lift.active_recorded) return -2;
+    return lifting_get(&lift, kind, NULL, &draw);
+}
+ORC_API void orc_bending_derivative(double prefactor, double equilibrium_angle, int dir, double speed, const double *s1,
+                                    const double *s2, int D, double *out) {
+    bending_derivative(prefactor, equilibrium_angle, dir, speed, s1, s2, D, out);
 }
 
 /* TwoCompositeObjectSummedBoundingPotentialEventHandler.send_event_time

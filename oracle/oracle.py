@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
     L.orc_cells_translate.argtypes = [i, ip, d, i, i]
     L.orc_cells_relative.argtypes = [i, ip, d, i, i]
     L.orc_nearby_cells.argtypes = [i, ip, i, d, i, ip]
+    L.orc_lifting_choose.argtypes = [i, i, p, i, p]
+    L.orc_bending_derivative.argtypes = [d, d, i, d, p, p, i, p]
     L.orc_chain_create.argtypes = [C.POINTER(abi.EcmcProgram)]
     L.orc_chain_create.restype = p
     L.orc_chain_destroy.argtypes = [p]
@@ -100,6 +102,23 @@ def time_from_float(t):
     oq, orr = C.c_double(), C.c_double()
     lib().orc_time_from_float(t, C.byref(oq), C.byref(orr))
     return oq.value, orr.value
+
+
+def lifting_choose(kind, rates, active_index, uniforms):
+    """Index of the next active unit after inserting (rate, index, index == active_index) in order into the lifting
+    scheme `kind` (abi.LIFTING_*); uniforms = the random() values behind the scheme's uniform draws, in call order."""
+    r = np.ascontiguousarray(rates, dtype=np.float64)
+    u = np.ascontiguousarray(list(uniforms) + [0.0, 0.0], dtype=np.float64)
+    return int(lib().orc_lifting_choose(kind, len(r), r.ctypes.data, active_index, u.ctypes.data))
+
+
+def bending_derivative(prefactor, equilibrium_angle, direction, speed, separation_one, separation_two):
+    s1 = np.ascontiguousarray(separation_one, dtype=np.float64)
+    s2 = np.ascontiguousarray(separation_two, dtype=np.float64)
+    out = np.empty(3)
+    lib().orc_bending_derivative(prefactor, equilibrium_angle, direction, speed, s1.ctypes.data, s2.ctypes.data, len(s1),
+                                 out.ctypes.data)
+    return out
 
 
 def _velocity(direction_or_velocity, dimension, speed=1.0):

@@ -364,6 +364,57 @@ def cell_bounding_traces():
                           ipcb=[1.5837], estimator=[1.5, 4], chain_time=0.78965, far_field=2))
 
 
+def lifting_vectors():
+    """The three lifting schemes and the bending potential of the running reference on random inputs: tests/golden/
+    lifting.npz. random.uniform is replaced by a + (b - a) * u with recorded u (what CPython computes from random())."""
+    rr.import_reference(REF)
+    import random as _random
+    from jellyfysh.lifting.inside_first_lifting import InsideFirstLifting
+    from jellyfysh.lifting.outside_first_lifting import OutsideFirstLifting
+    from jellyfysh.lifting.ratio_lifting import RatioLifting
+    from jellyfysh.potential.bending_potential import BendingPotential
+    rng = np.random.default_rng(4711)
+    n_cases, n_units = 600, 6
+    rates = np.zeros((n_cases, n_units))
+    active = np.zeros(n_cases, dtype=np.int32)
+    uniforms = rng.random((n_cases, 2))
+    expected = np.zeros((n_cases, 3), dtype=np.int32)
+    saved = _random.uniform
+    try:
+        for case in range(n_cases):
+            r = rng.normal(size=n_units) * rng.choice([0.1, 1.0, 30.0])
+            a = int(rng.integers(n_units))
+            r[a] = abs(r[a]) + 1e-3  # the active unit has a positive derivative
+            if not (np.delete(r, a) <= 0).any():
+                r[(a + 1) % n_units] = -abs(r[(a + 1) % n_units])
+            rates[case], active[case] = r, a
+            for k, cls in enumerate((InsideFirstLifting, OutsideFirstLifting, RatioLifting)):
+                draws = iter(uniforms[case])
+                _random.uniform = lambda lo, hi, _d=draws: lo + (hi - lo) * next(_d)
+                scheme = cls()
+                scheme.reset()
+                for i in range(n_units):
+                    scheme.insert(float(r[i]), (i,), i == a)
+                expected[case, k] = scheme.get_active_identifier()[0]
+    finally:
+        _random.uniform = saved
+    setting = _setting(10.0)
+    bending = BendingPotential(equilibrium_angle=1.9764, prefactor=75.9)
+    n_b = 400
+    s1 = rng.normal(size=(n_b, 3)) * 1.0
+    s2 = rng.normal(size=(n_b, 3)) * 1.0
+    direction = rng.integers(3, size=n_b).astype(np.int32)
+    triples = np.zeros((n_b, 3))
+    for i in range(n_b):
+        triples[i] = bending.derivative(_unit(int(direction[i]), speed=1.7), [float(x) for x in s1[i]],
+                                        [float(x) for x in s2[i]])
+    setting.reset()
+    np.savez_compressed(os.path.join(HERE, "lifting.npz"), rates=rates, active=active, uniforms=uniforms,
+                        expected=expected, bending_s1=s1, bending_s2=s2, bending_direction=direction,
+                        bending_triples=triples, bending_params=np.array([75.9, 1.9764, 1.7]))
+    print("lifting.npz:", n_cases, "lifting cases,", n_b, "bending triples")
+
+
 def dipole_traces():
     # C1: the shipped hard_disk_dipoles_cells.ini from the shipped PDB start configuration (81 dipoles = 162 disks,
     # 13^2 leaf-level cells, unbounded occupancy, hard-sphere pairs + hard-dipole tether, root units follow)
@@ -406,9 +457,11 @@ def water_traces():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "water"]
+    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "water", "lifting"]
     if "water" in which:
         water_traces()
+    if "lifting" in which:
+        lifting_vectors()
     if "dipoles" in which:
         dipole_traces()
     if "cell_bounding" in which:
