@@ -297,3 +297,69 @@ def test_shipped_water_config_matches_reference_statistics(tmp_path):
     distance = np.max(np.abs(ours - cdf))
     print("water O-O KS distance", distance, "samples", len(samples), "median", np.median(samples), stats)
     assert distance < 1.95 / np.sqrt(chains * 5) + 5.0e-3, distance
+
+
+def _dipole_pair_start(seed, length=1.0):
+    """Two dipoles (charges +1, -1 at separation ~0.1) with centres at least 0.3 apart, random orientations."""
+    rng = np.random.default_rng(seed)
+    while True:
+        centres = rng.uniform(0.0, length, size=(2, 3))
+        d = np.mod(centres[1] - centres[0] + length / 2, length) - length / 2
+        if np.linalg.norm(d) > 0.3:
+            break
+    roots = np.empty((2, 3))
+    leaves = np.empty((2, 2, 3))
+    for k in range(2):
+        axis = rng.normal(size=3)
+        axis *= 0.05 / np.linalg.norm(axis)
+        roots[k] = centres[k] % length
+        leaves[k, 0] = (centres[k] + axis) % length
+        leaves[k, 1] = (centres[k] - axis) % length
+    return roots, leaves
+
+
+def test_shipped_dipole_config_matches_reference_statistics(tmp_path):
+    """dipoles/cell_veto.ini of 2018_JCP_149_064113 (two dipoles: composite-object Coulomb handlers with cell veto on
+    anisotropic 3 x 5 x 7 root-level cells, harmonic bond, 1/r^6 repulsion between the opposite charges of different
+    dipoles as a factor between objects), unchanged except for the mediator line, run length, sampling interval and
+    output file: the separations between like and unlike charges of different dipoles follow the cumulative histograms
+    the reference ships (ReferenceDataDipoles_13.dat / _14.dat)."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import kat_replay as kr
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    chains, end, interval = 1024, 400.0, 4.0
+    ini = configs.shipped_ini(REF, "2018_JCP_149_064113", "dipoles", "cell_veto.ini")
+    ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 31" % chains)
+    ini = ini.replace("end_of_run_time = 500000", "end_of_run_time = %r" % end)
+    ini = ini.replace("sampling_interval = 0.56789", "sampling_interval = %r" % interval)
+    ini = ini.replace("output/2018_JCP_149_064113/dipoles/SamplesOfSeparation_CellVeto.dat", str(tmp_path / "separation.dat"))
+    assert "cuda_batched_mediator" in ini and str(tmp_path) in ini and "end_of_run_time = 400.0" in ini
+    starts = [_dipole_pair_start(900 + c) for c in range(chains)]
+    composites = (np.concatenate([r for r, _ in starts]), np.concatenate([l for _, l in starts]))
+    mediator, setting = build_reference_graph(ini, composites=composites)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["capacity_errors"] == 0 and stats["factor_pair_events"] > 0 and stats["bond_events"] > 0
+    ref = kr.load_npz("reference_cdfs")
+    per_chain = int(end / interval)
+    for name, pairs in (("13", 2), ("14", 2)):
+        samples = np.loadtxt(tmp_path / ("separation_%s.dat" % name), comments="#")
+        assert len(samples) == chains * per_chain * pairs
+        samples = samples.reshape(per_chain, chains * pairs)[per_chain // 2:].ravel()
+        x, cdf = ref["dipoles_%s_x" % name], ref["dipoles_%s_cdf" % name]
+        edges = x + 0.5 * (x[1] - x[0])
+        ours = np.searchsorted(np.sort(samples), edges, side="right") / len(samples)
+        distance = np.max(np.abs(ours - cdf))
+        print("dipoles", name, "KS distance", distance, "samples", len(samples), stats)
+        assert distance < 1.95 / np.sqrt(chains * 5) + 5.0e-3, (name, distance)
