@@ -37,11 +37,15 @@ def test_struct_layouts_match_the_header(tmp_path):
               "EcmcVetoTables": ["upper", "lower", "bounds"],
               "EcmcProgram": ["dimension", "system_length", "cells_per_side", "pair_handler", "pair_potential",
                               "pair_bounding_potential", "veto_enabled", "veto_potential", "veto_target_charge",
-                              "veto_tables", "chain_time", "initial_active", "seed"],
+                              "veto_tables", "chain_time", "initial_active", "seed", "nodes_per_root", "bonds",
+                              "bond_potential", "cell_level", "composite_lifting", "inter_factors", "inter_potential",
+                              "bending_children", "bending_separations", "boundary_keeps_factors", "bending_potential",
+                              "bending_offset", "bending_max_displacement"],
               "EcmcChainState": ["active", "time_q", "eoc_next_active", "event_counter", "stream", "pending_q",
-                                 "pending_stamp_r"],
+                                 "pending_stamp_r", "pending_root_position", "kept_kind", "kept_q", "kept_rate",
+                                 "kept_stamp_r"],
               "EcmcEventRecord": ["kind", "n_candidates", "time_q", "active_pos"],
-              "EcmcStats": ["events", "candidates", "capacity_errors"]}
+              "EcmcStats": ["events", "candidates", "capacity_errors", "bond_events", "factor_pair_events", "pair_targets"]}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, "int main(void) {"]
     for struct, names in fields.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (struct, struct))
