@@ -543,11 +543,20 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         const int IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, MIC = ECMC_POT_MERGED_IMAGE_COULOMB,
                   DEP = kPotHarmonic, LJ = ECMC_POT_LENNARD_JONES;
         MoleculeKernel kernel;
-        if (water) kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kWarpsPerBlock>
-                                      : molecule_kernel<IPCB, MIC, DEP, LJ, false, kWarpsPerBlock>;
-        else kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kWarpsPerBlock>
-                                : molecule_kernel<-1, -1, -1, -1, false, kWarpsPerBlock>;
-        kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
+        constexpr int kAlignedWarps = 8;
+        bool aligned = true;
+        if (const char *env = std::getenv("ECMC_MOLECULE_ALIGNED")) aligned = std::atoi(env) != 0;
+        if (water && aligned)
+            kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kAlignedWarps, true>
+                               : molecule_kernel<IPCB, MIC, DEP, LJ, false, kAlignedWarps, true>;
+        else if (water)
+            kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kWarpsPerBlock, false>
+                               : molecule_kernel<IPCB, MIC, DEP, LJ, false, kWarpsPerBlock, false>;
+        else
+            kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kWarpsPerBlock, false>
+                               : molecule_kernel<-1, -1, -1, -1, false, kWarpsPerBlock, false>;
+        const int warps = water && aligned ? kAlignedWarps : kWarpsPerBlock;
+        kernel<<<(h->n_chains + warps - 1) / warps, warps * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
     } else {
         const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
         kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);

@@ -155,7 +155,10 @@ ECMC_D double pair_derivative_lab(const PotentialParams &p, int dir, double spee
 // CAND / REAL / BOND / INTER: compile-time kinds of the bounding potential of the composite pairs, of the potential the
 // composite events are confirmed against (pair and cell veto), of the intramolecular pair factors and of the factors
 // between objects; -1 = decided at run time (the generic instantiation is four times the code).
-template <int CAND, int REAL, int BOND, int INTER, bool RECORD, int WARPS>
+// ALIGNED: the warps of a CTA meet at a barrier before every event. The kernel is bound by instruction fetch (thousands
+// of instructions per event, a handful of warps per SM, each somewhere else in the code); warps that walk through the
+// event together fetch every instruction once for all of them.
+template <int CAND, int REAL, int BOND, int INTER, bool RECORD, int WARPS, bool ALIGNED>
 __global__ void __launch_bounds__(WARPS * 32)
 molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ MoleculeProgram M, const DeviceState S,
                 const RunArgs A) {
@@ -164,7 +167,10 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int chain = S.first_chain + blockIdx.x * WARPS + warp;
-    if (chain >= S.first_chain + S.n_chains) return;
+    if (chain >= S.first_chain + S.n_chains) {
+        if (ALIGNED) while (!__syncthreads_and(1)) {}  // keep the barriers of the other warps complete
+        return;
+    }
     double *trig = trig_all + warp * kTrigDoubles;
     int *item_code = items_all + warp * 2 * kItemCapacity;  // type | sequence << 4
     int *item_target = item_code + kItemCapacity;
@@ -208,7 +214,15 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
 
     auto set_dir = [&](Vec3 &v, double value) { if (dir == 0) v.x = value; else if (dir == 1) v.y = value; else v.z = value; };
 
-    while (n_events < max_events) {
+    bool done = false;
+    while (true) {
+        if (ALIGNED) {
+            const bool finished = done || n_events >= max_events;
+            if (__syncthreads_and(finished)) break;
+            if (finished) continue;
+        } else if (n_events >= max_events) {
+            break;
+        }
         const StreamKey key = {P.seed, stream, ev};
         const int active_root = active / npr, active_child = active - active_root * npr;
         Time bt = time_inf();
@@ -496,6 +510,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                 }
             }
             stopped_by_time = true;
+            if (ALIGNED) { done = true; continue; }
             break;
         }
         if (was_pending) {
