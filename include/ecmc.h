@@ -137,7 +137,10 @@ typedef struct EcmcProgram {
     int32_t abi_version;      /* must be ECMC_ABI_VERSION */
     int32_t dimension;        /* 2 or 3; HypercubicSetting, jellyfysh/setting/hypercubic_setting.py:200-223 */
     int32_t n_particles;      /* point masses (leaf units) per chain */
-    int32_t reserved0;
+    int32_t no_cells;         /* 1: the configuration has no cell system (no internal state in the TagActivator; the pair
+                               * factors come from a FactorTypeMapInStateTagger, factor_type_map_in_state_tagger.py:83-107):
+                               * every other unit is a candidate of every event and there are no cell-boundary events.
+                               * Requires cells_per_side = 1, neighbor_layers = 0, max_surplus >= units - 1, no far field. */
     double system_length;
     double beta;
     /* CuboidPeriodicCells + SingleActiveCellOccupancy */

@@ -91,7 +91,7 @@ class EcmcVetoTables(C.Structure):
 
 class EcmcProgram(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("dimension", C.c_int32), ("n_particles", C.c_int32),
-                ("reserved0", C.c_int32),
+                ("no_cells", C.c_int32),
                 ("system_length", C.c_double), ("beta", C.c_double),
                 ("cells_per_side", C.c_int32 * ECMC_MAX_DIM), ("neighbor_layers", C.c_int32),
                 ("max_occupants", C.c_int32), ("max_surplus", C.c_int32),

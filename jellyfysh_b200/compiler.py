@@ -145,24 +145,33 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
 
     # ---- cell occupancy (tag_activator.py:82-135 keeps the internal states in _internal_states)
     internal_states = list(activator._internal_states)
-    if len(internal_states) != 1 or "SingleActiveCellOccupancy" not in _class_names(internal_states[0]):
-        raise _configuration_error("exactly one SingleActiveCellOccupancy internal state is required")
-    occupancy = internal_states[0]
-    cells = occupancy.cells
-    if "CuboidPeriodicCells" not in _class_names(cells):
-        raise _configuration_error("cells must be CuboidPeriodicCells")
-    molecules = levels == 2 and occupancy.cell_level == 1  # composite objects in root-level cells (water)
-    if occupancy.cell_level != levels and not molecules:
-        raise _configuration_error("cell_level must be 1 or the number of node levels")
-    max_occupants = occupancy._maximum_number_occupants  # cell_occupancy.py:70-72
-    unbounded = max_occupants <= 0
-    if unbounded:
-        # the reference keeps plain lists per cell and never uses the surplus; the device keeps `occupant_capacity`
-        # slots per cell and no surplus, so that an overflow surfaces as a capacity error
-        max_occupants, max_surplus = occupant_capacity, 0
-    cells_per_side = list(cells._cells_per_side)
-    neighbor_layers = cells._neighbor_layers
-    cell_objects = list(cells.yield_cells())  # flat index order (cuboid_cells.py:144-146)
+    # No internal state at all: the configuration has no cell system and its pair factors come from factor type maps
+    # (coulomb_atoms/power_bounded.ini). On the device that is EcmcProgram.no_cells: every other unit is a candidate
+    # of every event and there are no cell-boundary events.
+    no_cells = not internal_states
+    if no_cells:
+        if levels != 1:
+            raise _configuration_error("composite point objects without a cell system are not supported")
+        molecules, max_occupants, cells_per_side, neighbor_layers, cell_objects = False, 1, [1] * setting.dimension, 0, []
+    else:
+        if len(internal_states) != 1 or "SingleActiveCellOccupancy" not in _class_names(internal_states[0]):
+            raise _configuration_error("at most one internal state, a SingleActiveCellOccupancy, is supported")
+        occupancy = internal_states[0]
+        cells = occupancy.cells
+        if "CuboidPeriodicCells" not in _class_names(cells):
+            raise _configuration_error("cells must be CuboidPeriodicCells")
+        molecules = levels == 2 and occupancy.cell_level == 1  # composite objects in root-level cells (water)
+        if occupancy.cell_level != levels and not molecules:
+            raise _configuration_error("cell_level must be 1 or the number of node levels")
+        max_occupants = occupancy._maximum_number_occupants  # cell_occupancy.py:70-72
+        unbounded = max_occupants <= 0
+        if unbounded:
+            # the reference keeps plain lists per cell and never uses the surplus; the device keeps `occupant_capacity`
+            # slots per cell and no surplus, so that an overflow surfaces as a capacity error
+            max_occupants, max_surplus = occupant_capacity, 0
+        cells_per_side = list(cells._cells_per_side)
+        neighbor_layers = cells._neighbor_layers
+        cell_objects = list(cells.yield_cells())  # flat index order (cuboid_cells.py:144-146)
 
     # ---- handlers by kind
     pair_handlers, veto_handlers, boundary_handlers, eoc_handlers, start_handlers, control = [], [], [], [], [], []
@@ -175,7 +184,19 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                 factor_tagger_of[id(handler)] = tagger
     for handler in activator.get_event_handlers():
         names = _class_names(handler)
-        if id(handler) in factor_tagger_of:
+        if id(handler) in factor_tagger_of and levels == 1:
+            # point masses: the factor type map lists the pair factors themselves ("[0, 1], Coulomb" = the active
+            # atom with every other atom, factor_type_maps.py:333-347)
+            factor_map = factor_tagger_of[id(handler)]._factor_type_map
+            entries = {tuple(indices) for lists in factor_map.map.values() for indices in lists}
+            if not no_cells or entries != {(0, 1)}:
+                raise _configuration_error("factor type maps of point masses must hold the one pair factor [0, 1] "
+                                           "and need a configuration without cells")
+            if not names & {"TwoLeafUnitBoundingPotentialEventHandler", "TwoLeafUnitEventHandler"}:
+                raise _configuration_error("factor-type-map handler {0} has no device implementation"
+                                           .format(type(handler).__name__))
+            pair_handlers.append(handler)
+        elif id(handler) in factor_tagger_of:
             if "FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential" in names:
                 bending_handlers.append(handler)
             elif "TwoLeafUnitEventHandler" in names:
@@ -203,9 +224,11 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             raise _configuration_error("dumping handlers are not supported (device state is not picklable)")
         else:
             raise _configuration_error("event handler {0} has no device implementation".format(type(handler).__name__))
-    if len(eoc_handlers) != 1 or len(start_handlers) != 1 or not boundary_handlers:
+    if len(eoc_handlers) != 1 or len(start_handlers) != 1 or (not boundary_handlers and not no_cells):
         raise _configuration_error("exactly one end-of-chain handler, one start-of-run handler and a cell-boundary "
                                    "handler are required")
+    if no_cells and (boundary_handlers or veto_handlers or bounding_handlers):
+        raise _configuration_error("cell handlers without a cell system")
     start, eoc = start_handlers[0], eoc_handlers[0]
     velocity = list(start._initial_velocity)  # initial_chain_start_of_run_event_handler.py:86-88
     moving = [d for d, v in enumerate(velocity) if v != 0.0]
@@ -222,7 +245,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                              max_occupants=max_occupants,
                              max_surplus=n_particles if max_surplus is None else max_surplus,
                              chain_time=eoc._chain_time, speed=velocity[moving[0]], initial_direction=moving[0],
-                             initial_active=initial_leaf, seed=seed)
+                             initial_active=initial_leaf, seed=seed, no_cells=no_cells)
 
     # ---- composite point objects: factors of the factor type map
     inter_factors, inter_potential, bending = [], None, None

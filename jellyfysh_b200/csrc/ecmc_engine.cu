@@ -246,6 +246,15 @@ int build_device_program(EcmcHandle *h) {
     if (p.initial_active < 0 || p.initial_active >= p.n_particles || p.initial_direction < 0 ||
         p.initial_direction >= p.dimension)
         return fail(h, ECMC_ERR_INVALID, "initial_active / initial_direction out of range");
+    if (p.no_cells) {
+        for (int k = 0; k < p.dimension; k++)
+            if (p.cells_per_side[k] != 1) return fail(h, ECMC_ERR_INVALID, "no_cells needs cells_per_side = 1");
+        const int units = p.cell_level == 1 && p.nodes_per_root > 1 ? p.n_particles / p.nodes_per_root : p.n_particles;
+        if (p.neighbor_layers != 0 || p.max_occupants != 1 || p.max_surplus < units - 1 || p.veto_enabled != ECMC_FAR_NONE)
+            return fail(h, ECMC_ERR_INVALID, "no_cells needs neighbor_layers = 0, max_occupants = 1, max_surplus >= units - 1 "
+                                             "and no far field");
+    }
+    d.no_cells = p.no_cells ? 1 : 0;
     d.dimension = p.dimension;
     d.n_particles = p.n_particles;
     d.n_cells = 1;
@@ -480,11 +489,11 @@ EventKernel pick_kernel(const DeviceProgram &d, bool record) {
         return pick_far_pairs<-1, -1, -1>(record);
     }
     // the Lennard-Jones kernels assume chargeless handlers and modular cell translations (FAST in event_kernel)
-    const bool fast = !d.pair_use_charge && !d.veto_use_charge && d.translate_modular;
+    const bool fast = !d.pair_use_charge && !d.veto_use_charge && d.translate_modular && !d.no_cells;
     if (fast && cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record, single);
     if (fast && cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record, single);
     if (cand == HS && real == 0 && veto == 0) return pick_record<ECMC_POT_HARD_SPHERE, 0, 0>(record, false);
-    if (cand == IPCB && real == MIC && veto == MIC)
+    if (cand == IPCB && real == MIC && veto == MIC && !d.no_cells)
         return pick_record<ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, ECMC_POT_MERGED_IMAGE_COULOMB, ECMC_POT_MERGED_IMAGE_COULOMB>(record, single);
     return pick_record<-1, -1, -1>(record, false);
 }

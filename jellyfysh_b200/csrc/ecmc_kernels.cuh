@@ -342,6 +342,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     const bool translate_modular = FAST ? true : P.translate_modular != 0;
     const bool has_pairs = FAST ? true : P.pair_handler != ECMC_PAIR_NONE;
     const int dimension = FAST ? 3 : P.dimension;
+    const bool has_boundary = FAST ? true : P.no_cells == 0;  // without a cell system there is no cell boundary
     const bool cand_needs_du = needs_potential_change(resolve_kind<CAND>(P.cand_potential.kind));
     const bool has_veto = VETO != 0 && !FAR_PAIRS && P.veto_enabled == ECMC_FAR_CELL_VETO;
     const bool has_far_pairs = VETO != 0 && FAR_PAIRS;
@@ -443,7 +444,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                 if (entry >= 0 && entry < count) { target = list_target[entry]; s = list_seq[entry]; }
                 const bool is_pair = target >= 0;
                 const bool is_veto = entry == -2 && has_veto;
-                const bool is_boundary = entry == -1;
+                const bool is_boundary = entry == -1 && has_boundary;
                 Moving tp;
                 if (is_pair) {
                     if (from_cache && base == 0) {

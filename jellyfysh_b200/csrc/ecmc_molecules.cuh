@@ -264,7 +264,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             const int bending_base = inter_base + (factors_kept ? 0 : M.n_inter * n_roots);
             const int veto_base = bending_base + ((!factors_kept && M.bending_enabled) ? 1 : 0);
             const int boundary_base = veto_base + (P.veto_enabled == ECMC_FAR_CELL_VETO ? 1 : 0);
-            const int n_scan = boundary_base + 1;
+            const int n_scan = boundary_base + (P.no_cells ? 0 : 1);  // no cell system: no cell boundary
             unsigned long long best_key = 0x7ff0000000000000ull;
             double best_x = INFINITY;
             int best_seq = kSeqNone;

@@ -56,7 +56,7 @@ struct DeviceProgram {
     int pair_handler, pair_use_charge;
     int veto_enabled, veto_use_charge;
     uint32_t seed;
-    int pad;
+    int no_cells;  // EcmcProgram.no_cells: every other unit is a candidate, no cell-boundary events
     double length, half_length, beta, speed, chain_time, veto_target_charge;
     double side_length[3];
     // cand: the invertible potential the pair candidates are drawn from (the pair potential of a

@@ -12,7 +12,12 @@ class ProgramBuilder:
 
     def __init__(self, dimension, n_particles, system_length, beta, cells_per_side, neighbor_layers=1,
                  max_occupants=1, max_surplus=64, chain_time=1.0, speed=1.0, initial_direction=0,
-                 initial_active=0, seed=0):
+                 initial_active=0, seed=0, no_cells=False):
+        """no_cells: the configuration has no cell system (every other unit is a candidate of every event, no
+        cell-boundary events); cells_per_side and neighbor_layers are then ignored."""
+        if no_cells:
+            cells_per_side, neighbor_layers, max_occupants = [1] * dimension, 0, 1
+            max_surplus = max(max_surplus, n_particles)
         self.program = abi.EcmcProgram()
         p = self.program
         p.abi_version = abi.ECMC_ABI_VERSION
@@ -31,6 +36,7 @@ class ProgramBuilder:
         p.initial_direction = initial_direction
         p.initial_active = initial_active
         p.seed = seed
+        p.no_cells = int(no_cells)
         self._keep = []
         self.tables = None
 

@@ -1664,7 +1664,7 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
             candidate cand = veto_candidate(c);
             CONSIDER(cand);
         }
-        {
+        if (!c->prog.no_cells) {
             candidate cand = root_boundary_candidate(c, &boundary_position);
             n_cand++;
             if (lt_candidate(&cand, &best)) { best = cand; best_from_kept = 0; }
@@ -1908,7 +1908,7 @@ static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
             candidate cand = veto_candidate(c);
             if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
         }
-        {
+        if (!c->prog.no_cells) {
             candidate cand = boundary_candidate(c, &boundary_position);
             n_cand++;
             if (lt_candidate(&cand, &best)) best = cand;

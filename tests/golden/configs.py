@@ -495,3 +495,26 @@ def water_start(n_molecules, system_length, seed=1000, bond_length=1.012, bond_a
         leaves[m, 1] = oxygen % system_length
         leaves[m, 2] = (oxygen + oh_two) % system_length
     return roots, leaves
+
+
+def coulomb_power_bounded_ini(ref_root, n_atoms=2, end_of_run_time=1.0e9, sampling=False, output="/dev/null"):
+    """The shipped coulomb_atoms/power_bounded.ini -- no cell system: the Coulomb pair factors of the active atom with
+    every other atom come from a FactorTypeMapInStateTagger ("[0, 1], Coulomb") and are bounded by the inverse-power
+    Coulomb bounding potential -- for n_atoms atoms; only the size of the system, the run length and the output change."""
+    import os
+    text = shipped_ini(ref_root, "2018_JCP_149_064113", "coulomb_atoms", "power_bounded.ini")
+    text = text.replace("filename = config_files/", "filename = " + os.path.join(ref_root, "jellyfysh", "config_files") + "/")
+    text = text.replace("number_of_root_nodes = 2", f"number_of_root_nodes = {n_atoms}")
+    # the shipped file is sized for two atoms: one handler per possible partner
+    text = text.replace("number_event_handlers = 1", f"number_event_handlers = {max(n_atoms - 1, 1)}", 1)
+    text = text.replace("end_of_run_time = 100000", f"end_of_run_time = {end_of_run_time!r}")
+    text = text.replace("output/2018_JCP_149_064113/coulomb_atoms/SamplesOfSeparation_PowerBounded.dat", output)
+    if not sampling:
+        text = text.replace("    sampling (no_in_state_tagger),\n", "")
+        text = text.replace(", sampling", "")
+        start, rest = text.split("[Sampling]")
+        rest = rest.split("[EndOfChain]", 1)[1]
+        text = start + "[EndOfChain]" + rest
+        text = text.replace("output_handlers = separation_output_handler\n", "")
+        text = text.split("[SeparationOutputHandler]")[0]
+    return text

@@ -350,6 +350,17 @@ def chain_traces():
                           ipcb=[1.5837], estimator=[1.0, 4], chain_time=0.78965))
 
 
+def no_cell_traces():
+    # Coulomb atoms without a cell system (shipped coulomb_atoms/power_bounded.ini, sized for 6 atoms): the pair factors
+    # come from the factor type map, every other atom is a candidate of every event, no cell-boundary events
+    n, length = 6, 1.0
+    pos = configs.uniform_start(n, length, seed=21)
+    chain_trace("trace_coulomb_power_bounded", configs.coulomb_power_bounded_ini(REF, n_atoms=n), pos, seed=14, stream=7,
+                n_events=4000, snapshot_every=250, charges=np.ones(n),
+                meta=dict(n=n, cells_per_side=[1, 1, 1], system_length=length, beta=2.0, mic=[1.0, 3.45, 6, 2],
+                          ipcb=[1.5837], chain_time=0.78965, far_field=0))
+
+
 def cell_bounding_traces():
     # Coulomb atoms with the far field through TwoLeafUnitCellBoundingPotentialEventHandler (shipped
     # coulomb_atoms/cell_bounded.ini shape)
@@ -457,7 +468,9 @@ def water_traces():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "water", "lifting"]
+    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "water", "lifting", "no_cells"]
+    if "no_cells" in which:
+        no_cell_traces()
     if "water" in which:
         water_traces()
     if "lifting" in which:

@@ -203,6 +203,10 @@ class ReferenceRun:
             return EVENT_PAIR
         if names & {"TwoLeafUnitEventHandler", "TwoLeafUnitBoundingPotentialEventHandler"}:
             local = self._factor_map_handlers().get(id(handler))
+            if self.setting.number_of_node_levels == 1:
+                # point masses without a cell system: the factor type map lists the pair factors themselves
+                # (coulomb_atoms/power_bounded.ini, "[0, 1], Coulomb")
+                return EVENT_PAIR
             return EVENT_PAIR if local is None else (EVENT_BOND if local else EVENT_FACTOR_PAIR)
         return HOST_EVENT
 
@@ -464,7 +468,10 @@ class ReferenceRun:
         return np.array(self.records, dtype=RECORD_DTYPE)
 
     def _snapshot(self, max_occupants):
-        occ, surplus = self.occupancy(max_occupants)
+        if self.mediator._activator._internal_states:
+            occ, surplus = self.occupancy(max_occupants)
+        else:  # no cell system
+            occ, surplus = np.full((1, max_occupants), -1, dtype=np.int32), np.zeros(0, dtype=np.int32)
         active, direction, _, stamp = self._active()
         self.snapshots.append({"event": self.events, "positions": self.positions(), "roots": self.roots(),
                                "occupants": occ,

@@ -118,6 +118,36 @@ def test_coulomb_graph_compiles_with_charges():
         setting.reset()
 
 
+def test_power_bounded_graph_without_cells_compiles_and_replays(oracle):
+    """The shipped coulomb_atoms/power_bounded.ini (no cell system, pair factors from the factor type map) sized for
+    six atoms -> compiler -> oracle chain reproduces the reference trace of the same configuration bit for bit."""
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_coulomb_power_bounded")
+    mediator, setting = build_reference_graph(configs.coulomb_power_bounded_ini(REF, n_atoms=int(g["meta_n"]),
+                                                                                end_of_run_time=5.0), g["positions0"])
+    try:
+        state = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, state, seed=int(g["seed"][0]))
+        p = compiled.builder.program
+        assert p.no_cells == 1 and p.veto_enabled == 0 and p.max_surplus >= p.n_particles - 1
+        assert [p.cells_per_side[d] for d in range(3)] == [1, 1, 1] and p.neighbor_layers == 0
+        assert p.pair_handler == abi.PAIR_TWO_LEAF_UNIT_BOUNDING and p.pair_use_charge == 1
+        assert p.pair_potential.kind == abi.POT_MERGED_IMAGE_COULOMB
+        assert p.pair_bounding_potential.kind == abi.POT_INVERSE_POWER_COULOMB_BOUNDING
+        assert compiled.charge_name == "electric_charge" and p.chain_time == float(g["meta_chain_time"])
+        positions, charges, _ = compiler.positions_and_charges(state, compiled.charge_name)
+        assert np.array_equal(positions, g["positions0"])
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions, charges)
+        chain.start(stream=int(g["seed"][1]))
+        records = g["records"][:1500]
+        n, rec = chain.run(max_events=len(records), record=len(records))
+        assert n == len(records) and tu.records_equal_discrete(rec, records)
+        assert np.array_equal(rec["time_q"], records["time_q"]) and np.array_equal(rec["time_r"], records["time_r"])
+    finally:
+        setting.reset()
+
+
 def test_hard_disk_dipole_graph_compiles_and_replays(oracle):
     """C1: the shipped hard_disk_dipoles_cells.ini (composite point objects, leaf-level cells, unbounded occupancy,
     hard-sphere pairs + hard-dipole tether from the factor type map) -> compiler -> oracle chain reproduces the

@@ -195,6 +195,55 @@ def test_coulomb_batch_against_oracle(oracle):
     assert stats["pair_events"] > 100 and stats["veto_events"] > 1000
 
 
+@pytest.mark.parametrize("name", tu.NO_CELL_TRACES)
+def test_no_cells_reference_trace_replay(oracle, name):
+    """No cell system (shipped coulomb_atoms/power_bounded.ini shape): every other atom is a candidate of every event,
+    no cell-boundary events; every event of the reference trace on the device.
+
+    Every event of this configuration is a pair event of a few strongly coupled atoms, and half of them lift: the chain
+    is chaotic and amplifies the last-bit differences between the device arithmetic and libm by about 2 % per event
+    (measured on B200: 1.2e-12 after 500 events). The trace is therefore replayed in stretches of 100 events; at the
+    start of each stretch the device takes the state of the oracle, which reproduces the reference bit for bit
+    (tests/test_oracle_traces.py::test_no_cells_chain_replay_bit_exact)."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    stretch = 100
+    chain = oracle.OracleChain(tu.no_cells_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.start(stream=int(g["seed"][1]))
+    with engine.Engine(tu.no_cells_builder_of(g, ProgramBuilder), n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None], tu.charges_of(g)[None])
+        eng.start(first_stream=int(g["seed"][1]))
+        for done in range(0, len(records), stretch):
+            count = min(stretch, len(records) - done)
+            if done:
+                eng.upload_positions(chain.positions()[None], tu.charges_of(g)[None])
+                eng.set_chain_states(np.frombuffer(bytes(chain.state()), dtype=abi.chain_state_dtype()))
+                occupants, surplus = chain.cells()
+                eng.set_cells(occupants[None], [surplus])
+            rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+            assert stats["events"] == count and stats["capacity_errors"] == 0 and stats["boundary_events"] == 0
+            assert_records_match(rec[0], records[done:done + count], 1.0, f"{name}[{done}:{done + count}]")
+            n, ours = chain.run(max_events=count, record=count)
+            assert n == count and tu.records_equal_discrete(ours, records[done:done + count])
+            assert np.max(np.abs(eng.download_positions()[0] - chain.positions())) < RTOL
+
+
+def test_no_cells_batch_against_oracle(oracle):
+    """The same structure on a batch: 40 atoms of both signs per chain (two passes of pair lanes), 9 chains."""
+    n, length = 40, 1.0
+    mic = abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, 1.0, 3.45, 6, 2)
+    ipcb = abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, 1.5837)
+    pb = ProgramBuilder(3, n, length, 2.0, [1, 1, 1], 0, chain_time=0.78965, seed=33, no_cells=True)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT_BOUNDING, mic, ipcb, use_charge=True)
+    rng = np.random.default_rng(78)
+    n_chains = 9
+    positions = rng.uniform(0.0, length, size=(n_chains, n, 3))
+    charges = np.where(rng.random((n_chains, n)) < 0.5, 1.0, -1.0)
+    stats = _compare_batch_with_oracle(oracle, pb, positions, charges, 600, 4, "no cells", resync_every=100)
+    assert stats["pair_events"] > 1000 and stats["boundary_events"] == 0 and stats["veto_events"] == 0
+
+
 def test_coulomb_cell_bounding_batch_against_oracle(oracle):
     """Far field through TwoLeafUnitCellBoundingPotentialEventHandler: one candidate per occupied non-nearby cell
     (coulomb_atoms/cell_bounded.ini shape), charges of both signs, more occupied far cells than one pass holds."""

@@ -104,10 +104,12 @@ def test_many_chains_from_the_input_handler(tmp_path):
 
 
 @pytest.mark.parametrize("config,output", [("cell_veto.ini", "SamplesOfSeparation_CellVeto.dat"),
-                                           ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat")])
+                                           ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat"),
+                                           ("power_bounded.ini", "SamplesOfSeparation_PowerBounded.dat")])
 def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path, config, output):
     """The statistical check of the reference (README.md:169-189): the shipped coulomb_atoms/cell_veto.ini (far field
-    through the cell-veto handler) and cell_bounded.ini (through the cell-bounding potential handlers), run
+    through the cell-veto handler), cell_bounded.ini (through the cell-bounding potential handlers) and
+    power_bounded.ini (no cell system: the pair factor of the factor type map with its bounding potential), run
     unchanged except for the mediator line, the output file and the run length, must reproduce the cumulative
     histogram of the pair separation that the reference ships (ReferenceDataCoulombAtoms.dat, reversible Monte Carlo;
     fixture tests/golden/reference_cdfs.npz). 2048 chains in parallel give ~10^5 samples in a few seconds."""
@@ -119,7 +121,8 @@ def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path, con
     jellyfysh_b200.install()
     from jellyfysh.base.exceptions import EndOfRun
     path = os.path.join(REF, "jellyfysh", "config_files", "2018_JCP_149_064113", "coulomb_atoms", config)
-    ini = open(path).read()
+    ini = open(path).read().replace("filename = config_files/",
+                                    "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
     chains = 2048
     ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
     ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 11" % chains)

@@ -91,6 +91,37 @@ def test_cell_bounding_chain_replay_bit_exact(oracle, name):
     assert np.array_equal(chain.positions(), g["final_positions"])
 
 
+@pytest.mark.parametrize("name", tu.NO_CELL_TRACES)
+def test_no_cells_chain_replay_bit_exact(oracle, name):
+    """No cell system (shipped coulomb_atoms/power_bounded.ini, six atoms): the pair factors of the factor type map make
+    every other atom a candidate of every event (n_candidates = finite pair candidates + end of chain), there are no
+    cell-boundary events."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    chain = oracle.OracleChain(tu.no_cells_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        for f in tu.DISCRETE_FIELDS:
+            assert np.array_equal(rec[f], ref[f]), (f, done + int(np.nonzero(rec[f] != ref[f])[0][0]))
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            st = chain.state()
+            assert (st.active, st.direction) == (int(g["snap_active"][k]), int(g["snap_direction"][k]))
+            assert (st.time_q, st.time_r) == tuple(g["snap_time"][k])
+    assert (records["kind"] == 3).sum() == 0 and (records["kind"] == 1).sum() > 3000
+    assert np.array_equal(chain.positions(), g["final_positions"])
+    assert chain.stats()["capacity_errors"] == 0
+
+
 @pytest.mark.parametrize("name", tu.DIPOLE_TRACES)
 def test_composite_chain_replay_bit_exact(oracle, name):
     """C1, the shipped hard_disk_dipoles_cells.ini from the shipped start configuration: composite point objects

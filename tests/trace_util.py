@@ -6,6 +6,7 @@ from jellyfysh_b200 import abi
 
 TRACES = ["trace_lj_small", "trace_lj_surplus", "trace_coulomb_small", "trace_coulomb_surplus"]
 CELL_BOUNDING_TRACES = ["trace_coulomb_cell_bounded"]
+NO_CELL_TRACES = ["trace_coulomb_power_bounded"]
 DIPOLE_TRACES = ["trace_hard_disk_dipoles"]
 WATER_TRACES = ["trace_water", "trace_water_dense"]
 DISCRETE_FIELDS = ("kind", "target", "target_cell", "accepted", "n_candidates", "new_active", "new_direction")
@@ -45,6 +46,17 @@ def builder_of(g, builder_cls, tables=None, max_surplus=128):
     else:
         pb.set_veto(veto, tables if tables is not None else reference_tables(g), use_charge=use_charge,
                     target_charge=1.0)
+    return pb
+
+
+def no_cells_builder_of(g, builder_cls):
+    """The shipped coulomb_atoms/power_bounded.ini shape: no cell system, every other atom is a candidate of every event
+    (merged-image Coulomb bounded by the inverse-power Coulomb bounding potential)."""
+    handler, pot, bound, _, use_charge = potentials_of(g)
+    n = int(g["meta_n"])
+    pb = builder_cls(3, n, float(g["meta_system_length"]), float(g["meta_beta"]), [1, 1, 1], 0, max_occupants=1,
+                     max_surplus=n, chain_time=float(g["meta_chain_time"]), seed=int(g["seed"][0]), no_cells=True)
+    pb.set_pair(handler, pot, bound, use_charge=use_charge)
     return pb
 
 
