@@ -150,9 +150,9 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
     # of every event and there are no cell-boundary events.
     no_cells = not internal_states
     if no_cells:
-        if levels != 1:
-            raise _configuration_error("composite point objects without a cell system are not supported")
-        molecules, max_occupants, cells_per_side, neighbor_layers, cell_objects = False, 1, [1] * setting.dimension, 0, []
+        # composite point objects without cells are handled like those in root-level cells: whole objects are the
+        # candidates (dipoles/dipole_factors_*.ini, water/single_molecule.ini)
+        molecules, max_occupants, cells_per_side, neighbor_layers, cell_objects = levels == 2, 1, [1] * setting.dimension, 0, []
     else:
         if len(internal_states) != 1 or "SingleActiveCellOccupancy" not in _class_names(internal_states[0]):
             raise _configuration_error("at most one internal state, a SingleActiveCellOccupancy, is supported")
@@ -196,6 +196,14 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                 raise _configuration_error("factor-type-map handler {0} has no device implementation"
                                            .format(type(handler).__name__))
             pair_handlers.append(handler)
+        elif id(handler) in factor_tagger_of and no_cells and \
+                "TwoCompositeObjectSummedBoundingPotentialEventHandler" in names:
+            # "[0, 1, 2, 3], Coulomb": the object of the active leaf with every other object
+            factor_map = factor_tagger_of[id(handler)]._factor_type_map
+            entries = {tuple(indices) for lists in factor_map.map.values() for indices in lists}
+            if entries != {tuple(range(2 * nodes_per_root))}:
+                raise _configuration_error("the composite-object factor must join all leaves of two objects")
+            pair_handlers.append(handler)
         elif id(handler) in factor_tagger_of:
             if "FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential" in names:
                 bending_handlers.append(handler)
@@ -214,6 +222,9 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             veto_handlers.append(handler)
         elif "CellBoundaryEventHandler" in names:
             boundary_handlers.append(handler)
+        elif "SingleIndependentActiveSequentialDirectionEndOfChainEventHandler" in names:
+            # a subclass of the periodic-direction handler that rotates the velocity by an angle (general velocities)
+            raise _configuration_error("the sequential-direction end-of-chain handler has no device implementation")
         elif "SingleIndependentActivePeriodicDirectionEndOfChainEventHandler" in names:
             eoc_handlers.append(handler)
         elif "InitialChainStartOfRunEventHandler" in names:
@@ -408,15 +419,19 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                 raise _configuration_error("the composite-object handlers must share one lifting scheme")
             composite_lifting = veto_lifting
         # Does a cell-boundary event of the root trash the leaf-level factor handlers? (tag lists, tagger.py:163-200)
-        boundary_tagger = [tagger for tagger in activator._taggers
-                           if any(handler is boundary_handlers[0] for handler in tagger.get_event_handlers())][0]
-        factor_tags = {tagger.tag for tagger in factor_tagger_of.values()}
-        trashed = set(boundary_tagger.trashes)
-        if factor_tags and factor_tags & trashed and not factor_tags <= trashed:
-            raise _configuration_error("a cell-boundary event must trash all or none of the factor-type-map handlers")
+        keeps_factors = False
+        if not no_cells:
+            boundary_tagger = [tagger for tagger in activator._taggers
+                               if any(handler is boundary_handlers[0] for handler in tagger.get_event_handlers())][0]
+            factor_tags = {tagger.tag for tagger in factor_tagger_of.values()}
+            trashed = set(boundary_tagger.trashes)
+            if factor_tags and factor_tags & trashed and not factor_tags <= trashed:
+                raise _configuration_error("a cell-boundary event must trash all or none of the factor-type-map "
+                                           "handlers")
+            keeps_factors = not (factor_tags and factor_tags <= trashed)
         builder.set_molecules(composite_lifting if composite_lifting is not None else abi.LIFTING_INSIDE_FIRST,
                               inter_factors=inter_factors, inter_potential=inter_potential, bending=bending,
-                              boundary_keeps_factors=not (factor_tags and factor_tags <= trashed))
+                              boundary_keeps_factors=keeps_factors)
     elif veto_handlers and "CompositeObjectCellVetoEventHandler" in _class_names(veto_handlers[0]):
         raise _configuration_error("the composite-object cell-veto handler needs root-level cells")
     if len(charge_names) > 1:

@@ -518,3 +518,60 @@ def coulomb_power_bounded_ini(ref_root, n_atoms=2, end_of_run_time=1.0e9, sampli
         text = text.replace("output_handlers = separation_output_handler\n", "")
         text = text.split("[SeparationOutputHandler]")[0]
     return text
+
+
+def shipped_without_sampling(ref_root, relative, end_of_run_time=1.0e9, replacements=()):
+    """A shipped configuration file, unchanged in everything the hot path reads, with its sampling tagger, output
+    handlers and output files removed and the run length changed: for event-by-event recordings.
+    `relative`: path components below config_files; `replacements`: (old, new) text pairs applied first."""
+    import configparser
+    import io
+    import os
+    text = shipped_ini(ref_root, *relative)
+    text = text.replace("filename = config_files/", "filename = " + os.path.join(ref_root, "jellyfysh", "config_files") + "/")
+    for old, new in replacements:
+        assert old in text, old
+        text = text.replace(old, new)
+    parser = configparser.ConfigParser()
+    parser.optionxform = str
+    parser.read_string(text)
+    taggers = [line.strip().rstrip(",") for line in parser.get("TagActivator", "taggers").strip().splitlines()]
+    sampling = [t.split()[0] for t in taggers if "sampling" in t.split()[0]]
+    parser.set("TagActivator", "taggers", "\n" + ",\n".join(t for t in taggers if t.split()[0] not in sampling))
+    camel = lambda name: "".join(part.capitalize() for part in name.split("_"))
+    for tag in sampling:
+        handler = parser.get(camel(tag), "event_handler").split()[0]
+        parser.remove_section(camel(tag))
+        parser.remove_section(camel(handler))
+    for section in parser.sections():
+        for key in ("create", "trash"):
+            if parser.has_option(section, key):
+                kept = [item.strip() for item in parser.get(section, key).split(",") if item.strip() not in sampling]
+                parser.set(section, key, ", ".join(kept))
+    for handler in [h.strip().split()[0] for h in parser.get("InputOutputHandler", "output_handlers").split(",")]:
+        parser.remove_section(camel(handler))
+    parser.remove_option("InputOutputHandler", "output_handlers")
+    parser.set("FinalTimeEndOfRunEventHandler", "end_of_run_time", repr(end_of_run_time))
+    out = io.StringIO()
+    parser.write(out)
+    return out.getvalue()
+
+
+def dipole_start(n_dipoles, length=1.0, seed=900, minimum_distance=0.3, bond=0.1):
+    """n_dipoles dipoles (charges +1, -1 at separation `bond`) with centres at least minimum_distance apart."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    centres = []
+    while len(centres) < n_dipoles:
+        c = rng.uniform(0.0, length, size=3)
+        if all(np.linalg.norm(np.mod(c - o + length / 2, length) - length / 2) > minimum_distance for o in centres):
+            centres.append(c)
+    roots = np.empty((n_dipoles, 3))
+    leaves = np.empty((n_dipoles, 2, 3))
+    for k, c in enumerate(centres):
+        axis = rng.normal(size=3)
+        axis *= 0.5 * bond / np.linalg.norm(axis)
+        roots[k] = c % length
+        leaves[k, 0] = (c + axis) % length
+        leaves[k, 1] = (c - axis) % length
+    return roots, leaves

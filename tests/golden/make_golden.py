@@ -361,6 +361,32 @@ def no_cell_traces():
                           ipcb=[1.5837], chain_time=0.78965, far_field=0))
 
 
+def no_cell_molecule_traces():
+    # composite point objects without a cell system: the three shipped dipoles/dipole_factors_*.ini (composite-object
+    # Coulomb factor "[0, 1, 2, 3]" with each of the three lifting schemes, harmonic bond, 1/r^6 repulsion between
+    # unlike charges of different dipoles), sized for three dipoles
+    n = 3
+    for k, lifting in enumerate(("inside_first", "outside_first", "ratio")):
+        roots, leaves = configs.dipole_start(n, seed=41 + k)
+        ini = configs.shipped_without_sampling(
+            REF, ("2018_JCP_149_064113", "dipoles", f"dipole_factors_{lifting}.ini"),
+            replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                          ("number_event_handlers = 1", f"number_event_handlers = {2 * (n - 1)}")])
+        chain_trace(f"trace_dipole_factors_{lifting}", ini, None, seed=15 + k, stream=9 + k, n_events=3000,
+                    snapshot_every=250, composites=(roots, leaves), charges=np.tile([1.0, -1.0], n),
+                    meta=dict(n=2 * n, nodes_per_root=2, system_length=1.0, beta=1.0, chain_time=0.78965,
+                              mic=[1.0, 3.45, 6, 2], ipcb=[1.5837], harmonic=[200.0, 0.1, 2.0], repulsive=[6.0, 1.0e-6],
+                              lifting=k, initial_active=0, far_field=0))
+    # the shipped water/single_molecule.ini: harmonic bonds and the bending factor of one molecule, nothing else
+    roots, leaves = configs.water_start(1, 10.0, seed=7)
+    ini = configs.shipped_without_sampling(REF, ("2018_JCP_149_064113", "water", "single_molecule.ini"))
+    chain_trace("trace_water_single_molecule", ini, None, seed=19, stream=13, n_events=3000, snapshot_every=250,
+                composites=(roots, leaves), charges=np.array([0.41, -0.82, 0.41]),
+                meta=dict(n=3, nodes_per_root=3, system_length=10.0, beta=1.679, chain_time=2.12345,
+                          harmonic=[529.581, 1.012, 2.0], bending=[75.9, 1.9764], bending_offset=10.0,
+                          bending_max_displacement=0.1, initial_active=1, far_field=0))
+
+
 def cell_bounding_traces():
     # Coulomb atoms with the far field through TwoLeafUnitCellBoundingPotentialEventHandler (shipped
     # coulomb_atoms/cell_bounded.ini shape)
@@ -467,10 +493,11 @@ def water_traces():
                           bending_offset=10.0, bending_max_displacement=0.112321434, initial_active=1))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__":  # noqa
     which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "water", "lifting", "no_cells"]
     if "no_cells" in which:
         no_cell_traces()
+        no_cell_molecule_traces()
     if "water" in which:
         water_traces()
     if "lifting" in which:

@@ -223,8 +223,11 @@ class ReferenceRun:
     def _target_root_of(self, in_state):
         """The root of the composite object in the in-state that holds no active leaf unit."""
         from jellyfysh.base.node import yield_leaf_nodes
+        # an in-state from the cell taggers holds one branch per object, one from a factor type map one branch per leaf
+        active_roots = {cnode.value.identifier[0] for cnode in in_state
+                        if any(leaf.value.velocity is not None for leaf in yield_leaf_nodes(cnode))}
         for cnode in in_state:
-            if all(leaf.value.velocity is None for leaf in yield_leaf_nodes(cnode)):
+            if cnode.value.identifier[0] not in active_roots:
                 return cnode.value.identifier[0]
         raise RuntimeError("composite in-state without target")
 

@@ -148,6 +148,56 @@ def test_power_bounded_graph_without_cells_compiles_and_replays(oracle):
         setting.reset()
 
 
+@pytest.mark.parametrize("lifting", ["inside_first", "outside_first", "ratio"])
+def test_dipole_factors_graph_without_cells_compiles_and_replays(oracle, lifting):
+    """The shipped dipoles/dipole_factors_*.ini (composite objects without a cell system) sized for three dipoles ->
+    compiler -> oracle chain reproduces the reference trace of the same configuration bit for bit."""
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_dipole_factors_" + lifting)
+    n = int(g["meta_n"]) // 2
+    ini = configs.shipped_without_sampling(
+        REF, ("2018_JCP_149_064113", "dipoles", f"dipole_factors_{lifting}.ini"), end_of_run_time=5.0,
+        replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                      ("number_event_handlers = 1", f"number_event_handlers = {2 * (n - 1)}")])
+    mediator, setting = build_reference_graph(ini, composites=(g["roots0"], g["positions0"].reshape(n, 2, 3)))
+    try:
+        state = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, state, seed=int(g["seed"][0]))
+        p = compiled.builder.program
+        assert p.no_cells == 1 and p.cell_level == 1 and p.nodes_per_root == 2 and p.veto_enabled == 0
+        assert p.pair_handler == abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING and p.pair_use_charge == 1
+        assert p.composite_lifting == {"inside_first": abi.LIFTING_INSIDE_FIRST, "outside_first": abi.LIFTING_OUTSIDE_FIRST,
+                                       "ratio": abi.LIFTING_RATIO}[lifting]
+        assert p.n_bonds == 1 and p.n_inter_factors == 2
+        assert sorted((p.inter_factors[i][0], p.inter_factors[i][1]) for i in range(2)) == [(0, 1), (1, 0)]
+        positions, charges, roots = compiler.positions_and_charges(state, compiled.charge_name)
+        assert np.array_equal(positions, g["positions0"]) and np.array_equal(roots, g["roots0"])
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions, charges)
+        chain.set_roots(roots)
+        chain.start(stream=int(g["seed"][1]))
+        records = g["records"][:1500]
+        n_done, rec = chain.run(max_events=len(records), record=len(records))
+        assert n_done == len(records) and tu.records_equal_discrete(rec, records)
+        assert np.array_equal(rec["time_q"], records["time_q"]) and np.array_equal(rec["time_r"], records["time_r"])
+    finally:
+        setting.reset()
+
+
+def test_sequential_direction_end_of_chain_is_rejected():
+    """single_hard_disk_dipole.ini rotates the velocity by an angle at the end of a chain (a subclass of the
+    periodic-direction handler): not built on the device, and said so instead of being mistaken for its base class."""
+    from jellyfysh_b200 import compiler
+    from jellyfysh.base.exceptions import ConfigurationError
+    ini = configs.shipped_without_sampling(REF, ("hard_disk_dipoles", "single_hard_disk_dipole.ini"), end_of_run_time=5.0)
+    mediator, setting = build_reference_graph(ini)
+    try:
+        with pytest.raises(ConfigurationError, match="sequential-direction"):
+            compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())
+    finally:
+        setting.reset()
+
+
 def test_hard_disk_dipole_graph_compiles_and_replays(oracle):
     """C1: the shipped hard_disk_dipoles_cells.ini (composite point objects, leaf-level cells, unbounded occupancy,
     hard-sphere pairs + hard-dipole tether from the factor type map) -> compiler -> oracle chain reproduces the

@@ -321,12 +321,18 @@ def _dipole_pair_start(seed, length=1.0):
     return roots, leaves
 
 
-def test_shipped_dipole_config_matches_reference_statistics(tmp_path):
+@pytest.mark.parametrize("config,output", [
+    ("cell_veto.ini", "SamplesOfSeparation_CellVeto.dat"),
+    ("dipole_factors_inside_first.ini", "SamplesOfSeparation_DipoleFactors_InsideFirst.dat"),
+    ("dipole_factors_outside_first.ini", "SamplesOfSeparation_DipoleFactors_OutsideFirst.dat"),
+    ("dipole_factors_ratio.ini", "SamplesOfSeparation_DipoleFactors_Ratio.dat")])
+def test_shipped_dipole_config_matches_reference_statistics(tmp_path, config, output):
     """dipoles/cell_veto.ini of 2018_JCP_149_064113 (two dipoles: composite-object Coulomb handlers with cell veto on
     anisotropic 3 x 5 x 7 root-level cells, harmonic bond, 1/r^6 repulsion between the opposite charges of different
-    dipoles as a factor between objects), unchanged except for the mediator line, run length, sampling interval and
-    output file: the separations between like and unlike charges of different dipoles follow the cumulative histograms
-    the reference ships (ReferenceDataDipoles_13.dat / _14.dat)."""
+    dipoles as a factor between objects) and the three dipole_factors_*.ini (no cell system: the composite-object
+    Coulomb factor of the factor type map with inside-first, outside-first and ratio lifting), unchanged except for the
+    mediator line, run length, sampling interval and output file: the separations between like and unlike charges of
+    different dipoles follow the cumulative histograms the reference ships (ReferenceDataDipoles_13.dat / _14.dat)."""
     import sys
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -335,13 +341,13 @@ def test_shipped_dipole_config_matches_reference_statistics(tmp_path):
     import jellyfysh_b200
     jellyfysh_b200.install()
     chains, end, interval = 1024, 400.0, 4.0
-    ini = configs.shipped_ini(REF, "2018_JCP_149_064113", "dipoles", "cell_veto.ini")
+    ini = configs.shipped_ini(REF, "2018_JCP_149_064113", "dipoles", config)
     ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
     ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
     ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 31" % chains)
     ini = ini.replace("end_of_run_time = 500000", "end_of_run_time = %r" % end)
     ini = ini.replace("sampling_interval = 0.56789", "sampling_interval = %r" % interval)
-    ini = ini.replace("output/2018_JCP_149_064113/dipoles/SamplesOfSeparation_CellVeto.dat", str(tmp_path / "separation.dat"))
+    ini = ini.replace("output/2018_JCP_149_064113/dipoles/" + output, str(tmp_path / "separation.dat"))
     assert "cuda_batched_mediator" in ini and str(tmp_path) in ini and "end_of_run_time = 400.0" in ini
     starts = [_dipole_pair_start(900 + c) for c in range(chains)]
     composites = (np.concatenate([r for r, _ in starts]), np.concatenate([l for _, l in starts]))
@@ -365,4 +371,49 @@ def test_shipped_dipole_config_matches_reference_statistics(tmp_path):
         ours = np.searchsorted(np.sort(samples), edges, side="right") / len(samples)
         distance = np.max(np.abs(ours - cdf))
         print("dipoles", name, "KS distance", distance, "samples", len(samples), stats)
+        assert distance < 1.95 / np.sqrt(chains * 5) + 5.0e-3, (name, distance)
+
+
+def test_shipped_single_molecule_config_matches_reference_statistics(tmp_path):
+    """water/single_molecule.ini of 2018_JCP_149_064113 (one SPC/Fw molecule, no cell system: the two harmonic bonds and
+    the bending factor with its piecewise constant bound and ratio lifting), unchanged except for the mediator line, run
+    length and output file: bond lengths and bond angle, sampled by the reference's own BondLengthAndAngleOutputHandler,
+    follow the cumulative histograms the reference ships (ReferenceLengthSingleMolecule.dat / ReferenceAngle...)."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import kat_replay as kr
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    chains, end = 1024, 300.0
+    ini = configs.shipped_ini(REF, "2018_JCP_149_064113", "water", "single_molecule.ini")
+    ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 37" % chains)
+    ini = ini.replace("end_of_run_time = 500000", "end_of_run_time = %r" % end)
+    ini = ini.replace("output/2018_JCP_149_064113/water/SamplesOfBonds_SingleMolecule.dat", str(tmp_path / "bonds.dat"))
+    assert "cuda_batched_mediator" in ini and str(tmp_path) in ini and "end_of_run_time = 300.0" in ini
+    starts = [configs.water_start(1, 10.0, seed=500 + c) for c in range(chains)]
+    composites = (np.concatenate([r for r, _ in starts]), np.concatenate([l for _, l in starts]))
+    mediator, setting = build_reference_graph(ini, composites=composites)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["capacity_errors"] == 0 and stats["bond_events"] > 0 and stats["pair_events"] == 0
+    ref = kr.load_npz("reference_cdfs")
+    per_chain = int(end / 2.6789)
+    for name, suffix, per_sample in (("water_length", "Length", 2), ("water_angle", "Angle", 1)):
+        samples = np.loadtxt(tmp_path / ("bonds_%s.dat" % suffix), comments="#")
+        assert len(samples) == chains * per_chain * per_sample
+        samples = samples.reshape(per_chain, chains * per_sample)[per_chain // 4:].ravel()
+        x, cdf = ref[name + "_x"], ref[name + "_cdf"]
+        edges = x + 0.5 * (x[1] - x[0])
+        ours = np.searchsorted(np.sort(samples), edges, side="right") / len(samples)
+        distance = np.max(np.abs(ours - cdf))
+        print("single molecule", name, "KS distance", distance, "samples", len(samples), stats)
         assert distance < 1.95 / np.sqrt(chains * 5) + 5.0e-3, (name, distance)

@@ -122,6 +122,36 @@ def test_no_cells_chain_replay_bit_exact(oracle, name):
     assert chain.stats()["capacity_errors"] == 0
 
 
+@pytest.mark.parametrize("name", sorted(tu.NO_CELL_MOLECULE_TRACES))
+def test_no_cells_composite_chain_replay_bit_exact(oracle, name):
+    """Composite point objects without a cell system: the three shipped dipoles/dipole_factors_*.ini (three dipoles;
+    composite-object Coulomb factor from the factor type map with inside-first / outside-first / ratio lifting, harmonic
+    bond, 1/r^6 repulsion between objects) and the shipped water/single_molecule.ini (bonds and bending only)."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    chain = oracle.OracleChain(tu.NO_CELL_MOLECULE_TRACES[name](g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        for f in tu.DISCRETE_FIELDS:
+            assert np.array_equal(rec[f], ref[f]), (f, done + int(np.nonzero(rec[f] != ref[f])[0][0]))
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            assert np.array_equal(chain.roots(), g["snap_roots"][k])
+    assert (records["kind"] == 3).sum() == 0
+    assert np.array_equal(chain.positions(), g["final_positions"]) and np.array_equal(chain.roots(), g["final_roots"])
+    assert chain.stats()["capacity_errors"] == 0
+
+
 @pytest.mark.parametrize("name", tu.DIPOLE_TRACES)
 def test_composite_chain_replay_bit_exact(oracle, name):
     """C1, the shipped hard_disk_dipoles_cells.ini from the shipped start configuration: composite point objects

@@ -60,6 +60,43 @@ def no_cells_builder_of(g, builder_cls):
     return pb
 
 
+def dipole_factors_builder_of(g, builder_cls):
+    """The shipped dipoles/dipole_factors_*.ini: composite-object Coulomb factor with a lifting scheme, harmonic bond,
+    1/r^6 repulsion between unlike charges of different dipoles; no cell system."""
+    pb = builder_cls(3, int(g["meta_n"]), float(g["meta_system_length"]), float(g["meta_beta"]), [1, 1, 1], 0,
+                     chain_time=float(g["meta_chain_time"]), initial_active=int(g["meta_initial_active"]),
+                     seed=int(g["seed"][0]), no_cells=True)
+    pb.set_pair(abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"]),
+                abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, *g["meta_ipcb"]), use_charge=True)
+    pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1)],
+                     bond_potential=abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, *g["meta_harmonic"]))
+    lifting = (abi.LIFTING_INSIDE_FIRST, abi.LIFTING_OUTSIDE_FIRST, abi.LIFTING_RATIO)[int(g["meta_lifting"])]
+    pb.set_molecules(lifting, inter_factors=[(0, 1), (1, 0)],
+                     inter_potential=abi.EcmcPotential.make(abi.POT_INVERSE_POWER, *g["meta_repulsive"]))
+    return pb
+
+
+def single_molecule_builder_of(g, builder_cls):
+    """The shipped water/single_molecule.ini: two harmonic bonds and the bending factor of one molecule."""
+    pb = builder_cls(3, int(g["meta_n"]), float(g["meta_system_length"]), float(g["meta_beta"]), [1, 1, 1], 0,
+                     chain_time=float(g["meta_chain_time"]), initial_active=int(g["meta_initial_active"]),
+                     seed=int(g["seed"][0]), no_cells=True)
+    pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1), (1, 2)],
+                     bond_potential=abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, *g["meta_harmonic"]))
+    pb.set_molecules(abi.LIFTING_INSIDE_FIRST,
+                     bending=dict(children=[0, 1, 2], separations=[1, 0, 1, 2], lifting=abi.LIFTING_RATIO,
+                                  potential=abi.EcmcPotential.make(abi.POT_BENDING, *g["meta_bending"]),
+                                  offset=float(g["meta_bending_offset"]),
+                                  max_displacement=float(g["meta_bending_max_displacement"])))
+    return pb
+
+
+NO_CELL_MOLECULE_TRACES = {"trace_dipole_factors_inside_first": dipole_factors_builder_of,
+                           "trace_dipole_factors_outside_first": dipole_factors_builder_of,
+                           "trace_dipole_factors_ratio": dipole_factors_builder_of,
+                           "trace_water_single_molecule": single_molecule_builder_of}
+
+
 def dipole_builder_of(g, builder_cls):
     """C1: hard-disk dipoles (two disks per root, leaf-level cells, hard-sphere pairs, hard-dipole tether)."""
     dimension = len(g["meta_cells_per_side"])
