@@ -13,6 +13,8 @@ nearby cells + surplus by exact LJ inversion, all other cells by cell veto. A "s
              H2D -> cell binning -> events -> D2H positions out, host clock around synchronous calls
   roofline   the event kernel against the measured HBM peak (algorithmic bytes per event) -- plus
              "fp64": the same kernel against the measured DFMA rate, which is the pipe that actually binds it
+  single_chain  N = 1 only: ns/event of ONE Lennard-Jones chain of 65536 particles (C5, the second half of the metric),
+             measured after the timed region on its own engine handle
   cpu_baseline  the unmodified reference (baseline/_ref, CPython) on the host cores, bounded sample; else the C port
 
 `--impl reference` times only the CPU reference arm, on rank 0.
@@ -46,6 +48,7 @@ def parse_args():
     parser.add_argument("--e2e-steps", type=int, default=8)
     parser.add_argument("--cpu-seconds", type=float, default=8.0, help="wall budget of the CPU baseline sample")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-single-chain", action="store_true", help="skip the C5 single-chain latency leg (N = 1 only)")
     return parser.parse_args()
 
 
@@ -258,6 +261,29 @@ def algorithmic_flops_per_event(pair_candidates):
     return 70.0 * pair_candidates + 30.0 + 6.0 + 25.0
 
 
+def single_chain_latency(device):
+    """The second half of BASELINE.json's metric, "ns/event single chain" (SURVEY.md 8d, C5): ONE Lennard-Jones chain of
+    65536 particles in 48^3 cells, same potential, density and far field as C2. One warp on the whole GPU: the number is
+    the latency of the dependent instruction chain of an event, not a throughput. Device time of the event kernel
+    (CUDA events on the engine's stream) after one warm-up launch."""
+    from jellyfysh_b200 import engine, workloads
+    n, cells, events = 65536, 48, 100000
+    builder, length = workloads.lennard_jones(n_particles=n, cells_per_side=cells, device=device)
+    start = workloads.lattice_start(1, n, cells, length)
+    with engine.Engine(builder, n_chains=1, device=device) as eng:
+        eng.upload_positions(start)
+        eng.start(first_stream=0)
+        eng.run(max_events=events)
+        eng.sync()
+        before = eng.kernel_seconds
+        for _ in range(2):
+            eng.run(max_events=events)
+        stats = eng.sync()
+        seconds = eng.kernel_seconds - before
+    return {"workload": "C5: single 3D Lennard-Jones chain, N = 65536, cells 48^3 nl=1, cell-veto far field",
+            "ns_per_event": 1e9 * seconds / stats["events"], "events": stats["events"], "unit": "ns/event"}
+
+
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -384,6 +410,8 @@ def run_ours(args, rank, local_rank, world):
                            "expected_pairs": world * args.chains * args.particles * (args.particles - 1) // 2},
             "event_mix": {k: all_stats[k] for k in ("pair_events", "veto_events", "veto_accepted", "boundary_events",
                                                     "end_of_chain_events", "bound_violations")}}
+    if world == 1 and not args.no_single_chain:
+        line["single_chain"] = single_chain_latency(local_rank)
     if world == 1 and not args.no_cpu_baseline:
         baseline = reference_sample(args, args.cpu_seconds)
         if baseline is None:
