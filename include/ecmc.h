@@ -78,7 +78,10 @@ enum EcmcPairHandlerKind {
     ECMC_PAIR_TWO_LEAF_UNIT = 1,
     /* TwoLeafUnitBoundingPotentialEventHandler: candidate from an invertible bounding potential, confirmed
      * against the real potential's derivative.
-     * jellyfysh/event_handler/two_leaf_unit_bounding_potential_event_handler.py:112-168 */
+     * jellyfysh/event_handler/two_leaf_unit_bounding_potential_event_handler.py:112-168.
+     * With cell_level = 1 (composite objects as the units of the cells / of a configuration without cells): one such
+     * handler per pair (active leaf, leaf of ANOTHER object) -- the non-local factor type map entries "[0, 2], Coulomb"
+     * ... of factor_set_dipoles_atomic.txt / factor_set_water_atomic.txt (dipoles/atom_factors.ini). */
     ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING = 2,
     /* TwoCompositeObjectSummedBoundingPotentialEventHandler: the active leaf against every leaf of a composite object
      * in a nearby cell / the surplus; candidate = minimum over the target leaves of the bounding potential's

@@ -175,7 +175,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
 
     # ---- handlers by kind
     pair_handlers, veto_handlers, boundary_handlers, eoc_handlers, start_handlers, control = [], [], [], [], [], []
-    bounding_handlers, bond_handlers, bending_handlers = [], [], []
+    bounding_handlers, bond_handlers, bending_handlers, leaf_pair_handlers = [], [], [], []
     # handlers fed by a factor type map are intramolecular factors (factor_type_map_in_state_tagger.py:83-107)
     factor_tagger_of = {}
     for tagger in activator._taggers:
@@ -204,6 +204,16 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             if entries != {tuple(range(2 * nodes_per_root))}:
                 raise _configuration_error("the composite-object factor must join all leaves of two objects")
             pair_handlers.append(handler)
+        elif id(handler) in factor_tagger_of and no_cells and "TwoLeafUnitBoundingPotentialEventHandler" in names:
+            # "[0, 2], Coulomb", "[0, 3], Coulomb", ...: the Coulomb interaction as bounded leaf-to-leaf factors between
+            # the objects; the device handles them only if every leaf of one object is paired with every leaf of the other
+            factor_map = factor_tagger_of[id(handler)]._factor_type_map
+            entries = {tuple(indices) for lists in factor_map.map.values() for indices in lists}
+            wanted = {(a, nodes_per_root + b) for a in range(nodes_per_root) for b in range(nodes_per_root)}
+            if entries != wanted:
+                raise _configuration_error("bounded leaf-to-leaf factors must join every leaf of one object with every "
+                                           "leaf of the other")
+            leaf_pair_handlers.append(handler)
         elif id(handler) in factor_tagger_of:
             if "FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential" in names:
                 bending_handlers.append(handler)
@@ -332,6 +342,22 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                     _lifting_kind(handler._lifting) != composite_lifting:
                 raise _configuration_error("nearby and surplus composite-object handlers must be alike")
         builder.set_pair(abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, potential, bounding, use_charge=charge is not None)
+        if charge is not None:
+            charge_names.add(charge)
+    elif leaf_pair_handlers:
+        # molecules without cells, Coulomb as bounded factors between leaves of different objects
+        if pair_handlers or not molecules:
+            raise _configuration_error("bounded leaf-to-leaf factors cannot be combined with other pair handlers")
+        first = leaf_pair_handlers[0]
+        potential = potential_descriptor(first._potential)
+        bounding = potential_descriptor(first._bounding_potential)
+        charge = _charge_name(first._potential_charges)
+        for handler in leaf_pair_handlers[1:]:
+            if not _same_potential(potential, potential_descriptor(handler._potential)) or \
+                    not _same_potential(bounding, potential_descriptor(handler._bounding_potential)) or \
+                    _charge_name(handler._potential_charges) != charge:
+                raise _configuration_error("the bounded leaf-to-leaf handlers must be alike")
+        builder.set_pair(abi.PAIR_TWO_LEAF_UNIT_BOUNDING, potential, bounding, use_charge=charge is not None)
         if charge is not None:
             charge_names.add(charge)
     elif pair_handlers:

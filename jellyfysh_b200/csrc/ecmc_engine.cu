@@ -305,8 +305,10 @@ int build_device_program(EcmcHandle *h) {
         MoleculeProgram &m = h->mprog;
         if (p.dimension != 3 || d.nodes_per_root > 3 || p.max_occupants != 1)
             return fail(h, ECMC_ERR_INVALID, "molecules need dimension 3, nodes_per_root <= 3 and max_occupants = 1");
-        if (p.pair_handler != ECMC_PAIR_NONE && p.pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING)
-            return fail(h, ECMC_ERR_INVALID, "molecules need the composite-object pair handler");
+        // ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING here: one bounded handler per pair of leaves of different objects
+        if (p.pair_handler != ECMC_PAIR_NONE && p.pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING &&
+            p.pair_handler != ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING)
+            return fail(h, ECMC_ERR_INVALID, "molecules need the composite-object pair handler or bounded leaf-to-leaf factors");
         if (p.veto_enabled != ECMC_FAR_NONE && p.veto_enabled != ECMC_FAR_CELL_VETO)
             return fail(h, ECMC_ERR_INVALID, "molecules support the cell-veto far field only");
         if (p.composite_lifting < ECMC_LIFTING_INSIDE_FIRST || p.composite_lifting > ECMC_LIFTING_RATIO)

@@ -214,6 +214,10 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
 
     auto set_dir = [&](Vec3 &v, double value) { if (dir == 0) v.x = value; else if (dir == 1) v.y = value; else v.z = value; };
 
+    // the Coulomb interaction as bounded leaf-to-leaf factors between the objects, one TwoLeafUnitBoundingPotential-
+    // EventHandler per pair of leaves (dipoles/atom_factors.ini), instead of one composite-object handler per pair of
+    // objects: the candidates are the same lanes, an event is confirmed against its own pair only and lifts to the target
+    const bool leaf_pairs = P.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING;
     bool done = false;
     while (true) {
         if (ALIGNED) {
@@ -255,7 +259,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             restore_stamp.q = stp->pending_stamp_q; restore_stamp.r = stp->pending_stamp_r;
         } else {
             const bool factors_kept = kept_kind != ECMC_EVENT_NONE;
-            const int nearby_slots = P.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING ? P.n_nearby : 0;
+            const int nearby_slots = (P.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || leaf_pairs) ? P.n_nearby : 0;
             const int n_pair_slots = nearby_slots ? nearby_slots + n_surplus : 0;
             // scan positions: [0, n_pair_slots) objects, then bonds, inter-object factors (one per object and factor),
             // bending, veto, boundary
@@ -349,7 +353,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                             const double c1 = P.pair_use_charge ? acharge : 1.0, c2 = P.pair_use_charge ? tp.charge : 1.0;
                             dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c1, c2, du);
                             kind = ECMC_EVENT_PAIR;
-                            rec_target = root;
+                            rec_target = leaf_pairs ? target : root;
                         } else {
                             const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
                             const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
@@ -443,7 +447,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                     const double x = now.r + dt;
                     const bool finite = kind != ECMC_EVENT_NONE && x < INFINITY;
                     // the reference counts one candidate per handler: the first leaf of an object stands for the pair
-                    n_cand += __popc(__ballot_sync(kFull, finite && !(type == ITEM_PAIR_LEAF && (seq & 3) != 0)));
+                    n_cand += __popc(__ballot_sync(kFull, finite && !(type == ITEM_PAIR_LEAF && (seq & 3) != 0 && !leaf_pairs)));
                     const unsigned long long k64 = finite ? time_key(x) : 0x7ff0000000000000ull;
                     const int owner = warp_argmin(k64, finite ? seq : kSeqNone, lane);
                     const unsigned long long pass_key = __shfl_sync(kFull, k64, owner);
@@ -549,10 +553,13 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
         case ECMC_EVENT_PAIR:
         case ECMC_EVENT_CELL_VETO: {
             const bool veto = kind == ECMC_EVENT_CELL_VETO;
-            const int target_root = veto ? occ[bcell] : btarget;
-            rec_target = target_root;
+            // leaf_pairs: btarget is the target LEAF; the loops below then run over that one leaf only
+            const bool one_leaf = leaf_pairs && !veto;
+            const int target_root = veto ? occ[bcell] : (one_leaf ? btarget / npr : btarget);
+            rec_target = one_leaf ? btarget : target_root;
             if (veto) n_veto++; else n_pair++;
             if (target_root < 0) break;
+            const int k_first = one_leaf ? btarget - target_root * npr : 0, k_last = one_leaf ? k_first + 1 : npr;
             const bool use_charge = veto ? P.veto_use_charge : P.pair_use_charge;
             double bounding_rate = veto ? brate : 0.0;
             double factor_derivative = 0.0;
@@ -560,7 +567,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             Vec3 tpos[4];
             double tcharge[4];
             const PotentialParams &real_potential = veto ? P.veto_potential : P.real_potential;
-            for (int k = 0; k < npr; k++) {
+            for (int k = k_first; k < k_last; k++) {
                 const Particle tp = part[target_root * npr + k];
                 tpos[k] = lab_position(tp);
                 tcharge[k] = tp.charge;
@@ -586,12 +593,14 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                     const double u = confirm_draw(key.seed, key.stream, key.event, draw++);
                     if (event_rate <= 0.0 + (bounding_rate - 0.0) * u) break;
                     confirmed = true;
+                    // TwoLeafUnitBoundingPotentialEventHandler.send_out_state (:148-168): the target leaf takes over
+                    if (one_leaf) break;
                     local_derivatives[active - active_root * npr] = veto ? factor_derivative : event_rate;
                 }
                 const Particle lp = part[local];
                 const Vec3 lpos = i < 0 ? apos : lab_position(lp);
                 const double lcharge = i < 0 ? acharge : lp.charge;
-                for (int j = 0; j < npr; j++) {
+                for (int j = k_first; j < k_last; j++) {
                     const double c1 = use_charge ? lcharge : 1.0, c2 = use_charge ? tcharge[j] : 1.0;
                     const double pairwise = pair_derivative_lab<REAL>(real_potential, dir, speed, lpos, tpos[j], c1, c2, L,
                                                                       half, trig, lane);
@@ -600,6 +609,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                 }
             }
             if (!confirmed) break;
+            if (one_leaf) { new_active = btarget; break; }
             Lifting lift;
             lifting_reset(lift);
             for (int pass = 0; pass < 2; pass++) {

@@ -1455,6 +1455,26 @@ static candidate composite_pair_candidate(OrcChain *c, int target_root) {
     return cand;
 }
 
+/* Leaf-to-leaf factors with a bounding potential between the active leaf and leaf k of another object, each handled by a
+ * TwoLeafUnitBoundingPotentialEventHandler (two_leaf_unit_bounding_potential_event_handler.py:112-146) fed by non-local
+ * factor type map entries ("[0, 2], Coulomb" ... of factor_set_dipoles_atomic.txt: every leaf of one object with every
+ * leaf of the other). The draw is keyed like the composite handler's: (pair time, target object), double k. */
+static candidate leaf_pair_candidate(OrcChain *c, int target) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_PAIR; cand.target = target; cand.target_cell = -1; cand.rate = 0.0;
+    double sep[ECMC_MAX_DIM] = {0, 0, 0};
+    separation_vector(c->pos + c->st.active * c->D, c->pos + target * c->D, c->D, c->L, sep);
+    double c1 = c->prog.pair_use_charge ? c->charge[c->st.active] : 1.0;
+    double c2 = c->prog.pair_use_charge ? c->charge[target] : 1.0;
+    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter,
+                          ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target / c->npr), (uint32_t)(target % c->npr));
+    double dt = pot_displacement(&c->pair_bound, c->st.direction, c->prog.speed, sep, c->D, c1, c2,
+                                 rng_expovariate(u, c->prog.beta));
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, dt);
+    return cand;
+}
+
 /* A two-leaf factor between the active leaf and a leaf of another object (non-local factor type map entry), handled by
  * a TwoLeafUnitEventHandler (two_leaf_unit_event_handler.py:105-138) */
 static candidate factor_pair_candidate(OrcChain *c, int target) {
@@ -1625,6 +1645,16 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
                 candidate cand = composite_pair_candidate(c, c->surplus[s]);
                 CONSIDER(cand);
             }
+        } else if (c->prog.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING) {
+            /* one bounded handler per leaf of every other object */
+            for (int i = 0; i < nn + c->n_surplus; i++) {
+                int t = i < nn ? c->occ[nearby[i]] : c->surplus[i - nn];
+                if (t < 0) continue;
+                for (int k = 0; k < npr; k++) {
+                    candidate cand = leaf_pair_candidate(c, t * npr + k);
+                    CONSIDER(cand);
+                }
+            }
         }
         /* the leaf-level factors: recomputed, unless a cell-boundary event left their handlers running */
         if (c->st.kept_kind != ECMC_EVENT_NONE) {
@@ -1736,6 +1766,24 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         /* two_composite_object_summed_bounding_potential_event_handler.py:158-202 /
          * composite_object_cell_veto_event_handler.py:110-162 (+ mediator.py:265-292 for the occupant of the cell) */
         int veto = best.kind == ECMC_EVENT_CELL_VETO;
+        if (!veto && c->prog.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING) {
+            /* TwoLeafUnitBoundingPotentialEventHandler.send_out_state (:148-168) +
+             * _calculate_out_state_of_two_leaf_unit_bounding_potential (event_handler_with_bounding_potential.py:75-101) */
+            rec_target = best.target;
+            c->stats.pair_events++;
+            double sep[ECMC_MAX_DIM] = {0, 0, 0};
+            separation_vector(pa, c->pos + best.target * D, D, c->L, sep);
+            double c1 = c->prog.pair_use_charge ? c->charge[old_active] : 1.0;
+            double c2 = c->prog.pair_use_charge ? c->charge[best.target] : 1.0;
+            double bounding_rate = pot_derivative(&c->pair_bound, dir, c->prog.speed, sep, D, c1, c2);
+            double real = pot_derivative(&c->pair_pot, dir, c->prog.speed, sep, D, c1, c2);
+            if (real > 0) {
+                if (bounding_rate < real) c->stats.bound_violations++;
+                double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+                if (0 + (bounding_rate - 0) * u < real) { accepted = 1; new_active = best.target; }
+            }
+            break;
+        }
         int target_root = veto ? c->occ[best.target_cell] : best.target;
         rec_target = target_root;
         if (veto) c->stats.veto_events++; else c->stats.pair_events++;

@@ -377,6 +377,35 @@ def no_cell_molecule_traces():
                     meta=dict(n=2 * n, nodes_per_root=2, system_length=1.0, beta=1.0, chain_time=0.78965,
                               mic=[1.0, 3.45, 6, 2], ipcb=[1.5837], harmonic=[200.0, 0.1, 2.0], repulsive=[6.0, 1.0e-6],
                               lifting=k, initial_active=0, far_field=0))
+    # the shipped dipoles/atom_factors.ini: the Coulomb interaction as bounded leaf-to-leaf factors between the dipoles
+    # ("[0, 2], Coulomb" ...: TwoLeafUnitBoundingPotentialEventHandler fed by the factor type map), three dipoles
+    roots, leaves = configs.dipole_start(n, seed=44)
+    ini = configs.shipped_without_sampling(
+        REF, ("2018_JCP_149_064113", "dipoles", "atom_factors.ini"),
+        replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                      ("number_event_handlers = 2", f"number_event_handlers = {2 * (n - 1)}"),
+                      ("number_event_handlers = 1", f"number_event_handlers = {2 * (n - 1)}")])
+    chain_trace("trace_dipole_atom_factors", ini, None, seed=21, stream=15, n_events=3000, snapshot_every=250,
+                composites=(roots, leaves), charges=np.tile([1.0, -1.0], n),
+                meta=dict(n=2 * n, nodes_per_root=2, system_length=1.0, beta=1.0, chain_time=0.78965,
+                          mic=[1.0, 3.45, 6, 2], ipcb=[1.5837], harmonic=[200.0, 0.1, 2.0], repulsive=[6.0, 1.0e-6],
+                          lifting=0, initial_active=0, far_field=0, leaf_pairs=1))
+    # the shipped water/coulomb_power_bounded_lj_inverted.ini: three water molecules without a cell system, Coulomb as
+    # nine bounded leaf-to-leaf factors per pair of molecules, Lennard-Jones between the oxygens, bonds, bending
+    nw = 3
+    roots, leaves = configs.water_start(nw, 10.0, seed=11, jitter=0.2)
+    ini = configs.shipped_without_sampling(
+        REF, ("2018_JCP_149_064113", "water", "coulomb_power_bounded_lj_inverted.ini"),
+        replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {nw}"),
+                      ("number_event_handlers = 3", f"number_event_handlers = {3 * (nw - 1)}"),
+                      ("number_event_handlers = 1\nfactor_type_maps = factor_type_maps\n\n[LennardJonesEventHandler]",
+                       f"number_event_handlers = {nw - 1}\nfactor_type_maps = factor_type_maps\n\n[LennardJonesEventHandler]")])
+    chain_trace("trace_water_atomic_factors", ini, None, seed=23, stream=17, n_events=3000, snapshot_every=250,
+                composites=(roots, leaves), charges=np.tile([0.41, -0.82, 0.41], nw),
+                meta=dict(n=3 * nw, nodes_per_root=3, system_length=10.0, beta=1.679, chain_time=2.12345,
+                          mic=[332.0, 3.45, 6, 2], ipcb=[531.2], lj=[0.6217012, 3.165492], harmonic=[529.581, 1.012, 2.0],
+                          bending=[75.9, 1.9764], bending_offset=10.0, bending_max_displacement=0.1, initial_active=1,
+                          far_field=0, leaf_pairs=1))
     # the shipped water/single_molecule.ini: harmonic bonds and the bending factor of one molecule, nothing else
     roots, leaves = configs.water_start(1, 10.0, seed=7)
     ini = configs.shipped_without_sampling(REF, ("2018_JCP_149_064113", "water", "single_molecule.ini"))

@@ -207,6 +207,9 @@ class ReferenceRun:
                 # point masses without a cell system: the factor type map lists the pair factors themselves
                 # (coulomb_atoms/power_bounded.ini, "[0, 1], Coulomb")
                 return EVENT_PAIR
+            if local is False and "TwoLeafUnitBoundingPotentialEventHandler" in names:
+                # bounded leaf-to-leaf factors between different objects (dipoles/atom_factors.ini): pair events
+                return EVENT_PAIR
             return EVENT_PAIR if local is None else (EVENT_BOND if local else EVENT_FACTOR_PAIR)
         return HOST_EVENT
 
@@ -235,6 +238,11 @@ class ReferenceRun:
     def _is_composite_pair(handler):
         return "TwoCompositeObjectSummedBoundingPotentialEventHandler" in {c.__name__ for c in type(handler).__mro__}
 
+    def _is_leaf_pair_between_objects(self, handler):
+        names = {c.__name__ for c in type(handler).__mro__}
+        return (self.setting.number_of_node_levels == 2 and "TwoLeafUnitBoundingPotentialEventHandler" in names
+                and self._factor_map_handlers().get(id(handler)) is False)
+
     def _target_of_pair(self, in_state):
         from jellyfysh.base.node import yield_leaf_nodes
         for cnode in in_state:
@@ -255,6 +263,11 @@ class ReferenceRun:
             def send_event_time(*args, _h=h, _kind=kind, _orig=orig_time):
                 if _kind == EVENT_PAIR and run._is_composite_pair(_h):
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_root_of(args[0])))
+                elif _kind == EVENT_PAIR and run._is_leaf_pair_between_objects(_h):
+                    # keyed like the composite-object handler: (pair time, target object), double = target child
+                    leaf, npr = run._target_of_pair(args[0]), run.setting.number_of_nodes_per_root_node
+                    run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, leaf // npr))
+                    run.rng.di = leaf % npr
                 elif _kind in (EVENT_PAIR, EVENT_CELL_BOUNDING):
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_of_pair(args[0])))
                 elif _kind in (EVENT_BOND, EVENT_FACTOR_PAIR):

@@ -257,11 +257,14 @@ def test_hard_disk_dipoles_polarization_statistics(tmp_path):
         assert distance < 1.95 / np.sqrt(chains * 10) + 5.0e-3, (key, distance)
 
 
-def test_shipped_water_config_matches_reference_statistics(tmp_path):
-    """C4 statistical check: the shipped water/coulomb_cell_veto_lj_inverted.ini (two SPC/Fw molecules),
-    unchanged except for the mediator line, the run length, the sampling interval and the output file, run as many
-    independent device chains, reproduces the cumulative histogram of the oxygen-oxygen separation the reference ships
-    (ReferenceOOSeparation.dat; fixture tests/golden/reference_cdfs.npz)."""
+@pytest.mark.parametrize("config", ["coulomb_cell_veto_lj_inverted.ini", "coulomb_power_bounded_lj_inverted.ini"])
+def test_shipped_water_config_matches_reference_statistics(tmp_path, config):
+    """C4 statistical check (SURVEY 8c): the shipped water/coulomb_cell_veto_lj_inverted.ini (two SPC/Fw molecules;
+    composite-object Coulomb handlers on root-level cells) and water/coulomb_power_bounded_lj_inverted.ini (no cell
+    system, Coulomb as nine bounded leaf-to-leaf factors between the molecules), unchanged except for the mediator line,
+    the run length, the sampling interval and the output file, run as many independent device chains, reproduce the
+    cumulative histogram of the oxygen-oxygen separation the reference ships (ReferenceOOSeparation.dat; fixture
+    tests/golden/reference_cdfs.npz)."""
     import sys
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -269,12 +272,26 @@ def test_shipped_water_config_matches_reference_statistics(tmp_path):
     from jellyfysh.base.exceptions import EndOfRun
     import jellyfysh_b200
     jellyfysh_b200.install()
-    chains, end, interval = 1024, 2000.0, 20.0
-    ini = configs.water_ini(REF, n_molecules=2, end_of_run_time=end, sampling_interval=interval,
-                            output=str(tmp_path / "oo_separation.dat"))
+    cell_veto = config == "coulomb_cell_veto_lj_inverted.ini"
+    # Two molecules that start apart have to find each other. The pairwise factors of the second file move the pair
+    # together more slowly than the composite-object handlers with their lifting over six leaves: measured on B200, the
+    # distance to the reference histogram after simulated times 500 / 2000 / 8000 is 0.72 / 0.24 / 0.003.
+    chains, end, interval = 1024, 2000.0 if cell_veto else 8000.0, 20.0
+    if cell_veto:
+        ini = configs.water_ini(REF, n_molecules=2, end_of_run_time=end, sampling_interval=interval,
+                                output=str(tmp_path / "oo_separation.dat"))
+        assert "number_trials = 1000" in ini
+    else:
+        ini = configs.shipped_ini(REF, "2018_JCP_149_064113", "water", config)
+        ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+        ini = ini.replace("end_of_run_time = 500000", "end_of_run_time = %r" % end)
+        ini = ini.replace("sampling_interval = 2.6789", "sampling_interval = %r" % interval)
+        ini = ini.replace("output/2018_JCP_149_064113/water/SamplesOfOOSeparation_CoulombPowerBounded_LJInverted.dat",
+                          str(tmp_path / "oo_separation.dat"))
+        assert str(tmp_path) in ini and "sampling_interval = 20.0" in ini
     ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
     ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 29" % chains)
-    assert "number_trials = 1000" in ini and "number_of_root_nodes = 2" in ini
+    assert "number_of_root_nodes = 2" in ini
     # Every chain starts from its own pair of well separated molecules: the random input handler of the shipped file
     # can put a hydrogen next to the other oxygen, which has no repulsive core for it -- such a chain collapses (event
     # rate -> infinity) in the reference as well.
@@ -288,7 +305,7 @@ def test_shipped_water_config_matches_reference_statistics(tmp_path):
         stats = mediator.statistics
     finally:
         setting.reset()
-    assert stats["capacity_errors"] == 0 and stats["bond_events"] > 0 and stats["veto_events"] > 0
+    assert stats["capacity_errors"] == 0 and stats["bond_events"] > 0 and (stats["veto_events"] > 0) == cell_veto
     samples = np.loadtxt(tmp_path / "oo_separation.dat", comments="#")
     per_chain = int(end / interval)
     assert len(samples) == chains * per_chain
@@ -325,12 +342,14 @@ def _dipole_pair_start(seed, length=1.0):
     ("cell_veto.ini", "SamplesOfSeparation_CellVeto.dat"),
     ("dipole_factors_inside_first.ini", "SamplesOfSeparation_DipoleFactors_InsideFirst.dat"),
     ("dipole_factors_outside_first.ini", "SamplesOfSeparation_DipoleFactors_OutsideFirst.dat"),
-    ("dipole_factors_ratio.ini", "SamplesOfSeparation_DipoleFactors_Ratio.dat")])
+    ("dipole_factors_ratio.ini", "SamplesOfSeparation_DipoleFactors_Ratio.dat"),
+    ("atom_factors.ini", "SamplesOfSeparation_AtomFactors.dat")])
 def test_shipped_dipole_config_matches_reference_statistics(tmp_path, config, output):
     """dipoles/cell_veto.ini of 2018_JCP_149_064113 (two dipoles: composite-object Coulomb handlers with cell veto on
     anisotropic 3 x 5 x 7 root-level cells, harmonic bond, 1/r^6 repulsion between the opposite charges of different
     dipoles as a factor between objects) and the three dipole_factors_*.ini (no cell system: the composite-object
-    Coulomb factor of the factor type map with inside-first, outside-first and ratio lifting), unchanged except for the
+    Coulomb factor of the factor type map with inside-first, outside-first and ratio lifting) and atom_factors.ini (the
+    Coulomb interaction as four bounded leaf-to-leaf factors between the dipoles), unchanged except for the
     mediator line, run length, sampling interval and output file: the separations between like and unlike charges of
     different dipoles follow the cumulative histograms the reference ships (ReferenceDataDipoles_13.dat / _14.dat)."""
     import sys

@@ -66,7 +66,9 @@ def dipole_factors_builder_of(g, builder_cls):
     pb = builder_cls(3, int(g["meta_n"]), float(g["meta_system_length"]), float(g["meta_beta"]), [1, 1, 1], 0,
                      chain_time=float(g["meta_chain_time"]), initial_active=int(g["meta_initial_active"]),
                      seed=int(g["seed"][0]), no_cells=True)
-    pb.set_pair(abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"]),
+    # atom_factors.ini: the Coulomb interaction as bounded leaf-to-leaf factors between the objects
+    handler = abi.PAIR_TWO_LEAF_UNIT_BOUNDING if "meta_leaf_pairs" in g else abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING
+    pb.set_pair(handler, abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"]),
                 abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, *g["meta_ipcb"]), use_charge=True)
     pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1)],
                      bond_potential=abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, *g["meta_harmonic"]))
@@ -91,9 +93,26 @@ def single_molecule_builder_of(g, builder_cls):
     return pb
 
 
+def water_atomic_builder_of(g, builder_cls):
+    """The shipped water/coulomb_power_bounded_lj_inverted.ini: no cell system, Coulomb as bounded leaf-to-leaf factors
+    between the molecules, Lennard-Jones between the oxygens, harmonic bonds, bending."""
+    pb = single_molecule_builder_of(g, builder_cls)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT_BOUNDING, abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"]),
+                abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, *g["meta_ipcb"]), use_charge=True)
+    pb.set_molecules(abi.LIFTING_INSIDE_FIRST, inter_factors=[(1, 1)],
+                     inter_potential=abi.EcmcPotential.make(abi.POT_LENNARD_JONES, *g["meta_lj"]),
+                     bending=dict(children=[0, 1, 2], separations=[1, 0, 1, 2], lifting=abi.LIFTING_RATIO,
+                                  potential=abi.EcmcPotential.make(abi.POT_BENDING, *g["meta_bending"]),
+                                  offset=float(g["meta_bending_offset"]),
+                                  max_displacement=float(g["meta_bending_max_displacement"])))
+    return pb
+
+
 NO_CELL_MOLECULE_TRACES = {"trace_dipole_factors_inside_first": dipole_factors_builder_of,
                            "trace_dipole_factors_outside_first": dipole_factors_builder_of,
                            "trace_dipole_factors_ratio": dipole_factors_builder_of,
+                           "trace_dipole_atom_factors": dipole_factors_builder_of,
+                           "trace_water_atomic_factors": water_atomic_builder_of,
                            "trace_water_single_molecule": single_molecule_builder_of}
 
 
