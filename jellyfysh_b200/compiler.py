@@ -239,10 +239,9 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             eoc_handlers.append(handler)
         elif "InitialChainStartOfRunEventHandler" in names:
             start_handlers.append(handler)
-        elif names & {"SamplingEventHandler", "EndOfRunEventHandler"}:
+        elif names & {"SamplingEventHandler", "EndOfRunEventHandler", "DumpingEventHandler"}:
+            # host control events; a dumping event writes the device checkpoint (CudaBatchedMediator._dump)
             control.append(handler)
-        elif "DumpingEventHandler" in names:
-            raise _configuration_error("dumping handlers are not supported (device state is not picklable)")
         else:
             raise _configuration_error("event handler {0} has no device implementation".format(type(handler).__name__))
     if len(eoc_handlers) != 1 or len(start_handlers) != 1 or (not boundary_handlers and not no_cells):

@@ -46,7 +46,7 @@ class CudaBatchedMediator(Mediator):
     def __init__(self, input_output_handler: InputOutputHandler, state_handler: StateHandler, scheduler: Scheduler,
                  activator: Activator, number_of_chains: int = 1, device: int = 0, seed: int = 0,
                  first_random_stream: int = 0, maximum_surplus: int = 0, occupant_capacity: int = 8,
-                 events_per_launch: int = 4000000) -> None:
+                 events_per_launch: int = 4000000, resume_file: str = "") -> None:
         """
         Parameters follow SingleProcessMediator (single_process_mediator.py:57-72); in addition:
 
@@ -58,6 +58,9 @@ class CudaBatchedMediator(Mediator):
         events_per_launch : upper limit of events per chain and kernel launch; a chain that needs more to reach the
             next control time is continued by further launches, and one that stops advancing in time (a collapsing
             configuration, e.g. overlapping molecules with unbounded attraction) raises an error instead of hanging.
+        resume_file : a dump written by a DumpingEventHandler of an earlier run of the same configuration (the file name
+            of its DumpingOutputHandler plus ".npz"): the chains continue from it, event for event as the uninterrupted
+            run would (the role of jellyfysh/resume.py, whose dill of the reference's mediator cannot hold device state).
         """
         self._logger = logging.getLogger(__name__)
         if number_of_chains < 1:
@@ -90,6 +93,8 @@ class CudaBatchedMediator(Mediator):
         self._statistics = {}
         self._control_times = {}
         self._events_per_launch = max(int(events_per_launch), 1)
+        if resume_file:
+            self._resume(resume_file, all_charges)
 
     # ---- state hand-over to the reference's state handler ------------------------------------------------------
     def _load_chain_into_state_handler(self, chain, positions, states, roots=None):
@@ -134,6 +139,41 @@ class CudaBatchedMediator(Mediator):
             self._load_chain_into_state_handler(chain, positions, states, roots)
             self._input_output_handler.write(handler.output_handler, self._state_handler.extract_global_state())
 
+    # ---- dumping / resuming (DumpingEventHandler + DumpingOutputHandler, dumping_output_handler.py:70-90; resume.py) ----
+    def _dump(self, handler):
+        """The device state of all chains plus the schedule of the control handlers, next to the file name the
+        configuration gives its DumpingOutputHandler (that handler itself pickles the reference's mediator, which a device
+        handle does not survive)."""
+        output = self._input_output_handler._output_handlers_dictionary[handler.output_handler]
+        path = output._output_filename + ".npz"
+        controls = self._compiled.control_handlers
+        times = np.array([[self._control_times[h].quotient, self._control_times[h].remainder] for h in controls])
+        # the dumping handler itself has not been rescheduled yet: its next time follows from its own event time
+        self._engine.save_checkpoint(path)
+        with np.load(path) as data:
+            arrays = dict(data)
+        arrays["control_times"] = times
+        arrays["control_names"] = np.array([type(h).__name__ for h in controls])
+        arrays["dumping_handler"] = np.array(controls.index(handler))
+        np.savez_compressed(path, **arrays)
+        print("Writing dump into file {0}".format(path))
+
+    def _resume(self, path, charges):
+        controls = self._compiled.control_handlers
+        self._engine.load_checkpoint(path, charges)
+        with np.load(path) as data:
+            names, times, dumping = data["control_names"].tolist(), data["control_times"], int(data["dumping_handler"])
+        if names != [type(h).__name__ for h in controls]:
+            raise compiler._configuration_error("the dump {0} belongs to a configuration with other control handlers"
+                                                .format(path))
+        for index, handler in enumerate(controls):
+            # fixed-interval handlers continue from their own last event time (fixed_interval_*_event_handler.py)
+            handler._event_time = Time(float(times[index][0]), float(times[index][1]))
+            if index == dumping:
+                self._control_times[handler] = handler.send_event_time()  # the dump was written at this handler's event
+            else:
+                self._control_times[handler] = handler._event_time
+
     # ---- the loop ------------------------------------------------------------------------------------------------
     def run(self) -> None:
         """Advance all chains from control event to control event until the end-of-run handler fires."""
@@ -152,7 +192,10 @@ class CudaBatchedMediator(Mediator):
                 positions, roots, states = self._download()
                 self._load_chain_into_state_handler(0, positions, states, roots)
                 raise EndOfRun
-            self._write_output(handler)
+            if "DumpingEventHandler" in names:
+                self._dump(handler)
+            else:
+                self._write_output(handler)
             self._control_times[handler] = handler.send_event_time()
 
     def _advance_to(self, event_time):

@@ -436,3 +436,49 @@ def test_shipped_single_molecule_config_matches_reference_statistics(tmp_path):
         distance = np.max(np.abs(ours - cdf))
         print("single molecule", name, "KS distance", distance, "samples", len(samples), stats)
         assert distance < 1.95 / np.sqrt(chains * 5) + 5.0e-3, (name, distance)
+
+
+def test_shipped_dump_config_dumps_and_resumes(tmp_path):
+    """coulomb_atoms/power_bounded_dump.ini: its FixedIntervalDumpingEventHandler writes the device checkpoint next to the
+    DumpingOutputHandler's file name, and a second mediator built from the same file with `resume_file` continues from
+    the last dump to the end of the run exactly like the uninterrupted run (the role of resume.py)."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    chains = 64
+    ini = configs.shipped_ini(REF, "2018_JCP_149_064113", "coulomb_atoms", "power_bounded_dump.ini")
+    ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("end_of_run_time = 2000", "end_of_run_time = 30")
+    ini = ini.replace("dumping_interval = 1100", "dumping_interval = 11")
+    ini = ini.replace("filename = dump.dat", "filename = " + str(tmp_path / "dump.dat"))
+    ini = ini.replace("output/2018_JCP_149_064113/coulomb_atoms/SamplesOfSeparation_PowerBoundedDump.dat",
+                      str(tmp_path / "separation.dat"))
+    assert str(tmp_path / "dump.dat") in ini and "dumping_interval = 11" in ini and "end_of_run_time = 30" in ini
+
+    def run(extra):
+        text = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 41%s" % (chains, extra))
+        mediator, setting = build_reference_graph(text)
+        try:
+            with pytest.raises(EndOfRun):
+                mediator.run()
+            mediator.post_run()
+            return mediator.engine.download_positions(), mediator.engine.chain_states(), mediator.statistics
+        finally:
+            setting.reset()
+
+    full_positions, full_states, full_stats = run("")
+    # DumpingOutputHandler tags its file name with the interpreter (dump_cpython_3_12_3.dat); the device dump sits next to it
+    import glob
+    dump_path, = glob.glob(str(tmp_path / "dump*.dat.npz"))
+    dump = np.load(dump_path)
+    assert np.all(dump["chain_states"]["time_q"] == 22.0) and np.all(dump["chain_states"]["time_r"] == 0.0)
+    dumped_events = int(dump["chain_states"]["event_counter"].sum())
+    resumed_positions, resumed_states, resumed_stats = run("\nresume_file = " + dump_path)
+    assert np.array_equal(full_positions, resumed_positions)
+    for field in ("active", "direction", "time_q", "time_r", "event_counter", "eoc_q", "eoc_r"):
+        assert np.array_equal(full_states[field], resumed_states[field]), field
+    assert resumed_stats["events"] == full_stats["events"] - dumped_events > 0
