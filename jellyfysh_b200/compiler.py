@@ -224,7 +224,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                                            .format(type(handler).__name__))
         elif "TwoCompositeObjectSummedBoundingPotentialEventHandler" in names:
             pair_handlers.append(handler)
-        elif "TwoLeafUnitCellBoundingPotentialEventHandler" in names:
+        elif names & {"TwoLeafUnitCellBoundingPotentialEventHandler", "TwoCompositeObjectCellBoundingPotentialEventHandler"}:
             bounding_handlers.append(handler)
         elif "TwoLeafUnitBoundingPotentialEventHandler" in names or "TwoLeafUnitEventHandler" in names:
             pair_handlers.append(handler)
@@ -415,9 +415,22 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
         first = bounding_handlers[0]
         potential = potential_descriptor(first._potential)
         charge = first._charge
+        composite_bounding = "TwoCompositeObjectCellBoundingPotentialEventHandler" in _class_names(first)
+        if composite_bounding != molecules:
+            raise _configuration_error("composite-object cell-bounding handlers need root-level cells, leaf-unit ones "
+                                       "leaf-level cells")
         for handler in bounding_handlers[1:]:
-            if not _same_potential(potential, potential_descriptor(handler._potential)) or handler._charge != charge:
+            if not _same_potential(potential, potential_descriptor(handler._potential)) or handler._charge != charge or \
+                    type(handler) is not type(first):
                 raise _configuration_error("cell-bounding handlers must share potential and charge")
+        if composite_bounding:
+            # charge correction factor = active charge x max |target charges| (dipole_monte_carlo_estimator.py:158-186)
+            if "DipoleMonteCarloEstimator" not in _class_names(first._bounding_potential._estimator):
+                raise _configuration_error("the composite-object cell-bounding handler needs the dipole Monte Carlo estimator")
+            bounding_lifting = _lifting_kind(first._lifting)
+            if composite_lifting is not None and bounding_lifting != composite_lifting:
+                raise _configuration_error("the composite-object handlers must share one lifting scheme")
+            composite_lifting = bounding_lifting
         index_of = {cell: index for index, cell in enumerate(cell_objects)}
         bounds = np.zeros((len(cell_objects), dimension, 2))
         stored = first._bounding_potential._derivative_bounds  # a bare dict when no lower bounds were asked for
@@ -434,8 +447,6 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             charge_names.add(charge)
     # ---- molecules: lifting scheme of the composite-object handlers, factors between objects, bending
     if molecules:
-        if bounding_handlers:
-            raise _configuration_error("cell-bounding handlers for composite objects are not supported")
         if veto_handlers:
             if "CompositeObjectCellVetoEventHandler" not in _class_names(veto_handlers[0]):
                 raise _configuration_error("root-level cells need the composite-object cell-veto handler")

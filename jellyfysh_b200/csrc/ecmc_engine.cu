@@ -309,8 +309,8 @@ int build_device_program(EcmcHandle *h) {
         if (p.pair_handler != ECMC_PAIR_NONE && p.pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING &&
             p.pair_handler != ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING)
             return fail(h, ECMC_ERR_INVALID, "molecules need the composite-object pair handler or bounded leaf-to-leaf factors");
-        if (p.veto_enabled != ECMC_FAR_NONE && p.veto_enabled != ECMC_FAR_CELL_VETO)
-            return fail(h, ECMC_ERR_INVALID, "molecules support the cell-veto far field only");
+        // ECMC_FAR_CELL_BOUNDING here: TwoCompositeObjectCellBoundingPotentialEventHandler, one candidate per object in a
+        // cell that is not nearby
         if (p.composite_lifting < ECMC_LIFTING_INSIDE_FIRST || p.composite_lifting > ECMC_LIFTING_RATIO)
             return fail(h, ECMC_ERR_INVALID, "unknown lifting scheme");
         if (p.n_inter_factors < 0 || p.n_inter_factors > ECMC_MAX_INTER_FACTORS)

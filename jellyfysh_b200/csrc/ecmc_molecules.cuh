@@ -32,7 +32,8 @@ struct MoleculeProgram {
 };
 
 constexpr int kItemCapacity = 192;  // work items per chunk (two ints each: 1.5 KB per warp)
-enum ItemType { ITEM_PAIR_LEAF = 0, ITEM_INTER = 1, ITEM_BOND = 2, ITEM_BENDING = 3, ITEM_VETO = 4, ITEM_BOUNDARY = 5 };
+enum ItemType { ITEM_PAIR_LEAF = 0, ITEM_INTER = 1, ITEM_BOND = 2, ITEM_BENDING = 3, ITEM_VETO = 4, ITEM_BOUNDARY = 5,
+                ITEM_FAR_OBJECT = 6 };
 
 struct Vec3 {
     double x, y, z;
@@ -251,7 +252,8 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             bkind = stp->pending_kind;
             bt.q = stp->pending_q; bt.r = stp->pending_r;
             brate = stp->pending_rate;
-            if (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_BOND || bkind == ECMC_EVENT_FACTOR_PAIR)
+            if (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_BOND || bkind == ECMC_EVENT_FACTOR_PAIR ||
+                bkind == ECMC_EVENT_CELL_BOUNDING)
                 btarget = stp->pending_target;
             else bcell = stp->pending_target;
             restore = true;
@@ -261,9 +263,11 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             const bool factors_kept = kept_kind != ECMC_EVENT_NONE;
             const int nearby_slots = (P.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || leaf_pairs) ? P.n_nearby : 0;
             const int n_pair_slots = nearby_slots ? nearby_slots + n_surplus : 0;
-            // scan positions: [0, n_pair_slots) objects, then bonds, inter-object factors (one per object and factor),
-            // bending, veto, boundary
-            const int bond_base = n_pair_slots;
+            // scan positions: [0, n_pair_slots) objects, then (cell-bounding far field: one per cell) the objects in cells
+            // that are not nearby, bonds, inter-object factors (one per object and factor), bending, veto, boundary
+            const bool far_objects = P.veto_enabled == ECMC_FAR_CELL_BOUNDING;
+            const int far_base = n_pair_slots;
+            const int bond_base = far_base + (far_objects ? P.n_cells : 0);
             const int inter_base = bond_base + (factors_kept ? 0 : P.n_bonds);
             const int bending_base = inter_base + (factors_kept ? 0 : M.n_inter * n_roots);
             const int veto_base = bending_base + ((!factors_kept && M.bending_enabled) ? 1 : 0);
@@ -292,6 +296,12 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                     } else if (s < n_pair_slots) {
                         target = sur[s - nearby_slots];
                         type = ITEM_PAIR_LEAF; copies = npr;
+                    } else if (s < bond_base) {
+                        // CellBoundingPotentialTagger (cell_bounding_potential_tagger.py:150-155)
+                        const int cell = s - far_base;
+                        if (!cell_is_nearby(P, cell, cid0, cid1, cid2) && occ[cell] >= 0) {
+                            type = ITEM_FAR_OBJECT; target = cell; copies = 1;
+                        }
                     } else if (s < inter_base) {
                         const int b = s - bond_base;
                         const int partner = P.bonds[b][0] == active_child ? P.bonds[b][1]
@@ -367,6 +377,27 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                             rec_target = target;
                             is_factor = true;
                         }
+                    } else if (type == ITEM_FAR_OBJECT) {
+                        // TwoCompositeObjectCellBoundingPotentialEventHandler.send_event_time
+                        // (two_composite_object_cell_bounding_potential_event_handler.py:152-196): constant event rate =
+                        // bound of the relative cell x the estimator's charge correction factor, active charge x
+                        // max |target charges| (dipole_monte_carlo_estimator.py:158-186)
+                        const int root = occ[target];
+                        const int relative = relative_cell_of(P, target, cid0, cid1, cid2);
+                        double charge_product = 1.0;
+                        if (P.veto_use_charge) {
+                            double largest = 0.0;
+                            for (int k = 0; k < npr; k++) largest = fmax(largest, fabs(part[root * npr + k].charge));
+                            charge_product = acharge * largest;
+                        }
+                        const double *bound = P.bounds + (relative * P.dimension + dir) * 2;
+                        rate = charge_product > 0.0 ? __ldg(bound) * charge_product : -__ldg(bound + 1) * charge_product;
+                        const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, root), 0);
+                        const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                        dt = rate > 0.0 ? du / rate * P.inv_speed : INFINITY;
+                        cell = relative;
+                        kind = ECMC_EVENT_CELL_BOUNDING;
+                        rec_target = root;
                     } else if (type == ITEM_BENDING) {
                         // _displacement_from_piecewise_constant_bounding_potential
                         // (event_handler_with_bounding_potential.py:282-332)
@@ -504,8 +535,8 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                 stp->pending_kind = bkind;
                 stp->pending_q = bt.q; stp->pending_r = bt.r;
                 stp->pending_rate = brate;
-                stp->pending_target = (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_BOND || bkind == ECMC_EVENT_FACTOR_PAIR)
-                                          ? btarget : bcell;
+                stp->pending_target = (bkind == ECMC_EVENT_PAIR || bkind == ECMC_EVENT_BOND || bkind == ECMC_EVENT_FACTOR_PAIR ||
+                                       bkind == ECMC_EVENT_CELL_BOUNDING) ? btarget : bcell;
                 if (!was_pending) {
                     stp->pending_position = best_from_kept ? kept_pos : vcomp(apos, dir);
                     stp->pending_root_position = best_from_kept ? kept_root : vcomp(rpos, dir);
@@ -551,17 +582,21 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
         uint32_t draw = 0;
         switch (kind) {
         case ECMC_EVENT_PAIR:
+        case ECMC_EVENT_CELL_BOUNDING:
         case ECMC_EVENT_CELL_VETO: {
-            const bool veto = kind == ECMC_EVENT_CELL_VETO;
+            // far: TwoCompositeObjectCellBoundingPotentialEventHandler.send_out_state (:198-246) -- the cell veto's
+            // out-state with a known target object; the stored rate is per length, the bound's derivative is rate x speed
+            const bool far = kind == ECMC_EVENT_CELL_BOUNDING;
+            const bool veto = kind == ECMC_EVENT_CELL_VETO || far;
             // leaf_pairs: btarget is the target LEAF; the loops below then run over that one leaf only
             const bool one_leaf = leaf_pairs && !veto;
-            const int target_root = veto ? occ[bcell] : (one_leaf ? btarget / npr : btarget);
+            const int target_root = far ? btarget : (veto ? occ[bcell] : (one_leaf ? btarget / npr : btarget));
             rec_target = one_leaf ? btarget : target_root;
-            if (veto) n_veto++; else n_pair++;
+            if (veto && !far) n_veto++; else n_pair++;
             if (target_root < 0) break;
             const int k_first = one_leaf ? btarget - target_root * npr : 0, k_last = one_leaf ? k_first + 1 : npr;
             const bool use_charge = veto ? P.veto_use_charge : P.pair_use_charge;
-            double bounding_rate = veto ? brate : 0.0;
+            double bounding_rate = far ? brate * speed : (veto ? brate : 0.0);
             double factor_derivative = 0.0;
             double target_derivatives[4] = {0.0, 0.0, 0.0, 0.0};
             Vec3 tpos[4];
@@ -622,7 +657,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                 }
             }
             new_active = lifting_get(lift, M.composite_lifting, key, draw);
-            if (veto) count_rare(A, lane, 3);
+            if (veto && !far) count_rare(A, lane, 3);
             break;
         }
         case ECMC_EVENT_BOND:

@@ -1455,6 +1455,38 @@ static candidate composite_pair_candidate(OrcChain *c, int target_root) {
     return cand;
 }
 
+/* TwoCompositeObjectCellBoundingPotentialEventHandler.send_event_time
+ * (two_composite_object_cell_bounding_potential_event_handler.py:152-196): the composite object `target_root` in a cell that
+ * is not nearby the active ROOT's cell; constant event rate = bound of the relative cell times the charge correction
+ * factor of the DipoleMonteCarloEstimator, active charge x max |target charges| (dipole_monte_carlo_estimator.py:158-186;
+ * CellBoundingPotential._standard_velocity_displacement_with_charges, cell_bounding_potential.py:155-190) */
+static candidate composite_cell_bounding_candidate(OrcChain *c, int target_root) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_CELL_BOUNDING; cand.target = target_root;
+    int dir = c->st.direction, npr = c->npr;
+    int active_cell = position_to_cell(&c->cells, c->root_pos + (c->st.active / npr) * c->D);
+    int target_cell = position_to_cell(&c->cells, c->root_pos + target_root * c->D);
+    int relative_cell = cells_relative(&c->cells, target_cell, active_cell);
+    cand.target_cell = relative_cell;
+    double charge_product = 1.0;
+    if (c->prog.veto_use_charge) {
+        double largest = 0.0;
+        for (int k = 0; k < npr; k++) {
+            double a = fabs(c->charge[target_root * npr + k]);
+            if (a > largest) largest = a; /* max(abs(charge) for charge in target_charges) */
+        }
+        charge_product = c->charge[c->st.active] * largest;
+    }
+    if (charge_product > 0.0) cand.rate = c->bounds[(relative_cell * c->D + dir) * 2 + 0] * charge_product;
+    else cand.rate = -c->bounds[(relative_cell * c->D + dir) * 2 + 1] * charge_product;
+    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target_root), 0);
+    double dU = rng_expovariate(u, c->prog.beta);
+    double displacement = cand.rate > 0 ? dU / cand.rate : ORC_INF;
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, displacement / c->prog.speed);
+    return cand;
+}
+
 /* Leaf-to-leaf factors with a bounding potential between the active leaf and leaf k of another object, each handled by a
  * TwoLeafUnitBoundingPotentialEventHandler (two_leaf_unit_bounding_potential_event_handler.py:112-146) fed by non-local
  * factor type map entries ("[0, 2], Coulomb" ... of factor_set_dipoles_atomic.txt: every leaf of one object with every
@@ -1693,6 +1725,18 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         if (c->prog.veto_enabled == ECMC_FAR_CELL_VETO) {
             candidate cand = veto_candidate(c);
             CONSIDER(cand);
+        } else if (c->prog.veto_enabled == ECMC_FAR_CELL_BOUNDING) {
+            /* CellBoundingPotentialTagger (cell_bounding_potential_tagger.py:150-155): every occupied cell that is not
+             * nearby the active cell */
+            for (int cell = 0; cell < c->cells.n_cells; cell++) {
+                int t = c->occ[cell];
+                if (t < 0) continue;
+                int is_near = 0;
+                for (int i = 0; i < nn; i++) if (nearby[i] == cell) { is_near = 1; break; }
+                if (is_near) continue;
+                candidate cand = composite_cell_bounding_candidate(c, t);
+                CONSIDER(cand);
+            }
         }
         if (!c->prog.no_cells) {
             candidate cand = root_boundary_candidate(c, &boundary_position);
@@ -1762,10 +1806,14 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
     const double *pa = c->pos + old_active * D;
     switch (best.kind) {
     case ECMC_EVENT_PAIR:
+    case ECMC_EVENT_CELL_BOUNDING:
     case ECMC_EVENT_CELL_VETO: {
         /* two_composite_object_summed_bounding_potential_event_handler.py:158-202 /
-         * composite_object_cell_veto_event_handler.py:110-162 (+ mediator.py:265-292 for the occupant of the cell) */
-        int veto = best.kind == ECMC_EVENT_CELL_VETO;
+         * composite_object_cell_veto_event_handler.py:110-162 (+ mediator.py:265-292 for the occupant of the cell) /
+         * two_composite_object_cell_bounding_potential_event_handler.py:198-246: like the cell veto with a known target
+         * object; the stored rate is a rate per length, the bounding potential's derivative is that times the speed */
+        int far = best.kind == ECMC_EVENT_CELL_BOUNDING;
+        int veto = best.kind == ECMC_EVENT_CELL_VETO || far;
         if (!veto && c->prog.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING) {
             /* TwoLeafUnitBoundingPotentialEventHandler.send_out_state (:148-168) +
              * _calculate_out_state_of_two_leaf_unit_bounding_potential (event_handler_with_bounding_potential.py:75-101) */
@@ -1784,11 +1832,11 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
             }
             break;
         }
-        int target_root = veto ? c->occ[best.target_cell] : best.target;
+        int target_root = (veto && !far) ? c->occ[best.target_cell] : best.target;
         rec_target = target_root;
-        if (veto) c->stats.veto_events++; else c->stats.pair_events++;
+        if (veto && !far) c->stats.veto_events++; else c->stats.pair_events++;
         if (target_root < 0) break;
-        double bounding_rate = veto ? best.rate : 0.0;
+        double bounding_rate = far ? best.rate * c->prog.speed : (veto ? best.rate : 0.0);
         double factor_derivative = 0.0;
         double target_derivatives[4] = {0, 0, 0, 0};
         const opotential *real = veto ? &c->veto_pot : &c->pair_pot;
@@ -1813,7 +1861,7 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         /* the summed-bounding handler passes the clipped event rate, the cell-veto handler the factor derivative */
         new_active = composite_lifting(c, target_root, veto ? factor_derivative : event_rate, target_derivatives, &draw);
         accepted = 1;
-        if (veto) c->stats.veto_accepted++;
+        if (veto && !far) c->stats.veto_accepted++;
         break;
     }
     case ECMC_EVENT_BOND:

@@ -416,6 +416,24 @@ def no_cell_molecule_traces():
                           bending_max_displacement=0.1, initial_active=1, far_field=0))
 
 
+def composite_cell_bounding_traces():
+    # the shipped dipoles/cell_bounded.ini sized for four dipoles: composite-object Coulomb handlers for nearby cells and
+    # the surplus, TwoCompositeObjectCellBoundingPotentialEventHandler for every object in a cell that is not nearby
+    # (3 x 5 x 7 root-level cells), harmonic bond, 1/r^6 repulsion, factors kept across cell-boundary events of the root
+    n = 4
+    roots, leaves = configs.dipole_start(n, seed=47, minimum_distance=0.25)
+    ini = configs.shipped_without_sampling(
+        REF, ("2018_JCP_149_064113", "dipoles", "cell_bounded.ini"),
+        replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                      ("number_event_handlers = 1", f"number_event_handlers = {2 * (n - 1)}"),
+                      ("number_trials = 1000", "number_trials = 100")])
+    chain_trace("trace_dipole_cell_bounded", ini, None, seed=25, stream=19, n_events=4000, snapshot_every=250,
+                composites=(roots, leaves), charges=np.tile([1.0, -1.0], n),
+                meta=dict(n=2 * n, nodes_per_root=2, system_length=1.0, beta=1.0, chain_time=0.78965,
+                          cells_per_side=[3, 5, 7], neighbor_layers=1, mic=[1.0, 3.45, 6, 2], ipcb=[1.5837],
+                          harmonic=[200.0, 0.1, 2.0], repulsive=[6.0, 1.0e-6], lifting=0, initial_active=0, far_field=2))
+
+
 def cell_bounding_traces():
     # Coulomb atoms with the far field through TwoLeafUnitCellBoundingPotentialEventHandler (shipped
     # coulomb_atoms/cell_bounded.ini shape)
@@ -535,6 +553,7 @@ if __name__ == "__main__":  # noqa
         dipole_traces()
     if "cell_bounding" in which:
         cell_bounding_traces()
+        composite_cell_bounding_traces()
     if "potentials" in which:
         potential_vectors()
     if "base" in which:

@@ -191,7 +191,7 @@ class ReferenceRun:
         names = {cls.__name__ for cls in type(handler).__mro__}
         if "CellVetoEventHandler" in names:
             return EVENT_CELL_VETO
-        if "TwoLeafUnitCellBoundingPotentialEventHandler" in names:
+        if names & {"TwoLeafUnitCellBoundingPotentialEventHandler", "TwoCompositeObjectCellBoundingPotentialEventHandler"}:
             return EVENT_CELL_BOUNDING
         if "CellBoundaryEventHandler" in names:
             return EVENT_CELL_BOUNDARY
@@ -238,6 +238,10 @@ class ReferenceRun:
     def _is_composite_pair(handler):
         return "TwoCompositeObjectSummedBoundingPotentialEventHandler" in {c.__name__ for c in type(handler).__mro__}
 
+    @staticmethod
+    def _is_composite_cell_bounding(handler):
+        return "TwoCompositeObjectCellBoundingPotentialEventHandler" in {c.__name__ for c in type(handler).__mro__}
+
     def _is_leaf_pair_between_objects(self, handler):
         names = {c.__name__ for c in type(handler).__mro__}
         return (self.setting.number_of_node_levels == 2 and "TwoLeafUnitBoundingPotentialEventHandler" in names
@@ -261,7 +265,8 @@ class ReferenceRun:
             orig_time, orig_out = h.send_event_time, h.send_out_state
 
             def send_event_time(*args, _h=h, _kind=kind, _orig=orig_time):
-                if _kind == EVENT_PAIR and run._is_composite_pair(_h):
+                if (_kind == EVENT_PAIR and run._is_composite_pair(_h)) or \
+                        (_kind == EVENT_CELL_BOUNDING and run._is_composite_cell_bounding(_h)):
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_root_of(args[0])))
                 elif _kind == EVENT_PAIR and run._is_leaf_pair_between_objects(_h):
                     # keyed like the composite-object handler: (pair time, target object), double = target child
@@ -374,6 +379,9 @@ class ReferenceRun:
             rec["target"] = winner._target_leaf_units[0].identifier[0]  # the target composite object (root)
         elif kind in (EVENT_PAIR, EVENT_BOND, EVENT_FACTOR_PAIR):
             rec["target"] = [self.leaf_id(u.identifier) for u in winner._leaf_units if u.velocity is None][0]
+        elif kind == EVENT_CELL_BOUNDING and self._is_composite_cell_bounding(winner):
+            rec["target"] = winner._target_leaf_units[0].identifier[0]  # the target composite object (root)
+            rec["target_cell"] = self._cell_index(winner._relative_cell)
         elif kind == EVENT_CELL_BOUNDING:
             rec["target"] = [u.identifier[0] for u in winner._leaf_units if u.velocity is None][0]
             rec["target_cell"] = self._cell_index(winner._relative_cell)

@@ -216,6 +216,31 @@ def test_atom_factors_graph_compiles_and_replays(oracle):
         setting.reset()
 
 
+def test_dipole_cell_bounded_graph_compiles_and_replays(oracle):
+    """The shipped dipoles/cell_bounded.ini (TwoCompositeObjectCellBoundingPotentialEventHandler for the far field) sized
+    for four dipoles -> compiler -> oracle chain reproduces the reference trace bit for bit. The bounds come from the
+    reference's Monte Carlo estimator, whose draws the recorder keys by purpose, so the rebuilt graph has the same bounds."""
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_dipole_cell_bounded")
+    n = int(g["meta_n"]) // 2
+    ini = configs.shipped_without_sampling(
+        REF, ("2018_JCP_149_064113", "dipoles", "cell_bounded.ini"), end_of_run_time=5.0,
+        replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                      ("number_event_handlers = 1", f"number_event_handlers = {2 * (n - 1)}"),
+                      ("number_trials = 1000", "number_trials = 100")])
+    mediator, setting = build_reference_graph(ini, composites=(g["roots0"], g["positions0"].reshape(n, 2, 3)))
+    try:
+        state = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, state, seed=int(g["seed"][0]))
+        p = compiled.builder.program
+        assert p.veto_enabled == abi.FAR_CELL_BOUNDING and p.cell_level == 1 and p.no_cells == 0
+        assert p.pair_handler == abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING and p.composite_lifting == abi.LIFTING_INSIDE_FIRST
+        assert [p.cells_per_side[d] for d in range(3)] == [3, 5, 7] and p.boundary_keeps_factors == 1
+        assert compiled.builder.tables["bounds"].shape == (105, 3, 2)
+    finally:
+        setting.reset()
+
+
 def test_sequential_direction_end_of_chain_is_rejected():
     """single_hard_disk_dipole.ini rotates the velocity by an angle at the end of a chain (a subclass of the
     periodic-direction handler): not built on the device, and said so instead of being mistaken for its base class."""

@@ -265,6 +265,40 @@ def test_no_cells_composite_reference_trace_replay(oracle, name):
             assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL * max(1.0, length)
 
 
+@pytest.mark.parametrize("name", tu.COMPOSITE_CELL_BOUNDING_TRACES)
+def test_composite_cell_bounding_reference_trace_replay(oracle, name):
+    """The shipped dipoles/cell_bounded.ini (four dipoles) on the device: composite-object cell-bounding candidates for
+    the objects in cells that are not nearby, every event of the reference trace, in resynchronised stretches."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    stretch = 100
+    chain = oracle.OracleChain(tu.dipole_cell_bounded_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    with engine.Engine(tu.dipole_cell_bounded_builder_of(g, ProgramBuilder), n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None], tu.charges_of(g)[None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        for done in range(0, len(records), stretch):
+            count = min(stretch, len(records) - done)
+            if done:
+                eng.upload_positions(chain.positions()[None], tu.charges_of(g)[None])
+                eng.upload_roots(chain.roots()[None])
+                eng.set_chain_states(np.frombuffer(bytes(chain.state()), dtype=abi.chain_state_dtype()))
+                occupants, surplus = chain.cells()
+                eng.set_cells(occupants[None], [surplus])
+            rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+            assert stats["events"] == count and stats["capacity_errors"] == 0
+            assert_records_match(rec[0], records[done:done + count], length, f"{name}[{done}:{done + count}]")
+            n, ours = chain.run(max_events=count, record=count)
+            assert n == count and tu.records_equal_discrete(ours, records[done:done + count])
+            assert np.max(np.abs(eng.download_positions()[0] - chain.positions())) < RTOL * max(1.0, length)
+            occ, surplus = eng.cells()
+            assert np.array_equal(occ[0], chain.cells()[0])
+
+
 def test_no_cells_batch_against_oracle(oracle):
     """The same structure on a batch: 40 atoms of both signs per chain (two passes of pair lanes), 9 chains."""
     n, length = 40, 1.0

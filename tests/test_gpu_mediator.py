@@ -343,7 +343,8 @@ def _dipole_pair_start(seed, length=1.0):
     ("dipole_factors_inside_first.ini", "SamplesOfSeparation_DipoleFactors_InsideFirst.dat"),
     ("dipole_factors_outside_first.ini", "SamplesOfSeparation_DipoleFactors_OutsideFirst.dat"),
     ("dipole_factors_ratio.ini", "SamplesOfSeparation_DipoleFactors_Ratio.dat"),
-    ("atom_factors.ini", "SamplesOfSeparation_AtomFactors.dat")])
+    ("atom_factors.ini", "SamplesOfSeparation_AtomFactors.dat"),
+    ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat")])
 def test_shipped_dipole_config_matches_reference_statistics(tmp_path, config, output):
     """dipoles/cell_veto.ini of 2018_JCP_149_064113 (two dipoles: composite-object Coulomb handlers with cell veto on
     anisotropic 3 x 5 x 7 root-level cells, harmonic bond, 1/r^6 repulsion between the opposite charges of different

@@ -122,6 +122,39 @@ def test_no_cells_chain_replay_bit_exact(oracle, name):
     assert chain.stats()["capacity_errors"] == 0
 
 
+@pytest.mark.parametrize("name", tu.COMPOSITE_CELL_BOUNDING_TRACES)
+def test_composite_cell_bounding_chain_replay_bit_exact(oracle, name):
+    """The shipped dipoles/cell_bounded.ini sized for four dipoles: TwoCompositeObjectCellBoundingPotentialEventHandler for
+    the objects in cells that are not nearby (two thirds of all events), composite-object Coulomb handlers for the rest,
+    root-level 3 x 5 x 7 cells with cell-boundary events of the root."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    chain = oracle.OracleChain(tu.dipole_cell_bounded_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        for f in tu.DISCRETE_FIELDS:
+            assert np.array_equal(rec[f], ref[f]), (f, done + int(np.nonzero(rec[f] != ref[f])[0][0]))
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            assert np.array_equal(chain.roots(), g["snap_roots"][k])
+            occ, surplus = chain.cells()
+            assert np.array_equal(occ, g["snap_occupants"][k])
+            ns = int(g["snap_n_surplus"][k])
+            assert sorted(surplus.tolist()) == sorted(g["snap_surplus"][k][:ns].tolist())
+    assert (records["kind"] == 5).sum() > 2000 and (records["kind"] == 3).sum() > 100
+    assert np.array_equal(chain.positions(), g["final_positions"]) and np.array_equal(chain.roots(), g["final_roots"])
+
+
 @pytest.mark.parametrize("name", sorted(tu.NO_CELL_MOLECULE_TRACES))
 def test_no_cells_composite_chain_replay_bit_exact(oracle, name):
     """Composite point objects without a cell system: the three shipped dipoles/dipole_factors_*.ini (three dipoles;

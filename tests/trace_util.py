@@ -78,6 +78,27 @@ def dipole_factors_builder_of(g, builder_cls):
     return pb
 
 
+def dipole_cell_bounded_builder_of(g, builder_cls):
+    """The shipped dipoles/cell_bounded.ini: composite-object Coulomb handlers for nearby cells and the surplus, the
+    composite-object cell-bounding handler for all other occupied cells (bounds as the reference's estimator built
+    them), harmonic bond, 1/r^6 repulsion between objects; root-level cells."""
+    n = int(g["meta_n"])
+    npr = int(g["meta_nodes_per_root"])
+    pb = builder_cls(3, n, float(g["meta_system_length"]), float(g["meta_beta"]),
+                     [int(c) for c in g["meta_cells_per_side"]], int(g["meta_neighbor_layers"]), max_occupants=1,
+                     max_surplus=n // npr, chain_time=float(g["meta_chain_time"]),
+                     initial_active=int(g["meta_initial_active"]), seed=int(g["seed"][0]))
+    mic = abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"])
+    pb.set_pair(abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, mic,
+                abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, *g["meta_ipcb"]), use_charge=True)
+    pb.set_cell_bounding(mic, g["bounds"], use_charge=True, target_charge=1.0)
+    pb.set_composite(npr, bonds=[(0, 1)],
+                     bond_potential=abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, *g["meta_harmonic"]))
+    pb.set_molecules(abi.LIFTING_INSIDE_FIRST, inter_factors=[(0, 1), (1, 0)],
+                     inter_potential=abi.EcmcPotential.make(abi.POT_INVERSE_POWER, *g["meta_repulsive"]))
+    return pb
+
+
 def single_molecule_builder_of(g, builder_cls):
     """The shipped water/single_molecule.ini: two harmonic bonds and the bending factor of one molecule."""
     pb = builder_cls(3, int(g["meta_n"]), float(g["meta_system_length"]), float(g["meta_beta"]), [1, 1, 1], 0,
@@ -108,6 +129,7 @@ def water_atomic_builder_of(g, builder_cls):
     return pb
 
 
+COMPOSITE_CELL_BOUNDING_TRACES = ["trace_dipole_cell_bounded"]
 NO_CELL_MOLECULE_TRACES = {"trace_dipole_factors_inside_first": dipole_factors_builder_of,
                            "trace_dipole_factors_outside_first": dipole_factors_builder_of,
                            "trace_dipole_factors_ratio": dipole_factors_builder_of,
