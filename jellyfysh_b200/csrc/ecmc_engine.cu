@@ -554,7 +554,10 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         const int IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, MIC = ECMC_POT_MERGED_IMAGE_COULOMB,
                   DEP = kPotHarmonic, LJ = ECMC_POT_LENNARD_JONES;
         MoleculeKernel kernel;
-        constexpr int kAlignedWarps = 8;
+#ifndef ECMC_ALIGNED_WARPS
+#define ECMC_ALIGNED_WARPS 8
+#endif
+        constexpr int kAlignedWarps = ECMC_ALIGNED_WARPS;
         bool aligned = true;
         if (const char *env = std::getenv("ECMC_MOLECULE_ALIGNED")) aligned = std::atoi(env) != 0;
         if (water && aligned)
