@@ -44,7 +44,8 @@ def _run_one(args):
 
 
 def _run_one_unguarded(args):
-    ini_text, positions, seed, warmup_seconds, budget_seconds, segments = args
+    ini_text, positions, seed, warmup_seconds, budget_seconds, segments = args[:6]
+    composites = args[6] if len(args) > 6 else None
     sys.path.insert(0, REF_ROOT)
     import warnings
     warnings.filterwarnings("ignore")
@@ -59,8 +60,19 @@ def _run_one_unguarded(args):
     if positions is not None:
         iterator = iter([list(map(float, p)) for p in positions])
         setting.random_position = lambda: next(iterator)
-    with contextlib.redirect_stdout(io.StringIO()):
-        mediator = factory.build_from_config(config, to_camel_case(config.get("Run", "mediator")), "jellyfysh.mediator")
+    restore = None
+    if composites is not None:
+        # composite point objects (dipoles, molecules): the start configuration goes through the node creator of the
+        # reference's random input handler, like the positions above (tests/golden/configs.py: patch_composite_start)
+        sys.path.insert(0, os.path.join(HERE, "..", "tests", "golden"))
+        import configs
+        restore = configs.patch_composite_start(composites)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mediator = factory.build_from_config(config, to_camel_case(config.get("Run", "mediator")), "jellyfysh.mediator")
+    finally:
+        if restore is not None:
+            restore()
     init_seconds = time.perf_counter() - t_init
     scheduler = mediator._scheduler
     original = scheduler.get_succeeding_event
@@ -92,12 +104,12 @@ def _run_one_unguarded(args):
     return state["done"], init_seconds
 
 
-def run_segments(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0, segments=1):
+def run_segments(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0, segments=1, composites=None):
     """One chain per entry of positions_per_process in parallel processes, `segments` consecutive timed segments of
     budget_seconds each after the warm-up. Returns ([events/s summed over processes per segment], processes,
     total events, mean init seconds)."""
-    jobs = [(ini_text, positions, 1000 + k, warmup_seconds, budget_seconds, segments)
-            for k, positions in enumerate(positions_per_process)]
+    jobs = [(ini_text, positions, 1000 + k, warmup_seconds, budget_seconds, segments,
+             None if composites is None else composites[k]) for k, positions in enumerate(positions_per_process)]
     context = multiprocessing.get_context("spawn")
     with context.Pool(len(jobs)) as pool:
         results = pool.map(_run_one, jobs)
@@ -109,10 +121,10 @@ def run_segments(ini_text, positions_per_process, warmup_seconds=2.0, budget_sec
     return rates, len(jobs), events, sum(init for _, init in results) / len(results)
 
 
-def run(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0):
+def run(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0, composites=None):
     """Single timed segment: (events per second summed over processes, processes, events, mean init seconds)."""
     rates, processes, events, init_seconds = run_segments(ini_text, positions_per_process, warmup_seconds,
-                                                          budget_seconds, 1)
+                                                          budget_seconds, 1, composites)
     return rates[0], processes, events, init_seconds
 
 
