@@ -104,6 +104,7 @@ def main():
     parser.add_argument("--only", default="")
     args = parser.parse_args()
     runs = [("c1", lambda: c1_dipoles(4096)), ("c3_64", lambda: c3_coulomb(64, 4096)),
+            ("c3_128", lambda: c3_coulomb(128, 4096)), ("c3_256", lambda: c3_coulomb(256, 2048)),
             ("c3_512", lambda: c3_coulomb(512, 1024)), ("c4_2", lambda: c4_water(2, 4096)),
             ("c4_32", lambda: c4_water(32, 1024)), ("c5", c5_single_chain)]
     results = [run() for name, run in runs if not args.only or name in args.only.split(",")]
