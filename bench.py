@@ -80,7 +80,36 @@ class ClockSampler:
     def close_window(self):
         self.window[1] = time.perf_counter()
 
+    def _poll_nvml(self):
+        """NVML directly (what nvidia-smi reads), every 5 ms: the timed region of the default run lasts a quarter of a
+        second, in which a `nvidia-smi -lms` loop delivers only a handful of lines."""
+        import pynvml
+        names = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        while not self._stop.is_set():
+            try:
+                clock = pynvml.nvmlDeviceGetClockInfo(self._nvml_handle, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._nvml_handle)
+            except pynvml.NVMLError:
+                break
+            fields = [str(clock), str(self._nvml_max)] + ["Active" if reasons & bit else "Not Active" for bit, _ in names]
+            self.samples.append((time.perf_counter(), fields))
+            self._stop.wait(0.005)
+
     def __enter__(self):
+        self._stop = threading.Event()
+        self.source = "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml_handle = pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
+            self._nvml_max = pynvml.nvmlDeviceGetMaxClockInfo(self._nvml_handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._nvml_handle)  # raises where it is not supported
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return self
+        except Exception:  # noqa: BLE001 - fall back to the nvidia-smi loop
+            pass
         try:
             self.process = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.FIELDS,
                                              "--format=csv,noheader,nounits", "-lms", "20"],
@@ -98,6 +127,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), parts))
 
     def __exit__(self, *exc):
+        self._stop.set()
         if self.process is not None:
             self.process.terminate()
             try:
@@ -119,7 +149,7 @@ class ClockSampler:
                 if value.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": int(samples[0][1]), "reasons": sorted(reasons),
-                "samples": len(samples), "samples_inside_timed_region": len(inside)}
+                "samples": len(samples), "samples_inside_timed_region": len(inside), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------------------
