@@ -48,6 +48,8 @@ def parse_args():
     parser.add_argument("--e2e-steps", type=int, default=8)
     parser.add_argument("--cpu-seconds", type=float, default=8.0, help="wall budget of the CPU baseline sample")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--ref-seconds", type=float, default=None,
+                        help="--impl reference: wall-clock length of one step (default min(20, 60 / (W + K)) s)")
     parser.add_argument("--no-single-chain", action="store_true", help="skip the C5 single-chain latency leg (N = 1 only)")
     return parser.parse_args()
 
@@ -217,7 +219,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     steps = args.warmup + args.steps
-    seconds = max(0.5, min(20.0, 60.0 / steps))
+    seconds = args.ref_seconds if args.ref_seconds else max(0.5, min(20.0, 60.0 / steps))
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
     import configs
