@@ -21,10 +21,13 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Chains (warps) per CTA; must divide ECMC_RESIDENT_WARPS (28). Measured on C2 (profiles/README.md): 1 / 2 / 4 / 7 / 14
+// warps -> 8.07 / 7.96 / 7.92 / 7.97 / 8.23e8 events/s; 28 does not fit the static shared memory (2 KB per warp).
 #ifndef ECMC_WARPS_PER_BLOCK
-#define ECMC_WARPS_PER_BLOCK 4
+#define ECMC_WARPS_PER_BLOCK 14
 #endif
 constexpr int kWarpsPerBlock = ECMC_WARPS_PER_BLOCK;
+static_assert(ECMC_RESIDENT_WARPS % ECMC_WARPS_PER_BLOCK == 0, "whole CTAs must fill the resident warps of an SM");
 
 struct EventPair {
     cudaEvent_t start, stop;
