@@ -28,6 +28,9 @@ thread_local std::string g_create_error;
 #endif
 constexpr int kWarpsPerBlock = ECMC_WARPS_PER_BLOCK;
 static_assert(ECMC_RESIDENT_WARPS % ECMC_WARPS_PER_BLOCK == 0, "whole CTAs must fill the resident warps of an SM");
+// molecule_kernel without the per-event CTA barrier (composite objects other than water, ECMC_MOLECULE_ALIGNED=0): small
+// CTAs leave the compiler its 168 registers (a CTA of 14 warps would cap them at 128)
+constexpr int kMoleculeWarps = 4;
 
 struct EventPair {
     cudaEvent_t start, stop;
@@ -567,12 +570,12 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
             kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kAlignedWarps, true>
                                : molecule_kernel<IPCB, MIC, DEP, LJ, false, kAlignedWarps, true>;
         else if (water)
-            kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kWarpsPerBlock, false>
-                               : molecule_kernel<IPCB, MIC, DEP, LJ, false, kWarpsPerBlock, false>;
+            kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kMoleculeWarps, false>
+                               : molecule_kernel<IPCB, MIC, DEP, LJ, false, kMoleculeWarps, false>;
         else
-            kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kWarpsPerBlock, false>
-                               : molecule_kernel<-1, -1, -1, -1, false, kWarpsPerBlock, false>;
-        const int warps = water && aligned ? kAlignedWarps : kWarpsPerBlock;
+            kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kMoleculeWarps, false>
+                               : molecule_kernel<-1, -1, -1, -1, false, kMoleculeWarps, false>;
+        const int warps = water && aligned ? kAlignedWarps : kMoleculeWarps;
         kernel<<<(h->n_chains + warps - 1) / warps, warps * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
     } else {
         const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
@@ -731,7 +734,7 @@ ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_s
         CUDA_TRY(h, cudaMemcpyAsync(h->d_streams, streams, sizeof(uint32_t) * h->n_chains, cudaMemcpyHostToDevice, h->stream));
     const int blocks = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (h->molecules)
-        molecule_start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
+        molecule_start_kernel<kMoleculeWarps><<<(h->n_chains + kMoleculeWarps - 1) / kMoleculeWarps, kMoleculeWarps * 32, 0, h->stream>>>(
             h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
             h->program.initial_direction, h->d_stats);
     else
