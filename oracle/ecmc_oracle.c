@@ -103,6 +103,11 @@ ORC_API double orc_time_sub(double q1, double r1, double q2, double r2) {
     otime a = {q1, r1}, b = {q2, r2};
     return time_sub(a, b);
 }
+/* the order of the scheduler's heap, heap.c:176-178 / :217-233 (Time.__lt__, base/time.py:167-182) */
+ORC_API int orc_time_lt(double q1, double r1, double q2, double r2) {
+    otime a = {q1, r1}, b = {q2, r2};
+    return time_lt(a, b);
+}
 ORC_API void orc_time_from_float(double t, double *out_q, double *out_r) {
     otime x = time_from_float(t);
     *out_q = x.q; *out_r = x.r;

@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
     L.orc_time_sub.argtypes = [d, d, d, d]
     L.orc_time_sub.restype = d
     L.orc_time_from_float.argtypes = [d, dp, dp]
+    L.orc_time_lt.argtypes = [d, d, d, d]
+    L.orc_time_lt.restype = i
     L.orc_correct_position_entry.argtypes = [d, d]
     L.orc_correct_position_entry.restype = d
     L.orc_correct_separation_entry.argtypes = [d, d]
@@ -96,6 +98,10 @@ def time_add(q, r, other):
 
 def time_sub(q1, r1, q2, r2):
     return lib().orc_time_sub(q1, r1, q2, r2)
+
+
+def time_lt(q1, r1, q2, r2):
+    return bool(lib().orc_time_lt(q1, r1, q2, r2))
 
 
 def time_from_float(t):

@@ -38,3 +38,58 @@ def test_cells_and_boundaries_bit_exact(oracle, geo):
     for s, so, po in zip(g[f"geo{geo}_sep_in"], g[f"geo{geo}_sep_out"], g[f"geo{geo}_pos_out"]):
         assert lib.orc_correct_separation_entry(s, length) == so
         assert lib.orc_correct_position_entry(s, length) == po
+
+
+def test_time_order_matches_the_compiled_reference_heap(oracle):
+    """The argmin the Scheduler would pop: the reference's own heap (oracle/_ref/libref_heap.so, compiled in place from
+    jellyfysh/scheduler/heap_scheduler/heap.c) pops random Times -- equal quotients, tiny and huge remainders, stale
+    entries removed lazily through the validity callback -- in exactly the order of the oracle's comparison."""
+    import ctypes as C
+    import functools
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "_ref", "libref_heap.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (no reference checkout on this machine)")
+    heap_lib = C.CDLL(path)
+
+    class HeapEntry(C.Structure):
+        _fields_ = [("time_quotient", C.c_double), ("time_remainder", C.c_double), ("event_handler", C.c_void_p),
+                    ("counter", C.c_uint)]
+
+    callback_type = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint)
+    heap_lib.construct_heap.restype = C.c_void_p
+    heap_lib.destroy_heap.argtypes = [C.c_void_p]
+    heap_lib.insert.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_uint]
+    heap_lib.insert.restype = C.c_size_t
+    heap_lib.root.argtypes = [C.c_void_p, C.c_void_p, callback_type]
+    heap_lib.root.restype = HeapEntry
+
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        n = 200
+        times = []
+        for _ in range(n):
+            q, r = oracle.time_from_float(float(rng.integers(0, 4)) + float(rng.random()))
+            q, r = oracle.time_add(q, r, float(rng.random()) * 10.0 ** float(rng.integers(-12, 2)))
+            times.append((q, r))
+        times[5] = (times[4][0], np.nextafter(times[4][1], 2.0))   # neighbours in the last bit of the remainder
+        stale = set(int(i) + 1 for i in rng.choice(n, size=n // 4, replace=False))
+        popped = set()
+        callback = callback_type(lambda scheduler, handler, counter: int(handler in stale or handler in popped))
+        heap = heap_lib.construct_heap()
+        try:
+            for index, (q, r) in enumerate(times):
+                assert heap_lib.insert(heap, q, r, index + 1, 0) != C.c_size_t(-1).value
+            order = []
+            while True:
+                entry = heap_lib.root(heap, None, callback)
+                if entry.event_handler is None:
+                    break
+                order.append(entry.event_handler - 1)
+                popped.add(entry.event_handler)
+        finally:
+            heap_lib.destroy_heap(heap)
+        valid = [i for i in range(n) if i + 1 not in stale]
+        assert len(set(times[i] for i in valid)) == len(valid)   # no exact ties: the order is unique
+        compare = lambda a, b: -1 if oracle.time_lt(*times[a], *times[b]) else (1 if oracle.time_lt(*times[b], *times[a]) else 0)
+        assert order == sorted(valid, key=functools.cmp_to_key(compare))
