@@ -11,6 +11,13 @@ for path in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "gol
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the installed copy of the unmodified reference (git-ignored) is what the compiler / mediator tests build their
+    # object graphs with: on a fresh checkout next to the reference checkout, install it before collection
+    try:
+        import runpy
+        runpy.run_path(os.path.join(ROOT, "baseline", "install_ref.py"))["install"]()
+    except Exception as error:  # noqa: BLE001 - those tests then skip and say why
+        sys.stderr.write(f"baseline/_ref not installed: {error}\n")
 
 
 @pytest.fixture(scope="session")
