@@ -497,7 +497,7 @@ EventKernel pick_kernel(const DeviceProgram &d, bool record) {
         return pick_far_pairs<-1, -1, -1>(record);
     }
     // the Lennard-Jones kernels assume chargeless handlers and modular cell translations (FAST in event_kernel)
-    const bool fast = !d.pair_use_charge && !d.veto_use_charge && d.translate_modular && !d.no_cells;
+    const bool fast = !d.pair_use_charge && !d.veto_use_charge && d.translate_modular && !d.no_cells && d.dimension == 3;
     if (fast && cand == LJ && real == 0 && veto == LJ) return pick_record<ECMC_POT_LENNARD_JONES, 0, ECMC_POT_LENNARD_JONES>(record, single);
     if (fast && cand == LJ && real == 0 && veto == 0) return pick_record<ECMC_POT_LENNARD_JONES, 0, 0>(record, single);
     if (cand == HS && real == 0 && veto == 0) return pick_record<ECMC_POT_HARD_SPHERE, 0, 0>(record, false);
@@ -754,6 +754,12 @@ ECMC_API int ecmc_upload_chain_states(EcmcHandle *h, const EcmcChainState *state
             s.active_cell < 0 || s.active_cell >= h->dprog.n_cells || s.eoc_next_active < 0 ||
             s.eoc_next_active >= h->dprog.n_particles)
             return fail(h, ECMC_ERR_INVALID, "chain state " + std::to_string(c) + " out of range");
+        // kept candidates index particles / cells on the device: a corrupt checkpoint must not read out of bounds
+        const int index_limit = std::max(h->dprog.n_particles, h->dprog.n_cells);
+        if (s.pending_kind < ECMC_EVENT_NONE || s.pending_kind > 16 ||
+            (s.pending_kind != ECMC_EVENT_NONE && (s.pending_target < -1 || s.pending_target >= index_limit)) ||
+            s.kept_kind < -1 || s.kept_kind > 16 || (s.kept_kind > 0 && (s.kept_target < -1 || s.kept_target >= index_limit)))
+            return fail(h, ECMC_ERR_INVALID, "chain state " + std::to_string(c) + ": kept candidate out of range");
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaMemcpyAsync(h->state.chains, states, sizeof(EcmcChainState) * h->n_chains, cudaMemcpyHostToDevice, h->stream));

@@ -928,7 +928,7 @@ start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
     }
     __syncwarp();
     if (lane == 0) {
-        EcmcChainState st;
+        EcmcChainState st = {};  // every field defined: the state is downloaded, compared and checkpointed as bytes
         st.active = initial_active; st.direction = initial_direction;
         st.time_q = 0.0; st.time_r = 0.0;
         st.event_counter = 0;

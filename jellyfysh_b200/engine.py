@@ -130,6 +130,7 @@ class Engine:
     def upload_positions(self, positions, charges=None):
         pos = _f64(positions, (self.n_chains, self.n_particles, self.dimension))
         ch = None if charges is None else _f64(charges, (self.n_chains, self.n_particles))
+        self._charges = None if ch is None else ch.copy()  # part of a checkpoint (the device records are never read back)
         self._check(self._lib.ecmc_upload_positions(self._h, _ptr(pos), _ptr(ch)))
         self._check(self._lib.ecmc_sync(self._h, None))  # the host buffers may go away after this call
 
@@ -231,19 +232,30 @@ class Engine:
         arrays = {"positions": self.download_positions(), "chain_states": self.chain_states(), "occupants": occupants,
                   "surplus": padded, "n_surplus": n_surplus,
                   "layout": np.array([self.n_chains, self.n_particles, self.dimension, self.n_cells, self.max_occupants,
-                                      self.max_surplus, self.nodes_per_root], dtype=np.int64)}
+                                      self.max_surplus, self.nodes_per_root], dtype=np.int64),
+                  "fingerprint": np.frombuffer(self._builder.fingerprint(), dtype=np.uint8)}
+        if getattr(self, "_charges", None) is not None:
+            arrays["charges"] = self._charges
         if self.nodes_per_root > 1:
             arrays["roots"] = self.download_roots()
         np.savez_compressed(path, **arrays)
 
     def load_checkpoint(self, path, charges=None):
-        """Restore a state written by save_checkpoint into an engine of the same program and number of chains
-        (charges are part of the start configuration, not of the checkpoint: pass them again if the program uses them)."""
+        """Restore a state written by save_checkpoint into an engine of the same program and number of chains. The
+        checkpoint carries the charges it was started with (`charges` overrides them) and a fingerprint of the program
+        (seed, potentials, cell system, handler kinds): a dump of another program is refused."""
         with np.load(path) as data:
             layout = [self.n_chains, self.n_particles, self.dimension, self.n_cells, self.max_occupants, self.max_surplus,
                       self.nodes_per_root]
             if data["layout"].tolist() != layout:
                 raise ValueError("checkpoint layout {0} does not match this engine {1}".format(data["layout"].tolist(), layout))
+            if "fingerprint" in data and data["fingerprint"].tobytes() != self._builder.fingerprint():
+                raise ValueError("the checkpoint was written by a different program (seed, potentials or handlers differ)")
+            if charges is None and "charges" in data:
+                charges = data["charges"]
+            program = self._builder.program
+            if charges is None and (program.pair_use_charge or program.veto_use_charge):
+                raise ValueError("the program uses charges and the checkpoint holds none: pass charges=")
             self.upload_positions(data["positions"], charges)
             if self.nodes_per_root > 1:
                 self.upload_roots(data["roots"])

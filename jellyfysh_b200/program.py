@@ -40,6 +40,18 @@ class ProgramBuilder:
         self._keep = []
         self.tables = None
 
+    def fingerprint(self) -> bytes:
+        """32 bytes that identify the program (every scalar of the EcmcProgram incl. seed, potentials and handler kinds,
+        plus the far-field tables): stored in checkpoints so that a dump of another program is refused on load."""
+        import hashlib
+        copy = abi.EcmcProgram.from_buffer_copy(bytes(self.program))
+        copy.veto_tables = None  # an address, not content
+        digest = hashlib.sha256(bytes(copy))
+        for array in self._keep:
+            if isinstance(array, np.ndarray):
+                digest.update(array.tobytes())
+        return digest.digest()
+
     @property
     def n_cells(self):
         p = self.program

@@ -578,8 +578,12 @@ def test_checkpoint_resume_is_bit_exact(oracle, tmp_path):
         straight.sync()
         first.run(max_events=500)
         first.save_checkpoint(tmp_path / "water.npz")
+        other, _ = _lj_batch(oracle, n_chains=12, n=100, cells=4, length=5.2, seed=22)  # the same shapes, another seed
+        with engine.Engine(other, n_chains=12) as foreign:
+            with pytest.raises(ValueError):
+                foreign.load_checkpoint(tmp_path / "lj.npz")
         with engine.Engine(wb, n_chains=1) as resumed:
-            resumed.load_checkpoint(tmp_path / "water.npz", charges=charges)
+            resumed.load_checkpoint(tmp_path / "water.npz")  # the charges of the start configuration are in the file
             resumed.run(max_events=700)
             resumed.sync()
             assert np.array_equal(resumed.download_positions(), straight.download_positions())
