@@ -356,6 +356,22 @@ int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_min, doubl
 int ecmc_separation_histogram_subset(EcmcHandle *h, int32_t first, int32_t stride, int32_t n_bins, double r_min,
                                      double r_max, uint64_t *histogram);
 
+/* ---- execution options (no reference counterpart: how the device schedules the same events) ------------------
+ * The Lennard-Jones / cell-veto configurations (chargeless 3D Lennard-Jones pair factors in the nearby cells and the
+ * surplus, Lennard-Jones cell veto, one occupant per cell) are advanced by a kernel that evaluates several successive
+ * events of a chain side by side under the assumption that they are rejected cell vetoes, and commits them up to the
+ * first event that is not (csrc/ecmc_spec.cuh). The committed events -- winner, target, lifting, times, positions --
+ * are those of the one-event-at-a-time loop (single_process_mediator.py:91-156), event for event.
+ *   ECMC_OPTION_BATCHED_EVENTS    1 (default) / 0: fall back to the one-event-at-a-time kernel
+ *   ECMC_OPTION_PRUNE_CANDIDATES  1 (default) / 0: in ecmc_run / ecmc_run_from_host a pair candidate that provably cannot
+ *                                 precede the cell-veto / cell-boundary candidate of its event is not inverted (its
+ *                                 potential change is bounded from below by the uniform it is drawn from, its energy
+ *                                 rise by the largest force on its line). Winners are unchanged; EcmcStats.candidates
+ *                                 then counts the evaluated finite candidates only. ecmc_run_recorded never prunes.
+ *   ECMC_OPTION_LANES_PER_EVENT   4 (default: 8 events per batch) or 8 (4 events per batch) */
+enum EcmcOption { ECMC_OPTION_BATCHED_EVENTS = 1, ECMC_OPTION_PRUNE_CANDIDATES = 2, ECMC_OPTION_LANES_PER_EVENT = 3 };
+int ecmc_set_option(EcmcHandle *h, int option, int value);
+
 /* The CUDA stream the handle launches on (a cudaStream_t), so callers can time with events on it. */
 void *ecmc_stream(EcmcHandle *h);
 /* Seconds of device time (CUDA events on the handle's stream) spent in event kernels since create. */

@@ -12,6 +12,7 @@
 
 #include "ecmc_kernels.cuh"
 #include "ecmc_molecules.cuh"
+#include "ecmc_spec.cuh"
 
 using namespace ecmc;
 
@@ -60,6 +61,9 @@ struct EcmcHandle {
     double kernel_seconds = 0.0;
     uint64_t kernel_launches = 0;
     bool started = false;
+    bool spec = true;        // Lennard-Jones / cell-veto programs: lj_spec_kernel (ecmc_set_option)
+    bool spec_prune = true;  // ... with the force-bound pruning of pair candidates in ecmc_run / ecmc_run_from_host
+    int spec_lanes = 4;      // lanes per speculated event (4: 8 events per batch, 8: 4 events per batch)
     std::string error;
 };
 
@@ -506,6 +510,40 @@ EventKernel pick_kernel(const DeviceProgram &d, bool record) {
     return pick_record<-1, -1, -1>(record, false);
 }
 
+// ---- the Lennard-Jones / cell-veto kernel that evaluates several events side by side (ecmc_spec.cuh) -------------
+struct SpecLaunch {
+    EventKernel kernel = nullptr;
+    size_t shared_bytes = 0;
+    int capacity = 0;
+};
+
+template <bool RECORD, bool PRUNE>
+EventKernel pick_spec_lanes(int lanes) {
+    return lanes == 8 ? lj_spec_kernel<RECORD, PRUNE, 8, kWarpsPerBlock> : lj_spec_kernel<RECORD, PRUNE, 4, kWarpsPerBlock>;
+}
+
+// Chargeless 3D Lennard-Jones pair factors with a Lennard-Jones cell veto, one occupant per cell, modular cell
+// translations, and a candidate list (nearby cells + the longest possible surplus list) that fits the shared memory
+// of a CTA next to its sibling on the SM. Everything else runs event_kernel.
+bool pick_spec(const EcmcHandle *h, bool record, SpecLaunch *out) {
+    const DeviceProgram &d = h->dprog;
+    if (!h->spec || h->molecules || d.nodes_per_root > 1) return false;
+    if (d.dimension != 3 || d.no_cells || !d.translate_modular || d.pair_use_charge || d.veto_use_charge) return false;
+    if (d.max_occupants != 1 || d.pair_handler != ECMC_PAIR_TWO_LEAF_UNIT || d.veto_enabled != ECMC_FAR_CELL_VETO) return false;
+    if (d.cand_potential.kind != ECMC_POT_LENNARD_JONES || d.veto_potential.kind != ECMC_POT_LENNARD_JONES) return false;
+    for (int k = 0; k < 3; k++)
+        if (d.upper[k].n_entries <= 0) return false;
+    const bool prune = h->spec_prune && !record;
+    const int capacity = (d.n_nearby + d.max_surplus + 31) / 32 * 32;
+    const size_t bytes = (size_t)kWarpsPerBlock * capacity * ((prune ? 3 : 2) + 1) * sizeof(double);
+    if (bytes > 100 * 1024) return false;  // two CTAs per SM
+    out->capacity = capacity;
+    out->shared_bytes = bytes;
+    if (record) out->kernel = pick_spec_lanes<true, false>(h->spec_lanes);
+    else out->kernel = prune ? pick_spec_lanes<false, true>(h->spec_lanes) : pick_spec_lanes<false, false>(h->spec_lanes);
+    return true;
+}
+
 int acquire_events(EcmcHandle *h, EventPair *out) {
     if (!h->free_events.empty()) {
         *out = h->free_events.back();
@@ -542,6 +580,7 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
     args.records = d_records;
     args.records_per_chain = records_per_chain;
     args.stats = h->d_stats;
+    args.list_capacity = 0;
     EventPair ev;
     int rc = acquire_events(h, &ev);
     if (rc) return rc;
@@ -578,8 +617,15 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         const int warps = water && aligned ? kAlignedWarps : kMoleculeWarps;
         kernel<<<(h->n_chains + warps - 1) / warps, warps * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
     } else {
-        const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
-        kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
+        SpecLaunch spec;
+        if (pick_spec(h, d_records != nullptr, &spec)) {
+            args.list_capacity = spec.capacity;
+            CUDA_TRY(h, cudaFuncSetAttribute(spec.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec.shared_bytes));
+            spec.kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, h->stream>>>(h->dprog, h->state, args);
+        } else {
+            const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
+            kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
+        }
     }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(ev.stop, h->stream));
@@ -626,6 +672,10 @@ ECMC_API int ecmc_create(const EcmcProgram *program, int device, int n_chains, E
     h->device = device;
     h->n_chains = n_chains;
     h->program = *program;
+    // development switches (A/B measurements); the supported interface is ecmc_set_option
+    if (const char *env = std::getenv("ECMC_SPEC")) h->spec = std::atoi(env) != 0;
+    if (const char *env = std::getenv("ECMC_SPEC_PRUNE")) h->spec_prune = std::atoi(env) != 0;
+    if (const char *env = std::getenv("ECMC_SPEC_LANES")) h->spec_lanes = std::atoi(env) == 8 ? 8 : 4;
     int rc = ECMC_OK;
     do {
         if ((err = cudaSetDevice(device)) != cudaSuccess) { rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
@@ -876,7 +926,14 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
     args.records = nullptr;
     args.records_per_chain = 0;
     args.stats = h->d_stats;
-    const EventKernel kernel = pick_kernel(d, false);
+    args.list_capacity = 0;
+    EventKernel kernel = pick_kernel(d, false);
+    SpecLaunch spec;
+    if (pick_spec(h, false, &spec)) {
+        kernel = spec.kernel;
+        args.list_capacity = spec.capacity;
+        CUDA_TRY(h, cudaFuncSetAttribute(spec.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec.shared_bytes));
+    }
     const size_t per_chain = (size_t)d.n_particles;
     const int base = h->n_chains / slices, extra = h->n_chains % slices;
     int first = 0;
@@ -899,7 +956,7 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
         const int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, s>>>(
             d, slice, nullptr, first_stream, h->program.initial_active, h->program.initial_direction, h->d_stats);
-        kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(d, slice, args);
+        kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, s>>>(d, slice, args);
         CUDA_TRY(h, cudaGetLastError());
         h->kernel_launches++;
         if (positions_out) {
@@ -950,6 +1007,19 @@ ECMC_API int ecmc_separation_histogram_subset(EcmcHandle *h, int32_t first, int3
     } while (0);
     cudaFree(d_histogram);
     return rc;
+}
+
+ECMC_API int ecmc_set_option(EcmcHandle *h, int option, int value) {
+    if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
+    switch (option) {
+    case ECMC_OPTION_BATCHED_EVENTS: h->spec = value != 0; return ECMC_OK;
+    case ECMC_OPTION_PRUNE_CANDIDATES: h->spec_prune = value != 0; return ECMC_OK;
+    case ECMC_OPTION_LANES_PER_EVENT:
+        if (value != 4 && value != 8) return fail(h, ECMC_ERR_INVALID, "lanes per event: 4 or 8");
+        h->spec_lanes = value;
+        return ECMC_OK;
+    default: return fail(h, ECMC_ERR_INVALID, "unknown option " + std::to_string(option));
+    }
 }
 
 ECMC_API void *ecmc_stream(EcmcHandle *h) { return h ? (void *)h->stream : nullptr; }

@@ -202,6 +202,8 @@ struct LennardJones {
     double r0sq;     // squared position of the minimum, 2^(1/3) sigma^2
     double four_over_k;
     double u_min;    // -k / 4
+    double r_inflection_sq;  // squared distance of the largest attractive force, (26/7)^(1/3) sigma^2
+    double force_max;        // that force, |U'| at the inflection point
 };
 ECMC_HD LennardJones make_lennard_jones(double prefactor, double characteristic_length) {
     LennardJones p;
@@ -211,6 +213,8 @@ ECMC_HD LennardJones make_lennard_jones(double prefactor, double characteristic_
     p.r0sq = 1.2599210498948731648 * p.sigma2;  // 2^(1/3)
     p.four_over_k = 4.0 / prefactor;
     p.u_min = -0.25 * prefactor;
+    p.r_inflection_sq = pow(26.0 / 7.0, 1.0 / 3.0) * p.sigma2;
+    p.force_max = prefactor / characteristic_length * (6.0 * pow(7.0 / 26.0, 7.0 / 6.0) - 12.0 * pow(7.0 / 26.0, 13.0 / 6.0));
     return p;
 }
 // U(r^2) = k [(s/r)^12 - (s/r)^6] (lennard_jones_potential.py:83-98) as k x3 (x3 - 1), x3 = (s^2/r^2)^3

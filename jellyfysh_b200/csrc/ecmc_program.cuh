@@ -97,6 +97,7 @@ struct RunArgs {
     EcmcEventRecord *records;
     int records_per_chain;
     EcmcStats *stats;
+    int list_capacity;      // lj_spec_kernel: entries of the per-chain candidate list in shared memory
 };
 
 }  // namespace ecmc

@@ -1,0 +1,542 @@
+// ecmc_spec.cuh -- the Lennard-Jones / cell-veto event kernel (workloads C2 and C5): one warp advances one Markov
+// chain, W = 32 / G events at a time.
+//
+// Nine events out of ten of this configuration are REJECTED CELL VETOES: the cell-veto candidate
+// (CellVetoEventHandler.send_event_time, cell_veto_event_handler.py:200-238) is the earliest, its target cell is empty
+// or its confirmation fails (leaf_unit_cell_veto_event_handler.py:117-149), and nothing changes but the position of the
+// active particle along its line and the time. The veto candidate of event k (Walker cell, bound, time increment) is a
+// function of the random stream, the event index and the direction only -- not of any position. So the kernel assumes
+// that the next W events are rejected vetoes: under that assumption the time and the position of the active particle
+// before each of them follow from the veto increments alone (the same additions the one-event-at-a-time loop performs,
+// in the same order), and the W events can be evaluated side by side:
+//
+//   lane = e * G + g      event e of the batch, share g of its work
+//   g = 0 draws the veto (uniform, time), g = 1 the Walker table index, g = 2 the confirmation number
+//   every lane walks over its share of the candidate list (entries g, g + G, ...) for ITS event: separation along the
+//   line of motion from the position before event e, potential change keyed by (event, target), Lennard-Jones
+//   inversion, running minimum on (time, sequence number) -- the scheduler's order (heap.c:176-178) --, then G lanes
+//   combine by log2(G) shuffle steps
+//   the lane g = 0 compares with the veto, the cell boundary and the end of chain, and -- if the veto won -- looks up
+//   the occupant of the target cell and confirms against the real derivative
+//
+// The first event that is NOT a plain rejected veto (a pair event, an accepted veto, a cell boundary, the end of the
+// chain, a time limit, or a time slice that left the cell) ends the batch: the events before it are committed in one
+// step, that event itself goes through the general out-state code (the same as event_kernel's), and everything after
+// it was computed from a wrong assumption and is thrown away. With 9 % breaking events, W = 8 commits 6.1 events per
+// batch on average; the work thrown away is the price for (a) no per-event warp argmin, gather, loop and commit
+// overhead, (b) lanes that never diverge between candidate kinds, (c) W independent dependent-load chains (Walker
+// entry -> occupant -> particle) in flight at once instead of one per event.
+//
+// The candidate list (occupants of the 27 nearby cells + surplus) lives in shared memory together with, per target, the
+// coordinate along the line of motion and the squared distance from that line -- which only change when the list
+// does -- and is rebuilt after every event that changes the active particle, its cell or the direction.
+//
+// PRUNE (ecmc_run; never with event records): a pair candidate is only inverted if it can fire before the earliest
+// of (veto, boundary) of its event. The potential change it draws is at least u / beta (-log(1 - u) >= u), and the
+// energy cannot rise faster than max |dU/dr| over the part of the potential the line of motion can reach, a number
+// that depends on the target's distance from the line only and is stored with the list. One multiplication and one
+// comparison decide; everything within rounding distance of the threshold is computed in full. The winner of every
+// event is unchanged (tests/test_gpu_spec.py), only EcmcStats.candidates then counts the evaluated candidates.
+#pragma once
+
+#include "ecmc_kernels.cuh"
+
+namespace ecmc {
+
+// Upper bound of |dU/dx| of the Lennard-Jones pair energy on a straight line at squared distance perp2 from the
+// target: |dU/dx| = |sd| / r |U'(r)| <= sup over r >= sqrt(perp2) of |U'(r)|. |U'| falls with r on the repulsive side
+// and peaks at r = (26/7)^(1/6) sigma on the attractive side.
+ECMC_D double lj_force_bound(const LennardJones &p, double perp2) {
+    if (!(perp2 > 0.0)) return INFINITY;
+    const double inv = 1.0 / perp2;
+    const double x = p.sigma2 * inv;
+    const double x3 = x * x * x;
+    const double here = p.k * x3 * fabs(fma(12.0, x3, -6.0)) * sqrt(inv);
+    const double bound = perp2 < p.r_inflection_sq ? fmax(here, p.force_max) : here;
+    return bound * (1.0 + 1.0e-9);
+}
+
+// key of a candidate time in the scheduler's order: see time_key (a rounding-negative x sorts first)
+ECMC_D double time_order(double x) { return x > 0.0 ? x : 0.0; }
+
+template <bool RECORD, bool PRUNE, int G, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
+lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
+    static_assert(G == 4 || G == 8, "lanes per event");
+    constexpr int W = 32 / G;
+    constexpr int kDoubles = PRUNE ? 3 : 2;
+    extern __shared__ double spec_shared[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int chain = S.first_chain + blockIdx.x * WARPS + warp;
+    if (chain >= S.first_chain + S.n_chains) return;
+    // the candidate list of this chain: coordinate along the line of motion, squared distance from it, (force bound),
+    // target particle, sequence number (= slot in the scan order of the reference's taggers)
+    const int cap = A.list_capacity;
+    double *l_p0 = spec_shared + (size_t)warp * cap * (kDoubles + 1);
+    double *l_perp2 = l_p0 + cap;
+    double *l_bound = l_p0 + 2 * cap;  // PRUNE only
+    int *l_target = reinterpret_cast<int *>(l_p0 + kDoubles * cap);
+    int *l_seq = l_target + cap;
+    int count = -1;  // entries of the valid list; -1: rebuild
+
+    const LennardJones &lj = P.cand_potential.lj;
+    Particle *part = S.particles + (size_t)chain * P.n_particles;
+    int *occ = S.occupants + (size_t)chain * P.n_cells;
+    int *sur = S.surplus + (size_t)chain * P.max_surplus;
+    EcmcChainState *stp = S.chains + chain;
+
+    // chain state -> registers (uniform over the warp)
+    int active = stp->active, dir = stp->direction;
+    Time now = {stp->time_q, stp->time_r};
+    Time eoc = {stp->eoc_q, stp->eoc_r};
+    int eoc_next = stp->eoc_next_active;
+    int active_cell = stp->active_cell;
+    unsigned long long ev = stp->event_counter;
+    const uint32_t stream = stp->stream;
+    bool was_pending = stp->pending_kind != ECMC_EVENT_NONE;
+    int n_surplus = S.n_surplus[chain];
+    Moving a = rotate_in(part[active], dir);
+    int cid0 = (active_cell / P.cumulative[0]) % P.per_side[0];
+    int cid1 = (active_cell / P.cumulative[1]) % P.per_side[1];
+    int cid2 = (active_cell / P.cumulative[2]) % P.per_side[2];
+    int next_cell = 0;
+    auto next_boundary = [&]() {
+        const int id = dir == 0 ? cid0 : (dir == 1 ? cid1 : cid2);
+        const int nid = id + 1 == P.per_side[dir] ? 0 : id + 1;
+        next_cell = active_cell + (nid - id) * P.cumulative[dir];
+        return __ldg(P.cell_min_axis + dir * P.max_per_side + nid);
+    };
+    double boundary = next_boundary();
+
+    const Time until = {A.until_q, A.until_r};
+    const double L = P.length, half = P.half_length, speed = P.speed;
+    const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
+    const int e = lane / G, g = lane % G, leader = lane - g;
+
+    Counters n = {0, 0, 0ull, 0ull};
+    bool stopped_by_time = false;
+
+    while (n.events < max_events) {
+        // the interaction winner of the event that goes through the general out-state code
+        Time bt = time_inf();
+        int bkind = ECMC_EVENT_NONE, btarget = -1, bcell = -1;
+        double brate = 0.0;
+        int n_cand = 0;
+        double u_confirmation = 0.0;
+        double kept_position = 0.0;
+        Time kept_stamp = now;
+        if (was_pending) {
+            // a candidate that survived a host control event: nothing is recomputed, no draws are consumed
+            bkind = stp->pending_kind;
+            bt.q = stp->pending_q; bt.r = stp->pending_r;
+            brate = stp->pending_rate;
+            if (bkind == ECMC_EVENT_PAIR) btarget = stp->pending_target; else bcell = stp->pending_target;
+            kept_position = stp->pending_position;
+            kept_stamp.q = stp->pending_stamp_q; kept_stamp.r = stp->pending_stamp_r;
+            u_confirmation = stream_double({P.seed, stream, ev}, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+        } else {
+            if (count < 0) {
+                // ---- rebuild the candidate list: occupants of the nearby cells (ExcludedCellsTagger,
+                // excluded_cells_tagger.py:129-132), then the surplus (SurplusCellsTagger, :129-131)
+                const int n_slots = P.n_nearby + n_surplus;
+                int found_so_far = 0;
+                for (int cursor = 0; cursor < n_slots; cursor += 32) {
+                    const int s = cursor + lane;
+                    int found = -1;
+                    if (s < P.n_nearby) {
+                        const int code = __ldg(P.nearby + s);
+                        int x = cid0 + (code & 1023), y = cid1 + ((code >> 10) & 1023), z = cid2 + (code >> 20);
+                        if (x >= P.per_side[0]) x -= P.per_side[0];
+                        if (y >= P.per_side[1]) y -= P.per_side[1];
+                        if (z >= P.per_side[2]) z -= P.per_side[2];
+                        found = occ[x * P.cumulative[0] + y * P.cumulative[1] + z * P.cumulative[2]];
+                    } else if (s < n_slots) {
+                        found = sur[s - P.n_nearby];
+                    }
+                    const unsigned occupied = __ballot_sync(kFull, found >= 0);
+                    if (found >= 0) {
+                        const int rank = found_so_far + __popc(occupied & ((1u << lane) - 1u));
+                        l_target[rank] = found;
+                        l_seq[rank] = s;
+                    }
+                    found_so_far += __popc(occupied);
+                }
+                __syncwarp();
+                for (int base = 0; base < found_so_far; base += 32) {
+                    const int i = base + lane;
+                    if (i < found_so_far) {
+                        const Moving tp = rotate_in(part[l_target[i]], dir);
+                        const double s1 = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                        const double s2 = correct_separation_in_box(tp.p2 - a.p2, L, half);
+                        const double perp2 = fma(s1, s1, s2 * s2);
+                        l_p0[i] = tp.p0;
+                        l_perp2[i] = perp2;
+                        if (PRUNE) l_bound[i] = lj_force_bound(lj, perp2);
+                    }
+                }
+                __syncwarp();
+                count = found_so_far;
+            }
+
+            // ---- W events side by side ---------------------------------------------------------------------
+            const int w_eff = (int)min((unsigned)W, max_events - n.events);
+            const StreamKey key = {P.seed, stream, ev + (unsigned long long)e};
+            const uint32_t special_slot = g == 0 ? ECMC_SLOT(ECMC_SLOT_VETO_TIME, 0)
+                                                 : (g == 1 ? ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0) : ECMC_SLOT(ECMC_SLOT_CONFIRM, 0));
+            const Philox4 b = stream_block(key, special_slot, 0);
+            const double u_first = words_to_double(b.w[0], b.w[1]), u_second = words_to_double(b.w[2], b.w[3]);
+            const DeviceWalker *w = &P.upper[dir];  // chargeless handlers: the charge factor is 1 > 0
+            // random.choice(table) = table[_randbelow(n)]: rejection on the top bits of successive words (lane g = 1)
+            uint32_t choice = 0;
+            {
+                bool found = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t r = b.w[j] >> (32 - w->bits);
+                    if (!found && r < (uint32_t)w->n_entries) { choice = r; found = true; }
+                }
+                if (g == 1)
+                    for (uint32_t block = 1; !found; block++) {
+                        const Philox4 more = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0), block);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t r = more.w[j] >> (32 - w->bits);
+                            if (!found && r < (uint32_t)w->n_entries) { choice = r; found = true; }
+                        }
+                    }
+            }
+            choice = __shfl_sync(kFull, choice, leader + 1);
+            const double u_conf = __shfl_sync(kFull, u_first, leader + 2);
+            // the veto candidate of event e (meaningful on the leaders): Walker.sample_cell (walker.py:114-118),
+            // expovariate(beta) / (total rate * speed)
+            const WalkerEntry entry = w->entries[choice];
+            const bool first_cell = 0.0 + (w->mean_rate - 0.0) * u_first <= entry.rate_a;
+            const int relative = first_cell ? entry.cell_a : entry.cell_b;
+            const double veto_rate = first_cell ? entry.bound_a : entry.bound_b;
+            const double veto_dt = -log_unit_interval(1.0 - u_second) * P.inv_beta * w->inv_total_rate_speed;
+
+            // time and position before every event of the batch if all earlier ones are rejected vetoes: the additions
+            // of Time.__add__ (time.py:115-133) and of the time slice (abstracts.py:82-95), one event after the other
+            Time my_now = now, my_veto_time = now;
+            double my_x = a.p0, my_next_x = a.p0, my_veto_dt = 0.0;
+            bool my_left = false;
+            Time end_now = now;
+            double end_x = a.p0;
+            {
+                Time t = now;
+                double x = a.p0;
+#pragma unroll
+                for (int k = 0; k < W; k++) {
+                    const double dtv = __shfl_sync(kFull, veto_dt, k * G);
+                    const double xr = t.r + dtv;
+                    const double fl = floor(xr);
+                    Time t_next;
+                    t_next.q = t.q + fl; t_next.r = xr - fl;
+                    const double dt = time_sub(t_next, t);
+                    const double x_next = correct_position_entry(__dadd_rn(x, __dmul_rn(speed, dt)), L);
+                    const bool left = boundary == 0.0 ? x_next < x : x_next >= boundary;
+                    if (e == k) {
+                        my_now = t; my_x = x; my_next_x = x_next; my_left = left; my_veto_dt = dtv; my_veto_time = t_next;
+                    }
+                    t = t_next;
+                    x = x_next;
+                }
+                end_now = t;
+                end_x = x;
+            }
+            // special candidates of event e
+            const double xv = my_now.r + my_veto_dt;
+            double boundary_separation = boundary - my_x;
+            if (boundary_separation < 0.0) boundary_separation = boundary_separation + L;  // next_image, hypercubic_setting.py:191
+            const double xb = my_now.r + boundary_separation * P.inv_speed;
+            // PRUNE: no pair candidate beyond this displacement can be the interaction winner of event e
+            const double reach = PRUNE ? fma(speed * (fmin(xv, xb) - my_now.r), 1.0 + 1.0e-9, 1.0e-12) : 0.0;
+
+            // ---- pair candidates of event e: entries g, g + G, ... of the list
+            double best_x = INFINITY;
+            int best_seq = kSeqNone, best_target = -1, n_finite = 0;
+            for (int base = 0; base < count; base += G) {
+                const int i = base + g;
+                const bool valid = i < count;
+                const int target = valid ? l_target[i] : 0;
+                const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target), 0);
+                const double u = words_to_double(pb.w[0], pb.w[1]);
+                bool evaluate = valid;
+                if (PRUNE) evaluate = valid && !(l_bound[i] * reach < u * P.inv_beta * (1.0 - 1.0e-9));
+                if (PRUNE && !__any_sync(kFull, evaluate)) continue;
+                const double s0 = correct_separation_in_box((valid ? l_p0[i] : 0.0) - my_x, L, half);
+                const double perp2 = valid ? l_perp2[i] : 1.0;
+                const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                const double x = my_now.r + lj_displacement(lj, s0, perp2, du) * P.inv_speed;
+                if (evaluate && x < INFINITY) {  // heap_scheduler.py:139; NaN never wins
+                    n_finite++;
+                    const int seq = l_seq[i];
+                    const double kx = time_order(x), kb = time_order(best_x);
+                    if (kx < kb || (kx == kb && seq < best_seq)) { best_x = x; best_seq = seq; best_target = target; }
+                }
+            }
+            // combine the G shares of an event
+#pragma unroll
+            for (int offset = 1; offset < G; offset <<= 1) {
+                const double ox = __shfl_xor_sync(kFull, best_x, offset);
+                const int oseq = __shfl_xor_sync(kFull, best_seq, offset);
+                const int otarget = __shfl_xor_sync(kFull, best_target, offset);
+                n_finite += __shfl_xor_sync(kFull, n_finite, offset);
+                const double ko = time_order(ox), kb = time_order(best_x);
+                if (ko < kb || (ko == kb && oseq < best_seq)) { best_x = ox; best_seq = oseq; best_target = otarget; }
+            }
+
+            // ---- the winner of event e, on the leader lanes
+            int my_kind = best_seq != kSeqNone ? ECMC_EVENT_PAIR : ECMC_EVENT_NONE;
+            int my_cell = -1, my_target = best_target, my_occupant = -1;
+            double my_best = best_x;
+            bool plain = false, violation = false;
+            int my_candidates = n_finite;
+            if (g == 0 && e < w_eff) {
+                // sequence numbers: pair slots in scan order, then veto, then boundary
+                if (xv < INFINITY) {
+                    my_candidates++;
+                    if (time_order(xv) < time_order(my_best) || my_kind == ECMC_EVENT_NONE) { my_best = xv; my_kind = ECMC_EVENT_CELL_VETO; }
+                }
+                if (xb < INFINITY) {
+                    my_candidates++;
+                    if (time_order(xb) < time_order(my_best) || my_kind == ECMC_EVENT_NONE) { my_best = xb; my_kind = ECMC_EVENT_CELL_BOUNDARY; }
+                }
+                const double fl = floor(my_best);
+                Time t_event;
+                t_event.q = my_now.q + fl; t_event.r = my_best - fl;
+                const bool wins = my_kind == ECMC_EVENT_CELL_VETO && !time_lt(eoc, t_event) && time_lt(t_event, until);
+                if (my_kind == ECMC_EVENT_CELL_VETO) {
+                    // translate(active cell, relative cell), per axis (cuboid_periodic_cells.py:182-207; modular)
+                    int tx = cid0 + (relative & 1023), ty = cid1 + ((relative >> 10) & 1023), tz = cid2 + (relative >> 20);
+                    if (tx >= P.per_side[0]) tx -= P.per_side[0];
+                    if (ty >= P.per_side[1]) ty -= P.per_side[1];
+                    if (tz >= P.per_side[2]) tz -= P.per_side[2];
+                    my_cell = tx * P.cumulative[0] + ty * P.cumulative[1] + tz * P.cumulative[2];
+                    my_target = -1;
+                } else if (my_kind == ECMC_EVENT_CELL_BOUNDARY) {
+                    my_cell = next_cell;
+                    my_target = -1;
+                }
+                if (wins) {
+                    // mediator.py:265-292 + leaf_unit_cell_veto_event_handler.py:117-149, at the position after the time slice
+                    bool accepted = false;
+                    my_occupant = occ[my_cell];
+                    if (my_occupant >= 0) {
+                        const Moving tp = rotate_in(part[my_occupant], dir);
+                        const double sx = correct_separation_in_box(tp.p0 - my_next_x, L, half);
+                        const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                        const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
+                        const double real = lj_derivative(P.veto_potential.lj, sx, fma(sy, sy, sz * sz)) * speed;
+                        if (real > 0.0) {
+                            violation = veto_rate < real;
+                            accepted = 0.0 + (veto_rate - 0.0) * u_conf < real;
+                        }
+                    }
+                    plain = !accepted && !my_left;
+                }
+            }
+            const unsigned breaking = __ballot_sync(kFull, g == 0 && !plain);
+            // events 0 .. e_star - 1 are plain rejected vetoes
+            const int e_star = breaking ? min(w_eff, (__ffs(breaking) - 1) / G) : w_eff;
+
+            // ---- commit them
+            if (e_star > 0) {
+                const bool mine = g == 0 && e < e_star;
+                if (RECORD && mine && (int)(n.events + e) < A.records_per_chain) {
+                    EcmcEventRecord rec;
+                    rec.kind = ECMC_EVENT_CELL_VETO; rec.target = my_occupant; rec.target_cell = my_cell;
+                    rec.accepted = 0; rec.n_candidates = my_candidates + 1;
+                    rec.new_active = active; rec.new_direction = dir; rec.reserved = 0;
+                    rec.time_q = my_veto_time.q; rec.time_r = my_veto_time.r;
+                    Moving after = a;
+                    after.p0 = my_next_x;
+                    const Particle lab = rotate_out(after, dir);
+                    rec.active_pos[0] = lab.x; rec.active_pos[1] = lab.y; rec.active_pos[2] = lab.z;
+                    A.records[(size_t)chain * A.records_per_chain + n.events + e] = rec;
+                }
+                n.candidates += (unsigned long long)(__reduce_add_sync(kFull, mine ? my_candidates + 1 : 0));
+                const unsigned violations = __ballot_sync(kFull, mine && violation);
+                if (violations && lane == 0 && A.stats)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(A.stats) + 7, (unsigned long long)__popc(violations));
+                n.targets += (unsigned long long)e_star * (unsigned long long)count;
+                n.events += (unsigned)e_star;
+                n.veto += (unsigned)e_star;
+                ev += (unsigned long long)e_star;
+                if (e_star < W) {
+                    now.q = __shfl_sync(kFull, my_now.q, e_star * G);
+                    now.r = __shfl_sync(kFull, my_now.r, e_star * G);
+                    a.p0 = __shfl_sync(kFull, my_x, e_star * G);
+                } else {
+                    now = end_now;
+                    a.p0 = end_x;
+                }
+            }
+            if (e_star >= w_eff) continue;  // the event limit, or a whole batch of rejected vetoes
+            // ---- event e_star goes through the general out-state code below
+            const int source = e_star * G;
+            bkind = __shfl_sync(kFull, my_kind, source);
+            btarget = __shfl_sync(kFull, my_target, source);
+            bcell = __shfl_sync(kFull, my_cell, source);
+            brate = bkind == ECMC_EVENT_CELL_VETO ? __shfl_sync(kFull, veto_rate, source) : 0.0;  // stored by the veto handler only
+            n_cand = __shfl_sync(kFull, my_candidates, source);
+            u_confirmation = __shfl_sync(kFull, u_conf, source);
+            const double x_star = __shfl_sync(kFull, my_best, source);
+            if (bkind != ECMC_EVENT_NONE) {
+                const double fl = floor(x_star);
+                bt.q = now.q + fl; bt.r = x_star - fl;
+            }
+            n.targets += (unsigned long long)count;
+        }
+
+        // ================= one event, general: the tail of event_kernel for this configuration =================
+        n_cand++;  // the end-of-chain candidate lives in the scheduler since the chain started
+        const bool eoc_first = time_lt(eoc, bt);
+        const Time event_time = eoc_first ? eoc : bt;
+        const int kind = eoc_first ? ECMC_EVENT_END_OF_CHAIN : bkind;
+        if (!time_lt(event_time, until)) {
+            // a host control event comes first: the interaction winner stays scheduled
+            if (lane == 0) {
+                stp->pending_kind = bkind;
+                stp->pending_q = bt.q; stp->pending_r = bt.r;
+                stp->pending_rate = brate;
+                stp->pending_target = bkind == ECMC_EVENT_PAIR ? btarget : bcell;
+                if (!was_pending) {
+                    stp->pending_position = a.p0;
+                    stp->pending_stamp_q = now.q; stp->pending_stamp_r = now.r;
+                }
+            }
+            stopped_by_time = true;
+            break;
+        }
+        if (was_pending) {
+            if (lane == 0) stp->pending_kind = ECMC_EVENT_NONE;
+            if (kind != ECMC_EVENT_END_OF_CHAIN) {
+                a.p0 = kept_position;  // the kept handler's in-state predates the control event's time slice
+                now = kept_stamp;
+            }
+            was_pending = false;
+        }
+        // time slice of the active particle (event_handler/abstracts/abstracts.py:82-95)
+        const double x_before = a.p0;
+        a.p0 = correct_position_entry(__dadd_rn(x_before, __dmul_rn(speed, time_sub(event_time, now))), L);
+        now = event_time;
+        const bool left_cell = boundary == 0.0 ? a.p0 < x_before : a.p0 >= boundary;
+        int new_active = active, accepted = 0, rec_target = -1;
+        switch (kind) {
+        case ECMC_EVENT_PAIR:  // two_leaf_unit_event_handler.py:140-154
+            rec_target = btarget;
+            accepted = 1;
+            new_active = btarget;
+            count_rare(A, lane, 1);
+            break;
+        case ECMC_EVENT_CELL_VETO: {
+            const int t = occ[bcell];
+            rec_target = t;
+            if (t >= 0) {
+                const Moving tp = rotate_in(part[t], dir);
+                const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
+                const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
+                const double real = lj_derivative(P.veto_potential.lj, sx, fma(sy, sy, sz * sz)) * speed;
+                if (real > 0.0) {
+                    if (brate < real) count_rare(A, lane, 7);
+                    if (0.0 + (brate - 0.0) * u_confirmation < real) { accepted = 1; new_active = t; }
+                }
+            }
+            n.veto++;
+            if (accepted) count_rare(A, lane, 3);
+            break;
+        }
+        case ECMC_EVENT_CELL_BOUNDARY:  // lands exactly on the lower boundary of the new cell (cell_boundary_event_handler.py:158-173)
+            count_rare(A, lane, 4);
+            a.p0 = boundary;
+            break;
+        case ECMC_EVENT_END_OF_CHAIN:  // abstracts/end_of_chain_event_handler.py:107-187, new direction = (d + 1) mod D
+            new_active = eoc_next;
+            rec_target = new_active;
+            accepted = 1;
+            count_rare(A, lane, 5);
+            break;
+        default: break;
+        }
+        if (RECORD && lane == 0 && (int)n.events < A.records_per_chain) {
+            EcmcEventRecord rec;
+            rec.kind = kind; rec.target = rec_target; rec.target_cell = kind == ECMC_EVENT_END_OF_CHAIN ? -1 : bcell;
+            rec.accepted = accepted; rec.n_candidates = n_cand;
+            rec.new_active = new_active;
+            rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % 3 : dir;
+            rec.reserved = 0;
+            rec.time_q = event_time.q; rec.time_r = event_time.r;
+            const Particle lab = rotate_out(a, dir);
+            rec.active_pos[0] = lab.x; rec.active_pos[1] = lab.y; rec.active_pos[2] = lab.z;
+            A.records[(size_t)chain * A.records_per_chain + n.events] = rec;
+        }
+        ev++;
+        n.events++;
+        n.candidates += (unsigned long long)n_cand;
+        const bool moved_on = new_active != active || kind == ECMC_EVENT_CELL_BOUNDARY || kind == ECMC_EVENT_END_OF_CHAIN || left_cell;
+        if (moved_on) {
+            count = -1;  // the candidate list belongs to the old active particle / cell / direction
+            Particle lab = rotate_out(a, dir);
+            if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir == 2 ? 0 : dir + 1;
+            // SingleActiveCellOccupancy.update (single_active_cell_occupancy.py:149-203)
+            const bool handed_over = new_active != active;
+            if (handed_over) {
+                int delta = 0;
+                if (lane == 0) {
+                    store_position(part + active, lab);
+                    delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, active_cell, active);
+                }
+                delta = __shfl_sync(kFull, delta, 0);
+                if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+                __syncwarp();
+                active = new_active;
+                lab = part[active];
+            }
+            // the oracle recomputes the cell from the position after every event; only these events can change it
+            a = rotate_in(lab, dir);
+            cell_identifier_of(P, lab, cid0, cid1, cid2);
+            active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
+            if (handed_over) {
+                int delta = 0;
+                if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, 1, active_cell, active);
+                delta = __shfl_sync(kFull, delta, 0);
+                if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+                __syncwarp();
+            }
+            boundary = next_boundary();
+        }
+        if (kind == ECMC_EVENT_END_OF_CHAIN) {
+            // the next end-of-chain candidate: chain_time after this one, new active by randint
+            // (single_independent_active_periodic_direction_end_of_chain_event_handler.py:203-237)
+            eoc = time_add(now, time_sub(now, now) + P.chain_time);
+            eoc_next = (int)stream_randbelow({P.seed, stream, ev}, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)P.n_particles);
+        }
+    }
+
+    if (stopped_by_time) {
+        // the sampling / end-of-run handler time-slices the active unit (fixed_interval_sampling_event_handler.py:96-109)
+        a.p0 = correct_position_entry(__dadd_rn(a.p0, __dmul_rn(speed, time_sub(until, now))), L);
+        now = until;
+    }
+    if (lane == 0) {
+        store_position(part + active, rotate_out(a, dir));
+        stp->active = active; stp->direction = dir;
+        stp->time_q = now.q; stp->time_r = now.r;
+        stp->eoc_q = eoc.q; stp->eoc_r = eoc.r;
+        stp->eoc_next_active = eoc_next; stp->active_cell = active_cell;
+        stp->event_counter = ev;
+        S.n_surplus[chain] = n_surplus;
+        if (A.stats) {
+            unsigned long long *st = reinterpret_cast<unsigned long long *>(A.stats);
+            if (n.events) atomicAdd(st + 0, (unsigned long long)n.events);
+            if (n.veto) atomicAdd(st + 2, (unsigned long long)n.veto);
+            if (n.candidates) atomicAdd(st + 6, n.candidates);
+            if (n.targets) atomicAdd(st + 11, n.targets);
+        }
+    }
+}
+
+}  // namespace ecmc

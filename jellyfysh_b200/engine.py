@@ -60,6 +60,7 @@ def library() -> C.CDLL:
     lib.ecmc_run_from_host.argtypes = [vp, vp, vp, u32, d, d, i64, vp, stats]
     lib.ecmc_separation_histogram.argtypes = [vp, i32, d, d, vp]
     lib.ecmc_separation_histogram_subset.argtypes = [vp, i32, i32, i32, d, d, vp]
+    lib.ecmc_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.ecmc_stream.argtypes = [vp]
     lib.ecmc_stream.restype = vp
     lib.ecmc_kernel_seconds.argtypes = [vp]
@@ -179,6 +180,12 @@ class Engine:
             n[c] = len(items)
             sur[c, :len(items)] = items
         self._check(self._lib.ecmc_upload_cells(self._h, _ptr(occ), _ptr(sur), _ptr(n)))
+
+    OPTION_BATCHED_EVENTS, OPTION_PRUNE_CANDIDATES, OPTION_LANES_PER_EVENT = 1, 2, 3
+
+    def set_option(self, option, value):
+        """ecmc_set_option: how the device schedules the events (batched speculative evaluation, candidate pruning)."""
+        self._check(self._lib.ecmc_set_option(self._h, int(option), int(value)))
 
     # ---- the hot path ----------------------------------------------------------------------------------
     def run(self, until=(INF, INF), max_events=0):

@@ -84,8 +84,24 @@ def test_c2_bench_program_event_parity(oracle):
         _compare_stretch(oracle, builder, eng, sample, 2000, None, length, "C2 after 24k events")
         eng.run(max_events=34000)
         eng.sync()
-        longest = _compare_stretch(oracle, builder, eng, sample, 2000, None, length, "C2 after 60k events")
-        assert longest > 14  # more than 30 gathered targets: the candidate list no longer fits one pass of lanes
+        _compare_stretch(oracle, builder, eng, sample, 2000, None, length, "C2 after 60k events")
+
+
+def test_c2_long_run_event_parity(oracle):
+    """The same program with room for 192 surplus particles, 1.5 x 10^5 events per chain on the device alone, then 2000
+    events against the oracle: the reference never promotes a surplus particle into a freed cell
+    (single_active_cell_occupancy.py:186-193), so by then the candidate list holds many more targets than the 27
+    nearby cells."""
+    n_chains, n, cells = 1024, 1024, 12
+    builder, length = workloads.lennard_jones(n_particles=n, cells_per_side=cells, max_surplus=192)
+    start = workloads.lattice_start(n_chains, n, cells, length)
+    with engine.Engine(builder, n_chains=n_chains) as eng:
+        eng.upload_positions(start)
+        eng.start(first_stream=9000)
+        eng.run(max_events=150000)
+        eng.sync()
+        longest = _compare_stretch(oracle, builder, eng, (0, 1, 500, 1023), 2000, None, length, "C2 after 1.5e5 events")
+        assert longest > 30  # more gathered targets than one pass of 32 lanes holds
 
 
 def test_c2_crowded_cells_event_parity(oracle):
