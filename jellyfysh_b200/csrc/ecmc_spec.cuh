@@ -32,11 +32,13 @@
 // does -- and is rebuilt after every event that changes the active particle, its cell or the direction.
 //
 // PRUNE (ecmc_run; never with event records): a pair candidate is only inverted if it can fire before the earliest
-// of (veto, boundary) of its event. The potential change it draws is at least u / beta (-log(1 - u) >= u), and the
-// energy cannot rise faster than max |dU/dr| over the part of the potential the line of motion can reach, a number
-// that depends on the target's distance from the line only and is stored with the list. One multiplication and one
-// comparison decide; everything within rounding distance of the threshold is computed in full. The winner of every
-// event is unchanged (tests/test_gpu_spec.py), only EcmcStats.candidates then counts the evaluated candidates.
+// of (veto, boundary) of its event. The potential change it draws is at least u / beta (-log(1 - u) >= u), and along
+// the next `reach` of the line of motion the energy cannot rise by more than reach x max |dU/dr| over the distances
+// the pair can have there. That force bound is computed when the list is built, for a window of displacement ahead
+// of the active particle (24 mean veto steps; the list is rebuilt when half of it is used up), and stored with the
+// list: one multiplication and one comparison per (event, target) decide, everything within rounding distance of the
+// threshold -- or beyond the window -- is computed in full. The winner of every event is unchanged
+// (tests/test_gpu_spec.py), only EcmcStats.candidates then counts the evaluated candidates.
 #pragma once
 
 #include "ecmc_kernels.cuh"
@@ -79,6 +81,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     int *l_target = reinterpret_cast<int *>(l_p0 + kDoubles * cap);
     int *l_seq = l_target + cap;
     int count = -1;  // entries of the valid list; -1: rebuild
+    double x_build = 0.0, window = 0.0;  // PRUNE: where the list was built, and how far its force bounds reach
 
     const LennardJones &lj = P.cand_potential.lj;
     Particle *part = S.particles + (size_t)chain * P.n_particles;
@@ -93,7 +96,8 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     int eoc_next = stp->eoc_next_active;
     int active_cell = stp->active_cell;
     unsigned long long ev = stp->event_counter;
-    const uint32_t stream = stp->stream;
+    // (through REDUX: the key of the random stream is then provably warp-uniform and its round keys live in uniform registers)
+    const uint32_t stream = __reduce_or_sync(kFull, stp->stream);
     bool was_pending = stp->pending_kind != ECMC_EVENT_NONE;
     int n_surplus = S.n_surplus[chain];
     Moving a = rotate_in(part[active], dir);
@@ -136,11 +140,18 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             kept_stamp.q = stp->pending_stamp_q; kept_stamp.r = stp->pending_stamp_r;
             u_confirmation = stream_double({P.seed, stream, ev}, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
         } else {
+            if (PRUNE && count >= 0) {
+                // the force bounds of the list hold for a window of displacement from where it was built
+                double travelled = a.p0 - x_build;
+                if (travelled < 0.0) travelled += L;
+                if (!(travelled <= 0.5 * window)) count = -1;
+            }
             if (count < 0) {
                 // ---- rebuild the candidate list: occupants of the nearby cells (ExcludedCellsTagger,
                 // excluded_cells_tagger.py:129-132), then the surplus (SurplusCellsTagger, :129-131)
                 const int n_slots = P.n_nearby + n_surplus;
                 int found_so_far = 0;
+#pragma unroll 1
                 for (int cursor = 0; cursor < n_slots; cursor += 32) {
                     const int s = cursor + lane;
                     int found = -1;
@@ -163,6 +174,11 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                     found_so_far += __popc(occupied);
                 }
                 __syncwarp();
+                if (PRUNE) {
+                    x_build = a.p0;
+                    window = fmin(24.0 * speed * P.inv_beta * P.upper[dir].inv_total_rate_speed, 0.25 * L);
+                }
+#pragma unroll 1
                 for (int base = 0; base < found_so_far; base += 32) {
                     const int i = base + lane;
                     if (i < found_so_far) {
@@ -172,7 +188,14 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                         const double perp2 = fma(s1, s1, s2 * s2);
                         l_p0[i] = tp.p0;
                         l_perp2[i] = perp2;
-                        if (PRUNE) l_bound[i] = lj_force_bound(lj, perp2);
+                        if (PRUNE) {
+                            // smallest distance of the pair while the active particle covers the window
+                            const double ahead = correct_separation_in_box(tp.p0 - a.p0, L, half);
+                            const double behind = ahead - window;
+                            double nearest = (ahead >= 0.0 && behind <= 0.0) ? 0.0 : fmin(fabs(ahead), fabs(behind));
+                            if (behind < -half) nearest = fmin(nearest, half - window);  // the separation wraps around
+                            l_bound[i] = lj_force_bound(lj, fma(nearest, nearest, perp2));
+                        }
                     }
                 }
                 __syncwarp();
@@ -190,21 +213,17 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             // random.choice(table) = table[_randbelow(n)]: rejection on the top bits of successive words (lane g = 1)
             uint32_t choice = 0;
             {
-                bool found = false;
+                bool found = g != 1;  // only the lanes g = 1 hold the table-index words
+                Philox4 words = b;
+                for (uint32_t block = 1;; block++) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t r = b.w[j] >> (32 - w->bits);
-                    if (!found && r < (uint32_t)w->n_entries) { choice = r; found = true; }
-                }
-                if (g == 1)
-                    for (uint32_t block = 1; !found; block++) {
-                        const Philox4 more = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0), block);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint32_t r = more.w[j] >> (32 - w->bits);
-                            if (!found && r < (uint32_t)w->n_entries) { choice = r; found = true; }
-                        }
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t r = words.w[j] >> (32 - w->bits);
+                        if (!found && r < (uint32_t)w->n_entries) { choice = r; found = true; }
                     }
+                    if (__all_sync(kFull, found)) break;  // all four words rejected: 0.1 % of the draws for 1701 of 2048
+                    words = stream_block(key, ECMC_SLOT(ECMC_SLOT_VETO_CHOICE, 0), block);
+                }
             }
             choice = __shfl_sync(kFull, choice, leader + 1);
             const double u_conf = __shfl_sync(kFull, u_first, leader + 2);
@@ -218,62 +237,97 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
 
             // time and position before every event of the batch if all earlier ones are rejected vetoes: the additions
             // of Time.__add__ (time.py:115-133) and of the time slice (abstracts.py:82-95), one event after the other
-            Time my_now = now, my_veto_time = now;
-            double my_x = a.p0, my_next_x = a.p0, my_veto_dt = 0.0;
-            bool my_left = false;
-            Time end_now = now;
-            double end_x = a.p0;
-            {
-                Time t = now;
-                double x = a.p0;
-#pragma unroll
-                for (int k = 0; k < W; k++) {
-                    const double dtv = __shfl_sync(kFull, veto_dt, k * G);
-                    const double xr = t.r + dtv;
-                    const double fl = floor(xr);
-                    Time t_next;
-                    t_next.q = t.q + fl; t_next.r = xr - fl;
-                    const double dt = time_sub(t_next, t);
-                    const double x_next = correct_position_entry(__dadd_rn(x, __dmul_rn(speed, dt)), L);
-                    const bool left = boundary == 0.0 ? x_next < x : x_next >= boundary;
-                    if (e == k) {
-                        my_now = t; my_x = x; my_next_x = x_next; my_left = left; my_veto_dt = dtv; my_veto_time = t_next;
-                    }
-                    t = t_next;
-                    x = x_next;
+            // lane (e, .) applies the increments of the events 0 .. e - 1 and stops
+            Time my_now = now;
+            double my_x = a.p0;
+#pragma unroll 1
+            for (int k = 0; k < W - 1; k++) {
+                const double dtv = __shfl_sync(kFull, veto_dt, k * G);
+                const double xr = my_now.r + dtv;
+                const double fl = floor(xr);
+                Time t_next;
+                t_next.q = my_now.q + fl; t_next.r = xr - fl;
+                const double x_raw = __dadd_rn(my_x, __dmul_rn(speed, time_sub(t_next, my_now)));
+                if (k < e) {
+                    my_now = t_next;
+                    my_x = x_raw >= L ? x_raw - L : x_raw;  // correct_position_entry for [0, 2 L); anything else breaks below
                 }
-                end_now = t;
-                end_x = x;
             }
-            // special candidates of event e
+            // ... and its own event as a rejected veto
+            const double my_veto_dt = __shfl_sync(kFull, veto_dt, leader);
             const double xv = my_now.r + my_veto_dt;
+            Time my_veto_time;
+            {
+                const double fl = floor(xv);
+                my_veto_time.q = my_now.q + fl; my_veto_time.r = xv - fl;
+            }
+            const double my_raw_x = __dadd_rn(my_x, __dmul_rn(speed, time_sub(my_veto_time, my_now)));
+            const double my_next_x = my_raw_x >= L ? my_raw_x - L : my_raw_x;
+            // a time slice that leaves the cell (without a boundary event) or the range of the short modulo ends the batch
+            const bool my_left = (boundary == 0.0 ? my_next_x < my_x : my_next_x >= boundary) || !(my_raw_x >= 0.0 && my_raw_x < 2.0 * L);
+            // special candidates of event e
             double boundary_separation = boundary - my_x;
             if (boundary_separation < 0.0) boundary_separation = boundary_separation + L;  // next_image, hypercubic_setting.py:191
             const double xb = my_now.r + boundary_separation * P.inv_speed;
             // PRUNE: no pair candidate beyond this displacement can be the interaction winner of event e
             const double reach = PRUNE ? fma(speed * (fmin(xv, xb) - my_now.r), 1.0 + 1.0e-9, 1.0e-12) : 0.0;
+            bool beyond_window = false;  // PRUNE: the stored force bounds do not cover this event
+            if (PRUNE) {
+                double travelled = my_x - x_build;
+                if (travelled < 0.0) travelled += L;
+                beyond_window = !(travelled + reach <= window);
+            }
 
             // ---- pair candidates of event e: entries g, g + G, ... of the list
             double best_x = INFINITY;
             int best_seq = kSeqNone, best_target = -1, n_finite = 0;
-            for (int base = 0; base < count; base += G) {
-                const int i = base + g;
-                const bool valid = i < count;
-                const int target = valid ? l_target[i] : 0;
-                const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, target), 0);
-                const double u = words_to_double(pb.w[0], pb.w[1]);
-                bool evaluate = valid;
-                if (PRUNE) evaluate = valid && !(l_bound[i] * reach < u * P.inv_beta * (1.0 - 1.0e-9));
-                if (PRUNE && !__any_sync(kFull, evaluate)) continue;
-                const double s0 = correct_separation_in_box((valid ? l_p0[i] : 0.0) - my_x, L, half);
-                const double perp2 = valid ? l_perp2[i] : 1.0;
+            // TwoLeafUnitEventHandler.send_event_time (two_leaf_unit_event_handler.py:127-138) for list entry i with the
+            // uniform u of its potential change
+            auto candidate = [&](int i, double u) {
+                const double s0 = correct_separation_in_box(l_p0[i] - my_x, L, half);
                 const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
-                const double x = my_now.r + lj_displacement(lj, s0, perp2, du) * P.inv_speed;
-                if (evaluate && x < INFINITY) {  // heap_scheduler.py:139; NaN never wins
+                const double x = my_now.r + lj_displacement(lj, s0, l_perp2[i], du) * P.inv_speed;
+                if (x < INFINITY) {  // heap_scheduler.py:139; NaN never wins
                     n_finite++;
                     const int seq = l_seq[i];
                     const double kx = time_order(x), kb = time_order(best_x);
-                    if (kx < kb || (kx == kb && seq < best_seq)) { best_x = x; best_seq = seq; best_target = target; }
+                    if (kx < kb || (kx == kb && seq < best_seq)) { best_x = x; best_seq = seq; best_target = l_target[i]; }
+                }
+            };
+            if (!PRUNE) {
+#pragma unroll 1
+                for (int base = 0; base < count; base += G) {
+                    const int i = min(base + g, count - 1);  // lanes beyond the end repeat the last entry
+                    const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, l_target[i]), 0);
+                    const int finite_before = n_finite;
+                    candidate(i, words_to_double(pb.w[0], pb.w[1]));
+                    if (base + g >= count) n_finite = finite_before;  // (the repeated entry changes nothing else)
+                }
+            } else {
+                // Pruned: the loop only draws the uniforms and compares them with the force bound; the rare candidate
+                // that may fire before the special candidates waits in a one-entry queue per lane and is inverted
+                // when a lane needs its queue again, or after the loop -- once per batch instead of once per pass.
+                const double threshold = reach * (P.beta / (1.0 - 1.0e-9));  // bound * reach < u / beta (1 - 1e-9)
+                int queued = -1;
+                double queued_u = 0.0;
+#pragma unroll 1
+                for (int base = 0;; base += G) {
+                    const bool last = base >= count;
+                    const int i = base + g;
+                    bool maybe = false;
+                    double u = 0.0;
+                    if (!last) {
+                        const bool valid = i < count;
+                        const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, valid ? l_target[i] : 0), 0);
+                        u = words_to_double(pb.w[0], pb.w[1]);
+                        maybe = valid && (beyond_window || !(l_bound[i] * threshold < u));
+                    }
+                    if (__any_sync(kFull, queued >= 0 && (last || maybe))) {
+                        if (queued >= 0) candidate(queued, queued_u);
+                        queued = -1;
+                    }
+                    if (last) break;
+                    if (maybe) { queued = i; queued_u = u; }
                 }
             }
             // combine the G shares of an event
@@ -364,14 +418,10 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 n.events += (unsigned)e_star;
                 n.veto += (unsigned)e_star;
                 ev += (unsigned long long)e_star;
-                if (e_star < W) {
-                    now.q = __shfl_sync(kFull, my_now.q, e_star * G);
-                    now.r = __shfl_sync(kFull, my_now.r, e_star * G);
-                    a.p0 = __shfl_sync(kFull, my_x, e_star * G);
-                } else {
-                    now = end_now;
-                    a.p0 = end_x;
-                }
+                // the state before event e_star = the state after event e_star - 1
+                now.q = __shfl_sync(kFull, my_veto_time.q, (e_star - 1) * G);
+                now.r = __shfl_sync(kFull, my_veto_time.r, (e_star - 1) * G);
+                a.p0 = __shfl_sync(kFull, my_next_x, (e_star - 1) * G);
             }
             if (e_star >= w_eff) continue;  // the event limit, or a whole batch of rejected vetoes
             // ---- event e_star goes through the general out-state code below

@@ -508,7 +508,9 @@ def test_split_launches_equal_one_launch(oracle):
         for _ in range(3):
             two.run(max_events=300)
         s2 = two.sync()
-        assert s1 == s2
+        # (candidates: with candidate pruning the count of EVALUATED candidates depends on where a launch rebuilt its
+        # candidate list; the committed events do not)
+        assert {k: v for k, v in s1.items() if k != "candidates"} == {k: v for k, v in s2.items() if k != "candidates"}
         assert np.array_equal(one.download_positions(), two.download_positions())
         assert np.array_equal(one.chain_states(), two.chain_states())
         assert two.kernel_launches == 3 and two.kernel_seconds > 0.0
@@ -516,8 +518,8 @@ def test_split_launches_equal_one_launch(oracle):
 
 def test_pruned_launches_reach_the_same_state(oracle):
     """The kernel instantiations with and without event records must commit the same events: identical positions, cells
-    and chain states bit for bit, the same event counts. (A build with -DECMC_PRUNE skips pair candidates that provably
-    cannot win in launches without records; then only the count of finite candidates may differ.)"""
+    and chain states bit for bit, the same event counts. (Launches without records skip pair candidates that provably
+    cannot win -- ECMC_OPTION_PRUNE_CANDIDATES --; then only the count of finite candidates may differ.)"""
     pb, positions = _lj_batch(oracle, n_chains=64, n=100, cells=4, length=5.2, seed=14)
     with engine.Engine(pb, n_chains=64) as pruned, engine.Engine(pb, n_chains=64) as exact:
         for eng in (pruned, exact):
@@ -534,7 +536,7 @@ def test_pruned_launches_reach_the_same_state(oracle):
         for key in ("events", "pair_events", "veto_events", "veto_accepted", "boundary_events", "end_of_chain_events",
                     "pair_targets"):
             assert s1[key] == s2[key], key
-        assert 0 < s1["candidates"] <= s2["candidates"]  # equal unless the library was built with -DECMC_PRUNE
+        assert 0 < s1["candidates"] <= s2["candidates"]
         assert s1["pair_events"] > 10000 and s1["veto_accepted"] > 100
 
 
