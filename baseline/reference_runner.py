@@ -46,6 +46,9 @@ def _run_one(args):
 def _run_one_unguarded(args):
     ini_text, positions, seed, warmup_seconds, budget_seconds, segments = args[:6]
     composites = args[6] if len(args) > 6 else None
+    # segment_events: a segment ends after that many events (the bench's "step" of the same workload) instead of after
+    # budget_seconds; budget_seconds then bounds the whole run (unfinished segments are dropped)
+    segment_events = args[7] if len(args) > 7 else None
     sys.path.insert(0, REF_ROOT)
     import warnings
     warnings.filterwarnings("ignore")
@@ -79,6 +82,20 @@ def _run_one_unguarded(args):
     state = {"events": 0, "t0": None, "deadline": None, "done": []}
     started = time.perf_counter()
 
+    def get_succeeding_event_by_events():
+        winner = original()
+        now = time.perf_counter()
+        if state["t0"] is None:
+            state["t0"] = now
+        if any(tag in type(winner).__name__ for tag in INTERACTION_HANDLERS):
+            state["events"] += 1
+            if state["events"] >= segment_events:
+                state["done"].append((state["events"], now - state["t0"]))
+                state["t0"], state["events"] = now, 0
+        if len(state["done"]) >= segments or now - started >= budget_seconds:
+            raise _Stop()
+        return winner
+
     def get_succeeding_event():
         winner = original()
         now = time.perf_counter()
@@ -95,7 +112,7 @@ def _run_one_unguarded(args):
             state["t0"], state["deadline"], state["events"] = now, now + budget_seconds, 0
         return winner
 
-    scheduler.get_succeeding_event = get_succeeding_event
+    scheduler.get_succeeding_event = get_succeeding_event_by_events if segment_events else get_succeeding_event
     try:
         with contextlib.redirect_stdout(io.StringIO()):
             mediator.run()
@@ -119,6 +136,31 @@ def run_segments(ini_text, positions_per_process, warmup_seconds=2.0, budget_sec
     rates = [sum(done[k][0] / done[k][1] for done, _ in results) for k in range(segments)]
     events = sum(events for done, _ in results for events, _ in done)
     return rates, len(jobs), events, sum(init for _, init in results) / len(results)
+
+
+def run_event_segments(ini_text, positions_per_process, segment_events, segments, skip, max_seconds, composites=None):
+    """One chain per process; every chain runs `segments` consecutive segments of `segment_events` events each (a bench
+    step of the same workload), at most max_seconds of wall clock. The first `skip` segments are the warm-up. Returns
+    (events/s = sum over processes of timed events / timed seconds, processes, timed events, mean init seconds,
+    timed segments completed by the slowest process)."""
+    jobs = [(ini_text, positions, 1000 + k, 0.0, max_seconds, segments,
+             None if composites is None else composites[k], int(segment_events))
+            for k, positions in enumerate(positions_per_process)]
+    context = multiprocessing.get_context("spawn")
+    with context.Pool(len(jobs)) as pool:
+        results = pool.map(_run_one, jobs)
+    failures = [r[1] for r in results if r[0] == "error"]
+    if failures:
+        raise RuntimeError("the reference failed in %d of %d processes: %s" % (len(failures), len(jobs), failures[0]))
+    rate, events, completed = 0.0, 0, None
+    for done, _ in results:
+        timed = done[skip:]
+        if not timed:
+            raise RuntimeError("the reference did not finish its warm-up segments within %.0f s" % max_seconds)
+        rate += sum(e for e, _ in timed) / sum(t for _, t in timed)
+        events += sum(e for e, _ in timed)
+        completed = len(timed) if completed is None else min(completed, len(timed))
+    return rate, len(jobs), events, sum(init for _, init in results) / len(results), completed
 
 
 def run(ini_text, positions_per_process, warmup_seconds=2.0, budget_seconds=10.0, composites=None):

@@ -1,23 +1,31 @@
-"""bench.py -- ECMC events/sec of the batched Lennard-Jones workload C2 on N B200 GPUs.
+"""bench.py -- ECMC events/sec of the batched event-chain kernels on N B200 GPUs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): 3D Lennard-Jones, N = 1024 particles per chain, 4096 independent chains per
-GPU (weak scaling: every rank owns its own 4096 chains and random streams, no data-path collective), cells 12^3,
-nearby cells + surplus by exact LJ inversion, all other cells by cell veto. A "step" advances every chain by
-`--events` events (one ecmc_run launch). One JSON line is printed by rank 0:
+Default workload C2 (BASELINE.json configs[1], the configuration the metric is quoted on): 3D Lennard-Jones, N = 1024
+particles per chain, 4096 independent chains per GPU (weak scaling: every rank owns its own chains and random streams, no
+data-path collective), cells 12^3, nearby cells + surplus by exact LJ inversion, all other cells by cell veto. The other
+BASELINE configurations are `--workload c1` (shipped hard-disk dipoles), `c3` (Coulomb atoms, `--particles` 64..512),
+`c4` (SPC/Fw water, 32 molecules, the oxygen-oxygen histogram of every step all-reduced over the ranks inside the timed
+region) and `c5` (one Lennard-Jones chain of 65536 particles; value = 1 / latency). A "step" advances every chain by
+`events_per_chain_per_step` events (one ecmc_run launch). One JSON line is printed by rank 0:
 
   value      events/s over all ranks, chain state resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e        the same step through the host-buffer entry point ecmc_run_from_host: pinned host positions in ->
-             H2D -> cell binning -> events -> D2H positions out, host clock around synchronous calls
-  roofline   the event kernel against the measured HBM peak (algorithmic bytes per event) -- plus
-             "fp64": the same kernel against the measured DFMA rate, which is the pipe that actually binds it
-  single_chain  N = 1 only: ns/event of ONE Lennard-Jones chain of 65536 particles (C5, the second half of the metric),
-             measured after the timed region on its own engine handle
-  cpu_baseline  the unmodified reference (baseline/_ref, CPython) on the host cores, bounded sample; else the C port
+  e2e        the same step from HOST buffers: pinned host configuration in -> H2D -> cell binning / start of run ->
+             events -> D2H configuration out; step k+1 reads the configuration step k wrote and uses fresh random
+             streams, so the steps walk through the same stretch of the chains' history as the device-timed steps;
+             host clock around synchronous calls
+  roofline   the event kernel against the measured HBM peak: SURVEY.md 8(d)'s algorithmic bytes per event x the events of
+             one launch / the launch duration measured in THIS run (CUDA events around every launch);
+             "traffic" only when a committed ncu capture of the SAME kernel exists (source named, else null)
+  fp64       the same launch against the DFMA rate measured in this run (operation count of the reference formulae)
+  single_chain  N = 1 and C2 only: ns/event of ONE Lennard-Jones chain of 65536 particles (C5, the second half of the
+             metric), measured after the timed region on its own engine handle
+  cpu_baseline  the unmodified reference (baseline/_ref, CPython) on the host cores over the same event window per chain
 
-`--impl reference` times only the CPU reference arm, on rank 0.
+`--impl reference` times only the CPU reference arm, on rank 0: one chain per core, W + K steps of the same number of
+events per chain as the device arm's steps (the same window of every chain's history), the K last ones timed.
 """
 import argparse
 import ctypes
@@ -38,29 +46,266 @@ UNIT = "events/s"
 def parse_args():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=40)
+    parser.add_argument("--steps", type=int, default=20)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    parser.add_argument("--chains", type=int, default=4096, help="independent chains per GPU")
-    parser.add_argument("--particles", type=int, default=1024)
-    parser.add_argument("--cells", type=int, default=12)
-    parser.add_argument("--events", type=int, default=1024, help="events per chain and step")
+    parser.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    parser.add_argument("--chains", type=int, default=None, help="independent chains per GPU (default: the workload's)")
+    parser.add_argument("--particles", type=int, default=None, help="C2 / C3: particles per chain; C4: molecules")
+    parser.add_argument("--cells", type=int, default=None, help="C2: cells per side")
+    parser.add_argument("--events", type=int, default=None, help="events per chain and step")
     parser.add_argument("--e2e-steps", type=int, default=8)
-    parser.add_argument("--cpu-seconds", type=float, default=8.0, help="wall budget of the CPU baseline sample")
+    parser.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the CPU baseline sample")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--ref-seconds", type=float, default=None,
-                        help="--impl reference: wall-clock length of one step (default min(20, 60 / (W + K)) s)")
-    parser.add_argument("--no-single-chain", action="store_true", help="skip the C5 single-chain latency leg (N = 1 only)")
+                        help="--impl reference: steps are wall-clock segments of this length instead of event-bounded ones")
+    parser.add_argument("--ref-max-seconds", type=float, default=150.0, help="--impl reference: bound of the whole run")
+    parser.add_argument("--no-single-chain", action="store_true", help="skip the C5 single-chain latency leg (N = 1, C2)")
     return parser.parse_args()
 
 
-def workload_config(args, world):
-    return {"workload": "C2: 3D Lennard-Jones (prefactor 4, sigma 1), density 0.5, cells %d^3 nl=1, cell-veto far field, "
-                        "chain_time 10, beta 1" % args.cells,
-            "particles_per_chain": args.particles, "chains_per_gpu": args.chains,
-            "events_per_chain_per_step": args.events, "parallelism": "chains sharded over %d GPU(s)" % world,
-            "l2": "chain state (particles + cell occupancy) of one GPU = %.0f MB > 126 MB L2"
-                  % ((args.chains * args.particles * 32 + args.chains * args.cells ** 3 * 4) / 1e6)}
+# ---------------------------------------------------------------------------------------------------------
+# workloads: program, start configuration, algorithmic bytes / operations, the reference's INI
+# ---------------------------------------------------------------------------------------------------------
+class Workload:
+    """One BASELINE configuration. Subclasses fill: name, text, chains, events, dimension, nearby (cells read per
+    event), charged, composite (root units), and build the device program / the reference job."""
+    composite = False
+    charged = False
+
+    def __init__(self, args):
+        self.args = args
+
+    def config(self, world):
+        out = {"workload": self.text, "chains_per_gpu": self.chains, "events_per_chain_per_step": self.events,
+               "particles_per_chain": self.particles, "parallelism": "chains sharded over %d GPU(s)" % world}
+        return out
+
+    # device side ------------------------------------------------------------------------------------
+    def engine(self, device, first_chain):
+        """(started Engine, dict of pinned-able host arrays: positions [, charges, roots])"""
+        raise NotImplementedError
+
+    def bytes_per_event(self, stats):
+        """B_event = 8D (active position) + 4K (occupancy slots of the nearby cells) + n_cand (8D [+ 8 if
+        charged]) (target positions) + 4 + 8D (cell-veto target slot + position) + 8D + 16 (write active position + time)
+        + 8 (two occupancy updates); n_cand = the pair targets gathered per event, measured in this run. Tables are not
+        charged. Also returned: the same count with the 32-byte padded records the device actually moves."""
+        d, k = self.dimension, self.nearby
+        n_cand = stats["pair_targets"] / max(stats["events"], 1)
+        per_target = 8 * d + (8 if self.charged else 0)
+        algorithmic = 8 * d + 4 * k + n_cand * per_target + (4 + 8 * d) + (8 * d + 16) + 8
+        layout = 32 + 4 * k + n_cand * 32 + (4 + 32) + (32 + 16) + 8
+        return algorithmic, layout, n_cand
+
+    def flops_per_event(self, n_cand):
+        raise NotImplementedError
+
+    # reference side ---------------------------------------------------------------------------------
+    def reference_job(self, cores):
+        """(ini text, [positions or None] per process, composites or None) for baseline/reference_runner.py"""
+        raise NotImplementedError
+
+
+class LennardJones(Workload):
+    name, dimension, nearby = "C2", 3, 27
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.particles = args.particles or 1024
+        self.cells = args.cells or 12
+        self.chains = args.chains or 4096
+        self.events = args.events or 1024
+        self.length = float((self.particles / 0.5) ** (1.0 / 3.0))
+        self.text = ("%s: 3D Lennard-Jones (prefactor 4, sigma 1), density 0.5, N = %d, cells %d^3 nl=1 one occupant per cell, "
+                     "exact inversion for nearby cells + surplus, cell-veto far field, chain_time 10, beta 1, jittered "
+                     "lattice start" % (self.name, self.particles, self.cells))
+
+    def config(self, world):
+        out = super().config(world)
+        state_mb = (self.chains * self.particles * 32 + self.chains * self.cells ** 3 * 4) / 1e6
+        out["l2"] = "chain state (particles + cell occupancy) of one GPU = %.0f MB %s 126 MB L2" % (
+            state_mb, ">" if state_mb > 126 else "<")
+        return out
+
+    def builder(self, device):
+        from jellyfysh_b200 import workloads
+        return workloads.lennard_jones(n_particles=self.particles, cells_per_side=self.cells, device=device)[0]
+
+    def engine(self, device, first_chain):
+        from jellyfysh_b200 import engine, workloads
+        positions = workloads.lattice_start(self.chains, self.particles, self.cells, self.length, first_chain=first_chain)
+        eng = engine.Engine(self.builder(device), n_chains=self.chains, device=device)
+        eng.upload_positions(positions)
+        eng.start(first_stream=first_chain)
+        return eng, {"positions": positions}
+
+    def flops_per_event(self, n_cand):
+        """Operation count of the reference formulae: ~70 fp64 operations per Lennard-Jones pair candidate
+        (separation 9, energy 2 x 8, inversion 8, root displacement 7, expovariate, time), ~30 veto draw, ~6 boundary,
+        ~25 argmin / commit."""
+        return 70.0 * n_cand + 30.0 + 6.0 + 25.0
+
+    def reference_job(self, cores):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import configs
+        from jellyfysh_b200 import workloads
+        # one handler instance per possible surplus particle: the reference raises when the list outgrows its pool
+        ini = configs.lennard_jones_ini(self.particles, self.length, self.cells, chain_time=10.0, surplus_handlers=400)
+        return ini, list(workloads.lattice_start(cores, self.particles, self.cells, self.length)), None
+
+
+class SingleChain(LennardJones):
+    name = "C5"
+
+    def __init__(self, args):
+        args.particles = args.particles or 65536
+        args.cells = args.cells or 48
+        args.chains = args.chains or 1
+        args.events = args.events or 20000
+        super().__init__(args)
+
+
+class CoulombAtoms(Workload):
+    name, dimension, nearby, charged = "C3", 3, 27, True
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.particles = args.particles or 64
+        self.chains = args.chains or {64: 4096, 128: 4096, 256: 2048, 512: 1024}.get(self.particles, 1024)
+        self.events = args.events or 1000
+        self.length = 1.0
+        import numpy as np
+        self.cells = int(np.ceil((2 * self.particles) ** (1.0 / 3.0)))
+        self.text = ("C3: Coulomb atoms (coulomb_atoms/cell_veto.ini shape), N = %d charges +1, L = 1, beta 2, merged-image "
+                     "Coulomb (alpha 3.45, cutoffs 6 / 2) bounded by the inverse-power Coulomb bound in the nearby cells, "
+                     "cell veto (inner-point estimator, 10 points per side) elsewhere, cells %d^3, uniform random start"
+                     % (self.particles, self.cells))
+
+    def engine(self, device, first_chain):
+        import numpy as np
+        from jellyfysh_b200 import engine, workloads
+        builder, _ = workloads.coulomb_atoms(n_particles=self.particles, device=device)
+        positions = workloads.uniform_start(self.chains, self.particles, self.length, first_chain=first_chain)
+        charges = np.ones((self.chains, self.particles))
+        eng = engine.Engine(builder, n_chains=self.chains, device=device)
+        eng.upload_positions(positions, charges)
+        eng.start(first_stream=first_chain)
+        return eng, {"positions": positions, "charges": charges}
+
+    def flops_per_event(self, n_cand):
+        """~45 operations per bounded pair candidate (inverse-power Coulomb bound), one merged-image Coulomb derivative
+        (2140 operations) per confirmed pair / cell-veto event -- about one per event --, veto, boundary."""
+        return 45.0 * n_cand + 2140.0 + 30.0 + 6.0 + 25.0
+
+    def reference_job(self, cores):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import configs
+        ini = configs.coulomb_atoms_ini(self.particles, [self.cells] * 3, points_per_side=10)
+        return ini, [configs.uniform_start(self.particles, 1.0, seed=1000 + k) for k in range(cores)], None
+
+
+class HardDiskDipoles(Workload):
+    name, dimension, nearby, composite = "C1", 2, 9, True
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.particles = 162
+        self.chains = args.chains or 4096
+        self.events = args.events or 4000
+        self.text = ("C1: shipped hard_disk_dipoles/hard_disk_dipoles_cells.ini: 81 hard-disk dipoles (162 disks, tethered "
+                     "pairs), 2D, L = 12.836, 13^2 leaf-level cells, shipped start configuration, every chain its own "
+                     "random stream")
+
+    def engine(self, device, first_chain):
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import trace_util as tu
+        from jellyfysh_b200 import engine
+        from jellyfysh_b200.program import ProgramBuilder
+        g = tu.load_trace("trace_hard_disk_dipoles")
+        builder = tu.dipole_builder_of(g, ProgramBuilder)
+        positions = np.tile(g["positions0"], (self.chains, 1, 1))
+        roots = np.tile(g["roots0"], (self.chains, 1, 1))
+        eng = engine.Engine(builder, n_chains=self.chains, device=device)
+        eng.upload_positions(positions)
+        eng.upload_roots(roots)
+        eng.start(first_stream=first_chain)
+        return eng, {"positions": positions, "roots": roots}
+
+    def flops_per_event(self, n_cand):
+        """~25 operations per hard-disk pair candidate (separation, discriminant, root), tether lanes, argmin / commit."""
+        return 25.0 * n_cand + 2 * 40.0 + 25.0
+
+    def reference_job(self, cores):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import configs
+        import reference_runner
+        roots, leaves = configs.read_pdb_dipoles(reference_runner.REF_ROOT)
+        return configs.hard_disk_dipoles_cells_ini(reference_runner.REF_ROOT), [None] * cores, [(roots, leaves)] * cores
+
+
+class Water(Workload):
+    name, dimension, nearby, charged, composite = "C4", 3, 125, True, True
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.molecules = args.particles or 32
+        self.particles = 3 * self.molecules
+        self.chains = args.chains or 1024
+        self.events = args.events or 500
+        self.text = ("C4: SPC/Fw water (water/coulomb_cell_veto_lj_inverted.ini), %d molecules, L = 10, beta 1.679, "
+                     "merged-image Coulomb between molecules (inverse-power bound nearby, cell veto elsewhere), Lennard-Jones "
+                     "between oxygens, harmonic bonds + bending, inside-first lifting, cells 6^3 nl=2; replica sweep: the "
+                     "oxygen-oxygen separation histogram (1000 bins) of every step is all-reduced over the ranks inside "
+                     "the timed region" % self.molecules)
+
+    def engine(self, device, first_chain):
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import configs
+        import trace_util as tu
+        from jellyfysh_b200 import engine
+        from jellyfysh_b200.program import ProgramBuilder
+        g = dict(tu.load_trace("trace_water"))
+        g["meta_n"] = np.asarray(self.particles)
+        builder = tu.water_builder_of(g, ProgramBuilder)
+        roots = np.empty((self.chains, self.molecules, 3))
+        leaves = np.empty((self.chains, self.particles, 3))
+        for c in range(self.chains):
+            r, l = configs.water_start(self.molecules, 10.0, seed=first_chain + c)
+            roots[c], leaves[c] = r, l.reshape(-1, 3)
+        charges = np.tile([0.41, -0.82, 0.41], (self.chains, self.molecules))
+        eng = engine.Engine(builder, n_chains=self.chains, device=device)
+        eng.upload_positions(leaves, charges)
+        eng.upload_roots(roots)
+        eng.start(first_stream=first_chain)
+        return eng, {"positions": leaves, "charges": charges, "roots": roots}
+
+    def bytes_per_event(self, stats):
+        """As Workload.bytes_per_event with composite targets: a gathered target is a molecule, three charged leaves."""
+        n_cand = stats["pair_targets"] / max(stats["events"], 1)
+        algorithmic = 24 + 4 * self.nearby + n_cand * 3 * 32 + (4 + 3 * 32) + (24 + 24 + 16) + 8
+        return algorithmic, algorithmic, n_cand
+
+    def flops_per_event(self, n_cand):
+        """Three bounded leaf-leaf candidates per gathered molecule (~45 operations each), ~10 intramolecular / LJ factors,
+        and the out-state of a composite pair: up to nine merged-image Coulomb derivatives (2140 each; ~3 per event)."""
+        return 3 * 45.0 * n_cand + 10 * 60.0 + 3 * 2140.0 + 60.0
+
+    def reference_job(self, cores):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import configs
+        import reference_runner
+        starts = [configs.water_start(self.molecules, 10.0, seed=k) for k in range(cores)]
+        ini = configs.water_ini(reference_runner.REF_ROOT, n_molecules=self.molecules, number_trials=200)
+        return ini, [None] * cores, [(r, l.reshape(self.molecules, 3, 3)) for r, l in starts]
+
+
+WORKLOADS = {"c1": HardDiskDipoles, "c2": LennardJones, "c3": CoulombAtoms, "c4": Water, "c5": SingleChain}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -83,7 +328,7 @@ class ClockSampler:
         self.window[1] = time.perf_counter()
 
     def _poll_nvml(self):
-        """NVML directly (what nvidia-smi reads), every 5 ms: the timed region of the default run lasts a quarter of a
+        """NVML directly (what nvidia-smi reads), every 5 ms: the timed region of the default run lasts a fraction of a
         second, in which a `nvidia-smi -lms` loop delivers only a handful of lines."""
         import pynvml
         names = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
@@ -157,30 +402,50 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU baselines
 # ---------------------------------------------------------------------------------------------------------
-def reference_sample(args, seconds):
-    """The unmodified reference on all host cores, one chain per core, `seconds` of wall clock each."""
-    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+def interpreter():
+    return "CPython %d.%d" % sys.version_info[:2]
+
+
+def reference_by_events(workload, warmup, steps, max_seconds):
+    """The unmodified reference on all host cores, one chain per core: `warmup` + `steps` segments of the workload's
+    events-per-step each -- the same window of every chain's history as the device arm's steps -- within max_seconds of
+    wall clock (fewer timed segments if the budget ends first). None when baseline/_ref is not installed."""
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
-    import configs
     import reference_runner
-    from jellyfysh_b200 import workloads
     if not reference_runner.available():
         return None
     cores = os.cpu_count() or 1
-    length = float((args.particles / 0.5) ** (1.0 / 3.0))
-    # one handler instance per possible surplus particle: the reference raises when the list outgrows its pool
-    ini = configs.lennard_jones_ini(args.particles, length, args.cells, chain_time=10.0, surplus_handlers=400)
-    positions = workloads.lattice_start(cores, args.particles, args.cells, length)
-    rate, processes, events, init_seconds = reference_runner.run(ini, list(positions), warmup_seconds=2.0,
-                                                                  budget_seconds=seconds)
-    return {"value": rate, "unit": UNIT, "cores": processes, "kind": "reference",
-            "sample": "unmodified JeLLyFysh 1.1 (baseline/_ref, CPython %d.%d) single_process_mediator, one chain of the "
-                      "same workload per core for %.0f s after 2 s warm-up: %d events; init %.1f s per process not counted"
-                      % (sys.version_info[0], sys.version_info[1], seconds, events, init_seconds)}
+    ini, positions, composites = workload.reference_job(cores)
+    rate, processes, events, init_seconds, completed = reference_runner.run_event_segments(
+        ini, positions, workload.events, warmup + steps, warmup, max_seconds, composites=composites)
+    window = "events %d..%d of every chain" % (warmup * workload.events, (warmup + completed) * workload.events)
+    return {"value": rate, "unit": UNIT, "cores": processes, "kind": "reference", "timed_steps": completed,
+            "event_window_per_chain": [warmup * workload.events, (warmup + completed) * workload.events],
+            "sample": "unmodified JeLLyFysh 1.1 (baseline/_ref, %s) single_process_mediator, one chain of the same "
+                      "workload per core, %d warm-up + %d timed steps of %d events per chain (%s): %d events; init %.1f s "
+                      "per process not counted" % (interpreter(), warmup, completed, workload.events, window, events,
+                                                   init_seconds)}
+
+
+def reference_by_seconds(workload, warmup, steps, seconds):
+    """The same with steps that are wall-clock segments (`--ref-seconds`)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import reference_runner
+    if not reference_runner.available():
+        return None
+    cores = os.cpu_count() or 1
+    ini, positions, composites = workload.reference_job(cores)
+    rates, processes, events, init_seconds = reference_runner.run_segments(
+        ini, positions, warmup_seconds=0.0, budget_seconds=seconds, segments=warmup + steps, composites=composites)
+    value = sum(rates[warmup:]) / steps
+    return {"value": value, "unit": UNIT, "cores": processes, "kind": "reference",
+            "sample": "unmodified JeLLyFysh 1.1 (baseline/_ref, %s) single_process_mediator, one chain of the same workload "
+                      "per core, %d warm-up + %d timed segments of %.1f s: %d events; init %.1f s per process not counted"
+                      % (interpreter(), warmup, steps, seconds, events, init_seconds)}
 
 
 def _port_worker(job):
-    particles, cells, chain, events = job
+    particles, cells, chain, warm_events, events = job
     from jellyfysh_b200 import workloads
     from oracle import oracle
     builder, length = _PORT_STATE
@@ -188,7 +453,7 @@ def _port_worker(job):
     chain_object = oracle.OracleChain(builder)
     chain_object.set_positions(positions)
     chain_object.start(stream=chain)
-    chain_object.run(max_events=events // 10)
+    chain_object.run(max_events=warm_events)
     t0 = time.perf_counter()
     n, _ = chain_object.run(max_events=events)
     return n, time.perf_counter() - t0
@@ -197,58 +462,51 @@ def _port_worker(job):
 _PORT_STATE = None
 
 
-def port_sample(args, builder, length, seconds):
-    """The oracle's C port of the same algorithm on all host cores (fork: the program's tables are inherited)."""
+def port_sample(workload, warmup, steps):
+    """No installed reference on this box: the oracle's C port of the same algorithm (Lennard-Jones workloads only) on
+    all host cores over the same event window per chain (fork: the program's tables are inherited)."""
     import multiprocessing
     global _PORT_STATE
-    _PORT_STATE = (builder, length)
+    if not isinstance(workload, LennardJones):
+        raise RuntimeError("baseline/_ref is not installed and the C port only covers the Lennard-Jones workloads")
+    from jellyfysh_b200 import workloads
+    _PORT_STATE = workloads.lennard_jones(n_particles=workload.particles, cells_per_side=workload.cells, veto=True)
     cores = os.cpu_count() or 1
-    events = max(1000, int(seconds * 2.5e5))  # ~4 us per event and core
     context = multiprocessing.get_context("fork")
     with context.Pool(cores) as pool:
-        results = pool.map(_port_worker, [(args.particles, args.cells, c, events) for c in range(cores)])
+        results = pool.map(_port_worker, [(workload.particles, workload.cells, c, warmup * workload.events,
+                                           steps * workload.events) for c in range(cores)])
     rate = sum(n / dt for n, dt in results)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "event_window_per_chain": [warmup * workload.events, (warmup + steps) * workload.events],
             "sample": "oracle/ecmc_oracle.c (plain-C restatement of the reference algorithm), one chain of the same "
-                      "workload per core, %d events each after a 10%% warm-up" % events}
+                      "workload per core, %d events each after %d warm-up events" % (steps * workload.events,
+                                                                                     warmup * workload.events)}
 
 
 def run_reference_arm(args, rank, world):
-    """`--impl reference`: the CPU reference on the host cores, rank 0 only. One pool of processes (one chain per core)
-    runs the warm-up steps and the K timed steps back to back; a step is a bounded wall-clock segment."""
+    """`--impl reference`: the CPU reference on the host cores, rank 0 only."""
     if rank != 0:
         return
-    steps = args.warmup + args.steps
-    seconds = args.ref_seconds if args.ref_seconds else max(0.5, min(20.0, 60.0 / steps))
-    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-    sys.path.insert(0, os.path.join(ROOT, "baseline"))
-    import configs
-    import reference_runner
-    from jellyfysh_b200 import workloads
-    cores = os.cpu_count() or 1
-    length = float((args.particles / 0.5) ** (1.0 / 3.0))
-    if reference_runner.available():
-        # one handler instance per possible surplus particle: the reference raises when the list outgrows its pool
-        ini = configs.lennard_jones_ini(args.particles, length, args.cells, chain_time=10.0, surplus_handlers=400)
-        positions = workloads.lattice_start(cores, args.particles, args.cells, length)
-        rates, processes, events, init_seconds = reference_runner.run_segments(
-            ini, list(positions), warmup_seconds=0.0, budget_seconds=seconds, segments=steps)
-        value = sum(rates[args.warmup:]) / args.steps
-        sample = {"value": value, "unit": UNIT, "cores": processes, "kind": "reference",
-                  "sample": "unmodified JeLLyFysh 1.1 (baseline/_ref, CPython %d.%d) single_process_mediator, one chain "
-                            "of the same workload per core, %d warm-up + %d timed segments of %.1f s: %d events; init "
-                            "%.1f s per process not counted"
-                            % (sys.version_info[0], sys.version_info[1], args.warmup, args.steps, seconds, events,
-                               init_seconds)}
+    workload = WORKLOADS[args.workload](args)
+    t0 = time.perf_counter()
+    if args.ref_seconds:
+        sample = reference_by_seconds(workload, args.warmup, args.steps, args.ref_seconds)
     else:
-        # no installed reference on this box: the C port of its algorithm (oracle) instead
-        builder, length = workloads.lennard_jones(n_particles=args.particles, cells_per_side=args.cells)
-        sample = port_sample(args, builder, length, seconds)
-        value = sample["value"]
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * seconds, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-            "cpu_baseline": sample,
+        sample = reference_by_events(workload, args.warmup, args.steps, args.ref_max_seconds)
+    if sample is None:
+        sample = port_sample(workload, args.warmup, args.steps)
+    wall = time.perf_counter() - t0
+    value = sample["value"]
+    timed_steps = sample.get("timed_steps", args.steps)
+    # one step = events_per_chain_per_step events of every one of the `cores` chains
+    ms_per_step = 1e3 * args.ref_seconds if args.ref_seconds else 1e3 * workload.events * sample["cores"] / value
+    config = workload.config(world)
+    config["chains_timed"] = sample["cores"]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": timed_steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": sample, "wall_seconds": wall,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -277,20 +535,22 @@ def dfma_peak(device):
     return value if value > 0 else None
 
 
-def algorithmic_bytes_per_event(stats, args):
-    """active position 8D + occupancy of the K nearby cells 4K + one 32-byte particle record per pair
-    candidate + cell-veto target slot and record (4 + 32 when the cell is occupied; counted always) + write-back of the
-    active position and time 8D + 16 + two occupancy updates 8."""
-    # pair candidates = the targets gathered from the nearby cells and the surplus: the handler calls the reference makes
-    pair_candidates = stats["pair_targets"] / stats["events"]
-    return 24.0 + 4.0 * 27 + 32.0 * pair_candidates + 36.0 + 40.0 + 8.0, pair_candidates
-
-
-def algorithmic_flops_per_event(pair_candidates):
-    """Operation count of the reference formulae: ~70 fp64 operations per Lennard-Jones pair candidate
-    (separation 9, energy 2 x 8, inversion 8, root displacement 7, expovariate, time), ~30 for the veto draw,
-    ~6 boundary, ~25 argmin / commit."""
-    return 70.0 * pair_candidates + 30.0 + 6.0 + 25.0
+def committed_capture(kernel_name):
+    """The ncu summary under profiles/ whose "kernel_name" is the kernel this run launched (ecmc_kernel_name), if any: an
+    annotation from a committed capture of the same kernel, NOT a measurement of this run."""
+    folder = os.path.join(ROOT, "profiles")
+    best = None
+    for name in sorted(os.listdir(folder)) if os.path.isdir(folder) else []:
+        if not name.endswith("ncu_summary.json"):
+            continue
+        try:
+            with open(os.path.join(folder, name)) as handle:
+                summary = json.load(handle)
+        except (OSError, ValueError):
+            continue
+        if summary.get("kernel_name") == kernel_name:
+            best = (name, summary)  # the last one in name order = the latest round
+    return best
 
 
 def single_chain_latency(device):
@@ -312,79 +572,132 @@ def single_chain_latency(device):
             eng.run(max_events=events)
         stats = eng.sync()
         seconds = eng.kernel_seconds - before
+        kernel = eng.kernel_name()
     return {"workload": "C5: single 3D Lennard-Jones chain, N = 65536, cells 48^3 nl=1, cell-veto far field",
-            "ns_per_event": 1e9 * seconds / stats["events"], "events": stats["events"], "unit": "ns/event"}
+            "ns_per_event": 1e9 * seconds / stats["events"], "events": stats["events"], "unit": "ns/event",
+            "event_window": [events, 3 * events], "kernel": kernel}
 
 
 def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from jellyfysh_b200 import engine, sharding, workloads
+    from jellyfysh_b200 import sharding
 
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    builder, length = workloads.lennard_jones(n_particles=args.particles, cells_per_side=args.cells, device=local_rank)
-    first_chain, _ = sharding.chain_shard(rank, world, args.chains)
-    positions = workloads.lattice_start(args.chains, args.particles, args.cells, length, first_chain=first_chain)
-    eng = engine.Engine(builder, n_chains=args.chains, device=local_rank)
-    eng.upload_positions(positions)
-    eng.start(first_stream=first_chain)
-    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=device)
+    workload = WORKLOADS[args.workload](args)
+    first_chain, _ = sharding.chain_shard(rank, world, workload.chains)
+    eng, host = workload.engine(local_rank, first_chain)
+    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=device)
+    kernel_name = eng.kernel_name()
+    water = isinstance(workload, Water)
+    oo_histogram = np.zeros(1000, dtype=np.uint64)
+    oo_total = torch.zeros(1000, dtype=torch.int64, device=device)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with ClockSampler(local_rank) as clocks:  # nvidia-smi needs ~0.1 s to start: it runs through the warm-up
+    def step():
+        eng.run(max_events=workload.events)
+        if water:
+            # the replica sweep's estimator: oxygen-oxygen separations of this rank's chains on the device,
+            # then ONE all-reduce of the 1000-bin histogram over the ranks, every step
+            oo_histogram[:] = 0
+            eng.separation_histogram(1000, 2.0, 7.0, out=oo_histogram, first=1, stride=3)
+            reduced = sharding.reduce_histogram(oo_histogram.astype(np.int64), device=device)
+            oo_total.add_(torch.as_tensor(np.asarray(reduced), device=device))
+
+    with ClockSampler(local_rank) as clocks:  # the sampler needs ~0.1 s to start: it runs through the warm-up
         for _ in range(args.warmup):
-            eng.run(max_events=args.events)
-        eng.sync()
+            step()
+        warm_stats = eng.sync()
         launches_before = eng.kernel_launches
         kernel_seconds_before = eng.kernel_seconds
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         clocks.open_window()
+        wall0 = time.perf_counter()
         start.record(stream)
         for _ in range(args.steps):
-            eng.run(max_events=args.events)
+            step()
         stop.record(stream)
         stop.synchronize()
         barrier()
+        wall_seconds = time.perf_counter() - wall0
         clocks.close_window()
         time.sleep(0.05)
     stats = eng.sync()
-    elapsed_ms = start.elapsed_time(stop)
+    # C4: the step holds host-synchronous pieces (histogram download, all-reduce), so its time is the host clock between
+    # the two barriers; otherwise the CUDA events on the launching stream
+    elapsed_ms = 1e3 * wall_seconds if water else start.elapsed_time(stop)
     launches = eng.kernel_launches - launches_before
     kernel_seconds = eng.kernel_seconds - kernel_seconds_before
+    _, surplus = eng.cells() if not workload.composite else (None, [])
+    mean_surplus = float(np.mean([len(s) for s in surplus])) if surplus else None
 
-    # ---- end to end through the host-buffer entry point
-    pinned_in = torch.from_numpy(positions).pin_memory()
-    pinned_out = torch.empty_like(pinned_in).pin_memory()
-    host_in, host_out = pinned_in.numpy(), pinned_out.numpy()
-    for _ in range(2):  # warm-up: first-touch of the pinned buffers, stream creation
-        eng.run_from_host(host_in, first_stream=first_chain, max_events=args.events, out=host_out)
+    # ---- end to end from host buffers ----------------------------------------------------------------------------
+    pinned = {name: [torch.from_numpy(np.ascontiguousarray(array)).pin_memory() for _ in range(2)]
+              for name, array in host.items()}
+    for name, array in host.items():
+        pinned[name][0].numpy()[...] = array
+    h2d = sum(array.nbytes for array in host.values())
+    d2h = host["positions"].nbytes + (host["roots"].nbytes if "roots" in host else 0) + 96
+    total_chains = world * workload.chains
+
+    def e2e_step(k):
+        """Configuration in from the pinned buffer step k - 1 wrote, out into the other one; fresh random streams."""
+        source, target = k % 2, (k + 1) % 2
+        first_stream = first_chain + (k + 1) * total_chains
+        charges = pinned["charges"][0].numpy() if "charges" in pinned else None
+        if workload.composite:
+            eng.upload_positions(pinned["positions"][source].numpy(), charges)
+            eng.upload_roots(pinned["roots"][source].numpy())
+            eng.start(first_stream=first_stream)
+            eng.run(max_events=workload.events)
+            step_stats = eng.sync()
+            pinned["positions"][target].numpy()[...] = eng.download_positions()
+            pinned["roots"][target].numpy()[...] = eng.download_roots()
+            return step_stats
+        _, step_stats = eng.run_from_host(pinned["positions"][source].numpy(), charges, first_stream=first_stream,
+                                          max_events=workload.events, out=pinned["positions"][target].numpy())
+        return step_stats
+
+    e2e_warmup = 2
+    for k in range(e2e_warmup):  # first touch of the pinned buffers, stream creation
+        e2e_step(k)
     e2e_launches_before = eng.kernel_launches
     barrier()
     t0 = time.perf_counter()
-    e2e_events = 0
-    for _ in range(args.e2e_steps):
-        _, e2e_stats = eng.run_from_host(host_in, first_stream=first_chain, max_events=args.events, out=host_out)
-        e2e_events += e2e_stats["events"]
+    e2e_events, e2e_targets = 0, 0
+    for k in range(e2e_warmup, e2e_warmup + args.e2e_steps):
+        step_stats = e2e_step(k)
+        e2e_events += step_stats["events"]
+        e2e_targets += step_stats["pair_targets"]
     barrier()
     e2e_seconds = time.perf_counter() - t0
     # per chain slice: pack, start, events, unpack (ecmc_kernel_launches counts the event kernels)
     e2e_launches = 4 * (eng.kernel_launches - e2e_launches_before)
 
     # ---- an observable reduced over ranks (SURVEY 8e): pair-separation histogram of all chains, one NCCL all-reduce
-    import numpy as _np
-    local_histogram = eng.separation_histogram(256, 0.0, length * 3 ** 0.5 / 2.0)
-    histogram = sharding.reduce_histogram(local_histogram.astype(_np.int64), device=torch.device("cuda", local_rank))
+    if water:
+        histogram = oo_total.cpu().numpy()
+        observable = {"kind": "oxygen-oxygen separation histogram on [2, 7] (ecmc_separation_histogram_subset), accumulated "
+                              "over the warm-up and timed steps, all-reduced over the ranks every step inside the timed region",
+                      "bins": 1000, "samples": int(histogram.sum())}
+    else:
+        box = float(eng._builder.program.system_length)
+        local_histogram = eng.separation_histogram(256, 0.0, box * workload.dimension ** 0.5 / 2.0)
+        histogram = sharding.reduce_histogram(local_histogram.astype(np.int64), device=device)
+        observable = {"kind": "pair-separation histogram of all chains (ecmc_separation_histogram), summed over ranks by one "
+                              "all-reduce after the timed region", "bins": 256, "pairs_counted": int(histogram.sum()),
+                      "expected_pairs": world * workload.chains * workload.particles * (workload.particles - 1) // 2}
 
     # ---- reduce over ranks (NCCL): event counters are summed, times are the slowest rank's
-    device = torch.device("cuda", local_rank)
     all_stats = sharding.reduce_counters(stats, device=device)
     total_e2e_events = int(sharding.reduce_histogram([e2e_events], device=device)[0])
     max_ms, max_e2e_seconds, _ = sharding.reduce_max([elapsed_ms, e2e_seconds, kernel_seconds], device=device).tolist()
@@ -397,57 +710,78 @@ def run_ours(args, rank, local_rank, world):
     value = total_events / (max_ms * 1e-3)
     e2e_value = total_e2e_events / max_e2e_seconds
     peaks, peak_source = measured_peaks()
-    bytes_per_event, pair_candidates = algorithmic_bytes_per_event(stats, args)
+    bytes_per_event, layout_bytes, n_cand = workload.bytes_per_event(stats)
     # per launch, this rank: algorithmic bytes of one launch / average launch duration (per-launch CUDA events)
     events_per_launch = stats["events"] / launches
     launch_seconds = kernel_seconds / launches
     achieved_gbs = events_per_launch * bytes_per_event / launch_seconds * 1e-9
-    traffic = None
-    summary_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    ncu = {}
-    if os.path.exists(summary_path):
-        with open(summary_path) as handle:
-            ncu = json.load(handle)
-        traffic = ncu.get("dram_bytes_per_launch")
+    capture = committed_capture(kernel_name)
+    traffic, traffic_source = None, None
+    if capture is not None:
+        traffic = capture[1].get("dram_bytes_per_launch")
+        traffic_source = ("profiles/%s: ncu --set full capture of the same kernel (%s), %d events per launch -- an annotation "
+                          "from a committed capture, not measured in this run" %
+                          (capture[0], kernel_name, int(capture[1].get("events_per_launch", 0))))
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_source,
-                "kernel": "ecmc::event_kernel<LJ, 0, LJ>", "algorithmic_bytes_per_event": bytes_per_event,
+                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_source,
+                "peak_source": peak_source, "kernel": kernel_name,
+                "algorithmic_bytes_per_event": bytes_per_event, "layout_bytes_per_event": layout_bytes,
+                "bytes_formula": "SURVEY.md 8(d): 8D + 4K + n_cand (8D [+8 charged]) + (4 + 8D) + (8D + 16) + 8, n_cand = "
+                                 "pair targets gathered per event in the timed region; layout = the same with the 32-byte "
+                                 "records the device moves",
                 "events_per_launch": events_per_launch, "launch_ms": 1e3 * launch_seconds,
-                "pair_candidates_per_event": pair_candidates,
-                "note": "the chain state is L2-resident and the kernel is bound by instruction issue (a dependent chain of "
-                        "~1000 warp instructions per event, a quarter of them fp64), not by HBM: see fp64 and "
-                        "profiles/"}
+                "pair_targets_per_event": n_cand,
+                "note": "the chain state the events touch is L2-resident (DRAM traffic is a few % of the algorithmic bytes) and "
+                        "the kernel is bound by instruction issue and the latency of each chain's dependent instruction "
+                        "sequence, not by HBM: see fp64 and profiles/"}
     dfma = dfma_peak(local_rank)
-    flops_per_event = algorithmic_flops_per_event(pair_candidates)
+    flops_per_event = workload.flops_per_event(n_cand)
     achieved_tflops = events_per_launch * flops_per_event / launch_seconds * 1e-12
     fp64 = {"achieved_algorithmic_tflops": achieved_tflops, "peak_dfma_tflops": dfma,
             "frac_algorithmic": None if not dfma else achieved_tflops / dfma,
             "algorithmic_flops_per_event": flops_per_event,
-            "ncu_fp64_pipe_utilisation_pct": ncu.get("fp64_pipe_pct"),
-            "ncu_issue_slot_utilisation_pct": ncu.get("issue_active_pct"),
-            "ncu_warp_instructions_per_event": ncu.get("warp_instructions_per_event"),
             "peak_source": "tools/fp64_peak.cu measured in this run (2 flop per DFMA)"}
+    if capture is not None:
+        fp64["committed_capture"] = {"source": "profiles/" + capture[0], "kernel": kernel_name,
+                                     "fp64_pipe_utilisation_pct": capture[1].get("fp64_pipe_pct"),
+                                     "issue_slot_utilisation_pct": capture[1].get("issue_active_pct"),
+                                     "warp_instructions_per_event": capture[1].get("warp_instructions_per_event"),
+                                     "note": "ncu figures of a committed capture of the same kernel, not of this run"}
+    config = workload.config(world)
+    config["event_window_per_chain"] = {"before_timed_region": args.warmup * workload.events,
+                                        "timed_region": [args.warmup * workload.events,
+                                                         (args.warmup + args.steps) * workload.events],
+                                        "pair_targets_per_event_warmup": warm_stats["pair_targets"] / max(warm_stats["events"], 1),
+                                        "pair_targets_per_event_timed": n_cand,
+                                        "mean_surplus_particles_at_end": mean_surplus}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(positions.nbytes), "d2h_bytes_per_step": int(positions.nbytes) + 96,
-                    "steps": args.e2e_steps, "call": "ecmc_run_from_host: pinned host positions -> H2D -> cell binning -> events -> D2H, pipelined over "
-                            "chain slices on separate streams"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": args.e2e_steps, "ms_per_step": 1e3 * max_e2e_seconds / args.e2e_steps,
+                    "host_gb_per_s_per_rank": (h2d + d2h) * args.e2e_steps / max_e2e_seconds * 1e-9,
+                    "pair_targets_per_event": e2e_targets / max(e2e_events, 1),
+                    "call": ("ecmc_upload_positions + ecmc_upload_roots + ecmc_start + ecmc_run + ecmc_sync + "
+                             "ecmc_download_positions + ecmc_download_roots per step" if workload.composite else
+                             "ecmc_run_from_host: pinned host configuration -> H2D -> cell binning -> events -> D2H, "
+                             "pipelined over chain slices on separate streams") +
+                            "; step k + 1 starts from the configuration step k returned, with fresh random streams"},
             "gpu_launches": int(launches + e2e_launches),
-            "roofline": roofline, "fp64": fp64,
-            "observable": {"kind": "pair-separation histogram of all chains (ecmc_separation_histogram), summed over "
-                                   "ranks by one all-reduce", "bins": 256, "pairs_counted": int(histogram.sum()),
-                           "expected_pairs": world * args.chains * args.particles * (args.particles - 1) // 2},
+            "roofline": roofline, "fp64": fp64, "observable": observable,
             "event_mix": {k: all_stats[k] for k in ("pair_events", "veto_events", "veto_accepted", "boundary_events",
                                                     "end_of_chain_events", "bound_violations")}}
-    if world == 1 and not args.no_single_chain:
+    if world == 1 and isinstance(workload, SingleChain):
+        line["single_chain"] = {"workload": workload.text, "ns_per_event": 1e9 * kernel_seconds / stats["events"],
+                                "events": stats["events"], "unit": "ns/event", "kernel": kernel_name}
+    elif world == 1 and args.workload == "c2" and not args.no_single_chain:
         line["single_chain"] = single_chain_latency(local_rank)
+    eng.close()
     if world == 1 and not args.no_cpu_baseline:
-        baseline = reference_sample(args, args.cpu_seconds)
+        # the same window of every chain's history, as far as the wall budget allows
+        baseline = reference_by_events(workload, args.warmup, args.steps, args.cpu_seconds)
         if baseline is None:
-            baseline = port_sample(args, builder, length, args.cpu_seconds)
+            baseline = port_sample(workload, args.warmup, min(args.steps, 4))
         line["cpu_baseline"] = baseline
     emit(line)
     if world > 1:

@@ -377,6 +377,10 @@ void *ecmc_stream(EcmcHandle *h);
 /* Seconds of device time (CUDA events on the handle's stream) spent in event kernels since create. */
 double ecmc_kernel_seconds(EcmcHandle *h);
 uint64_t ecmc_kernel_launches(EcmcHandle *h);
+/* Name of the event kernel that ecmc_run (record = 0) / ecmc_run_recorded (record = 1) launches for this handle's program
+ * and options, e.g. "lj_spec_kernel<record=0, prune=1, lanes=4, warps=14>": the string a profile of the run is matched
+ * against (bench.py, profiles/). Valid until the next call on the handle. */
+const char *ecmc_kernel_name(EcmcHandle *h, int record);
 
 /* ---- batched potential arithmetic on the device -------------------------------------------------------
  * Back the host-side Potential classes -- derivative(velocity, separation, charges) and

@@ -64,6 +64,7 @@ struct EcmcHandle {
     bool spec = true;        // Lennard-Jones / cell-veto programs: lj_spec_kernel (ecmc_set_option)
     bool spec_prune = true;  // ... with the force-bound pruning of pair candidates in ecmc_run / ecmc_run_from_host
     int spec_lanes = 4;      // lanes per speculated event (4: 8 events per batch, 8: 4 events per batch)
+    std::string kernel_name; // ecmc_kernel_name
     std::string error;
 };
 
@@ -1025,6 +1026,39 @@ ECMC_API int ecmc_set_option(EcmcHandle *h, int option, int value) {
 ECMC_API void *ecmc_stream(EcmcHandle *h) { return h ? (void *)h->stream : nullptr; }
 ECMC_API double ecmc_kernel_seconds(EcmcHandle *h) { return h ? h->kernel_seconds : 0.0; }
 ECMC_API uint64_t ecmc_kernel_launches(EcmcHandle *h) { return h ? h->kernel_launches : 0; }
+
+ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
+    if (!h) return "";
+    const DeviceProgram &d = h->dprog;
+    auto potential = [](int kind) -> std::string {
+        switch (kind) {
+        case 0: return "none";
+        case ECMC_POT_LENNARD_JONES: return "LJ";
+        case ECMC_POT_HARD_SPHERE: return "HS";
+        case ECMC_POT_MERGED_IMAGE_COULOMB: return "MIC";
+        case ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING: return "IPCB";
+        case ECMC_POT_INVERSE_POWER: return "IP";
+        default: return "pot" + std::to_string(kind);
+        }
+    };
+    const std::string cand = d.pair_handler == ECMC_PAIR_NONE ? "none" : potential(d.cand_potential.kind);
+    const std::string real = d.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING ? potential(d.real_potential.kind) : "none";
+    const std::string veto = d.veto_enabled ? potential(d.veto_potential.kind) : "none";
+    SpecLaunch spec;
+    if (h->molecules) {
+        h->kernel_name = "molecule_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto + ", record=" + std::to_string(record != 0) + ">";
+    } else if (pick_spec(h, record != 0, &spec)) {
+        h->kernel_name = "lj_spec_kernel<record=" + std::to_string(record != 0) + ", prune=" +
+                         std::to_string(h->spec_prune && !record) + ", lanes=" + std::to_string(h->spec_lanes) + ", warps=" +
+                         std::to_string(kWarpsPerBlock) + ">";
+    } else {
+        h->kernel_name = "event_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto +
+                         (d.nodes_per_root > 1 ? ", composite" : "") +
+                         (d.veto_enabled == ECMC_FAR_CELL_BOUNDING ? ", far_pairs" : "") + ", record=" +
+                         std::to_string(record != 0) + ", warps=" + std::to_string(kWarpsPerBlock) + ">";
+    }
+    return h->kernel_name.c_str();
+}
 
 // ==========================================================================================================
 // batched potential arithmetic

@@ -67,6 +67,8 @@ def library() -> C.CDLL:
     lib.ecmc_kernel_seconds.restype = d
     lib.ecmc_kernel_launches.argtypes = [vp]
     lib.ecmc_kernel_launches.restype = u64
+    lib.ecmc_kernel_name.argtypes = [vp, C.c_int]
+    lib.ecmc_kernel_name.restype = C.c_char_p
     lib.ecmc_potential_derivative.argtypes = [pot, C.c_int, d, vp, sz, vp, vp, vp, C.c_int]
     lib.ecmc_potential_displacement.argtypes = [pot, C.c_int, d, vp, sz, vp, vp, vp, vp, C.c_int]
     lib.ecmc_random_doubles.argtypes = [u32, u32, u64, u32, u32, sz, vp]
@@ -280,6 +282,10 @@ class Engine:
     @property
     def kernel_launches(self):
         return int(self._lib.ecmc_kernel_launches(self._h))
+
+    def kernel_name(self, record=False):
+        """ecmc_kernel_name: the event kernel ecmc_run (or ecmc_run_recorded) launches for this program and options."""
+        return self._lib.ecmc_kernel_name(self._h, int(bool(record))).decode()
 
 
 # ---- batched potential arithmetic and the random stream -----------------------------------------------------

@@ -45,7 +45,10 @@ def test_c2_full_size_properties():
         for _ in range(3):  # the same events in three launches
             two.run(max_events=events // 3)
         stats_two = two.sync()
-        assert stats_one == stats_two
+        # (candidates: with candidate pruning the count of EVALUATED candidates depends on where a launch rebuilt its
+        # candidate list; the committed events do not)
+        assert {k: v for k, v in stats_one.items() if k != "candidates"} == \
+            {k: v for k, v in stats_two.items() if k != "candidates"}
         assert stats_one["events"] == n_chains * events
         assert stats_one["events"] == stats_one["pair_events"] + stats_one["veto_events"] + \
             stats_one["boundary_events"] + stats_one["end_of_chain_events"]

@@ -1,7 +1,11 @@
-"""Summarise an ncu report of the event kernel into profiles/: python tools/ncu_summary.py <report.ncu-rep> <tag>.
+"""Summarise an ncu report of an event kernel into profiles/:
 
-Writes profiles/<tag>_ncu_summary.json (the numbers bench.py's roofline object quotes: DRAM bytes per launch, fp64
-pipe utilisation, issue utilisation, registers, instruction mix per event) and copies it to profiles/ncu_summary.json."""
+    python tools/ncu_summary.py <report.ncu-rep> <tag> [events per launch] [ecmc_kernel_name string]
+
+Writes profiles/<tag>_ncu_summary.json: DRAM bytes per launch, fp64 pipe utilisation, issue utilisation, registers,
+stalls, instruction mix per event. With the fourth argument (what Engine.kernel_name() returned for the captured run) the
+summary carries "kernel_name", and bench.py quotes it -- labelled as a committed capture -- when a run launches the same
+kernel."""
 import collections
 import csv
 import io
@@ -22,6 +26,7 @@ def ncu_csv(report, page, extra=()):
 def main():
     report, tag = sys.argv[1], sys.argv[2]
     events_per_launch = float(sys.argv[3]) if len(sys.argv) > 3 else None
+    kernel_name = sys.argv[4] if len(sys.argv) > 4 else None
     raw = ncu_csv(report, "raw")
     header, units, values = raw[0], raw[1], raw[2]
     metric = {h: (v, u) for h, u, v in zip(header, units, values)}
@@ -52,6 +57,8 @@ def main():
                             for name, v in metric.items() if name.startswith("smsp__average_warps_issue_stalled_")
                             and name.endswith("_per_issue_active.ratio") and float(v[0]) >= 0.05},
     }
+    if kernel_name:
+        summary["kernel_name"] = kernel_name
     if events_per_launch:
         summary["events_per_launch"] = events_per_launch
         summary["warp_instructions_per_event"] = summary["warp_instructions"] / events_per_launch
@@ -70,7 +77,7 @@ def main():
     if events_per_launch:
         summary["instruction_mix_per_event"] = {op: round(n / events_per_launch, 1) for op, n in mix.most_common(24)}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    for name in (f"{tag}_ncu_summary.json", "ncu_summary.json"):
+    for name in (f"{tag}_ncu_summary.json",):
         with open(os.path.join(ROOT, "profiles", name), "w") as handle:
             json.dump(summary, handle, indent=1)
     print(json.dumps(summary, indent=1))
