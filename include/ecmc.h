@@ -356,6 +356,18 @@ int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_min, doubl
 int ecmc_separation_histogram_subset(EcmcHandle *h, int32_t first, int32_t stride, int32_t n_bins, double r_min,
                                      double r_max, uint64_t *histogram);
 
+/* Polarization of every chain: sum over all leaf units of charge x (leaf position closest to its root unit), what
+ * PolarizationOutputHandler.write prints per sample (jellyfysh/input_output_handler/output_handler/
+ * polarization_output_handler.py:76-101, base/node.py:164-188), same order of additions. charges: [n_particles] (the
+ * output handler's own charge of every leaf, the same in all chains) or NULL for the charges uploaded with the positions.
+ * polarization: [n_chains][dimension] (host buffer, overwritten). Composite point objects only. */
+int ecmc_polarization(EcmcHandle *h, const double *charges, double *polarization);
+/* Bond lengths |r_H - r_O| (both bonds) and bond angles of every three-leaf object (child 1 = the centre) of every chain,
+ * what BondLengthAndAngleOutputHandler.write prints (bond_length_and_angle_output_handler.py:77-103), ADDED to two
+ * histograms of n_bins equal bins on [length_min, length_max] / [angle_min, angle_max] (host buffers). */
+int ecmc_bond_histograms(EcmcHandle *h, int32_t n_bins, double length_min, double length_max, double angle_min,
+                         double angle_max, uint64_t *length_histogram, uint64_t *angle_histogram);
+
 /* ---- execution options (no reference counterpart: how the device schedules the same events) ------------------
  * The Lennard-Jones / cell-veto configurations (chargeless 3D Lennard-Jones pair factors in the nearby cells and the
  * surplus, Lennard-Jones cell veto, one occupant per cell) are advanced by a kernel that evaluates several successive

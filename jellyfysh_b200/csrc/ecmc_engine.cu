@@ -1010,6 +1010,61 @@ ECMC_API int ecmc_separation_histogram_subset(EcmcHandle *h, int32_t first, int3
     return rc;
 }
 
+ECMC_API int ecmc_polarization(EcmcHandle *h, const double *charges, double *polarization) {
+    if (!h || !polarization) return fail(h, ECMC_ERR_INVALID, "null argument");
+    const DeviceProgram &d = h->dprog;
+    if (d.nodes_per_root < 2 || !h->state.roots) return fail(h, ECMC_ERR_INVALID, "polarization needs composite point objects");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    double *d_out = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)h->n_chains * d.dimension;
+    const size_t charge_bytes = charges ? sizeof(double) * (size_t)d.n_particles : 0;
+    CUDA_TRY(h, cudaMalloc(&d_out, bytes + charge_bytes));
+    double *d_charges = charges ? d_out + (size_t)h->n_chains * d.dimension : nullptr;
+    cudaError_t err = charges ? cudaMemcpyAsync(d_charges, charges, charge_bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+    if (err == cudaSuccess) {
+        polarization_kernel<<<(h->n_chains + 127) / 128, 128, 0, h->stream>>>(
+            h->state.particles, h->state.roots, d_charges, h->n_chains, d.n_particles / d.nodes_per_root, d.nodes_per_root,
+            d.dimension, d.length, d_out);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(polarization, d_out, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (err != cudaSuccess) return fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err));
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_bond_histograms(EcmcHandle *h, int32_t n_bins, double length_min, double length_max, double angle_min,
+                                  double angle_max, uint64_t *length_histogram, uint64_t *angle_histogram) {
+    if (!h || !length_histogram || !angle_histogram) return fail(h, ECMC_ERR_INVALID, "null argument");
+    const DeviceProgram &d = h->dprog;
+    if (d.nodes_per_root != 3 || d.dimension != 3) return fail(h, ECMC_ERR_INVALID, "bond histograms need objects of three leaves in 3D");
+    if (n_bins < 1 || n_bins > kHistogramMaxBins || !(length_max > length_min) || !(angle_max > angle_min))
+        return fail(h, ECMC_ERR_INVALID, "histograms need 1 <= n_bins <= 4096 and min < max");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    unsigned long long *d_histograms = nullptr;
+    const size_t bytes = sizeof(unsigned long long) * 2 * (size_t)n_bins;
+    CUDA_TRY(h, cudaMalloc(&d_histograms, bytes));
+    std::vector<unsigned long long> counts(2 * (size_t)n_bins);
+    const size_t n_objects = (size_t)h->n_chains * (d.n_particles / 3);
+    cudaError_t err = cudaMemsetAsync(d_histograms, 0, bytes, h->stream);
+    if (err == cudaSuccess) {
+        bond_histogram_kernel<<<(int)std::min<size_t>((n_objects + 255) / 256, 148 * 8), 256, 0, h->stream>>>(
+            h->state.particles, n_objects, d.length, n_bins, length_min, (double)n_bins / (length_max - length_min), angle_min,
+            (double)n_bins / (angle_max - angle_min), d_histograms, d_histograms + n_bins);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(counts.data(), d_histograms, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+    cudaFree(d_histograms);
+    if (err != cudaSuccess) return fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err));
+    for (int b = 0; b < n_bins; b++) {
+        length_histogram[b] += counts[b];
+        angle_histogram[b] += counts[n_bins + b];
+    }
+    return ECMC_OK;
+}
+
 ECMC_API int ecmc_set_option(EcmcHandle *h, int option, int value) {
     if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
     switch (option) {

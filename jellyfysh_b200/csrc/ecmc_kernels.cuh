@@ -1021,6 +1021,58 @@ separation_histogram_kernel(const Particle *particles, int n_particles, int n_ti
         if (bins[b]) atomicAdd(histogram + b, (unsigned long long)bins[b]);
 }
 
+// PolarizationOutputHandler.write (polarization_output_handler.py:76-101): per chain the sum over all leaf units of
+// charge x (leaf position closest to its root unit, base/node.py:164-188), in the reference's order of additions (root
+// by root, leaf by leaf, component by component) -- one thread per chain, the observable is sampled rarely.
+__global__ void __launch_bounds__(128)
+polarization_kernel(const Particle *particles, const Particle *roots, const double *charges, int n_chains, int n_roots,
+                    int nodes_per_root, int dimension, double length, double *out) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    const Particle *part = particles + (size_t)chain * n_roots * nodes_per_root;
+    const Particle *root = roots + (size_t)chain * n_roots;
+    const double half = 0.5 * length;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    for (int r = 0; r < n_roots; r++) {
+        const Particle c = root[r];
+        for (int k = 0; k < nodes_per_root; k++) {
+            const Particle leaf = part[r * nodes_per_root + k];
+            const double q = charges ? charges[r * nodes_per_root + k] : leaf.charge;
+            px = __dadd_rn(px, __dmul_rn(q, __dadd_rn(c.x, correct_separation_in_box(leaf.x - c.x, length, half))));
+            py = __dadd_rn(py, __dmul_rn(q, __dadd_rn(c.y, correct_separation_in_box(leaf.y - c.y, length, half))));
+            if (dimension > 2)
+                pz = __dadd_rn(pz, __dmul_rn(q, __dadd_rn(c.z, correct_separation_in_box(leaf.z - c.z, length, half))));
+        }
+    }
+    out[(size_t)chain * dimension] = px;
+    out[(size_t)chain * dimension + 1] = py;
+    if (dimension > 2) out[(size_t)chain * dimension + 2] = pz;
+}
+
+// BondLengthAndAngleOutputHandler.write (bond_length_and_angle_output_handler.py:77-103) for objects of three leaves
+// (hydrogen, oxygen, hydrogen): histograms of the two bond lengths |r_H - r_O| and of the angle between the two bonds
+// (base/vectors.py: angle_between_two_vectors = acos of the normalised dot product). One thread per object.
+__global__ void __launch_bounds__(256)
+bond_histogram_kernel(const Particle *particles, size_t n_objects, double length, int n_bins, double length_min,
+                      double inv_length_width, double angle_min, double inv_angle_width, unsigned long long *length_histogram,
+                      unsigned long long *angle_histogram) {
+    const double half = 0.5 * length;
+    for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < n_objects; o += (size_t)gridDim.x * blockDim.x) {
+        const Particle h1 = particles[3 * o], ox = particles[3 * o + 1], h2 = particles[3 * o + 2];
+        const double ax = correct_separation_in_box(h1.x - ox.x, length, half), ay = correct_separation_in_box(h1.y - ox.y, length, half),
+                     az = correct_separation_in_box(h1.z - ox.z, length, half);
+        const double bx = correct_separation_in_box(h2.x - ox.x, length, half), by = correct_separation_in_box(h2.y - ox.y, length, half),
+                     bz = correct_separation_in_box(h2.z - ox.z, length, half);
+        const double na = sqrt(fma(ax, ax, fma(ay, ay, az * az))), nb = sqrt(fma(bx, bx, fma(by, by, bz * bz)));
+        const double values[3] = {na, nb, acos(fma(ax, bx, fma(ay, by, az * bz)) / (na * nb))};
+        for (int k = 0; k < 3; k++) {
+            const double scaled = k < 2 ? (values[k] - length_min) * inv_length_width : (values[k] - angle_min) * inv_angle_width;
+            if (scaled >= 0.0 && scaled <= (double)n_bins)
+                atomicAdd((k < 2 ? length_histogram : angle_histogram) + min((int)scaled, n_bins - 1), 1ull);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // batched potential arithmetic (ecmc_potential_derivative / ecmc_potential_displacement): one warp per element
 // for the merged-image Coulomb sum, one thread per element otherwise.

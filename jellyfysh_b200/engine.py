@@ -60,6 +60,8 @@ def library() -> C.CDLL:
     lib.ecmc_run_from_host.argtypes = [vp, vp, vp, u32, d, d, i64, vp, stats]
     lib.ecmc_separation_histogram.argtypes = [vp, i32, d, d, vp]
     lib.ecmc_separation_histogram_subset.argtypes = [vp, i32, i32, i32, d, d, vp]
+    lib.ecmc_polarization.argtypes = [vp, vp, vp]
+    lib.ecmc_bond_histograms.argtypes = [vp, i32, d, d, d, d, vp, vp]
     lib.ecmc_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.ecmc_stream.argtypes = [vp]
     lib.ecmc_stream.restype = vp
@@ -226,6 +228,21 @@ class Engine:
         self._check(self._lib.ecmc_separation_histogram_subset(self._h, int(first), int(stride), int(n_bins),
                                                                float(r_min), float(r_max), _ptr(out)))
         return out
+
+    def polarization(self, charges=None):
+        """ecmc_polarization: [n_chains][dimension], sum of charge x closest leaf position over all leaves of a chain;
+        charges[n_particles] (the same in every chain) or None for the uploaded ones."""
+        out = np.empty((self.n_chains, self.dimension), dtype=np.float64)
+        ch = None if charges is None else _f64(charges, (self.n_particles,))
+        self._check(self._lib.ecmc_polarization(self._h, _ptr(ch), _ptr(out)))
+        return out
+
+    def bond_histograms(self, n_bins, length_range, angle_range, out=None):
+        """Add the bond lengths / bond angles of all three-leaf objects to (lengths, angles) uint64[n_bins] histograms."""
+        lengths, angles = out if out is not None else (np.zeros(n_bins, dtype=np.uint64), np.zeros(n_bins, dtype=np.uint64))
+        self._check(self._lib.ecmc_bond_histograms(self._h, int(n_bins), float(length_range[0]), float(length_range[1]),
+                                                   float(angle_range[0]), float(angle_range[1]), _ptr(lengths), _ptr(angles)))
+        return lengths, angles
 
     # ---- checkpoint / resume (the role of DumpingOutputHandler + resume.py, jellyfysh/resume.py; SURVEY 8f N3) ----
     def save_checkpoint(self, path):

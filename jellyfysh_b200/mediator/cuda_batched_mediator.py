@@ -13,8 +13,9 @@ state handler, scheduler, activator -- all built by the reference's factory from
     activator = tag_activator
     input_output_handler = input_output_handler
     number_of_chains = 4096        ; independent Markov chains advanced at once (default 1)
-    device = 0
+    devices = 0, 1, 2, 3           ; CUDA devices; the chains are split into contiguous blocks, one engine per device
     seed = 0
+    device_observables = true      ; histogram-type output handlers are accumulated on the device (see below)
 
 (see INTEGRATION.md for how the module becomes `jellyfysh.mediator.cuda_batched_mediator`).
 
@@ -24,8 +25,17 @@ calls at their own event times -- here between `ecmc_run(until = their time)` la
 into the reference's state handler so that the reference's output handlers see exactly what they expect.
 The scheduler object is kept for the host control events only (the device argmin replaces it for interaction events).
 Chain 0 starts from the state the input handler produced; chains c > 0 from further reads of the same input handler.
+
+Sampling at scale (`device_observables = true`): the reference's output handlers print every sample of every chain from a
+Python loop (SeparationOutputHandler: N (N - 1) / 2 lines per chain and sample). With thousands of chains the observables
+are accumulated where the configurations live instead -- ecmc_separation_histogram[_subset] (SeparationOutputHandler,
+OxygenOxygenSeparationOutputHandler), ecmc_polarization (PolarizationOutputHandler: one vector per chain and sample, written
+in the reference's text format), ecmc_bond_histograms (BondLengthAndAngleOutputHandler) -- and the histograms are written
+next to the output handler's file (`<filename>.histogram.npz`: edges, counts) at the end of the run; `observables` holds
+them. Output handlers of other types keep the chain-by-chain path.
 """
 import logging
+from typing import Sequence
 
 import numpy as np
 
@@ -37,21 +47,26 @@ from jellyfysh.mediator.mediator import Mediator
 from jellyfysh.scheduler import Scheduler
 from jellyfysh.state_handler import StateHandler
 
-from jellyfysh_b200 import compiler, engine
+from jellyfysh_b200 import compiler, engine, sharding
 
 
 class CudaBatchedMediator(Mediator):
-    """Mediator that advances `number_of_chains` independent chains on one CUDA device."""
+    """Mediator that advances `number_of_chains` independent chains on one or several CUDA devices."""
 
     def __init__(self, input_output_handler: InputOutputHandler, state_handler: StateHandler, scheduler: Scheduler,
                  activator: Activator, number_of_chains: int = 1, device: int = 0, seed: int = 0,
                  first_random_stream: int = 0, maximum_surplus: int = 0, occupant_capacity: int = 8,
-                 events_per_launch: int = 4000000, resume_file: str = "") -> None:
+                 events_per_launch: int = 4000000, resume_file: str = "", devices: Sequence[int] = (),
+                 device_observables: bool = False, histogram_bins: int = 1000) -> None:
         """
         Parameters follow SingleProcessMediator (single_process_mediator.py:57-72); in addition:
 
-        number_of_chains : independent Markov chains on the device.
-        device : CUDA device index.
+        number_of_chains : independent Markov chains, all devices together.
+        device : CUDA device index (one device).
+        devices : CUDA device indices; the chains are split into contiguous blocks (sharding.split_chains), one engine
+            per entry (an index may repeat: several engines on one device), chain c reads random stream
+            first_random_stream + c whatever the number of devices, so the chains do not depend on the split.
+        device_observables, histogram_bins : accumulate the samples of histogram-type output handlers on the devices.
         seed, first_random_stream : chain c reads the counter-based random stream (seed, first_random_stream + c).
         maximum_surplus : capacity of the per-chain surplus list (0: one slot per particle).
         occupant_capacity : occupants per cell kept on the device when the reference's cell occupancy is unbounded.
@@ -85,11 +100,24 @@ class CudaBatchedMediator(Mediator):
                 all_charges[chain] = charges
             if roots is not None:
                 all_roots[chain] = roots
-        self._engine = engine.Engine(self._compiled.builder, n_chains=number_of_chains, device=device)
-        self._engine.upload_positions(all_positions, all_charges)
-        if all_roots is not None:
-            self._engine.upload_roots(all_roots)
-        self._engine.start(first_stream=first_random_stream)
+        device_list = [int(d) for d in devices] if len(devices) else [int(device)]
+        if number_of_chains < len(device_list):
+            raise compiler._configuration_error("more devices than chains")
+        self._shards = sharding.split_chains(number_of_chains, len(device_list))
+        self._engines = []
+        for (first, count), index in zip(self._shards, device_list):
+            eng = engine.Engine(self._compiled.builder, n_chains=count, device=index)
+            eng.upload_positions(all_positions[first:first + count],
+                                 None if all_charges is None else all_charges[first:first + count])
+            if all_roots is not None:
+                eng.upload_roots(all_roots[first:first + count])
+            eng.start(first_stream=first_random_stream + first)
+            self._engines.append(eng)
+        self._engine = self._engines[0]
+        self._device_observables = bool(device_observables)
+        self._histogram_bins = int(histogram_bins)
+        self._observables = {}
+        self._template_charges = {}
         self._statistics = {}
         self._control_times = {}
         self._events_per_launch = max(int(events_per_launch), 1)
@@ -127,12 +155,78 @@ class CudaBatchedMediator(Mediator):
         self._state_handler.insert_into_global_state(cnodes)
 
     def _download(self):
-        positions = self._engine.download_positions()
-        roots = self._engine.download_roots() if self._compiled.nodes_per_root > 1 else None
-        return positions, roots, self._engine.chain_states()
+        positions = np.concatenate([eng.download_positions() for eng in self._engines])
+        roots = (np.concatenate([eng.download_roots() for eng in self._engines])
+                 if self._compiled.nodes_per_root > 1 else None)
+        return positions, roots, self.chain_states()
+
+    def chain_states(self):
+        """Lifting state (EcmcChainState) of all chains, in chain order over the devices."""
+        return np.concatenate([eng.chain_states() for eng in self._engines])
+
+    # ---- observables accumulated on the devices ---------------------------------------------------------------
+    def _sample_on_device(self, name):
+        """One sampling event of the output handler `name`, if its observable has a device accumulator. The handlers
+        and their observables: separation_output_handler.py:75-97, oxygen_oxygen_separation_output_handler.py:78-97,
+        polarization_output_handler.py:76-101, bond_length_and_angle_output_handler.py:77-103."""
+        output = self._input_output_handler._output_handlers_dictionary[name]
+        kinds = {cls.__name__ for cls in type(output).__mro__}
+        program = self._compiled.builder.program
+        length, dimension, bins = float(program.system_length), int(program.dimension), self._histogram_bins
+        npr = self._compiled.nodes_per_root
+        if "SeparationOutputHandler" in kinds or "OxygenOxygenSeparationOutputHandler" in kinds:
+            oxygen = "OxygenOxygenSeparationOutputHandler" in kinds
+            if oxygen and npr != 3:
+                return False
+            entry = self._observables.setdefault(name, {
+                "kind": "oxygen_oxygen_separation" if oxygen else "separation", "filename": output._output_filename,
+                "edges": np.linspace(0.0, length * dimension ** 0.5 / 2.0, bins + 1),
+                "counts": np.zeros(bins, dtype=np.uint64), "samples": 0})
+            for eng in self._engines:
+                eng.separation_histogram(bins, entry["edges"][0], entry["edges"][-1], out=entry["counts"],
+                                         first=1 if oxygen else 0, stride=npr if oxygen else 1)
+            entry["samples"] += 1
+            return True
+        if "PolarizationOutputHandler" in kinds and npr > 1:
+            if name not in self._template_charges:
+                template = self._state_handler.extract_global_state()
+                self._template_charges[name] = np.array([child.value.charge[output._charge] for cnode in template
+                                                         for child in cnode.children], dtype=np.float64)
+            vectors = np.concatenate([eng.polarization(self._template_charges[name]) for eng in self._engines])
+            for vector in vectors:  # one line per chain and sample, the reference's format
+                print("\t".join(map(str, vector.tolist())), file=output._file)
+            entry = self._observables.setdefault(name, {"kind": "polarization", "filename": output._output_filename,
+                                                        "samples": 0})
+            entry["samples"] += 1
+            return True
+        if "BondLengthAndAngleOutputHandler" in kinds and npr == 3 and dimension == 3:
+            entry = self._observables.setdefault(name, {
+                "kind": "bond_length_and_angle", "filename": output._output_filename,
+                "length_edges": np.linspace(0.0, length / 2.0, bins + 1), "angle_edges": np.linspace(0.0, np.pi, bins + 1),
+                "length_counts": np.zeros(bins, dtype=np.uint64), "angle_counts": np.zeros(bins, dtype=np.uint64),
+                "samples": 0})
+            for eng in self._engines:
+                eng.bond_histograms(bins, (0.0, length / 2.0), (0.0, np.pi),
+                                    out=(entry["length_counts"], entry["angle_counts"]))
+            entry["samples"] += 1
+            return True
+        return False
+
+    def _write_observables(self):
+        for entry in self._observables.values():
+            arrays = {key: value for key, value in entry.items() if isinstance(value, np.ndarray)}
+            if arrays:
+                np.savez(entry["filename"] + ".histogram.npz", samples=np.asarray(entry["samples"]), **arrays)
+
+    @property
+    def observables(self):
+        """Observables accumulated on the devices so far: {output handler name: {kind, edges, counts, samples, ...}}."""
+        return self._observables
 
     def _write_output(self, handler):
         if handler.output_handler is None:
+            return
+        if self._device_observables and self._sample_on_device(handler.output_handler):
             return
         positions, roots, states = self._download()
         for chain in range(self._number_of_chains):
@@ -149,7 +243,8 @@ class CudaBatchedMediator(Mediator):
         controls = self._compiled.control_handlers
         times = np.array([[self._control_times[h].quotient, self._control_times[h].remainder] for h in controls])
         # the dumping handler itself has not been rescheduled yet: its next time follows from its own event time
-        self._engine.save_checkpoint(path)
+        for index, eng in enumerate(self._engines):
+            eng.save_checkpoint(path if index == 0 else path[:-4] + ".device%d.npz" % index)
         with np.load(path) as data:
             arrays = dict(data)
         arrays["control_times"] = times
@@ -160,7 +255,9 @@ class CudaBatchedMediator(Mediator):
 
     def _resume(self, path, charges):
         controls = self._compiled.control_handlers
-        self._engine.load_checkpoint(path, charges)
+        for index, (eng, (first, count)) in enumerate(zip(self._engines, self._shards)):
+            eng.load_checkpoint(path if index == 0 else path[:-4] + ".device%d.npz" % index,
+                                None if charges is None else charges[first:first + count])
         with np.load(path) as data:
             names, times, dumping = data["control_names"].tolist(), data["control_times"], int(data["dumping_handler"])
         if names != [type(h).__name__ for h in controls]:
@@ -189,6 +286,7 @@ class CudaBatchedMediator(Mediator):
             names = {cls.__name__ for cls in type(handler).__mro__}
             if "EndOfRunEventHandler" in names:
                 self._write_output(handler)
+                self._write_observables()
                 positions, roots, states = self._download()
                 self._load_chain_into_state_handler(0, positions, states, roots)
                 raise EndOfRun
@@ -203,12 +301,13 @@ class CudaBatchedMediator(Mediator):
         until = (event_time.quotient, event_time.remainder)
         stalled = 0
         while True:
-            before = self._engine.chain_states()
-            self._engine.run(until=until, max_events=self._events_per_launch)
-            stats = self._engine.sync()
-            for key, value in stats.items():
-                self._statistics[key] = self._statistics.get(key, 0) + value
-            after = self._engine.chain_states()
+            before = self.chain_states()
+            for eng in self._engines:  # asynchronous: the devices run side by side
+                eng.run(until=until, max_events=self._events_per_launch)
+            for eng in self._engines:
+                for key, value in eng.sync().items():
+                    self._statistics[key] = self._statistics.get(key, 0) + value
+            after = self.chain_states()
             behind = (after["time_q"] != until[0]) | (after["time_r"] != until[1])
             if not behind.any():
                 return
@@ -226,7 +325,12 @@ class CudaBatchedMediator(Mediator):
 
     @property
     def engine(self):
+        """The engine of the first device."""
         return self._engine
+
+    @property
+    def engines(self):
+        return list(self._engines)
 
     def update_logging(self) -> None:
         self._logger = logging.getLogger(__name__)

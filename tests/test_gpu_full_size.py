@@ -196,3 +196,48 @@ def test_subset_separation_histogram_matches_numpy():
         expected += np.histogram(np.sqrt(np.sum(sep * sep, axis=1)), bins=500, range=(0.0, r_max))[0]
     assert ours.sum() == n_chains * m * (m - 1) // 2
     assert np.abs(ours.astype(np.int64) - expected).sum() <= 4
+
+
+def test_polarization_and_bond_histograms_match_numpy():
+    """ecmc_polarization and ecmc_bond_histograms on water molecules after some events, against numpy on the downloaded
+    configuration: the observables of PolarizationOutputHandler (polarization_output_handler.py:76-101 with
+    base/node.py:164-188) and BondLengthAndAngleOutputHandler (bond_length_and_angle_output_handler.py:77-103)."""
+    import configs
+    import trace_util as tu
+    from jellyfysh_b200.program import ProgramBuilder
+    n_chains, n_molecules = 12, 16
+    g = dict(tu.load_trace("trace_water"))
+    g["meta_n"] = np.asarray(3 * n_molecules)
+    builder = tu.water_builder_of(g, ProgramBuilder)
+    length = 10.0
+    roots = np.empty((n_chains, n_molecules, 3))
+    leaves = np.empty((n_chains, 3 * n_molecules, 3))
+    for c in range(n_chains):
+        r, l = configs.water_start(n_molecules, length, seed=40 + c)
+        roots[c], leaves[c] = r, l.reshape(-1, 3)
+    charges = np.tile([0.41, -0.82, 0.41], (n_chains, n_molecules))
+    with engine.Engine(builder, n_chains=n_chains) as eng:
+        eng.upload_positions(leaves, charges)
+        eng.upload_roots(roots)
+        eng.start(first_stream=0)
+        eng.run(max_events=400)
+        eng.sync()
+        polarization = eng.polarization()
+        other = np.linspace(-1.0, 1.0, 3 * n_molecules)
+        polarization_other = eng.polarization(other)
+        lengths, angles = eng.bond_histograms(200, (0.5, 1.5), (1.0, 2.8))
+        eng.bond_histograms(200, (0.5, 1.5), (1.0, 2.8), out=(lengths, angles))  # accumulates
+        now, now_roots = eng.download_positions(), eng.download_roots()
+    half = length / 2.0
+    closest = np.repeat(now_roots, 3, axis=1) + (np.mod(now - np.repeat(now_roots, 3, axis=1) + half, length) - half)
+    assert np.max(np.abs(polarization - np.einsum("cn,cnd->cd", charges, closest))) < 1e-11
+    assert np.max(np.abs(polarization_other - np.einsum("n,cnd->cd", other, closest))) < 1e-11
+    molecules = now.reshape(n_chains, n_molecules, 3, 3)
+    one = np.mod(molecules[:, :, 0] - molecules[:, :, 1] + half, length) - half
+    two = np.mod(molecules[:, :, 2] - molecules[:, :, 1] + half, length) - half
+    n_one, n_two = np.linalg.norm(one, axis=2), np.linalg.norm(two, axis=2)
+    expected_lengths = np.histogram(np.concatenate([n_one.ravel(), n_two.ravel()]), bins=200, range=(0.5, 1.5))[0]
+    expected_angles = np.histogram(np.arccos(np.sum(one * two, axis=2) / (n_one * n_two)).ravel(), bins=200, range=(1.0, 2.8))[0]
+    assert lengths.sum() == 2 * 2 * n_chains * n_molecules and angles.sum() == 2 * n_chains * n_molecules
+    assert np.abs(lengths.astype(np.int64) - 2 * expected_lengths).sum() <= 4
+    assert np.abs(angles.astype(np.int64) - 2 * expected_angles).sum() <= 4

@@ -103,6 +103,54 @@ def test_many_chains_from_the_input_handler(tmp_path):
     assert len(set(states["event_counter"].tolist())) > 1  # the chains are different
 
 
+def test_several_engines_and_device_observables(tmp_path):
+    """`devices = 0, 0, 0` (three engines, here on one device; chain blocks 3 + 3 + 2) and `device_observables`: the chains
+    are those of a single engine, chain for chain, and the separation histogram accumulated on the device is the histogram
+    of the lines the reference's SeparationOutputHandler prints for the same run."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    from jellyfysh.base.exceptions import EndOfRun
+    g = tu.load_trace("trace_lj_small")
+    n, length, chains, end, interval, bins = int(g["meta_n"]), float(g["meta_system_length"]), 8, 1.7, 0.4, 50
+    rng = np.random.default_rng(3)
+    grid = np.stack(np.meshgrid(*[np.arange(4)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)[:n]
+    positions = np.concatenate([(grid + 0.5) * (length / 4) + rng.uniform(-0.1, 0.1, size=grid.shape) for _ in range(chains)])
+    results = {}
+    for tag, extra in (("one", ""), ("three", "\ndevices = 0, 0, 0\ndevice_observables = true\nhistogram_bins = %d" % bins)):
+        folder = tmp_path / tag
+        folder.mkdir()
+        ini = _device_ini(g, folder, chains, end, interval).replace("first_random_stream", "first_random_stream")
+        ini = ini.replace("[CudaBatchedMediator]", "[CudaBatchedMediator]" + extra)
+        mediator, setting = build_reference_graph(ini, positions)
+        try:
+            with pytest.raises(EndOfRun):
+                mediator.run()
+            mediator.post_run()
+            results[tag] = (mediator.chain_states(), np.concatenate([e.download_positions() for e in mediator.engines]),
+                            mediator.statistics, dict(mediator.observables), len(mediator.engines))
+        finally:
+            setting.reset()
+    one, three = results["one"], results["three"]
+    assert one[4] == 1 and three[4] == 3
+    assert np.array_equal(one[0], three[0]) and np.array_equal(one[1], three[1])
+    assert {k: v for k, v in one[2].items()} == {k: v for k, v in three[2].items()}
+    # the reference's output handler printed every separation of every sample of the first run
+    lines = np.loadtxt(tmp_path / "one" / "separation.dat", comments="#")
+    samples = int(end / interval)
+    assert len(lines) == samples * chains * n * (n - 1) // 2
+    observable = three[3]["separation_output_handler"]
+    assert observable["samples"] == samples and len(observable["counts"]) == bins
+    expected, _ = np.histogram(lines, bins=observable["edges"])
+    assert int(observable["counts"].sum()) == len(lines)
+    # (a separation within rounding distance of a bin edge may fall on the other side of it)
+    assert np.abs(observable["counts"].astype(np.int64) - expected).sum() <= 4
+    with np.load(str(tmp_path / "three" / "separation.dat") + ".histogram.npz") as written:
+        assert np.array_equal(written["counts"], observable["counts"]) and int(written["samples"]) == samples
+
+
 @pytest.mark.parametrize("config,output", [("cell_veto.ini", "SamplesOfSeparation_CellVeto.dat"),
                                            ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat"),
                                            ("power_bounded.ini", "SamplesOfSeparation_PowerBounded.dat")])

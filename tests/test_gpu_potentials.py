@@ -57,6 +57,31 @@ def test_reference_known_answers():
     assert not failures, failures[:5]
 
 
+def test_reference_known_answers_through_the_host_potential_classes():
+    """The same constants through jellyfysh_b200.potential: classes with the reference's names, constructor arguments
+    and derivative / displacement signatures (potential.py:154-181, 218-301), so this loop reads like the reference's
+    own unit tests -- `LennardJonesPotential(prefactor=0.5, characteristic_length=0.3).derivative([0, 1, 0], [...])`."""
+    from jellyfysh_b200 import potential
+    failures = []
+    for rec in kr.load_kats():
+        separation = rec["args"][1]
+        box = {"system_length": rec["length"] if rec["length"] is not None else 1.0, "dimension": len(separation)}
+        instance = potential.BY_NAME[rec["cls"]](**rec["init"], **box)
+        assert instance.number_separation_arguments == 1
+        assert len(rec["args"]) == 2 + instance.number_charge_arguments + \
+            (1 if rec["method"] == "displacement" and instance.potential_change_required else 0), rec["test"]
+        value = getattr(instance, rec["method"])(*rec["args"])
+        expected = float("inf") if rec["expected"] == "inf" else rec["expected"]
+        if not (kr.kat_matches(value, expected, min(rec["places"], 12)) or close([value], [expected])):
+            failures.append((rec["test"], rec["args"], value, expected))
+    assert not failures, failures[:5]
+    # batched form: one launch for many separations
+    lj = potential.LennardJonesPotential(prefactor=4.0, characteristic_length=1.0, system_length=10.0, dimension=3)
+    separations = np.random.default_rng(5).uniform(-3.0, 3.0, size=(1000, 3))
+    batch = lj.derivatives(0, separations)
+    assert batch.shape == (1000,) and batch[17] == lj.derivative(0, separations[17])
+
+
 def lj_derivative_scale(k, s, sep, direction, speed=1.0):
     """The Lennard-Jones derivative is the difference of the r^-14 and r^-8 terms and vanishes at the minimum:
     compare on the scale of the two terms."""
