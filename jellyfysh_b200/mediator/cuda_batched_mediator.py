@@ -57,7 +57,7 @@ class CudaBatchedMediator(Mediator):
                  activator: Activator, number_of_chains: int = 1, device: int = 0, seed: int = 0,
                  first_random_stream: int = 0, maximum_surplus: int = 0, occupant_capacity: int = 8,
                  events_per_launch: int = 4000000, resume_file: str = "", devices: Sequence[int] = (),
-                 device_observables: bool = False, histogram_bins: int = 1000) -> None:
+                 device_observables: bool = False, histogram_bins: int = 1000, device_estimators: bool = False) -> None:
         """
         Parameters follow SingleProcessMediator (single_process_mediator.py:57-72); in addition:
 
@@ -67,6 +67,8 @@ class CudaBatchedMediator(Mediator):
             per entry (an index may repeat: several engines on one device), chain c reads random stream
             first_random_stream + c whatever the number of devices, so the chains do not depend on the split.
         device_observables, histogram_bins : accumulate the samples of histogram-type output handlers on the devices.
+        device_estimators : the estimators of cell-veto handlers / cell-bounding potentials evaluate their points on the
+            device (jellyfysh_b200/estimators.py) when the activator is initialised, instead of point by point in Python.
         seed, first_random_stream : chain c reads the counter-based random stream (seed, first_random_stream + c).
         maximum_surplus : capacity of the per-chain surplus list (0: one slot per particle).
         occupant_capacity : occupants per cell kept on the device when the reference's cell occupancy is unbounded.
@@ -81,6 +83,11 @@ class CudaBatchedMediator(Mediator):
         if number_of_chains < 1:
             raise compiler._configuration_error("number_of_chains must be at least 1")
         state_handler.initialize(input_output_handler.read())
+        if device_estimators:
+            from jellyfysh_b200 import estimators
+            first_device = int(devices[0]) if len(devices) else int(device)
+            self._logger.info("%d estimator(s) evaluate their points on device %d",
+                              estimators.accelerate_activator(activator, first_device), first_device)
         super().__init__(input_output_handler, state_handler, scheduler, activator)
         template = state_handler.extract_global_state()
         self._compiled = compiler.compile_program(activator, template, seed=seed,

@@ -350,3 +350,37 @@ def test_unsupported_graphs_are_rejected(lj_graph):
     occupancy._cell_level = 2
     with pytest.raises(ConfigurationError):
         compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())
+
+
+def test_shipped_pdb_start_configuration_through_the_reference_input_handler():
+    """config_files/hard_disk_dipoles/hard_disk_dipoles_cells.ini UNCHANGED (with its `pdb_input_handler`): where
+    MDAnalysis is not installed, jellyfysh_b200.install() provides the .pdb reader the reference's PdbInputHandler needs
+    (jellyfysh_b200/shims/MDAnalysis). The start configuration the reference builds from it -- coordinates rounded through
+    float32 as MDAnalysis stores them, pdb_input_handler.py:165, barycentres over shortest separations :172-186 -- is the
+    one the C1 trace fixture starts from, and the graph compiles to the C1 device program."""
+    import jellyfysh_b200
+    from jellyfysh_b200 import compiler
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    jellyfysh_b200.install()
+    import MDAnalysis
+    text = configs.shipped_ini(REF, "hard_disk_dipoles", "hard_disk_dipoles_cells.ini")
+    text = text.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+    text = text.replace("output/hard_disk_dipoles/", "/tmp/jf_b200_pdb_test_")
+    assert "input_handler = pdb_input_handler" in text
+    mediator, setting = build_reference_graph(text)
+    try:
+        state = mediator._state_handler.extract_global_state()
+        roots = np.array([node.value.position for node in state])
+        leaves = np.array([[child.value.position for child in node.children] for node in state])
+        compiled = compiler.compile_program(mediator._activator, state, seed=1)
+    finally:
+        setting.reset()
+    expected_roots, expected_leaves = configs.read_pdb_dipoles(REF)
+    assert np.array_equal(leaves, expected_leaves) and np.array_equal(roots, expected_roots)
+    g = tu.load_trace("trace_hard_disk_dipoles")
+    assert np.array_equal(leaves.reshape(-1, 2), g["positions0"]) and np.array_equal(roots, g["roots0"])
+    assert compiled.nodes_per_root == 2 and compiled.n_particles == 162
+    if "shim" in getattr(MDAnalysis, "__version__", ""):
+        with pytest.raises(NotImplementedError):
+            MDAnalysis.Writer("x.pdb", 3)

@@ -531,3 +531,62 @@ def test_shipped_dump_config_dumps_and_resumes(tmp_path):
     for field in ("active", "direction", "time_q", "time_r", "event_counter", "eoc_q", "eoc_r"):
         assert np.array_equal(full_states[field], resumed_states[field]), field
     assert resumed_stats["events"] == full_stats["events"] - dumped_events > 0
+
+
+def test_device_estimators_reproduce_the_reference_bounds():
+    """jellyfysh_b200.estimators.accelerate on the reference's four estimator classes (inner_point_estimator.py:139-163,
+    boundary_point_estimator.py:108-174, dipole_monte_carlo_estimator.py:100-155 -- same draws of Python's `random` in
+    the same order --, dipole_inner_point_estimator.py:100-163): the bounds of the device-backed `derivative_bound`
+    against the reference's own point-by-point loop for cells of the water cell system, merged-image Coulomb potential."""
+    import random
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from jellyfysh.base.exceptions import EndOfRun  # noqa: F401 - the package must be importable
+    from jellyfysh.setting import hypercubic_setting
+    import jellyfysh.setting as setting
+    from jellyfysh.estimator.inner_point_estimator import InnerPointEstimator
+    from jellyfysh.estimator.boundary_point_estimator import BoundaryPointEstimator
+    from jellyfysh.estimator.dipole_monte_carlo_estimator import DipoleMonteCarloEstimator
+    from jellyfysh.estimator.dipole_inner_point_estimator import DipoleInnerPointEstimator
+    from jellyfysh.potential.merged_image_coulomb_potential import MergedImageCoulombPotential
+    from jellyfysh.potential.lennard_jones_potential import LennardJonesPotential
+    from jellyfysh_b200 import estimators
+    setting.reset()
+    hypercubic_setting.HypercubicSetting(beta=1.679, dimension=3, system_length=10.0)
+    try:
+        coulomb = MergedImageCoulombPotential(prefactor=332.0)
+        cases = [
+            ("inner / Coulomb", lambda: InnerPointEstimator(potential=coulomb, prefactor=1.3, points_per_side=5)),
+            ("inner / Lennard-Jones", lambda: InnerPointEstimator(
+                potential=LennardJonesPotential(prefactor=0.6217012, characteristic_length=3.165492), prefactor=1.5,
+                points_per_side=4, empirical_bound=60.0)),
+            ("boundary / Coulomb", lambda: BoundaryPointEstimator(potential=coulomb, prefactor=1.2, points_per_side=6)),
+            ("dipole Monte Carlo", lambda: DipoleMonteCarloEstimator(
+                potential=coulomb, dipole_separation=1.3, dipole_charge=0.82, prefactor=1.1, number_trials=300)),
+            ("dipole inner point", lambda: DipoleInnerPointEstimator(
+                potential=coulomb, dipole_separation=1.3, dipole_charge=0.82, prefactor=1.2, points_per_side=4)),
+        ]
+        side = 10.0 / 6
+        regions = [([3 * side - side, -side, -side], [3 * side + side, side, side]),          # three cells away along x
+                   ([-4 * side, 2 * side, -3 * side], [-2 * side, 4 * side, -side]),           # a corner cell (wraps)
+                   ([2 * side, 2 * side, 2 * side], [4 * side, 4 * side, 4 * side])]
+        for name, make in cases:
+            for lower, upper in regions:
+                for direction in range(3):
+                    for both in (True, False):
+                        reference = make()
+                        random.seed(77)
+                        expected = reference.derivative_bound(list(lower), list(upper), direction, both)
+                        ours = make()
+                        assert estimators.accelerate(ours), name
+                        random.seed(77)
+                        got = ours.derivative_bound(list(lower), list(upper), direction, both)
+                        assert len(got) == len(expected) == (2 if both else 1), name
+                        # (the dipole inner point estimator normalises a gradient of nearly cancelling derivatives: the
+                        # device's 1e-13 shows up as 1e-8 in the orientation of its dipoles)
+                        tolerance = 1e-6 if name == "dipole inner point" else 1e-10
+                        for a, b in zip(got, expected):
+                            assert abs(a - b) <= tolerance * max(1.0, abs(b)), (name, lower, direction, got, expected)
+    finally:
+        setting.reset()

@@ -76,9 +76,10 @@ def main():
         mix[match.group(2) if match else "?"] += count
     if events_per_launch:
         summary["instruction_mix_per_event"] = {op: round(n / events_per_launch, 1) for op, n in mix.most_common(24)}
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    folder = os.environ.get("NCU_SUMMARY_DIR", os.path.join(ROOT, "profiles"))  # on the GPU box: gpurun_out
+    os.makedirs(folder, exist_ok=True)
     for name in (f"{tag}_ncu_summary.json",):
-        with open(os.path.join(ROOT, "profiles", name), "w") as handle:
+        with open(os.path.join(folder, name), "w") as handle:
             json.dump(summary, handle, indent=1)
     print(json.dumps(summary, indent=1))
 
