@@ -307,6 +307,10 @@ int ecmc_abi_version(void);
 /* positions: [n_chains][n_particles][dimension] doubles; charges: [n_chains][n_particles] or NULL (all 1.0). */
 int ecmc_upload_positions(EcmcHandle *h, const double *positions, const double *charges);
 int ecmc_download_positions(EcmcHandle *h, double *positions);
+/* One chain only -- what an output handler or a dump of a single chain needs (the four methods of the reference's state
+ * handler contract, jellyfysh/state_handler/state_handler.py:63-165, read one global state): positions
+ * [n_particles][dimension]; roots [n_particles / nodes_per_root][dimension] or NULL; state (lifting state) or NULL. */
+int ecmc_download_chain(EcmcHandle *h, int chain, double *positions, double *roots, EcmcChainState *state);
 /* Root-unit positions of composite objects, [n_chains][n_particles / nodes_per_root][dimension] (programs with
  * nodes_per_root > 1 only; ECMC_ERR_INVALID otherwise). Must be uploaded before ecmc_start. */
 int ecmc_upload_roots(EcmcHandle *h, const double *roots);

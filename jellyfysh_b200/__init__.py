@@ -26,4 +26,9 @@ def install():
     sys.modules["jellyfysh.mediator.cuda_batched_mediator"] = module
     import jellyfysh.mediator
     jellyfysh.mediator.cuda_batched_mediator = module
+    # `state_handler = cuda_state_handler` (optional): the state-handler contract over the chains of the device engines
+    handler = importlib.import_module("jellyfysh_b200.state_handler.cuda_state_handler")
+    sys.modules["jellyfysh.state_handler.cuda_state_handler"] = handler
+    import jellyfysh.state_handler
+    jellyfysh.state_handler.cuda_state_handler = handler
     return module

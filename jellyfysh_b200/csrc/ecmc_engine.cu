@@ -749,6 +749,29 @@ ECMC_API int ecmc_download_positions(EcmcHandle *h, double *positions) {
     return collect_timings(h);
 }
 
+ECMC_API int ecmc_download_chain(EcmcHandle *h, int chain, double *positions, double *roots, EcmcChainState *state) {
+    if (!h || !positions) return fail(h, ECMC_ERR_INVALID, "null argument");
+    if (chain < 0 || chain >= h->n_chains) return fail(h, ECMC_ERR_INVALID, "chain index out of range");
+    const DeviceProgram &d = h->dprog;
+    if (roots && d.nodes_per_root <= 1) return fail(h, ECMC_ERR_INVALID, "the program has no composite objects");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)d.n_particles, n_roots = roots ? n / d.nodes_per_root : 0;
+    unpack_particles_kernel<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(h->state.particles + (size_t)chain * n, h->d_staging,
+                                                                        n, d.dimension);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(positions, h->d_staging, n * d.dimension * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (roots) {  // (the staging buffer is reused: stream order keeps the two copies apart)
+        unpack_particles_kernel<<<(int)((n_roots + 255) / 256), 256, 0, h->stream>>>(h->state.roots + (size_t)chain * n_roots,
+                                                                                  h->d_staging, n_roots, d.dimension);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaMemcpyAsync(roots, h->d_staging, n_roots * d.dimension * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (state)
+        CUDA_TRY(h, cudaMemcpyAsync(state, h->state.chains + chain, sizeof(EcmcChainState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return collect_timings(h);
+}
+
 ECMC_API int ecmc_upload_roots(EcmcHandle *h, const double *roots) {
     if (!h || !roots) return fail(h, ECMC_ERR_INVALID, "null argument");
     if (h->dprog.nodes_per_root <= 1) return fail(h, ECMC_ERR_INVALID, "the program has no composite objects");
@@ -1097,7 +1120,8 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
         }
     };
     const std::string cand = d.pair_handler == ECMC_PAIR_NONE ? "none" : potential(d.cand_potential.kind);
-    const std::string real = d.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING ? potential(d.real_potential.kind) : "none";
+    const bool bounded = d.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING || d.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING;
+    const std::string real = bounded ? potential(d.real_potential.kind) : "none";
     const std::string veto = d.veto_enabled ? potential(d.veto_potential.kind) : "none";
     SpecLaunch spec;
     if (h->molecules) {

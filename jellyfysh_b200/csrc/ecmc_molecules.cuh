@@ -210,7 +210,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
     const double L = P.length, half = P.half_length, speed = P.speed;
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
     unsigned n_events = 0, n_pair = 0, n_veto = 0, n_eoc = 0, n_bond = 0, n_factor = 0, n_boundary = 0;
-    unsigned long long n_candidates = 0;
+    unsigned long long n_candidates = 0, n_targets = 0;  // n_targets: gathered target objects (EcmcStats.pair_targets)
     bool stopped_by_time = false;
 
     auto set_dir = [&](Vec3 &v, double value) { if (dir == 0) v.x = value; else if (dir == 1) v.y = value; else v.z = value; };
@@ -321,6 +321,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                     } else if (s < n_scan) {
                         type = ITEM_BOUNDARY; target = 0; copies = 1;
                     }
+                    n_targets += (unsigned long long)__popc(__ballot_sync(kFull, type == ITEM_PAIR_LEAF || type == ITEM_FAR_OBJECT));
                     // exclusive prefix sum of `copies` over the lanes: where this lane's items go
                     int offset = copies;
 #pragma unroll
@@ -808,6 +809,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             if (n_candidates) atomicAdd(st + 6, n_candidates);
             if (n_bond) atomicAdd(st + 9, (unsigned long long)n_bond);
             if (n_factor) atomicAdd(st + 10, (unsigned long long)n_factor);
+            if (n_targets) atomicAdd(st + 11, n_targets);
         }
     }
 }

@@ -47,6 +47,7 @@ def library() -> C.CDLL:
     lib.ecmc_last_error.restype = C.c_char_p
     lib.ecmc_upload_positions.argtypes = [vp, vp, vp]
     lib.ecmc_download_positions.argtypes = [vp, vp]
+    lib.ecmc_download_chain.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.ecmc_upload_roots.argtypes = [vp, vp]
     lib.ecmc_download_roots.argtypes = [vp, vp]
     lib.ecmc_start.argtypes = [vp, vp, u32]
@@ -143,6 +144,15 @@ class Engine:
         out = np.empty((self.n_chains, self.n_particles, self.dimension), dtype=np.float64)
         self._check(self._lib.ecmc_download_positions(self._h, _ptr(out)))
         return out
+
+    def download_chain(self, chain):
+        """ecmc_download_chain: (positions[N][D], roots[N / npr][D] or None, lifting state record) of one chain."""
+        positions = np.empty((self.n_particles, self.dimension), dtype=np.float64)
+        roots = (np.empty((self.n_particles // self.nodes_per_root, self.dimension), dtype=np.float64)
+                 if self.nodes_per_root > 1 else None)
+        state = np.zeros(1, dtype=abi.chain_state_dtype())
+        self._check(self._lib.ecmc_download_chain(self._h, int(chain), _ptr(positions), _ptr(roots), _ptr(state)))
+        return positions, roots, state[0]
 
     def upload_roots(self, roots):
         """Root-unit positions of composite objects, [n_chains][n_particles / nodes_per_root][dimension]."""

@@ -121,6 +121,9 @@ class CudaBatchedMediator(Mediator):
             eng.start(first_stream=first_random_stream + first)
             self._engines.append(eng)
         self._engine = self._engines[0]
+        if hasattr(state_handler, "bind"):  # cuda_state_handler: reads single chains straight from the engines
+            program = self._compiled.builder.program
+            state_handler.bind(self._engines, self._shards, program.speed, program.dimension, self._compiled.nodes_per_root)
         self._device_observables = bool(device_observables)
         self._histogram_bins = int(histogram_bins)
         self._observables = {}
@@ -136,6 +139,9 @@ class CudaBatchedMediator(Mediator):
         """Write one chain's device state through the public state-handler contract
         (state_handler.py:63-165): positions of all units, velocity / time stamp of the active leaf unit and, for
         composite point objects, of its root unit (velocity * weight, event_handler/abstracts/abstracts.py:165-190)."""
+        if hasattr(self._state_handler, "load"):
+            self._state_handler.load(positions[chain], None if roots is None else roots[chain], states[chain])
+            return
         speed = self._compiled.builder.program.speed
         dimension = self._compiled.builder.program.dimension
         npr = self._compiled.nodes_per_root

@@ -151,6 +151,52 @@ def test_several_engines_and_device_observables(tmp_path):
         assert np.array_equal(written["counts"], observable["counts"]) and int(written["samples"]) == samples
 
 
+def test_cuda_state_handler_reads_single_chains(tmp_path):
+    """`state_handler = cuda_state_handler`: the reference's state-handler contract (state_handler.py:63-165) over the
+    chains of the device engines -- select_chain(c) downloads chain c alone (ecmc_download_chain) and the four contract
+    methods then describe it: positions of all units, velocity and time stamp of the active unit only."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    from jellyfysh.base.exceptions import EndOfRun
+    g = tu.load_trace("trace_lj_small")
+    n, length, chains = int(g["meta_n"]), float(g["meta_system_length"]), 5
+    rng = np.random.default_rng(8)
+    grid = np.stack(np.meshgrid(*[np.arange(4)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)[:n]
+    positions = np.concatenate([(grid + 0.5) * (length / 4) + rng.uniform(-0.1, 0.1, size=grid.shape) for _ in range(chains)])
+    ini = _device_ini(g, tmp_path, chains, 1.3, None).replace("state_handler = tree_state_handler",
+                                                              "state_handler = cuda_state_handler")
+    ini = ini.replace("[TreeStateHandler]", "[CudaStateHandler]").replace("[CudaBatchedMediator]",
+                                                                          "[CudaBatchedMediator]\ndevices = 0, 0")
+    assert "cuda_state_handler" in ini and "[CudaStateHandler]" in ini
+    mediator, setting = build_reference_graph(ini, positions)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        handler = mediator._state_handler
+        assert type(handler).__mro__[0].__name__.startswith("CudaStateHandler") and handler.number_of_chains == chains
+        everything = np.concatenate([e.download_positions() for e in mediator.engines])
+        states = mediator.chain_states()
+        for chain in (3, 0, 4):
+            handler.select_chain(chain)
+            assert handler.selected_chain == chain
+            state = handler.extract_global_state()
+            assert np.array_equal(np.array([node.value.position for node in state]), everything[chain])
+            moving = [node.value for node in state if node.value.velocity is not None]
+            assert len(moving) == 1 and moving[0].identifier == (int(states[chain]["active"]),)
+            assert moving[0].velocity[int(states[chain]["direction"])] == 1.0
+            assert (moving[0].time_stamp.quotient, moving[0].time_stamp.remainder) == \
+                (float(states[chain]["time_q"]), float(states[chain]["time_r"]))
+            active = handler.extract_active_global_state()
+            assert len(active) == 1 and active[0].value.identifier == moving[0].identifier
+        with pytest.raises(IndexError):
+            handler.select_chain(chains)
+    finally:
+        setting.reset()
+
+
 @pytest.mark.parametrize("config,output", [("cell_veto.ini", "SamplesOfSeparation_CellVeto.dat"),
                                            ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat"),
                                            ("power_bounded.ini", "SamplesOfSeparation_PowerBounded.dat")])
