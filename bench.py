@@ -670,6 +670,27 @@ def run_ours(args, rank, local_rank, world):
     e2e_warmup = 2
     for k in range(e2e_warmup):  # first touch of the pinned buffers, stream creation
         e2e_step(k)
+
+    def link_rate(to_device):
+        """GB/s of one pinned-host <-> device copy of the positions buffer alone (CUDA events): what bounds an e2e step."""
+        host_buffer = pinned["positions"][0]
+        device_buffer = torch.empty_like(host_buffer, device=device)
+        begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 0.0
+        for _ in range(3):
+            begin.record()
+            if to_device:
+                device_buffer.copy_(host_buffer, non_blocking=True)
+            else:
+                host_buffer.copy_(device_buffer, non_blocking=True)
+            end.record()
+            end.synchronize()
+            best = max(best, host_buffer.numel() * 8 / (begin.elapsed_time(end) * 1e-3) * 1e-9)
+        return best
+
+    h2d_rate = link_rate(True)
+    d2h_rate = link_rate(False)
+    # (the probe copies buffer 0 to the device and back: its content is unchanged)
     e2e_launches_before = eng.kernel_launches
     barrier()
     t0 = time.perf_counter()
@@ -761,6 +782,9 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps, "ms_per_step": 1e3 * max_e2e_seconds / args.e2e_steps,
                     "host_gb_per_s_per_rank": (h2d + d2h) * args.e2e_steps / max_e2e_seconds * 1e-9,
+                    "link_gb_per_s": {"h2d": h2d_rate, "d2h": d2h_rate,
+                                      "note": "one pinned copy of the positions buffer alone on rank 0, best of 3: h2d_bytes / "
+                                              "h2d rate is the floor of a step before its last slice can start"},
                     "pair_targets_per_event": e2e_targets / max(e2e_events, 1),
                     "call": ("ecmc_upload_positions + ecmc_upload_roots + ecmc_start + ecmc_run + ecmc_sync + "
                              "ecmc_download_positions + ecmc_download_roots per step" if workload.composite else

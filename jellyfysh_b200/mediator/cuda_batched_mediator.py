@@ -57,7 +57,8 @@ class CudaBatchedMediator(Mediator):
                  activator: Activator, number_of_chains: int = 1, device: int = 0, seed: int = 0,
                  first_random_stream: int = 0, maximum_surplus: int = 0, occupant_capacity: int = 8,
                  events_per_launch: int = 4000000, resume_file: str = "", devices: Sequence[int] = (),
-                 device_observables: bool = False, histogram_bins: int = 1000, device_estimators: bool = False) -> None:
+                 device_observables: bool = False, histogram_bins: int = 1000, device_estimators: bool = False,
+                 equilibration_samples: int = 0) -> None:
         """
         Parameters follow SingleProcessMediator (single_process_mediator.py:57-72); in addition:
 
@@ -67,6 +68,7 @@ class CudaBatchedMediator(Mediator):
             per entry (an index may repeat: several engines on one device), chain c reads random stream
             first_random_stream + c whatever the number of devices, so the chains do not depend on the split.
         device_observables, histogram_bins : accumulate the samples of histogram-type output handlers on the devices.
+        equilibration_samples : device observables skip the first samples of every output handler (start configuration).
         device_estimators : the estimators of cell-veto handlers / cell-bounding potentials evaluate their points on the
             device (jellyfysh_b200/estimators.py) when the activator is initialised, instead of point by point in Python.
         seed, first_random_stream : chain c reads the counter-based random stream (seed, first_random_stream + c).
@@ -126,6 +128,9 @@ class CudaBatchedMediator(Mediator):
             state_handler.bind(self._engines, self._shards, program.speed, program.dimension, self._compiled.nodes_per_root)
         self._device_observables = bool(device_observables)
         self._histogram_bins = int(histogram_bins)
+        self._equilibration_samples = int(equilibration_samples)
+        self._skipped = {}
+        self._timings = {"advance_seconds": 0.0, "output_seconds": 0.0}
         self._observables = {}
         self._template_charges = {}
         self._statistics = {}
@@ -184,6 +189,11 @@ class CudaBatchedMediator(Mediator):
         polarization_output_handler.py:76-101, bond_length_and_angle_output_handler.py:77-103."""
         output = self._input_output_handler._output_handlers_dictionary[name]
         kinds = {cls.__name__ for cls in type(output).__mro__}
+        known = {"SeparationOutputHandler", "OxygenOxygenSeparationOutputHandler", "PolarizationOutputHandler",
+                 "BondLengthAndAngleOutputHandler"}
+        if kinds & known and self._skipped.get(name, 0) < self._equilibration_samples:
+            self._skipped[name] = self._skipped.get(name, 0) + 1
+            return True
         program = self._compiled.builder.program
         length, dimension, bins = float(program.system_length), int(program.dimension), self._histogram_bins
         npr = self._compiled.nodes_per_root
@@ -291,23 +301,34 @@ class CudaBatchedMediator(Mediator):
         for handler in controls:
             if handler not in self._control_times:
                 self._control_times[handler] = handler.send_event_time()
+        import time as _time
         while True:
             handler = min(controls, key=lambda h: self._control_times[h])
             event_time = self._control_times[handler]
+            t0 = _time.perf_counter()
             self._advance_to(event_time)
-            self._event_handler_with_shortest_event_time = handler
-            names = {cls.__name__ for cls in type(handler).__mro__}
-            if "EndOfRunEventHandler" in names:
-                self._write_output(handler)
-                self._write_observables()
-                positions, roots, states = self._download()
-                self._load_chain_into_state_handler(0, positions, states, roots)
-                raise EndOfRun
-            if "DumpingEventHandler" in names:
-                self._dump(handler)
-            else:
-                self._write_output(handler)
-            self._control_times[handler] = handler.send_event_time()
+            self._timings["advance_seconds"] += _time.perf_counter() - t0
+            t0 = _time.perf_counter()
+            try:
+                self._handle_control_event(handler)
+            finally:
+                self._timings["output_seconds"] += _time.perf_counter() - t0
+
+    def _handle_control_event(self, handler):
+        """What the reference's mediate methods do for sampling, dumping and end-of-run handlers (mediator.py:377-385)."""
+        self._event_handler_with_shortest_event_time = handler
+        names = {cls.__name__ for cls in type(handler).__mro__}
+        if "EndOfRunEventHandler" in names:
+            self._write_output(handler)
+            self._write_observables()
+            positions, roots, states = self._download()
+            self._load_chain_into_state_handler(0, positions, states, roots)
+            raise EndOfRun
+        if "DumpingEventHandler" in names:
+            self._dump(handler)
+        else:
+            self._write_output(handler)
+        self._control_times[handler] = handler.send_event_time()
 
     def _advance_to(self, event_time):
         """ecmc_run(until = event_time), in launches of at most events_per_launch events per chain."""
@@ -330,6 +351,11 @@ class CudaBatchedMediator(Mediator):
                 chain = int(np.nonzero(behind)[0][0])
                 raise RuntimeError("chain {0} does not advance in time any more ({1} events per launch): "
                                    "collapsing configuration?".format(chain, self._events_per_launch))
+
+    @property
+    def timings(self):
+        """Host seconds spent advancing the chains (device launches) and in control events (sampling, dumps)."""
+        return dict(self._timings)
 
     @property
     def statistics(self):

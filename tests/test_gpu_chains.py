@@ -397,6 +397,34 @@ def test_hard_disk_dipoles_reference_trace():
         assert stats["bond_events"] > 5 and stats["capacity_errors"] == 0
 
 
+def test_hard_disk_dipoles_free_running_horizon():
+    """How long a FREE-RUNNING device chain of the shipped hard-disk dipole configuration follows the reference trace
+    (no re-seeding from the oracle): hard-disk chains are chaotic, so a last-bit difference in one collision time (the
+    device regroups the arithmetic) grows by a factor per collision until a different disk is hit. The test measures the
+    horizon -- the first event whose discrete fields differ -- and requires every event before it to agree in time within
+    the error growth that horizon implies; it documents the number rather than hiding it behind re-seeding."""
+    g = tu.load_trace("trace_hard_disk_dipoles")
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    pb = tu.dipole_builder_of(g, ProgramBuilder)
+    n = len(records)
+    with engine.Engine(pb, n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        rec, _ = eng.run_recorded(max_events=n, records_per_chain=n)
+    ours = rec[0]
+    differs = np.zeros(n, dtype=bool)
+    for field in tu.DISCRETE_FIELDS:
+        differs |= ours[field] != records[field]
+    horizon = int(np.nonzero(differs)[0][0]) if differs.any() else n
+    errors = np.abs((ours["time_q"] - records["time_q"]) + (ours["time_r"] - records["time_r"]))[:horizon]
+    print(f"free-running horizon: {horizon} of {n} events; time error after 100 events {errors[min(100, horizon - 1)]:.2e}, "
+          f"at the horizon {errors[-1]:.2e}")
+    assert horizon >= 120
+    assert np.all(errors[:120] < 1e-12 * np.maximum(1.0, records["time_q"][:120]))
+
+
 @pytest.mark.parametrize("name", tu.WATER_TRACES)
 def test_water_reference_trace_replay(name):
     """C4: the shipped water/coulomb_cell_veto_lj_inverted.ini recorded from the running reference (composite-object

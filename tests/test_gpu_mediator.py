@@ -247,6 +247,50 @@ def test_shipped_coulomb_atoms_config_matches_reference_statistics(tmp_path, con
     assert 0.2 < np.median(samples) < 0.8
 
 
+def test_coulomb_atoms_at_scale_with_device_observables_and_estimators(tmp_path):
+    """The shipped coulomb_atoms/cell_veto.ini with 4096 chains on two engines, its cell-veto bounds estimated on the device
+    (device_estimators) and its SeparationOutputHandler samples accumulated on the device (device_observables): the
+    cumulative histogram still follows ReferenceDataCoulombAtoms.dat, and sampling costs a small part of the run."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import kat_replay as kr
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    from jellyfysh.base.exceptions import EndOfRun
+    path = os.path.join(REF, "jellyfysh", "config_files", "2018_JCP_149_064113", "coulomb_atoms", "cell_veto.ini")
+    ini = open(path).read().replace("filename = config_files/",
+                                    "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+    chains, bins = 4096, 4000
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 12\ndevices = 0, 0\n"
+                      "device_observables = true\ndevice_estimators = true\nhistogram_bins = %d\n"
+                      "equilibration_samples = 10" % (chains, bins))
+    ini = ini.replace("end_of_run_time = 100000", "end_of_run_time = 40")
+    ini = ini.replace("output/2018_JCP_149_064113/coulomb_atoms/SamplesOfSeparation_CellVeto.dat", str(tmp_path / "separation.dat"))
+    mediator, setting = build_reference_graph(ini)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats, timings = mediator.statistics, mediator.timings
+        observable = mediator.observables["separation_output_handler"]
+    finally:
+        setting.reset()
+    assert stats["bound_violations"] == 0 and stats["capacity_errors"] == 0
+    per_chain = int(40 / 0.56789) - 10
+    assert observable["samples"] == per_chain and int(observable["counts"].sum()) == chains * per_chain  # two atoms: one pair
+    g = kr.load_npz("reference_cdfs")
+    x, cdf = g["coulomb_atoms_x"], g["coulomb_atoms_cdf"]
+    edges = x + 0.5 * (x[1] - x[0])
+    cumulative = np.concatenate([[0.0], np.cumsum(observable["counts"])]) / observable["counts"].sum()
+    ours = np.interp(edges, observable["edges"], cumulative)
+    distance = np.max(np.abs(ours - cdf))
+    print("KS distance", distance, "timings", timings)
+    assert distance < 1.95 / np.sqrt(chains * 10) + 1.0e-3 + 1.0 / bins, distance
+    assert timings["output_seconds"] < 0.25 * timings["advance_seconds"], timings
+
+
 def _dipole_ini(tmp_path, chains, end_of_run_time, sampling):
     ini = configs.hard_disk_dipoles_cells_ini(REF, end_of_run_time=end_of_run_time, sampling=sampling,
                                               output=str(tmp_path / "polarization.dat"))
@@ -600,6 +644,9 @@ def test_device_estimators_reproduce_the_reference_bounds():
     from jellyfysh_b200 import estimators
     setting.reset()
     hypercubic_setting.HypercubicSetting(beta=1.679, dimension=3, system_length=10.0)
+    setting.set_number_of_root_nodes(2)
+    setting.set_number_of_nodes_per_root_node(3)
+    setting.set_number_of_node_levels(2)
     try:
         coulomb = MergedImageCoulombPotential(prefactor=332.0)
         cases = [
