@@ -700,7 +700,25 @@ def run_ours(args, rank, local_rank, world):
         e2e_events += step_stats["events"]
         e2e_targets += step_stats["pair_targets"]
     barrier()
-    e2e_seconds = time.perf_counter() - t0
+    sync_e2e_seconds = time.perf_counter() - t0
+    sync_e2e_events = e2e_events
+    e2e_seconds = sync_e2e_seconds
+    pipelined = not workload.composite
+    if pipelined:
+        # the same steps through the non-blocking form of the call: ecmc_submit_from_host enqueues a step, the steps are
+        # ordered slice by slice on the device (step k + 1 reads the pinned buffer step k writes), ecmc_wait at the end.
+        # Every byte of every step still crosses the host link; only the host thread does not block between steps.
+        first = e2e_warmup + args.e2e_steps
+        charges = pinned["charges"][0].numpy() if "charges" in pinned else None
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(first, first + args.e2e_steps):
+            eng.submit_from_host(pinned["positions"][k % 2].numpy(), charges, first_stream=first_chain + (k + 1) * total_chains,
+                                 max_events=workload.events, out=pinned["positions"][(k + 1) % 2].numpy())
+        wait_stats = eng.wait()
+        barrier()
+        e2e_seconds = time.perf_counter() - t0
+        e2e_events, e2e_targets = wait_stats["events"], wait_stats["pair_targets"]
     # per chain slice: pack, start, events, unpack (ecmc_kernel_launches counts the event kernels)
     e2e_launches = 4 * (eng.kernel_launches - e2e_launches_before)
 
@@ -720,8 +738,10 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- reduce over ranks (NCCL): event counters are summed, times are the slowest rank's
     all_stats = sharding.reduce_counters(stats, device=device)
-    total_e2e_events = int(sharding.reduce_histogram([e2e_events], device=device)[0])
-    max_ms, max_e2e_seconds, _ = sharding.reduce_max([elapsed_ms, e2e_seconds, kernel_seconds], device=device).tolist()
+    total_e2e_events, total_sync_events = [int(v) for v in
+                                           sharding.reduce_histogram([e2e_events, sync_e2e_events], device=device)]
+    max_ms, max_e2e_seconds, max_sync_seconds = sharding.reduce_max([elapsed_ms, e2e_seconds, sync_e2e_seconds],
+                                                                    device=device).tolist()
     total_events = all_stats["events"]
     if rank != 0:
         if world > 1:
@@ -786,10 +806,14 @@ def run_ours(args, rank, local_rank, world):
                                       "note": "one pinned copy of the positions buffer alone on rank 0, best of 3: h2d_bytes / "
                                               "h2d rate is the floor of a step before its last slice can start"},
                     "pair_targets_per_event": e2e_targets / max(e2e_events, 1),
+                    "synchronous": {"value": total_sync_events / max_sync_seconds, "ms_per_step": 1e3 * max_sync_seconds / args.e2e_steps,
+                                    "call": "the blocking form (ecmc_run_from_host / the upload-start-run-download calls), one "
+                                            "step at a time"},
                     "call": ("ecmc_upload_positions + ecmc_upload_roots + ecmc_start + ecmc_run + ecmc_sync + "
                              "ecmc_download_positions + ecmc_download_roots per step" if workload.composite else
-                             "ecmc_run_from_host: pinned host configuration -> H2D -> cell binning -> events -> D2H, "
-                             "pipelined over chain slices on separate streams") +
+                             "ecmc_submit_from_host x steps + ecmc_wait: per step pinned host configuration -> H2D -> cell "
+                             "binning -> events -> D2H on the streams of the chain slices; the host does not block between "
+                             "steps, the device orders them slice by slice") +
                             "; step k + 1 starts from the configuration step k returned, with fresh random streams"},
             "gpu_launches": int(launches + e2e_launches),
             "roofline": roofline, "fp64": fp64, "observable": observable,

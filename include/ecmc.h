@@ -345,6 +345,14 @@ int ecmc_run_recorded(EcmcHandle *h, double until_q, double until_r, int64_t max
 int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
                        double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
                        EcmcStats *stats);
+/* The same step without blocking: ecmc_submit_from_host enqueues the copies and kernels of one step and returns,
+ * ecmc_wait blocks until every submitted step has completed and returns the counters summed over them. Steps submitted
+ * back to back are ordered chain slice by chain slice (stream order), so step k + 1 may read the buffer step k writes
+ * (positions_in of k + 1 == positions_out of k), and the host copies of one slice overlap the events of the others across
+ * steps. The host buffers must be page-locked and stay valid until ecmc_wait; no other call on the handle in between. */
+int ecmc_submit_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
+                          double until_q, double until_r, int64_t max_events_per_chain, double *positions_out);
+int ecmc_wait(EcmcHandle *h, EcmcStats *stats);
 /* ---- observables --------------------------------------------------------------------------------------------
  * Histogram of the shortest pair separations |r_ij| (all pairs i < j of every chain) into n_bins equal bins on
  * [r_min, r_max]: what SeparationOutputHandler.write prints sample by sample

@@ -65,6 +65,7 @@ struct EcmcHandle {
     bool spec_prune = true;  // ... with the force-bound pruning of pair candidates in ecmc_run / ecmc_run_from_host
     int spec_lanes = 4;      // lanes per speculated event (4: 8 events per batch, 8: 4 events per batch)
     std::string kernel_name; // ecmc_kernel_name
+    bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
     std::string error;
 };
 
@@ -922,9 +923,11 @@ ECMC_API int ecmc_run_recorded(EcmcHandle *h, double until_q, double until_r, in
 // Host buffers in, host buffers out. The chains are cut into slices; every slice runs its own
 // H2D -> pack -> start -> events -> unpack -> D2H sequence on its own stream, so the copies of one slice overlap the
 // event kernels of the others (the kernels of different slices run concurrently: a slice fills only part of the GPU).
-ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
-                                double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
-                                EcmcStats *stats) {
+// ecmc_submit_from_host only enqueues: successive steps are ordered slice by slice by their streams, so a step may read
+// the host buffer the step before it writes, and the copies of a slice overlap the events of the other slices across
+// steps as well. ecmc_wait synchronises the slices and returns the counters of all steps submitted since the last wait.
+ECMC_API int ecmc_submit_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
+                                   double until_q, double until_r, int64_t max_events_per_chain, double *positions_out) {
     if (!h || !positions_in) return fail(h, ECMC_ERR_INVALID, "null argument");
     if (h->dprog.nodes_per_root > 1 && !h->roots_uploaded)
         return fail(h, ECMC_ERR_STATE, "composite objects: ecmc_upload_roots before ecmc_run_from_host");
@@ -934,7 +937,7 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
         return fail(h, ECMC_ERR_INVALID, "neither a time limit nor an event limit: the run would not end");
     CUDA_TRY(h, cudaSetDevice(h->device));
     const DeviceProgram &d = h->dprog;
-    int max_slices = 4;
+    int max_slices = 8;
     if (const char *env = std::getenv("ECMC_HOST_SLICES")) max_slices = std::max(1, std::atoi(env));
     const int slices = std::max(1, std::min(max_slices, h->n_chains / 256));
     while ((int)h->slice_streams.size() < slices) {
@@ -942,7 +945,7 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
         CUDA_TRY(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         h->slice_streams.push_back(s);
     }
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // earlier work on the handle's stream comes first
+    if (!h->slices_busy) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // earlier work on the handle's stream comes first
     RunArgs args;
     args.until_q = until_q;
     args.until_r = until_r;
@@ -991,9 +994,25 @@ ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const
         }
         first += count;
     }
-    for (int k = 0; k < slices; k++) CUDA_TRY(h, cudaStreamSynchronize(h->slice_streams[k]));
+    h->slices_busy = true;
     h->started = true;
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_wait(EcmcHandle *h, EcmcStats *stats) {
+    if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (cudaStream_t s : h->slice_streams) CUDA_TRY(h, cudaStreamSynchronize(s));
+    h->slices_busy = false;
     return ecmc_sync(h, stats);
+}
+
+ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
+                                double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
+                                EcmcStats *stats) {
+    const int rc = ecmc_submit_from_host(h, positions_in, charges, first_stream, until_q, until_r, max_events_per_chain,
+                                         positions_out);
+    return rc ? rc : ecmc_wait(h, stats);
 }
 
 ECMC_API int ecmc_separation_histogram(EcmcHandle *h, int32_t n_bins, double r_min, double r_max, uint64_t *histogram) {

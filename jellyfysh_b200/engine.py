@@ -59,6 +59,8 @@ def library() -> C.CDLL:
     lib.ecmc_sync.argtypes = [vp, stats]
     lib.ecmc_run_recorded.argtypes = [vp, d, d, i64, vp, i32, stats]
     lib.ecmc_run_from_host.argtypes = [vp, vp, vp, u32, d, d, i64, vp, stats]
+    lib.ecmc_submit_from_host.argtypes = [vp, vp, vp, u32, d, d, i64, vp]
+    lib.ecmc_wait.argtypes = [vp, stats]
     lib.ecmc_separation_histogram.argtypes = [vp, i32, d, d, vp]
     lib.ecmc_separation_histogram_subset.argtypes = [vp, i32, i32, i32, d, d, vp]
     lib.ecmc_polarization.argtypes = [vp, vp, vp]
@@ -229,6 +231,24 @@ class Engine:
         self._check(self._lib.ecmc_run_from_host(self._h, _ptr(pos), _ptr(ch), int(first_stream), float(until[0]),
                                                  float(until[1]), int(max_events), _ptr(out), C.byref(stats)))
         return out, stats.as_dict()
+
+    def submit_from_host(self, positions, charges=None, first_stream=0, until=(INF, INF), max_events=0, out=None):
+        """ecmc_submit_from_host: the step of run_from_host, enqueued only. `positions`, `charges` and `out` must be
+        page-locked C-contiguous float64 arrays of the engine's shape (they are used in place, nothing is copied here) and
+        stay alive until wait(); steps submitted back to back may chain through their buffers (out of one = positions of
+        the next)."""
+        for array, shape in ((positions, (self.n_chains, self.n_particles, self.dimension)),
+                             (charges, (self.n_chains, self.n_particles)), (out, (self.n_chains, self.n_particles, self.dimension))):
+            if array is not None and (array.dtype != np.float64 or not array.flags["C_CONTIGUOUS"] or array.shape != shape):
+                raise ValueError("submit_from_host needs C-contiguous float64 arrays of shape {0}".format(shape))
+        self._check(self._lib.ecmc_submit_from_host(self._h, _ptr(positions), _ptr(charges), int(first_stream),
+                                                    float(until[0]), float(until[1]), int(max_events), _ptr(out)))
+
+    def wait(self):
+        """ecmc_wait: block until all submitted steps are complete; their summed counters."""
+        stats = abi.EcmcStats()
+        self._check(self._lib.ecmc_wait(self._h, C.byref(stats)))
+        return stats.as_dict()
 
     def separation_histogram(self, n_bins, r_min, r_max, out=None, first=0, stride=1):
         """Add the pair-separation counts of the current configuration of all chains to `out` (uint64[n_bins]);

@@ -28,8 +28,11 @@ class _Region:
 
     def __init__(self, estimator, device):
         from jellyfysh import setting
+        from jellyfysh.setting import hypercubic_setting
+        if not hypercubic_setting.initialized():
+            raise compiler._configuration_error("device estimators need the hypercubic setting")
         self.dimension = int(setting.dimension)
-        self.length = float(setting.system_length)
+        self.length = float(hypercubic_setting.system_length)
         self.periodic = estimator._correct_separation.__name__ != "<lambda>"
         self.record = compiler.potential_descriptor(estimator._potential)
         self.device = device

@@ -23,7 +23,8 @@ def _box(system_length, dimension):
         return float(system_length), int(dimension)
     try:  # the reference's global setting (jellyfysh/setting/__init__.py), if it is there
         from jellyfysh import setting
-        return (float(setting.system_length) if system_length is None else float(system_length),
+        from jellyfysh.setting import hypercubic_setting
+        return (float(hypercubic_setting.system_length) if system_length is None else float(system_length),
                 int(setting.dimension) if dimension is None else int(dimension))
     except Exception as error:  # noqa: BLE001
         raise ValueError("system_length and dimension are needed (no initialised jellyfysh.setting)") from error

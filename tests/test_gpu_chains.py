@@ -544,6 +544,33 @@ def test_split_launches_equal_one_launch(oracle):
         assert two.kernel_launches == 3 and two.kernel_seconds > 0.0
 
 
+def test_submitted_host_steps_equal_blocking_host_steps(oracle):
+    """ecmc_submit_from_host x 3 + ecmc_wait (steps chained through two host buffers, ordered on the device slice by slice)
+    against three blocking ecmc_run_from_host calls: the same configurations, the same counters."""
+    pb, positions = _lj_batch(oracle, n_chains=600, seed=21)
+    buffers = [np.ascontiguousarray(positions.copy()), np.empty_like(positions)]
+    try:
+        import torch
+        pinned = [torch.from_numpy(b).pin_memory() for b in buffers]  # page-locked: the copies really are asynchronous
+        buffers = [p.numpy() for p in pinned]
+    except ImportError:
+        pass
+    with engine.Engine(pb, n_chains=600) as blocking, engine.Engine(pb, n_chains=600) as queued:
+        current, totals = positions, {}
+        for k in range(3):
+            current, stats = blocking.run_from_host(current, first_stream=1000 * k, max_events=150)
+            for key, value in stats.items():
+                totals[key] = totals.get(key, 0) + value
+        for k in range(3):
+            queued.submit_from_host(buffers[k % 2], first_stream=1000 * k, max_events=150, out=buffers[(k + 1) % 2])
+        stats = queued.wait()
+        assert np.array_equal(buffers[1], current)
+        assert {k: v for k, v in stats.items() if k != "candidates"} == {k: v for k, v in totals.items() if k != "candidates"}
+        assert np.array_equal(queued.download_positions(), blocking.download_positions())
+        with pytest.raises(ValueError):
+            queued.submit_from_host(positions[:10], max_events=5, out=buffers[0])
+
+
 def test_pruned_launches_reach_the_same_state(oracle):
     """The kernel instantiations with and without event records must commit the same events: identical positions, cells
     and chain states bit for bit, the same event counts. (Launches without records skip pair candidates that provably
