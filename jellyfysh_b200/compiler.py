@@ -157,6 +157,14 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
         if len(internal_states) != 1 or "SingleActiveCellOccupancy" not in _class_names(internal_states[0]):
             raise _configuration_error("at most one internal state, a SingleActiveCellOccupancy, is supported")
         occupancy = internal_states[0]
+        # single_active_cell_occupancy.py:62-92: with `charge = <name>` only units with that charge unequal zero are stored
+        # (and take part as active units). The device bins every unit: a configuration that relies on the filter is refused
+        # instead of being run with neutral units in the cells.
+        probe = _ProbeUnit()
+        occupancy._is_relevant_unit(probe)
+        if probe.charge.names:
+            raise _configuration_error("SingleActiveCellOccupancy with a charge filter (charge = {0}) is not supported"
+                                       .format(probe.charge.names[0]))
         cells = occupancy.cells
         if "CuboidPeriodicCells" not in _class_names(cells):
             raise _configuration_error("cells must be CuboidPeriodicCells")

@@ -594,7 +594,8 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
                     // expovariate(beta) / (total rate * charge factor * speed): the reciprocal of the table's part is
                     // precomputed, chargeless handlers never divide
                     dt = exponential * w->inv_total_rate_speed;
-                    if (veto_use_charge) dt = exponential / (w->total_rate * charge_factor * speed);
+                    // (a neutral active unit has no cell-veto events: a zero rate is an infinite time, not -inf)
+                    if (veto_use_charge) dt = charge_factor > 0.0 ? exponential / (w->total_rate * charge_factor * speed) : INFINITY;
                     kind = ECMC_EVENT_CELL_VETO;
                     seq = special_seq;
                 } else if (is_boundary) {

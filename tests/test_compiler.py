@@ -350,6 +350,13 @@ def test_unsupported_graphs_are_rejected(lj_graph):
     occupancy._cell_level = 2
     with pytest.raises(ConfigurationError):
         compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())
+    occupancy._cell_level = 1
+    compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())
+    # a cell occupancy that stores only units with a non-zero charge (single_active_cell_occupancy.py:92): the device
+    # would bin the neutral units too, so the configuration is refused
+    occupancy._is_relevant_unit = lambda unit: unit.charge["electric_charge"] != 0
+    with pytest.raises(ConfigurationError, match="charge filter"):
+        compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())
 
 
 def test_shipped_pdb_start_configuration_through_the_reference_input_handler():
