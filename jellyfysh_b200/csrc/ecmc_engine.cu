@@ -13,6 +13,7 @@
 #include "ecmc_kernels.cuh"
 #include "ecmc_molecules.cuh"
 #include "ecmc_spec.cuh"
+#include "ecmc_spec_cta.cuh"
 
 using namespace ecmc;
 
@@ -64,6 +65,7 @@ struct EcmcHandle {
     bool spec = true;        // Lennard-Jones / cell-veto programs: lj_spec_kernel (ecmc_set_option)
     bool spec_prune = true;  // ... with the force-bound pruning of pair candidates in ecmc_run / ecmc_run_from_host
     int spec_lanes = 4;      // lanes per speculated event (4: 8 events per batch, 8: 4 events per batch)
+    bool chain_blocks = true; // few chains: lj_chain_kernel, one CTA of four warps per chain (ecmc_spec_cta.cuh)
     std::string kernel_name; // ecmc_kernel_name
     bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
     std::string error;
@@ -517,7 +519,10 @@ struct SpecLaunch {
     EventKernel kernel = nullptr;
     size_t shared_bytes = 0;
     int capacity = 0;
+    bool chain_blocks = false;  // lj_chain_kernel: one CTA of kChainWarps warps per chain
 };
+// lj_chain_kernel while every chain can have an SM of its own
+constexpr int kChainKernelMaxChains = 148;
 
 template <bool RECORD, bool PRUNE>
 EventKernel pick_spec_lanes(int lanes) {
@@ -541,6 +546,14 @@ bool pick_spec(const EcmcHandle *h, bool record, SpecLaunch *out) {
     if (bytes > 100 * 1024) return false;  // two CTAs per SM
     out->capacity = capacity;
     out->shared_bytes = bytes;
+    // few chains (the single large chain C5): one CTA of four warps per chain, 32 events per batch
+    out->chain_blocks = h->chain_blocks && h->n_chains <= kChainKernelMaxChains;
+    if (out->chain_blocks) {
+        out->shared_bytes = (size_t)capacity * ((prune ? 3 : 2) + 1) * sizeof(double);
+        if (record) out->kernel = lj_chain_kernel<true, false>;
+        else out->kernel = prune ? lj_chain_kernel<false, true> : lj_chain_kernel<false, false>;
+        return true;
+    }
     if (record) out->kernel = pick_spec_lanes<true, false>(h->spec_lanes);
     else out->kernel = prune ? pick_spec_lanes<false, true>(h->spec_lanes) : pick_spec_lanes<false, false>(h->spec_lanes);
     return true;
@@ -623,7 +636,10 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         if (pick_spec(h, d_records != nullptr, &spec)) {
             args.list_capacity = spec.capacity;
             CUDA_TRY(h, cudaFuncSetAttribute(spec.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec.shared_bytes));
-            spec.kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, h->stream>>>(h->dprog, h->state, args);
+            if (spec.chain_blocks)
+                spec.kernel<<<h->n_chains, kChainWarps * 32, spec.shared_bytes, h->stream>>>(h->dprog, h->state, args);
+            else
+                spec.kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, h->stream>>>(h->dprog, h->state, args);
         } else {
             const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
             kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
@@ -678,6 +694,7 @@ ECMC_API int ecmc_create(const EcmcProgram *program, int device, int n_chains, E
     if (const char *env = std::getenv("ECMC_SPEC")) h->spec = std::atoi(env) != 0;
     if (const char *env = std::getenv("ECMC_SPEC_PRUNE")) h->spec_prune = std::atoi(env) != 0;
     if (const char *env = std::getenv("ECMC_SPEC_LANES")) h->spec_lanes = std::atoi(env) == 8 ? 8 : 4;
+    if (const char *env = std::getenv("ECMC_CHAIN_BLOCKS")) h->chain_blocks = std::atoi(env) != 0;
     int rc = ECMC_OK;
     do {
         if ((err = cudaSetDevice(device)) != cudaSuccess) { rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
@@ -983,7 +1000,8 @@ ECMC_API int ecmc_submit_from_host(EcmcHandle *h, const double *positions_in, co
         const int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, s>>>(
             d, slice, nullptr, first_stream, h->program.initial_active, h->program.initial_direction, h->d_stats);
-        kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, s>>>(d, slice, args);
+        if (spec.chain_blocks) kernel<<<count, kChainWarps * 32, spec.shared_bytes, s>>>(d, slice, args);
+        else kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, s>>>(d, slice, args);
         CUDA_TRY(h, cudaGetLastError());
         h->kernel_launches++;
         if (positions_out) {
@@ -1112,6 +1130,7 @@ ECMC_API int ecmc_set_option(EcmcHandle *h, int option, int value) {
     switch (option) {
     case ECMC_OPTION_BATCHED_EVENTS: h->spec = value != 0; return ECMC_OK;
     case ECMC_OPTION_PRUNE_CANDIDATES: h->spec_prune = value != 0; return ECMC_OK;
+    case ECMC_OPTION_CHAIN_BLOCKS: h->chain_blocks = value != 0; return ECMC_OK;
     case ECMC_OPTION_LANES_PER_EVENT:
         if (value != 4 && value != 8) return fail(h, ECMC_ERR_INVALID, "lanes per event: 4 or 8");
         h->spec_lanes = value;
@@ -1145,6 +1164,9 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
     SpecLaunch spec;
     if (h->molecules) {
         h->kernel_name = "molecule_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto + ", record=" + std::to_string(record != 0) + ">";
+    } else if (pick_spec(h, record != 0, &spec) && spec.chain_blocks) {
+        h->kernel_name = "lj_chain_kernel<record=" + std::to_string(record != 0) + ", prune=" +
+                         std::to_string(h->spec_prune && !record) + ", warps per chain=" + std::to_string(kChainWarps) + ">";
     } else if (pick_spec(h, record != 0, &spec)) {
         h->kernel_name = "lj_spec_kernel<record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", lanes=" + std::to_string(h->spec_lanes) + ", warps=" +

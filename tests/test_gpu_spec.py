@@ -16,7 +16,8 @@ from jellyfysh_b200.engine import Engine
 
 pytestmark = pytest.mark.gpu
 
-BATCHED, PRUNE, LANES = Engine.OPTION_BATCHED_EVENTS, Engine.OPTION_PRUNE_CANDIDATES, Engine.OPTION_LANES_PER_EVENT
+BATCHED, PRUNE, LANES, BLOCKS = (Engine.OPTION_BATCHED_EVENTS, Engine.OPTION_PRUNE_CANDIDATES, Engine.OPTION_LANES_PER_EVENT,
+                                 Engine.OPTION_CHAIN_BLOCKS)
 
 
 def _program(n=216, cells=7, max_surplus=64, chain_time=2.5):
@@ -28,7 +29,7 @@ def _program(n=216, cells=7, max_surplus=64, chain_time=2.5):
 def _started(builder, positions, first_stream, **options):
     eng = engine.Engine(builder, n_chains=len(positions))
     for option, value in options.items():
-        eng.set_option({"batched": BATCHED, "prune": PRUNE, "lanes": LANES}[option], value)
+        eng.set_option({"batched": BATCHED, "prune": PRUNE, "lanes": LANES, "blocks": BLOCKS}[option], value)
     eng.upload_positions(positions)
     eng.start(first_stream=first_stream)
     return eng
@@ -47,12 +48,16 @@ def _assert_same_state(one, two, tag):
     assert a[3] == b[3], tag
 
 
-@pytest.mark.parametrize("lanes", [4, 8])
-def test_batched_kernel_commits_the_events_of_the_single_event_kernel(lanes):
+@pytest.mark.parametrize("lanes,blocks", [(4, 0), (8, 0), (4, 1)])
+def test_batched_kernel_commits_the_events_of_the_single_event_kernel(lanes, blocks):
+    """blocks = 1: lj_chain_kernel (one CTA of four warps per chain, 32 events per batch; engines of at most 148 chains),
+    blocks = 0: lj_spec_kernel (one warp per chain, 8 or 4 events per batch)."""
     n_chains, n, cells, events = 96, 216, 7, 3000
     builder, length = _program(n, cells)
     positions = workloads.lattice_start(n_chains, n, cells, length, jitter=0.15)
-    with _started(builder, positions, 11, batched=0) as single, _started(builder, positions, 11, lanes=lanes) as batched:
+    with _started(builder, positions, 11, batched=0) as single, \
+            _started(builder, positions, 11, lanes=lanes, blocks=blocks) as batched:
+        assert ("lj_chain_kernel" if blocks else "lj_spec_kernel") in batched.kernel_name(record=True)
         ref, ref_stats = single.run_recorded(max_events=events, records_per_chain=events)
         rec, stats = batched.run_recorded(max_events=events, records_per_chain=events)
         assert stats == ref_stats
@@ -66,12 +71,15 @@ def test_batched_kernel_commits_the_events_of_the_single_event_kernel(lanes):
         _assert_same_state(single, batched, "after the recorded launch")
 
 
-def test_pruning_does_not_change_the_chains():
+@pytest.mark.parametrize("blocks", [0, 1])
+def test_pruning_does_not_change_the_chains(blocks):
     n_chains, n, cells = 128, 216, 7
     builder, length = _program(n, cells)
     positions = workloads.lattice_start(n_chains, n, cells, length, jitter=0.15)
-    with _started(builder, positions, 500, prune=0) as full, _started(builder, positions, 500, prune=1) as pruned, \
+    with _started(builder, positions, 500, prune=0, blocks=blocks) as full, \
+            _started(builder, positions, 500, prune=1, blocks=blocks) as pruned, \
             _started(builder, positions, 500, batched=0) as single:
+        assert ("lj_chain_kernel" if blocks else "lj_spec_kernel") in pruned.kernel_name()
         totals = []
         for eng in (full, pruned, single):
             for events in (1, 2, 3, 5, 8, 13, 968, 4000):
@@ -86,11 +94,13 @@ def test_pruning_does_not_change_the_chains():
         assert totals[1]["candidates"] < totals[0]["candidates"]  # the pruned run evaluated fewer candidates
 
 
-def test_time_limits_cut_batches_like_the_single_event_kernel():
+@pytest.mark.parametrize("blocks", [0, 1])
+def test_time_limits_cut_batches_like_the_single_event_kernel(blocks):
     n_chains, n, cells = 64, 216, 7
     builder, length = _program(n, cells, chain_time=0.7)
     positions = workloads.lattice_start(n_chains, n, cells, length, jitter=0.15)
-    with _started(builder, positions, 40, batched=0) as single, _started(builder, positions, 40, prune=1) as batched:
+    with _started(builder, positions, 40, batched=0) as single, \
+            _started(builder, positions, 40, prune=1, blocks=blocks) as batched:
         for eng in (single, batched):
             for k in range(1, 40):
                 eng.run(until=(float(k // 8), (k % 8) / 8.0))  # sampling times every 1/8
@@ -118,3 +128,20 @@ def test_pruned_bench_program_against_the_oracle(oracle):
             eng.sync()
         _assert_same_state(pruned, single, "30 launches of 1024 events")
         _compare_stretch(oracle, builder, pruned, (0, 17, 1023), 1500, None, length, "C2 pruned, after 30k events")
+
+
+def test_single_large_chain_in_a_block_against_the_oracle(oracle):
+    """C5 through lj_chain_kernel (the default for one chain): 60 000 pruned events of the chain of 65536 particles, then
+    2000 events against an oracle chain seeded from the device, and the whole trajectory against the one-warp kernel."""
+    from test_gpu_full_size_parity import _compare_stretch
+    n, cells = 65536, 48
+    builder, length = workloads.lennard_jones(n_particles=n, cells_per_side=cells)
+    positions = workloads.lattice_start(1, n, cells, length)
+    with _started(builder, positions, 0) as blocked, _started(builder, positions, 0, blocks=0) as warped:
+        assert "lj_chain_kernel" in blocked.kernel_name() and "lj_spec_kernel" in warped.kernel_name()
+        for eng in (blocked, warped):
+            for events in (7, 1000, 58993):
+                eng.run(max_events=events)
+            eng.sync()
+        _assert_same_state(blocked, warped, "60 000 events of the single chain")
+        _compare_stretch(oracle, builder, blocked, (0,), 2000, None, length, "C5 in a block, after 60k events")
