@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ECMC_ABI_VERSION 3
+#define ECMC_ABI_VERSION 4
 #define ECMC_MAX_BONDS 4
 #define ECMC_MAX_DIM 3
 
@@ -213,6 +213,17 @@ typedef struct EcmcProgram {
     EcmcPotential bending_potential;
     double bending_offset;
     double bending_max_displacement;
+    /* ---- general velocities: two-dimensional composite point objects without a cell system whose end-of-chain handler
+     * is SingleIndependentActiveSequentialDirectionEndOfChainEventHandler
+     * (single_independent_active_sequential_direction_end_of_chain_event_handler.py:64-122, the shipped
+     * hard_disk_dipoles/hard_disk_dipoles.ini): every end of chain rotates the velocity by delta_phi,
+     * (vx, vy) -> (vx cos - vy sin, vx sin + vy cos) with eoc_cos = cos(delta_phi), eoc_sin = sin(delta_phi) as the
+     * handler computes them. The pair factors of such a program are the bonds (inside an object) and the inter_factors
+     * (leaf a of the active object against leaf b of every other object), all with hard potentials; the velocity of
+     * the active leaf and of its root unit live in EcmcChainState.velocity / root_velocity. */
+    int32_t eoc_sequential;
+    int32_t reserved2;
+    double eoc_cos, eoc_sin;
 } EcmcProgram;
 
 /* ---- per-chain lifting state ("who is active, where is the clock") ------------------------------------
@@ -249,6 +260,13 @@ typedef struct EcmcChainState {
     double kept_rate;
     double kept_position, kept_root_position;
     double kept_stamp_q, kept_stamp_r;
+    /* Programs with general velocities (EcmcProgram.eoc_sequential): velocity of the active leaf unit and of its root
+     * unit -- the root's is kept as the reference accumulates it (velocity changes times the weight,
+     * event_handler/abstracts/abstracts.py:165-227), not recomputed from the leaf's --, and the second coordinates of
+     * the in-state of a kept candidate (pending_position / pending_root_position hold the first ones). */
+    double velocity[2];
+    double root_velocity[2];
+    double pending_position_y, pending_root_position_y;
 } EcmcChainState;
 
 enum EcmcEventKind {

@@ -1,7 +1,7 @@
 """ctypes mirror of include/ecmc.h (the C ABI of libecmc_b200.so). Plain data only, no computation."""
 import ctypes as C
 
-ECMC_ABI_VERSION = 3
+ECMC_ABI_VERSION = 4
 ECMC_MAX_DIM = 3
 ECMC_MAX_BONDS = 4
 ECMC_MAX_INTER_FACTORS = 4
@@ -111,7 +111,8 @@ class EcmcProgram(C.Structure):
                 ("bending_enabled", C.c_int32), ("bending_lifting", C.c_int32),
                 ("bending_children", C.c_int32 * 3), ("bending_separations", C.c_int32 * 4), ("boundary_keeps_factors", C.c_int32),
                 ("bending_potential", EcmcPotential), ("bending_offset", C.c_double),
-                ("bending_max_displacement", C.c_double)]
+                ("bending_max_displacement", C.c_double),
+                ("eoc_sequential", C.c_int32), ("reserved2", C.c_int32), ("eoc_cos", C.c_double), ("eoc_sin", C.c_double)]
 
 
 class EcmcChainState(C.Structure):
@@ -127,7 +128,9 @@ class EcmcChainState(C.Structure):
                 ("pending_root_position", C.c_double),
                 ("kept_kind", C.c_int32), ("kept_target", C.c_int32), ("kept_q", C.c_double), ("kept_r", C.c_double),
                 ("kept_rate", C.c_double), ("kept_position", C.c_double), ("kept_root_position", C.c_double),
-                ("kept_stamp_q", C.c_double), ("kept_stamp_r", C.c_double)]
+                ("kept_stamp_q", C.c_double), ("kept_stamp_r", C.c_double),
+                ("velocity", C.c_double * 2), ("root_velocity", C.c_double * 2),
+                ("pending_position_y", C.c_double), ("pending_root_position_y", C.c_double)]
 
 
 class EcmcEventRecord(C.Structure):
@@ -167,8 +170,10 @@ def chain_state_dtype():
                      ("pending_root_position", "<f8"),
                      ("kept_kind", "<i4"), ("kept_target", "<i4"), ("kept_q", "<f8"), ("kept_r", "<f8"),
                      ("kept_rate", "<f8"), ("kept_position", "<f8"), ("kept_root_position", "<f8"),
-                     ("kept_stamp_q", "<f8"), ("kept_stamp_r", "<f8")])
+                     ("kept_stamp_q", "<f8"), ("kept_stamp_r", "<f8"),
+                     ("velocity", "<f8", (2,)), ("root_velocity", "<f8", (2,)),
+                     ("pending_position_y", "<f8"), ("pending_root_position_y", "<f8")])
 
 
 assert C.sizeof(EcmcEventRecord) == 72
-assert C.sizeof(EcmcChainState) == 192
+assert C.sizeof(EcmcChainState) == 240

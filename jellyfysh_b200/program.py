@@ -82,6 +82,26 @@ class ProgramBuilder:
             p.bond_potential = bond_potential
         return self
 
+    def set_sequential_direction(self, delta_phi_degree, sphere_potential, sphere_factors):
+        """General velocities (two-dimensional composite point objects without a cell system): the end-of-chain handler
+        SingleIndependentActiveSequentialDirectionEndOfChainEventHandler rotates the velocity by delta_phi_degree;
+        sphere_factors = (child a, child b) leaf factors between different objects with sphere_potential (hard spheres)."""
+        import math
+        p = self.program
+        if p.dimension != 2 or not p.no_cells:
+            raise ValueError("general velocities: two dimensions, no cell system")
+        delta_phi = delta_phi_degree * math.pi / 180.0  # the handler's own expressions (:97-99)
+        p.eoc_sequential = 1
+        p.eoc_cos = math.cos(delta_phi)
+        p.eoc_sin = math.sin(delta_phi)
+        if len(sphere_factors) > abi.ECMC_MAX_INTER_FACTORS:
+            raise ValueError("too many inter-object factors")
+        p.n_inter_factors = len(sphere_factors)
+        for i, (a, b) in enumerate(sphere_factors):
+            p.inter_factors[i][0], p.inter_factors[i][1] = a, b
+        p.inter_potential = sphere_potential
+        return self
+
     def set_molecules(self, lifting, inter_factors=(), inter_potential=None, bending=None, boundary_keeps_factors=True):
         """Composite objects in root-level cells (water): the pair handler set by set_pair(PAIR_TWO_COMPOSITE_...)
         and the cell veto act on whole objects with the given lifting scheme; inter_factors = (child a, child b) leaf

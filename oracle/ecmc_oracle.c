@@ -1042,8 +1042,11 @@ ORC_API OrcChain *orc_chain_create(const EcmcProgram *prog) {
     if (pot_make(&c->bending_pot, &prog->bending_potential, c->L)) goto fail;
     c->npr = prog->nodes_per_root > 1 ? prog->nodes_per_root : 1;
     c->molecules = prog->cell_level == 1 && c->npr > 1;
-    if ((prog->pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || prog->n_inter_factors > 0 ||
-         prog->bending_enabled) && !c->molecules) goto fail;
+    if ((prog->pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || prog->bending_enabled ||
+         (prog->n_inter_factors > 0 && !prog->eoc_sequential)) && !c->molecules) goto fail;
+    /* general velocities: two-dimensional composite point objects without a cell system, hard potentials only */
+    if (prog->eoc_sequential && (c->D != 2 || !prog->no_cells || c->npr < 2 || c->molecules ||
+                                 prog->pair_handler != ECMC_PAIR_NONE || prog->veto_enabled)) goto fail;
     if (c->molecules && (c->D != 3 || c->npr > 4 || prog->max_occupants != 1)) goto fail;
     if (c->N % c->npr || prog->n_bonds < 0 || prog->n_bonds > ECMC_MAX_BONDS) goto fail;
     if (prog->n_bonds > 0 && c->npr == 1) goto fail;
@@ -1194,6 +1197,16 @@ ORC_API void orc_chain_start(OrcChain *c, uint32_t stream) {
     }
     schedule_end_of_chain(c);
     c->st.pending_kind = ECMC_EVENT_NONE;
+    if (c->prog.eoc_sequential) {
+        /* InitialChainStartOfRunEventHandler (initial_chain_start_of_run_event_handler.py:92-131): the active leaf gets
+         * speed along the initial direction, its root unit that velocity times the leaf's weight
+         * (_register_velocity_change_leaf_cnode, abstracts.py:165-190) */
+        double weight = 1.0 / c->npr;
+        for (int d = 0; d < 2; d++) {
+            c->st.velocity[d] = d == c->prog.initial_direction ? c->prog.speed : 0.0;
+            c->st.root_velocity[d] = c->st.velocity[d] * weight;
+        }
+    }
     c->started = 1;
     memset(&c->stats, 0, sizeof(c->stats));
 }
@@ -1326,6 +1339,16 @@ static void time_slice_active(OrcChain *c, otime event_time) {
     double *pa = c->pos + c->st.active * c->D;
     otime stamp = {c->st.time_q, c->st.time_r};
     double dt = time_sub(event_time, stamp);
+    if (c->prog.eoc_sequential) {
+        /* general velocities: every component of the leaf and of its root unit, each with its own velocity */
+        double *pr = c->root_pos + (c->st.active / c->npr) * c->D;
+        for (int d = 0; d < c->D; d++) {
+            pa[d] = correct_position_entry(pa[d] + c->st.velocity[d] * dt, c->L);
+            pr[d] = correct_position_entry(pr[d] + c->st.root_velocity[d] * dt, c->L);
+        }
+        c->st.time_q = event_time.q; c->st.time_r = event_time.r;
+        return;
+    }
     for (int d = 0; d < c->D; d++) {
         double v = d == c->st.direction ? c->prog.speed : 0.0;
         pa[d] = correct_position_entry(pa[d] + v * dt, c->L);
@@ -1934,8 +1957,159 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
 
 /* One iteration of SingleProcessMediator.run (single_process_mediator.py:91-156) restricted to device
  * events. Returns 0 if the next event time is not < until (nothing committed, candidate kept pending). */
+/* ---- general velocities: two-dimensional hard disks tethered into dipoles, no cell system, the velocity rotated at
+ * every end of chain (hard_disk_dipoles/hard_disk_dipoles.ini). Candidates of an event: the hard-sphere factor with
+ * every leaf of every other object (factor type map entries between different objects, factor_type_maps.py:333-347,
+ * recorded as ECMC_EVENT_FACTOR_PAIR), the tether with the partner leaf (ECMC_EVENT_BOND), the end of chain. Hard
+ * potentials draw no random numbers (TwoLeafUnitEventHandler.send_event_time, two_leaf_unit_event_handler.py:105-138
+ * with potential_change_required False) and always lift. */
+static candidate disk_candidate(OrcChain *c, int kind, const opotential *pot, int target) {
+    candidate cand;
+    cand.kind = kind; cand.target = target; cand.target_cell = -1; cand.rate = 0.0;
+    double sep[ECMC_MAX_DIM] = {0, 0, 0};
+    separation_vector(c->pos + c->st.active * c->D, c->pos + target * c->D, c->D, c->L, sep);
+    double velocity[ECMC_MAX_DIM] = {c->st.velocity[0], c->st.velocity[1], 0.0};
+    double dt = pot->kind == ECMC_POT_HARD_SPHERE ? hs_displacement(pot->p0, velocity, sep, c->D)
+                                                  : hd_displacement(pot->p0, pot->p1, velocity, sep, c->D);
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, dt);
+    return cand;
+}
+
+/* The velocity of a root unit after the velocity changes of an out-state, as _register_velocity_change_leaf_cnode and
+ * _commit_sub_tree_non_leaf_velocity_change accumulate them (abstracts.py:165-227): `change` is the sum over the leaves
+ * of (leaf change x leaf weight) in registration order; a unit without velocity takes the change, one with velocity adds
+ * it and loses its velocity when every component is below 1e-13. Returns 0 if the unit ends without velocity. */
+static int disk_root_velocity(double *velocity, int had_velocity, const double *change) {
+    if (!had_velocity) { velocity[0] = change[0]; velocity[1] = change[1]; return 1; }
+    velocity[0] += change[0]; velocity[1] += change[1];
+    return !(fabs(velocity[0]) < 1.0e-13 && fabs(velocity[1]) < 1.0e-13);
+}
+
+static int disk_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
+    const int npr = c->npr, D = c->D;
+    candidate best;
+    int n_cand = 0;
+    best.kind = ECMC_EVENT_NONE; best.t.q = ORC_INF; best.t.r = ORC_INF; best.target = -1; best.target_cell = -1;
+    best.rate = 0.0;
+    int was_pending = c->st.pending_kind != ECMC_EVENT_NONE;
+    if (was_pending) {
+        best.kind = c->st.pending_kind;
+        best.t.q = c->st.pending_q; best.t.r = c->st.pending_r;
+        best.target = c->st.pending_target;
+    } else {
+        const int active_root = c->st.active / npr, active_child = c->st.active % npr;
+        /* factors between different objects: (child a, child b) entries with a = the active child */
+        for (int root = 0; root < c->N / npr; root++) {
+            if (root == active_root) continue;
+            for (int f = 0; f < c->prog.n_inter_factors; f++) {
+                if (c->prog.inter_factors[f][0] != active_child) continue;
+                candidate cand = disk_candidate(c, ECMC_EVENT_FACTOR_PAIR, &c->inter_pot, root * npr + c->prog.inter_factors[f][1]);
+                if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
+            }
+        }
+        for (int b = 0; b < c->prog.n_bonds; b++) {
+            int partner = -1;
+            if (c->prog.bonds[b][0] == active_child) partner = c->prog.bonds[b][1];
+            else if (c->prog.bonds[b][1] == active_child) partner = c->prog.bonds[b][0];
+            if (partner < 0) continue;
+            candidate cand = disk_candidate(c, ECMC_EVENT_BOND, &c->bond_pot, active_root * npr + partner);
+            if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
+        }
+    }
+    {
+        candidate interaction = best;
+        candidate cand;
+        cand.kind = ECMC_EVENT_END_OF_CHAIN; cand.target = c->st.eoc_next_active; cand.target_cell = -1; cand.rate = 0.0;
+        cand.t.q = c->st.eoc_q; cand.t.r = c->st.eoc_r;
+        n_cand++;
+        if (lt_candidate(&cand, &best)) best = cand;
+        if (!time_lt(best.t, until)) {
+            c->st.pending_kind = interaction.kind;
+            c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
+            c->st.pending_rate = 0.0;
+            c->st.pending_target = interaction.target;
+            if (!was_pending) {
+                const double *pa = c->pos + c->st.active * D, *pr = c->root_pos + (c->st.active / npr) * D;
+                c->st.pending_position = pa[0]; c->st.pending_position_y = pa[1];
+                c->st.pending_root_position = pr[0]; c->st.pending_root_position_y = pr[1];
+                c->st.pending_stamp_q = c->st.time_q;
+                c->st.pending_stamp_r = c->st.time_r;
+            }
+            return 0;
+        }
+    }
+    c->st.pending_kind = ECMC_EVENT_NONE;
+    if (was_pending && best.kind != ECMC_EVENT_END_OF_CHAIN) {
+        double *pa = c->pos + c->st.active * D, *pr = c->root_pos + (c->st.active / npr) * D;
+        pa[0] = c->st.pending_position; pa[1] = c->st.pending_position_y;
+        pr[0] = c->st.pending_root_position; pr[1] = c->st.pending_root_position_y;
+        c->st.time_q = c->st.pending_stamp_q;
+        c->st.time_r = c->st.pending_stamp_r;
+    }
+    const int old_active = c->st.active;
+    int new_active = old_active;
+    time_slice_active(c, best.t);
+    const double old_velocity[2] = {c->st.velocity[0], c->st.velocity[1]};
+    double new_velocity[2] = {old_velocity[0], old_velocity[1]};
+    switch (best.kind) {
+    case ECMC_EVENT_FACTOR_PAIR: new_active = best.target; c->stats.factor_pair_events++; break;
+    case ECMC_EVENT_BOND: new_active = best.target; c->stats.bond_events++; break;
+    case ECMC_EVENT_END_OF_CHAIN:
+        /* _get_new_velocity, single_independent_active_sequential_direction_end_of_chain_event_handler.py:101-122 */
+        new_velocity[0] = old_velocity[0] * c->prog.eoc_cos - old_velocity[1] * c->prog.eoc_sin;
+        new_velocity[1] = old_velocity[0] * c->prog.eoc_sin + old_velocity[1] * c->prog.eoc_cos;
+        new_active = c->st.eoc_next_active;
+        c->stats.end_of_chain_events++;
+        break;
+    default: break;
+    }
+    {
+        /* velocity changes of the leaves, -old for the old active leaf and +new for the new one (the same leaf at an end
+         * of chain: -old + new, end_of_chain_event_handler.py:143-168; _exchange_velocity, abstracts.py:296-321), carried
+         * to the root units with the leaf weight */
+        const double weight = 1.0 / npr;
+        const int old_root = old_active / npr, new_root = new_active / npr;
+        double change[2];
+        if (new_active == old_active) {
+            if (best.kind == ECMC_EVENT_END_OF_CHAIN) {
+                for (int d = 0; d < 2; d++) change[d] = (-old_velocity[d] + new_velocity[d]) * weight;
+                disk_root_velocity(c->st.root_velocity, 1, change);
+            }
+        } else if (new_root == old_root) {
+            for (int d = 0; d < 2; d++) {
+                change[d] = -old_velocity[d] * weight;
+                change[d] += new_velocity[d] * weight;
+            }
+            disk_root_velocity(c->st.root_velocity, 1, change);
+        } else {
+            /* the old root loses its velocity (|v w - v w| < 1e-13), the new root takes new x weight */
+            for (int d = 0; d < 2; d++) c->st.root_velocity[d] = new_velocity[d] * weight;
+        }
+        c->st.velocity[0] = new_velocity[0]; c->st.velocity[1] = new_velocity[1];
+    }
+    if (rec) {
+        memset(rec, 0, sizeof(*rec));
+        rec->kind = best.kind;
+        rec->target = best.kind == ECMC_EVENT_END_OF_CHAIN ? new_active : best.target;
+        rec->target_cell = -1;
+        rec->accepted = 1;
+        rec->n_candidates = n_cand;
+        rec->time_q = best.t.q; rec->time_r = best.t.r;
+        for (int d = 0; d < D; d++) rec->active_pos[d] = c->pos[old_active * D + d];
+    }
+    c->st.event_counter++;
+    c->stats.events++;
+    c->stats.candidates += (uint64_t)n_cand;
+    c->st.active = new_active;
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN) schedule_end_of_chain(c);
+    if (rec) { rec->new_active = c->st.active; rec->new_direction = 0; }
+    return 1;
+}
+
 static int chain_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
     if (c->molecules) return molecule_step(c, until, rec);
+    if (c->prog.eoc_sequential) return disk_step(c, until, rec);
     candidate best;
     int n_cand = 0;
     double boundary_position = 0.0;

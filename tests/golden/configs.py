@@ -369,6 +369,31 @@ def hard_disk_dipoles_cells_ini(ref_root, n_dipoles=81, end_of_run_time=1.0e9, s
     return text
 
 
+def hard_disk_dipoles_ini(ref_root, end_of_run_time=1.0e9, sampling=False, output="/dev/null", chain_time=None):
+    """config_files/hard_disk_dipoles/hard_disk_dipoles.ini (no cell system: every other disk is a candidate of every
+    event; the sequential-direction end-of-chain handler rotates the velocity by 20 degrees per chain) with its shipped
+    PDB start configuration -- read by the reference's PdbInputHandler through MDAnalysis or jellyfysh_b200's stand-in --,
+    absolute file names, the run length and optionally without the sampling handler."""
+    import os
+    text = shipped_ini(ref_root, "hard_disk_dipoles", "hard_disk_dipoles.ini")
+    text = text.replace("filename = config_files/", "filename = " + os.path.join(ref_root, "jellyfysh", "config_files") + "/")
+    text = text.replace("end_of_run_time = 15015000", f"end_of_run_time = {end_of_run_time!r}")
+    text = text.replace("output/hard_disk_dipoles/Polarization_81Dipoles.dat", output)
+    if chain_time is not None:
+        text = text.replace("chain_time = 6.0", f"chain_time = {chain_time!r}")
+    assert "input_handler = pdb_input_handler" in text and str(end_of_run_time) in text
+    if not sampling:
+        text = text.replace("    polarization_sampling (no_in_state_tagger),\n", "")
+        text = text.replace(", polarization_sampling", "")
+        text = text.replace("polarization_sampling, ", "")
+        start, rest = text.split("[PolarizationSampling]")
+        rest = rest.split("[EndOfChain]", 1)[1]
+        text = start + "[EndOfChain]" + rest
+        text = text.replace("output_handlers = polarization_output_handler\n", "")
+        text = text.split("[PolarizationOutputHandler]")[0]
+    return text
+
+
 def read_pdb_dipoles(ref_root, system_length=12.836):
     """(roots[81][2], leaves[81][2][2]) of the shipped PDB start configuration as PdbInputHandler.read builds them
     (pdb_input_handler.py:146-190): MDAnalysis keeps coordinates as float32; the root is the barycentre over the

@@ -510,6 +510,40 @@ def dipole_traces():
                           hard_dipole=[0.952380952380952, 1.047619047619048], max_occupants=6))
 
 
+def sequential_dipole_trace():
+    # the shipped hard_disk_dipoles.ini: no cell system (160 hard-disk candidates + the tether per event), general
+    # velocities -- the sequential-direction end-of-chain handler rotates the velocity by 20 degrees every chain time.
+    # The start configuration goes through the reference's own PdbInputHandler (MDAnalysis or the stand-in).
+    shims = os.path.join(HERE, "..", "..", "jellyfysh_b200", "shims")
+    try:
+        import MDAnalysis  # noqa: F401
+    except ImportError:
+        sys.path.append(os.path.abspath(shims))
+    roots, leaves = configs.read_pdb_dipoles(REF)
+    name, seed, stream, n_events = "trace_hard_disk_dipoles_sequential", 23, 4, 5000
+    run = rr.ReferenceRun(REF, configs.hard_disk_dipoles_ini(REF, chain_time=1.5), seed=seed, stream=stream)
+    try:
+        positions0, roots0 = run.positions(), run.roots()
+        assert np.array_equal(positions0, leaves.reshape(-1, 2)) and np.array_equal(roots0, roots)
+        records = run.run(max_events=n_events, snapshot_every=250, max_occupants=1)
+        out = {"records": records, "positions0": positions0, "roots0": roots0, "final_positions": run.positions(),
+               "final_roots": run.roots(), "seed": np.array([seed, stream], dtype=np.int64),
+               "snap_roots": np.array([s["roots"] for s in run.snapshots]),
+               "snap_velocities": np.array([s["velocities"] for s in run.snapshots])}
+        meta = dict(n=162, system_length=12.836, beta=1.0, chain_time=1.5, nodes_per_root=2,
+                    hard_sphere=[0.476190476190476], hard_dipole=[0.952380952380952, 1.047619047619048],
+                    delta_phi_degree=20.0)
+        out.update({"meta_" + k: np.asarray(v) for k, v in meta.items()})
+        out.update(_pack_snapshots(run))
+        out["host_times"] = np.array(run.host_times, dtype=np.float64).reshape(-1, 3)
+    finally:
+        run.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    kinds = np.bincount(records["kind"], minlength=9)
+    print(f"{name}.npz: {len(records)} events, kinds pair/veto/boundary/eoc/cell-bounding/bond = {kinds[1:7].tolist()}, "
+          f"snapshots = {len(run.snapshots)}")
+
+
 def _composite_veto_tables(run):
     """Tables of the CompositeObjectCellVetoEventHandler (same layout as the leaf-unit handler's)."""
     return _tables_of(run)
@@ -541,7 +575,8 @@ def water_traces():
 
 
 if __name__ == "__main__":  # noqa
-    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "water", "lifting", "no_cells"]
+    which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "sequential", "water", "lifting",
+                             "no_cells"]
     if "no_cells" in which:
         no_cell_traces()
         no_cell_molecule_traces()
@@ -551,6 +586,8 @@ if __name__ == "__main__":  # noqa
         lifting_vectors()
     if "dipoles" in which:
         dipole_traces()
+    if "sequential" in which:
+        sequential_dipole_trace()
     if "cell_bounding" in which:
         cell_bounding_traces()
         composite_cell_bounding_traces()

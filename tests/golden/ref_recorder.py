@@ -500,7 +500,19 @@ class ReferenceRun:
         self.snapshots.append({"event": self.events, "positions": self.positions(), "roots": self.roots(),
                                "occupants": occ,
                                "surplus": surplus, "active": active, "direction": direction,
-                               "time_q": stamp.quotient, "time_r": stamp.remainder})
+                               "time_q": stamp.quotient, "time_r": stamp.remainder,
+                               "velocities": self.velocities()})
+
+    def velocities(self):
+        """Velocity vectors of the active units, leaf first then its ancestors, padded to three components (general
+        velocities: the sequential-direction end-of-chain handler rotates them)."""
+        sh = self.mediator._state_handler
+        ids = sorted(sh._lifting_state._lifting_dictionary.keys(), key=len, reverse=True)
+        out = np.zeros((2, 3))
+        for row, identifier in enumerate(ids[:2]):
+            velocity, _ = sh._lifting_state.get(identifier)
+            out[row, :len(velocity)] = velocity
+        return out
 
 
 def default_ref_root():

@@ -218,6 +218,45 @@ def test_composite_chain_replay_bit_exact(oracle, name):
     assert stats["capacity_errors"] == 0 and stats["bond_events"] > 500 and stats["pair_events"] > 4000
 
 
+def test_sequential_direction_chain_replay_bit_exact(oracle):
+    """The shipped hard_disk_dipoles.ini (no cell system: 160 hard-disk candidates and the tether per event) with GENERAL
+    velocities: SingleIndependentActiveSequentialDirectionEndOfChainEventHandler rotates the velocity by 20 degrees at
+    every end of chain (:101-122). 5000 events of the running reference from the shipped PDB start configuration:
+    every event bit for bit, and at the snapshots the leaf and root positions and the velocities of the active leaf and
+    of its root unit -- the root's as the reference accumulates it from velocity changes (abstracts.py:165-227)."""
+    g = tu.load_trace("trace_hard_disk_dipoles_sequential")
+    records = g["records"]
+    chain = oracle.OracleChain(tu.sequential_dipole_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"])
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        for f in tu.DISCRETE_FIELDS:
+            assert np.array_equal(rec[f], ref[f]), (f, done + int(np.nonzero(rec[f] != ref[f])[0][0]))
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            assert np.array_equal(chain.roots(), g["snap_roots"][k])
+            state = chain.state()
+            assert state.active == int(g["snap_active"][k])
+            assert [state.velocity[0], state.velocity[1]] == g["snap_velocities"][k][0, :2].tolist()
+            assert [state.root_velocity[0], state.root_velocity[1]] == g["snap_velocities"][k][1, :2].tolist()
+    assert np.array_equal(chain.positions(), g["final_positions"])
+    assert np.array_equal(chain.roots(), g["final_roots"])
+    stats = chain.stats()
+    assert stats["end_of_chain_events"] > 150 and stats["bond_events"] > 1500 and stats["factor_pair_events"] > 2000
+    # the velocity really is general: both components non-zero, and its norm drifts from 1 only by rounding
+    velocities = g["snap_velocities"][:, 0, :2]
+    assert np.all(velocities[1:] != 0.0) and np.max(np.abs(np.linalg.norm(velocities, axis=1) - 1.0)) < 1e-13
+
+
 @pytest.mark.parametrize("name", tu.WATER_TRACES)
 def test_water_chain_replay_bit_exact(oracle, name):
     """C4, the shipped water/coulomb_cell_veto_lj_inverted.ini: composite-object Coulomb pair and cell-veto events with

@@ -150,6 +150,19 @@ def dipole_builder_of(g, builder_cls):
     return pb
 
 
+def sequential_dipole_builder_of(g, builder_cls):
+    """The shipped hard_disk_dipoles.ini: hard-disk dipoles without a cell system, general velocities (the
+    sequential-direction end-of-chain handler rotates the velocity by delta_phi per chain)."""
+    pb = builder_cls(2, int(g["meta_n"]), float(g["meta_system_length"]), float(g["meta_beta"]), [1, 1], 0,
+                     chain_time=float(g["meta_chain_time"]), seed=int(g["seed"][0]), no_cells=True)
+    pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1)],
+                     bond_potential=abi.EcmcPotential.make(abi.POT_HARD_DIPOLE, *g["meta_hard_dipole"]))
+    pb.set_sequential_direction(float(g["meta_delta_phi_degree"]),
+                                abi.EcmcPotential.make(abi.POT_HARD_SPHERE, *g["meta_hard_sphere"]),
+                                [(0, 0), (0, 1), (1, 0), (1, 1)])
+    return pb
+
+
 def water_builder_of(g, builder_cls, max_surplus=None):
     """C4: SPC/Fw-like water (water/coulomb_cell_veto_lj_inverted.ini): composite-object Coulomb handlers with
     inside-first lifting on root-level cells, Lennard-Jones between the oxygens, harmonic bonds, bending."""
