@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBRARY = os.path.join(HERE, "libecmc_b200.so")
 SOURCES = [os.path.join(CSRC, "ecmc_engine.cu")]
-HEADERS = [os.path.join(CSRC, name) for name in ("ecmc_math.cuh", "ecmc_program.cuh", "ecmc_kernels.cuh", "ecmc_molecules.cuh", "ecmc_spec.cuh", "ecmc_spec_cta.cuh", "ecmc_log_table.cuh")] + \
+HEADERS = [os.path.join(CSRC, name) for name in ("ecmc_math.cuh", "ecmc_program.cuh", "ecmc_kernels.cuh", "ecmc_molecules.cuh", "ecmc_spec.cuh", "ecmc_spec_cta.cuh", "ecmc_disks.cuh", "ecmc_log_table.cuh")] + \
           [os.path.join(ROOT, "include", "ecmc.h")]
 
 

@@ -149,7 +149,18 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
     # (coulomb_atoms/power_bounded.ini). On the device that is EcmcProgram.no_cells: every other unit is a candidate
     # of every event and there are no cell-boundary events.
     no_cells = not internal_states
-    if no_cells:
+    # General velocities: the sequential-direction end-of-chain handler rotates the velocity by an angle
+    # (single_independent_active_sequential_direction_end_of_chain_event_handler.py:64-122). On the device that is the
+    # disk kernel: two-dimensional composite point objects without a cell system whose pair factors -- all with hard
+    # potentials -- come from factor type maps (hard_disk_dipoles/hard_disk_dipoles.ini, single_hard_disk_dipole.ini).
+    sequential = any("SingleIndependentActiveSequentialDirectionEndOfChainEventHandler" in _class_names(handler)
+                     for handler in activator.get_event_handlers())
+    if sequential and not (no_cells and levels == 2 and dimension == 2):
+        raise _configuration_error("the sequential-direction end-of-chain handler is supported for two-dimensional "
+                                   "composite point objects without a cell system")
+    if sequential:
+        molecules, max_occupants, cells_per_side, neighbor_layers, cell_objects = False, 1, [1] * setting.dimension, 0, []
+    elif no_cells:
         # composite point objects without cells are handled like those in root-level cells: whole objects are the
         # candidates (dipoles/dipole_factors_*.ini, water/single_molecule.ini)
         molecules, max_occupants, cells_per_side, neighbor_layers, cell_objects = levels == 2, 1, [1] * setting.dimension, 0, []
@@ -240,10 +251,8 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             veto_handlers.append(handler)
         elif "CellBoundaryEventHandler" in names:
             boundary_handlers.append(handler)
-        elif "SingleIndependentActiveSequentialDirectionEndOfChainEventHandler" in names:
-            # a subclass of the periodic-direction handler that rotates the velocity by an angle (general velocities)
-            raise _configuration_error("the sequential-direction end-of-chain handler has no device implementation")
         elif "SingleIndependentActivePeriodicDirectionEndOfChainEventHandler" in names:
+            # (the sequential-direction handler is a subclass: same chain time and draw of the next active unit)
             eoc_handlers.append(handler)
         elif "InitialChainStartOfRunEventHandler" in names:
             start_handlers.append(handler)
@@ -292,7 +301,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                     raise _configuration_error("all intramolecular pair factors must share one potential")
                 bond_potential = potential
             else:
-                if not molecules:
+                if not molecules and not sequential:
                     raise _configuration_error("factors between composite objects need root-level cells")
                 if inter_potential is not None and not _same_potential(inter_potential, potential):
                     raise _configuration_error("all pair factors between composite objects must share one potential")
@@ -314,6 +323,18 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                         if pair not in inter_factors:
                             inter_factors.append(pair)
         builder.set_composite(nodes_per_root, bonds, bond_potential)
+        if sequential:
+            hard = (abi.POT_HARD_SPHERE, abi.POT_HARD_DIPOLE)
+            if pair_handlers or leaf_pair_handlers or bending_handlers or \
+                    any(potential is not None and potential.kind not in hard for potential in (bond_potential, inter_potential)):
+                raise _configuration_error("general velocities are supported for hard potentials in factor type maps only")
+            # the handler keeps cos / sin of the angle (:97-99); the angle in degrees is recovered for the builder, which
+            # recomputes them by the handler's own expressions -- and the result is checked against the handler's values
+            import math
+            delta_phi_degree = math.degrees(math.atan2(eoc._sin_delta_phi, eoc._cos_delta_phi)) % 360.0
+            builder.set_sequential_direction(delta_phi_degree, inter_potential, inter_factors)
+            builder.program.eoc_cos, builder.program.eoc_sin = eoc._cos_delta_phi, eoc._sin_delta_phi
+            inter_factors, inter_potential = [], None
         if bending_handlers:
             first = bending_handlers[0]
             factor_map = factor_tagger_of[id(first)]._factor_type_map

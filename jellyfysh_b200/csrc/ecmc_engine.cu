@@ -14,6 +14,7 @@
 #include "ecmc_molecules.cuh"
 #include "ecmc_spec.cuh"
 #include "ecmc_spec_cta.cuh"
+#include "ecmc_disks.cuh"
 
 using namespace ecmc;
 
@@ -54,6 +55,8 @@ struct EcmcHandle {
     bool roots_uploaded = false;
     bool molecules = false;           // composite objects in root-level cells: molecule_kernel
     MoleculeProgram mprog;
+    bool disks = false;               // general velocities (EcmcProgram.eoc_sequential): disk_kernel
+    DiskProgram kprog{};
     double *d_staging = nullptr;      // [n_chains][n_particles][dimension] + charges
     double *d_staging_charges = nullptr;
     uint32_t *d_streams = nullptr;
@@ -68,6 +71,8 @@ struct EcmcHandle {
     bool chain_blocks = true; // few chains: lj_chain_kernel, one CTA of four warps per chain (ecmc_spec_cta.cuh)
     std::string kernel_name; // ecmc_kernel_name
     bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
+    unsigned long long *d_changed = nullptr;  // particles written back by ecmc_submit_from_host_sparse since the last wait
+    uint64_t host_bytes_written = 0;          // ... as bytes, accumulated by ecmc_wait
     std::string error;
 };
 
@@ -313,8 +318,36 @@ int build_device_program(EcmcHandle *h) {
     // molecules: composite objects in root-level cells (water)
     h->molecules = p.cell_level == 1 && d.nodes_per_root > 1;
     std::memset(&h->mprog, 0, sizeof(h->mprog));
-    if ((p.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || p.n_inter_factors > 0 || p.bending_enabled) && !h->molecules)
+    if ((p.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || p.bending_enabled ||
+         (p.n_inter_factors > 0 && !p.eoc_sequential)) && !h->molecules)
         return fail(h, ECMC_ERR_INVALID, "composite-object handlers need cell_level = 1 and nodes_per_root > 1");
+    // general velocities: two-dimensional composite point objects without a cell system, hard potentials only
+    h->disks = p.eoc_sequential != 0;
+    std::memset(&h->kprog, 0, sizeof(h->kprog));
+    if (h->disks) {
+        DiskProgram &k = h->kprog;
+        if (p.dimension != 2 || !p.no_cells || d.nodes_per_root < 2 || h->molecules || p.pair_handler != ECMC_PAIR_NONE ||
+            p.veto_enabled != ECMC_FAR_NONE)
+            return fail(h, ECMC_ERR_INVALID, "general velocities need two dimensions, composite point objects, no cell system "
+                                             "and factor-type-map pair factors only");
+        if (p.n_inter_factors < 0 || p.n_inter_factors > ECMC_MAX_INTER_FACTORS)
+            return fail(h, ECMC_ERR_INVALID, "n_inter_factors out of range");
+        auto hard = [](int kind) { return kind == ECMC_POT_HARD_SPHERE || kind == ECMC_POT_HARD_DIPOLE; };
+        if ((p.n_inter_factors > 0 && !hard(p.inter_potential.kind)) || (p.n_bonds > 0 && !hard(p.bond_potential.kind)))
+            return fail(h, ECMC_ERR_INVALID, "general velocities need hard potentials");
+        k.n_inter = p.n_inter_factors;
+        for (int f = 0; f < p.n_inter_factors; f++)
+            for (int j = 0; j < 2; j++) {
+                if (p.inter_factors[f][j] < 0 || p.inter_factors[f][j] >= d.nodes_per_root)
+                    return fail(h, ECMC_ERR_INVALID, "inter-object factor child index out of range");
+                k.inter[f][j] = p.inter_factors[f][j];
+            }
+        k.inter_kind = p.inter_potential.kind; k.inter_p0 = p.inter_potential.params[0]; k.inter_p1 = p.inter_potential.params[1];
+        k.bond_kind = p.bond_potential.kind; k.bond_p0 = p.bond_potential.params[0]; k.bond_p1 = p.bond_potential.params[1];
+        k.eoc_cos = p.eoc_cos; k.eoc_sin = p.eoc_sin;
+        k.weight = 1.0 / d.nodes_per_root;
+        k.initial_direction = p.initial_direction;
+    }
     if (h->molecules) {
         MoleculeProgram &m = h->mprog;
         if (p.dimension != 3 || d.nodes_per_root > 3 || p.max_occupants != 1)
@@ -601,7 +634,12 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
     if (rc) return rc;
     const int blocks = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
     CUDA_TRY(h, cudaEventRecord(ev.start, h->stream));
-    if (h->molecules) {
+    if (h->disks) {
+        constexpr int kDiskWarps = 4;
+        const int disk_blocks = (h->n_chains + kDiskWarps - 1) / kDiskWarps;
+        if (d_records) disk_kernel<true, kDiskWarps><<<disk_blocks, kDiskWarps * 32, 0, h->stream>>>(h->dprog, h->kprog, h->state, args);
+        else disk_kernel<false, kDiskWarps><<<disk_blocks, kDiskWarps * 32, 0, h->stream>>>(h->dprog, h->kprog, h->state, args);
+    } else if (h->molecules) {
         // the shipped water configurations: Coulomb bound / merged-image Coulomb / harmonic bonds / Lennard-Jones
         const DeviceProgram &d = h->dprog;
         const bool water = d.cand_potential.kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING &&
@@ -833,6 +871,9 @@ ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_s
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
             h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
             h->program.initial_direction, h->d_stats);
+    if (h->disks)
+        disk_start_kernel<<<(h->n_chains + 127) / 128, 128, 0, h->stream>>>(h->state, h->dprog.speed, h->kprog.weight,
+                                                                           h->kprog.initial_direction);
     CUDA_TRY(h, cudaGetLastError());
     h->started = true;
     return ECMC_OK;
@@ -943,12 +984,58 @@ ECMC_API int ecmc_run_recorded(EcmcHandle *h, double until_q, double until_r, in
 // ecmc_submit_from_host only enqueues: successive steps are ordered slice by slice by their streams, so a step may read
 // the host buffer the step before it writes, and the copies of a slice overlap the events of the other slices across
 // steps as well. ecmc_wait synchronises the slices and returns the counters of all steps submitted since the last wait.
-ECMC_API int ecmc_submit_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
-                                   double until_q, double until_r, int64_t max_events_per_chain, double *positions_out) {
+namespace {
+
+// Sparse write-back of a step: every particle whose coordinates differ from the staged input of the step is written
+// straight into the caller's pinned host buffer (a device-visible mapping of it): only the changed coordinates cross the
+// link -- the particles that were active during the step, about one in ten for a step of 1024 events on 1024 particles.
+__global__ void __launch_bounds__(256)
+write_changed_particles_kernel(const Particle *particles, const double *staged, double *host_out, size_t n, int dimension,
+                               unsigned long long *changed) {
+    unsigned mine = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const Particle p = particles[i];
+        const double *in = staged + i * dimension;
+        bool differs = __double_as_longlong(p.x) != __double_as_longlong(in[0]);
+        if (dimension > 1) differs = differs || __double_as_longlong(p.y) != __double_as_longlong(in[1]);
+        if (dimension > 2) differs = differs || __double_as_longlong(p.z) != __double_as_longlong(in[2]);
+        if (differs) {
+            double *out = host_out + i * dimension;
+            out[0] = p.x;
+            if (dimension > 1) out[1] = p.y;
+            if (dimension > 2) out[2] = p.z;
+            mine++;
+        }
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(changed, (unsigned long long)mine);
+}
+
+int submit_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
+                     double until_q, double until_r, int64_t max_events_per_chain, double *positions_out, bool sparse) {
     if (!h || !positions_in) return fail(h, ECMC_ERR_INVALID, "null argument");
+    double *mapped_out = nullptr;
+    if (sparse) {
+        if (!positions_out) return fail(h, ECMC_ERR_INVALID, "sparse write-back needs positions_out");
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        cudaPointerAttributes attributes{};
+        if (cudaPointerGetAttributes(&attributes, positions_out) != cudaSuccess || attributes.type != cudaMemoryTypeHost ||
+            !attributes.devicePointer) {
+            cudaGetLastError();
+            return fail(h, ECMC_ERR_INVALID, "sparse write-back needs positions_out in pinned host memory the device can "
+                                             "address (ecmc_host_alloc, cudaHostAlloc, cudaHostRegister)");
+        }
+        mapped_out = static_cast<double *>(attributes.devicePointer);
+        if (!h->d_changed) {
+            int rc_alloc = device_alloc(h, &h->d_changed, 1);
+            if (rc_alloc) return rc_alloc;
+            CUDA_TRY(h, cudaMemset(h->d_changed, 0, sizeof(unsigned long long)));
+        }
+    }
     if (h->dprog.nodes_per_root > 1 && !h->roots_uploaded)
         return fail(h, ECMC_ERR_STATE, "composite objects: ecmc_upload_roots before ecmc_run_from_host");
-    if (h->molecules) return fail(h, ECMC_ERR_INVALID, "molecules: use ecmc_upload_positions / _roots, ecmc_start, ecmc_run");
+    if (h->molecules || h->disks)
+        return fail(h, ECMC_ERR_INVALID, "molecules / general velocities: use ecmc_upload_positions / _roots, ecmc_start, ecmc_run");
     if (std::isnan(until_q) || std::isnan(until_r)) return fail(h, ECMC_ERR_INVALID, "until time is NaN");
     if (max_events_per_chain <= 0 && std::isinf(until_q))
         return fail(h, ECMC_ERR_INVALID, "neither a time limit nor an event limit: the run would not end");
@@ -1004,7 +1091,13 @@ ECMC_API int ecmc_submit_from_host(EcmcHandle *h, const double *positions_in, co
         else kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, s>>>(d, slice, args);
         CUDA_TRY(h, cudaGetLastError());
         h->kernel_launches++;
-        if (positions_out) {
+        if (sparse) {
+            write_changed_particles_kernel<<<copy_blocks, 256, 0, s>>>(h->state.particles + offset,
+                                                                       h->d_staging + offset * d.dimension,
+                                                                       mapped_out + offset * d.dimension, n, d.dimension,
+                                                                       h->d_changed);
+            CUDA_TRY(h, cudaGetLastError());
+        } else if (positions_out) {
             unpack_particles_kernel<<<copy_blocks, 256, 0, s>>>(h->state.particles + offset,
                                                                 h->d_staging + offset * d.dimension, n, d.dimension);
             CUDA_TRY(h, cudaMemcpyAsync(positions_out + offset * d.dimension, h->d_staging + offset * d.dimension,
@@ -1017,13 +1110,47 @@ ECMC_API int ecmc_submit_from_host(EcmcHandle *h, const double *positions_in, co
     return ECMC_OK;
 }
 
+}  // namespace
+
+ECMC_API int ecmc_submit_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
+                                   double until_q, double until_r, int64_t max_events_per_chain, double *positions_out) {
+    return submit_from_host(h, positions_in, charges, first_stream, until_q, until_r, max_events_per_chain, positions_out, false);
+}
+
+ECMC_API int ecmc_submit_from_host_sparse(EcmcHandle *h, const double *positions_in, const double *charges,
+                                          uint32_t first_stream, double until_q, double until_r,
+                                          int64_t max_events_per_chain, double *positions_out) {
+    return submit_from_host(h, positions_in, charges, first_stream, until_q, until_r, max_events_per_chain, positions_out, true);
+}
+
 ECMC_API int ecmc_wait(EcmcHandle *h, EcmcStats *stats) {
     if (!h) return fail(h, ECMC_ERR_INVALID, "null handle");
     CUDA_TRY(h, cudaSetDevice(h->device));
     for (cudaStream_t s : h->slice_streams) CUDA_TRY(h, cudaStreamSynchronize(s));
     h->slices_busy = false;
+    if (h->d_changed) {
+        unsigned long long changed = 0;
+        CUDA_TRY(h, cudaMemcpy(&changed, h->d_changed, sizeof(changed), cudaMemcpyDeviceToHost));
+        CUDA_TRY(h, cudaMemset(h->d_changed, 0, sizeof(changed)));
+        h->host_bytes_written += changed * (uint64_t)h->dprog.dimension * sizeof(double);
+    }
     return ecmc_sync(h, stats);
 }
+
+ECMC_API uint64_t ecmc_host_bytes_written(EcmcHandle *h) { return h ? h->host_bytes_written : 0; }
+
+ECMC_API int ecmc_host_alloc(size_t bytes, void **out) {
+    if (!out || bytes == 0) return ECMC_ERR_INVALID;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return ECMC_ERR_CUDA;
+    }
+    *out = p;
+    return ECMC_OK;
+}
+
+ECMC_API int ecmc_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? ECMC_OK : ECMC_ERR_CUDA; }
 
 ECMC_API int ecmc_run_from_host(EcmcHandle *h, const double *positions_in, const double *charges, uint32_t first_stream,
                                 double until_q, double until_r, int64_t max_events_per_chain, double *positions_out,
@@ -1162,7 +1289,9 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
     const std::string real = bounded ? potential(d.real_potential.kind) : "none";
     const std::string veto = d.veto_enabled ? potential(d.veto_potential.kind) : "none";
     SpecLaunch spec;
-    if (h->molecules) {
+    if (h->disks) {
+        h->kernel_name = "disk_kernel<record=" + std::to_string(record != 0) + ">";
+    } else if (h->molecules) {
         h->kernel_name = "molecule_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto + ", record=" + std::to_string(record != 0) + ">";
     } else if (pick_spec(h, record != 0, &spec) && spec.chain_blocks) {
         h->kernel_name = "lj_chain_kernel<record=" + std::to_string(record != 0) + ", prune=" +

@@ -60,6 +60,11 @@ def library() -> C.CDLL:
     lib.ecmc_run_recorded.argtypes = [vp, d, d, i64, vp, i32, stats]
     lib.ecmc_run_from_host.argtypes = [vp, vp, vp, u32, d, d, i64, vp, stats]
     lib.ecmc_submit_from_host.argtypes = [vp, vp, vp, u32, d, d, i64, vp]
+    lib.ecmc_submit_from_host_sparse.argtypes = [vp, vp, vp, u32, d, d, i64, vp]
+    lib.ecmc_host_bytes_written.argtypes = [vp]
+    lib.ecmc_host_bytes_written.restype = C.c_uint64
+    lib.ecmc_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.ecmc_host_free.argtypes = [vp]
     lib.ecmc_wait.argtypes = [vp, stats]
     lib.ecmc_separation_histogram.argtypes = [vp, i32, d, d, vp]
     lib.ecmc_separation_histogram_subset.argtypes = [vp, i32, i32, i32, d, d, vp]
@@ -232,8 +237,11 @@ class Engine:
                                                  float(until[1]), int(max_events), _ptr(out), C.byref(stats)))
         return out, stats.as_dict()
 
-    def submit_from_host(self, positions, charges=None, first_stream=0, until=(INF, INF), max_events=0, out=None):
-        """ecmc_submit_from_host: the step of run_from_host, enqueued only. `positions`, `charges` and `out` must be
+    def submit_from_host(self, positions, charges=None, first_stream=0, until=(INF, INF), max_events=0, out=None,
+                         sparse=False):
+        """ecmc_submit_from_host: the step of run_from_host, enqueued only. sparse: ecmc_submit_from_host_sparse -- `out`
+        (normally the same array as `positions`, allocated by pinned_array) already holds the input configuration and only
+        the coordinates of the particles that moved are written into it, by the device. `positions`, `charges` and `out` must be
         page-locked C-contiguous float64 arrays of the engine's shape (they are used in place, nothing is copied here) and
         stay alive until wait(); steps submitted back to back may chain through their buffers (out of one = positions of
         the next)."""
@@ -241,8 +249,14 @@ class Engine:
                              (charges, (self.n_chains, self.n_particles)), (out, (self.n_chains, self.n_particles, self.dimension))):
             if array is not None and (array.dtype != np.float64 or not array.flags["C_CONTIGUOUS"] or array.shape != shape):
                 raise ValueError("submit_from_host needs C-contiguous float64 arrays of shape {0}".format(shape))
-        self._check(self._lib.ecmc_submit_from_host(self._h, _ptr(positions), _ptr(charges), int(first_stream),
-                                                    float(until[0]), float(until[1]), int(max_events), _ptr(out)))
+        call = self._lib.ecmc_submit_from_host_sparse if sparse else self._lib.ecmc_submit_from_host
+        self._check(call(self._h, _ptr(positions), _ptr(charges), int(first_stream), float(until[0]), float(until[1]),
+                         int(max_events), _ptr(out)))
+
+    @property
+    def host_bytes_written(self):
+        """ecmc_host_bytes_written: bytes the device wrote into host buffers by sparse write-backs (valid after wait())."""
+        return int(self._lib.ecmc_host_bytes_written(self._h))
 
     def wait(self):
         """ecmc_wait: block until all submitted steps are complete; their summed counters."""
@@ -333,6 +347,37 @@ class Engine:
     def kernel_name(self, record=False):
         """ecmc_kernel_name: the event kernel ecmc_run (or ecmc_run_recorded) launches for this program and options."""
         return self._lib.ecmc_kernel_name(self._h, int(bool(record))).decode()
+
+
+class _PinnedBlock:
+    """Owner of one ecmc_host_alloc block; frees it when the last array over it is gone."""
+
+    def __init__(self, n_bytes):
+        self.pointer = C.c_void_p()
+        if library().ecmc_host_alloc(int(n_bytes), C.byref(self.pointer)) != 0:
+            raise MemoryError("ecmc_host_alloc({0}) failed".format(n_bytes))
+        self.buffer = (C.c_char * int(n_bytes)).from_address(self.pointer.value)
+
+    def __del__(self):
+        if self.pointer:
+            library().ecmc_host_free(self.pointer)
+            self.pointer = C.c_void_p()
+
+
+def pinned_array(shape, dtype=np.float64):
+    """numpy array over page-locked, device-addressable host memory (ecmc_host_alloc): the buffers of the *_from_host
+    calls, required by the sparse write-back."""
+    n_bytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    block = _PinnedBlock(max(n_bytes, 1))
+    array = np.frombuffer(block.buffer, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    array.flags.writeable = True
+    _PINNED_OWNERS[id(block)] = block  # np.frombuffer keeps block.buffer alive, not the block: keep the owner too
+    import weakref
+    weakref.finalize(array, _PINNED_OWNERS.pop, id(block), None)
+    return array
+
+
+_PINNED_OWNERS = {}
 
 
 # ---- batched potential arithmetic and the random stream -----------------------------------------------------

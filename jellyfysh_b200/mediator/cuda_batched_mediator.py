@@ -125,7 +125,8 @@ class CudaBatchedMediator(Mediator):
         self._engine = self._engines[0]
         if hasattr(state_handler, "bind"):  # cuda_state_handler: reads single chains straight from the engines
             program = self._compiled.builder.program
-            state_handler.bind(self._engines, self._shards, program.speed, program.dimension, self._compiled.nodes_per_root)
+            state_handler.bind(self._engines, self._shards, program.speed, program.dimension, self._compiled.nodes_per_root,
+                               bool(program.eoc_sequential))
         self._device_observables = bool(device_observables)
         self._histogram_bins = int(histogram_bins)
         self._equilibration_samples = int(equilibration_samples)
@@ -147,29 +148,11 @@ class CudaBatchedMediator(Mediator):
         if hasattr(self._state_handler, "load"):
             self._state_handler.load(positions[chain], None if roots is None else roots[chain], states[chain])
             return
-        speed = self._compiled.builder.program.speed
-        dimension = self._compiled.builder.program.dimension
-        npr = self._compiled.nodes_per_root
+        from jellyfysh_b200.state_handler.cuda_state_handler import fill_tree
+        program = self._compiled.builder.program
         cnodes = self._state_handler.extract_global_state()
-        state = states[chain]
-        active, direction = int(state["active"]), int(state["direction"])
-
-        def fill(unit, position, unit_speed):
-            unit.position = [float(x) for x in position]
-            if unit_speed is None:
-                unit.velocity, unit.time_stamp = None, None
-            else:
-                unit.velocity = [unit_speed if d == direction else 0.0 for d in range(dimension)]
-                unit.time_stamp = Time(float(state["time_q"]), float(state["time_r"]))
-
-        for index, cnode in enumerate(cnodes):
-            if roots is None:
-                fill(cnode.value, positions[chain, index], speed if index == active else None)
-                continue
-            is_active_root = index == active // npr
-            fill(cnode.value, roots[chain, index], speed * cnode.children[0].weight if is_active_root else None)
-            for k, child in enumerate(cnode.children):
-                fill(child.value, positions[chain, index * npr + k], speed if index * npr + k == active else None)
+        fill_tree(cnodes, positions[chain], None if roots is None else roots[chain], states[chain], program.speed,
+                  program.dimension, self._compiled.nodes_per_root, bool(program.eoc_sequential))
         self._state_handler.insert_into_global_state(cnodes)
 
     def _download(self):

@@ -99,7 +99,8 @@ class ProgramBuilder:
         p.n_inter_factors = len(sphere_factors)
         for i, (a, b) in enumerate(sphere_factors):
             p.inter_factors[i][0], p.inter_factors[i][1] = a, b
-        p.inter_potential = sphere_potential
+        if sphere_potential is not None:
+            p.inter_potential = sphere_potential
         return self
 
     def set_molecules(self, lifting, inter_factors=(), inter_potential=None, bending=None, boundary_keeps_factors=True):

@@ -32,11 +32,13 @@ class CudaStateHandler(TreeStateHandler):
         self._engines, self._shards = [], []
         self._speed, self._dimension, self._nodes_per_root = 1.0, 3, 1
         self._selected = None
+        self._general = False
 
-    def bind(self, engines, shards, speed, dimension, nodes_per_root):
+    def bind(self, engines, shards, speed, dimension, nodes_per_root, general_velocities=False):
         """engines with their (first chain, number of chains) blocks, in chain order."""
         self._engines, self._shards = list(engines), list(shards)
         self._speed, self._dimension, self._nodes_per_root = float(speed), int(dimension), int(nodes_per_root)
+        self._general = bool(general_velocities)
 
     @property
     def number_of_chains(self):
@@ -59,25 +61,36 @@ class CudaStateHandler(TreeStateHandler):
 
     def load(self, positions, roots, state):
         """Fill the tree from arrays: positions[N][D], roots[N / nodes_per_root][D] or None, an EcmcChainState record."""
-        npr = self._nodes_per_root
-        active, direction = int(state["active"]), int(state["direction"])
-        stamp = Time(float(state["time_q"]), float(state["time_r"]))
         cnodes = self.extract_global_state()
-
-        def fill(unit, position, unit_speed):
-            unit.position = [float(x) for x in position]
-            if unit_speed is None:
-                unit.velocity, unit.time_stamp = None, None
-            else:
-                unit.velocity = [unit_speed if d == direction else 0.0 for d in range(self._dimension)]
-                unit.time_stamp = stamp
-
-        for index, cnode in enumerate(cnodes):
-            if roots is None:
-                fill(cnode.value, positions[index], self._speed if index == active else None)
-                continue
-            is_active_root = index == active // npr
-            fill(cnode.value, roots[index], self._speed * cnode.children[0].weight if is_active_root else None)
-            for k, child in enumerate(cnode.children):
-                fill(child.value, positions[index * npr + k], self._speed if index * npr + k == active else None)
+        fill_tree(cnodes, positions, roots, state, self._speed, self._dimension, self._nodes_per_root, self._general)
         self.insert_into_global_state(cnodes)
+
+
+def fill_tree(cnodes, positions, roots, state, speed, dimension, nodes_per_root, general_velocities=False):
+    """Write one chain's device state into root cnodes (tree_state_handler.py:213-230): positions of all units, velocity
+    and time stamp of the active leaf unit and, for composite point objects, of its root unit -- velocity x weight
+    (event_handler/abstracts/abstracts.py:165-190), or, for programs with general velocities, the velocities the chain
+    state carries (EcmcChainState.velocity / root_velocity)."""
+    npr = nodes_per_root
+    active, direction = int(state["active"]), int(state["direction"])
+    stamp = Time(float(state["time_q"]), float(state["time_r"]))
+
+    def fill(unit, position, velocity):
+        unit.position = [float(x) for x in position]
+        unit.velocity, unit.time_stamp = velocity, (None if velocity is None else stamp)
+
+    def along_direction(unit_speed):
+        return [unit_speed if d == direction else 0.0 for d in range(dimension)]
+
+    for index, cnode in enumerate(cnodes):
+        if roots is None:
+            fill(cnode.value, positions[index], along_direction(speed) if index == active else None)
+            continue
+        if general_velocities:
+            leaf_velocity = [float(v) for v in state["velocity"][:dimension]]
+            root_velocity = [float(v) for v in state["root_velocity"][:dimension]]
+        else:
+            leaf_velocity, root_velocity = along_direction(speed), along_direction(speed * cnode.children[0].weight)
+        fill(cnode.value, roots[index], root_velocity if index == active // npr else None)
+        for k, child in enumerate(cnode.children):
+            fill(child.value, positions[index * npr + k], leaf_velocity if index * npr + k == active else None)

@@ -249,16 +249,65 @@ def test_dipole_cell_bounded_graph_compiles(oracle):
         setting.reset()
 
 
-def test_sequential_direction_end_of_chain_is_rejected():
-    """single_hard_disk_dipole.ini rotates the velocity by an angle at the end of a chain (a subclass of the
-    periodic-direction handler): not built on the device, and said so instead of being mistaken for its base class."""
-    from jellyfysh_b200 import compiler
-    from jellyfysh.base.exceptions import ConfigurationError
+def test_single_hard_disk_dipole_graph_compiles(oracle):
+    """single_hard_disk_dipole.ini: one tethered pair of disks, no sphere factors, the velocity rotated by 23 degrees at
+    every end of chain (general velocities) -> compiler -> a disk program; the oracle runs it (tether events and ends of
+    chain only) and the velocity stays a unit vector that is not along an axis."""
+    from jellyfysh_b200 import abi, compiler
+    import math
     ini = configs.shipped_without_sampling(REF, ("hard_disk_dipoles", "single_hard_disk_dipole.ini"), end_of_run_time=5.0)
     mediator, setting = build_reference_graph(ini)
     try:
-        with pytest.raises(ConfigurationError, match="sequential-direction"):
-            compiler.compile_program(mediator._activator, mediator._state_handler.extract_global_state())
+        template = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, template, seed=3)
+        p = compiled.builder.program
+        assert (p.dimension, p.n_particles, p.nodes_per_root, p.no_cells, p.eoc_sequential) == (2, 2, 2, 1, 1)
+        assert p.n_bonds == 1 and p.bond_potential.kind == abi.POT_HARD_DIPOLE and p.n_inter_factors == 0
+        assert p.pair_handler == abi.PAIR_NONE and p.chain_time == 0.5
+        assert (p.eoc_cos, p.eoc_sin) == (math.cos(23.0 * math.pi / 180.0), math.sin(23.0 * math.pi / 180.0))
+        positions, charges, roots = compiler.positions_and_charges(template, compiled.charge_name)
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions)
+        chain.set_roots(roots)
+        chain.start(stream=1)
+        n, rec = chain.run(max_events=400, record=400)
+        stats = chain.stats()
+        assert n == 400 and stats["bond_events"] > 100 and stats["end_of_chain_events"] > 50
+        assert stats["bond_events"] + stats["end_of_chain_events"] == 400
+        velocity = chain.state().velocity[:]
+        assert abs(math.hypot(*velocity) - 1.0) < 1e-13 and all(abs(v) > 1e-3 for v in velocity)
+    finally:
+        setting.reset()
+
+
+def test_sequential_direction_graph_compiles_and_replays(oracle):
+    """The shipped hard_disk_dipoles.ini (81 dipoles from the shipped PDB file, no cell system, sequential-direction end
+    of chain) -> compiler -> oracle chain reproduces the reference's recorded run bit for bit."""
+    from jellyfysh_b200 import abi, compiler
+    import jellyfysh_b200
+    jellyfysh_b200.install()  # MDAnalysis stand-in for the PdbInputHandler where MDAnalysis is not installed
+    g = tu.load_trace("trace_hard_disk_dipoles_sequential")
+    mediator, setting = build_reference_graph(configs.hard_disk_dipoles_ini(REF, end_of_run_time=50.0,
+                                                                            chain_time=float(g["meta_chain_time"])))
+    try:
+        template = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, template, seed=int(g["seed"][0]))
+        p = compiled.builder.program
+        assert (p.dimension, p.n_particles, p.nodes_per_root, p.no_cells, p.eoc_sequential) == (2, 162, 2, 1, 1)
+        assert p.n_bonds == 1 and p.bond_potential.kind == abi.POT_HARD_DIPOLE
+        assert p.n_inter_factors == 4 and p.inter_potential.kind == abi.POT_HARD_SPHERE
+        assert sorted((p.inter_factors[i][0], p.inter_factors[i][1]) for i in range(4)) == [(0, 0), (0, 1), (1, 0), (1, 1)]
+        reference = tu.sequential_dipole_builder_of(g, oracle.ProgramBuilder).program
+        assert (p.eoc_cos, p.eoc_sin, p.chain_time) == (reference.eoc_cos, reference.eoc_sin, reference.chain_time)
+        positions, charges, roots = compiler.positions_and_charges(template, compiled.charge_name)
+        assert np.array_equal(positions, g["positions0"]) and np.array_equal(roots, g["roots0"])
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions)
+        chain.set_roots(roots)
+        chain.start(stream=int(g["seed"][1]))
+        n, rec = chain.run(max_events=3000, record=3000)
+        assert n == 3000 and tu.records_equal_discrete(rec, g["records"][:3000])
+        assert np.array_equal(rec["time_r"], g["records"]["time_r"][:3000])
     finally:
         setting.reset()
 

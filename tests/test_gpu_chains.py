@@ -265,6 +265,127 @@ def test_no_cells_composite_reference_trace_replay(oracle, name):
             assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL * max(1.0, length)
 
 
+def test_sequential_direction_reference_trace_replay(oracle):
+    """General velocities on the device (disk_kernel): the shipped hard_disk_dipoles.ini -- no cell system, 160 hard-disk
+    candidates and the tether per event, the velocity rotated by 20 degrees at every end of chain
+    (single_independent_active_sequential_direction_end_of_chain_event_handler.py:101-122) -- every one of the 5000 events
+    of the running reference from the shipped start configuration, in stretches of 40 events that each start from the
+    oracle's state (bit-exact with the reference over the whole trace; hard disks are chaotic). After every stretch the
+    leaf and root positions and the velocities of the active leaf and of its root unit are compared."""
+    g = tu.load_trace("trace_hard_disk_dipoles_sequential")
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    stretch = 40
+    chain = oracle.OracleChain(tu.sequential_dipole_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"])
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    totals = dict.fromkeys(["bond_events", "factor_pair_events", "end_of_chain_events"], 0)
+    with engine.Engine(tu.sequential_dipole_builder_of(g, ProgramBuilder), n_chains=1) as eng:
+        assert "disk_kernel" in eng.kernel_name(record=True)
+        eng.upload_positions(g["positions0"][None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        for done in range(0, len(records), stretch):
+            count = min(stretch, len(records) - done)
+            if done:
+                eng.upload_positions(chain.positions()[None])
+                eng.upload_roots(chain.roots()[None])
+                eng.set_chain_states(np.frombuffer(bytes(chain.state()), dtype=abi.chain_state_dtype()))
+            rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+            assert stats["events"] == count and stats["capacity_errors"] == 0
+            assert_records_match(rec[0], records[done:done + count], length, f"sequential[{done}:{done + count}]")
+            n, ours = chain.run(max_events=count, record=count)
+            assert n == count and tu.records_equal_discrete(ours, records[done:done + count])
+            assert np.max(np.abs(eng.download_positions()[0] - chain.positions())) < RTOL * max(1.0, length)
+            assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL * max(1.0, length)
+            st, ref = eng.chain_states()[0], chain.state()
+            assert int(st["active"]) == ref.active and int(st["eoc_next_active"]) == ref.eoc_next_active
+            assert np.max(np.abs(st["velocity"] - np.array(ref.velocity[:]))) < RTOL
+            assert np.max(np.abs(st["root_velocity"] - np.array(ref.root_velocity[:]))) < RTOL
+            for key in totals:
+                totals[key] += stats[key]
+    ref_stats = chain.stats()
+    assert all(totals[key] == ref_stats[key] for key in totals), (totals, ref_stats)
+    assert totals["end_of_chain_events"] > 150 and totals["bond_events"] > 1500 and totals["factor_pair_events"] > 2000
+
+
+def _sequential_dipole_batch(n_chains, columns=4, rows=7, length=9.0, seed=11, chain_time=0.7, delta_phi=23.0):
+    """columns x rows hard-disk dipoles on a jittered lattice, no cell system, general velocities."""
+    hs = abi.EcmcPotential.make(abi.POT_HARD_SPHERE, 0.476190476190476)
+    tether = abi.EcmcPotential.make(abi.POT_HARD_DIPOLE, 0.952380952380952, 1.047619047619048)
+    n_roots = columns * rows
+
+    def build(cls):
+        pb = cls(2, 2 * n_roots, length, 1.0, [1, 1], 0, chain_time=chain_time, seed=seed, no_cells=True)
+        pb.set_composite(2, bonds=[(0, 1)], bond_potential=tether)
+        pb.set_sequential_direction(delta_phi, hs, [(0, 0), (0, 1), (1, 0), (1, 1)])
+        return pb
+    rng = np.random.default_rng(500 + seed)
+    grid = np.stack(np.meshgrid(np.arange(columns), np.arange(rows), indexing="ij"), axis=-1).reshape(-1, 2)
+    roots = np.empty((n_chains, n_roots, 2))
+    leaves = np.empty((n_chains, n_roots, 2, 2))
+    for c in range(n_chains):
+        centre = (grid + 0.5) * np.array([length / columns, length / rows]) + rng.uniform(-0.02, 0.02, size=(n_roots, 2))
+        angle = rng.uniform(-0.05, 0.05, size=n_roots)
+        half = 0.5 * rng.uniform(0.96, 1.04, size=n_roots)
+        offset = np.stack([np.cos(angle), np.sin(angle)], axis=1) * half[:, None]
+        roots[c] = centre % length
+        leaves[c, :, 0] = (centre + offset) % length
+        leaves[c, :, 1] = (centre - offset) % length
+    return build, roots, leaves.reshape(n_chains, 2 * n_roots, 2)
+
+
+def test_sequential_direction_batch_against_oracle(oracle):
+    """Seeded batch of chains with general velocities against the oracle, re-seeded every 40 events; every chain has its
+    own start configuration and random stream (the end of chain draws the next active leaf)."""
+    build, roots, leaves = _sequential_dipole_batch(n_chains=7)
+    stats = _compare_batch_with_oracle(oracle, build(ProgramBuilder), leaves, None, 1600, 21, "sequential dipoles",
+                                       resync_every=40, roots=roots)
+    assert stats["factor_pair_events"] > 200 and stats["bond_events"] > 500 and stats["end_of_chain_events"] > 50
+
+
+def test_sequential_direction_time_limits_keep_candidates(oracle):
+    """Host control events between the device events (the shipped file samples the polarization every 10.01): the kept
+    candidate, its in-state (both coordinates of the leaf and of the root unit) and the time slices at the sampling
+    times against the oracle; between two limits the chains run at most 30 events, so no re-seeding is needed."""
+    build, roots, leaves = _sequential_dipole_batch(n_chains=3, seed=12)
+    length = 9.0
+    chains = []
+    for c in range(3):
+        chain = oracle.OracleChain(build(oracle.ProgramBuilder))
+        chain.set_positions(leaves[c])
+        chain.set_roots(roots[c])
+        chain.start(stream=40 + c)
+        chains.append(chain)
+    with engine.Engine(build(ProgramBuilder), n_chains=3) as eng:
+        eng.upload_positions(leaves)
+        eng.upload_roots(roots)
+        eng.start(first_stream=40)
+        for k in range(1, 25):
+            t = 0.37 * k
+            until = (float(np.floor(t)), float(t - np.floor(t)))
+            rec, stats = eng.run_recorded(until=until, records_per_chain=64)
+            states = eng.chain_states()
+            positions, root_positions = eng.download_positions(), eng.download_roots()
+            for c, chain in enumerate(chains):
+                n, ref = chain.run(until=until, record=64)
+                assert stats["events"] >= n
+                if n:
+                    assert_records_match(rec[c][:n], ref[:n], length, f"limit {k} chain {c}")
+                st = chain.state()
+                assert (states[c]["time_q"], states[c]["time_r"]) == until
+                assert int(states[c]["pending_kind"]) == st.pending_kind and int(states[c]["pending_target"]) == st.pending_target
+                assert int(states[c]["event_counter"]) == st.event_counter
+                assert np.max(np.abs(positions[c] - chain.positions())) < RTOL * length
+                assert np.max(np.abs(root_positions[c] - chain.roots())) < RTOL * length
+            # the chains are chaotic: continue from the oracle's state
+            eng.upload_positions(np.stack([chain.positions() for chain in chains]))
+            eng.upload_roots(np.stack([chain.roots() for chain in chains]))
+            eng.set_chain_states(np.concatenate([np.frombuffer(bytes(chain.state()), dtype=abi.chain_state_dtype())
+                                                 for chain in chains]))
+
+
 @pytest.mark.parametrize("name", tu.COMPOSITE_CELL_BOUNDING_TRACES)
 def test_composite_cell_bounding_reference_trace_replay(oracle, name):
     """The shipped dipoles/cell_bounded.ini (four dipoles) on the device: composite-object cell-bounding candidates for

@@ -395,6 +395,157 @@ def test_hard_disk_dipoles_polarization_statistics(tmp_path):
         assert distance < 1.95 / np.sqrt(chains * 10) + 5.0e-3, (key, distance)
 
 
+def _sequential_dipole_ini(tmp_path, chains, end_of_run_time, sampling):
+    ini = configs.hard_disk_dipoles_ini(REF, end_of_run_time=end_of_run_time, sampling=sampling,
+                                        output=str(tmp_path / "polarization.dat"))
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 17\n"
+                                                 "first_random_stream = 9" % chains)
+    return ini
+
+
+def test_shipped_hard_disk_dipoles_without_cells_runs_on_the_device(oracle, tmp_path):
+    """config_files/hard_disk_dipoles/hard_disk_dipoles.ini (no cell system, general velocities: the sequential-direction
+    end-of-chain handler) through CudaBatchedMediator with only the mediator line changed, from the shipped PDB start
+    configuration. The final state handed back to the reference's tree state handler -- leaf and root positions, the
+    general velocities of the active leaf and of its root unit -- is the one the oracle reaches (bit-exact with the
+    reference on this configuration, tests/test_oracle_traces.py)."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    g = tu.load_trace("trace_hard_disk_dipoles_sequential")
+    end = 25.0
+    mediator, setting = build_reference_graph(_sequential_dipole_ini(tmp_path, 1, end, sampling=True))
+    try:
+        assert "disk_kernel" in mediator.engine.kernel_name()
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        state = mediator._state_handler.extract_global_state()
+        roots = np.array([node.value.position for node in state])
+        leaves = np.array([child.value.position for node in state for child in node.children])
+        active = [(node.value.identifier, node.value.velocity) for node in state if node.value.velocity is not None]
+        active += [(child.value.identifier, child.value.velocity) for node in state for child in node.children
+                   if child.value.velocity is not None]
+        stats = mediator.statistics
+        builder = mediator._compiled.builder
+    finally:
+        setting.reset()
+    assert stats["events"] > 100 and stats["bond_events"] > 20 and stats["factor_pair_events"] > 20
+    assert stats["end_of_chain_events"] == int(end / 6.0)
+    chain = oracle.OracleChain(builder)
+    chain.set_positions(g["positions0"])
+    chain.set_roots(g["roots0"])
+    chain.start(stream=9)
+    total = 0
+    for k in list(range(1, int(end / 10.01) + 1)) + [None]:
+        until = oracle.time_from_float(end if k is None else 10.01 * k)
+        n, _ = chain.run(until=until)
+        total += n
+    assert total == stats["events"]
+    assert np.max(np.abs(leaves - chain.positions())) < 1e-12 * 12.836
+    assert np.max(np.abs(roots - chain.roots())) < 1e-12 * 12.836
+    st = chain.state()
+    assert len(active) == 2  # the active disk and its dipole
+    assert active[0][0] == (st.active // 2,) and active[1][0] == (st.active // 2, st.active % 2)
+    assert np.max(np.abs(np.array(active[1][1]) - np.array(st.velocity[:]))) < 1e-12
+    assert np.max(np.abs(np.array(active[0][1]) - np.array(st.root_velocity[:]))) < 1e-12
+    assert all(abs(v) > 1e-3 for v in active[1][1])  # rotated four times by 20 degrees: not along an axis
+    samples = np.loadtxt(tmp_path / "polarization.dat", comments="#")
+    assert samples.shape == (int(end / 10.01) + 1, 2)  # first_event_time_zero = True
+
+
+def test_hard_disk_dipoles_without_cells_polarization_statistics(tmp_path):
+    """Statistical check of the shipped hard_disk_dipoles.ini on the device: the polarization of the 81 dipoles
+    sampled by the reference's own PolarizationOutputHandler from 256 device chains with general velocities follows the
+    cumulative histograms the reference ships for this system (ReferenceDataP{x,y}_81Dipoles_NewtonianECMC.dat)."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import kat_replay as kr
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    chains, end, interval = 256, 300300.0, 3003.0  # see test_hard_disk_dipoles_polarization_statistics
+    ini = _sequential_dipole_ini(tmp_path, chains, end, sampling=True).replace("sampling_interval = 10.01",
+                                                                               "sampling_interval = %r" % interval)
+    assert "sampling_interval = 3003.0" in ini
+    mediator, setting = build_reference_graph(ini)
+    try:
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    # (the last end of chain falls on the end-of-run time itself and is not run)
+    assert stats["capacity_errors"] == 0 and stats["end_of_chain_events"] == chains * (int(end / 6.0) - 1)
+    samples = np.loadtxt(tmp_path / "polarization.dat", comments="#")
+    per_chain = int(end / interval) + 1
+    assert samples.shape == (chains * per_chain, 2)
+    samples = samples.reshape(per_chain, chains, 2)[per_chain // 5:].reshape(-1, 2)  # all chains share the start
+    ref = kr.load_npz("reference_cdfs")
+    for axis, key in enumerate(("dipoles_px", "dipoles_py")):
+        x, cdf = ref[key + "_x"], ref[key + "_cdf"]
+        edges = x + 0.5 * (x[1] - x[0])
+        ours = np.searchsorted(np.sort(samples[:, axis]), edges, side="right") / len(samples)
+        distance = np.max(np.abs(ours - cdf))
+        print(key, "KS distance", distance, "samples", len(samples), "events", stats["events"])
+        assert distance < 1.95 / np.sqrt(chains * 10) + 5.0e-3, (key, distance)
+
+
+def test_shipped_single_hard_disk_dipole_matches_the_analytic_distributions(tmp_path):
+    """config_files/hard_disk_dipoles/single_hard_disk_dipole.ini on the device (one tethered pair of disks, the velocity
+    rotated by 23 degrees at every end of chain): the polarization sampled by the reference's PolarizationOutputHandler from
+    512 chains -- each from its own draw of the reference's random input handler -- follows the analytic distributions the
+    reference's plot script compares with (output/hard_disk_dipoles/plot_histogram_single_hard_disk_dipole.py:61-77,
+    :104-106): extension rho with cumulative (rho^2 - min^2) / (max^2 - min^2), angle uniform on (-pi, pi]."""
+    import sys
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from jellyfysh.base.exceptions import EndOfRun
+    import jellyfysh_b200
+    jellyfysh_b200.install()
+    chains, interval, per_chain = 512, 2.215132, 120
+    end = interval * (per_chain - 0.5)
+    ini = configs.shipped_ini(REF, "hard_disk_dipoles", "single_hard_disk_dipole.ini")
+    ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+    ini = ini.replace("end_of_run_time = 3322698", "end_of_run_time = %r" % end)
+    ini = ini.replace("output/hard_disk_dipoles/Polarization_SingleHardDiskDipole.dat", str(tmp_path / "polarization.dat"))
+    ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
+    ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 5" % chains)
+    assert repr(end) in ini and "polarization.dat" in ini
+    mediator, setting = build_reference_graph(ini)
+    try:
+        assert "disk_kernel" in mediator.engine.kernel_name()
+        with pytest.raises(EndOfRun):
+            mediator.run()
+        mediator.post_run()
+        stats = mediator.statistics
+    finally:
+        setting.reset()
+    assert stats["bond_events"] > 0 and stats["factor_pair_events"] == 0
+    assert stats["end_of_chain_events"] == chains * int(end / 0.5)
+    samples = np.loadtxt(tmp_path / "polarization.dat", comments="#")
+    assert samples.shape == (chains * per_chain, 2)
+    samples = samples.reshape(per_chain, chains, 2)[per_chain // 6:].reshape(-1, 2)
+    rho, theta = np.hypot(samples[:, 0], samples[:, 1]), np.arctan2(samples[:, 1], samples[:, 0])
+    lo, hi = 0.6666666666666666, 1.333333333333333
+    assert rho.min() >= lo - 1e-12 and rho.max() <= hi + 1e-12
+    grid = np.linspace(lo, hi, 1001)
+    ours = np.searchsorted(np.sort(rho), grid, side="right") / len(rho)
+    d_rho = np.max(np.abs(ours - (grid ** 2 - lo ** 2) / (hi ** 2 - lo ** 2)))
+    grid = np.linspace(-np.pi, np.pi, 1001)
+    ours = np.searchsorted(np.sort(theta), grid, side="right") / len(theta)
+    d_theta = np.max(np.abs(ours - (grid + np.pi) / (2.0 * np.pi)))
+    print("KS distances: extension", d_rho, "angle", d_theta, "samples", len(rho), "events", stats["events"])
+    bound = 1.95 / np.sqrt(chains * 10) + 5.0e-3  # conservative: 10 independent samples per chain
+    assert d_rho < bound and d_theta < bound, (d_rho, d_theta, bound)
+
+
 @pytest.mark.parametrize("config", ["coulomb_cell_veto_lj_inverted.ini", "coulomb_power_bounded_lj_inverted.ini"])
 def test_shipped_water_config_matches_reference_statistics(tmp_path, config):
     """C4 statistical check (SURVEY 8c): the shipped water/coulomb_cell_veto_lj_inverted.ini (two SPC/Fw molecules;
