@@ -582,7 +582,7 @@ def run_ours(args, rank, local_rank, world):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from jellyfysh_b200 import sharding
+    from jellyfysh_b200 import engine, sharding
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -719,7 +719,30 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         e2e_seconds = time.perf_counter() - t0
         e2e_events, e2e_targets = wait_stats["events"], wait_stats["pair_targets"]
-    # per chain slice: pack, start, events, unpack (ecmc_kernel_launches counts the event kernels)
+    # The same steps with the sparse write-back (ecmc_submit_from_host_sparse): ONE pinned buffer, every step uploads the
+    # whole configuration from it and the device writes back, into the same buffer, only the coordinates of the particles
+    # that moved during the step (the active ones: about a tenth of all for these steps). After every step the buffer is
+    # the complete configuration, which the next step uploads.
+    sparse_seconds, sparse_events, sparse_targets, sparse_bytes = 0.0, 0, 0, 0
+    if pipelined:
+        first = e2e_warmup + 2 * args.e2e_steps
+        in_place = engine.pinned_array(host["positions"].shape)
+        in_place[...] = pinned["positions"][first % 2].numpy()  # the configuration the last full-copy step returned
+        eng.submit_from_host(in_place, charges, first_stream=first_chain + (first + 1) * total_chains,
+                             max_events=workload.events, out=in_place, sparse=True)
+        eng.wait()
+        written_before = eng.host_bytes_written
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(first + 1, first + 1 + args.e2e_steps):
+            eng.submit_from_host(in_place, charges, first_stream=first_chain + (k + 1) * total_chains,
+                                 max_events=workload.events, out=in_place, sparse=True)
+        sparse_stats = eng.wait()
+        barrier()
+        sparse_seconds = time.perf_counter() - t0
+        sparse_events, sparse_targets = sparse_stats["events"], sparse_stats["pair_targets"]
+        sparse_bytes = (eng.host_bytes_written - written_before) / args.e2e_steps
+    # per chain slice: pack, start, events, unpack / write-back (ecmc_kernel_launches counts the event kernels)
     e2e_launches = 4 * (eng.kernel_launches - e2e_launches_before)
 
     # ---- an observable reduced over ranks: pair-separation histogram of all chains, one NCCL all-reduce
@@ -738,10 +761,10 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- reduce over ranks (NCCL): event counters are summed, times are the slowest rank's
     all_stats = sharding.reduce_counters(stats, device=device)
-    total_e2e_events, total_sync_events = [int(v) for v in
-                                           sharding.reduce_histogram([e2e_events, sync_e2e_events], device=device)]
-    max_ms, max_e2e_seconds, max_sync_seconds = sharding.reduce_max([elapsed_ms, e2e_seconds, sync_e2e_seconds],
-                                                                    device=device).tolist()
+    total_e2e_events, total_sync_events, total_sparse_events = [int(v) for v in sharding.reduce_histogram(
+        [e2e_events, sync_e2e_events, sparse_events], device=device)]
+    max_ms, max_e2e_seconds, max_sync_seconds, max_sparse_seconds = sharding.reduce_max(
+        [elapsed_ms, e2e_seconds, sync_e2e_seconds, sparse_seconds], device=device).tolist()
     total_events = all_stats["events"]
     if rank != 0:
         if world > 1:
@@ -795,26 +818,41 @@ def run_ours(args, rank, local_rank, world):
                                         "pair_targets_per_event_warmup": warm_stats["pair_targets"] / max(warm_stats["events"], 1),
                                         "pair_targets_per_event_timed": n_cand,
                                         "mean_surplus_particles_at_end": mean_surplus}
+    full_copy = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                 "steps": args.e2e_steps, "ms_per_step": 1e3 * max_e2e_seconds / args.e2e_steps,
+                 "host_gb_per_s_per_rank": (h2d + d2h) * args.e2e_steps / max_e2e_seconds * 1e-9,
+                 "pair_targets_per_event": e2e_targets / max(e2e_events, 1),
+                 "call": ("ecmc_upload_positions + ecmc_upload_roots + ecmc_start + ecmc_run + ecmc_sync + "
+                          "ecmc_download_positions + ecmc_download_roots per step" if workload.composite else
+                          "ecmc_submit_from_host x steps + ecmc_wait: per step pinned host configuration -> H2D -> cell "
+                          "binning -> events -> D2H of the whole configuration on the streams of the chain slices; the host "
+                          "does not block between steps, the device orders them slice by slice") +
+                         "; step k + 1 starts from the configuration step k returned, with fresh random streams"}
+    e2e = dict(full_copy)
+    if pipelined and max_sparse_seconds > 0.0:
+        # the headline: the same steps, the configuration returned through the sparse write-back
+        e2e = {"value": total_sparse_events / max_sparse_seconds, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(sparse_bytes) + 96, "steps": args.e2e_steps,
+               "ms_per_step": 1e3 * max_sparse_seconds / args.e2e_steps,
+               "host_gb_per_s_per_rank": (h2d + sparse_bytes + 96) * args.e2e_steps / max_sparse_seconds * 1e-9,
+               "pair_targets_per_event": sparse_targets / max(sparse_events, 1),
+               "call": "ecmc_submit_from_host_sparse x steps + ecmc_wait, in place on one pinned buffer: per step the whole "
+                       "host configuration -> H2D -> cell binning -> events -> the device writes the coordinates of the "
+                       "particles that moved (d2h_bytes_per_step, measured: ecmc_host_bytes_written) straight into the host "
+                       "buffer, which then is the complete configuration again and is what step k + 1 uploads; fresh random "
+                       "streams per step; the host does not block between steps",
+               "full_copy": full_copy}
+    e2e["link_gb_per_s"] = {"h2d": h2d_rate, "d2h": d2h_rate,
+                            "note": "one pinned copy of the positions buffer alone on rank 0, best of 3: h2d_bytes / h2d rate "
+                                    "is the floor of a step before its last slice can start"}
+    e2e["synchronous"] = {"value": total_sync_events / max_sync_seconds, "ms_per_step": 1e3 * max_sync_seconds / args.e2e_steps,
+                          "call": "the blocking form (ecmc_run_from_host / the upload-start-run-download calls), full copy "
+                                  "both ways, one step at a time"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": args.e2e_steps, "ms_per_step": 1e3 * max_e2e_seconds / args.e2e_steps,
-                    "host_gb_per_s_per_rank": (h2d + d2h) * args.e2e_steps / max_e2e_seconds * 1e-9,
-                    "link_gb_per_s": {"h2d": h2d_rate, "d2h": d2h_rate,
-                                      "note": "one pinned copy of the positions buffer alone on rank 0, best of 3: h2d_bytes / "
-                                              "h2d rate is the floor of a step before its last slice can start"},
-                    "pair_targets_per_event": e2e_targets / max(e2e_events, 1),
-                    "synchronous": {"value": total_sync_events / max_sync_seconds, "ms_per_step": 1e3 * max_sync_seconds / args.e2e_steps,
-                                    "call": "the blocking form (ecmc_run_from_host / the upload-start-run-download calls), one "
-                                            "step at a time"},
-                    "call": ("ecmc_upload_positions + ecmc_upload_roots + ecmc_start + ecmc_run + ecmc_sync + "
-                             "ecmc_download_positions + ecmc_download_roots per step" if workload.composite else
-                             "ecmc_submit_from_host x steps + ecmc_wait: per step pinned host configuration -> H2D -> cell "
-                             "binning -> events -> D2H on the streams of the chain slices; the host does not block between "
-                             "steps, the device orders them slice by slice") +
-                            "; step k + 1 starts from the configuration step k returned, with fresh random streams"},
+            "e2e": e2e,
             "gpu_launches": int(launches + e2e_launches),
             "roofline": roofline, "fp64": fp64, "observable": observable,
             "event_mix": {k: all_stats[k] for k in ("pair_events", "veto_events", "veto_accepted", "boundary_events",

@@ -692,6 +692,34 @@ def test_submitted_host_steps_equal_blocking_host_steps(oracle):
             queued.submit_from_host(positions[:10], max_events=5, out=buffers[0])
 
 
+def test_sparse_write_back_equals_the_full_copy(oracle):
+    """ecmc_submit_from_host_sparse: three steps chained IN PLACE through one pinned buffer (ecmc_host_alloc), the device
+    writing only the coordinates of the particles that moved, against three blocking full-copy ecmc_run_from_host calls:
+    the buffer ends as the same complete configuration bit for bit; the bytes written are those of the particles that
+    differ between the input and the output of each step; ordinary (pageable) memory is refused."""
+    pb, positions = _lj_batch(oracle, n_chains=600, seed=22)
+    buffer = engine.pinned_array(positions.shape)
+    buffer[...] = positions
+    with engine.Engine(pb, n_chains=600) as blocking, engine.Engine(pb, n_chains=600) as sparse:
+        current, totals, moved = positions, {}, 0
+        for k in range(3):
+            after, stats = blocking.run_from_host(current, first_stream=1000 * k, max_events=150)
+            moved += int(np.count_nonzero(np.any(after != current, axis=2)))
+            current = after
+            for key, value in stats.items():
+                totals[key] = totals.get(key, 0) + value
+        for k in range(3):
+            sparse.submit_from_host(buffer, first_stream=1000 * k, max_events=150, out=buffer, sparse=True)
+        stats = sparse.wait()
+        assert np.array_equal(buffer, current)
+        assert {k: v for k, v in stats.items() if k != "candidates"} == {k: v for k, v in totals.items() if k != "candidates"}
+        assert np.array_equal(sparse.download_positions(), blocking.download_positions())
+        assert sparse.host_bytes_written == moved * 3 * 8 and 0 < moved < 0.5 * 3 * positions.shape[0] * positions.shape[1]
+        pageable = positions.copy()
+        with pytest.raises(RuntimeError, match="pinned"):
+            sparse.submit_from_host(pageable, max_events=5, out=pageable, sparse=True)
+
+
 def test_pruned_launches_reach_the_same_state(oracle):
     """The kernel instantiations with and without event records must commit the same events: identical positions, cells
     and chain states bit for bit, the same event counts. (Launches without records skip pair candidates that provably
