@@ -690,6 +690,10 @@ def run_ours(args, rank, local_rank, world):
 
     h2d_rate = link_rate(True)
     d2h_rate = link_rate(False)
+    # all ranks at once: what the box's host memory and PCIe complex deliver to N GPUs together (per rank)
+    barrier()
+    shared_h2d_rate = link_rate(True)
+    barrier()
     # (the probe copies buffer 0 to the device and back: its content is unchanged)
     e2e_launches_before = eng.kernel_launches
     barrier()
@@ -724,6 +728,7 @@ def run_ours(args, rank, local_rank, world):
     # that moved during the step (the active ones: about a tenth of all for these steps). After every step the buffer is
     # the complete configuration, which the next step uploads.
     sparse_seconds, sparse_events, sparse_targets, sparse_bytes = 0.0, 0, 0, 0
+    staged_launches = eng.kernel_launches - e2e_launches_before
     if pipelined:
         first = e2e_warmup + 2 * args.e2e_steps
         in_place = engine.pinned_array(host["positions"].shape)
@@ -742,8 +747,10 @@ def run_ours(args, rank, local_rank, world):
         sparse_seconds = time.perf_counter() - t0
         sparse_events, sparse_targets = sparse_stats["events"], sparse_stats["pair_targets"]
         sparse_bytes = (eng.host_bytes_written - written_before) / args.e2e_steps
-    # per chain slice: pack, start, events, unpack / write-back (ecmc_kernel_launches counts the event kernels)
-    e2e_launches = 4 * (eng.kernel_launches - e2e_launches_before)
+    # staged steps, per chain slice: pack, start, events, unpack (ecmc_kernel_launches counts the event kernels); a sparse
+    # step of a Lennard-Jones / cell-veto program is one launch per chain slice, of any other program again four
+    fused = pipelined and "lj_spec_kernel" in kernel_name
+    e2e_launches = 4 * staged_launches + (1 if fused else 4) * (eng.kernel_launches - e2e_launches_before - staged_launches)
 
     # ---- an observable reduced over ranks: pair-separation histogram of all chains, one NCCL all-reduce
     if water:
@@ -837,12 +844,16 @@ def run_ours(args, rank, local_rank, world):
                "host_gb_per_s_per_rank": (h2d + sparse_bytes + 96) * args.e2e_steps / max_sparse_seconds * 1e-9,
                "pair_targets_per_event": sparse_targets / max(sparse_events, 1),
                "call": "ecmc_submit_from_host_sparse x steps + ecmc_wait, in place on one pinned buffer: per step the whole "
-                       "host configuration -> H2D -> cell binning -> events -> the device writes the coordinates of the "
-                       "particles that moved (d2h_bytes_per_step, measured: ecmc_host_bytes_written) straight into the host "
-                       "buffer, which then is the complete configuration again and is what step k + 1 uploads; fresh random "
-                       "streams per step; the host does not block between steps",
+                       "host configuration crosses the link to the device" +
+                       (" -- read by the event kernel itself, which bins it into the cells, runs the events and writes every "
+                        "position it changes through to the host buffer (one launch per chain slice)" if fused else
+                        " (H2D copy) -> cell binning -> events -> the device writes the coordinates of the particles that "
+                        "moved straight into the host buffer") +
+                       " (d2h_bytes_per_step, measured: ecmc_host_bytes_written); the buffer then is the complete "
+                       "configuration again and is what step k + 1 reads; fresh random streams per step; the host does not "
+                       "block between steps",
                "full_copy": full_copy}
-    e2e["link_gb_per_s"] = {"h2d": h2d_rate, "d2h": d2h_rate,
+    e2e["link_gb_per_s"] = {"h2d": h2d_rate, "d2h": d2h_rate, "h2d_all_ranks_at_once_per_rank": shared_h2d_rate,
                             "note": "one pinned copy of the positions buffer alone on rank 0, best of 3: h2d_bytes / h2d rate "
                                     "is the floor of a step before its last slice can start"}
     e2e["synchronous"] = {"value": total_sync_events / max_sync_seconds, "ms_per_step": 1e3 * max_sync_seconds / args.e2e_steps,

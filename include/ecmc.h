@@ -426,9 +426,13 @@ int ecmc_bond_histograms(EcmcHandle *h, int32_t n_bins, double length_min, doubl
  *   ECMC_OPTION_LANES_PER_EVENT   4 (default: 8 events per batch) or 8 (4 events per batch)
  *   ECMC_OPTION_CHAIN_BLOCKS      1 (default) / 0: engines of at most 148 chains (the single large chain of the metric's
  *                                 "ns/event single chain") give every chain a CTA of four warps that evaluates 32 events
- *                                 per batch (csrc/ecmc_spec_cta.cuh) instead of one warp with 8; same committed events */
+ *                                 per batch (csrc/ecmc_spec_cta.cuh) instead of one warp with 8; same committed events
+ *   ECMC_OPTION_FUSED_HOST_STEPS  1 (default) / 0: ecmc_submit_from_host_sparse of these programs runs a host step as ONE
+ *                                 launch per chain slice -- the kernel reads the start configuration from the pinned
+ *                                 buffer itself, bins it into the cells, runs the events and writes every position it
+ *                                 changes through to the buffer -- instead of copy, pack, start, events, write-back */
 enum EcmcOption { ECMC_OPTION_BATCHED_EVENTS = 1, ECMC_OPTION_PRUNE_CANDIDATES = 2, ECMC_OPTION_LANES_PER_EVENT = 3,
-                  ECMC_OPTION_CHAIN_BLOCKS = 4 };
+                  ECMC_OPTION_CHAIN_BLOCKS = 4, ECMC_OPTION_FUSED_HOST_STEPS = 5 };
 int ecmc_set_option(EcmcHandle *h, int option, int value);
 
 /* The CUDA stream the handle launches on (a cudaStream_t), so callers can time with events on it. */

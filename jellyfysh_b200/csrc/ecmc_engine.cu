@@ -69,6 +69,7 @@ struct EcmcHandle {
     bool spec_prune = true;  // ... with the force-bound pruning of pair candidates in ecmc_run / ecmc_run_from_host
     int spec_lanes = 4;      // lanes per speculated event (4: 8 events per batch, 8: 4 events per batch)
     bool chain_blocks = true; // few chains: lj_chain_kernel, one CTA of four warps per chain (ecmc_spec_cta.cuh)
+    bool host_fused = true;   // sparse host steps of Lennard-Jones / cell-veto programs as ONE launch per chain slice
     std::string kernel_name; // ecmc_kernel_name
     bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
     unsigned long long *d_changed = nullptr;  // particles written back by ecmc_submit_from_host_sparse since the last wait
@@ -561,6 +562,11 @@ template <bool RECORD, bool PRUNE>
 EventKernel pick_spec_lanes(int lanes) {
     return lanes == 8 ? lj_spec_kernel<RECORD, PRUNE, 8, kWarpsPerBlock> : lj_spec_kernel<RECORD, PRUNE, 4, kWarpsPerBlock>;
 }
+// the whole-host-step form of the same kernel (RunArgs.host_in / host_out)
+EventKernel pick_spec_host(bool prune, int lanes) {
+    if (prune) return lanes == 8 ? lj_spec_kernel<false, true, 8, kWarpsPerBlock, true> : lj_spec_kernel<false, true, 4, kWarpsPerBlock, true>;
+    return lanes == 8 ? lj_spec_kernel<false, false, 8, kWarpsPerBlock, true> : lj_spec_kernel<false, false, 4, kWarpsPerBlock, true>;
+}
 
 // Chargeless 3D Lennard-Jones pair factors with a Lennard-Jones cell veto, one occupant per cell, modular cell
 // translations, and a candidate list (nearby cells + the longest possible surplus list) that fits the shared memory
@@ -621,7 +627,7 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
     if (max_events <= 0 && std::isinf(until_q))
         return fail(h, ECMC_ERR_INVALID, "neither a time limit nor an event limit: the run would not end");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    RunArgs args;
+    RunArgs args{};
     args.until_q = until_q;
     args.until_r = until_r;
     args.max_events = max_events;
@@ -1050,7 +1056,7 @@ int submit_from_host(EcmcHandle *h, const double *positions_in, const double *ch
         h->slice_streams.push_back(s);
     }
     if (!h->slices_busy) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // earlier work on the handle's stream comes first
-    RunArgs args;
+    RunArgs args{};
     args.until_q = until_q;
     args.until_r = until_r;
     args.max_events = max_events_per_chain;
@@ -1066,11 +1072,70 @@ int submit_from_host(EcmcHandle *h, const double *positions_in, const double *ch
         CUDA_TRY(h, cudaFuncSetAttribute(spec.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec.shared_bytes));
     }
     const size_t per_chain = (size_t)d.n_particles;
-    const int base = h->n_chains / slices, extra = h->n_chains % slices;
+    // Lennard-Jones / cell-veto programs with a sparse write-back: one launch per chain slice does the whole step -- the
+    // kernel reads the configuration from the pinned buffer itself, bins it, runs the events and writes the positions it
+    // changes through to the buffer (lj_spec_kernel<..., HOST>); nothing is staged, no copy engine is involved
+    bool fused = sparse && !charges && spec.kernel && !spec.chain_blocks && h->host_fused;
+    bool fused_copy = true;
+    if (const char *env = std::getenv("ECMC_FUSED_ZEROCOPY")) fused_copy = std::atoi(env) == 0;
+    if (fused) {
+        cudaPointerAttributes attributes{};
+        if (cudaPointerGetAttributes(&attributes, positions_in) != cudaSuccess || attributes.type != cudaMemoryTypeHost ||
+            !attributes.devicePointer) {
+            cudaGetLastError();
+            fused = false;  // pageable input: the staged path copies it
+        } else {
+            args.host_in = static_cast<const double *>(attributes.devicePointer);
+            if (fused_copy) args.host_in = h->d_staging;  // the copy engine brings the slice, the kernel reads the staging buffer
+            args.host_out = mapped_out;
+            args.first_stream = first_stream;
+            args.initial_active = h->program.initial_active;
+            args.initial_direction = h->program.initial_direction;
+            args.host_writes = h->d_changed;
+            kernel = pick_spec_host(h->spec_prune, h->spec_lanes);
+            CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec.shared_bytes));
+        }
+    }
+    int fused_slices = 32;
+    if (const char *env = std::getenv("ECMC_FUSED_SLICES")) fused_slices = std::max(1, std::atoi(env));
+    const int base_slices = slices;
+    if (fused) {
+        const int wanted = std::max(1, std::min(fused_slices, h->n_chains / (2 * kWarpsPerBlock)));
+        while ((int)h->slice_streams.size() < wanted) {
+            cudaStream_t s;
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            h->slice_streams.push_back(s);
+        }
+    }
+    const int n_slices = fused ? std::max(1, std::min(fused_slices, h->n_chains / (2 * kWarpsPerBlock))) : base_slices;
+    // (whole CTAs per slice: a slice boundary inside a CTA would leave warps idle)
+    const int ctas = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int base = fused ? 0 : h->n_chains / n_slices, extra = fused ? 0 : h->n_chains % n_slices;
     int first = 0;
-    for (int k = 0; k < slices; k++) {
-        const int count = base + (k < extra ? 1 : 0);
+    for (int k = 0; k < n_slices; k++) {
+        int count = base + (k < extra ? 1 : 0);
+        if (fused) {
+            const int cta_first = (int)((long long)ctas * k / n_slices), cta_last = (int)((long long)ctas * (k + 1) / n_slices);
+            count = std::min(h->n_chains, cta_last * kWarpsPerBlock) - cta_first * kWarpsPerBlock;
+            if (count <= 0) continue;
+        }
         cudaStream_t s = h->slice_streams[k];
+        if (fused) {
+            if (fused_copy) {
+                const size_t offset = (size_t)first * per_chain * 3, n = (size_t)count * per_chain * 3;
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_staging + offset, positions_in + offset, n * sizeof(double),
+                                            cudaMemcpyHostToDevice, s));
+            }
+            DeviceState slice = h->state;
+            slice.first_chain = first;
+            slice.n_chains = count;
+            const int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+            kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, s>>>(d, slice, args);
+            CUDA_TRY(h, cudaGetLastError());
+            h->kernel_launches++;
+            first += count;
+            continue;
+        }
         const size_t offset = (size_t)first * per_chain, n = (size_t)count * per_chain;
         CUDA_TRY(h, cudaMemcpyAsync(h->d_staging + offset * d.dimension, positions_in + offset * d.dimension,
                                     n * d.dimension * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -1258,6 +1323,7 @@ ECMC_API int ecmc_set_option(EcmcHandle *h, int option, int value) {
     case ECMC_OPTION_BATCHED_EVENTS: h->spec = value != 0; return ECMC_OK;
     case ECMC_OPTION_PRUNE_CANDIDATES: h->spec_prune = value != 0; return ECMC_OK;
     case ECMC_OPTION_CHAIN_BLOCKS: h->chain_blocks = value != 0; return ECMC_OK;
+    case ECMC_OPTION_FUSED_HOST_STEPS: h->host_fused = value != 0; return ECMC_OK;
     case ECMC_OPTION_LANES_PER_EVENT:
         if (value != 4 && value != 8) return fail(h, ECMC_ERR_INVALID, "lanes per event: 4 or 8");
         h->spec_lanes = value;

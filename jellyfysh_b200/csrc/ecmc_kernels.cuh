@@ -874,13 +874,9 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
 // InitialChainStartOfRunEventHandler (initial_chain_start_of_run_event_handler.py:92-131). One warp per chain.
 // Particles enter in identifier order: the first max_occupants of a cell become occupants, the rest surplus.
 // ---------------------------------------------------------------------------------------------------------
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams, uint32_t first_stream,
-             int initial_active, int initial_direction, EcmcStats *stats) {
-    const int lane = threadIdx.x & 31;
-    const int chain = S.first_chain + blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (chain >= S.first_chain + S.n_chains) return;
+// start of run of ONE chain by its warp (all 32 lanes call it)
+ECMC_D void start_chain(const DeviceProgram &P, const DeviceState &S, const uint32_t *streams, uint32_t first_stream,
+                        int initial_active, int initial_direction, EcmcStats *stats, int chain, int lane) {
     Particle *part = S.particles + (size_t)chain * P.n_particles;
     const int m = P.max_occupants;
     int *occ = S.occupants + (size_t)chain * P.n_cells * m;
@@ -953,6 +949,16 @@ start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
         S.n_surplus[chain] = n_surplus;
         if (overflow && stats) atomicAdd(reinterpret_cast<unsigned long long *>(stats) + 8, (unsigned long long)overflow);
     }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams, uint32_t first_stream,
+             int initial_active, int initial_direction, EcmcStats *stats) {
+    const int lane = threadIdx.x & 31;
+    const int chain = S.first_chain + blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (chain >= S.first_chain + S.n_chains) return;
+    start_chain(P, S, streams, first_stream, initial_active, initial_direction, stats, chain, lane);
 }
 
 // host layout [n_chains][n_particles][dimension] (+ charges [n_chains][n_particles]) <-> 32-byte particle records

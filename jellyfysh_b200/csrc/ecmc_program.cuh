@@ -98,6 +98,14 @@ struct RunArgs {
     int records_per_chain;
     EcmcStats *stats;
     int list_capacity;      // lj_spec_kernel: entries of the per-chain candidate list in shared memory
+    // lj_spec_kernel<..., HOST = true> (a whole host step in one launch, ecmc_submit_from_host_sparse): the chain's warp
+    // reads its start configuration from the caller's pinned buffer (device-visible mapping), bins it into the cells,
+    // starts the run, and writes every position it changes through to the same kind of buffer
+    const double *host_in;  // [n_chains][n_particles][3]
+    double *host_out;
+    uint32_t first_stream;
+    int initial_active, initial_direction;
+    unsigned long long *host_writes;  // counts the particles written to host_out
 };
 
 }  // namespace ecmc

@@ -61,7 +61,12 @@ ECMC_D double lj_force_bound(const LennardJones &p, double perp2) {
 // key of a candidate time in the scheduler's order: see time_key (a rounding-negative x sorts first)
 ECMC_D double time_order(double x) { return x > 0.0 ? x : 0.0; }
 
-template <bool RECORD, bool PRUNE, int G, int WARPS>
+// HOST: one launch is a whole step from host buffers (ecmc_submit_from_host_sparse): before the events the warp reads
+// its chain's start configuration from RunArgs.host_in (the caller's pinned buffer, read over the link by the loads of
+// the kernel itself -- no staging copy, no separate pack / start kernels waiting for a free SM), bins it into the cells
+// and starts the run (start_chain); every position the events change is written through to RunArgs.host_out -- the
+// position of a particle when it hands the activity over, and the last active particle at the end.
+template <bool RECORD, bool PRUNE, int G, int WARPS, bool HOST = false>
 __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     static_assert(G == 4 || G == 8, "lanes per event");
@@ -88,6 +93,35 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     int *occ = S.occupants + (size_t)chain * P.n_cells;
     int *sur = S.surplus + (size_t)chain * P.max_surplus;
     EcmcChainState *stp = S.chains + chain;
+    unsigned host_writes = 0;
+    if (HOST) {
+        // the start configuration: 3 n doubles, read as a flat array (coalesced, eight loads in flight per lane) and
+        // scattered into the 32-byte particle records; chargeless programs only (charge = 1)
+        const double *in = A.host_in + (size_t)chain * P.n_particles * 3;
+        double *records = reinterpret_cast<double *>(part);
+        const int n_values = P.n_particles * 3;
+#pragma unroll 1
+        for (int base = 0; base < n_values; base += 256) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = base + j * 32 + lane;
+                v[j] = idx < n_values ? __ldcv(in + idx) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = base + j * 32 + lane;
+                if (idx < n_values) {
+                    const int particle = idx / 3;
+                    records[4 * particle + (idx - 3 * particle)] = v[j];
+                }
+            }
+        }
+        for (int i = lane; i < P.n_particles; i += 32) records[4 * i + 3] = 1.0;
+        __syncwarp();
+        start_chain(P, S, nullptr, A.first_stream, A.initial_active, A.initial_direction, A.stats, chain, lane);
+        __syncwarp();
+    }
 
     // chain state -> registers (uniform over the warp)
     int active = stp->active, dir = stp->direction;
@@ -285,6 +319,11 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             // uniform u of its potential change
             auto candidate = [&](int i, double u) {
                 const double s0 = correct_separation_in_box(l_p0[i] - my_x, L, half);
+#ifdef ECMC_SPEC_PREFILTER
+                // second level of the pruning: the exact energy rise over the reach of this event (one division) against
+                // the lower bound u / beta of the potential change; only what may fire is inverted
+                if (PRUNE && !lj_may_fire_within(lj, s0, l_perp2[i], reach, u * P.inv_beta)) return;
+#endif
                 const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
                 const double x = my_now.r + lj_displacement(lj, s0, l_perp2[i], du) * P.inv_speed;
                 if (x < INFINITY) {  // heap_scheduler.py:139; NaN never wins
@@ -310,6 +349,36 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 const double threshold = reach * (P.beta / (1.0 - 1.0e-9));  // bound * reach < u / beta (1 - 1e-9)
                 int queued = -1;
                 double queued_u = 0.0;
+#ifdef ECMC_SPEC_UNROLL2
+                // two list entries per iteration: their Philox blocks are independent dependency chains
+#pragma unroll 1
+                for (int base = 0;; base += 2 * G) {
+                    const bool last = base >= count;
+                    const int ia = base + g, ib = base + G + g;
+                    bool maybe_a = false, maybe_b = false;
+                    double ua = 0.0, ub = 0.0;
+                    if (!last) {
+                        const bool valid_a = ia < count, valid_b = ib < count;
+                        const Philox4 pa = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, valid_a ? l_target[ia] : 0), 0);
+                        const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, valid_b ? l_target[ib] : 0), 0);
+                        ua = words_to_double(pa.w[0], pa.w[1]);
+                        ub = words_to_double(pb.w[0], pb.w[1]);
+                        maybe_a = valid_a && (beyond_window || !(l_bound[ia] * threshold < ua));
+                        maybe_b = valid_b && (beyond_window || !(l_bound[ib] * threshold < ub));
+                    }
+                    if (__any_sync(kFull, queued >= 0 && (last || maybe_a || maybe_b))) {
+                        if (queued >= 0) candidate(queued, queued_u);
+                        queued = -1;
+                    }
+                    if (last) break;
+                    if (maybe_a) { queued = ia; queued_u = ua; }
+                    if (__any_sync(kFull, maybe_a && maybe_b)) {  // both entries of a lane: rare
+                        if (maybe_a && maybe_b) candidate(queued, queued_u);
+                        if (maybe_a && maybe_b) queued = -1;
+                    }
+                    if (maybe_b) { queued = ib; queued_u = ub; }
+                }
+#else
 #pragma unroll 1
                 for (int base = 0;; base += G) {
                     const bool last = base >= count;
@@ -329,6 +398,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                     if (last) break;
                     if (maybe) { queued = i; queued_u = u; }
                 }
+#endif
             }
             // combine the G shares of an event
 #pragma unroll
@@ -537,6 +607,11 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 int delta = 0;
                 if (lane == 0) {
                     store_position(part + active, lab);
+                    if (HOST) {
+                        double *out = A.host_out + ((size_t)chain * P.n_particles + active) * 3;
+                        out[0] = lab.x; out[1] = lab.y; out[2] = lab.z;
+                        host_writes++;
+                    }
                     delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, active_cell, active);
                 }
                 delta = __shfl_sync(kFull, delta, 0);
@@ -573,6 +648,12 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     }
     if (lane == 0) {
         store_position(part + active, rotate_out(a, dir));
+        if (HOST) {
+            const Particle lab = rotate_out(a, dir);
+            double *out = A.host_out + ((size_t)chain * P.n_particles + active) * 3;
+            out[0] = lab.x; out[1] = lab.y; out[2] = lab.z;
+            if (A.host_writes) atomicAdd(A.host_writes, (unsigned long long)(host_writes + 1));
+        }
         stp->active = active; stp->direction = dir;
         stp->time_q = now.q; stp->time_r = now.r;
         stp->eoc_q = eoc.q; stp->eoc_r = eoc.r;

@@ -569,7 +569,7 @@ def shipped_without_sampling(ref_root, relative, end_of_run_time=1.0e9, replacem
         parser.remove_section(camel(tag))
         parser.remove_section(camel(handler))
     for section in parser.sections():
-        for key in ("create", "trash"):
+        for key in ("create", "trash", "activate", "deactivate"):
             if parser.has_option(section, key):
                 kept = [item.strip() for item in parser.get(section, key).split(",") if item.strip() not in sampling]
                 parser.set(section, key, ", ".join(kept))

@@ -171,6 +171,27 @@ def test_lennard_jones_batch_against_oracle(oracle):
     assert stats["pair_events"] > 1000 and stats["veto_accepted"] > 0 and stats["end_of_chain_events"] > 0
 
 
+def test_lennard_jones_2d_against_oracle(oracle):
+    """Two-dimensional Lennard-Jones with a cell veto: the Lennard-Jones kernels that hard-wire three dimensions must not
+    be picked (pick_kernel), the end of chain rotates the direction through two axes only."""
+    pot = abi.EcmcPotential.make(abi.POT_LENNARD_JONES, 4.0, 1.0)
+    cells, length, n, n_chains = 5, 6.5, 30, 11
+    bounds, far = oracle.inner_point_derivative_bounds(pot, length, [cells] * 2, 1, prefactor=4.0, points_per_side=3)
+    pb = ProgramBuilder(2, n, length, 1.0, [cells] * 2, 1, max_occupants=1, max_surplus=n, chain_time=1.3, seed=5)
+    pb.set_pair(abi.PAIR_TWO_LEAF_UNIT, pot)
+    pb.set_veto(pot, oracle.veto_tables(bounds, far))
+    rng = np.random.default_rng(7)
+    side = int(np.ceil(n ** 0.5))
+    grid = np.stack(np.meshgrid(*[np.arange(side)] * 2, indexing="ij"), axis=-1).reshape(-1, 2)[:n]
+    positions = np.stack([((grid + 0.5) * (length / side) + rng.uniform(-0.12, 0.12, size=(n, 2))) % length
+                          for _ in range(n_chains)])
+    with engine.Engine(pb, n_chains=n_chains) as eng:
+        assert "event_kernel" in eng.kernel_name()  # not the batched kernel, which is three-dimensional
+    stats = _compare_batch_with_oracle(oracle, pb, positions, None, 1200, 300, "lj 2d", resync_every=300)
+    assert stats["pair_events"] > 1000 and stats["veto_events"] > 1000 and stats["end_of_chain_events"] > 100
+    assert stats["boundary_events"] > 100
+
+
 def test_several_occupants_per_cell_against_oracle(oracle):
     pb, positions = _lj_batch(oracle, n_chains=9, n=100, cells=4, length=5.2, seed=9, max_occupants=2)
     _compare_batch_with_oracle(oracle, pb, positions, None, 800, 50, "lj m=3")
@@ -692,15 +713,20 @@ def test_submitted_host_steps_equal_blocking_host_steps(oracle):
             queued.submit_from_host(positions[:10], max_events=5, out=buffers[0])
 
 
-def test_sparse_write_back_equals_the_full_copy(oracle):
+@pytest.mark.parametrize("fused", [True, False])
+def test_sparse_write_back_equals_the_full_copy(oracle, fused):
     """ecmc_submit_from_host_sparse: three steps chained IN PLACE through one pinned buffer (ecmc_host_alloc), the device
     writing only the coordinates of the particles that moved, against three blocking full-copy ecmc_run_from_host calls:
-    the buffer ends as the same complete configuration bit for bit; the bytes written are those of the particles that
-    differ between the input and the output of each step; ordinary (pageable) memory is refused."""
+    the buffer ends as the same complete configuration bit for bit; ordinary (pageable) memory is refused.
+    fused: the whole step is one launch per chain slice (lj_spec_kernel<HOST>: the kernel reads the pinned buffer itself,
+    bins, runs the events and writes every hand-over through) -- the bytes written are one position per hand-over plus
+    the last active particle of every chain; otherwise copy -> pack -> start -> events -> write-back of the particles that
+    differ from the step's input, whose bytes are exactly those."""
     pb, positions = _lj_batch(oracle, n_chains=600, seed=22)
     buffer = engine.pinned_array(positions.shape)
     buffer[...] = positions
     with engine.Engine(pb, n_chains=600) as blocking, engine.Engine(pb, n_chains=600) as sparse:
+        sparse.set_option(engine.Engine.OPTION_FUSED_HOST_STEPS, int(fused))
         current, totals, moved = positions, {}, 0
         for k in range(3):
             after, stats = blocking.run_from_host(current, first_stream=1000 * k, max_events=150)
@@ -714,7 +740,12 @@ def test_sparse_write_back_equals_the_full_copy(oracle):
         assert np.array_equal(buffer, current)
         assert {k: v for k, v in stats.items() if k != "candidates"} == {k: v for k, v in totals.items() if k != "candidates"}
         assert np.array_equal(sparse.download_positions(), blocking.download_positions())
-        assert sparse.host_bytes_written == moved * 3 * 8 and 0 < moved < 0.5 * 3 * positions.shape[0] * positions.shape[1]
+        assert 0 < moved < 0.5 * 3 * positions.shape[0] * positions.shape[1]
+        if fused:
+            hand_overs = totals["pair_events"] + totals["veto_accepted"] + totals["end_of_chain_events"]
+            assert moved * 24 <= sparse.host_bytes_written <= (hand_overs + 3 * 600) * 24
+        else:
+            assert sparse.host_bytes_written == moved * 3 * 8
         pageable = positions.copy()
         with pytest.raises(RuntimeError, match="pinned"):
             sparse.submit_from_host(pageable, max_events=5, out=pageable, sparse=True)
