@@ -12,10 +12,14 @@ region) and `c5` (one Lennard-Jones chain of 65536 particles; value = 1 / latenc
 `events_per_chain_per_step` events (one ecmc_run launch). One JSON line is printed by rank 0:
 
   value      events/s over all ranks, chain state resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e        the same step from HOST buffers: pinned host configuration in -> H2D -> cell binning / start of run ->
-             events -> D2H configuration out; step k+1 reads the configuration step k wrote and uses fresh random
-             streams, so the steps walk through the same stretch of the chains' history as the device-timed steps;
-             host clock around synchronous calls
+  e2e        the same steps from HOST buffers: every step takes the configuration from a pinned host buffer (the whole
+             configuration crosses the link), bins it into the cells, runs the events and returns the configuration to
+             the host -- through ecmc_submit_from_host_sparse (only the particles that moved are written back, by the
+             device; "full_copy": ecmc_submit_from_host, "synchronous": the blocking ecmc_run_from_host). The chains
+             restart from the start configuration with the same random streams and CONTINUE from step to step
+             (ECMC_OPTION_CONTINUE_HOST_STEPS), so a leg runs the events of the device-timed region: --warmup untimed
+             steps, then --e2e-steps (default --steps) timed ones; host clock between barriers. Composite objects (c1,
+             c4): upload / start / run / download calls, a start of run per step
   roofline   the event kernel against the measured HBM peak: SURVEY.md 8(d)'s algorithmic bytes per event x the events of
              one launch / the launch duration measured in THIS run (CUDA events around every launch);
              "traffic" only when a committed ncu capture of the SAME kernel exists (source named, else null)
@@ -54,7 +58,8 @@ def parse_args():
     parser.add_argument("--particles", type=int, default=None, help="C2 / C3: particles per chain; C4: molecules")
     parser.add_argument("--cells", type=int, default=None, help="C2: cells per side")
     parser.add_argument("--events", type=int, default=None, help="events per chain and step")
-    parser.add_argument("--e2e-steps", type=int, default=8)
+    parser.add_argument("--e2e-steps", type=int, default=None,
+                        help="steps of each end-to-end leg (default: --steps, the same number the device-timed region runs)")
     parser.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the CPU baseline sample")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--ref-seconds", type=float, default=None,
@@ -649,27 +654,21 @@ def run_ours(args, rank, local_rank, world):
     d2h = host["positions"].nbytes + (host["roots"].nbytes if "roots" in host else 0) + 96
     total_chains = world * workload.chains
 
-    def e2e_step(k):
-        """Configuration in from the pinned buffer step k - 1 wrote, out into the other one; fresh random streams."""
-        source, target = k % 2, (k + 1) % 2
-        first_stream = first_chain + (k + 1) * total_chains
-        charges = pinned["charges"][0].numpy() if "charges" in pinned else None
-        if workload.composite:
-            eng.upload_positions(pinned["positions"][source].numpy(), charges)
-            eng.upload_roots(pinned["roots"][source].numpy())
-            eng.start(first_stream=first_stream)
-            eng.run(max_events=workload.events)
-            step_stats = eng.sync()
-            pinned["positions"][target].numpy()[...] = eng.download_positions()
-            pinned["roots"][target].numpy()[...] = eng.download_roots()
-            return step_stats
-        _, step_stats = eng.run_from_host(pinned["positions"][source].numpy(), charges, first_stream=first_stream,
-                                          max_events=workload.events, out=pinned["positions"][target].numpy())
-        return step_stats
+    pipelined = not workload.composite
+    charges = pinned["charges"][0].numpy() if "charges" in pinned else None
 
-    e2e_warmup = 2
-    for k in range(e2e_warmup):  # first touch of the pinned buffers, stream creation
-        e2e_step(k)
+    def e2e_step(k):
+        """Composite objects: configuration in from the pinned buffer step k - 1 wrote, out into the other one; a start of
+        run with fresh random streams per step (upload, start, run, download calls)."""
+        source, target = k % 2, (k + 1) % 2
+        eng.upload_positions(pinned["positions"][source].numpy(), charges)
+        eng.upload_roots(pinned["roots"][source].numpy())
+        eng.start(first_stream=first_chain + (k + 1) * total_chains)
+        eng.run(max_events=workload.events)
+        step_stats = eng.sync()
+        pinned["positions"][target].numpy()[...] = eng.download_positions()
+        pinned["roots"][target].numpy()[...] = eng.download_roots()
+        return step_stats
 
     def link_rate(to_device):
         """GB/s of one pinned-host <-> device copy of the positions buffer alone (CUDA events): what bounds an e2e step."""
@@ -696,61 +695,80 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     # (the probe copies buffer 0 to the device and back: its content is unchanged)
     e2e_launches_before = eng.kernel_launches
-    barrier()
-    t0 = time.perf_counter()
-    e2e_events, e2e_targets = 0, 0
-    for k in range(e2e_warmup, e2e_warmup + args.e2e_steps):
-        step_stats = e2e_step(k)
-        e2e_events += step_stats["events"]
-        e2e_targets += step_stats["pair_targets"]
-    barrier()
-    sync_e2e_seconds = time.perf_counter() - t0
-    sync_e2e_events = e2e_events
-    e2e_seconds = sync_e2e_seconds
-    pipelined = not workload.composite
-    if pipelined:
-        # the same steps through the non-blocking form of the call: ecmc_submit_from_host enqueues a step, the steps are
-        # ordered slice by slice on the device (step k + 1 reads the pinned buffer step k writes), ecmc_wait at the end.
-        # Every byte of every step still crosses the host link; only the host thread does not block between steps.
-        first = e2e_warmup + args.e2e_steps
-        charges = pinned["charges"][0].numpy() if "charges" in pinned else None
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(first, first + args.e2e_steps):
-            eng.submit_from_host(pinned["positions"][k % 2].numpy(), charges, first_stream=first_chain + (k + 1) * total_chains,
-                                 max_events=workload.events, out=pinned["positions"][(k + 1) % 2].numpy())
-        wait_stats = eng.wait()
-        barrier()
-        e2e_seconds = time.perf_counter() - t0
-        e2e_events, e2e_targets = wait_stats["events"], wait_stats["pair_targets"]
-    # The same steps with the sparse write-back (ecmc_submit_from_host_sparse): ONE pinned buffer, every step uploads the
-    # whole configuration from it and the device writes back, into the same buffer, only the coordinates of the particles
-    # that moved during the step (the active ones: about a tenth of all for these steps). After every step the buffer is
-    # the complete configuration, which the next step uploads.
-    sparse_seconds, sparse_events, sparse_targets, sparse_bytes = 0.0, 0, 0, 0
-    staged_launches = eng.kernel_launches - e2e_launches_before
-    if pipelined:
-        first = e2e_warmup + 2 * args.e2e_steps
-        in_place = engine.pinned_array(host["positions"].shape)
-        in_place[...] = pinned["positions"][first % 2].numpy()  # the configuration the last full-copy step returned
-        eng.submit_from_host(in_place, charges, first_stream=first_chain + (first + 1) * total_chains,
-                             max_events=workload.events, out=in_place, sparse=True)
-        eng.wait()
+
+    def host_leg(mode):
+        """One end-to-end leg over the SAME events as the device-timed region: the chains restart from the start
+        configuration with the same random streams, and every step takes the configuration from the pinned host buffer the
+        step before returned it in, continuing the chains (ECMC_OPTION_CONTINUE_HOST_STEPS: the lifting state stays on the
+        device, the cell occupancy is rebuilt from the uploaded configuration). --warmup untimed steps, then --e2e-steps
+        timed ones. mode: "blocking" (ecmc_run_from_host per step), "full" (ecmc_submit_from_host x steps + ecmc_wait, the
+        whole configuration copied back), "sparse" (ecmc_submit_from_host_sparse in place on one buffer)."""
+        buffers = [engine.pinned_array(host["positions"].shape)] if mode == "sparse" else \
+                  [pinned["positions"][0].numpy(), pinned["positions"][1].numpy()]
+        buffers[0][...] = host["positions"]
+        eng.set_option(eng.OPTION_CONTINUE_HOST_STEPS, 1)
+        eng.upload_positions(host["positions"], charges)
+        eng.start(first_stream=first_chain)
+        n = len(buffers)
+
+        def submit(k):
+            if mode == "blocking":
+                return eng.run_from_host(buffers[k % n], charges, max_events=workload.events, out=buffers[(k + 1) % n])[1]
+            eng.submit_from_host(buffers[k % n], charges, max_events=workload.events, out=buffers[(k + 1) % n],
+                                 sparse=mode == "sparse")
+            return None
+        for k in range(args.warmup):
+            submit(k)
+        if mode != "blocking":
+            eng.wait()
         written_before = eng.host_bytes_written
+        launches_before = eng.kernel_launches
         barrier()
         t0 = time.perf_counter()
-        for k in range(first + 1, first + 1 + args.e2e_steps):
-            eng.submit_from_host(in_place, charges, first_stream=first_chain + (k + 1) * total_chains,
-                                 max_events=workload.events, out=in_place, sparse=True)
-        sparse_stats = eng.wait()
+        events, targets = 0, 0
+        for k in range(args.warmup, args.warmup + args.e2e_steps):
+            step_stats = submit(k)
+            if step_stats is not None:
+                events += step_stats["events"]
+                targets += step_stats["pair_targets"]
+        if mode != "blocking":
+            wait_stats = eng.wait()
+            events, targets = wait_stats["events"], wait_stats["pair_targets"]
         barrier()
-        sparse_seconds = time.perf_counter() - t0
-        sparse_events, sparse_targets = sparse_stats["events"], sparse_stats["pair_targets"]
-        sparse_bytes = (eng.host_bytes_written - written_before) / args.e2e_steps
-    # staged steps, per chain slice: pack, start, events, unpack (ecmc_kernel_launches counts the event kernels); a sparse
-    # step of a Lennard-Jones / cell-veto program is one launch per chain slice, of any other program again four
+        seconds = time.perf_counter() - t0
+        eng.set_option(eng.OPTION_CONTINUE_HOST_STEPS, 0)
+        return {"seconds": seconds, "events": events, "targets": targets, "launches": eng.kernel_launches - launches_before,
+                "bytes_written": (eng.host_bytes_written - written_before) / args.e2e_steps}
+
+    sparse_seconds, sparse_events, sparse_targets, sparse_bytes = 0.0, 0, 0, 0
     fused = pipelined and "lj_spec_kernel" in kernel_name
-    e2e_launches = 4 * staged_launches + (1 if fused else 4) * (eng.kernel_launches - e2e_launches_before - staged_launches)
+    if pipelined:
+        blocking_leg = host_leg("blocking")
+        full_leg = host_leg("full")
+        sparse_leg = host_leg("sparse")
+        sync_e2e_seconds, sync_e2e_events = blocking_leg["seconds"], blocking_leg["events"]
+        e2e_seconds, e2e_events, e2e_targets = full_leg["seconds"], full_leg["events"], full_leg["targets"]
+        sparse_seconds, sparse_events, sparse_targets = sparse_leg["seconds"], sparse_leg["events"], sparse_leg["targets"]
+        sparse_bytes = sparse_leg["bytes_written"]
+        # staged steps, per chain slice: pack, start, events, unpack (ecmc_kernel_launches counts the event kernels); a
+        # sparse step of a Lennard-Jones / cell-veto program is one launch per chain slice, of any other program four
+        e2e_launches = 4 * (blocking_leg["launches"] + full_leg["launches"]) + (1 if fused else 4) * sparse_leg["launches"]
+    else:
+        e2e_warmup = 2
+        for k in range(e2e_warmup):  # first touch of the pinned buffers
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_events, e2e_targets = 0, 0
+        for k in range(e2e_warmup, e2e_warmup + args.e2e_steps):
+            step_stats = e2e_step(k)
+            e2e_events += step_stats["events"]
+            e2e_targets += step_stats["pair_targets"]
+        barrier()
+        sync_e2e_seconds = time.perf_counter() - t0
+        sync_e2e_events = e2e_events
+        e2e_seconds = sync_e2e_seconds
+        e2e_launches = 4 * (eng.kernel_launches - e2e_launches_before)
 
     # ---- an observable reduced over ranks (SURVEY 8e): pair-separation histogram of all chains, one NCCL all-reduce
     if water:
@@ -834,7 +852,11 @@ def run_ours(args, rank, local_rank, world):
                           "ecmc_submit_from_host x steps + ecmc_wait: per step pinned host configuration -> H2D -> cell "
                           "binning -> events -> D2H of the whole configuration on the streams of the chain slices; the host "
                           "does not block between steps, the device orders them slice by slice") +
-                         "; step k + 1 starts from the configuration step k returned, with fresh random streams"}
+                         ("; step k + 1 starts from the configuration step k returned, with fresh random streams"
+                          if workload.composite else
+                          "; the chains restart from the start configuration and run the same events as the device-timed "
+                          "region (--warmup untimed steps first): step k + 1 uploads the configuration step k returned and "
+                          "continues the chains, their lifting state stays on the device (ECMC_OPTION_CONTINUE_HOST_STEPS)")}
     e2e = dict(full_copy)
     if pipelined and max_sparse_seconds > 0.0:
         # the headline: the same steps, the configuration returned through the sparse write-back
@@ -850,8 +872,10 @@ def run_ours(args, rank, local_rank, world):
                         " (H2D copy) -> cell binning -> events -> the device writes the coordinates of the particles that "
                         "moved straight into the host buffer") +
                        " (d2h_bytes_per_step, measured: ecmc_host_bytes_written); the buffer then is the complete "
-                       "configuration again and is what step k + 1 reads; fresh random streams per step; the host does not "
-                       "block between steps",
+                       "configuration again and is what step k + 1 reads; the chains restart from the start configuration "
+                       "and run the same events as the device-timed region (--warmup untimed steps first), continuing from "
+                       "step to step (ECMC_OPTION_CONTINUE_HOST_STEPS: lifting state on the device, cell occupancy rebuilt "
+                       "from every uploaded configuration); the host does not block between steps",
                "full_copy": full_copy}
     e2e["link_gb_per_s"] = {"h2d": h2d_rate, "d2h": d2h_rate, "h2d_all_ranks_at_once_per_rank": shared_h2d_rate,
                             "note": "one pinned copy of the positions buffer alone on rank 0, best of 3: h2d_bytes / h2d rate "
@@ -905,6 +929,8 @@ def emit(line):
 def main():
     global _RESULT_FD
     args = parse_args()
+    if args.e2e_steps is None:
+        args.e2e_steps = args.steps
     sys.stdout.flush()
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)  # file-descriptor level: also catches what native libraries print

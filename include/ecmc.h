@@ -430,9 +430,16 @@ int ecmc_bond_histograms(EcmcHandle *h, int32_t n_bins, double length_min, doubl
  *   ECMC_OPTION_FUSED_HOST_STEPS  1 (default) / 0: ecmc_submit_from_host_sparse of these programs runs a host step as ONE
  *                                 launch per chain slice -- the kernel reads the start configuration from the pinned
  *                                 buffer itself, bins it into the cells, runs the events and writes every position it
- *                                 changes through to the buffer -- instead of copy, pack, start, events, write-back */
+ *                                 changes through to the buffer -- instead of copy, pack, start, events, write-back
+ *   ECMC_OPTION_CONTINUE_HOST_STEPS 0 (default) / 1: a step of ecmc_run_from_host / ecmc_submit_from_host[_sparse] on a
+ *                                 handle that has run before CONTINUES its chains -- active unit, direction, clock, end of
+ *                                 chain, event counter and random stream stay what the last launch left on the device,
+ *                                 only the configuration comes from the host and the cell occupancy is rebuilt from it
+ *                                 (first_stream is then ignored) -- instead of a start of run per step
+ *                                 (initial_chain_start_of_run_event_handler.py:92-131). While no cell holds two
+ *                                 particles the events are those of an uninterrupted ecmc_run, bit for bit. */
 enum EcmcOption { ECMC_OPTION_BATCHED_EVENTS = 1, ECMC_OPTION_PRUNE_CANDIDATES = 2, ECMC_OPTION_LANES_PER_EVENT = 3,
-                  ECMC_OPTION_CHAIN_BLOCKS = 4, ECMC_OPTION_FUSED_HOST_STEPS = 5 };
+                  ECMC_OPTION_CHAIN_BLOCKS = 4, ECMC_OPTION_FUSED_HOST_STEPS = 5, ECMC_OPTION_CONTINUE_HOST_STEPS = 6 };
 int ecmc_set_option(EcmcHandle *h, int option, int value);
 
 /* The CUDA stream the handle launches on (a cudaStream_t), so callers can time with events on it. */

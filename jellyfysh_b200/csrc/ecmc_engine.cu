@@ -70,6 +70,7 @@ struct EcmcHandle {
     int spec_lanes = 4;      // lanes per speculated event (4: 8 events per batch, 8: 4 events per batch)
     bool chain_blocks = true; // few chains: lj_chain_kernel, one CTA of four warps per chain (ecmc_spec_cta.cuh)
     bool host_fused = true;   // sparse host steps of Lennard-Jones / cell-veto programs as ONE launch per chain slice
+    bool host_continue = false; // host steps continue the chains instead of starting a new run each (ecmc_set_option)
     std::string kernel_name; // ecmc_kernel_name
     bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
     unsigned long long *d_changed = nullptr;  // particles written back by ecmc_submit_from_host_sparse since the last wait
@@ -876,7 +877,7 @@ ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_s
     else
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
             h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
-            h->program.initial_direction, h->d_stats);
+            h->program.initial_direction, h->d_stats, false);
     if (h->disks)
         disk_start_kernel<<<(h->n_chains + 127) / 128, 128, 0, h->stream>>>(h->state, h->dprog.speed, h->kprog.weight,
                                                                            h->kprog.initial_direction);
@@ -1075,6 +1076,9 @@ int submit_from_host(EcmcHandle *h, const double *positions_in, const double *ch
     // Lennard-Jones / cell-veto programs with a sparse write-back: one launch per chain slice does the whole step -- the
     // kernel reads the configuration from the pinned buffer itself, bins it, runs the events and writes the positions it
     // changes through to the buffer (lj_spec_kernel<..., HOST>); nothing is staged, no copy engine is involved
+    // ECMC_OPTION_CONTINUE_HOST_STEPS: from the second step on the chains continue (lifting state kept on the device)
+    const bool keep_state = h->host_continue && h->started;
+    args.keep_state = keep_state ? 1 : 0;
     bool fused = sparse && !charges && spec.kernel && !spec.chain_blocks && h->host_fused;
     bool fused_copy = true;
     if (const char *env = std::getenv("ECMC_FUSED_ZEROCOPY")) fused_copy = std::atoi(env) == 0;
@@ -1151,7 +1155,7 @@ int submit_from_host(EcmcHandle *h, const double *positions_in, const double *ch
         slice.n_chains = count;
         const int blocks = (count + kWarpsPerBlock - 1) / kWarpsPerBlock;
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, s>>>(
-            d, slice, nullptr, first_stream, h->program.initial_active, h->program.initial_direction, h->d_stats);
+            d, slice, nullptr, first_stream, h->program.initial_active, h->program.initial_direction, h->d_stats, keep_state);
         if (spec.chain_blocks) kernel<<<count, kChainWarps * 32, spec.shared_bytes, s>>>(d, slice, args);
         else kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, s>>>(d, slice, args);
         CUDA_TRY(h, cudaGetLastError());
@@ -1324,6 +1328,7 @@ ECMC_API int ecmc_set_option(EcmcHandle *h, int option, int value) {
     case ECMC_OPTION_PRUNE_CANDIDATES: h->spec_prune = value != 0; return ECMC_OK;
     case ECMC_OPTION_CHAIN_BLOCKS: h->chain_blocks = value != 0; return ECMC_OK;
     case ECMC_OPTION_FUSED_HOST_STEPS: h->host_fused = value != 0; return ECMC_OK;
+    case ECMC_OPTION_CONTINUE_HOST_STEPS: h->host_continue = value != 0; return ECMC_OK;
     case ECMC_OPTION_LANES_PER_EVENT:
         if (value != 4 && value != 8) return fail(h, ECMC_ERR_INVALID, "lanes per event: 4 or 8");
         h->spec_lanes = value;

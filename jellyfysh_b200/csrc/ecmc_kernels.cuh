@@ -874,9 +874,14 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
 // InitialChainStartOfRunEventHandler (initial_chain_start_of_run_event_handler.py:92-131). One warp per chain.
 // Particles enter in identifier order: the first max_occupants of a cell become occupants, the rest surplus.
 // ---------------------------------------------------------------------------------------------------------
-// start of run of ONE chain by its warp (all 32 lanes call it)
+// start of run of ONE chain by its warp (all 32 lanes call it).
+// keep_state (host steps that CONTINUE their chains, ECMC_OPTION_CONTINUE_HOST_STEPS): the configuration was replaced by
+// the caller's, the lifting state of the chain -- active particle, direction, clock, end of chain, event counter, random
+// stream -- stays what the last launch left; only the cell occupancy is rebuilt from the positions
+// (SingleActiveCellOccupancy.initialize, :95-121) and a kept candidate is dropped.
 ECMC_D void start_chain(const DeviceProgram &P, const DeviceState &S, const uint32_t *streams, uint32_t first_stream,
-                        int initial_active, int initial_direction, EcmcStats *stats, int chain, int lane) {
+                        int initial_active, int initial_direction, EcmcStats *stats, int chain, int lane,
+                        bool keep_state = false) {
     Particle *part = S.particles + (size_t)chain * P.n_particles;
     const int m = P.max_occupants;
     int *occ = S.occupants + (size_t)chain * P.n_cells * m;
@@ -924,7 +929,20 @@ ECMC_D void start_chain(const DeviceProgram &P, const DeviceState &S, const uint
         overflow = __shfl_sync(kFull, overflow, 0);
     }
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && keep_state) {
+        EcmcChainState st = S.chains[chain];
+        int id[3];
+        const Particle a = part[st.active];
+        cell_identifier_of(P, a, id);
+        st.active_cell = flat_cell(P, id);
+        const int delta = occupancy_remove(occ, sur, n_surplus, m, st.active_cell, st.active);
+        if (delta == 2) overflow++; else n_surplus += delta;
+        st.pending_kind = ECMC_EVENT_NONE;
+        st.kept_kind = 0;
+        S.chains[chain] = st;
+        S.n_surplus[chain] = n_surplus;
+        if (overflow && stats) atomicAdd(reinterpret_cast<unsigned long long *>(stats) + 8, (unsigned long long)overflow);
+    } else if (lane == 0) {
         EcmcChainState st = {};  // every field defined: the state is downloaded, compared and checkpointed as bytes
         st.active = initial_active; st.direction = initial_direction;
         st.time_q = 0.0; st.time_r = 0.0;
@@ -954,11 +972,11 @@ ECMC_D void start_chain(const DeviceProgram &P, const DeviceState &S, const uint
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams, uint32_t first_stream,
-             int initial_active, int initial_direction, EcmcStats *stats) {
+             int initial_active, int initial_direction, EcmcStats *stats, bool keep_state) {
     const int lane = threadIdx.x & 31;
     const int chain = S.first_chain + blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (chain >= S.first_chain + S.n_chains) return;
-    start_chain(P, S, streams, first_stream, initial_active, initial_direction, stats, chain, lane);
+    start_chain(P, S, streams, first_stream, initial_active, initial_direction, stats, chain, lane, keep_state);
 }
 
 // host layout [n_chains][n_particles][dimension] (+ charges [n_chains][n_particles]) <-> 32-byte particle records

@@ -106,6 +106,7 @@ struct RunArgs {
     uint32_t first_stream;
     int initial_active, initial_direction;
     unsigned long long *host_writes;  // counts the particles written to host_out
+    int keep_state;         // the step continues the chains (start_chain)
 };
 
 }  // namespace ecmc

@@ -119,7 +119,8 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
         }
         for (int i = lane; i < P.n_particles; i += 32) records[4 * i + 3] = 1.0;
         __syncwarp();
-        start_chain(P, S, nullptr, A.first_stream, A.initial_active, A.initial_direction, A.stats, chain, lane);
+        start_chain(P, S, nullptr, A.first_stream, A.initial_active, A.initial_direction, A.stats, chain, lane,
+                    A.keep_state != 0);
         __syncwarp();
     }
 
@@ -319,11 +320,6 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             // uniform u of its potential change
             auto candidate = [&](int i, double u) {
                 const double s0 = correct_separation_in_box(l_p0[i] - my_x, L, half);
-#ifdef ECMC_SPEC_PREFILTER
-                // second level of the pruning: the exact energy rise over the reach of this event (one division) against
-                // the lower bound u / beta of the potential change; only what may fire is inverted
-                if (PRUNE && !lj_may_fire_within(lj, s0, l_perp2[i], reach, u * P.inv_beta)) return;
-#endif
                 const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
                 const double x = my_now.r + lj_displacement(lj, s0, l_perp2[i], du) * P.inv_speed;
                 if (x < INFINITY) {  // heap_scheduler.py:139; NaN never wins
@@ -349,36 +345,6 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 const double threshold = reach * (P.beta / (1.0 - 1.0e-9));  // bound * reach < u / beta (1 - 1e-9)
                 int queued = -1;
                 double queued_u = 0.0;
-#ifdef ECMC_SPEC_UNROLL2
-                // two list entries per iteration: their Philox blocks are independent dependency chains
-#pragma unroll 1
-                for (int base = 0;; base += 2 * G) {
-                    const bool last = base >= count;
-                    const int ia = base + g, ib = base + G + g;
-                    bool maybe_a = false, maybe_b = false;
-                    double ua = 0.0, ub = 0.0;
-                    if (!last) {
-                        const bool valid_a = ia < count, valid_b = ib < count;
-                        const Philox4 pa = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, valid_a ? l_target[ia] : 0), 0);
-                        const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, valid_b ? l_target[ib] : 0), 0);
-                        ua = words_to_double(pa.w[0], pa.w[1]);
-                        ub = words_to_double(pb.w[0], pb.w[1]);
-                        maybe_a = valid_a && (beyond_window || !(l_bound[ia] * threshold < ua));
-                        maybe_b = valid_b && (beyond_window || !(l_bound[ib] * threshold < ub));
-                    }
-                    if (__any_sync(kFull, queued >= 0 && (last || maybe_a || maybe_b))) {
-                        if (queued >= 0) candidate(queued, queued_u);
-                        queued = -1;
-                    }
-                    if (last) break;
-                    if (maybe_a) { queued = ia; queued_u = ua; }
-                    if (__any_sync(kFull, maybe_a && maybe_b)) {  // both entries of a lane: rare
-                        if (maybe_a && maybe_b) candidate(queued, queued_u);
-                        if (maybe_a && maybe_b) queued = -1;
-                    }
-                    if (maybe_b) { queued = ib; queued_u = ub; }
-                }
-#else
 #pragma unroll 1
                 for (int base = 0;; base += G) {
                     const bool last = base >= count;
@@ -398,7 +364,6 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                     if (last) break;
                     if (maybe) { queued = i; queued_u = u; }
                 }
-#endif
             }
             // combine the G shares of an event
 #pragma unroll

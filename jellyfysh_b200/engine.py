@@ -203,7 +203,7 @@ class Engine:
         self._check(self._lib.ecmc_upload_cells(self._h, _ptr(occ), _ptr(sur), _ptr(n)))
 
     OPTION_BATCHED_EVENTS, OPTION_PRUNE_CANDIDATES, OPTION_LANES_PER_EVENT, OPTION_CHAIN_BLOCKS = 1, 2, 3, 4
-    OPTION_FUSED_HOST_STEPS = 5
+    OPTION_FUSED_HOST_STEPS, OPTION_CONTINUE_HOST_STEPS = 5, 6
 
     def set_option(self, option, value):
         """ecmc_set_option: how the device schedules the events (batched speculative evaluation, candidate pruning)."""

@@ -751,6 +751,48 @@ def test_sparse_write_back_equals_the_full_copy(oracle, fused):
             sparse.submit_from_host(pageable, max_events=5, out=pageable, sparse=True)
 
 
+@pytest.mark.parametrize("sparse", [True, False])
+def test_continued_host_steps_equal_the_resident_run(oracle, sparse):
+    """ECMC_OPTION_CONTINUE_HOST_STEPS: host steps that keep the lifting state of their chains on the device and take only
+    the configuration from the host (cell occupancy rebuilt from it every step) against ONE engine that runs the same
+    events without leaving the device. While no cell holds two particles the rebuilt occupancy is the one the resident
+    chain carries, so positions and chain states agree bit for bit; chains that did put a particle into the surplus are
+    only required to have run their events."""
+    n_chains, steps, events = 300, 4, 150
+    pb, positions = _lj_batch(oracle, n_chains=n_chains, seed=23)
+    buffer = engine.pinned_array(positions.shape)
+    buffer[...] = positions
+    with engine.Engine(pb, n_chains=n_chains) as resident, engine.Engine(pb, n_chains=n_chains) as stepped:
+        resident.upload_positions(positions)
+        resident.start(first_stream=77)
+        clean = np.ones(n_chains, dtype=bool)  # no surplus particle at any step boundary so far
+        for k in range(steps):
+            resident.run(max_events=events)
+            resident.sync()
+            if k + 1 < steps:
+                clean &= np.array([len(surplus) == 0 for surplus in resident.cells()[1]])
+        stepped.set_option(engine.Engine.OPTION_CONTINUE_HOST_STEPS, 1)
+        stepped.upload_positions(positions)
+        stepped.start(first_stream=77)
+        total = 0
+        for k in range(steps):
+            if sparse:
+                stepped.submit_from_host(buffer, first_stream=12345, max_events=events, out=buffer, sparse=True)
+                total += stepped.wait()["events"]
+            else:
+                out, stats = stepped.run_from_host(buffer, first_stream=12345, max_events=events)
+                buffer[...] = out
+                total += stats["events"]
+        assert total == n_chains * steps * events
+        assert clean.sum() > n_chains // 2, clean.sum()
+        ours, theirs = stepped.chain_states(), resident.chain_states()
+        assert np.array_equal(ours["event_counter"], theirs["event_counter"])
+        assert np.array_equal(ours["stream"], theirs["stream"])
+        for field in ("active", "direction", "time_q", "time_r", "eoc_q", "eoc_r", "eoc_next_active", "active_cell"):
+            assert np.array_equal(ours[field][clean], theirs[field][clean]), field
+        assert np.array_equal(buffer[clean], resident.download_positions()[clean])
+
+
 def test_pruned_launches_reach_the_same_state(oracle):
     """The kernel instantiations with and without event records must commit the same events: identical positions, cells
     and chain states bit for bit, the same event counts. (Launches without records skip pair candidates that provably
