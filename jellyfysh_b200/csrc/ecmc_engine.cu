@@ -73,6 +73,7 @@ struct EcmcHandle {
     bool host_continue = false; // host steps continue the chains instead of starting a new run each (ecmc_set_option)
     std::string kernel_name; // ecmc_kernel_name
     bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
+    int slices_layout = 0;    // ... and how its chains were cut into slices (steps are ordered slice by slice)
     unsigned long long *d_changed = nullptr;  // particles written back by ecmc_submit_from_host_sparse since the last wait
     uint64_t host_bytes_written = 0;          // ... as bytes, accumulated by ecmc_wait
     std::string error;
@@ -582,14 +583,15 @@ bool pick_spec(const EcmcHandle *h, bool record, SpecLaunch *out) {
         if (d.upper[k].n_entries <= 0) return false;
     const bool prune = h->spec_prune && !record;
     const int capacity = (d.n_nearby + d.max_surplus + 31) / 32 * 32;
-    const size_t bytes = (size_t)kWarpsPerBlock * capacity * ((prune ? 3 : 2) + 1) * sizeof(double);
+    // per entry: coordinate, squared distance from the line, (force bound), target + sequence number, (live index)
+    const size_t bytes = (size_t)kWarpsPerBlock * capacity * (prune ? 5 : 3) * sizeof(double);
     if (bytes > 100 * 1024) return false;  // two CTAs per SM
     out->capacity = capacity;
     out->shared_bytes = bytes;
     // few chains (the single large chain C5): one CTA of four warps per chain, 32 events per batch
     out->chain_blocks = h->chain_blocks && h->n_chains <= kChainKernelMaxChains;
     if (out->chain_blocks) {
-        out->shared_bytes = (size_t)capacity * ((prune ? 3 : 2) + 1) * sizeof(double);
+        out->shared_bytes = (size_t)capacity * (prune ? 5 : 3) * sizeof(double);
         if (record) out->kernel = lj_chain_kernel<true, false>;
         else out->kernel = prune ? lj_chain_kernel<false, true> : lj_chain_kernel<false, false>;
         return true;
@@ -1112,6 +1114,11 @@ int submit_from_host(EcmcHandle *h, const double *positions_in, const double *ch
         }
     }
     const int n_slices = fused ? std::max(1, std::min(fused_slices, h->n_chains / (2 * kWarpsPerBlock))) : base_slices;
+    // Steps in flight are ordered stream by stream: a step that cuts the chains differently waits for them
+    const int layout = n_slices * 2 + (fused ? 1 : 0);
+    if (h->slices_busy && layout != h->slices_layout)
+        for (cudaStream_t s : h->slice_streams) CUDA_TRY(h, cudaStreamSynchronize(s));
+    h->slices_layout = layout;
     // (whole CTAs per slice: a slice boundary inside a CTA would leave warps idle)
     const int ctas = (h->n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int base = fused ? 0 : h->n_chains / n_slices, extra = fused ? 0 : h->n_chains % n_slices;

@@ -37,8 +37,11 @@
 // the pair can have there. That force bound is computed when the list is built, for a window of displacement ahead
 // of the active particle (24 mean veto steps; the list is rebuilt when half of it is used up), and stored with the
 // list: one multiplication and one comparison per (event, target) decide, everything within rounding distance of the
-// threshold -- or beyond the window -- is computed in full. The winner of every event is unchanged
-// (tests/test_gpu_spec.py), only EcmcStats.candidates then counts the evaluated candidates.
+// threshold -- or beyond the window -- is computed in full. About half of the targets do not even need their random
+// number: a pair whose energy cannot rise anywhere on the window (the target stays ahead of the active particle and
+// outside the minimum sphere, or behind it and inside) has no event there whatever potential change it draws, so the
+// events inside the window walk over the other, "live", entries only (l_live). The winner of every event is
+// unchanged (tests/test_gpu_spec.py), only EcmcStats.candidates then counts the evaluated candidates.
 #pragma once
 
 #include "ecmc_kernels.cuh"
@@ -57,6 +60,18 @@ ECMC_D double lj_force_bound(const LennardJones &p, double perp2) {
     const double bound = perp2 < p.r_inflection_sq ? fmax(here, p.force_max) : here;
     return bound * (1.0 + 1.0e-9);
 }
+
+// PRUNE: the window of displacement the force bounds of a candidate list cover, in mean cell-veto steps (the list is
+// rebuilt when half of it is used up). Measured on C2 (profiles/README.md).
+#ifndef ECMC_SPEC_WINDOW_STEPS
+#define ECMC_SPEC_WINDOW_STEPS 24.0
+#endif
+constexpr double kWindowSteps = ECMC_SPEC_WINDOW_STEPS;
+// ... and the fraction of the window after which the list is rebuilt
+#ifndef ECMC_SPEC_WINDOW_USE
+#define ECMC_SPEC_WINDOW_USE 0.5
+#endif
+constexpr double kWindowUse = ECMC_SPEC_WINDOW_USE;
 
 // key of a candidate time in the scheduler's order: see time_key (a rounding-negative x sorts first)
 ECMC_D double time_order(double x) { return x > 0.0 ? x : 0.0; }
@@ -80,11 +95,15 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     // the candidate list of this chain: coordinate along the line of motion, squared distance from it, (force bound),
     // target particle, sequence number (= slot in the scan order of the reference's taggers)
     const int cap = A.list_capacity;
-    double *l_p0 = spec_shared + (size_t)warp * cap * (kDoubles + 1);
+    // PRUNE: one more int per entry, the indices of the entries that can fire at all inside the window (l_live)
+    constexpr int kEntryDoubles = PRUNE ? kDoubles + 2 : kDoubles + 1;
+    double *l_p0 = spec_shared + (size_t)warp * cap * kEntryDoubles;
     double *l_perp2 = l_p0 + cap;
     double *l_bound = l_p0 + 2 * cap;  // PRUNE only
     int *l_target = reinterpret_cast<int *>(l_p0 + kDoubles * cap);
     int *l_seq = l_target + cap;
+    int *l_live = l_seq + cap;  // PRUNE only
+    int n_live = 0;
     int count = -1;  // entries of the valid list; -1: rebuild
     double x_build = 0.0, window = 0.0;  // PRUNE: where the list was built, and how far its force bounds reach
 
@@ -179,7 +198,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 // the force bounds of the list hold for a window of displacement from where it was built
                 double travelled = a.p0 - x_build;
                 if (travelled < 0.0) travelled += L;
-                if (!(travelled <= 0.5 * window)) count = -1;
+                if (!(travelled <= kWindowUse * window)) count = -1;
             }
             if (count < 0) {
                 // ---- rebuild the candidate list: occupants of the nearby cells (ExcludedCellsTagger,
@@ -211,11 +230,13 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 __syncwarp();
                 if (PRUNE) {
                     x_build = a.p0;
-                    window = fmin(24.0 * speed * P.inv_beta * P.upper[dir].inv_total_rate_speed, 0.25 * L);
+                    window = fmin(kWindowSteps * speed * P.inv_beta * P.upper[dir].inv_total_rate_speed, 0.25 * L);
                 }
+                n_live = 0;
 #pragma unroll 1
                 for (int base = 0; base < found_so_far; base += 32) {
                     const int i = base + lane;
+                    bool live = false;
                     if (i < found_so_far) {
                         const Moving tp = rotate_in(part[l_target[i]], dir);
                         const double s1 = correct_separation_in_box(tp.p1 - a.p1, L, half);
@@ -230,7 +251,20 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                             double nearest = (ahead >= 0.0 && behind <= 0.0) ? 0.0 : fmin(fabs(ahead), fabs(behind));
                             if (behind < -half) nearest = fmin(nearest, half - window);  // the separation wraps around
                             l_bound[i] = lj_force_bound(lj, fma(nearest, nearest, perp2));
+                            // A pair whose energy cannot rise anywhere on the window -- the target stays ahead and outside
+                            // the minimum sphere (attractive while approaching), or stays behind and inside it (repulsive
+                            // while receding) -- has no event there whatever potential change it draws: it needs no
+                            // random number at all. (Margins keep the rule on the safe side of rounding.)
+                            const double end2 = fma(behind, behind, perp2);  // squared distance at the end of the window
+                            const bool falls = (behind > 1.0e-9 * L && end2 > lj.r0sq * (1.0 + 1.0e-9)) ||
+                                               (ahead < -1.0e-9 * L && behind >= -half && end2 < lj.r0sq * (1.0 - 1.0e-9));
+                            live = !falls;
                         }
+                    }
+                    if (PRUNE) {
+                        const unsigned alive = __ballot_sync(kFull, live);
+                        if (live) l_live[n_live + __popc(alive & ((1u << lane) - 1u))] = i;
+                        n_live += __popc(alive);
                     }
                 }
                 __syncwarp();
@@ -345,14 +379,19 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 const double threshold = reach * (P.beta / (1.0 - 1.0e-9));  // bound * reach < u / beta (1 - 1e-9)
                 int queued = -1;
                 double queued_u = 0.0;
+                // events inside the window walk over the live entries only; an event beyond it over the whole list
+                const int my_count = beyond_window ? count : n_live;
+                const int walk = __any_sync(kFull, beyond_window) ? count : n_live;
 #pragma unroll 1
                 for (int base = 0;; base += G) {
-                    const bool last = base >= count;
-                    const int i = base + g;
+                    const bool last = base >= walk;
+                    const int k = base + g;
+                    int i = 0;
                     bool maybe = false;
                     double u = 0.0;
                     if (!last) {
-                        const bool valid = i < count;
+                        const bool valid = k < my_count;
+                        i = valid ? (beyond_window ? k : l_live[k]) : 0;
                         const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, valid ? l_target[i] : 0), 0);
                         u = words_to_double(pb.w[0], pb.w[1]);
                         maybe = valid && (beyond_window || !(l_bound[i] * threshold < u));

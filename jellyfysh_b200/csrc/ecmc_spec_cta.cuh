@@ -45,6 +45,9 @@ lj_chain_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, co
     double *l_bound = l_p0 + 2 * cap;  // PRUNE only
     int *l_target = reinterpret_cast<int *>(l_p0 + kDoubles * cap);
     int *l_seq = l_target + cap;
+    int *l_live = l_seq + cap;  // PRUNE only: the entries that can fire at all inside the window (ecmc_spec.cuh)
+    __shared__ int s_live;
+    int n_live = 0;
     int count = -1;  // entries of the valid list; -1: rebuild
     double x_build = 0.0, window = 0.0;
 
@@ -113,7 +116,7 @@ lj_chain_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, co
             if (PRUNE && count >= 0) {
                 double travelled = a.p0 - x_build;
                 if (travelled < 0.0) travelled += L;
-                if (!(travelled <= 0.5 * window)) count = -1;
+                if (!(travelled <= kWindowUse * window)) count = -1;
             }
             if (count < 0) {
                 // ---- warp 0 rebuilds the candidate list (the code of lj_spec_kernel), the others wait
@@ -142,13 +145,13 @@ lj_chain_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, co
                         }
                         found_so_far += __popc(occupied);
                     }
-                    if (lane == 0) s_count = found_so_far;
+                    if (lane == 0) { s_count = found_so_far; s_live = 0; }
                 }
                 __syncthreads();
                 count = s_count;
                 if (PRUNE) {
                     x_build = a.p0;
-                    window = fmin(24.0 * speed * P.inv_beta * P.upper[dir].inv_total_rate_speed, 0.25 * L);
+                    window = fmin(kWindowSteps * speed * P.inv_beta * P.upper[dir].inv_total_rate_speed, 0.25 * L);
                 }
                 // positions of the targets: all four warps share the entries
 #pragma unroll 1
@@ -165,9 +168,16 @@ lj_chain_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, co
                         double nearest = (ahead >= 0.0 && behind <= 0.0) ? 0.0 : fmin(fabs(ahead), fabs(behind));
                         if (behind < -half) nearest = fmin(nearest, half - window);
                         l_bound[i] = lj_force_bound(lj, fma(nearest, nearest, perp2));
+                        // entries whose energy cannot rise anywhere on the window need no random number (ecmc_spec.cuh);
+                        // the order of the live entries is free: the winner is a minimum over (time, sequence number)
+                        const double end2 = fma(behind, behind, perp2);
+                        const bool falls = (behind > 1.0e-9 * L && end2 > lj.r0sq * (1.0 + 1.0e-9)) ||
+                                           (ahead < -1.0e-9 * L && behind >= -half && end2 < lj.r0sq * (1.0 - 1.0e-9));
+                        if (!falls) l_live[atomicAdd(&s_live, 1)] = i;
                     }
                 }
                 __syncthreads();
+                n_live = s_live;
             }
 
             // ---- 32 events side by side ----------------------------------------------------------------------
@@ -281,14 +291,18 @@ lj_chain_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, co
                 const double threshold = reach * (P.beta / (1.0 - 1.0e-9));
                 int queued = -1;
                 double queued_u = 0.0;
+                const int my_count = beyond_window ? count : n_live;
+                const int walk = __any_sync(kFull, beyond_window) ? count : n_live;
 #pragma unroll 1
                 for (int base = 0;; base += G) {
-                    const bool last = base >= count;
-                    const int i = base + g;
+                    const bool last = base >= walk;
+                    const int k = base + g;
+                    int i = 0;
                     bool maybe = false;
                     double u = 0.0;
                     if (!last) {
-                        const bool valid = i < count;
+                        const bool valid = k < my_count;
+                        i = valid ? (beyond_window ? k : l_live[k]) : 0;
                         const Philox4 pb = stream_block(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, valid ? l_target[i] : 0), 0);
                         u = words_to_double(pb.w[0], pb.w[1]);
                         maybe = valid && (beyond_window || !(l_bound[i] * threshold < u));
