@@ -53,7 +53,7 @@ def parse_args():
     parser.add_argument("--steps", type=int, default=20)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    parser.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    parser.add_argument("--workload", default="c2", choices=["c1", "c1n", "c2", "c3", "c4", "c5"])
     parser.add_argument("--chains", type=int, default=None, help="independent chains per GPU (default: the workload's)")
     parser.add_argument("--particles", type=int, default=None, help="C2 / C3: particles per chain; C4: molecules")
     parser.add_argument("--cells", type=int, default=None, help="C2: cells per side")
@@ -206,7 +206,10 @@ class CoulombAtoms(Workload):
     def reference_job(self, cores):
         sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
         import configs
-        ini = configs.coulomb_atoms_ini(self.particles, [self.cells] * 3, points_per_side=10)
+        # (uniform random start: up to a few dozen particles share a cell at N = 512; one surplus handler per particle is
+        # always enough)
+        ini = configs.coulomb_atoms_ini(self.particles, [self.cells] * 3, points_per_side=10,
+                                        surplus_handlers=max(16, self.particles // 2))
         return ini, [configs.uniform_start(self.particles, 1.0, seed=1000 + k) for k in range(cores)], None
 
 
@@ -249,6 +252,52 @@ class HardDiskDipoles(Workload):
         import reference_runner
         roots, leaves = configs.read_pdb_dipoles(reference_runner.REF_ROOT)
         return configs.hard_disk_dipoles_cells_ini(reference_runner.REF_ROOT), [None] * cores, [(roots, leaves)] * cores
+
+
+class HardDiskDipolesNoCells(HardDiskDipoles):
+    """The no-cell sibling of C1: every other disk is a candidate of every event, general velocities."""
+    name, nearby = "C1n", 0
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.events = args.events or 1000
+        self.text = ("C1n: shipped hard_disk_dipoles/hard_disk_dipoles.ini: the same 81 hard-disk dipoles without a cell "
+                     "system (160 hard-disk candidates + the tether per event) and with general velocities (the "
+                     "sequential-direction end of chain rotates the velocity by 20 degrees), shipped start configuration, "
+                     "every chain its own random stream")
+
+    def engine(self, device, first_chain):
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import trace_util as tu
+        from jellyfysh_b200 import engine
+        from jellyfysh_b200.program import ProgramBuilder
+        g = tu.load_trace("trace_hard_disk_dipoles_sequential")
+        builder = tu.sequential_dipole_builder_of(g, ProgramBuilder)
+        builder.program.chain_time = 6.0  # the shipped value (the committed trace was recorded with shorter chains)
+        positions = np.tile(g["positions0"], (self.chains, 1, 1))
+        roots = np.tile(g["roots0"], (self.chains, 1, 1))
+        eng = engine.Engine(builder, n_chains=self.chains, device=device)
+        eng.upload_positions(positions)
+        eng.upload_roots(roots)
+        eng.start(first_stream=first_chain)
+        return eng, {"positions": positions, "roots": roots}
+
+    def reference_job(self, cores):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import configs
+        import reference_runner
+        # the shipped file reads its start configuration through PdbInputHandler: where MDAnalysis is not installed the
+        # (spawned) reference processes find jellyfysh_b200's .pdb reader under that name
+        try:
+            import MDAnalysis  # noqa: F401
+        except ImportError:
+            shims = os.path.join(ROOT, "jellyfysh_b200", "shims")
+            os.environ["PYTHONPATH"] = shims + os.pathsep + os.environ.get("PYTHONPATH", "")
+            if shims not in sys.path:
+                sys.path.append(shims)  # multiprocessing's spawn hands the parent's sys.path to the children
+        return configs.hard_disk_dipoles_ini(reference_runner.REF_ROOT), [None] * cores, None
 
 
 class Water(Workload):
@@ -310,7 +359,7 @@ class Water(Workload):
         return ini, [None] * cores, [(r, l.reshape(self.molecules, 3, 3)) for r, l in starts]
 
 
-WORKLOADS = {"c1": HardDiskDipoles, "c2": LennardJones, "c3": CoulombAtoms, "c4": Water, "c5": SingleChain}
+WORKLOADS = {"c1": HardDiskDipoles, "c1n": HardDiskDipolesNoCells, "c2": LennardJones, "c3": CoulombAtoms, "c4": Water, "c5": SingleChain}
 
 
 # ---------------------------------------------------------------------------------------------------------

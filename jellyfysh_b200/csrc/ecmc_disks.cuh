@@ -68,7 +68,7 @@ disk_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ Dis
     const unsigned max_events = A.max_events > 0 ? (unsigned)min(A.max_events, 0x7fffffffLL) : 0x7fffffffu;
     const int n_factor_slots = n_roots * K.n_inter, n_slots = n_factor_slots + P.n_bonds;
     unsigned n_events = 0, n_bond = 0, n_factor = 0, n_eoc = 0;
-    unsigned long long n_candidates = 0;
+    unsigned long long n_candidates = 0, n_targets = 0;
     bool stopped_by_time = false;
 
     while (n_events < max_events) {
@@ -88,7 +88,7 @@ disk_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ Dis
             const int active_root = active / npr, active_child = active - active_root * npr;
             const double vv = dot3(vx, vy, 0.0, vx, vy, 0.0);
             double best_x = INFINITY;
-            int best_seq = kSeqNone, best_target = -1, best_kind = ECMC_EVENT_NONE, count = 0;
+            int best_seq = kSeqNone, best_target = -1, best_kind = ECMC_EVENT_NONE, count = 0, evaluated = 0;
             for (int s = lane; s < n_slots; s += 32) {
                 int target = -1, kind = ECMC_EVENT_NONE;
                 if (s < n_factor_slots) {
@@ -107,6 +107,7 @@ disk_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ Dis
                     }
                 }
                 if (target < 0) continue;
+                evaluated++;
                 const Particle q = part[target];
                 const double sx = correct_separation_in_box(q.x - a.x, L, half);
                 const double sy = correct_separation_in_box(q.y - a.y, L, half);
@@ -118,6 +119,7 @@ disk_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ Dis
                 if (x < best_x) { best_x = x; best_seq = s; best_target = target; best_kind = kind; }
             }
             n_cand = __reduce_add_sync(kFull, count);
+            n_targets += (unsigned long long)__reduce_add_sync(kFull, evaluated);  // handler calls of the reference
             const bool have = best_seq != kSeqNone;
             const int owner = warp_argmin(have ? ordered_key(best_x) : ~0ull, best_seq, lane);
             best_seq = __shfl_sync(kFull, best_seq, owner);
@@ -257,6 +259,7 @@ disk_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ Dis
             if (n_candidates) atomicAdd(st + 6, n_candidates);
             if (n_bond) atomicAdd(st + 9, (unsigned long long)n_bond);
             if (n_factor) atomicAdd(st + 10, (unsigned long long)n_factor);
+            if (n_targets) atomicAdd(st + 11, n_targets);
         }
     }
 }
