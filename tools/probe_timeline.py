@@ -21,6 +21,9 @@ buffers = [engine.pinned_array(positions.shape) for _ in range(2)]
 buffers[0][...] = positions
 torch.cuda.init()
 with engine.Engine(builder, n_chains=n_chains) as eng:
+    eng.set_option(eng.OPTION_CONTINUE_HOST_STEPS, 1)
+    eng.upload_positions(positions)
+    eng.start(first_stream=0)
     def submit(k):
         if sparse:
             eng.submit_from_host(buffers[0], first_stream=(k + 1) * n_chains, max_events=events, out=buffers[0], sparse=True)
@@ -48,6 +51,6 @@ with engine.Engine(builder, n_chains=n_chains) as eng:
         by_name[name] = (total + (end - start), count + 1)
     for name, (total, count) in sorted(by_name.items(), key=lambda item: -item[1][0]):
         print(f"{total / 1e3:10.3f} ms  {count:5d} x  mean {total / count / 1e3:8.3f} ms  {name}")
-    print("first 80 activities: start [ms], duration [ms], name")
-    for start, end, name in rows[:80]:
+    print("activities: start [ms], duration [ms], name")
+    for start, end, name in rows[:int(sys.argv[3]) if len(sys.argv) > 3 else 80]:
         print(f"{(start - t0) / 1e3:9.3f} {(end - start) / 1e3:9.3f}  {name}")
