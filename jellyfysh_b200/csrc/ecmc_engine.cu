@@ -71,6 +71,7 @@ struct EcmcHandle {
     bool chain_blocks = true; // few chains: lj_chain_kernel, one CTA of four warps per chain (ecmc_spec_cta.cuh)
     bool host_fused = true;   // sparse host steps of Lennard-Jones / cell-veto programs as ONE launch per chain slice
     bool host_continue = false; // host steps continue the chains instead of starting a new run each (ecmc_set_option)
+    bool spec_coulomb = true;   // Coulomb atoms (bound / merged-image Coulomb / cell veto): the batched kernel too
     std::string kernel_name; // ecmc_kernel_name
     bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
     int slices_layout = 0;    // ... and how its chains were cut into slices (steps are ordered slice by slice)
@@ -556,6 +557,7 @@ struct SpecLaunch {
     size_t shared_bytes = 0;
     int capacity = 0;
     bool chain_blocks = false;  // lj_chain_kernel: one CTA of kChainWarps warps per chain
+    bool coulomb = false;       // the Coulomb model of lj_spec_kernel
 };
 // lj_chain_kernel while every chain can have an SM of its own
 constexpr int kChainKernelMaxChains = 148;
@@ -563,6 +565,12 @@ constexpr int kChainKernelMaxChains = 148;
 template <bool RECORD, bool PRUNE>
 EventKernel pick_spec_lanes(int lanes) {
     return lanes == 8 ? lj_spec_kernel<RECORD, PRUNE, 8, kWarpsPerBlock> : lj_spec_kernel<RECORD, PRUNE, 4, kWarpsPerBlock>;
+}
+// the Coulomb atoms (C3): the same batch with the inverse-power Coulomb bound, merged-image Coulomb and charges
+template <bool RECORD, bool PRUNE>
+EventKernel pick_spec_coulomb(int lanes) {
+    return lanes == 8 ? lj_spec_kernel<RECORD, PRUNE, 8, kWarpsPerBlock, false, kSpecCoulomb>
+                      : lj_spec_kernel<RECORD, PRUNE, 4, kWarpsPerBlock, false, kSpecCoulomb>;
 }
 // the whole-host-step form of the same kernel (RunArgs.host_in / host_out)
 EventKernel pick_spec_host(bool prune, int lanes) {
@@ -576,18 +584,34 @@ EventKernel pick_spec_host(bool prune, int lanes) {
 bool pick_spec(const EcmcHandle *h, bool record, SpecLaunch *out) {
     const DeviceProgram &d = h->dprog;
     if (!h->spec || h->molecules || d.nodes_per_root > 1) return false;
-    if (d.dimension != 3 || d.no_cells || !d.translate_modular || d.pair_use_charge || d.veto_use_charge) return false;
-    if (d.max_occupants != 1 || d.pair_handler != ECMC_PAIR_TWO_LEAF_UNIT || d.veto_enabled != ECMC_FAR_CELL_VETO) return false;
-    if (d.cand_potential.kind != ECMC_POT_LENNARD_JONES || d.veto_potential.kind != ECMC_POT_LENNARD_JONES) return false;
+    if (d.dimension != 3 || d.no_cells || !d.translate_modular) return false;
+    if (d.max_occupants != 1 || d.veto_enabled != ECMC_FAR_CELL_VETO) return false;
+    const bool lennard_jones = d.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT && !d.pair_use_charge && !d.veto_use_charge &&
+                               d.cand_potential.kind == ECMC_POT_LENNARD_JONES && d.veto_potential.kind == ECMC_POT_LENNARD_JONES;
+    // Coulomb atoms: pair candidates from the inverse-power Coulomb bound confirmed against merged-image Coulomb, the same
+    // potential for the cell veto
+    const bool coulomb = d.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING && h->spec_coulomb &&
+                         d.cand_potential.kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING &&
+                         d.real_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB &&
+                         d.veto_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB;
+    if (!lennard_jones && !coulomb) return false;
     for (int k = 0; k < 3; k++)
-        if (d.upper[k].n_entries <= 0) return false;
+        if (d.upper[k].n_entries <= 0 || (coulomb && d.veto_use_charge && d.lower[k].n_entries <= 0)) return false;
     const bool prune = h->spec_prune && !record;
     const int capacity = (d.n_nearby + d.max_surplus + 31) / 32 * 32;
-    // per entry: coordinate, squared distance from the line, (force bound), target + sequence number, (live index)
-    const size_t bytes = (size_t)kWarpsPerBlock * capacity * (prune ? 5 : 3) * sizeof(double);
+    // per entry: coordinate, squared distance from the line, (force bound), (charge product), target + sequence number,
+    // (live index); Coulomb: plus the scratch of the Ewald sum per warp
+    const size_t bytes = (size_t)kWarpsPerBlock * capacity * ((prune ? 5 : 3) + (coulomb ? 1 : 0)) * sizeof(double) +
+                         (coulomb ? (size_t)kWarpsPerBlock * kTrigDoubles * sizeof(double) : 0);
     if (bytes > 100 * 1024) return false;  // two CTAs per SM
     out->capacity = capacity;
     out->shared_bytes = bytes;
+    out->coulomb = coulomb;
+    if (coulomb) {
+        if (record) out->kernel = pick_spec_coulomb<true, false>(h->spec_lanes);
+        else out->kernel = prune ? pick_spec_coulomb<false, true>(h->spec_lanes) : pick_spec_coulomb<false, false>(h->spec_lanes);
+        return true;
+    }
     // few chains (the single large chain C5): one CTA of four warps per chain, 32 events per batch
     out->chain_blocks = h->chain_blocks && h->n_chains <= kChainKernelMaxChains;
     if (out->chain_blocks) {
@@ -1081,7 +1105,7 @@ int submit_from_host(EcmcHandle *h, const double *positions_in, const double *ch
     // ECMC_OPTION_CONTINUE_HOST_STEPS: from the second step on the chains continue (lifting state kept on the device)
     const bool keep_state = h->host_continue && h->started;
     args.keep_state = keep_state ? 1 : 0;
-    bool fused = sparse && !charges && spec.kernel && !spec.chain_blocks && h->host_fused;
+    bool fused = sparse && !charges && spec.kernel && !spec.chain_blocks && !spec.coulomb && h->host_fused;
     bool fused_copy = true;
     if (const char *env = std::getenv("ECMC_FUSED_ZEROCOPY")) fused_copy = std::atoi(env) == 0;
     if (fused) {
@@ -1374,6 +1398,10 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
     } else if (pick_spec(h, record != 0, &spec) && spec.chain_blocks) {
         h->kernel_name = "lj_chain_kernel<record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", warps per chain=" + std::to_string(kChainWarps) + ">";
+    } else if (pick_spec(h, record != 0, &spec) && spec.coulomb) {
+        h->kernel_name = "lj_spec_kernel<coulomb, record=" + std::to_string(record != 0) + ", prune=" +
+                         std::to_string(h->spec_prune && !record) + ", lanes=" + std::to_string(h->spec_lanes) + ", warps=" +
+                         std::to_string(kWarpsPerBlock) + ">";
     } else if (pick_spec(h, record != 0, &spec)) {
         h->kernel_name = "lj_spec_kernel<record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", lanes=" + std::to_string(h->spec_lanes) + ", warps=" +

@@ -81,12 +81,27 @@ ECMC_D double time_order(double x) { return x > 0.0 ? x : 0.0; }
 // the kernel itself -- no staging copy, no separate pack / start kernels waiting for a free SM), bins it into the cells
 // and starts the run (start_chain); every position the events change is written through to RunArgs.host_out -- the
 // position of a particle when it hands the activity over, and the last active particle at the end.
-template <bool RECORD, bool PRUNE, int G, int WARPS, bool HOST = false>
+//
+// MODEL: kSpecLennardJones -- chargeless Lennard-Jones pair factors, Lennard-Jones cell veto (C2, C5) --, or kSpecCoulomb --
+// the Coulomb atoms of C3 (coulomb_atoms/cell_veto.ini): pair candidates from the inverse-power Coulomb bound
+// (TwoLeafUnitBoundingPotentialEventHandler, two_leaf_unit_bounding_potential_event_handler.py:112-168) confirmed against
+// the merged-image Coulomb derivative, the same derivative for the cell veto (leaf_unit_cell_veto_event_handler.py:
+// 117-149), with charges. The batch is the same; what differs is the inversion of a pair candidate, the force bound and
+// the rule for the live entries (a repulsive pair cannot fire while the target stays behind, an attractive one while it
+// stays ahead), the Walker table by the sign of the active charge, and the confirmation of a veto, which is a
+// warp-wide Ewald sum: the leaders only collect the separations, the warp then evaluates them one after the other, in
+// event order, up to the first event that ends the batch.
+constexpr int kSpecLennardJones = 0, kSpecCoulomb = 1;
+
+template <bool RECORD, bool PRUNE, int G, int WARPS, bool HOST = false, int MODEL = kSpecLennardJones>
 __global__ void __launch_bounds__(WARPS * 32, ECMC_RESIDENT_WARPS / WARPS)
 lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const RunArgs A) {
     static_assert(G == 4 || G == 8, "lanes per event");
+    static_assert(!(HOST && MODEL != kSpecLennardJones), "host steps in one launch: chargeless programs only");
+    constexpr bool COULOMB = MODEL == kSpecCoulomb;
+    constexpr int IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, MIC = ECMC_POT_MERGED_IMAGE_COULOMB;
     constexpr int W = 32 / G;
-    constexpr int kDoubles = PRUNE ? 3 : 2;
+    constexpr int kDoubles = (PRUNE ? 3 : 2) + (COULOMB ? 1 : 0);
     extern __shared__ double spec_shared[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -103,11 +118,15 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     int *l_target = reinterpret_cast<int *>(l_p0 + kDoubles * cap);
     int *l_seq = l_target + cap;
     int *l_live = l_seq + cap;  // PRUNE only
+    double *l_kc = l_p0 + (PRUNE ? 3 : 2) * cap;  // COULOMB only: prefactor x charge product of the pair
+    // COULOMB: per-warp scratch of the Ewald sum (mic_derivative_warp), behind the lists of all warps
+    double *trig = spec_shared + (size_t)WARPS * cap * kEntryDoubles + (size_t)warp * kTrigDoubles;
     int n_live = 0;
     int count = -1;  // entries of the valid list; -1: rebuild
     double x_build = 0.0, window = 0.0;  // PRUNE: where the list was built, and how far its force bounds reach
 
     const LennardJones &lj = P.cand_potential.lj;
+    const bool pair_use_charge = COULOMB && P.pair_use_charge != 0, veto_use_charge = COULOMB && P.veto_use_charge != 0;
     Particle *part = S.particles + (size_t)chain * P.n_particles;
     int *occ = S.occupants + (size_t)chain * P.n_cells;
     int *sur = S.surplus + (size_t)chain * P.max_surplus;
@@ -175,7 +194,16 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     Counters n = {0, 0, 0ull, 0ull};
     bool stopped_by_time = false;
 
-    while (n.events < max_events) {
+    // COULOMB: the kernel is several thousand instructions (the Ewald sum, two inversions), and warps that are all
+    // somewhere else in it starve on instruction fetch (measured: 19 of 26 % of the stall samples on the Ewald sum alone):
+    // the warps of a CTA meet at a barrier before every batch, like the chains of molecule_kernel before every event.
+    bool done = false;
+    while (COULOMB || n.events < max_events) {
+        if constexpr (COULOMB) {
+            const bool finished = done || n.events >= max_events;
+            if (__syncthreads_and(finished)) break;
+            if (finished) continue;
+        }
         // the interaction winner of the event that goes through the general out-state code
         Time bt = time_inf();
         int bkind = ECMC_EVENT_NONE, btarget = -1, bcell = -1;
@@ -230,7 +258,16 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 __syncwarp();
                 if (PRUNE) {
                     x_build = a.p0;
+                    if constexpr (COULOMB) {
+                        // mean cell-veto step of this active charge: 1 / (beta total rate |charge factor|)
+                        double factor = veto_use_charge ? a.charge * 1.0 : 1.0;
+                        if (veto_use_charge && P.veto_target_charge != 1.0) factor = factor / P.veto_target_charge;
+                        const DeviceWalker *wb = factor > 0.0 ? &P.upper[dir] : &P.lower[dir];
+                        const double step = speed * P.inv_beta / (wb->total_rate * fabs(factor) * speed);
+                        window = fmin(kWindowSteps * (step < INFINITY ? step : L), 0.25 * L);
+                    } else {
                     window = fmin(kWindowSteps * speed * P.inv_beta * P.upper[dir].inv_total_rate_speed, 0.25 * L);
+                    }
                 }
                 n_live = 0;
 #pragma unroll 1
@@ -244,12 +281,27 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                         const double perp2 = fma(s1, s1, s2 * s2);
                         l_p0[i] = tp.p0;
                         l_perp2[i] = perp2;
+                        double kc = 0.0;
+                        if constexpr (COULOMB) {
+                            // prefactor c1 c2 as InversePowerCoulombBoundingPotential gets it (displacement_time<IPCB>)
+                            kc = P.cand_potential.p0 * (pair_use_charge ? a.charge : 1.0) * (pair_use_charge ? tp.charge : 1.0);
+                            l_kc[i] = kc;
+                        }
                         if (PRUNE) {
                             // smallest distance of the pair while the active particle covers the window
                             const double ahead = correct_separation_in_box(tp.p0 - a.p0, L, half);
                             const double behind = ahead - window;
                             double nearest = (ahead >= 0.0 && behind <= 0.0) ? 0.0 : fmin(fabs(ahead), fabs(behind));
                             if (behind < -half) nearest = fmin(nearest, half - window);  // the separation wraps around
+                            if constexpr (COULOMB) {
+                                // |d/dx (kc / r)| = |kc| |sx| / r^3 <= |kc| / r^2 at the smallest distance on the window
+                                l_bound[i] = fabs(kc) / fma(nearest, nearest, perp2) * (1.0 + 1.0e-9);
+                                // the bound kc / r falls while a repulsive pair recedes (target behind) and while an
+                                // attractive one approaches (target ahead); a neutral pair never fires
+                                const bool falls = kc > 0.0 ? (ahead < -1.0e-9 * L && behind >= -half)
+                                                            : (kc < 0.0 ? behind > 1.0e-9 * L : true);
+                                live = !falls;
+                            } else {
                             l_bound[i] = lj_force_bound(lj, fma(nearest, nearest, perp2));
                             // A pair whose energy cannot rise anywhere on the window -- the target stays ahead and outside
                             // the minimum sphere (attractive while approaching), or stays behind and inside it (repulsive
@@ -259,6 +311,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                             const bool falls = (behind > 1.0e-9 * L && end2 > lj.r0sq * (1.0 + 1.0e-9)) ||
                                                (ahead < -1.0e-9 * L && behind >= -half && end2 < lj.r0sq * (1.0 - 1.0e-9));
                             live = !falls;
+                            }
                         }
                     }
                     if (PRUNE) {
@@ -279,6 +332,15 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             const Philox4 b = stream_block(key, special_slot, 0);
             const double u_first = words_to_double(b.w[0], b.w[1]), u_second = words_to_double(b.w[2], b.w[3]);
             const DeviceWalker *w = &P.upper[dir];  // chargeless handlers: the charge factor is 1 > 0
+            // InnerPointEstimator.charge_correction_factor (inner_point_estimator.py:165-192), as event_kernel forms it
+            double charge_factor = 1.0;
+            if constexpr (COULOMB) {
+                if (veto_use_charge) {
+                    charge_factor = a.charge * 1.0;
+                    if (P.veto_target_charge != 1.0) charge_factor = charge_factor / P.veto_target_charge;
+                }
+                if (!(charge_factor > 0.0)) { charge_factor *= -1.0; w = &P.lower[dir]; }
+            }
             // random.choice(table) = table[_randbelow(n)]: rejection on the top bits of successive words (lane g = 1)
             uint32_t choice = 0;
             {
@@ -301,8 +363,16 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             const WalkerEntry entry = w->entries[choice];
             const bool first_cell = 0.0 + (w->mean_rate - 0.0) * u_first <= entry.rate_a;
             const int relative = first_cell ? entry.cell_a : entry.cell_b;
-            const double veto_rate = first_cell ? entry.bound_a : entry.bound_b;
-            const double veto_dt = -log_unit_interval(1.0 - u_second) * P.inv_beta * w->inv_total_rate_speed;
+            double veto_rate = first_cell ? entry.bound_a : entry.bound_b;
+            double veto_dt = -log_unit_interval(1.0 - u_second) * P.inv_beta * w->inv_total_rate_speed;
+            if constexpr (COULOMB) {
+                veto_rate = veto_rate * charge_factor;
+                // (a neutral active unit has no cell-veto events)
+                if (veto_use_charge)
+                    veto_dt = charge_factor > 0.0
+                                  ? -log_unit_interval(1.0 - u_second) * P.inv_beta / (w->total_rate * charge_factor * speed)
+                                  : INFINITY;
+            }
 
             // time and position before every event of the batch if all earlier ones are rejected vetoes: the additions
             // of Time.__add__ (time.py:115-133) and of the time slice (abstracts.py:82-95), one event after the other
@@ -355,7 +425,10 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             auto candidate = [&](int i, double u) {
                 const double s0 = correct_separation_in_box(l_p0[i] - my_x, L, half);
                 const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
-                const double x = my_now.r + lj_displacement(lj, s0, l_perp2[i], du) * P.inv_speed;
+                double displacement;
+                if constexpr (COULOMB) displacement = ipcb_displacement(l_kc[i], s0, l_perp2[i], du, L);
+                else displacement = lj_displacement(lj, s0, l_perp2[i], du);
+                const double x = my_now.r + displacement * P.inv_speed;
                 if (x < INFINITY) {  // heap_scheduler.py:139; NaN never wins
                     n_finite++;
                     const int seq = l_seq[i];
@@ -421,6 +494,9 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             double my_best = best_x;
             bool plain = false, violation = false;
             int my_candidates = n_finite;
+            // COULOMB: the veto of this event won and its target cell is occupied: separation and charge of the occupant
+            bool confirm = false, confirm_left = false;
+            double csx = 0.0, csy = 0.0, csz = 0.0, cc2 = 1.0;
             if (g == 0 && e < w_eff) {
                 // sequence numbers: pair slots in scan order, then veto, then boundary
                 if (xv < INFINITY) {
@@ -456,13 +532,43 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                         const double sx = correct_separation_in_box(tp.p0 - my_next_x, L, half);
                         const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
                         const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
+                        if constexpr (COULOMB) {
+                            confirm = true;
+                            csx = sx; csy = sy; csz = sz;
+                            cc2 = veto_use_charge ? tp.charge : 1.0;
+                        } else {
                         const double real = lj_derivative(P.veto_potential.lj, sx, fma(sy, sy, sz * sz)) * speed;
                         if (real > 0.0) {
                             violation = veto_rate < real;
                             accepted = 0.0 + (veto_rate - 0.0) * u_conf < real;
                         }
+                        }
                     }
                     plain = !accepted && !my_left;
+                    confirm_left = my_left;
+                }
+            }
+            if constexpr (COULOMB) {
+                // The merged-image Coulomb derivative is a sum over the 32 lanes (mic_derivative_warp): the confirmations of
+                // the batch are evaluated by the whole warp one after the other, in event order, up to the first event that
+                // ends the batch anyway (everything after it is discarded).
+                const unsigned ends = __ballot_sync(kFull, g == 0 && !(plain || (confirm && !confirm_left)));
+                const int first_end = ends ? __ffs(ends) - 1 : 32;
+                unsigned todo = __ballot_sync(kFull, confirm && !confirm_left) & (first_end < 32 ? (1u << first_end) - 1u : kFull);
+                const double c1 = veto_use_charge ? a.charge : 1.0;
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const double real = derivative_warp<MIC>(P.veto_potential, 0, speed, __shfl_sync(kFull, csx, src),
+                                                             __shfl_sync(kFull, csy, src), __shfl_sync(kFull, csz, src), c1,
+                                                             __shfl_sync(kFull, cc2, src), trig, lane);
+                    const double rate = __shfl_sync(kFull, veto_rate, src), u = __shfl_sync(kFull, u_conf, src);
+                    const bool accepted = real > 0.0 && 0.0 + (rate - 0.0) * u < real;
+                    if (lane == src) {
+                        violation = real > 0.0 && rate < real;
+                        plain = !accepted;  // (this leader has not left its cell: confirm_left is false)
+                    }
+                    if (accepted) break;  // the batch ends here
                 }
             }
             const unsigned breaking = __ballot_sync(kFull, g == 0 && !plain);
@@ -532,6 +638,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 }
             }
             stopped_by_time = true;
+            if constexpr (COULOMB) { done = true; continue; }
             break;
         }
         if (was_pending) {
@@ -551,8 +658,24 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
         switch (kind) {
         case ECMC_EVENT_PAIR:  // two_leaf_unit_event_handler.py:140-154
             rec_target = btarget;
+            if constexpr (COULOMB) {
+                // two_leaf_unit_bounding_potential_event_handler.py:148-168 + event_handler_with_bounding_potential.py:75-101
+                const Moving tp = rotate_in(part[btarget], dir);
+                const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
+                const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
+                const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
+                const double c1 = pair_use_charge ? a.charge : 1.0, c2 = pair_use_charge ? tp.charge : 1.0;
+                const double bounding_rate = derivative_warp<IPCB>(P.cand_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
+                const double real = derivative_warp<MIC>(P.real_potential, 0, speed, sx, sy, sz, c1, c2, trig, lane);
+                if (real > 0.0) {
+                    if (bounding_rate < real) count_rare(A, lane, 7);
+                    if (0.0 + (bounding_rate - 0.0) * u_confirmation < real) accepted = 1;
+                }
+                if (accepted) new_active = btarget;
+            } else {
             accepted = 1;
             new_active = btarget;
+            }
             count_rare(A, lane, 1);
             break;
         case ECMC_EVENT_CELL_VETO: {
@@ -563,7 +686,11 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 const double sx = correct_separation_in_box(tp.p0 - a.p0, L, half);
                 const double sy = correct_separation_in_box(tp.p1 - a.p1, L, half);
                 const double sz = correct_separation_in_box(tp.p2 - a.p2, L, half);
-                const double real = lj_derivative(P.veto_potential.lj, sx, fma(sy, sy, sz * sz)) * speed;
+                double real;
+                if constexpr (COULOMB)
+                    real = derivative_warp<MIC>(P.veto_potential, 0, speed, sx, sy, sz, veto_use_charge ? a.charge : 1.0,
+                                                veto_use_charge ? tp.charge : 1.0, trig, lane);
+                else real = lj_derivative(P.veto_potential.lj, sx, fma(sy, sy, sz * sz)) * speed;
                 if (real > 0.0) {
                     if (brate < real) count_rare(A, lane, 7);
                     if (0.0 + (brate - 0.0) * u_confirmation < real) { accepted = 1; new_active = t; }

@@ -145,3 +145,95 @@ def test_single_large_chain_in_a_block_against_the_oracle(oracle):
             eng.sync()
         _assert_same_state(blocked, warped, "60 000 events of the single chain")
         _compare_stretch(oracle, builder, blocked, (0,), 2000, None, length, "C5 in a block, after 60k events")
+
+
+# ---- the Coulomb model of the batched kernel (C3: inverse-power Coulomb bound, merged-image Coulomb, charges) ------------
+_COULOMB_PROGRAMS = {}
+
+
+def _coulomb_program(n=64, chain_time=0.78965):
+    """(builder, length); the cell-veto tables are built once per program and module."""
+    if (n, chain_time) not in _COULOMB_PROGRAMS:
+        _COULOMB_PROGRAMS[(n, chain_time)] = workloads.coulomb_atoms(n_particles=n, chain_time=chain_time, points_per_side=4)
+    return _COULOMB_PROGRAMS[(n, chain_time)]
+
+
+def _coulomb_started(builder, positions, charges, first_stream, **options):
+    eng = engine.Engine(builder, n_chains=len(positions))
+    for option, value in options.items():
+        eng.set_option({"batched": BATCHED, "prune": PRUNE, "lanes": LANES}[option], value)
+    eng.upload_positions(positions, charges)
+    eng.start(first_stream=first_stream)
+    return eng
+
+
+def _coulomb_chains(n_chains, n, length, mixed):
+    positions = workloads.uniform_start(n_chains, n, length)
+    charges = np.ones((n_chains, n))
+    if mixed:  # both signs: attractive pairs, the lower-bound Walker tables for negative active charges
+        charges[:, 1::2] = -1.0
+    return positions, charges
+
+
+@pytest.mark.parametrize("lanes,mixed", [(4, False), (8, False), (4, True)])
+def test_coulomb_batched_kernel_commits_the_events_of_the_single_event_kernel(lanes, mixed):
+    """lj_spec_kernel<coulomb> against event_kernel<IPCB, MIC, MIC> on the same chains: every field of every event record,
+    times and positions bit for bit, the same counters."""
+    n_chains, n, events = 48, 64, 2500
+    builder, length = _coulomb_program(n)
+    positions, charges = _coulomb_chains(n_chains, n, length, mixed)
+    with _coulomb_started(builder, positions, charges, 11, batched=0) as single, \
+            _coulomb_started(builder, positions, charges, 11, lanes=lanes) as batched:
+        assert "lj_spec_kernel<coulomb" in batched.kernel_name(record=True)
+        assert "event_kernel" in single.kernel_name(record=True)
+        ref, ref_stats = single.run_recorded(max_events=events, records_per_chain=events)
+        rec, stats = batched.run_recorded(max_events=events, records_per_chain=events)
+        assert stats == ref_stats
+        assert stats["pair_events"] > 0 and stats["veto_accepted"] > 0 and stats["boundary_events"] > 0 and \
+            stats["end_of_chain_events"] > 0 and stats["veto_events"] > 10 * stats["pair_events"]
+        for field in rec.dtype.names:
+            same = rec[field] == ref[field]
+            if not np.all(same):
+                chain, event = [int(v[0]) for v in np.nonzero(~same.reshape(n_chains, events, -1).all(axis=2))]
+                raise AssertionError(f"{field}: chain {chain} event {event}: {rec[chain][event]} vs {ref[chain][event]}")
+        _assert_same_state(single, batched, "after the recorded launch")
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_coulomb_pruning_does_not_change_the_chains(mixed):
+    n_chains, n = 96, 64
+    builder, length = _coulomb_program(n)
+    positions, charges = _coulomb_chains(n_chains, n, length, mixed)
+    with _coulomb_started(builder, positions, charges, 500, prune=0) as full, \
+            _coulomb_started(builder, positions, charges, 500, prune=1) as pruned, \
+            _coulomb_started(builder, positions, charges, 500, batched=0) as single:
+        assert "lj_spec_kernel<coulomb" in pruned.kernel_name() and "prune=1" in pruned.kernel_name()
+        totals = []
+        for eng in (full, pruned, single):
+            for events in (1, 2, 3, 5, 8, 13, 968, 4000):
+                eng.run(max_events=events)
+            totals.append(eng.sync())
+        _assert_same_state(full, pruned, "pruned vs unpruned")
+        _assert_same_state(full, single, "batched vs single-event kernel")
+        assert totals[0] == totals[2]
+        for key in totals[0]:
+            if key != "candidates":
+                assert totals[0][key] == totals[1][key], key
+        assert totals[1]["candidates"] < totals[0]["candidates"]
+
+
+def test_coulomb_time_limits_cut_batches_like_the_single_event_kernel():
+    n_chains, n = 48, 64
+    builder, length = _coulomb_program(n, chain_time=0.3)
+    positions, charges = _coulomb_chains(n_chains, n, length, True)
+    with _coulomb_started(builder, positions, charges, 40, batched=0) as single, \
+            _coulomb_started(builder, positions, charges, 40, prune=1) as batched:
+        for eng in (single, batched):
+            for k in range(1, 40):
+                eng.run(until=(float(k // 16), (k % 16) / 16.0))
+                eng.run(max_events=3)
+            eng.run(until=(3.0, 0.0625))
+            eng.sync()
+        _assert_same_state(single, batched, "after interleaved time limits")
+        states = batched.chain_states()
+        assert np.all(states["time_q"] == 3.0) and np.all(states["time_r"] == 0.0625)
