@@ -72,6 +72,7 @@ struct EcmcHandle {
     bool host_fused = true;   // sparse host steps of Lennard-Jones / cell-veto programs as ONE launch per chain slice
     bool host_continue = false; // host steps continue the chains instead of starting a new run each (ecmc_set_option)
     bool spec_coulomb = true;   // Coulomb atoms (bound / merged-image Coulomb / cell veto): the batched kernel too
+    int coulomb_warps = 0;      // ... with this many chains per CTA (7, 14 or 28; 0: the largest that fits)
     std::string kernel_name; // ecmc_kernel_name
     bool slices_busy = false; // ecmc_submit_from_host work in flight on the slice streams (until ecmc_wait)
     int slices_layout = 0;    // ... and how its chains were cut into slices (steps are ordered slice by slice)
@@ -558,6 +559,7 @@ struct SpecLaunch {
     int capacity = 0;
     bool chain_blocks = false;  // lj_chain_kernel: one CTA of kChainWarps warps per chain
     bool coulomb = false;       // the Coulomb model of lj_spec_kernel
+    int warps = kWarpsPerBlock; // chains per CTA
 };
 // lj_chain_kernel while every chain can have an SM of its own
 constexpr int kChainKernelMaxChains = 148;
@@ -567,10 +569,15 @@ EventKernel pick_spec_lanes(int lanes) {
     return lanes == 8 ? lj_spec_kernel<RECORD, PRUNE, 8, kWarpsPerBlock> : lj_spec_kernel<RECORD, PRUNE, 4, kWarpsPerBlock>;
 }
 // the Coulomb atoms (C3): the same batch with the inverse-power Coulomb bound, merged-image Coulomb and charges
-template <bool RECORD, bool PRUNE>
+template <bool RECORD, bool PRUNE, int WARPS>
 EventKernel pick_spec_coulomb(int lanes) {
-    return lanes == 8 ? lj_spec_kernel<RECORD, PRUNE, 8, kWarpsPerBlock, false, kSpecCoulomb>
-                      : lj_spec_kernel<RECORD, PRUNE, 4, kWarpsPerBlock, false, kSpecCoulomb>;
+    return lanes == 8 ? lj_spec_kernel<RECORD, PRUNE, 8, WARPS, false, kSpecCoulomb>
+                      : lj_spec_kernel<RECORD, PRUNE, 4, WARPS, false, kSpecCoulomb>;
+}
+template <int WARPS>
+EventKernel pick_spec_coulomb_warps(bool record, bool prune, int lanes) {
+    if (record) return pick_spec_coulomb<true, false, WARPS>(lanes);
+    return prune ? pick_spec_coulomb<false, true, WARPS>(lanes) : pick_spec_coulomb<false, false, WARPS>(lanes);
 }
 // the whole-host-step form of the same kernel (RunArgs.host_in / host_out)
 EventKernel pick_spec_host(bool prune, int lanes) {
@@ -601,15 +608,32 @@ bool pick_spec(const EcmcHandle *h, bool record, SpecLaunch *out) {
     const int capacity = (d.n_nearby + d.max_surplus + 31) / 32 * 32;
     // per entry: coordinate, squared distance from the line, (force bound), (charge product), target + sequence number,
     // (live index); Coulomb: plus the scratch of the Ewald sum per warp
-    const size_t bytes = (size_t)kWarpsPerBlock * capacity * ((prune ? 5 : 3) + (coulomb ? 1 : 0)) * sizeof(double) +
-                         (coulomb ? (size_t)kWarpsPerBlock * kTrigDoubles * sizeof(double) : 0);
-    if (bytes > 100 * 1024) return false;  // two CTAs per SM
+    // warps (chains) per CTA. The Coulomb model aligns the warps of a CTA at a barrier per batch, and the more warps fetch
+    // the same instructions together the better (measured on C3, N = 64: 7 / 14 / 28 warps -> 5.2 / 6.3 / 8.0e8 events/s):
+    // the largest CTA whose lists fit the shared memory of an SM, even if fewer warps than the register file allows are
+    // then resident
+    int warps = kWarpsPerBlock;
+    auto bytes_of = [&](int w) {
+        return (size_t)w * capacity * ((prune ? 5 : 3) + (coulomb ? 1 : 0)) * sizeof(double) +
+               (coulomb ? (size_t)w * kTrigDoubles * sizeof(double) : 0);
+    };
+    if (coulomb) {
+        warps = h->coulomb_warps;
+        if (warps == 0)
+            for (int w : {28, 14, 7})
+                if (warps == 0 && bytes_of(w) <= 200 * 1024) warps = w;
+        if (warps == 0) return false;
+    }
+    const size_t bytes = bytes_of(warps);
+    if (coulomb ? bytes > 200 * 1024 : bytes > 100 * 1024) return false;  // Lennard-Jones: two CTAs per SM
     out->capacity = capacity;
     out->shared_bytes = bytes;
     out->coulomb = coulomb;
+    out->warps = warps;
     if (coulomb) {
-        if (record) out->kernel = pick_spec_coulomb<true, false>(h->spec_lanes);
-        else out->kernel = prune ? pick_spec_coulomb<false, true>(h->spec_lanes) : pick_spec_coulomb<false, false>(h->spec_lanes);
+        out->kernel = warps == 7 ? pick_spec_coulomb_warps<7>(record, prune, h->spec_lanes)
+                                 : (warps == 28 ? pick_spec_coulomb_warps<28>(record, prune, h->spec_lanes)
+                                                : pick_spec_coulomb_warps<14>(record, prune, h->spec_lanes));
         return true;
     }
     // few chains (the single large chain C5): one CTA of four warps per chain, 32 events per batch
@@ -710,7 +734,8 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
             if (spec.chain_blocks)
                 spec.kernel<<<h->n_chains, kChainWarps * 32, spec.shared_bytes, h->stream>>>(h->dprog, h->state, args);
             else
-                spec.kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, h->stream>>>(h->dprog, h->state, args);
+                spec.kernel<<<(h->n_chains + spec.warps - 1) / spec.warps, spec.warps * 32, spec.shared_bytes, h->stream>>>(
+                    h->dprog, h->state, args);
         } else {
             const EventKernel kernel = pick_kernel(h->dprog, d_records != nullptr);
             kernel<<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(h->dprog, h->state, args);
@@ -766,6 +791,10 @@ ECMC_API int ecmc_create(const EcmcProgram *program, int device, int n_chains, E
     if (const char *env = std::getenv("ECMC_SPEC_PRUNE")) h->spec_prune = std::atoi(env) != 0;
     if (const char *env = std::getenv("ECMC_SPEC_LANES")) h->spec_lanes = std::atoi(env) == 8 ? 8 : 4;
     if (const char *env = std::getenv("ECMC_CHAIN_BLOCKS")) h->chain_blocks = std::atoi(env) != 0;
+    if (const char *env = std::getenv("ECMC_COULOMB_WARPS")) {
+        const int warps = std::atoi(env);
+        if (warps == 7 || warps == 14 || warps == 28) h->coulomb_warps = warps;
+    }
     int rc = ECMC_OK;
     do {
         if ((err = cudaSetDevice(device)) != cudaSuccess) { rc = fail(h, ECMC_ERR_CUDA, cudaGetErrorString(err)); break; }
@@ -1188,7 +1217,8 @@ int submit_from_host(EcmcHandle *h, const double *positions_in, const double *ch
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, s>>>(
             d, slice, nullptr, first_stream, h->program.initial_active, h->program.initial_direction, h->d_stats, keep_state);
         if (spec.chain_blocks) kernel<<<count, kChainWarps * 32, spec.shared_bytes, s>>>(d, slice, args);
-        else kernel<<<blocks, kWarpsPerBlock * 32, spec.shared_bytes, s>>>(d, slice, args);
+        else if (spec.kernel) kernel<<<(count + spec.warps - 1) / spec.warps, spec.warps * 32, spec.shared_bytes, s>>>(d, slice, args);
+        else kernel<<<blocks, kWarpsPerBlock * 32, 0, s>>>(d, slice, args);
         CUDA_TRY(h, cudaGetLastError());
         h->kernel_launches++;
         if (sparse) {
@@ -1401,7 +1431,7 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
     } else if (pick_spec(h, record != 0, &spec) && spec.coulomb) {
         h->kernel_name = "lj_spec_kernel<coulomb, record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", lanes=" + std::to_string(h->spec_lanes) + ", warps=" +
-                         std::to_string(kWarpsPerBlock) + ">";
+                         std::to_string(spec.warps) + ">";
     } else if (pick_spec(h, record != 0, &spec)) {
         h->kernel_name = "lj_spec_kernel<record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", lanes=" + std::to_string(h->spec_lanes) + ", warps=" +

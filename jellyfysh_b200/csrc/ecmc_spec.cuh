@@ -197,9 +197,14 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
     // COULOMB: the kernel is several thousand instructions (the Ewald sum, two inversions), and warps that are all
     // somewhere else in it starve on instruction fetch (measured: 19 of 26 % of the stall samples on the Ewald sum alone):
     // the warps of a CTA meet at a barrier before every batch, like the chains of molecule_kernel before every event.
+#ifdef ECMC_SPEC_ALIGN_LJ
+    constexpr bool ALIGNED = true;   // (experiment: the barrier for the Lennard-Jones model as well)
+#else
+    constexpr bool ALIGNED = COULOMB;
+#endif
     bool done = false;
-    while (COULOMB || n.events < max_events) {
-        if constexpr (COULOMB) {
+    while (ALIGNED || n.events < max_events) {
+        if constexpr (ALIGNED) {
             const bool finished = done || n.events >= max_events;
             if (__syncthreads_and(finished)) break;
             if (finished) continue;
@@ -638,7 +643,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                 }
             }
             stopped_by_time = true;
-            if constexpr (COULOMB) { done = true; continue; }
+            if constexpr (ALIGNED) { done = true; continue; }
             break;
         }
         if (was_pending) {
