@@ -416,7 +416,9 @@ int ecmc_bond_histograms(EcmcHandle *h, int32_t n_bins, double length_min, doubl
  * surplus, Lennard-Jones cell veto, one occupant per cell) are advanced by a kernel that evaluates several successive
  * events of a chain side by side under the assumption that they are rejected cell vetoes, and commits them up to the
  * first event that is not (csrc/ecmc_spec.cuh). The committed events -- winner, target, lifting, times, positions --
- * are those of the one-event-at-a-time loop (single_process_mediator.py:91-156), event for event.
+ * are those of the one-event-at-a-time loop (single_process_mediator.py:91-156), event for event. The Coulomb atoms
+ * (pair candidates from the inverse-power Coulomb bound confirmed against merged-image Coulomb, merged-image Coulomb cell
+ * veto, one occupant per cell, with charges) run the same batch with their potentials (csrc/ecmc_spec.cuh, kSpecCoulomb).
  *   ECMC_OPTION_BATCHED_EVENTS    1 (default) / 0: fall back to the one-event-at-a-time kernel
  *   ECMC_OPTION_PRUNE_CANDIDATES  1 (default) / 0: in ecmc_run / ecmc_run_from_host a pair candidate that provably cannot
  *                                 precede the cell-veto / cell-boundary candidate of its event is not inverted (its
