@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ECMC_ABI_VERSION 4
+#define ECMC_ABI_VERSION 5
 #define ECMC_MAX_BONDS 4
 #define ECMC_MAX_DIM 3
 
@@ -222,8 +222,24 @@ typedef struct EcmcProgram {
      * (leaf a of the active object against leaf b of every other object), all with hard potentials; the velocity of
      * the active leaf and of its root unit live in EcmcChainState.velocity / root_velocity. */
     int32_t eoc_sequential;
-    int32_t reserved2;
+    /* ---- root-unit-active mode (the shipped dipoles/dipole_motion.ini): composite point objects of TWO leaves without a
+     * cell system whose independent active unit alternates between a leaf unit and the ROOT unit of an object -- the whole
+     * object then moves, root and leaves with the full velocity. RootLeafUnitActiveSwitcher
+     * (root_leaf_unit_active_switcher.py:102-228) switches: switch_chain_length[0] after the root unit handed over to a
+     * leaf (or after the start of the run) the root unit of the active leaf takes over (aim_mode root_unit_active),
+     * switch_chain_length[1] later one of its leaves, drawn by random.choice, takes over again (aim_mode
+     * leaf_unit_active); every switch re-creates the end-of-chain candidate. While a root unit is active the factors are
+     * those of the root-unit-active handlers with the potentials of the leaf mode: per other object one
+     * RootUnitActiveTwoCompositeObjectSummedBoundingPotentialEventHandler
+     * (root_unit_active_two_composite_object_summed_bounding_potential_event_handler.py:116-190: minimum over ALL pairs
+     * (local leaf, target leaf) of the bounding potential's displacement, confirmed against the summed derivatives, the
+     * target object takes over as a whole) with pair_potential / pair_bounding_potential, and per inter_factors entry
+     * (a, b) and other object one RootUnitActiveTwoLeafUnitEventHandler (root_unit_active_two_leaf_unit_event_handler.py:
+     * 72-125: local leaf a against leaf b of the other object, which then takes over as a whole) with inter_potential.
+     * Requires nodes_per_root = 2, no_cells, pair_handler = ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING. */
+    int32_t root_mode;
     double eoc_cos, eoc_sin;
+    double switch_chain_length[2];
 } EcmcProgram;
 
 /* ---- per-chain lifting state ("who is active, where is the clock") ------------------------------------
@@ -241,7 +257,8 @@ typedef struct EcmcChainState {
     uint32_t stream;          /* random-stream id of this chain (Philox key word 0) */
     int32_t pending_kind;     /* EcmcEventKind of a candidate kept across a host control event, or 0 */
     int32_t pending_target;   /* pair / bond: target id; veto, boundary: target cell */
-    int32_t reserved;
+    int32_t mode;             /* EcmcProgram.root_mode: 1 while the ROOT unit of `active`'s object is the independent active
+                               * unit (`active` is then the first leaf of that object), 0 while the leaf `active` is */
     double pending_q, pending_r;
     double pending_rate;      /* bounding event rate stored by the handler for the confirmation step */
     /* The kept handler computes its out-state from the in-state it was given BEFORE the control event
@@ -267,6 +284,13 @@ typedef struct EcmcChainState {
     double velocity[2];
     double root_velocity[2];
     double pending_position_y, pending_root_position_y;
+    /* EcmcProgram.root_mode: the candidate event time of the RootLeafUnitActiveSwitcher that is running (time stamp of the
+     * root unit when it was created + its chain length) and the time of the last committed end of chain (the
+     * _last_committed_event_time that a re-created end-of-chain candidate continues from,
+     * single_independent_active_periodic_direction_end_of_chain_event_handler.py:203-215). While a root unit is active,
+     * pending_position / pending_position_y hold the in-state coordinates of its first / second leaf. */
+    double switch_q, switch_r;
+    double eoc_last_q, eoc_last_r;
 } EcmcChainState;
 
 enum EcmcEventKind {
@@ -278,7 +302,8 @@ enum EcmcEventKind {
     ECMC_EVENT_CELL_BOUNDING = 5, /* pair factor of a non-nearby cell, found through the cell-bounding potential */
     ECMC_EVENT_BOND = 6,          /* intramolecular two-leaf factor of the factor type map (EcmcProgram.bonds) */
     ECMC_EVENT_FACTOR_PAIR = 7,   /* two-leaf factor between different objects (EcmcProgram.inter_factors) */
-    ECMC_EVENT_BENDING = 8        /* three-leaf bending factor */
+    ECMC_EVENT_BENDING = 8,       /* three-leaf bending factor */
+    ECMC_EVENT_SWITCH = 9         /* RootLeafUnitActiveSwitcher: the root unit / a leaf unit of the same object takes over */
 };
 
 /* One committed event, as the scheduler + winning handler of the reference would report it. */
@@ -291,7 +316,7 @@ typedef struct EcmcEventRecord {
     int32_t n_candidates;     /* finite candidate times that entered the argmin */
     int32_t new_active;       /* active particle after the event */
     int32_t new_direction;
-    int32_t reserved;
+    int32_t mode;             /* EcmcChainState.mode after the event (0 unless the program has a root-unit-active mode) */
     double time_q, time_r;    /* event time */
     double active_pos[ECMC_MAX_DIM]; /* position of the (old) active particle after the event */
 } EcmcEventRecord;
@@ -483,6 +508,7 @@ void ecmc_random_words(uint32_t seed, uint32_t stream, uint64_t event, uint32_t 
 #define ECMC_SLOT_LIFTING 6u         /* doubles -> Lifting.insert / RatioLifting draws */
 #define ECMC_SLOT_FACTOR_TIME 7u     /* index = target leaf; factor-type-map pair factors: double 0 -> expovariate(beta) */
 #define ECMC_SLOT_BENDING_TIME 8u    /* double 0 -> expovariate(beta) of the bending factor */
+#define ECMC_SLOT_SWITCH 9u          /* words -> random.choice over the leaves of the object whose root unit hands over */
 /* Composite-object pair candidates draw double k of (ECMC_SLOT_PAIR_TIME, target root) for target leaf k. All draws of an
  * out-state come from ECMC_SLOT_CONFIRM in call order: 0 = confirmation, 1 = Lifting.insert of the active unit,
  * 2 = RatioLifting.get_active_identifier. */

@@ -1,7 +1,7 @@
 """ctypes mirror of include/ecmc.h (the C ABI of libecmc_b200.so). Plain data only, no computation."""
 import ctypes as C
 
-ECMC_ABI_VERSION = 4
+ECMC_ABI_VERSION = 5
 ECMC_MAX_DIM = 3
 ECMC_MAX_BONDS = 4
 ECMC_MAX_INTER_FACTORS = 4
@@ -41,6 +41,7 @@ EVENT_CELL_BOUNDING = 5
 EVENT_BOND = 6
 EVENT_FACTOR_PAIR = 7
 EVENT_BENDING = 8
+EVENT_SWITCH = 9
 
 FAR_NONE = 0
 FAR_CELL_VETO = 1
@@ -48,7 +49,7 @@ FAR_CELL_BOUNDING = 2
 EVENT_NAMES = {EVENT_NONE: "none", EVENT_PAIR: "pair", EVENT_CELL_VETO: "cell_veto",
                EVENT_CELL_BOUNDARY: "cell_boundary", EVENT_END_OF_CHAIN: "end_of_chain",
                EVENT_CELL_BOUNDING: "cell_bounding", EVENT_BOND: "bond", EVENT_FACTOR_PAIR: "factor_pair",
-               EVENT_BENDING: "bending"}
+               EVENT_BENDING: "bending", EVENT_SWITCH: "switch"}
 
 SLOT_PAIR_TIME = 1
 SLOT_VETO_TIME = 2
@@ -58,6 +59,7 @@ SLOT_END_OF_CHAIN = 5
 SLOT_LIFTING = 6
 SLOT_FACTOR_TIME = 7
 SLOT_BENDING_TIME = 8
+SLOT_SWITCH = 9
 
 
 def slot(kind: int, index: int = 0) -> int:
@@ -112,7 +114,8 @@ class EcmcProgram(C.Structure):
                 ("bending_children", C.c_int32 * 3), ("bending_separations", C.c_int32 * 4), ("boundary_keeps_factors", C.c_int32),
                 ("bending_potential", EcmcPotential), ("bending_offset", C.c_double),
                 ("bending_max_displacement", C.c_double),
-                ("eoc_sequential", C.c_int32), ("reserved2", C.c_int32), ("eoc_cos", C.c_double), ("eoc_sin", C.c_double)]
+                ("eoc_sequential", C.c_int32), ("root_mode", C.c_int32), ("eoc_cos", C.c_double), ("eoc_sin", C.c_double),
+                ("switch_chain_length", C.c_double * 2)]
 
 
 class EcmcChainState(C.Structure):
@@ -122,7 +125,7 @@ class EcmcChainState(C.Structure):
                 ("eoc_next_active", C.c_int32), ("active_cell", C.c_int32),
                 ("event_counter", C.c_uint64),
                 ("stream", C.c_uint32), ("pending_kind", C.c_int32),
-                ("pending_target", C.c_int32), ("reserved", C.c_int32),
+                ("pending_target", C.c_int32), ("mode", C.c_int32),
                 ("pending_q", C.c_double), ("pending_r", C.c_double), ("pending_rate", C.c_double),
                 ("pending_position", C.c_double), ("pending_stamp_q", C.c_double), ("pending_stamp_r", C.c_double),
                 ("pending_root_position", C.c_double),
@@ -130,13 +133,14 @@ class EcmcChainState(C.Structure):
                 ("kept_rate", C.c_double), ("kept_position", C.c_double), ("kept_root_position", C.c_double),
                 ("kept_stamp_q", C.c_double), ("kept_stamp_r", C.c_double),
                 ("velocity", C.c_double * 2), ("root_velocity", C.c_double * 2),
-                ("pending_position_y", C.c_double), ("pending_root_position_y", C.c_double)]
+                ("pending_position_y", C.c_double), ("pending_root_position_y", C.c_double),
+                ("switch_q", C.c_double), ("switch_r", C.c_double), ("eoc_last_q", C.c_double), ("eoc_last_r", C.c_double)]
 
 
 class EcmcEventRecord(C.Structure):
     _fields_ = [("kind", C.c_int32), ("target", C.c_int32), ("target_cell", C.c_int32), ("accepted", C.c_int32),
                 ("n_candidates", C.c_int32), ("new_active", C.c_int32), ("new_direction", C.c_int32),
-                ("reserved", C.c_int32),
+                ("mode", C.c_int32),
                 ("time_q", C.c_double), ("time_r", C.c_double), ("active_pos", C.c_double * ECMC_MAX_DIM)]
 
 
@@ -155,7 +159,7 @@ class EcmcStats(C.Structure):
 def record_dtype():
     import numpy as np
     return np.dtype([("kind", "<i4"), ("target", "<i4"), ("target_cell", "<i4"), ("accepted", "<i4"),
-                     ("n_candidates", "<i4"), ("new_active", "<i4"), ("new_direction", "<i4"), ("reserved", "<i4"),
+                     ("n_candidates", "<i4"), ("new_active", "<i4"), ("new_direction", "<i4"), ("mode", "<i4"),
                      ("time_q", "<f8"), ("time_r", "<f8"), ("active_pos", "<f8", (ECMC_MAX_DIM,))])
 
 
@@ -164,7 +168,7 @@ def chain_state_dtype():
     return np.dtype([("active", "<i4"), ("direction", "<i4"), ("time_q", "<f8"), ("time_r", "<f8"),
                      ("eoc_q", "<f8"), ("eoc_r", "<f8"), ("eoc_next_active", "<i4"), ("active_cell", "<i4"),
                      ("event_counter", "<u8"), ("stream", "<u4"), ("pending_kind", "<i4"),
-                     ("pending_target", "<i4"), ("reserved", "<i4"),
+                     ("pending_target", "<i4"), ("mode", "<i4"),
                      ("pending_q", "<f8"), ("pending_r", "<f8"), ("pending_rate", "<f8"),
                      ("pending_position", "<f8"), ("pending_stamp_q", "<f8"), ("pending_stamp_r", "<f8"),
                      ("pending_root_position", "<f8"),
@@ -172,8 +176,9 @@ def chain_state_dtype():
                      ("kept_rate", "<f8"), ("kept_position", "<f8"), ("kept_root_position", "<f8"),
                      ("kept_stamp_q", "<f8"), ("kept_stamp_r", "<f8"),
                      ("velocity", "<f8", (2,)), ("root_velocity", "<f8", (2,)),
-                     ("pending_position_y", "<f8"), ("pending_root_position_y", "<f8")])
+                     ("pending_position_y", "<f8"), ("pending_root_position_y", "<f8"),
+                     ("switch_q", "<f8"), ("switch_r", "<f8"), ("eoc_last_q", "<f8"), ("eoc_last_r", "<f8")])
 
 
 assert C.sizeof(EcmcEventRecord) == 72
-assert C.sizeof(EcmcChainState) == 240
+assert C.sizeof(EcmcChainState) == 272

@@ -190,7 +190,7 @@ disk_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ Dis
             rec.kind = kind; rec.target = kind == ECMC_EVENT_END_OF_CHAIN ? new_active : btarget; rec.target_cell = -1;
             rec.accepted = 1; rec.n_candidates = n_cand;
             rec.new_active = new_active; rec.new_direction = 0;
-            rec.reserved = 0;
+            rec.mode = 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
             rec.active_pos[0] = a.x; rec.active_pos[1] = a.y; rec.active_pos[2] = 0.0;
             A.records[(size_t)chain * A.records_per_chain + n_events] = rec;

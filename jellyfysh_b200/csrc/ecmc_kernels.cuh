@@ -780,7 +780,7 @@ event_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const
             rec.accepted = accepted; rec.n_candidates = n_cand;
             rec.new_active = new_active;
             rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % dimension : dir;
-            rec.reserved = 0;
+            rec.mode = 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
             const Particle lab = rotate_out(a, dir);
             rec.active_pos[0] = lab.x; rec.active_pos[1] = lab.y; rec.active_pos[2] = lab.z;
@@ -959,7 +959,7 @@ ECMC_D void start_chain(const DeviceProgram &P, const DeviceState &S, const uint
         st.eoc_q = eoc.q; st.eoc_r = eoc.r;
         const StreamKey key = {P.seed, st.stream, 0ull};
         st.eoc_next_active = draw_end_of_chain_active(P, key);
-        st.pending_kind = ECMC_EVENT_NONE; st.pending_target = 0; st.reserved = 0;
+        st.pending_kind = ECMC_EVENT_NONE; st.pending_target = 0; st.mode = 0;
         st.pending_q = 0.0; st.pending_r = 0.0; st.pending_rate = 0.0; st.pending_position = 0.0;
         st.pending_root_position = 0.0;
         st.pending_stamp_q = 0.0; st.pending_stamp_r = 0.0;

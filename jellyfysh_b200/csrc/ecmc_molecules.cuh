@@ -716,7 +716,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             rec.n_candidates = n_cand;
             rec.new_active = new_active;
             rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % P.dimension : dir;
-            rec.reserved = 0;
+            rec.mode = 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
             rec.active_pos[0] = apos.x; rec.active_pos[1] = apos.y; rec.active_pos[2] = apos.z;
             A.records[(size_t)chain * A.records_per_chain + n_events] = rec;
@@ -852,7 +852,7 @@ molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState
         st.eoc_q = eoc.q; st.eoc_r = eoc.r;
         const StreamKey key = {P.seed, st.stream, 0ull};
         st.eoc_next_active = draw_end_of_chain_active(P, key);
-        st.pending_kind = ECMC_EVENT_NONE; st.pending_target = 0; st.reserved = 0;
+        st.pending_kind = ECMC_EVENT_NONE; st.pending_target = 0; st.mode = 0;
         st.pending_q = 0.0; st.pending_r = 0.0; st.pending_rate = 0.0; st.pending_position = 0.0;
         st.pending_stamp_q = 0.0; st.pending_stamp_r = 0.0; st.pending_root_position = 0.0;
         st.kept_kind = ECMC_EVENT_NONE; st.kept_target = 0; st.kept_q = 0.0; st.kept_r = 0.0; st.kept_rate = 0.0;

@@ -587,7 +587,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
                     EcmcEventRecord rec;
                     rec.kind = ECMC_EVENT_CELL_VETO; rec.target = my_occupant; rec.target_cell = my_cell;
                     rec.accepted = 0; rec.n_candidates = my_candidates + 1;
-                    rec.new_active = active; rec.new_direction = dir; rec.reserved = 0;
+                    rec.new_active = active; rec.new_direction = dir; rec.mode = 0;
                     rec.time_q = my_veto_time.q; rec.time_r = my_veto_time.r;
                     Moving after = a;
                     after.p0 = my_next_x;
@@ -723,7 +723,7 @@ lj_spec_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, con
             rec.accepted = accepted; rec.n_candidates = n_cand;
             rec.new_active = new_active;
             rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % 3 : dir;
-            rec.reserved = 0;
+            rec.mode = 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
             const Particle lab = rotate_out(a, dir);
             rec.active_pos[0] = lab.x; rec.active_pos[1] = lab.y; rec.active_pos[2] = lab.z;

@@ -131,6 +131,20 @@ class ProgramBuilder:
             p.bending_max_displacement = bending["max_displacement"]
         return self
 
+    def set_root_mode(self, leaf_to_root_chain_length, root_to_leaf_chain_length):
+        """Root-unit-active mode (dipoles/dipole_motion.ini): two RootLeafUnitActiveSwitcher handlers alternate the
+        independent active unit between a leaf unit (for leaf_to_root_chain_length) and the root unit of its object (for
+        root_to_leaf_chain_length); the root-unit-active handlers use the pair and inter-object potentials of the leaf
+        mode. Needs set_pair(PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, ...), set_composite(2, ...), no cell system."""
+        p = self.program
+        if p.nodes_per_root != 2 or not p.no_cells or p.pair_handler != abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING:
+            raise ValueError("root-unit-active mode: composite objects of two leaves with the composite-object pair "
+                             "handler, no cell system")
+        p.root_mode = 1
+        p.switch_chain_length[0] = leaf_to_root_chain_length
+        p.switch_chain_length[1] = root_to_leaf_chain_length
+        return self
+
     def set_cell_bounding(self, potential, bounds, use_charge=False, target_charge=1.0):
         """Far field through TwoLeafUnitCellBoundingPotentialEventHandler: bounds[n_cells][dimension][2] holds
         (upper bound, -lower bound) of the derivative per relative cell (CellBoundingPotential._derivative_bounds)."""

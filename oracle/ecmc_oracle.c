@@ -1048,6 +1048,9 @@ ORC_API OrcChain *orc_chain_create(const EcmcProgram *prog) {
     if (prog->eoc_sequential && (c->D != 2 || !prog->no_cells || c->npr < 2 || c->molecules ||
                                  prog->pair_handler != ECMC_PAIR_NONE || prog->veto_enabled)) goto fail;
     if (c->molecules && (c->D != 3 || c->npr > 4 || prog->max_occupants != 1)) goto fail;
+    /* root-unit-active mode: dipoles without a cell system, composite-object pair handler */
+    if (prog->root_mode && (!c->molecules || c->npr != 2 || !prog->no_cells || prog->bending_enabled ||
+                            prog->pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING)) goto fail;
     if (c->N % c->npr || prog->n_bonds < 0 || prog->n_bonds > ECMC_MAX_BONDS) goto fail;
     if (prog->n_bonds > 0 && c->npr == 1) goto fail;
     c->root_pos = (double *)calloc((size_t)(c->N / c->npr) * c->D, sizeof(double));
@@ -1152,9 +1155,20 @@ static void occ_remove(OrcChain *c, int cell, int id) {
 static void schedule_end_of_chain(OrcChain *c) {
     otime now = {c->st.time_q, c->st.time_r};
     double new_chain_time = time_sub(now, now) + c->prog.chain_time;
+    if (c->prog.root_mode) {
+        /* the candidate is also re-created by a RootLeafUnitActiveSwitcher event, between two ends of chain:
+         * (_last_committed_event_time - current_time_stamp) + chain_time, :203-215 */
+        otime last = {c->st.eoc_last_q, c->st.eoc_last_r};
+        new_chain_time = time_sub(last, now) + c->prog.chain_time;
+    }
     otime t = time_add(now, new_chain_time);
     c->st.eoc_q = t.q; c->st.eoc_r = t.r;
-    if (c->npr == 1) {
+    if (c->prog.root_mode && c->st.mode == 1) {
+        /* the root unit was independent active: (randint(0, number_of_root_nodes - 1),), :226-229; recorded as the
+         * first leaf of that object */
+        c->st.eoc_next_active = (int)rng_randbelow(c->prog.seed, c->st.stream, c->st.event_counter,
+                                                   ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)(c->N / c->npr)) * c->npr;
+    } else if (c->npr == 1) {
         c->st.eoc_next_active = (int)rng_randbelow(c->prog.seed, c->st.stream, c->st.event_counter,
                                                    ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)c->N);
     } else {
@@ -1197,6 +1211,13 @@ ORC_API void orc_chain_start(OrcChain *c, uint32_t stream) {
     }
     schedule_end_of_chain(c);
     c->st.pending_kind = ECMC_EVENT_NONE;
+    if (c->prog.root_mode) {
+        /* the leaf-to-root switcher is created at the start of the run: time stamp of the root unit + chain length
+         * (RootLeafUnitActiveSwitcher.send_event_time, root_leaf_unit_active_switcher.py:102-127) */
+        otime zero = {0.0, 0.0};
+        otime t = time_add(zero, c->prog.switch_chain_length[0]);
+        c->st.switch_q = t.q; c->st.switch_r = t.r;
+    }
     if (c->prog.eoc_sequential) {
         /* InitialChainStartOfRunEventHandler (initial_chain_start_of_run_event_handler.py:92-131): the active leaf gets
          * speed along the initial direction, its root unit that velocity times the leaf's weight
@@ -1335,7 +1356,10 @@ static candidate boundary_candidate(OrcChain *c, double *boundary_out) {
 }
 
 /* BasicEventHandler._time_slice_unit for the active particle, abstracts/abstracts.py:82-95 */
+static void time_slice_object(OrcChain *c, otime event_time);
+
 static void time_slice_active(OrcChain *c, otime event_time) {
+    if (c->prog.root_mode && c->st.mode == 1) { time_slice_object(c, event_time); return; }
     double *pa = c->pos + c->st.active * c->D;
     otime stamp = {c->st.time_q, c->st.time_r};
     double dt = time_sub(event_time, stamp);
@@ -1671,7 +1695,10 @@ static int is_leaf_kind(int kind) {
            kind == ECMC_EVENT_FACTOR_PAIR;
 }
 
+static int root_mode_step(OrcChain *c, otime until, EcmcEventRecord *rec);
+
 static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
+    if (c->prog.root_mode && c->st.mode == 1) return root_mode_step(c, until, rec);
     candidate best;
     int n_cand = 0;
     double boundary_position = 0.0;
@@ -1780,6 +1807,13 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         cand.t.q = c->st.eoc_q; cand.t.r = c->st.eoc_r;
         n_cand++;
         if (lt_candidate(&cand, &best)) best = cand;
+        if (c->prog.root_mode) {
+            /* the leaf-to-root RootLeafUnitActiveSwitcher, in the scheduler since the last switch */
+            cand.kind = ECMC_EVENT_SWITCH; cand.target = -1;
+            cand.t.q = c->st.switch_q; cand.t.r = c->st.switch_r;
+            n_cand++;
+            if (lt_candidate(&cand, &best)) best = cand;
+        }
         if (!time_lt(best.t, until)) {
             c->st.pending_kind = interaction.kind;
             c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
@@ -1801,7 +1835,7 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         }
     }
     c->st.pending_kind = ECMC_EVENT_NONE;
-    if (was_pending && best.kind != ECMC_EVENT_END_OF_CHAIN) {
+    if (was_pending && best.kind != ECMC_EVENT_END_OF_CHAIN && best.kind != ECMC_EVENT_SWITCH) {
         c->pos[c->st.active * D + dir] = c->st.pending_position;
         c->root_pos[active_root * D + dir] = c->st.pending_root_position;
         c->st.time_q = c->st.pending_stamp_q;
@@ -1929,6 +1963,15 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         rec_target = new_active;
         accepted = 1;
         c->stats.end_of_chain_events++;
+        if (c->prog.root_mode) { c->st.eoc_last_q = best.t.q; c->st.eoc_last_r = best.t.r; }
+        break;
+    case ECMC_EVENT_SWITCH:
+        /* RootLeafUnitActiveSwitcher._send_out_state_root_unit_active (root_leaf_unit_active_switcher.py:171-208): the
+         * other leaves of the object take the velocity and the time stamp of the active leaf, the root unit ends with the
+         * full velocity; recorded with the first leaf of the object as the active one */
+        new_active = active_root * npr;
+        accepted = 1;
+        c->st.mode = 1;
         break;
     default: break;
     }
@@ -1938,7 +1981,7 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         rec->kind = best.kind;
         rec->target = rec_target;
         rec->target_cell = best.target_cell;
-        rec->accepted = best.kind == ECMC_EVENT_END_OF_CHAIN ? 1 : (new_active != old_active);
+        rec->accepted = (best.kind == ECMC_EVENT_END_OF_CHAIN || best.kind == ECMC_EVENT_SWITCH) ? 1 : (new_active != old_active);
         rec->n_candidates = n_cand;
         rec->time_q = best.t.q; rec->time_r = best.t.r;
         for (int d = 0; d < D; d++) rec->active_pos[d] = c->pos[old_active * D + d];
@@ -1949,8 +1992,208 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
     c->stats.candidates += (uint64_t)n_cand;
     if (best.kind == ECMC_EVENT_END_OF_CHAIN) c->st.direction = (c->st.direction + 1) % D;
     molecule_occupancy_update(c, new_active);
-    if (best.kind == ECMC_EVENT_END_OF_CHAIN) schedule_end_of_chain(c);
-    if (rec) { rec->new_active = c->st.active; rec->new_direction = c->st.direction; }
+    if (best.kind == ECMC_EVENT_SWITCH) {
+        /* the root-to-leaf switcher is created with the root unit's time stamp, the end of chain is re-created */
+        otime t = time_add(best.t, c->prog.switch_chain_length[1]);
+        c->st.switch_q = t.q; c->st.switch_r = t.r;
+    }
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN || best.kind == ECMC_EVENT_SWITCH) schedule_end_of_chain(c);
+    if (rec) { rec->new_active = c->st.active; rec->new_direction = c->st.direction; rec->mode = c->st.mode; }
+    return 1;
+}
+
+/* ---- the root unit of an object is the independent active unit (EcmcProgram.root_mode, dipoles/dipole_motion.ini):
+ * root and leaves move with the full velocity and carry one time stamp. `active` is the first leaf of the object. */
+static void time_slice_object(OrcChain *c, otime event_time) {
+    /* BasicEventHandler._time_slice_unit for the root unit and every leaf (abstracts.py:89-107) */
+    const int D = c->D, root = c->st.active / c->npr;
+    otime stamp = {c->st.time_q, c->st.time_r};
+    double dt = time_sub(event_time, stamp);
+    for (int d = 0; d < D; d++) {
+        double v = d == c->st.direction ? c->prog.speed : 0.0;
+        for (int k = 0; k < c->npr; k++) {
+            double *p = c->pos + (root * c->npr + k) * D;
+            p[d] = correct_position_entry(p[d] + v * dt, c->L);
+        }
+        double *pr = c->root_pos + root * D;
+        pr[d] = correct_position_entry(pr[d] + v * dt, c->L);
+    }
+    c->st.time_q = event_time.q; c->st.time_r = event_time.r;
+}
+
+static int root_mode_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
+    const int npr = c->npr, D = c->D, dir = c->st.direction, n_roots = c->N / npr;
+    const int active_root = c->st.active / npr;
+    candidate best;
+    int n_cand = 0;
+    best.kind = ECMC_EVENT_NONE; best.t.q = ORC_INF; best.t.r = ORC_INF; best.target = -1; best.target_cell = -1;
+    best.rate = 0.0;
+    const int was_pending = c->st.pending_kind != ECMC_EVENT_NONE;
+    otime now = {c->st.time_q, c->st.time_r};
+    if (was_pending) {
+        best.kind = c->st.pending_kind;
+        best.t.q = c->st.pending_q; best.t.r = c->st.pending_r;
+        best.target = c->st.pending_target;
+    } else {
+        for (int t = 0; t < n_roots; t++) {
+            if (t == active_root) continue;
+            /* RootUnitActiveTwoCompositeObjectSummedBoundingPotentialEventHandler.send_event_time (:116-152): minimum over
+             * the local leaf units x the target leaf units (both sorted by identifier) of the bounding potential's
+             * displacement, one expovariate each in that order */
+            candidate cand;
+            cand.kind = ECMC_EVENT_PAIR; cand.target = t; cand.target_cell = -1; cand.rate = 0.0;
+            double earliest = ORC_INF;
+            for (int i = 0; i < npr; i++)
+                for (int j = 0; j < npr; j++) {
+                    int local = active_root * npr + i, target = t * npr + j;
+                    double sep[ECMC_MAX_DIM] = {0, 0, 0};
+                    separation_vector(c->pos + local * D, c->pos + target * D, D, c->L, sep);
+                    double c1 = c->prog.pair_use_charge ? c->charge[local] : 1.0;
+                    double c2 = c->prog.pair_use_charge ? c->charge[target] : 1.0;
+                    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter,
+                                          ECMC_SLOT(ECMC_SLOT_PAIR_TIME, t), (uint32_t)(i * npr + j));
+                    double dt = pot_displacement(&c->pair_bound, dir, c->prog.speed, sep, D, c1, c2,
+                                                 rng_expovariate(u, c->prog.beta));
+                    if (dt < earliest) earliest = dt;
+                }
+            cand.t = time_add(now, earliest);
+            if (!isinf(cand.t.q)) { n_cand++; if (lt_candidate(&cand, &best)) best = cand; }
+            /* RootUnitActiveTwoLeafUnitEventHandler (send_event_time of TwoLeafUnitEventHandler,
+             * two_leaf_unit_event_handler.py:105-138, for the moving leaf of the factor): one per factor type map entry */
+            for (int f = 0; f < c->prog.n_inter_factors; f++) {
+                int local = active_root * npr + c->prog.inter_factors[f][0];
+                int target = t * npr + c->prog.inter_factors[f][1];
+                double sep[ECMC_MAX_DIM] = {0, 0, 0};
+                separation_vector(c->pos + local * D, c->pos + target * D, D, c->L, sep);
+                double dU = 0.0;
+                if (pot_needs_potential_change(c->inter_pot.kind)) {
+                    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter,
+                                          ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), (uint32_t)c->prog.inter_factors[f][0]);
+                    dU = rng_expovariate(u, c->prog.beta);
+                }
+                candidate fc;
+                fc.kind = ECMC_EVENT_FACTOR_PAIR; fc.target = target; fc.target_cell = -1; fc.rate = 0.0;
+                fc.t = time_add(now, pot_displacement(&c->inter_pot, dir, c->prog.speed, sep, D, 1.0, 1.0, dU));
+                if (!isinf(fc.t.q)) { n_cand++; if (lt_candidate(&fc, &best)) best = fc; }
+            }
+        }
+    }
+    {
+        candidate interaction = best;
+        candidate cand;
+        cand.kind = ECMC_EVENT_END_OF_CHAIN; cand.target = c->st.eoc_next_active; cand.target_cell = -1; cand.rate = 0.0;
+        cand.t.q = c->st.eoc_q; cand.t.r = c->st.eoc_r;
+        n_cand++;
+        if (lt_candidate(&cand, &best)) best = cand;
+        cand.kind = ECMC_EVENT_SWITCH; cand.target = -1;
+        cand.t.q = c->st.switch_q; cand.t.r = c->st.switch_r;
+        n_cand++;
+        if (lt_candidate(&cand, &best)) best = cand;
+        if (!time_lt(best.t, until)) {
+            c->st.pending_kind = interaction.kind;
+            c->st.pending_q = interaction.t.q; c->st.pending_r = interaction.t.r;
+            c->st.pending_rate = 0.0;
+            c->st.pending_target = interaction.target;
+            if (!was_pending) {
+                /* the in-state of the handler that stays in the scheduler: the coordinates of the two leaves */
+                c->st.pending_position = c->pos[(active_root * npr) * D + dir];
+                c->st.pending_position_y = c->pos[(active_root * npr + 1) * D + dir];
+                c->st.pending_root_position = c->root_pos[active_root * D + dir];
+                c->st.pending_stamp_q = c->st.time_q;
+                c->st.pending_stamp_r = c->st.time_r;
+            }
+            return 0;
+        }
+    }
+    c->st.pending_kind = ECMC_EVENT_NONE;
+    /* The root-unit-active handlers get a fresh copy of the objects for their out-state (mediator.py:
+     * get_arguments_composite_objects_lifting) and time-slice THAT to the event time; only the confirmation of the
+     * summed-bounding handler uses the leaf units it time-sliced in send_event_time (:149, :154-168). */
+    double in_state[2][ECMC_MAX_DIM];
+    for (int k = 0; k < npr; k++)
+        for (int d = 0; d < D; d++) in_state[k][d] = c->pos[(active_root * npr + k) * D + d];
+    otime in_stamp = now;
+    if (was_pending) {
+        in_state[0][dir] = c->st.pending_position;
+        in_state[1][dir] = c->st.pending_position_y;
+        in_stamp.q = c->st.pending_stamp_q; in_stamp.r = c->st.pending_stamp_r;
+    }
+    const int old_active = c->st.active;
+    int new_active = old_active, rec_target = -1;
+    time_slice_object(c, best.t);
+    switch (best.kind) {
+    case ECMC_EVENT_PAIR: {
+        /* send_out_state, :154-190 */
+        rec_target = best.target;
+        c->stats.pair_events++;
+        double dt = time_sub(best.t, in_stamp);
+        for (int k = 0; k < npr; k++)
+            for (int d = 0; d < D; d++) {
+                double v = d == dir ? c->prog.speed : 0.0;
+                in_state[k][d] = correct_position_entry(in_state[k][d] + v * dt, c->L);
+            }
+        double bounding_event_rate = 0.0, factor_derivative = 0.0;
+        for (int i = 0; i < npr; i++)
+            for (int j = 0; j < npr; j++) {
+                int local = active_root * npr + i, target = best.target * npr + j;
+                double sep[ECMC_MAX_DIM] = {0, 0, 0};
+                separation_vector(in_state[i], c->pos + target * D, D, c->L, sep);
+                double c1 = c->prog.pair_use_charge ? c->charge[local] : 1.0;
+                double c2 = c->prog.pair_use_charge ? c->charge[target] : 1.0;
+                double b = pot_derivative(&c->pair_bound, dir, c->prog.speed, sep, D, c1, c2);
+                bounding_event_rate += b > 0.0 ? b : 0.0;
+                factor_derivative += pot_derivative(&c->pair_pot, dir, c->prog.speed, sep, D, c1, c2);
+            }
+        if (factor_derivative > 0) {
+            if (bounding_event_rate < factor_derivative) c->stats.bound_violations++;
+            double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), 0);
+            if (0 + (bounding_event_rate - 0) * u < factor_derivative) new_active = best.target * npr;
+        }
+        break;
+    }
+    case ECMC_EVENT_FACTOR_PAIR:
+        /* RootUnitActiveTwoLeafUnitEventHandler.send_out_state (:102-125): the object of the target leaf takes over */
+        rec_target = best.target;
+        new_active = (best.target / npr) * npr;
+        c->stats.factor_pair_events++;
+        break;
+    case ECMC_EVENT_END_OF_CHAIN:
+        new_active = c->st.eoc_next_active;
+        rec_target = new_active;
+        c->stats.end_of_chain_events++;
+        c->st.eoc_last_q = best.t.q; c->st.eoc_last_r = best.t.r;
+        break;
+    case ECMC_EVENT_SWITCH: {
+        /* RootLeafUnitActiveSwitcher._send_out_state_leaf_unit_active (:129-169): random.choice over the leaves */
+        uint32_t chosen = rng_randbelow(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_SWITCH, 0),
+                                        (uint32_t)npr);
+        new_active = active_root * npr + (int)chosen;
+        c->st.mode = 0;
+        break;
+    }
+    default: break;
+    }
+    if (rec) {
+        memset(rec, 0, sizeof(*rec));
+        rec->kind = best.kind;
+        rec->target = rec_target;
+        rec->target_cell = -1;
+        rec->accepted = (best.kind == ECMC_EVENT_END_OF_CHAIN || best.kind == ECMC_EVENT_SWITCH) ? 1 : (new_active != old_active);
+        rec->n_candidates = n_cand;
+        rec->time_q = best.t.q; rec->time_r = best.t.r;
+        for (int d = 0; d < D; d++) rec->active_pos[d] = c->pos[old_active * D + d];
+    }
+    c->st.event_counter++;
+    c->stats.events++;
+    c->stats.candidates += (uint64_t)n_cand;
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN) c->st.direction = (c->st.direction + 1) % D;
+    molecule_occupancy_update(c, new_active);
+    if (best.kind == ECMC_EVENT_SWITCH) {
+        otime t = time_add(best.t, c->prog.switch_chain_length[0]);
+        c->st.switch_q = t.q; c->st.switch_r = t.r;
+    }
+    if (best.kind == ECMC_EVENT_END_OF_CHAIN || best.kind == ECMC_EVENT_SWITCH) schedule_end_of_chain(c);
+    if (rec) { rec->new_active = c->st.active; rec->new_direction = c->st.direction; rec->mode = c->st.mode; }
     return 1;
 }
 

@@ -280,7 +280,8 @@ def _pack_snapshots(run):
             "snap_n_surplus": np.array([len(s["surplus"]) for s in snaps], dtype=np.int32),
             "snap_active": np.array([s["active"] for s in snaps], dtype=np.int32),
             "snap_direction": np.array([s["direction"] for s in snaps], dtype=np.int32),
-            "snap_time": np.array([[s["time_q"], s["time_r"]] for s in snaps])}
+            "snap_time": np.array([[s["time_q"], s["time_r"]] for s in snaps]),
+            "snap_mode": np.array([s.get("mode", 0) for s in snaps], dtype=np.int32)}
 
 
 def chain_trace(name, ini, positions, seed, stream, n_events, snapshot_every, meta, charges=None, max_occupants=1,
@@ -359,6 +360,34 @@ def no_cell_traces():
                 n_events=4000, snapshot_every=250, charges=np.ones(n),
                 meta=dict(n=n, cells_per_side=[1, 1, 1], system_length=length, beta=2.0, mic=[1.0, 3.45, 6, 2],
                           ipcb=[1.5837], chain_time=0.78965, far_field=0))
+
+
+def dipole_motion_traces():
+    n = 3
+    # the shipped dipoles/dipole_motion.ini: the independent active unit alternates between a leaf unit and the root unit
+    # of a dipole (RootLeafUnitActiveSwitcher; root-unit-active composite-object and two-leaf handlers), three dipoles;
+    # once without and once with the shipped sampling events (candidates that survive a host control event)
+    roots, leaves = configs.dipole_start(n, seed=47)
+    replacements = [("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                    ("number_event_handlers = 2", f"number_event_handlers = {2 * (n - 1)}"),
+                    ("number_event_handlers = 1", f"number_event_handlers = {2 * (n - 1)}")]
+    meta = dict(n=2 * n, nodes_per_root=2, system_length=1.0, beta=1.0, chain_time=0.78965, mic=[1.0, 3.45, 6, 2],
+                ipcb=[1.5837], harmonic=[200.0, 0.1, 2.0], repulsive=[6.0, 1.0e-6], lifting=0, initial_active=0,
+                far_field=0, switch_chain_length=[0.69, 0.7])
+    ini = configs.shipped_without_sampling(REF, ("2018_JCP_149_064113", "dipoles", "dipole_motion.ini"),
+                                           replacements=replacements)
+    chain_trace("trace_dipole_motion", ini, None, seed=31, stream=21, n_events=4000, snapshot_every=250,
+                composites=(roots, leaves), charges=np.tile([1.0, -1.0], n), meta=meta)
+    ini = configs.shipped_ini(REF, "2018_JCP_149_064113", "dipoles", "dipole_motion.ini")
+    ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
+    for old, new in replacements + [("sampling_interval = 0.56789", "sampling_interval = 0.0831"),
+                                    ("filename = output/2018_JCP_149_064113/dipoles/SamplesOfSeparation_DipoleMotion.dat",
+                                     "filename = /tmp/jf_b200_golden_separation.dat")]:
+        assert old in ini, old
+        ini = ini.replace(old, new)
+    chain_trace("trace_dipole_motion_sampling", ini, None, seed=32, stream=22, n_events=2500, snapshot_every=250,
+                composites=(roots, leaves), charges=np.tile([1.0, -1.0], n),
+                meta=dict(meta, sampling_interval=0.0831))
 
 
 def no_cell_molecule_traces():
@@ -580,6 +609,8 @@ if __name__ == "__main__":  # noqa
     if "no_cells" in which:
         no_cell_traces()
         no_cell_molecule_traces()
+    if "no_cells" in which or "dipole_motion" in which:
+        dipole_motion_traces()
     if "water" in which:
         water_traces()
     if "lifting" in which:

@@ -54,6 +54,7 @@ def stream_double(seed, stream, event, slot, index):
 
 SLOT_PAIR_TIME, SLOT_VETO_TIME, SLOT_VETO_CHOICE, SLOT_CONFIRM, SLOT_END_OF_CHAIN, SLOT_LIFTING = 1, 2, 3, 4, 5, 6
 SLOT_FACTOR_TIME, SLOT_BENDING_TIME = 7, 8
+SLOT_SWITCH = 9  # words -> random.choice over the leaves when the root unit hands over to one of them
 SLOT_INIT = 15  # initial random positions (host side only)
 
 
@@ -100,6 +101,7 @@ class SlotRandom(random.Random):
 
 EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDARY, EVENT_END_OF_CHAIN, EVENT_CELL_BOUNDING = 1, 2, 3, 4, 5
 EVENT_BOND, EVENT_FACTOR_PAIR, EVENT_BENDING = 6, 7, 8
+EVENT_SWITCH = 9  # RootLeafUnitActiveSwitcher: the root unit / one leaf unit of the same object takes over
 HOST_EVENT = 0
 
 RECORD_DTYPE = np.dtype([("kind", "<i4"), ("target", "<i4"), ("target_cell", "<i4"), ("accepted", "<i4"),
@@ -199,8 +201,11 @@ class ReferenceRun:
             return EVENT_END_OF_CHAIN
         if "FixedSeparationsEventHandlerWithPiecewiseConstantBoundingPotential" in names:
             return EVENT_BENDING
-        if "TwoCompositeObjectSummedBoundingPotentialEventHandler" in names:
+        if names & {"TwoCompositeObjectSummedBoundingPotentialEventHandler",
+                    "RootUnitActiveTwoCompositeObjectSummedBoundingPotentialEventHandler"}:
             return EVENT_PAIR
+        if "RootLeafUnitActiveSwitcher" in names:
+            return EVENT_SWITCH
         if names & {"TwoLeafUnitEventHandler", "TwoLeafUnitBoundingPotentialEventHandler"}:
             local = self._factor_map_handlers().get(id(handler))
             if self.setting.number_of_node_levels == 1:
@@ -236,7 +241,9 @@ class ReferenceRun:
 
     @staticmethod
     def _is_composite_pair(handler):
-        return "TwoCompositeObjectSummedBoundingPotentialEventHandler" in {c.__name__ for c in type(handler).__mro__}
+        return bool({"TwoCompositeObjectSummedBoundingPotentialEventHandler",
+                     "RootUnitActiveTwoCompositeObjectSummedBoundingPotentialEventHandler"}
+                    & {c.__name__ for c in type(handler).__mro__})
 
     @staticmethod
     def _is_composite_cell_bounding(handler):
@@ -254,6 +261,14 @@ class ReferenceRun:
                 if leaf.value.velocity is None:
                     return self.leaf_id(leaf.value.identifier)
         raise RuntimeError("pair in-state without target")
+
+    def _moving_child_of_pair(self, in_state):
+        from jellyfysh.base.node import yield_leaf_nodes
+        for cnode in in_state:
+            for leaf in yield_leaf_nodes(cnode):
+                if leaf.value.velocity is not None:
+                    return leaf.value.identifier[-1]
+        raise RuntimeError("pair in-state without moving leaf")
 
     def _instrument(self):
         med = self.mediator
@@ -277,6 +292,10 @@ class ReferenceRun:
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_of_pair(args[0])))
                 elif _kind in (EVENT_BOND, EVENT_FACTOR_PAIR):
                     run.rng.set_context(run.events, make_slot(SLOT_FACTOR_TIME, run._target_of_pair(args[0])))
+                    if "RootUnitActiveTwoLeafUnitEventHandler" in {c.__name__ for c in type(_h).__mro__}:
+                        # the root unit is active: several moving leaves may meet the same target leaf, the double is
+                        # the child index of the moving leaf of this factor
+                        run.rng.di = run._moving_child_of_pair(args[0])
                 elif _kind == EVENT_BENDING:
                     run.rng.set_context(run.events, make_slot(SLOT_BENDING_TIME))
                 elif _kind == EVENT_CELL_VETO:
@@ -294,6 +313,8 @@ class ReferenceRun:
                 if _kind in (EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDING, EVENT_BENDING):
                     # confirmation, then the draws of the lifting scheme, in call order
                     run.rng.set_context(run.events, make_slot(SLOT_CONFIRM))
+                elif _kind == EVENT_SWITCH:
+                    run.rng.set_context(run.events, None, make_slot(SLOT_SWITCH))
                 else:
                     run.rng.clear_context()
                 try:
@@ -338,9 +359,14 @@ class ReferenceRun:
 
     def _active(self):
         sh = self.mediator._state_handler
-        ids = sorted(sh._lifting_state._lifting_dictionary.keys(), key=len)
-        assert len(ids) == self.setting.number_of_node_levels  # the active leaf and its ancestors
-        leaf = ids[-1]
+        ids = sorted(sh._lifting_state._lifting_dictionary.keys(), key=lambda i: (len(i), i))
+        leaves = [i for i in ids if len(i) == self.setting.number_of_node_levels]
+        # the active leaf and its ancestors -- or, with the root unit active, the root and all of its leaves (the first
+        # leaf then stands for the object)
+        self.mode = int(len(leaves) > 1)
+        assert len(ids) == self.setting.number_of_node_levels or \
+            len(leaves) == self.setting.number_of_nodes_per_root_node
+        leaf = leaves[0]
         velocity, stamp = sh._lifting_state.get(leaf)
         pos = sh._physical_state.get(leaf).value.position
         direction = [i for i, v in enumerate(velocity) if v != 0.0][0]
@@ -366,12 +392,14 @@ class ReferenceRun:
             if t is not None and "Sampling" in name:
                 self.host_times.append((self.events, t.quotient, t.remainder))
             return
-        n_interaction = sum(1 for _, h in pushed if self._kind_of(h) not in (HOST_EVENT, EVENT_END_OF_CHAIN))
+        n_interaction = sum(1 for _, h in pushed
+                            if self._kind_of(h) not in (HOST_EVENT, EVENT_END_OF_CHAIN, EVENT_SWITCH))
         rec = np.zeros((), dtype=RECORD_DTYPE)
         rec["kind"] = kind
         rec["target"] = -1
         rec["target_cell"] = -1
-        rec["n_candidates"] = n_interaction + 1
+        # + the end of chain (+ the switcher of a program with a root-unit-active mode): persistent candidates
+        rec["n_candidates"] = n_interaction + 1 + int(self._has_switcher())
         rec["time_q"] = winner._event_time.quotient
         rec["time_r"] = winner._event_time.remainder
         old_active = self._active()[0] if kind != EVENT_END_OF_CHAIN or self.events >= 0 else -1
@@ -391,7 +419,10 @@ class ReferenceRun:
             occ = self.mediator._activator.get_info_internal_state(winner, cell)
             rec["target"] = occ[0][0] if occ else -1
         elif kind == EVENT_END_OF_CHAIN:
-            rec["target"] = self.leaf_id(self.mediator._out_state_arguments[winner][0][0])
+            identifier = self.mediator._out_state_arguments[winner][0][0]
+            if len(identifier) < self.setting.number_of_node_levels:  # a root unit takes over: its first leaf
+                identifier = tuple(identifier) + (0,)
+            rec["target"] = self.leaf_id(identifier)
         self._current = (rec, old_active, kind)
         self.iterations.append((name, float(rec["time_q"] + rec["time_r"])))
 
@@ -403,7 +434,8 @@ class ReferenceRun:
         pos = sh._physical_state.get(self._identifier_of(old_active)).value.position
         rec["new_active"] = new_active
         rec["new_direction"] = direction
-        rec["accepted"] = int(new_active != old_active or kind == EVENT_END_OF_CHAIN)
+        rec["accepted"] = int(new_active != old_active or kind in (EVENT_END_OF_CHAIN, EVENT_SWITCH))
+        rec["reserved"] = self.mode  # 1: the root unit is active after the event
         if kind == EVENT_CELL_BOUNDARY:
             cells = self._cells()
             cell_level = self.mediator._activator._internal_states[0].cell_level
@@ -413,6 +445,11 @@ class ReferenceRun:
             rec["active_pos"][d] = pos[d]
         self.records.append(rec.copy())
         self.events += 1
+
+    def _has_switcher(self):
+        if getattr(self, "_switcher", None) is None:
+            self._switcher = any(self._kind_of(h) == EVENT_SWITCH for h in self.mediator._activator.get_event_handlers())
+        return self._switcher
 
     def _identifier_of(self, leaf):
         if self.setting.number_of_node_levels == 1:
@@ -500,7 +537,7 @@ class ReferenceRun:
         self.snapshots.append({"event": self.events, "positions": self.positions(), "roots": self.roots(),
                                "occupants": occ,
                                "surplus": surplus, "active": active, "direction": direction,
-                               "time_q": stamp.quotient, "time_r": stamp.remainder,
+                               "time_q": stamp.quotient, "time_r": stamp.remainder, "mode": self.mode,
                                "velocities": self.velocities()})
 
     def velocities(self):

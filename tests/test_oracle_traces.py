@@ -185,6 +185,44 @@ def test_no_cells_composite_chain_replay_bit_exact(oracle, name):
     assert chain.stats()["capacity_errors"] == 0
 
 
+def test_root_unit_active_mode_replay_bit_exact(oracle):
+    """The shipped dipoles/dipole_motion.ini (three dipoles): which unit is active after every event -- the root unit of
+    an object or one of its leaves (RootLeafUnitActiveSwitcher) -- and, with the shipped sampling events in between,
+    the candidates of the root-unit-active handlers that survive a host control event (their out-states time-slice a
+    fresh copy of the objects, the confirmation uses the leaf units of the in-state)."""
+    g = tu.load_trace("trace_dipole_motion")
+    chain = oracle.OracleChain(tu.dipole_motion_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    n, rec = chain.run(max_events=len(g["records"]), record=len(g["records"]))
+    assert np.array_equal(rec["mode"], g["records"]["reserved"])
+    assert (g["records"]["kind"] == 9).sum() > 100 and 0.3 < g["records"]["reserved"].mean() < 0.7
+    root = g["records"]["reserved"][:-1] == 1  # events that start with a root unit active
+    assert ((g["records"]["kind"][1:] == 1) & root).sum() > 500 and ((g["records"]["kind"][1:] == 7) & root).sum() > 50
+
+    g = tu.load_trace("trace_dipole_motion_sampling")
+    records, host = g["records"], g["host_times"]
+    chain = oracle.OracleChain(tu.dipole_motion_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    parts, done = [], 0
+    assert len(host) > 100
+    for events_before, q, r in host:
+        n, rec = chain.run(until=(q, r), record=10000)
+        parts.append(rec)
+        done += n
+        assert done == int(events_before)
+    n, rec = chain.run(max_events=len(records) - done, record=10000)
+    parts.append(rec)
+    ours = np.concatenate(parts)
+    assert tu.records_equal_discrete(ours, records) and np.array_equal(ours["mode"], records["reserved"])
+    assert np.array_equal(ours["time_q"], records["time_q"]) and np.array_equal(ours["time_r"], records["time_r"])
+    assert np.array_equal(ours["active_pos"], records["active_pos"])
+    assert np.array_equal(chain.positions(), g["final_positions"]) and np.array_equal(chain.roots(), g["final_roots"])
+
+
 @pytest.mark.parametrize("name", tu.DIPOLE_TRACES)
 def test_composite_chain_replay_bit_exact(oracle, name):
     """C1, the shipped hard_disk_dipoles_cells.ini from the shipped start configuration: composite point objects

@@ -78,6 +78,14 @@ def dipole_factors_builder_of(g, builder_cls):
     return pb
 
 
+def dipole_motion_builder_of(g, builder_cls):
+    """The shipped dipoles/dipole_motion.ini: the factors of dipole_factors_inside_first.ini while a leaf unit is active,
+    the root-unit-active handlers with the same potentials while a root unit is, RootLeafUnitActiveSwitcher in between."""
+    pb = dipole_factors_builder_of(g, builder_cls)
+    pb.set_root_mode(*[float(x) for x in g["meta_switch_chain_length"]])
+    return pb
+
+
 def dipole_cell_bounded_builder_of(g, builder_cls):
     """The shipped dipoles/cell_bounded.ini: composite-object Coulomb handlers for nearby cells and the surplus, the
     composite-object cell-bounding handler for all other occupied cells (bounds as the reference's estimator built
@@ -134,6 +142,7 @@ NO_CELL_MOLECULE_TRACES = {"trace_dipole_factors_inside_first": dipole_factors_b
                            "trace_dipole_factors_outside_first": dipole_factors_builder_of,
                            "trace_dipole_factors_ratio": dipole_factors_builder_of,
                            "trace_dipole_atom_factors": dipole_factors_builder_of,
+                           "trace_dipole_motion": dipole_motion_builder_of,
                            "trace_water_atomic_factors": water_atomic_builder_of,
                            "trace_water_single_molecule": single_molecule_builder_of}
 
