@@ -195,6 +195,9 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
     # ---- handlers by kind
     pair_handlers, veto_handlers, boundary_handlers, eoc_handlers, start_handlers, control = [], [], [], [], [], []
     bounding_handlers, bond_handlers, bending_handlers, leaf_pair_handlers = [], [], [], []
+    # root-unit-active mode (dipoles/dipole_motion.ini): the handlers that run while the ROOT unit of an object is the
+    # independent active unit, and the RootLeafUnitActiveSwitcher handlers that alternate between the two modes
+    root_pair_handlers, root_factor_handlers, switchers = [], [], []
     # handlers fed by a factor type map are intramolecular factors (factor_type_map_in_state_tagger.py:83-107)
     factor_tagger_of = {}
     for tagger in activator._taggers:
@@ -203,7 +206,13 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                 factor_tagger_of[id(handler)] = tagger
     for handler in activator.get_event_handlers():
         names = _class_names(handler)
-        if id(handler) in factor_tagger_of and levels == 1:
+        if "RootUnitActiveTwoCompositeObjectSummedBoundingPotentialEventHandler" in names:
+            root_pair_handlers.append(handler)
+        elif "RootUnitActiveTwoLeafUnitEventHandler" in names:
+            root_factor_handlers.append(handler)
+        elif "RootLeafUnitActiveSwitcher" in names:
+            switchers.append(handler)
+        elif id(handler) in factor_tagger_of and levels == 1:
             # point masses: the factor type map lists the pair factors themselves ("[0, 1], Coulomb" = the active
             # atom with every other atom, factor_type_maps.py:333-347)
             factor_map = factor_tagger_of[id(handler)]._factor_type_map
@@ -499,6 +508,54 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                               boundary_keeps_factors=keeps_factors)
     elif veto_handlers and "CompositeObjectCellVetoEventHandler" in _class_names(veto_handlers[0]):
         raise _configuration_error("the composite-object cell-veto handler needs root-level cells")
+    # ---- root-unit-active mode: the same factors with the root unit of an object active, and the switchers
+    if root_pair_handlers or root_factor_handlers or switchers:
+        # root_leaf_unit_active_switcher.py:59-100 (aim modes), :102-127 (chain length)
+        aims = sorted(switcher._aim_mode.name for switcher in switchers)
+        if not (no_cells and molecules and nodes_per_root == 2 and aims == ["leaf_unit_active", "root_unit_active"]):
+            raise _configuration_error("the root-unit-active mode needs composite objects of two leaves without a cell "
+                                       "system and one RootLeafUnitActiveSwitcher per aim mode")
+        leaf_pair = [h for h in pair_handlers if "TwoCompositeObjectSummedBoundingPotentialEventHandler" in _class_names(h)]
+        if not leaf_pair or not root_pair_handlers or bending_handlers or leaf_pair_handlers:
+            raise _configuration_error("the root-unit-active mode needs the composite-object pair handler in both modes")
+        first = leaf_pair[0]
+        for handler in root_pair_handlers:
+            # root_unit_active_two_composite_object_summed_bounding_potential_event_handler.py:66-114
+            factor_map = factor_tagger_of[id(handler)]._factor_type_map
+            entries = {tuple(indices) for lists in factor_map.map.values() for indices in lists}
+            if entries != {tuple(range(2 * nodes_per_root))} or \
+                    not _same_potential(potential_descriptor(first._potential), potential_descriptor(handler._potential)) or \
+                    not _same_potential(potential_descriptor(first._bounding_potential),
+                                        potential_descriptor(handler._bounding_potential)) or \
+                    _charge_name(handler._potential_charges) != _charge_name(first._potential_charges) or \
+                    _charge_name(handler._bounding_potential_charges) != _charge_name(first._potential_charges):
+                raise _configuration_error("the root-unit-active composite-object handler must use the factor, the "
+                                           "potentials and the charge of the leaf-unit-active one")
+        root_factors = []
+        for handler in root_factor_handlers:
+            factor_map = factor_tagger_of[id(handler)]._factor_type_map
+            if _charge_name(handler._charges) is not None or inter_potential is None or getattr(factor_map, "_local", True) or \
+                    not _same_potential(inter_potential, potential_descriptor(handler._potential)):
+                raise _configuration_error("the root-unit-active two-leaf handlers must use the potential of the "
+                                           "leaf-unit-active factors between the objects")
+            for child, entries in factor_map.map.items():
+                for indices in entries:
+                    other = [index for index in indices if index >= nodes_per_root]
+                    own = [index for index in indices if index < nodes_per_root]
+                    if len(indices) != 2 or len(other) != 1 or own != [child]:
+                        raise _configuration_error("unsupported factor between composite objects: {0}".format(indices))
+                    root_factors.append((child, other[0] - nodes_per_root))
+        if sorted(set(root_factors)) != sorted(inter_factors):
+            raise _configuration_error("the root-unit-active two-leaf handlers must cover the factors between the objects "
+                                       "of the leaf-unit-active mode")
+        # the run starts with a leaf unit active: the start-of-run tagger activates the switcher that aims at the root unit
+        tagger_of = {id(handler): tagger for tagger in activator._taggers for handler in tagger.get_event_handlers()}
+        to_root = [switcher for switcher in switchers if switcher._aim_mode.name == "root_unit_active"][0]
+        to_leaf = [switcher for switcher in switchers if switcher._aim_mode.name == "leaf_unit_active"][0]
+        start_tagger = tagger_of[id(start)]
+        if tagger_of[id(to_root)].tag not in start_tagger.activates or tagger_of[id(to_leaf)].tag in start_tagger.activates:
+            raise _configuration_error("the run must start with the leaf-to-root switcher activated")
+        builder.set_root_mode(to_root._chain_length, to_leaf._chain_length)
     if len(charge_names) > 1:
         raise _configuration_error("pair and cell-veto handlers use different charges: {0}".format(sorted(charge_names)))
     return CompiledProgram(builder, charge_names.pop() if charge_names else None, control, n_particles, nodes_per_root)

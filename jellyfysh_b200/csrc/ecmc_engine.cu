@@ -382,6 +382,18 @@ int build_device_program(EcmcHandle *h) {
         }
         m.bending_enabled = p.bending_enabled ? 1 : 0;
         m.boundary_keeps_factors = p.boundary_keeps_factors ? 1 : 0;
+        // root-unit-active mode (dipoles/dipole_motion.ini)
+        m.root_mode = p.root_mode ? 1 : 0;
+        if (p.root_mode) {
+            if (d.nodes_per_root != 2 || !p.no_cells || p.bending_enabled || p.veto_enabled != ECMC_FAR_NONE ||
+                p.pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING)
+                return fail(h, ECMC_ERR_INVALID, "the root-unit-active mode needs objects of two leaves with the composite-object "
+                                                 "pair handler and no cell system");
+            if (!(p.switch_chain_length[0] > 0.0) || !(p.switch_chain_length[1] > 0.0))
+                return fail(h, ECMC_ERR_INVALID, "switch_chain_length must be > 0");
+            m.switch_length[0] = p.switch_chain_length[0];
+            m.switch_length[1] = p.switch_chain_length[1];
+        }
         if (p.bending_enabled) {
             if (p.bending_potential.kind != ECMC_POT_BENDING || d.nodes_per_root != 3 || !(p.bending_max_displacement > 0.0) ||
                 p.bending_lifting < ECMC_LIFTING_INSIDE_FIRST || p.bending_lifting > ECMC_LIFTING_RATIO)
@@ -715,7 +727,10 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         constexpr int kAlignedWarps = ECMC_ALIGNED_WARPS;
         bool aligned = true;
         if (const char *env = std::getenv("ECMC_MOLECULE_ALIGNED")) aligned = std::atoi(env) != 0;
-        if (water && aligned)
+        if (h->mprog.root_mode)
+            kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kMoleculeWarps, false, true>
+                               : molecule_kernel<-1, -1, -1, -1, false, kMoleculeWarps, false, true>;
+        else if (water && aligned)
             kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kAlignedWarps, true>
                                : molecule_kernel<IPCB, MIC, DEP, LJ, false, kAlignedWarps, true>;
         else if (water)
@@ -724,7 +739,7 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         else
             kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kMoleculeWarps, false>
                                : molecule_kernel<-1, -1, -1, -1, false, kMoleculeWarps, false>;
-        const int warps = water && aligned ? kAlignedWarps : kMoleculeWarps;
+        const int warps = water && aligned && !h->mprog.root_mode ? kAlignedWarps : kMoleculeWarps;
         kernel<<<(h->n_chains + warps - 1) / warps, warps * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
     } else {
         SpecLaunch spec;
@@ -928,7 +943,7 @@ ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_s
     if (h->molecules)
         molecule_start_kernel<kMoleculeWarps><<<(h->n_chains + kMoleculeWarps - 1) / kMoleculeWarps, kMoleculeWarps * 32, 0, h->stream>>>(
             h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
-            h->program.initial_direction, h->d_stats);
+            h->program.initial_direction, h->d_stats, h->mprog.root_mode ? h->mprog.switch_length[0] : 0.0);
     else
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
             h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
@@ -955,6 +970,9 @@ ECMC_API int ecmc_upload_chain_states(EcmcHandle *h, const EcmcChainState *state
             (s.pending_kind != ECMC_EVENT_NONE && (s.pending_target < -1 || s.pending_target >= index_limit)) ||
             s.kept_kind < -1 || s.kept_kind > 16 || (s.kept_kind > 0 && (s.kept_target < -1 || s.kept_target >= index_limit)))
             return fail(h, ECMC_ERR_INVALID, "chain state " + std::to_string(c) + ": kept candidate out of range");
+        // root-unit-active mode: `active` is the first leaf of the object whose root unit is active
+        if (s.mode != 0 && (s.mode != 1 || !h->mprog.root_mode || s.active % 2 != 0 || s.eoc_next_active % 2 != 0))
+            return fail(h, ECMC_ERR_INVALID, "chain state " + std::to_string(c) + ": mode out of range");
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaMemcpyAsync(h->state.chains, states, sizeof(EcmcChainState) * h->n_chains, cudaMemcpyHostToDevice, h->stream));
@@ -1424,7 +1442,8 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
     if (h->disks) {
         h->kernel_name = "disk_kernel<record=" + std::to_string(record != 0) + ">";
     } else if (h->molecules) {
-        h->kernel_name = "molecule_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto + ", record=" + std::to_string(record != 0) + ">";
+        h->kernel_name = "molecule_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto + ", record=" + std::to_string(record != 0) +
+                         (h->mprog.root_mode ? ", root mode>" : ">");
     } else if (pick_spec(h, record != 0, &spec) && spec.chain_blocks) {
         h->kernel_name = "lj_chain_kernel<record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", warps per chain=" + std::to_string(kChainWarps) + ">";

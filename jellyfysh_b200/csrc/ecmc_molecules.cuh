@@ -29,6 +29,9 @@ struct MoleculeProgram {
     int boundary_keeps_factors;
     double bending_prefactor, bending_angle, bending_offset, bending_max_displacement;
     PotentialParams inter_potential;
+    // EcmcProgram.root_mode: chain lengths of the leaf-to-root and of the root-to-leaf RootLeafUnitActiveSwitcher
+    int root_mode, pad;
+    double switch_length[2];
 };
 
 constexpr int kItemCapacity = 192;  // work items per chunk (two ints each: 1.5 KB per warp)
@@ -159,10 +162,16 @@ ECMC_D double pair_derivative_lab(const PotentialParams &p, int dir, double spee
 // ALIGNED: the warps of a CTA meet at a barrier before every event. The kernel is bound by instruction fetch (thousands
 // of instructions per event, a handful of warps per SM, each somewhere else in the code); warps that walk through the
 // event together fetch every instruction once for all of them.
-template <int CAND, int REAL, int BOND, int INTER, bool RECORD, int WARPS, bool ALIGNED>
+// ROOT_MODE: the program has the root-unit-active mode of dipoles/dipole_motion.ini (EcmcProgram.root_mode: objects of two
+// leaves, no cell system). While EcmcChainState.mode is 1 the ROOT unit of the object of `active` (its first leaf) is the
+// independent active unit: root and both leaves move with the full velocity, the candidates are those of the
+// root-unit-active handlers (see include/ecmc.h), and RootLeafUnitActiveSwitcher events alternate between the two modes.
+// Compile-time, so that the other instantiations carry none of it.
+template <int CAND, int REAL, int BOND, int INTER, bool RECORD, int WARPS, bool ALIGNED, bool ROOT_MODE = false>
 __global__ void __launch_bounds__(WARPS * 32)
 molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ MoleculeProgram M, const DeviceState S,
                 const RunArgs A) {
+    static_assert(!(ROOT_MODE && ALIGNED), "the root-unit-active mode runs without the per-event CTA barrier");
     __shared__ double trig_all[WARPS * kTrigDoubles];
     __shared__ int items_all[WARPS * 2 * kItemCapacity];
     const int lane = threadIdx.x & 31;
@@ -202,6 +211,18 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
     Vec3 apos = lab_position(part[active]);     // the active leaf
     double acharge = part[active].charge;
     Vec3 rpos = lab_position(roots[active / npr]);  // its root unit
+    // root-unit-active mode: which unit is active, the running switcher, the last end of chain, and -- while the root unit
+    // is active -- the second leaf of its object (apos is the first one)
+    int mode = ROOT_MODE ? stp->mode : 0;
+    Time sw = {ROOT_MODE ? stp->switch_q : 0.0, ROOT_MODE ? stp->switch_r : 0.0};
+    Time eoc_last = {ROOT_MODE ? stp->eoc_last_q : 0.0, ROOT_MODE ? stp->eoc_last_r : 0.0};
+    Vec3 bpos = apos;
+    double bcharge = acharge;
+    if (ROOT_MODE && mode == 1) {
+        const Particle second = part[active + 1];
+        bpos = lab_position(second);
+        bcharge = second.charge;
+    }
     int cid0 = (active_cell / P.cumulative[0]) % P.per_side[0];
     int cid1 = (active_cell / P.cumulative[1]) % P.per_side[1];
     int cid2 = (active_cell / P.cumulative[2]) % P.per_side[2];
@@ -229,6 +250,231 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             break;
         }
         const StreamKey key = {P.seed, stream, ev};
+        if (ROOT_MODE && mode == 1) {
+            // ---- one event with the root unit of object `active / 2` as the independent active unit
+            const int active_root = active / npr;
+            Time bt = time_inf();
+            int bkind = ECMC_EVENT_NONE, btarget = -1, n_cand = 0;
+            // the leaf units as the handler that fires saw them in send_event_time (the confirmation of the
+            // summed-bounding handler uses those; every out-state time-slices a fresh copy of the objects)
+            Vec3 ia = apos, ib = bpos;
+            Time in_stamp = now;
+            if (was_pending) {
+                bkind = stp->pending_kind;
+                bt.q = stp->pending_q; bt.r = stp->pending_r;
+                btarget = stp->pending_target;
+                set_dir(ia, stp->pending_position);
+                set_dir(ib, stp->pending_position_y);
+                in_stamp.q = stp->pending_stamp_q; in_stamp.r = stp->pending_stamp_r;
+            } else {
+                // eight lanes per other object: (local leaf i, target leaf j) of the composite-object handler
+                // (root_unit_active_two_composite_object_summed_bounding_potential_event_handler.py:116-152, its minimum
+                // over the four pairs is part of the warp argmin), then the inter-object factors (a, b) of
+                // RootUnitActiveTwoLeafUnitEventHandler (two_leaf_unit_event_handler.py:105-138 for the moving leaf a)
+                const int n_items = (n_roots - 1) * 8;
+                unsigned long long best_key = 0x7ff0000000000000ull;
+                double best_x = INFINITY;
+                int best_seq = kSeqNone;
+                for (int base = 0; base < n_items; base += 32) {
+                    const int item = base + lane;
+                    const int object = item >> 3, within = item & 7;
+                    const int t = object < active_root ? object : object + 1;
+                    double dt = INFINITY;
+                    int kind = ECMC_EVENT_NONE, target = -1;
+                    if (item < n_items && (within < 4 || within - 4 < M.n_inter)) {
+                        const int local = within < 4 ? within >> 1 : M.inter[within - 4][0];
+                        const int leaf = t * npr + (within < 4 ? within & 1 : M.inter[within - 4][1]);
+                        const Particle tp = part[leaf];
+                        const Vec3 s3 = separation_lab(local == 0 ? apos : bpos, lab_position(tp), L, half);
+                        const double s0 = vcomp(s3, dir);
+                        const double s1 = dir == 0 ? s3.y : (dir == 1 ? s3.z : s3.x);
+                        const double s2 = dir == 0 ? s3.z : (dir == 1 ? s3.x : s3.y);
+                        if (within < 4) {
+                            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_PAIR_TIME, t), (uint32_t)within);
+                            const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                            const double c1 = P.pair_use_charge ? (local == 0 ? acharge : bcharge) : 1.0;
+                            const double c2 = P.pair_use_charge ? tp.charge : 1.0;
+                            dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c1, c2, du);
+                            kind = ECMC_EVENT_PAIR; target = t;
+                        } else {
+                            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, leaf), (uint32_t)local);
+                            const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                            dt = displacement_time<INTER>(M.inter_potential, 0, P.inv_speed, L, s0, s1, s2, 1.0, 1.0,
+                                                          needs_potential_change(resolve_kind<INTER>(M.inter_potential.kind)) ? du : 0.0);
+                            kind = ECMC_EVENT_FACTOR_PAIR; target = leaf;
+                        }
+                    }
+                    const double x = now.r + dt;
+                    const bool finite = kind != ECMC_EVENT_NONE && x < INFINITY;
+                    // one candidate per handler: an object whose composite pair has a finite time, every finite factor
+                    const unsigned pair_mask = __ballot_sync(kFull, finite && within < 4);
+                    for (int g = 0; g < 4; g++) n_cand += ((pair_mask >> (8 * g)) & 0xFu) != 0u;
+                    n_cand += __popc(__ballot_sync(kFull, finite && within >= 4));
+                    const unsigned long long k64 = finite ? time_key(x) : 0x7ff0000000000000ull;
+                    const int owner = warp_argmin(k64, finite ? item : kSeqNone, lane);
+                    const unsigned long long pass_key = __shfl_sync(kFull, k64, owner);
+                    const int pass_seq = __shfl_sync(kFull, finite ? item : kSeqNone, owner);
+                    if (pass_key < best_key || (pass_key == best_key && pass_seq < best_seq)) {
+                        best_key = pass_key; best_seq = pass_seq;
+                        best_x = __shfl_sync(kFull, x, owner);
+                        bkind = __shfl_sync(kFull, kind, owner);
+                        btarget = __shfl_sync(kFull, target, owner);
+                    }
+                }
+                n_targets += (unsigned long long)(n_roots - 1);
+                if (best_seq != kSeqNone) {
+                    const double fl = floor(best_x);
+                    bt.q = now.q + fl; bt.r = best_x - fl;
+                } else {
+                    bkind = ECMC_EVENT_NONE;
+                }
+            }
+            n_cand += 2;  // the end of chain and the root-to-leaf switcher, both in the scheduler all along
+            Time event_time = bt;
+            int kind = bkind;
+            if (time_lt(eoc, event_time)) { event_time = eoc; kind = ECMC_EVENT_END_OF_CHAIN; }
+            if (time_lt(sw, event_time)) { event_time = sw; kind = ECMC_EVENT_SWITCH; }
+            if (!time_lt(event_time, until)) {
+                if (lane == 0) {
+                    stp->pending_kind = bkind;
+                    stp->pending_q = bt.q; stp->pending_r = bt.r;
+                    stp->pending_rate = 0.0;
+                    stp->pending_target = btarget;
+                    if (!was_pending) {
+                        stp->pending_position = vcomp(apos, dir);
+                        stp->pending_position_y = vcomp(bpos, dir);
+                        stp->pending_root_position = vcomp(rpos, dir);
+                        stp->pending_stamp_q = now.q; stp->pending_stamp_r = now.r;
+                    }
+                }
+                stopped_by_time = true;
+                break;
+            }
+            if (was_pending && lane == 0) stp->pending_kind = ECMC_EVENT_NONE;
+            was_pending = false;
+            {
+                // time slice of the root unit and of both leaves, each with the full velocity (abstracts.py:89-107)
+                const double step = __dmul_rn(speed, time_sub(event_time, now));
+                set_dir(apos, correct_position_entry(__dadd_rn(vcomp(apos, dir), step), L));
+                set_dir(bpos, correct_position_entry(__dadd_rn(vcomp(bpos, dir), step), L));
+                set_dir(rpos, correct_position_entry(__dadd_rn(vcomp(rpos, dir), step), L));
+                now = event_time;
+            }
+            int new_active = active, rec_target = -1;
+            switch (kind) {
+            case ECMC_EVENT_PAIR: {
+                // send_out_state (:154-190): summed derivatives over the four pairs of leaves, in the handler's order
+                rec_target = btarget;
+                n_pair++;
+                const double step = __dmul_rn(speed, time_sub(event_time, in_stamp));
+                set_dir(ia, correct_position_entry(__dadd_rn(vcomp(ia, dir), step), L));
+                set_dir(ib, correct_position_entry(__dadd_rn(vcomp(ib, dir), step), L));
+                double bounding_rate = 0.0, factor_derivative = 0.0;
+                for (int i = 0; i < 2; i++)
+                    for (int j = 0; j < 2; j++) {
+                        const Particle tp = part[btarget * npr + j];
+                        const double c1 = P.pair_use_charge ? (i == 0 ? acharge : bcharge) : 1.0;
+                        const double c2 = P.pair_use_charge ? tp.charge : 1.0;
+                        const Vec3 from = i == 0 ? ia : ib, to = lab_position(tp);
+                        const double b = pair_derivative_lab<CAND>(P.cand_potential, dir, speed, from, to, c1, c2, L, half, trig, lane);
+                        bounding_rate += b > 0.0 ? b : 0.0;
+                        factor_derivative += pair_derivative_lab<REAL>(P.real_potential, dir, speed, from, to, c1, c2, L, half,
+                                                                       trig, lane);
+                    }
+                if (factor_derivative > 0.0) {
+                    if (bounding_rate < factor_derivative) count_rare(A, lane, 7);
+                    const double u = confirm_draw(key.seed, key.stream, key.event, 0);
+                    if (0.0 + (bounding_rate - 0.0) * u < factor_derivative) new_active = btarget * npr;
+                }
+                break;
+            }
+            case ECMC_EVENT_FACTOR_PAIR:
+                // RootUnitActiveTwoLeafUnitEventHandler.send_out_state (:102-125): the object of the target leaf takes over
+                rec_target = btarget;
+                new_active = (btarget / npr) * npr;
+                n_factor++;
+                break;
+            case ECMC_EVENT_END_OF_CHAIN:
+                new_active = eoc_next;
+                rec_target = eoc_next;
+                eoc_last = event_time;
+                n_eoc++;
+                break;
+            case ECMC_EVENT_SWITCH:
+                // _send_out_state_leaf_unit_active (root_leaf_unit_active_switcher.py:129-169): random.choice over the leaves
+                new_active = active + (int)stream_randbelow(key, ECMC_SLOT(ECMC_SLOT_SWITCH, 0), (uint32_t)npr);
+                break;
+            default: break;
+            }
+            const int new_mode = kind == ECMC_EVENT_SWITCH ? 0 : 1;
+            if (RECORD && lane == 0 && (int)n_events < A.records_per_chain) {
+                EcmcEventRecord rec;
+                rec.kind = kind; rec.target = rec_target; rec.target_cell = -1;
+                rec.accepted = (kind == ECMC_EVENT_END_OF_CHAIN || kind == ECMC_EVENT_SWITCH) ? 1 : (new_active != active);
+                rec.n_candidates = n_cand;
+                rec.new_active = new_active;
+                rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % P.dimension : dir;
+                rec.mode = new_mode;
+                rec.time_q = event_time.q; rec.time_r = event_time.r;
+                rec.active_pos[0] = apos.x; rec.active_pos[1] = apos.y; rec.active_pos[2] = apos.z;
+                A.records[(size_t)chain * A.records_per_chain + n_events] = rec;
+            }
+            ev++;
+            n_events++;
+            n_candidates += (unsigned long long)n_cand;
+            if (kind == ECMC_EVENT_END_OF_CHAIN) dir = dir + 1 == P.dimension ? 0 : dir + 1;
+            // commit the object, hand over
+            const int new_root = new_active / npr;
+            int delta = 0;
+            if (lane == 0) {
+                Particle p = part[active];
+                p.x = apos.x; p.y = apos.y; p.z = apos.z;
+                part[active] = p;
+                p = part[active + 1];
+                p.x = bpos.x; p.y = bpos.y; p.z = bpos.z;
+                part[active + 1] = p;
+                Particle r = roots[active_root];
+                r.x = rpos.x; r.y = rpos.y; r.z = rpos.z;
+                roots[active_root] = r;
+                if (new_root != active_root) delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, active_cell, active_root);
+            }
+            delta = __shfl_sync(kFull, delta, 0);
+            if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+            __syncwarp();
+            if (new_root != active_root) {
+                rpos = lab_position(roots[new_root]);
+                cid0 = (int)(rpos.x / P.side_length[0]);
+                cid1 = (int)(rpos.y / P.side_length[1]);
+                cid2 = (int)(rpos.z / P.side_length[2]);
+                active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
+                delta = 0;
+                if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, 1, active_cell, new_root);
+                delta = __shfl_sync(kFull, delta, 0);
+                if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+                __syncwarp();
+            }
+            active = new_active;
+            mode = new_mode;
+            {
+                const Particle first = part[active];
+                apos = lab_position(first);
+                acharge = first.charge;
+                if (mode == 1) {
+                    const Particle second = part[active + 1];
+                    bpos = lab_position(second);
+                    bcharge = second.charge;
+                }
+            }
+            if (kind == ECMC_EVENT_SWITCH) sw = time_add(event_time, M.switch_length[0]);
+            if (kind == ECMC_EVENT_END_OF_CHAIN || kind == ECMC_EVENT_SWITCH) {
+                // re-created by the switcher as well: (_last_committed_event_time - time stamp) + chain_time (:203-215)
+                eoc = time_add(now, time_sub(eoc_last, now) + P.chain_time);
+                const StreamKey next_key = {P.seed, stream, ev};
+                eoc_next = mode == 1 ? (int)stream_randbelow(next_key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)n_roots) * npr
+                                     : draw_end_of_chain_active(P, next_key);
+            }
+            continue;
+        }
         const int active_root = active / npr, active_child = active - active_root * npr;
         Time bt = time_inf();
         int bkind = ECMC_EVENT_NONE, btarget = -1, bcell = -1;
@@ -529,8 +775,13 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
 
         n_cand++;
         const bool eoc_first = time_lt(eoc, bt);
-        const Time event_time = eoc_first ? eoc : bt;
-        const int kind = eoc_first ? ECMC_EVENT_END_OF_CHAIN : bkind;
+        Time event_time = eoc_first ? eoc : bt;
+        int kind = eoc_first ? ECMC_EVENT_END_OF_CHAIN : bkind;
+        if (ROOT_MODE) {
+            // the leaf-to-root RootLeafUnitActiveSwitcher, in the scheduler since the last switch
+            n_cand++;
+            if (time_lt(sw, event_time)) { event_time = sw; kind = ECMC_EVENT_SWITCH; }
+        }
         if (!time_lt(event_time, until)) {
             if (lane == 0) {
                 stp->pending_kind = bkind;
@@ -555,7 +806,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             restore = true;
             restore_pos = kept_pos; restore_root = kept_root; restore_stamp = kept_stamp;
         }
-        if (restore && kind != ECMC_EVENT_END_OF_CHAIN) {
+        if (restore && kind != ECMC_EVENT_END_OF_CHAIN && !(ROOT_MODE && kind == ECMC_EVENT_SWITCH)) {
             set_dir(apos, restore_pos);
             set_dir(rpos, restore_root);
             now = restore_stamp;
@@ -704,19 +955,26 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
         case ECMC_EVENT_END_OF_CHAIN:
             new_active = eoc_next;
             rec_target = new_active;
+            if (ROOT_MODE) eoc_last = event_time;
             n_eoc++;
+            break;
+        case ECMC_EVENT_SWITCH:
+            // _send_out_state_root_unit_active (root_leaf_unit_active_switcher.py:171-208): the root unit takes over, the
+            // other leaf takes the velocity and the time stamp of the active one; `active` becomes the first leaf
+            new_active = active_root * npr;
             break;
         default: break;
         }
+        const bool to_root = ROOT_MODE && kind == ECMC_EVENT_SWITCH;
         if (new_active < 0) { count_rare(A, lane, 8); new_active = active; }
         if (RECORD && lane == 0 && (int)n_events < A.records_per_chain) {
             EcmcEventRecord rec;
-            rec.kind = kind; rec.target = rec_target; rec.target_cell = kind == ECMC_EVENT_END_OF_CHAIN ? -1 : bcell;
-            rec.accepted = kind == ECMC_EVENT_END_OF_CHAIN ? 1 : (new_active != active);
+            rec.kind = kind; rec.target = rec_target; rec.target_cell = (kind == ECMC_EVENT_END_OF_CHAIN || to_root) ? -1 : bcell;
+            rec.accepted = (kind == ECMC_EVENT_END_OF_CHAIN || to_root) ? 1 : (new_active != active);
             rec.n_candidates = n_cand;
             rec.new_active = new_active;
             rec.new_direction = kind == ECMC_EVENT_END_OF_CHAIN ? (dir + 1) % P.dimension : dir;
-            rec.mode = 0;
+            rec.mode = to_root ? 1 : 0;
             rec.time_q = event_time.q; rec.time_r = event_time.r;
             rec.active_pos[0] = apos.x; rec.active_pos[1] = apos.y; rec.active_pos[2] = apos.z;
             A.records[(size_t)chain * A.records_per_chain + n_events] = rec;
@@ -769,23 +1027,46 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
             __syncwarp();
         }
-        if (kind == ECMC_EVENT_END_OF_CHAIN) {
-            eoc = time_add(now, time_sub(now, now) + P.chain_time);
+        if (to_root) {
+            // the root unit is active from here on: the root-to-leaf switcher is created with the root's time stamp
+            mode = 1;
+            sw = time_add(event_time, M.switch_length[1]);
+            const Particle second = part[active + 1];
+            bpos = lab_position(second);
+            bcharge = second.charge;
+        }
+        if (kind == ECMC_EVENT_END_OF_CHAIN || to_root) {
+            // a switcher event re-creates the candidate between two ends of chain: (_last_committed_event_time - time
+            // stamp) + chain_time, single_independent_active_periodic_direction_end_of_chain_event_handler.py:203-215
+            eoc = time_add(now, (ROOT_MODE ? time_sub(eoc_last, now) : time_sub(now, now)) + P.chain_time);
             const StreamKey next_key = {P.seed, stream, ev};
-            eoc_next = draw_end_of_chain_active(P, next_key);
+            eoc_next = to_root ? (int)stream_randbelow(next_key, ECMC_SLOT(ECMC_SLOT_END_OF_CHAIN, 0), (uint32_t)n_roots) * npr
+                               : draw_end_of_chain_active(P, next_key);
         }
     }
 
     if (stopped_by_time) {
         const double dt = time_sub(until, now);
+        const bool whole = ROOT_MODE && mode == 1;  // the root unit is active: root and leaves with the full velocity
         set_dir(apos, correct_position_entry(__dadd_rn(vcomp(apos, dir), __dmul_rn(speed, dt)), L));
-        set_dir(rpos, correct_position_entry(__dadd_rn(vcomp(rpos, dir), __dmul_rn(P.root_speed, dt)), L));
+        if (whole) set_dir(bpos, correct_position_entry(__dadd_rn(vcomp(bpos, dir), __dmul_rn(speed, dt)), L));
+        set_dir(rpos, correct_position_entry(__dadd_rn(vcomp(rpos, dir), __dmul_rn(whole ? speed : P.root_speed, dt)), L));
         now = until;
     }
     if (lane == 0) {
         Particle p = part[active];
         p.x = apos.x; p.y = apos.y; p.z = apos.z;
         part[active] = p;
+        if (ROOT_MODE) {
+            if (mode == 1) {
+                p = part[active + 1];
+                p.x = bpos.x; p.y = bpos.y; p.z = bpos.z;
+                part[active + 1] = p;
+            }
+            stp->mode = mode;
+            stp->switch_q = sw.q; stp->switch_r = sw.r;
+            stp->eoc_last_q = eoc_last.q; stp->eoc_last_r = eoc_last.r;
+        }
         Particle r = roots[active / npr];
         r.x = rpos.x; r.y = rpos.y; r.z = rpos.z;
         roots[active / npr] = r;
@@ -819,7 +1100,8 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams,
-                      uint32_t first_stream, int initial_active, int initial_direction, EcmcStats *stats) {
+                      uint32_t first_stream, int initial_active, int initial_direction, EcmcStats *stats,
+                      double first_switch) {
     const int lane = threadIdx.x & 31;
     const int chain = S.first_chain + blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (chain >= S.first_chain + S.n_chains) return;
@@ -837,7 +1119,7 @@ molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState
             const int delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, flat_cell(P, id), r);
             if (delta == 2) overflow++; else n_surplus += delta;
         }
-        EcmcChainState st;
+        EcmcChainState st = {};  // every field defined: the state is downloaded, compared and checkpointed as bytes
         st.active = initial_active; st.direction = initial_direction;
         st.time_q = 0.0; st.time_r = 0.0;
         st.event_counter = 0;
@@ -857,6 +1139,12 @@ molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState
         st.pending_stamp_q = 0.0; st.pending_stamp_r = 0.0; st.pending_root_position = 0.0;
         st.kept_kind = ECMC_EVENT_NONE; st.kept_target = 0; st.kept_q = 0.0; st.kept_r = 0.0; st.kept_rate = 0.0;
         st.kept_position = 0.0; st.kept_root_position = 0.0; st.kept_stamp_q = 0.0; st.kept_stamp_r = 0.0;
+        if (first_switch > 0.0) {
+            // EcmcProgram.root_mode: the leaf-to-root switcher is created at the start of the run, time stamp of the root
+            // unit + chain length (root_leaf_unit_active_switcher.py:102-127)
+            const Time first = time_add(now, first_switch);
+            st.switch_q = first.q; st.switch_r = first.r;
+        }
         S.chains[chain] = st;
         S.n_surplus[chain] = n_surplus;
         if (overflow && stats) atomicAdd(reinterpret_cast<unsigned long long *>(stats) + 8, (unsigned long long)overflow);

@@ -91,6 +91,12 @@ def fill_tree(cnodes, positions, roots, state, speed, dimension, nodes_per_root,
             root_velocity = [float(v) for v in state["root_velocity"][:dimension]]
         else:
             leaf_velocity, root_velocity = along_direction(speed), along_direction(speed * cnode.children[0].weight)
+        # EcmcChainState.mode = 1 (root-unit-active mode, dipoles/dipole_motion.ini): the root unit of the object is the
+        # independent active unit, it and every one of its leaves move with the full velocity
+        whole_object = int(state["mode"]) == 1 and index == active // npr
+        if whole_object:
+            root_velocity = along_direction(speed)
         fill(cnode.value, roots[index], root_velocity if index == active // npr else None)
         for k, child in enumerate(cnode.children):
-            fill(child.value, positions[index * npr + k], leaf_velocity if index * npr + k == active else None)
+            fill(child.value, positions[index * npr + k],
+                 list(leaf_velocity) if whole_object or index * npr + k == active else None)

@@ -184,6 +184,47 @@ def test_dipole_factors_graph_without_cells_compiles_and_replays(oracle, lifting
         setting.reset()
 
 
+def test_dipole_motion_graph_compiles_and_replays(oracle):
+    """The shipped dipoles/dipole_motion.ini (root-unit-active handlers + RootLeafUnitActiveSwitcher) sized for three
+    dipoles -> compiler -> oracle chain reproduces the reference trace of the same configuration bit for bit."""
+    from jellyfysh.base.exceptions import ConfigurationError
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_dipole_motion")
+    n = int(g["meta_n"]) // 2
+    ini = configs.shipped_without_sampling(
+        REF, ("2018_JCP_149_064113", "dipoles", "dipole_motion.ini"), end_of_run_time=5.0,
+        replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                      ("number_event_handlers = 2", f"number_event_handlers = {2 * (n - 1)}"),
+                      ("number_event_handlers = 1", f"number_event_handlers = {2 * (n - 1)}")])
+    mediator, setting = build_reference_graph(ini, composites=(g["roots0"], g["positions0"].reshape(n, 2, 3)))
+    try:
+        state = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, state, seed=int(g["seed"][0]))
+        p = compiled.builder.program
+        assert p.no_cells == 1 and p.cell_level == 1 and p.nodes_per_root == 2 and p.veto_enabled == 0
+        assert p.pair_handler == abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING and p.pair_use_charge == 1
+        assert p.composite_lifting == abi.LIFTING_INSIDE_FIRST and p.n_bonds == 1 and p.n_inter_factors == 2
+        assert p.root_mode == 1 and (p.switch_chain_length[0], p.switch_chain_length[1]) == (0.69, 0.7)
+        positions, charges, roots = compiler.positions_and_charges(state, compiled.charge_name)
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions, charges)
+        chain.set_roots(roots)
+        chain.start(stream=int(g["seed"][1]))
+        records = g["records"][:2000]
+        n_done, rec = chain.run(max_events=len(records), record=len(records))
+        assert n_done == len(records) and tu.records_equal_discrete(rec, records)
+        assert np.array_equal(rec["mode"], records["reserved"]) and (rec["kind"] == abi.EVENT_SWITCH).sum() > 50
+        assert np.array_equal(rec["time_q"], records["time_q"]) and np.array_equal(rec["time_r"], records["time_r"])
+        # a root-unit-active handler with another potential than the leaf-unit-active one is refused
+        root_handler = [h for h in mediator._activator.get_event_handlers()
+                        if "RootUnitActiveTwoLeafUnitEventHandler" in {c.__name__ for c in type(h).__mro__}][0]
+        root_handler._potential = type(root_handler._potential)(prefactor=2.0e-6, power=6)
+        with pytest.raises(ConfigurationError, match="root-unit-active"):
+            compiler.compile_program(mediator._activator, state, seed=1)
+    finally:
+        setting.reset()
+
+
 def test_atom_factors_graph_compiles_and_replays(oracle):
     """The shipped dipoles/atom_factors.ini (Coulomb as bounded leaf-to-leaf factors between the dipoles, no cell system)
     sized for three dipoles -> compiler -> oracle chain reproduces the reference trace bit for bit."""

@@ -286,6 +286,91 @@ def test_no_cells_composite_reference_trace_replay(oracle, name):
             assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL * max(1.0, length)
 
 
+def test_root_unit_active_mode_reference_trace_replay(oracle):
+    """The shipped dipoles/dipole_motion.ini on the device (molecule_kernel<..., ROOT_MODE>): the independent active unit
+    alternates between a leaf unit and the ROOT unit of a dipole (RootLeafUnitActiveSwitcher,
+    root_leaf_unit_active_switcher.py:102-228; root-unit-active composite-object and two-leaf handlers). Every event of the
+    two reference traces -- without and with the shipped sampling events, which the device meets as time limits with a
+    kept candidate -- in stretches that start from the oracle's state (bit-exact with the reference over both traces);
+    which unit is active after every event (EcmcEventRecord.mode) is compared as well."""
+    g = tu.load_trace("trace_dipole_motion")
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    build = tu.dipole_motion_builder_of
+    stretch = 50
+    chain = oracle.OracleChain(build(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+
+    def resynchronise(eng):
+        eng.upload_positions(chain.positions()[None], tu.charges_of(g)[None])
+        eng.upload_roots(chain.roots()[None])
+        eng.set_chain_states(np.frombuffer(bytes(chain.state()), dtype=abi.chain_state_dtype()))
+        occupants, surplus = chain.cells()
+        eng.set_cells(occupants[None], [surplus])
+
+    with engine.Engine(build(g, ProgramBuilder), n_chains=1) as eng:
+        assert "root mode" in eng.kernel_name()
+        eng.upload_positions(g["positions0"][None], tu.charges_of(g)[None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        st, ref_st = eng.chain_states()[0], chain.state()
+        assert (st["switch_q"], st["switch_r"], st["mode"]) == (ref_st.switch_q, ref_st.switch_r, 0)
+        for done in range(0, len(records), stretch):
+            count = min(stretch, len(records) - done)
+            if done:
+                resynchronise(eng)
+            rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+            assert stats["events"] == count and stats["capacity_errors"] == 0
+            assert_records_match(rec[0], records[done:done + count], length, f"dipole motion[{done}:{done + count}]")
+            assert np.array_equal(rec[0]["mode"], records["reserved"][done:done + count])
+            n, ours = chain.run(max_events=count, record=count)
+            assert n == count and tu.records_equal_discrete(ours, records[done:done + count])
+            assert np.max(np.abs(eng.download_positions()[0] - chain.positions())) < RTOL
+            assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL
+            st, ref_st = eng.chain_states()[0], chain.state()
+            for field in ("mode", "active", "eoc_next_active", "event_counter"):
+                assert int(st[field]) == int(getattr(ref_st, field)), field
+            for field in ("switch_q", "eoc_last_q", "eoc_q"):
+                assert st[field] == getattr(ref_st, field), field
+            for field in ("switch_r", "eoc_last_r", "eoc_r"):
+                assert abs(st[field] - getattr(ref_st, field)) < RTOL, field
+
+    # with sampling events: six time limits per stretch, the candidates that survive them are the device's own
+    g = tu.load_trace("trace_dipole_motion_sampling")
+    records, host = g["records"], g["host_times"]
+    chain = oracle.OracleChain(build(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    kept_in_root_mode = 0
+    with engine.Engine(build(g, ProgramBuilder), n_chains=1) as eng:
+        eng.upload_positions(g["positions0"][None], tu.charges_of(g)[None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        done = 0
+        for k, (events_before, q, r) in enumerate(host):
+            if k and k % 6 == 0:
+                resynchronise(eng)
+            rec, stats = eng.run_recorded(until=(q, r), records_per_chain=200)
+            n, ours = chain.run(until=(q, r), record=200)
+            assert stats["events"] == n and done + n == int(events_before)
+            assert tu.records_equal_discrete(ours, records[done:done + n])
+            if n:
+                assert_records_match(rec[0][:n], records[done:done + n], length, f"dipole motion, sample {k}")
+                assert np.array_equal(rec[0]["mode"][:n], records["reserved"][done:done + n])
+            done += n
+            st, ref_st = eng.chain_states()[0], chain.state()
+            assert (st["time_q"], st["time_r"]) == (q, r)
+            assert (int(st["pending_kind"]), int(st["pending_target"]), int(st["mode"])) == \
+                (ref_st.pending_kind, ref_st.pending_target, ref_st.mode)
+            kept_in_root_mode += int(ref_st.mode == 1 and ref_st.pending_kind == abi.EVENT_PAIR)
+            assert np.max(np.abs(eng.download_positions()[0] - chain.positions())) < RTOL
+            assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL
+    assert len(host) > 100 and kept_in_root_mode > 20
+
+
 def test_sequential_direction_reference_trace_replay(oracle):
     """General velocities on the device (disk_kernel): the shipped hard_disk_dipoles.ini -- no cell system, 160 hard-disk
     candidates and the tether per event, the velocity rotated by 20 degrees at every end of chain

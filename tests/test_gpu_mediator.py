@@ -633,13 +633,15 @@ def _dipole_pair_start(seed, length=1.0):
     ("dipole_factors_outside_first.ini", "SamplesOfSeparation_DipoleFactors_OutsideFirst.dat"),
     ("dipole_factors_ratio.ini", "SamplesOfSeparation_DipoleFactors_Ratio.dat"),
     ("atom_factors.ini", "SamplesOfSeparation_AtomFactors.dat"),
-    ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat")])
+    ("cell_bounded.ini", "SamplesOfSeparation_CellBounded.dat"),
+    ("dipole_motion.ini", "SamplesOfSeparation_DipoleMotion.dat")])
 def test_shipped_dipole_config_matches_reference_statistics(tmp_path, config, output):
     """dipoles/cell_veto.ini of 2018_JCP_149_064113 (two dipoles: composite-object Coulomb handlers with cell veto on
     anisotropic 3 x 5 x 7 root-level cells, harmonic bond, 1/r^6 repulsion between the opposite charges of different
     dipoles as a factor between objects) and the three dipole_factors_*.ini (no cell system: the composite-object
     Coulomb factor of the factor type map with inside-first, outside-first and ratio lifting) and atom_factors.ini (the
-    Coulomb interaction as four bounded leaf-to-leaf factors between the dipoles), unchanged except for the
+    Coulomb interaction as four bounded leaf-to-leaf factors between the dipoles) and dipole_motion.ini (the independent
+    active unit alternates between a leaf unit and the root unit of a dipole), unchanged except for the
     mediator line, run length, sampling interval and output file: the separations between like and unlike charges of
     different dipoles follow the cumulative histograms the reference ships (ReferenceDataDipoles_13.dat / _14.dat)."""
     import sys
