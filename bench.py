@@ -9,7 +9,8 @@ data-path collective), cells 12^3, nearby cells + surplus by exact LJ inversion,
 BASELINE configurations are `--workload c1` (shipped hard-disk dipoles), `c3` (Coulomb atoms, `--particles` 64..512),
 `c4` (SPC/Fw water, 32 molecules, the oxygen-oxygen histogram of every step all-reduced over the ranks inside the timed
 region) and `c5` (one Lennard-Jones chain of 65536 particles; value = 1 / latency). A "step" advances every chain by
-`events_per_chain_per_step` events (one ecmc_run launch). One JSON line is printed by rank 0:
+`events_per_chain_per_step` events (one ecmc_run launch; C2: 4096 = four sweeps of the 1024 particles, `--events` changes
+it). One JSON line is printed by rank 0:
 
   value      events/s over all ranks, chain state resident in HBM, CUDA events on the launching stream, max over ranks
   e2e        the same steps from HOST buffers: every step takes the configuration from a pinned host buffer (the whole
@@ -120,7 +121,10 @@ class LennardJones(Workload):
         self.particles = args.particles or 1024
         self.cells = args.cells or 12
         self.chains = args.chains or 4096
-        self.events = args.events or 1024
+        # A step = 4096 events per chain = four sweeps of a chain's 1024 particles between two visits of the host. (Rounds 1
+        # and 2 measured steps of 1024 events, `--events 1024`: 2.4 ms of kernel per 100.7 MB upload, which eight ranks
+        # sharing one host cannot feed -- 5.4e9 events/s end to end on eight GPUs against 1.33e10 device-resident.)
+        self.events = args.events or 4096
         self.length = float((self.particles / 0.5) ** (1.0 / 3.0))
         self.text = ("%s: 3D Lennard-Jones (prefactor 4, sigma 1), density 0.5, N = %d, cells %d^3 nl=1 one occupant per cell, "
                      "exact inversion for nearby cells + surplus, cell-veto far field, chain_time 10, beta 1, jittered "
@@ -307,7 +311,9 @@ class Water(Workload):
         super().__init__(args)
         self.molecules = args.particles or 32
         self.particles = 3 * self.molecules
-        self.chains = args.chains or 1024
+        # one wave of the kernel's CTAs: sixteen chains (one per warp) on every one of the 148 SMs; with at most eight
+        # chains per SM (--chains 1024, the size of rounds 1 and 2) the kernel runs CTAs of eight warps
+        self.chains = args.chains or 2368
         self.events = args.events or 500
         self.text = ("C4: SPC/Fw water (water/coulomb_cell_veto_lj_inverted.ini), %d molecules, L = 10, beta 1.679, "
                      "merged-image Coulomb between molecules (inverse-power bound nearby, cell veto elsewhere), Lennard-Jones "

@@ -34,6 +34,17 @@ static_assert(ECMC_RESIDENT_WARPS % ECMC_WARPS_PER_BLOCK == 0, "whole CTAs must 
 // molecule_kernel without the per-event CTA barrier (composite objects other than water, ECMC_MOLECULE_ALIGNED=0): small
 // CTAs leave the compiler its 168 registers (a CTA of 14 warps would cap them at 128)
 constexpr int kMoleculeWarps = 4;
+// molecule_kernel with the per-event CTA barrier (the shipped water potentials): warps per CTA
+#ifndef ECMC_ALIGNED_WARPS
+#define ECMC_ALIGNED_WARPS 8
+#endif
+constexpr int kAlignedWarps = ECMC_ALIGNED_WARPS;
+// More chains than kAlignedWarps per SM: CTAs of sixteen aligned warps. The kernel's time is the latency of each chain's
+// dependent instructions, so warps per SM are throughput -- and ONE large CTA per SM, whose warps fetch the event's
+// instructions together, beats several small ones (measured on B200, 32 water molecules per chain, one wave of chains
+// each: 8 warps per SM 4.5e7, 12: 6.2e7, 16: 7.0e7 events/s at 128 registers and 200 B of spills, 20: 7.2e7 at 96
+// registers and 658 B; 2 CTAs x 8 warps 5.2e7, 4 x 4: 4.0e7, 3 x 6: 3.4e7).
+constexpr int kWideWarps = 16;
 
 struct EventPair {
     cudaEvent_t start, stop;
@@ -82,6 +93,26 @@ struct EcmcHandle {
 };
 
 namespace {
+
+// Which molecule_kernel a handle runs: the warps per CTA of the aligned kernel for the shipped water potentials (Coulomb
+// bound / merged-image Coulomb / harmonic bonds / Lennard-Jones; kAlignedWarps, or kWideWarps when there are more chains
+// than that per SM), kMoleculeWarps for the generic instantiation, -1 for the water potentials without the CTA barrier
+// (ECMC_MOLECULE_ALIGNED=0).
+int molecule_cta_warps(const EcmcHandle *h) {
+    const DeviceProgram &d = h->dprog;
+    const bool water = d.cand_potential.kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING &&
+                       d.real_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB &&
+                       (!d.veto_enabled || d.veto_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB) &&
+                       (d.n_bonds == 0 || (d.bond_potential.kind == ECMC_POT_DISPLACED_EVEN_POWER &&
+                                           d.bond_potential.dep.power == 2.0)) &&
+                       (h->mprog.n_inter == 0 || h->mprog.inter_potential.kind == ECMC_POT_LENNARD_JONES);
+    if (!water || h->mprog.root_mode) return kMoleculeWarps;
+    if (const char *env = std::getenv("ECMC_MOLECULE_ALIGNED"))
+        if (std::atoi(env) == 0) return -1;
+    int sm_count = 148;
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) sm_count = 148;
+    return h->n_chains > kAlignedWarps * sm_count ? kWideWarps : kAlignedWarps;
+}
 
 int fail(EcmcHandle *h, int code, const std::string &message) {
     if (h) h->error = message; else g_create_error = message;
@@ -709,27 +740,18 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         if (d_records) disk_kernel<true, kDiskWarps><<<disk_blocks, kDiskWarps * 32, 0, h->stream>>>(h->dprog, h->kprog, h->state, args);
         else disk_kernel<false, kDiskWarps><<<disk_blocks, kDiskWarps * 32, 0, h->stream>>>(h->dprog, h->kprog, h->state, args);
     } else if (h->molecules) {
-        // the shipped water configurations: Coulomb bound / merged-image Coulomb / harmonic bonds / Lennard-Jones
-        const DeviceProgram &d = h->dprog;
-        const bool water = d.cand_potential.kind == ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING &&
-                           d.real_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB &&
-                           (!d.veto_enabled || d.veto_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB) &&
-                           (d.n_bonds == 0 || (d.bond_potential.kind == ECMC_POT_DISPLACED_EVEN_POWER &&
-                                               d.bond_potential.dep.power == 2.0)) &&
-                           (h->mprog.n_inter == 0 || h->mprog.inter_potential.kind == ECMC_POT_LENNARD_JONES);
         typedef void (*MoleculeKernel)(const DeviceProgram, const MoleculeProgram, const DeviceState, const RunArgs);
         const int IPCB = ECMC_POT_INVERSE_POWER_COULOMB_BOUNDING, MIC = ECMC_POT_MERGED_IMAGE_COULOMB,
                   DEP = kPotHarmonic, LJ = ECMC_POT_LENNARD_JONES;
         MoleculeKernel kernel;
-#ifndef ECMC_ALIGNED_WARPS
-#define ECMC_ALIGNED_WARPS 8
-#endif
-        constexpr int kAlignedWarps = ECMC_ALIGNED_WARPS;
-        bool aligned = true;
-        if (const char *env = std::getenv("ECMC_MOLECULE_ALIGNED")) aligned = std::atoi(env) != 0;
+        const int warps = molecule_cta_warps(h);
+        const bool water = warps < 0 || warps > kMoleculeWarps, aligned = warps > kMoleculeWarps, wide = warps == kWideWarps;
         if (h->mprog.root_mode)
             kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kMoleculeWarps, false, true>
                                : molecule_kernel<-1, -1, -1, -1, false, kMoleculeWarps, false, true>;
+        else if (water && aligned && wide)
+            kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kWideWarps, true>
+                               : molecule_kernel<IPCB, MIC, DEP, LJ, false, kWideWarps, true>;
         else if (water && aligned)
             kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kAlignedWarps, true>
                                : molecule_kernel<IPCB, MIC, DEP, LJ, false, kAlignedWarps, true>;
@@ -739,8 +761,8 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         else
             kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kMoleculeWarps, false>
                                : molecule_kernel<-1, -1, -1, -1, false, kMoleculeWarps, false>;
-        const int warps = water && aligned && !h->mprog.root_mode ? kAlignedWarps : kMoleculeWarps;
-        kernel<<<(h->n_chains + warps - 1) / warps, warps * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
+        const int cta_warps = warps < 0 ? kMoleculeWarps : warps;
+        kernel<<<(h->n_chains + cta_warps - 1) / cta_warps, cta_warps * 32, 0, h->stream>>>(h->dprog, h->mprog, h->state, args);
     } else {
         SpecLaunch spec;
         if (pick_spec(h, d_records != nullptr, &spec)) {
@@ -1443,7 +1465,7 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
         h->kernel_name = "disk_kernel<record=" + std::to_string(record != 0) + ">";
     } else if (h->molecules) {
         h->kernel_name = "molecule_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto + ", record=" + std::to_string(record != 0) +
-                         (h->mprog.root_mode ? ", root mode>" : ">");
+                         (h->mprog.root_mode ? ", root mode>" : (molecule_cta_warps(h) == kWideWarps ? ", warps=16>" : ">"));
     } else if (pick_spec(h, record != 0, &spec) && spec.chain_blocks) {
         h->kernel_name = "lj_chain_kernel<record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", warps per chain=" + std::to_string(kChainWarps) + ">";
