@@ -223,17 +223,25 @@ def test_coulomb_pruning_does_not_change_the_chains(mixed):
 
 
 def test_coulomb_time_limits_cut_batches_like_the_single_event_kernel():
+    import copy
     n_chains, n = 48, 64
-    builder, length = _coulomb_program(n, chain_time=0.3)
+    # the module's program with a shorter chain time (a copy of the EcmcProgram; its tables stay those of the cached builder)
+    cached, length = _coulomb_program(n)
+    builder = copy.copy(cached)
+    builder.program = type(cached.program).from_buffer_copy(bytes(cached.program))
+    builder.program.chain_time = 0.3
     positions, charges = _coulomb_chains(n_chains, n, length, True)
     with _coulomb_started(builder, positions, charges, 40, batched=0) as single, \
             _coulomb_started(builder, positions, charges, 40, prune=1) as batched:
         for eng in (single, batched):
+            # time limits every 1 / 128 up to 0.3203: one end of chain (0.3) falls inside; the horizon of 3.06 this test
+            # started with cost 220 s of the GPU suite for the same code paths
             for k in range(1, 40):
-                eng.run(until=(float(k // 16), (k % 16) / 16.0))
+                eng.run(until=(0.0, k / 128.0))
                 eng.run(max_events=3)
-            eng.run(until=(3.0, 0.0625))
+            eng.run(until=(0.0, 0.3203125))
             eng.sync()
         _assert_same_state(single, batched, "after interleaved time limits")
         states = batched.chain_states()
-        assert np.all(states["time_q"] == 3.0) and np.all(states["time_r"] == 0.0625)
+        assert np.all(states["time_q"] == 0.0) and np.all(states["time_r"] == 0.3203125)
+        assert np.all(states["eoc_r"] > 0.3203125) and np.all(states["event_counter"] > 100)
