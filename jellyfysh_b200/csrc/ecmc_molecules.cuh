@@ -35,6 +35,10 @@ struct MoleculeProgram {
 };
 
 constexpr int kItemCapacity = 192;  // work items per chunk (two ints each: 1.5 KB per warp)
+// per-warp sine / cosine scratch of the merged-image Coulomb sums: one sum up to the largest Fourier cutoff, or the three
+// sums of mic_derivative_warp3 up to cutoff 6 (3 x 3 x 2 x 7 = 126 doubles; the shipped potentials use 6)
+constexpr int kMoleculeTrigDoubles = 128;
+static_assert(kMoleculeTrigDoubles >= kTrigDoubles, "one sum with the largest Fourier cutoff must fit");
 enum ItemType { ITEM_PAIR_LEAF = 0, ITEM_INTER = 1, ITEM_BOND = 2, ITEM_BENDING = 3, ITEM_VETO = 4, ITEM_BOUNDARY = 5,
                 ITEM_FAR_OBJECT = 6 };
 
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ MoleculeProgram M, const DeviceState S,
                 const RunArgs A) {
     static_assert(!(ROOT_MODE && ALIGNED), "the root-unit-active mode runs without the per-event CTA barrier");
-    __shared__ double trig_all[WARPS * kTrigDoubles];
+    __shared__ double trig_all[WARPS * kMoleculeTrigDoubles];
     __shared__ int items_all[WARPS * 2 * kItemCapacity];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -181,7 +185,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
         if (ALIGNED) while (!__syncthreads_and(1)) {}  // keep the barriers of the other warps complete
         return;
     }
-    double *trig = trig_all + warp * kTrigDoubles;
+    double *trig = trig_all + warp * kMoleculeTrigDoubles;
     int *item_code = items_all + warp * 2 * kItemCapacity;  // type | sequence << 4
     int *item_target = item_code + kItemCapacity;
 
@@ -870,6 +874,9 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             // event_handler_with_bounding_potential.py:170-220)
             double local_derivatives[4] = {0.0, 0.0, 0.0, 0.0};
             bool confirmed = false;
+            const bool three_sums = REAL == ECMC_POT_MERGED_IMAGE_COULOMB && !one_leaf && npr == 3 &&
+                                    real_potential.kind == ECMC_POT_MERGED_IMAGE_COULOMB &&
+                                    18 * (real_potential.mic.fourier_cutoff + 1) <= kMoleculeTrigDoubles;
             for (int i = -1; i < npr; i++) {
                 const int local = i < 0 ? active : active_root * npr + i;
                 if (i >= 0 && local == active) continue;
@@ -887,6 +894,27 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                 const Particle lp = part[local];
                 const Vec3 lpos = i < 0 ? apos : lab_position(lp);
                 const double lcharge = i < 0 ? acharge : lp.charge;
+                if (REAL == ECMC_POT_MERGED_IMAGE_COULOMB && three_sums) {
+                    // one local leaf against the three leaves of the target molecule: the three Ewald sums side by side,
+                    // multiplied as derivative_warp does (prefactor x charges x sum x speed)
+                    Vec3 s3[3];
+                    for (int j = 0; j < 3; j++) {
+                        const Vec3 lab = separation_lab(lpos, tpos[j], L, half);
+                        s3[j].x = vcomp(lab, dir);
+                        s3[j].y = dir == 0 ? lab.y : (dir == 1 ? lab.z : lab.x);
+                        s3[j].z = dir == 0 ? lab.z : (dir == 1 ? lab.x : lab.y);
+                    }
+                    double sums[3];
+                    mic_derivative_warp3(real_potential.mic, s3[0].x, s3[0].y, s3[0].z, s3[1].x, s3[1].y, s3[1].z, s3[2].x,
+                                         s3[2].y, s3[2].z, trig, lane, sums[0], sums[1], sums[2]);
+                    for (int j = 0; j < 3; j++) {
+                        const double c1 = use_charge ? lcharge : 1.0, c2 = use_charge ? tcharge[j] : 1.0;
+                        const double pairwise = real_potential.mic.prefactor * c1 * c2 * sums[j] * speed;
+                        if (i < 0) factor_derivative += pairwise; else local_derivatives[i] += pairwise;
+                        target_derivatives[j] -= pairwise;
+                    }
+                    continue;
+                }
                 for (int j = k_first; j < k_last; j++) {
                     const double c1 = use_charge ? lcharge : 1.0, c2 = use_charge ? tcharge[j] : 1.0;
                     const double pairwise = pair_derivative_lab<REAL>(real_potential, dir, speed, lpos, tpos[j], c1, c2, L,
