@@ -37,8 +37,7 @@ struct MoleculeProgram {
 constexpr int kItemCapacity = 192;  // work items per chunk (two ints each: 1.5 KB per warp)
 // per-warp sine / cosine scratch of the merged-image Coulomb sums: one sum up to the largest Fourier cutoff, or the three
 // sums of mic_derivative_warp3 up to cutoff 6 (3 x 3 x 2 x 7 = 126 doubles; the shipped potentials use 6)
-constexpr int kMoleculeTrigDoubles = 128;
-static_assert(kMoleculeTrigDoubles >= kTrigDoubles, "one sum with the largest Fourier cutoff must fit");
+constexpr int kMoleculeTrigDoubles = kTrigDoubles3;
 enum ItemType { ITEM_PAIR_LEAF = 0, ITEM_INTER = 1, ITEM_BOND = 2, ITEM_BENDING = 3, ITEM_VETO = 4, ITEM_BOUNDARY = 5,
                 ITEM_FAR_OBJECT = 6 };
 

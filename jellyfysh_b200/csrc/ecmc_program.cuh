@@ -47,6 +47,10 @@ struct PotentialParams {
 
 constexpr int kMaxFourierCutoff = 15;
 constexpr int kTrigDoubles = 3 * 2 * (kMaxFourierCutoff + 1);
+// the same for kernels that also evaluate three sums side by side (mic_derivative_warp3: 3 x 3 x 2 x (cutoff + 1) doubles,
+// up to cutoff 6 -- the shipped potentials; larger cutoffs take the sums one at a time)
+constexpr int kTrigDoubles3 = 128;
+static_assert(kTrigDoubles3 >= kTrigDoubles, "one sum with the largest Fourier cutoff must fit");
 constexpr int kMaxNearby = 343;  // (2 * 3 + 1)^3
 
 struct DeviceProgram {
