@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ECMC_ABI_VERSION 5
+#define ECMC_ABI_VERSION 6
 #define ECMC_MAX_BONDS 4
 #define ECMC_MAX_DIM 3
 
@@ -240,6 +240,26 @@ typedef struct EcmcProgram {
     int32_t root_mode;
     double eoc_cos, eoc_sin;
     double switch_chain_length[2];
+    /* ---- a cell system for ONE kind of leaf only (the shipped water/coulomb_power_bounded_lj_cell_bounded.ini):
+     * SingleActiveCellOccupancy(cell_level = 2, charge = <indicator>) stores only the leaves with child index
+     * cell_child - 1 of every object (the oxygens; single_active_cell_occupancy.py:62-121) in cells_per_side /
+     * neighbor_layers / max_occupants cells, and has an active cell only while such a leaf is active. 0: no such system.
+     * With it (requires cell_level = 1, pair_handler = ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, no_cells = 0):
+     *  - the composite-object pair factors come from the factor type map: every other object is a candidate of every event;
+     *  - while a leaf of that kind is active, the two-leaf factor inter_factors[0] = (cell_child - 1, cell_child - 1) with the
+     *    same leaf of the objects in nearby cells and of the surplus is handled by
+     *    TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential
+     *    (two_leaf_unit_event_handler_with_piecewise_constant_bounding_potential.py:103-162: constant bound = max(derivative
+     *    now, derivative after inter_bound_max_displacement) + inter_bound_offset, confirmed against inter_potential), with
+     *    those in all other cells by TwoLeafUnitCellBoundingPotentialEventHandler (veto_enabled = ECMC_FAR_CELL_BOUNDING,
+     *    veto_potential, veto_tables->bounds), and the cell boundary is that of the active LEAF;
+     *  - a cell-boundary event re-creates only the candidates found through the cells; the composite pairs, bonds and the
+     *    bending factor keep theirs (boundary_keeps_factors = 1, EcmcChainState.kept_*).
+     * Occupants, surplus and pending / kept targets of such a program are LEAF identifiers. */
+    int32_t cell_child;
+    int32_t reserved3;
+    double inter_bound_offset;
+    double inter_bound_max_displacement;
 } EcmcProgram;
 
 /* ---- per-chain lifting state ("who is active, where is the clock") ------------------------------------

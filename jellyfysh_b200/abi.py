@@ -1,7 +1,7 @@
 """ctypes mirror of include/ecmc.h (the C ABI of libecmc_b200.so). Plain data only, no computation."""
 import ctypes as C
 
-ECMC_ABI_VERSION = 5
+ECMC_ABI_VERSION = 6
 ECMC_MAX_DIM = 3
 ECMC_MAX_BONDS = 4
 ECMC_MAX_INTER_FACTORS = 4
@@ -115,7 +115,9 @@ class EcmcProgram(C.Structure):
                 ("bending_potential", EcmcPotential), ("bending_offset", C.c_double),
                 ("bending_max_displacement", C.c_double),
                 ("eoc_sequential", C.c_int32), ("root_mode", C.c_int32), ("eoc_cos", C.c_double), ("eoc_sin", C.c_double),
-                ("switch_chain_length", C.c_double * 2)]
+                ("switch_chain_length", C.c_double * 2),
+                ("cell_child", C.c_int32), ("reserved3", C.c_int32), ("inter_bound_offset", C.c_double),
+                ("inter_bound_max_displacement", C.c_double)]
 
 
 class EcmcChainState(C.Structure):

@@ -145,6 +145,20 @@ class ProgramBuilder:
         p.switch_chain_length[1] = root_to_leaf_chain_length
         return self
 
+    def set_leaf_cells(self, child, offset, max_displacement):
+        """A cell system that holds only the leaves with child index `child` of every object (SingleActiveCellOccupancy with
+        cell_level = 2 and a charge indicator, water/coulomb_power_bounded_lj_cell_bounded.ini): the two-leaf factor between
+        these leaves of different objects (inter_potential, set_molecules(inter_factors=[(child, child)])) is found through
+        the cells -- nearby cells and surplus with the piecewise constant bound (offset, max_displacement), all other cells
+        through set_cell_bounding --, the composite-object pair factors come from the factor type map."""
+        p = self.program
+        if p.no_cells or p.nodes_per_root < 2 or p.cell_level != 1 or not 0 <= child < p.nodes_per_root:
+            raise ValueError("leaf cells need composite objects (set_composite, set_molecules) and a cell system")
+        p.cell_child = child + 1
+        p.inter_bound_offset = offset
+        p.inter_bound_max_displacement = max_displacement
+        return self
+
     def set_cell_bounding(self, potential, bounds, use_charge=False, target_charge=1.0):
         """Far field through TwoLeafUnitCellBoundingPotentialEventHandler: bounds[n_cells][dimension][2] holds
         (upper bound, -lower bound) of the derivative per relative cell (CellBoundingPotential._derivative_bounds)."""

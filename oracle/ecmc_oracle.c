@@ -1048,6 +1048,14 @@ ORC_API OrcChain *orc_chain_create(const EcmcProgram *prog) {
     if (prog->eoc_sequential && (c->D != 2 || !prog->no_cells || c->npr < 2 || c->molecules ||
                                  prog->pair_handler != ECMC_PAIR_NONE || prog->veto_enabled)) goto fail;
     if (c->molecules && (c->D != 3 || c->npr > 4 || prog->max_occupants != 1)) goto fail;
+    /* a cell system for one kind of leaf only: composite-object pairs from the factor type map, one two-leaf factor
+     * between those leaves found through the cells */
+    if (prog->cell_child && (!c->molecules || prog->no_cells || prog->cell_child < 1 || prog->cell_child > c->npr ||
+                             prog->pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || prog->root_mode ||
+                             prog->n_inter_factors != 1 || prog->inter_factors[0][0] != prog->cell_child - 1 ||
+                             prog->inter_factors[0][1] != prog->cell_child - 1 || !prog->boundary_keeps_factors ||
+                             (prog->veto_enabled != ECMC_FAR_NONE && prog->veto_enabled != ECMC_FAR_CELL_BOUNDING) ||
+                             !(prog->inter_bound_max_displacement > 0.0))) goto fail;
     /* root-unit-active mode: dipoles without a cell system, composite-object pair handler */
     if (prog->root_mode && (!c->molecules || c->npr != 2 || !prog->no_cells || prog->bending_enabled ||
                             prog->pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING)) goto fail;
@@ -1190,7 +1198,13 @@ ORC_API void orc_chain_start(OrcChain *c, uint32_t stream) {
     int m = c->prog.max_occupants;
     for (int i = 0; i < c->cells.n_cells * m; i++) c->occ[i] = -1;
     c->n_surplus = 0;
-    if (c->molecules) {
+    if (c->molecules && c->prog.cell_child) {
+        /* cell_level = 2 with a charge indicator: only the leaves of one kind are stored (:95-121, _is_relevant_unit) */
+        for (int r = 0; r < c->N / c->npr; r++) {
+            int leaf = r * c->npr + c->prog.cell_child - 1;
+            occ_insert(c, position_to_cell(&c->cells, c->pos + leaf * c->D), leaf);
+        }
+    } else if (c->molecules) {
         /* cell_level = 1: the cells hold the root units (single_active_cell_occupancy.py:95-121) */
         for (int r = 0; r < c->N / c->npr; r++) occ_insert(c, position_to_cell(&c->cells, c->root_pos + r * c->D), r);
     } else {
@@ -1202,7 +1216,14 @@ ORC_API void orc_chain_start(OrcChain *c, uint32_t stream) {
     c->st.direction = c->prog.initial_direction;
     c->st.time_q = 0.0; c->st.time_r = 0.0;
     c->st.event_counter = 0;
-    if (c->molecules) {
+    if (c->molecules && c->prog.cell_child) {
+        /* the occupancy has an active cell only while a stored kind of leaf is active (:149-203) */
+        c->st.active_cell = 0;
+        if (c->st.active % c->npr == c->prog.cell_child - 1) {
+            c->st.active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
+            occ_remove(c, c->st.active_cell, c->st.active);
+        }
+    } else if (c->molecules) {
         c->st.active_cell = position_to_cell(&c->cells, c->root_pos + (c->st.active / c->npr) * c->D);
         occ_remove(c, c->st.active_cell, c->st.active / c->npr);
     } else {
@@ -1677,8 +1698,78 @@ static int composite_lifting(OrcChain *c, int target_root, double active_derivat
     return lifting_get(&lift, c->prog.composite_lifting, c, draw);
 }
 
+/* TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential.send_event_time
+ * (two_leaf_unit_event_handler_with_piecewise_constant_bounding_potential.py:103-131 on
+ * _displacement_from_piecewise_constant_bounding_potential, event_handler_with_bounding_potential.py:282-332): the active
+ * leaf against leaf `target` of another object; rate < 0 stands for "bounding event rate None" */
+static candidate piecewise_pair_candidate(OrcChain *c, int target) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_FACTOR_PAIR; cand.target = target; cand.target_cell = -1;
+    const int D = c->D, dir = c->st.direction;
+    const double *pa = c->pos + c->st.active * D, *pt = c->pos + target * D;
+    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
+    double potential_change = rng_expovariate(u, c->prog.beta);
+    double sep[ECMC_MAX_DIM] = {0, 0, 0}, moved[ECMC_MAX_DIM] = {0, 0, 0};
+    separation_vector(pa, pt, D, c->L, sep);
+    double one = pot_derivative(&c->inter_pot, dir, c->prog.speed, sep, D, 1.0, 1.0);
+    for (int d = 0; d < D; d++) {
+        double v = d == dir ? c->prog.speed : 0.0;
+        moved[d] = correct_position_entry(pa[d] + v * c->prog.inter_bound_max_displacement, c->L);
+    }
+    separation_vector(moved, pt, D, c->L, sep);
+    double two = pot_derivative(&c->inter_pot, dir, c->prog.speed, sep, D, 1.0, 1.0);
+    double constant = (one > two ? one : two) + c->prog.inter_bound_offset; /* max(a, b) */
+    double dt;
+    if (constant <= 0.0) { cand.rate = -1.0; dt = c->prog.inter_bound_max_displacement; }
+    else if (potential_change / constant < c->prog.inter_bound_max_displacement) { cand.rate = constant; dt = potential_change / constant; }
+    else { cand.rate = -1.0; dt = c->prog.inter_bound_max_displacement; }
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, dt);
+    return cand;
+}
+
+/* TwoLeafUnitCellBoundingPotentialEventHandler.send_event_time (two_leaf_unit_cell_bounding_potential_event_handler.py:
+ * 137-177) for the active leaf and leaf `target` in a cell that is not nearby; chargeless here. The draw is double 1 of
+ * the factor-time slot of the target leaf (the pair-time slots belong to the composite-object handlers). */
+static candidate leaf_cell_bounding_candidate(OrcChain *c, int target) {
+    candidate cand;
+    cand.kind = ECMC_EVENT_CELL_BOUNDING; cand.target = target;
+    int dir = c->st.direction;
+    int active_cell = position_to_cell(&c->cells, c->pos + c->st.active * c->D);
+    int target_cell = position_to_cell(&c->cells, c->pos + target * c->D);
+    int relative_cell = cells_relative(&c->cells, target_cell, active_cell);
+    cand.target_cell = relative_cell;
+    cand.rate = c->bounds[(relative_cell * c->D + dir) * 2 + 0];
+    double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 1);
+    double dU = rng_expovariate(u, c->prog.beta);
+    double displacement = cand.rate > 0 ? dU / cand.rate : ORC_INF;
+    otime now = {c->st.time_q, c->st.time_r};
+    cand.t = time_add(now, displacement / c->prog.speed);
+    return cand;
+}
+
+/* SingleActiveCellOccupancy.update (:149-203) for a cell system that stores one kind of leaf only: the old active leaf
+ * goes back into its cell if it is of that kind, the new one leaves its cell if it is */
+static void leaf_cells_occupancy_update(OrcChain *c, int new_active) {
+    const int kind = c->prog.cell_child - 1, npr = c->npr;
+    const int old_active = c->st.active;
+    const int old_relevant = old_active % npr == kind, new_relevant = new_active % npr == kind;
+    if (new_active != old_active) {
+        if (old_relevant) occ_insert(c, c->st.active_cell, old_active);
+        c->st.active_cell = 0;
+        if (new_relevant) {
+            c->st.active_cell = position_to_cell(&c->cells, c->pos + new_active * c->D);
+            occ_remove(c, c->st.active_cell, new_active);
+        }
+    } else if (new_relevant) {
+        c->st.active_cell = position_to_cell(&c->cells, c->pos + new_active * c->D);
+    }
+    c->st.active = new_active;
+}
+
 /* SingleActiveCellOccupancy.update for cell_level = 1: the active unit on the cell level is the root */
 static void molecule_occupancy_update(OrcChain *c, int new_active) {
+    if (c->prog.cell_child) { leaf_cells_occupancy_update(c, new_active); return; }
     int old_root = c->st.active / c->npr, new_root = new_active / c->npr;
     if (new_root != old_root) {
         occ_insert(c, c->st.active_cell, old_root);
@@ -1721,7 +1812,12 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
 #define CONSIDER(cand) do { if (!isinf((cand).t.q)) { n_cand++; if (lt_candidate(&(cand), &best)) { best = (cand); best_from_kept = 0; } } } while (0)
         int nearby[343];
         int nn = nearby_cells(&c->cells, c->st.active_cell, nearby);
-        if (c->prog.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING) {
+        const int leaf_cells = c->prog.cell_child != 0;
+        const int cell_leaf_active = leaf_cells && active_child == c->prog.cell_child - 1;
+        if (leaf_cells) {
+            /* the composite-object pairs come from the factor type map and belong to the handlers that a cell-boundary
+             * event leaves running: below, with the bonds and the bending factor */
+        } else if (c->prog.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING) {
             for (int i = 0; i < nn; i++) {
                 int t = c->occ[nearby[i]];
                 if (t < 0) continue;
@@ -1754,6 +1850,12 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
             }
         } else {
 #define CONSIDER_FACTOR(cand) do { if (!isinf((cand).t.q)) { n_cand++; if (lt_candidate(&(cand), &factor_best)) factor_best = (cand); } } while (0)
+            if (leaf_cells)
+                for (int r = 0; r < c->N / npr; r++) {
+                    if (r == active_root) continue;
+                    candidate cand = composite_pair_candidate(c, r);
+                    CONSIDER_FACTOR(cand);
+                }
             for (int b = 0; b < c->prog.n_bonds; b++) {
                 int partner = -1;
                 if (c->prog.bonds[b][0] == active_child) partner = c->prog.bonds[b][1];
@@ -1762,7 +1864,7 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
                 candidate cand = bond_candidate(c, active_root * npr + partner);
                 CONSIDER_FACTOR(cand);
             }
-            for (int f = 0; f < c->prog.n_inter_factors; f++) {
+            for (int f = 0; f < c->prog.n_inter_factors && !leaf_cells; f++) {
                 if (c->prog.inter_factors[f][0] != active_child) continue;
                 for (int r = 0; r < c->N / npr; r++) {
                     if (r == active_root) continue;
@@ -1777,7 +1879,35 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
 #undef CONSIDER_FACTOR
         }
         if (lt_candidate(&factor_best, &best)) { best = factor_best; best_from_kept = factor_from_kept; }
-        if (c->prog.veto_enabled == ECMC_FAR_CELL_VETO) {
+        if (leaf_cells) {
+            /* found through the cells of the active leaf, if it is of the stored kind (the occupancy has no active cell
+             * otherwise): ExcludedCellsTagger + SurplusCellsTagger -> the piecewise-constant-bound handler,
+             * CellBoundingPotentialTagger -> the cell-bounding handler, CellBoundaryTagger */
+            if (cell_leaf_active) {
+                for (int i = 0; i < nn; i++) {
+                    int t = c->occ[nearby[i]];
+                    if (t < 0) continue;
+                    candidate cand = piecewise_pair_candidate(c, t);
+                    CONSIDER(cand);
+                }
+                for (int sidx = 0; sidx < c->n_surplus; sidx++) {
+                    candidate cand = piecewise_pair_candidate(c, c->surplus[sidx]);
+                    CONSIDER(cand);
+                }
+                for (int cell = 0; cell < c->cells.n_cells && c->prog.veto_enabled == ECMC_FAR_CELL_BOUNDING; cell++) {
+                    int t = c->occ[cell];
+                    if (t < 0) continue;
+                    int is_near = 0;
+                    for (int i = 0; i < nn; i++) if (nearby[i] == cell) { is_near = 1; break; }
+                    if (is_near) continue;
+                    candidate cand = leaf_cell_bounding_candidate(c, t);
+                    CONSIDER(cand);
+                }
+                candidate cand = boundary_candidate(c, &boundary_position);
+                n_cand++;
+                if (lt_candidate(&cand, &best)) { best = cand; best_from_kept = 0; }
+            }
+        } else if (c->prog.veto_enabled == ECMC_FAR_CELL_VETO) {
             candidate cand = veto_candidate(c);
             CONSIDER(cand);
         } else if (c->prog.veto_enabled == ECMC_FAR_CELL_BOUNDING) {
@@ -1793,7 +1923,7 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
                 CONSIDER(cand);
             }
         }
-        if (!c->prog.no_cells) {
+        if (!c->prog.no_cells && !leaf_cells) {
             candidate cand = root_boundary_candidate(c, &boundary_position);
             n_cand++;
             if (lt_candidate(&cand, &best)) { best = cand; best_from_kept = 0; }
@@ -1876,6 +2006,23 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
          * object; the stored rate is a rate per length, the bounding potential's derivative is that times the speed */
         int far = best.kind == ECMC_EVENT_CELL_BOUNDING;
         int veto = best.kind == ECMC_EVENT_CELL_VETO || far;
+        if (far && c->prog.cell_child) {
+            /* TwoLeafUnitCellBoundingPotentialEventHandler.send_out_state (:179-211) between two leaves: the stored rate
+             * times the speed is the bounding event rate, confirmed against the real potential
+             * (event_handler_with_bounding_potential.py:75-101); recorded with the target's object */
+            rec_target = best.target / npr;
+            c->stats.pair_events++;
+            double sep[ECMC_MAX_DIM] = {0, 0, 0};
+            separation_vector(pa, c->pos + best.target * D, D, c->L, sep);
+            double bounding_rate = best.rate * c->prog.speed;
+            double real = pot_derivative(&c->veto_pot, dir, c->prog.speed, sep, D, 1.0, 1.0);
+            if (real > 0) {
+                if (bounding_rate < real) c->stats.bound_violations++;
+                double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+                if (0 + (bounding_rate - 0) * u < real) { accepted = 1; new_active = best.target; }
+            }
+            break;
+        }
         if (!veto && c->prog.pair_handler == ECMC_PAIR_TWO_LEAF_UNIT_BOUNDING) {
             /* TwoLeafUnitBoundingPotentialEventHandler.send_out_state (:148-168) +
              * _calculate_out_state_of_two_leaf_unit_bounding_potential (event_handler_with_bounding_potential.py:75-101) */
@@ -1929,6 +2076,20 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
     case ECMC_EVENT_BOND:
     case ECMC_EVENT_FACTOR_PAIR:
         rec_target = best.target;
+        if (best.kind == ECMC_EVENT_FACTOR_PAIR && c->prog.cell_child) {
+            /* TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential.send_out_state (:133-152) */
+            c->stats.factor_pair_events++;
+            if (best.rate < 0.0) break; /* bounding event rate None */
+            double sep[ECMC_MAX_DIM] = {0, 0, 0};
+            separation_vector(pa, c->pos + best.target * D, D, c->L, sep);
+            double real = pot_derivative(&c->inter_pot, dir, c->prog.speed, sep, D, 1.0, 1.0);
+            if (real > 0) {
+                if (best.rate < real) c->stats.bound_violations++;
+                double u = rng_double(c->prog.seed, c->st.stream, c->st.event_counter, ECMC_SLOT(ECMC_SLOT_CONFIRM, 0), draw++);
+                if (0.0 + (best.rate - 0.0) * u < real) { accepted = 1; new_active = best.target; }
+            }
+            break;
+        }
         accepted = 1;
         new_active = best.target;
         if (best.kind == ECMC_EVENT_BOND) c->stats.bond_events++; else c->stats.factor_pair_events++;
@@ -1955,7 +2116,10 @@ static int molecule_step(OrcChain *c, otime until, EcmcEventRecord *rec) {
         break;
     }
     case ECMC_EVENT_CELL_BOUNDARY:
-        c->root_pos[active_root * D + dir] = boundary_position;
+        /* the unit on the cell level lands on the boundary (cell_boundary_event_handler.py:158-173): the root unit, or
+         * the active leaf of a cell system of leaves */
+        if (c->prog.cell_child) c->pos[old_active * D + dir] = boundary_position;
+        else c->root_pos[active_root * D + dir] = boundary_position;
         c->stats.boundary_events++;
         break;
     case ECMC_EVENT_END_OF_CHAIN:

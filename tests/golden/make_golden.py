@@ -245,11 +245,12 @@ def _tables_of(run):
     if not vetoes:
         # cell-bounding configuration: CellBoundingPotential._derivative_bounds = (upper dict, lower dict)
         handler = [h for h in run.mediator._activator.get_event_handlers() if "CellBounding" in type(h).__name__][0]
-        upper, lower = handler._bounding_potential._derivative_bounds
+        stored = handler._bounding_potential._derivative_bounds  # a bare dict when no lower bounds were asked for
+        upper, lower = (stored, None) if isinstance(stored, dict) else stored
         for cell, per_direction in upper.items():
             for d in range(dim):
                 bounds[run._cell_index(cell), d, 0] = per_direction[d]
-                bounds[run._cell_index(cell), d, 1] = -lower[cell][d]
+                bounds[run._cell_index(cell), d, 1] = -lower[cell][d] if lower is not None else 0.0
         out["bounds"] = bounds
         return out
     veto = vetoes[0]
@@ -603,6 +604,29 @@ def water_traces():
                           bending_offset=10.0, bending_max_displacement=0.112321434, initial_active=1))
 
 
+def leaf_cell_water_traces():
+    # the shipped water/coulomb_power_bounded_lj_cell_bounded.ini: a cell system for the OXYGENS only (cell level 2 with a
+    # charge indicator), Lennard-Jones between the oxygens through it (piecewise constant bound for nearby cells and the
+    # surplus, cell-bounding potential for all other cells, cell boundary of the oxygen), composite-object Coulomb factors,
+    # bonds and bending from the factor type map. Twelve molecules in the shipped 6^3 cells; sixteen in 4^3 cells, where
+    # two oxygens share a cell now and then (surplus)
+    meta = dict(neighbor_layers=1, system_length=10.0, beta=1.679, chain_time=2.12345, nodes_per_root=3,
+                mic=[332.0, 3.45, 6, 2], ipcb=[531.2], lj=[0.6217012, 3.165492], harmonic=[529.581, 1.012, 2.0],
+                bending=[75.9, 1.9764], bending_offset=10.0, bending_max_displacement=0.112321434, initial_active=1,
+                lj_offset=10.0, lj_max_displacement=0.24353253124, cell_child=1, far_field=2)
+    for name, n, cells, seed, jitter in (("trace_water_lj_cell_bounded", 12, [6, 6, 6], 13, 0.2),
+                                         ("trace_water_lj_cell_bounded_dense", 16, [4, 4, 4], 14, 0.3)):
+        roots, leaves = configs.water_start(n, 10.0, seed=seed, jitter=jitter)
+        ini = configs.shipped_without_sampling(
+            REF, ("2018_JCP_149_064113", "water", "coulomb_power_bounded_lj_cell_bounded.ini"),
+            replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                          ("number_event_handlers = 1", f"number_event_handlers = {n - 1}"),
+                          ("cells_per_side = 6, 6, 6", "cells_per_side = " + ", ".join(map(str, cells)))])
+        chain_trace(name, ini, None, seed=41 + n, stream=31 + n, n_events=4000, snapshot_every=250, max_occupants=1,
+                    composites=(roots, leaves), charges=np.tile([0.41, -0.82, 0.41], n),
+                    meta=dict(meta, n=3 * n, cells_per_side=cells))
+
+
 if __name__ == "__main__":  # noqa
     which = sys.argv[1:] or ["potentials", "base", "traces", "cell_bounding", "dipoles", "sequential", "water", "lifting",
                              "no_cells"]
@@ -613,6 +637,8 @@ if __name__ == "__main__":  # noqa
         dipole_motion_traces()
     if "water" in which:
         water_traces()
+    if "water" in which or "leaf_cells" in which:
+        leaf_cell_water_traces()
     if "lifting" in which:
         lifting_vectors()
     if "dipoles" in which:

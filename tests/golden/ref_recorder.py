@@ -206,6 +206,10 @@ class ReferenceRun:
             return EVENT_PAIR
         if "RootLeafUnitActiveSwitcher" in names:
             return EVENT_SWITCH
+        if "TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential" in names:
+            # a two-leaf factor between objects whose candidate comes from a piecewise constant bound (the Lennard-Jones
+            # factor of the oxygens in nearby cells, water/coulomb_power_bounded_lj_cell_bounded.ini)
+            return EVENT_FACTOR_PAIR
         if names & {"TwoLeafUnitEventHandler", "TwoLeafUnitBoundingPotentialEventHandler"}:
             local = self._factor_map_handlers().get(id(handler))
             if self.setting.number_of_node_levels == 1:
@@ -288,6 +292,11 @@ class ReferenceRun:
                     leaf, npr = run._target_of_pair(args[0]), run.setting.number_of_nodes_per_root_node
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, leaf // npr))
                     run.rng.di = leaf % npr
+                elif _kind == EVENT_CELL_BOUNDING and run.setting.number_of_node_levels == 2:
+                    # a leaf-level cell-bounding handler next to composite-object pair handlers (which use the pair-time
+                    # slots of the objects): double 1 of the factor-time slot of the target leaf
+                    run.rng.set_context(run.events, make_slot(SLOT_FACTOR_TIME, run._target_of_pair(args[0])))
+                    run.rng.di = 1
                 elif _kind in (EVENT_PAIR, EVENT_CELL_BOUNDING):
                     run.rng.set_context(run.events, make_slot(SLOT_PAIR_TIME, run._target_of_pair(args[0])))
                 elif _kind in (EVENT_BOND, EVENT_FACTOR_PAIR):
@@ -310,7 +319,8 @@ class ReferenceRun:
                     run.rng.clear_context()
 
             def send_out_state(*args, _h=h, _kind=kind, _orig=orig_out):
-                if _kind in (EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDING, EVENT_BENDING):
+                if _kind in (EVENT_PAIR, EVENT_CELL_VETO, EVENT_CELL_BOUNDING, EVENT_BENDING) or \
+                        "TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential" in {c.__name__ for c in type(_h).__mro__}:
                     # confirmation, then the draws of the lifting scheme, in call order
                     run.rng.set_context(run.events, make_slot(SLOT_CONFIRM))
                 elif _kind == EVENT_SWITCH:

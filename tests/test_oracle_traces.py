@@ -185,6 +185,41 @@ def test_no_cells_composite_chain_replay_bit_exact(oracle, name):
     assert chain.stats()["capacity_errors"] == 0
 
 
+@pytest.mark.parametrize("name", tu.LEAF_CELL_WATER_TRACES)
+def test_leaf_cell_water_chain_replay_bit_exact(oracle, name):
+    """The shipped water/coulomb_power_bounded_lj_cell_bounded.ini (twelve molecules in its 6^3 cells, sixteen in 4^3 cells):
+    a cell system that stores the oxygens only; the Lennard-Jones factor between oxygens through
+    TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential (nearby cells) and
+    TwoLeafUnitCellBoundingPotentialEventHandler (all other cells), cell-boundary events of the active oxygen that leave the
+    composite-object Coulomb factors, the bonds and the bending factor running."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    chain = oracle.OracleChain(tu.leaf_cell_water_builder_of(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    done = 0
+    snap_events = list(g["snap_event"])
+    for k, event in enumerate(snap_events + [len(records)]):
+        n, rec = chain.run(max_events=int(event) - done, record=int(event) - done)
+        assert n == event - done
+        ref = records[done:event]
+        for f in tu.DISCRETE_FIELDS:
+            assert np.array_equal(rec[f], ref[f]), (f, done + int(np.nonzero(rec[f] != ref[f])[0][0]))
+        assert np.array_equal(rec["time_q"], ref["time_q"]) and np.array_equal(rec["time_r"], ref["time_r"])
+        assert np.array_equal(rec["active_pos"], ref["active_pos"])
+        done = int(event)
+        if k < len(snap_events):
+            assert np.array_equal(chain.positions(), g["snap_positions"][k])
+            assert np.array_equal(chain.roots(), g["snap_roots"][k])
+            occ, surplus = chain.cells()
+            assert np.array_equal(occ, g["snap_occupants"][k])
+    kinds = np.bincount(records["kind"], minlength=9)
+    assert kinds[5] > 1000 and kinds[7] > 40 and kinds[3] >= 3 and kinds[1] > 1500
+    assert np.array_equal(chain.positions(), g["final_positions"]) and np.array_equal(chain.roots(), g["final_roots"])
+    assert chain.stats()["capacity_errors"] == 0
+
+
 def test_root_unit_active_mode_replay_bit_exact(oracle):
     """The shipped dipoles/dipole_motion.ini (three dipoles): which unit is active after every event -- the root unit of
     an object or one of its leaves (RootLeafUnitActiveSwitcher) -- and, with the shipped sampling events in between,

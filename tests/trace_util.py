@@ -195,6 +195,34 @@ def water_builder_of(g, builder_cls, max_surplus=None):
     return pb
 
 
+LEAF_CELL_WATER_TRACES = ["trace_water_lj_cell_bounded", "trace_water_lj_cell_bounded_dense"]
+
+
+def leaf_cell_water_builder_of(g, builder_cls):
+    """The shipped water/coulomb_power_bounded_lj_cell_bounded.ini: composite-object Coulomb factors, bonds and bending from
+    the factor type map; a cell system for the oxygens only, through which the Lennard-Jones factor between oxygens is
+    found (piecewise constant bound for nearby cells + surplus, cell-bounding potential elsewhere)."""
+    n = int(g["meta_n"])
+    pb = builder_cls(3, n, float(g["meta_system_length"]), float(g["meta_beta"]),
+                     [int(c) for c in g["meta_cells_per_side"]], int(g["meta_neighbor_layers"]), max_occupants=1,
+                     max_surplus=n // 3, chain_time=float(g["meta_chain_time"]),
+                     initial_active=int(g["meta_initial_active"]), seed=int(g["seed"][0]))
+    pb.set_pair(abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING, abi.EcmcPotential.make(abi.POT_MERGED_IMAGE_COULOMB, *g["meta_mic"]),
+                abi.EcmcPotential.make(abi.POT_INVERSE_POWER_COULOMB_BOUNDING, *g["meta_ipcb"]), use_charge=True)
+    lj = abi.EcmcPotential.make(abi.POT_LENNARD_JONES, *g["meta_lj"])
+    pb.set_cell_bounding(lj, g["bounds"], use_charge=False)
+    pb.set_composite(int(g["meta_nodes_per_root"]), bonds=[(0, 1), (1, 2)],
+                     bond_potential=abi.EcmcPotential.make(abi.POT_DISPLACED_EVEN_POWER, *g["meta_harmonic"]))
+    child = int(g["meta_cell_child"])
+    pb.set_molecules(abi.LIFTING_INSIDE_FIRST, inter_factors=[(child, child)], inter_potential=lj,
+                     bending=dict(children=[0, 1, 2], separations=[1, 0, 1, 2], lifting=abi.LIFTING_RATIO,
+                                  potential=abi.EcmcPotential.make(abi.POT_BENDING, *g["meta_bending"]),
+                                  offset=float(g["meta_bending_offset"]),
+                                  max_displacement=float(g["meta_bending_max_displacement"])))
+    pb.set_leaf_cells(child, float(g["meta_lj_offset"]), float(g["meta_lj_max_displacement"]))
+    return pb
+
+
 def charges_of(g):
     return g["charges"] if "charges" in g else None
 
