@@ -106,7 +106,7 @@ int molecule_cta_warps(const EcmcHandle *h) {
                        (d.n_bonds == 0 || (d.bond_potential.kind == ECMC_POT_DISPLACED_EVEN_POWER &&
                                            d.bond_potential.dep.power == 2.0)) &&
                        (h->mprog.n_inter == 0 || h->mprog.inter_potential.kind == ECMC_POT_LENNARD_JONES);
-    if (!water || h->mprog.root_mode) return kMoleculeWarps;
+    if (!water || h->mprog.root_mode || h->mprog.cell_child) return kMoleculeWarps;
     if (const char *env = std::getenv("ECMC_MOLECULE_ALIGNED"))
         if (std::atoi(env) == 0) return -1;
     int sm_count = 148;
@@ -413,6 +413,20 @@ int build_device_program(EcmcHandle *h) {
         }
         m.bending_enabled = p.bending_enabled ? 1 : 0;
         m.boundary_keeps_factors = p.boundary_keeps_factors ? 1 : 0;
+        // a cell system for one kind of leaf (water/coulomb_power_bounded_lj_cell_bounded.ini)
+        m.cell_child = p.cell_child;
+        if (p.cell_child) {
+            if (p.no_cells || p.cell_child < 1 || p.cell_child > d.nodes_per_root || p.root_mode ||
+                p.pair_handler != ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || p.n_inter_factors != 1 ||
+                p.inter_factors[0][0] != p.cell_child - 1 || p.inter_factors[0][1] != p.cell_child - 1 ||
+                !p.boundary_keeps_factors || !(p.inter_bound_max_displacement > 0.0) ||
+                (p.veto_enabled != ECMC_FAR_NONE && p.veto_enabled != ECMC_FAR_CELL_BOUNDING) || p.veto_use_charge ||
+                !has_derivative(p.inter_potential.kind))
+                return fail(h, ECMC_ERR_INVALID, "leaf cells need composite-object pair factors, one chargeless two-leaf factor "
+                                                 "between the stored leaves, a cell system and boundary_keeps_factors");
+            m.inter_bound_offset = p.inter_bound_offset;
+            m.inter_bound_max_displacement = p.inter_bound_max_displacement;
+        }
         // root-unit-active mode (dipoles/dipole_motion.ini)
         m.root_mode = p.root_mode ? 1 : 0;
         if (p.root_mode) {
@@ -749,6 +763,9 @@ int launch_events(EcmcHandle *h, double until_q, double until_r, int64_t max_eve
         if (h->mprog.root_mode)
             kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kMoleculeWarps, false, true>
                                : molecule_kernel<-1, -1, -1, -1, false, kMoleculeWarps, false, true>;
+        else if (h->mprog.cell_child)
+            kernel = d_records ? molecule_kernel<-1, -1, -1, -1, true, kMoleculeWarps, false, false, true>
+                               : molecule_kernel<-1, -1, -1, -1, false, kMoleculeWarps, false, false, true>;
         else if (water && aligned && wide)
             kernel = d_records ? molecule_kernel<IPCB, MIC, DEP, LJ, true, kWideWarps, true>
                                : molecule_kernel<IPCB, MIC, DEP, LJ, false, kWideWarps, true>;
@@ -965,7 +982,8 @@ ECMC_API int ecmc_start(EcmcHandle *h, const uint32_t *streams, uint32_t first_s
     if (h->molecules)
         molecule_start_kernel<kMoleculeWarps><<<(h->n_chains + kMoleculeWarps - 1) / kMoleculeWarps, kMoleculeWarps * 32, 0, h->stream>>>(
             h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
-            h->program.initial_direction, h->d_stats, h->mprog.root_mode ? h->mprog.switch_length[0] : 0.0);
+            h->program.initial_direction, h->d_stats, h->mprog.root_mode ? h->mprog.switch_length[0] : 0.0,
+            h->mprog.cell_child);
     else
         start_kernel<kWarpsPerBlock><<<blocks, kWarpsPerBlock * 32, 0, h->stream>>>(
             h->dprog, h->state, streams ? h->d_streams : nullptr, first_stream, h->program.initial_active,
@@ -1465,7 +1483,8 @@ ECMC_API const char *ecmc_kernel_name(EcmcHandle *h, int record) {
         h->kernel_name = "disk_kernel<record=" + std::to_string(record != 0) + ">";
     } else if (h->molecules) {
         h->kernel_name = "molecule_kernel<cand=" + cand + ", real=" + real + ", veto=" + veto + ", record=" + std::to_string(record != 0) +
-                         (h->mprog.root_mode ? ", root mode>" : (molecule_cta_warps(h) == kWideWarps ? ", warps=16>" : ">"));
+                         (h->mprog.root_mode ? ", root mode>"
+                          : (h->mprog.cell_child ? ", leaf cells>" : (molecule_cta_warps(h) == kWideWarps ? ", warps=16>" : ">")));
     } else if (pick_spec(h, record != 0, &spec) && spec.chain_blocks) {
         h->kernel_name = "lj_chain_kernel<record=" + std::to_string(record != 0) + ", prune=" +
                          std::to_string(h->spec_prune && !record) + ", warps per chain=" + std::to_string(kChainWarps) + ">";

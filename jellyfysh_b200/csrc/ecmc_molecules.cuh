@@ -32,6 +32,10 @@ struct MoleculeProgram {
     // EcmcProgram.root_mode: chain lengths of the leaf-to-root and of the root-to-leaf RootLeafUnitActiveSwitcher
     int root_mode, pad;
     double switch_length[2];
+    // EcmcProgram.cell_child: the cells hold only the leaves with child index cell_child - 1 (0: no such system); the
+    // piecewise constant bound of the two-leaf factor between those leaves
+    int cell_child, pad2;
+    double inter_bound_offset, inter_bound_max_displacement;
 };
 
 constexpr int kItemCapacity = 192;  // work items per chunk (two ints each: 1.5 KB per warp)
@@ -39,7 +43,7 @@ constexpr int kItemCapacity = 192;  // work items per chunk (two ints each: 1.5 
 // sums of mic_derivative_warp3 up to cutoff 6 (3 x 3 x 2 x 7 = 126 doubles; the shipped potentials use 6)
 constexpr int kMoleculeTrigDoubles = kTrigDoubles3;
 enum ItemType { ITEM_PAIR_LEAF = 0, ITEM_INTER = 1, ITEM_BOND = 2, ITEM_BENDING = 3, ITEM_VETO = 4, ITEM_BOUNDARY = 5,
-                ITEM_FAR_OBJECT = 6 };
+                ITEM_FAR_OBJECT = 6, ITEM_NEAR_LEAF = 7 };
 
 struct Vec3 {
     double x, y, z;
@@ -170,11 +174,20 @@ ECMC_D double pair_derivative_lab(const PotentialParams &p, int dir, double spee
 // independent active unit: root and both leaves move with the full velocity, the candidates are those of the
 // root-unit-active handlers (see include/ecmc.h), and RootLeafUnitActiveSwitcher events alternate between the two modes.
 // Compile-time, so that the other instantiations carry none of it.
-template <int CAND, int REAL, int BOND, int INTER, bool RECORD, int WARPS, bool ALIGNED, bool ROOT_MODE = false>
+// LEAF_CELLS: the cell system stores ONE kind of leaf only (EcmcProgram.cell_child, the shipped
+// water/coulomb_power_bounded_lj_cell_bounded.ini: SingleActiveCellOccupancy with cell level 2 and a charge indicator). The
+// composite-object pairs then come from the factor type map (every other object, every event); while a leaf of that kind is
+// active, the two-leaf factor with the same leaf of other objects is found through the cells -- nearby cells and surplus by
+// TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential, all other cells by
+// TwoLeafUnitCellBoundingPotentialEventHandler --, and the cell boundary is that of the active leaf, whose events leave the
+// composite pairs, the bonds and the bending factor running. Occupants / surplus are leaf identifiers. Compile-time.
+template <int CAND, int REAL, int BOND, int INTER, bool RECORD, int WARPS, bool ALIGNED, bool ROOT_MODE = false,
+          bool LEAF_CELLS = false>
 __global__ void __launch_bounds__(WARPS * 32)
 molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__ MoleculeProgram M, const DeviceState S,
                 const RunArgs A) {
     static_assert(!(ROOT_MODE && ALIGNED), "the root-unit-active mode runs without the per-event CTA barrier");
+    static_assert(!(ROOT_MODE && LEAF_CELLS), "one special mode per instantiation");
     __shared__ double trig_all[WARPS * kMoleculeTrigDoubles];
     __shared__ int items_all[WARPS * 2 * kItemCapacity];
     const int lane = threadIdx.x & 31;
@@ -510,18 +523,26 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             restore_stamp.q = stp->pending_stamp_q; restore_stamp.r = stp->pending_stamp_r;
         } else {
             const bool factors_kept = kept_kind != ECMC_EVENT_NONE;
-            const int nearby_slots = (P.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || leaf_pairs) ? P.n_nearby : 0;
-            const int n_pair_slots = nearby_slots ? nearby_slots + n_surplus : 0;
+            // LEAF_CELLS: is a leaf of the stored kind active (does the occupancy have an active cell)?
+            const bool cell_leaf_active = LEAF_CELLS && active_child == M.cell_child - 1;
+            // LEAF_CELLS: one scan position per object for the composite pairs of the factor type map (unless kept), then
+            // the nearby cells and the surplus of the leaf cells
+            const int lc_pair_slots = LEAF_CELLS && !factors_kept ? n_roots : 0;
+            const int lc_near_slots = cell_leaf_active ? P.n_nearby + n_surplus : 0;
+            const int nearby_slots = LEAF_CELLS ? 0
+                : ((P.pair_handler == ECMC_PAIR_TWO_COMPOSITE_SUMMED_BOUNDING || leaf_pairs) ? P.n_nearby : 0);
+            const int n_pair_slots = LEAF_CELLS ? lc_pair_slots + lc_near_slots : (nearby_slots ? nearby_slots + n_surplus : 0);
             // scan positions: [0, n_pair_slots) objects, then (cell-bounding far field: one per cell) the objects in cells
             // that are not nearby, bonds, inter-object factors (one per object and factor), bending, veto, boundary
-            const bool far_objects = P.veto_enabled == ECMC_FAR_CELL_BOUNDING;
+            const bool far_objects = P.veto_enabled == ECMC_FAR_CELL_BOUNDING && (!LEAF_CELLS || cell_leaf_active);
             const int far_base = n_pair_slots;
             const int bond_base = far_base + (far_objects ? P.n_cells : 0);
             const int inter_base = bond_base + (factors_kept ? 0 : P.n_bonds);
-            const int bending_base = inter_base + (factors_kept ? 0 : M.n_inter * n_roots);
+            const int bending_base = inter_base + ((factors_kept || LEAF_CELLS) ? 0 : M.n_inter * n_roots);
             const int veto_base = bending_base + ((!factors_kept && M.bending_enabled) ? 1 : 0);
             const int boundary_base = veto_base + (P.veto_enabled == ECMC_FAR_CELL_VETO ? 1 : 0);
-            const int n_scan = boundary_base + (P.no_cells ? 0 : 1);  // no cell system: no cell boundary
+            // no cell system, or no active cell: no cell boundary
+            const int n_scan = boundary_base + ((P.no_cells || (LEAF_CELLS && !cell_leaf_active)) ? 0 : 1);
             unsigned long long best_key = 0x7ff0000000000000ull;
             double best_x = INFINITY;
             int best_seq = kSeqNone;
@@ -534,7 +555,22 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                 while (cursor < n_scan && count <= kItemCapacity - 96) {
                     const int s = cursor + lane;
                     int type = -1, target = -1, copies = 0;
-                    if (s < nearby_slots) {
+                    if (LEAF_CELLS && s < n_pair_slots) {
+                        if (s < lc_pair_slots) {
+                            if (s != active_root) { type = ITEM_PAIR_LEAF; target = s; copies = npr; }
+                        } else if (s - lc_pair_slots < P.n_nearby) {
+                            const int code = __ldg(P.nearby + (s - lc_pair_slots));
+                            int x = cid0 + (code & 1023), y = cid1 + ((code >> 10) & 1023), z = cid2 + (code >> 20);
+                            if (x >= P.per_side[0]) x -= P.per_side[0];
+                            if (y >= P.per_side[1]) y -= P.per_side[1];
+                            if (z >= P.per_side[2]) z -= P.per_side[2];
+                            target = occ[x * P.cumulative[0] + y * P.cumulative[1] + z * P.cumulative[2]];
+                            if (target >= 0) { type = ITEM_NEAR_LEAF; copies = 1; }
+                        } else {
+                            target = sur[s - lc_pair_slots - P.n_nearby];
+                            type = ITEM_NEAR_LEAF; copies = 1;
+                        }
+                    } else if (s < nearby_slots) {
                         const int code = __ldg(P.nearby + s);
                         int x = cid0 + (code & 1023), y = cid1 + ((code >> 10) & 1023), z = cid2 + (code >> 20);
                         if (x >= P.per_side[0]) x -= P.per_side[0];
@@ -599,7 +635,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                     double dt = INFINITY, rate = 0.0;
                     int kind = ECMC_EVENT_NONE, cell = -1, rec_target = -1;
                     bool is_factor = false;
-                    if (type == ITEM_PAIR_LEAF || type == ITEM_INTER || type == ITEM_BOND) {
+                    if (type == ITEM_PAIR_LEAF || type == ITEM_INTER || type == ITEM_BOND || type == ITEM_NEAR_LEAF) {
                         const Particle tp = part[target];
                         const Vec3 s3 = separation_lab(apos, lab_position(tp), L, half);
                         const double s0 = vcomp(s3, dir);
@@ -614,6 +650,28 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                             dt = displacement_time<CAND>(P.cand_potential, 0, P.inv_speed, L, s0, s1, s2, c1, c2, du);
                             kind = ECMC_EVENT_PAIR;
                             rec_target = leaf_pairs ? target : root;
+                            is_factor = LEAF_CELLS;  // (a cell-boundary event of the active leaf leaves these handlers running)
+                        } else if (type == ITEM_NEAR_LEAF) {
+                            // TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential.send_event_time (:103-131) on
+                            // _displacement_from_piecewise_constant_bounding_potential
+                            // (event_handler_with_bounding_potential.py:282-332): bound = max(derivative now, derivative after
+                            // max_displacement) + offset
+                            const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
+                            const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                            const double one = derivative_warp<INTER>(M.inter_potential, dir, speed, s3.x, s3.y, s3.z, 1.0, 1.0,
+                                                                      trig, lane);
+                            Vec3 moved = apos;
+                            set_dir(moved, correct_position_entry(
+                                __dadd_rn(vcomp(apos, dir), __dmul_rn(speed, M.inter_bound_max_displacement)), L));
+                            const Vec3 m3 = separation_lab(moved, lab_position(tp), L, half);
+                            const double two = derivative_warp<INTER>(M.inter_potential, dir, speed, m3.x, m3.y, m3.z, 1.0, 1.0,
+                                                                      trig, lane);
+                            const double constant = (one > two ? one : two) + M.inter_bound_offset;
+                            rate = -1.0;  // bounding event rate None
+                            dt = M.inter_bound_max_displacement;
+                            if (constant > 0.0 && du / constant < M.inter_bound_max_displacement) { rate = constant; dt = du / constant; }
+                            kind = ECMC_EVENT_FACTOR_PAIR;
+                            rec_target = target;
                         } else {
                             const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, target), 0);
                             const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
@@ -627,6 +685,19 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                             rec_target = target;
                             is_factor = true;
                         }
+                    } else if (type == ITEM_FAR_OBJECT && LEAF_CELLS) {
+                        // TwoLeafUnitCellBoundingPotentialEventHandler.send_event_time
+                        // (two_leaf_unit_cell_bounding_potential_event_handler.py:137-177) for the leaf in a cell that is not
+                        // nearby; chargeless; the draw is double 1 of the factor-time slot of the target leaf
+                        const int leaf = occ[target];
+                        const int relative = relative_cell_of(P, target, cid0, cid1, cid2);
+                        rate = __ldg(P.bounds + (relative * P.dimension + dir) * 2);
+                        const double u = stream_double(key, ECMC_SLOT(ECMC_SLOT_FACTOR_TIME, leaf), 1);
+                        const double du = -log_unit_interval(1.0 - u) * P.inv_beta;
+                        dt = rate > 0.0 ? du / rate * P.inv_speed : INFINITY;
+                        cell = relative;
+                        kind = ECMC_EVENT_CELL_BOUNDING;
+                        rec_target = leaf;
                     } else if (type == ITEM_FAR_OBJECT) {
                         // TwoCompositeObjectCellBoundingPotentialEventHandler.send_event_time
                         // (two_composite_object_cell_bounding_potential_event_handler.py:152-196): constant event rate =
@@ -719,9 +790,10 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                         dt = exponential / (w->total_rate * charge_factor * speed);
                         kind = ECMC_EVENT_CELL_VETO;
                     } else if (type == ITEM_BOUNDARY) {
-                        double separation = boundary - vcomp(rpos, dir);
+                        // the unit on the cell level: the root unit, or (LEAF_CELLS) the active leaf
+                        double separation = boundary - vcomp(LEAF_CELLS ? apos : rpos, dir);
                         if (separation < 0.0) separation = separation + L;
-                        dt = separation / P.root_speed;
+                        dt = separation / (LEAF_CELLS ? speed : P.root_speed);
                         cell = next_cell;
                         kind = ECMC_EVENT_CELL_BOUNDARY;
                     }
@@ -843,6 +915,22 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             // out-state with a known target object; the stored rate is per length, the bound's derivative is rate x speed
             const bool far = kind == ECMC_EVENT_CELL_BOUNDING;
             const bool veto = kind == ECMC_EVENT_CELL_VETO || far;
+            if (LEAF_CELLS && far) {
+                // TwoLeafUnitCellBoundingPotentialEventHandler.send_out_state (:179-211) between two leaves: the stored
+                // rate x speed is the bounding event rate, confirmed against the real potential; the target leaf takes
+                // over. Recorded with the target's object.
+                rec_target = btarget / npr;
+                n_pair++;
+                const double real = pair_derivative_lab<-1>(P.veto_potential, dir, speed, apos, lab_position(part[btarget]), 1.0,
+                                                            1.0, L, half, trig, lane);
+                const double bounding_rate = brate * speed;
+                if (real > 0.0) {
+                    if (bounding_rate < real) count_rare(A, lane, 7);
+                    const double u = confirm_draw(key.seed, key.stream, key.event, draw++);
+                    if (0.0 + (bounding_rate - 0.0) * u < real) new_active = btarget;
+                }
+                break;
+            }
             // leaf_pairs: btarget is the target LEAF; the loops below then run over that one leaf only
             const bool one_leaf = leaf_pairs && !veto;
             const int target_root = far ? btarget : (veto ? occ[bcell] : (one_leaf ? btarget / npr : btarget));
@@ -942,6 +1030,19 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
         case ECMC_EVENT_BOND:
         case ECMC_EVENT_FACTOR_PAIR:
             rec_target = btarget;
+            if (LEAF_CELLS && kind == ECMC_EVENT_FACTOR_PAIR) {
+                // TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential.send_out_state (:133-152)
+                n_factor++;
+                if (brate < 0.0) break;  // bounding event rate None
+                const double real = pair_derivative_lab<INTER>(M.inter_potential, dir, speed, apos, lab_position(part[btarget]),
+                                                               1.0, 1.0, L, half, trig, lane);
+                if (real > 0.0) {
+                    if (brate < real) count_rare(A, lane, 7);
+                    const double u = confirm_draw(key.seed, key.stream, key.event, draw++);
+                    if (0.0 + (brate - 0.0) * u < real) new_active = btarget;
+                }
+                break;
+            }
             new_active = btarget;
             if (kind == ECMC_EVENT_BOND) n_bond++; else n_factor++;
             break;
@@ -974,11 +1075,14 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             }
             break;
         }
-        case ECMC_EVENT_CELL_BOUNDARY:
-            // the root lands exactly on the lower boundary of its new cell (cell_boundary_event_handler.py:158-173)
-            set_dir(rpos, __ldg(P.cell_min_axis + dir * P.max_per_side + (bcell / P.cumulative[dir]) % P.per_side[dir]));
+        case ECMC_EVENT_CELL_BOUNDARY: {
+            // the unit on the cell level -- the root, or (LEAF_CELLS) the active leaf -- lands exactly on the lower boundary
+            // of its new cell (cell_boundary_event_handler.py:158-173)
+            const double landing = __ldg(P.cell_min_axis + dir * P.max_per_side + (bcell / P.cumulative[dir]) % P.per_side[dir]);
+            if (LEAF_CELLS) set_dir(apos, landing); else set_dir(rpos, landing);
             n_boundary++;
             break;
+        }
         case ECMC_EVENT_END_OF_CHAIN:
             new_active = eoc_next;
             rec_target = new_active;
@@ -1013,6 +1117,16 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
 
         // ---- commit + SingleActiveCellOccupancy.update on the cell level of the roots
         const int new_root = new_active / npr;
+        if (LEAF_CELLS && new_active != active && active_child == M.cell_child - 1) {
+            // the cells hold one kind of leaf: the old active leaf goes back into its cell if it is of that kind
+            // (single_active_cell_occupancy.py:149-203)
+            int delta = 0;
+            if (lane == 0) delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, active_cell, active);
+            delta = __shfl_sync(kFull, delta, 0);
+            if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+            __syncwarp();
+        }
+        const bool active_changed = new_active != active;
         if (new_active != active) {
             if (lane == 0) {
                 Particle p = part[active];
@@ -1030,7 +1144,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
                 Particle r = roots[active_root];
                 r.x = rpos.x; r.y = rpos.y; r.z = rpos.z;
                 roots[active_root] = r;
-                delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, active_cell, active_root);
+                if (!LEAF_CELLS) delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, active_cell, active_root);
             }
             delta = __shfl_sync(kFull, delta, 0);
             if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
@@ -1038,7 +1152,26 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             rpos = lab_position(roots[new_root]);
         }
         active = new_active;
-        {
+        if (LEAF_CELLS) {
+            // the active cell follows the active leaf while it is of the stored kind; a new active leaf of that kind leaves
+            // its cell
+            const bool relevant = active - new_root * npr == M.cell_child - 1;
+            if (relevant) {
+                cid0 = (int)(apos.x / P.side_length[0]);
+                cid1 = (int)(apos.y / P.side_length[1]);
+                cid2 = (int)(apos.z / P.side_length[2]);
+                active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
+                if (active_changed) {
+                    int delta = 0;
+                    if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, 1, active_cell, active);
+                    delta = __shfl_sync(kFull, delta, 0);
+                    if (delta == 2) count_rare(A, lane, 8); else n_surplus += delta;
+                    __syncwarp();
+                }
+            } else if (active_changed) {
+                active_cell = 0; cid0 = cid1 = cid2 = 0;
+            }
+        } else {
             // the cell of the root is recomputed from its position after every event, like the oracle does
             const int old_cell = active_cell;
             cid0 = (int)(rpos.x / P.side_length[0]);
@@ -1047,7 +1180,7 @@ molecule_kernel(const __grid_constant__ DeviceProgram P, const __grid_constant__
             active_cell = cid0 * P.cumulative[0] + cid1 * P.cumulative[1] + cid2 * P.cumulative[2];
             (void)old_cell;
         }
-        if (new_root != active_root) {
+        if (!LEAF_CELLS && new_root != active_root) {
             int delta = 0;
             if (lane == 0) delta = occupancy_remove(occ, sur, n_surplus, 1, active_cell, new_root);
             delta = __shfl_sync(kFull, delta, 0);
@@ -1128,7 +1261,7 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState S, const uint32_t *streams,
                       uint32_t first_stream, int initial_active, int initial_direction, EcmcStats *stats,
-                      double first_switch) {
+                      double first_switch, int cell_child) {
     const int lane = threadIdx.x & 31;
     const int chain = S.first_chain + blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (chain >= S.first_chain + S.n_chains) return;
@@ -1140,10 +1273,15 @@ molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState
     __syncwarp();
     if (lane == 0) {
         int n_surplus = 0, overflow = 0;
+        // EcmcProgram.cell_child: the cells hold only the leaves with child index cell_child - 1, by their own positions
+        // (SingleActiveCellOccupancy with cell level 2 and a charge indicator, :62-121), and have an active cell only while
+        // such a leaf is active
+        const Particle *leaves = S.particles + (size_t)chain * P.n_particles;
         for (int r = 0; r < n_roots; r++) {
             int id[3];
-            cell_identifier_of(P, roots[r], id);
-            const int delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, flat_cell(P, id), r);
+            cell_identifier_of(P, cell_child ? leaves[r * npr + cell_child - 1] : roots[r], id);
+            const int delta = occupancy_insert(occ, sur, n_surplus, 1, P.max_surplus, flat_cell(P, id),
+                                               cell_child ? r * npr + cell_child - 1 : r);
             if (delta == 2) overflow++; else n_surplus += delta;
         }
         EcmcChainState st = {};  // every field defined: the state is downloaded, compared and checkpointed as bytes
@@ -1152,10 +1290,15 @@ molecule_start_kernel(const __grid_constant__ DeviceProgram P, const DeviceState
         st.event_counter = 0;
         st.stream = streams ? streams[chain] : first_stream + (uint32_t)chain;
         int id[3];
-        cell_identifier_of(P, roots[initial_active / npr], id);
-        st.active_cell = flat_cell(P, id);
-        const int delta = occupancy_remove(occ, sur, n_surplus, 1, st.active_cell, initial_active / npr);
-        if (delta == 2) overflow++; else n_surplus += delta;
+        if (cell_child && initial_active % npr != cell_child - 1) {
+            st.active_cell = 0;
+        } else {
+            cell_identifier_of(P, cell_child ? leaves[initial_active] : roots[initial_active / npr], id);
+            st.active_cell = flat_cell(P, id);
+            const int delta = occupancy_remove(occ, sur, n_surplus, 1, st.active_cell,
+                                               cell_child ? initial_active : initial_active / npr);
+            if (delta == 2) overflow++; else n_surplus += delta;
+        }
         const Time now = {0.0, 0.0};
         const Time eoc = time_add(now, time_sub(now, now) + P.chain_time);
         st.eoc_q = eoc.q; st.eoc_r = eoc.r;

@@ -286,6 +286,57 @@ def test_no_cells_composite_reference_trace_replay(oracle, name):
             assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL * max(1.0, length)
 
 
+@pytest.mark.parametrize("name", tu.LEAF_CELL_WATER_TRACES)
+def test_leaf_cell_water_reference_trace_replay(oracle, name):
+    """The shipped water/coulomb_power_bounded_lj_cell_bounded.ini on the device (molecule_kernel<..., LEAF_CELLS>): a cell
+    system that stores the oxygens only, the Lennard-Jones factor between oxygens through the piecewise-constant-bound
+    handler (nearby cells, surplus) and the leaf-level cell-bounding handler (all other cells), cell-boundary events of the
+    active oxygen that leave the composite Coulomb factors, bonds and bending running. Every event of the reference traces
+    (12 molecules in 6^3 cells, 16 in 4^3), in stretches that start from the oracle's state; occupancy compared after each."""
+    g = tu.load_trace(name)
+    records = g["records"]
+    length = float(g["meta_system_length"])
+    stretch = 50
+    build = tu.leaf_cell_water_builder_of
+    chain = oracle.OracleChain(build(g, oracle.ProgramBuilder))
+    chain.set_positions(g["positions0"], tu.charges_of(g))
+    chain.set_roots(g["roots0"])
+    chain.start(stream=int(g["seed"][1]))
+    boundaries = 0
+    with engine.Engine(build(g, ProgramBuilder), n_chains=1) as eng:
+        assert "leaf cells" in eng.kernel_name()
+        eng.upload_positions(g["positions0"][None], tu.charges_of(g)[None])
+        eng.upload_roots(g["roots0"][None])
+        eng.start(first_stream=int(g["seed"][1]))
+        occupants, surplus = eng.cells()
+        ref_occupants, ref_surplus = chain.cells()
+        assert np.array_equal(occupants[0], ref_occupants) and sorted(surplus[0].tolist()) == sorted(ref_surplus.tolist())
+        assert int(eng.chain_states()[0]["active_cell"]) == chain.state().active_cell
+        for done in range(0, len(records), stretch):
+            count = min(stretch, len(records) - done)
+            if done:
+                eng.upload_positions(chain.positions()[None], tu.charges_of(g)[None])
+                eng.upload_roots(chain.roots()[None])
+                eng.set_chain_states(np.frombuffer(bytes(chain.state()), dtype=abi.chain_state_dtype()))
+                ref_occupants, ref_surplus = chain.cells()
+                eng.set_cells(ref_occupants[None], [ref_surplus])
+            rec, stats = eng.run_recorded(max_events=count, records_per_chain=count)
+            assert stats["events"] == count and stats["capacity_errors"] == 0
+            boundaries += stats["boundary_events"]
+            assert_records_match(rec[0], records[done:done + count], length, f"{name}[{done}:{done + count}]")
+            n, ours = chain.run(max_events=count, record=count)
+            assert n == count and tu.records_equal_discrete(ours, records[done:done + count])
+            assert np.max(np.abs(eng.download_positions()[0] - chain.positions())) < RTOL * length
+            assert np.max(np.abs(eng.download_roots()[0] - chain.roots())) < RTOL * length
+            occupants, surplus = eng.cells()
+            ref_occupants, ref_surplus = chain.cells()
+            assert np.array_equal(occupants[0], ref_occupants) and sorted(surplus[0].tolist()) == sorted(ref_surplus.tolist())
+            st, ref_st = eng.chain_states()[0], chain.state()
+            assert (int(st["active"]), int(st["active_cell"]), int(st["kept_kind"])) == \
+                (ref_st.active, ref_st.active_cell, ref_st.kept_kind)
+    assert boundaries == int((records["kind"] == 3).sum()) >= 3
+
+
 def test_root_unit_active_mode_reference_trace_replay(oracle):
     """The shipped dipoles/dipole_motion.ini on the device (molecule_kernel<..., ROOT_MODE>): the independent active unit
     alternates between a leaf unit and the ROOT unit of a dipole (RootLeafUnitActiveSwitcher,
