@@ -149,6 +149,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
     # (coulomb_atoms/power_bounded.ini). On the device that is EcmcProgram.no_cells: every other unit is a candidate
     # of every event and there are no cell-boundary events.
     no_cells = not internal_states
+    leaf_cell_child = None  # the child index a cell system with a charge indicator stores, if there is one
     # General velocities: the sequential-direction end-of-chain handler rotates the velocity by an angle
     # (single_independent_active_sequential_direction_end_of_chain_event_handler.py:64-122). On the device that is the
     # disk kernel: two-dimensional composite point objects without a cell system whose pair factors -- all with hard
@@ -169,17 +170,25 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             raise _configuration_error("at most one internal state, a SingleActiveCellOccupancy, is supported")
         occupancy = internal_states[0]
         # single_active_cell_occupancy.py:62-92: with `charge = <name>` only units with that charge unequal zero are stored
-        # (and take part as active units). The device bins every unit: a configuration that relies on the filter is refused
-        # instead of being run with neutral units in the cells.
+        # (and take part as active units). The device supports that for ONE kind of leaf of composite objects -- an
+        # indicator charge that is non-zero for exactly one child index, the oxygen cells of
+        # water/coulomb_power_bounded_lj_cell_bounded.ini (EcmcProgram.cell_child) --; any other configuration that relies on
+        # the filter is refused instead of being run with neutral units in the cells.
         probe = _ProbeUnit()
         occupancy._is_relevant_unit(probe)
         if probe.charge.names:
-            raise _configuration_error("SingleActiveCellOccupancy with a charge filter (charge = {0}) is not supported"
-                                       .format(probe.charge.names[0]))
+            stored = [[k for k, child in enumerate(cnode.children) if occupancy._is_relevant_unit(child.value)]
+                      for cnode in extracted_global_state]
+            if levels != 2 or occupancy.cell_level != 2 or any(len(kinds) != 1 or kinds != stored[0] for kinds in stored):
+                raise _configuration_error("SingleActiveCellOccupancy with a charge filter (charge = {0}) is only supported "
+                                           "as a leaf-level cell system for one child index of composite objects"
+                                           .format(probe.charge.names[0]))
+            leaf_cell_child = stored[0][0]
         cells = occupancy.cells
         if "CuboidPeriodicCells" not in _class_names(cells):
             raise _configuration_error("cells must be CuboidPeriodicCells")
-        molecules = levels == 2 and occupancy.cell_level == 1  # composite objects in root-level cells (water)
+        # composite objects in root-level cells (water), or with a cell system for one kind of leaf
+        molecules = levels == 2 and (occupancy.cell_level == 1 or leaf_cell_child is not None)
         if occupancy.cell_level != levels and not molecules:
             raise _configuration_error("cell_level must be 1 or the number of node levels")
         max_occupants = occupancy._maximum_number_occupants  # cell_occupancy.py:70-72
@@ -198,6 +207,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
     # root-unit-active mode (dipoles/dipole_motion.ini): the handlers that run while the ROOT unit of an object is the
     # independent active unit, and the RootLeafUnitActiveSwitcher handlers that alternate between the two modes
     root_pair_handlers, root_factor_handlers, switchers = [], [], []
+    near_leaf_handlers = []  # TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential through the leaf cells
     # handlers fed by a factor type map are intramolecular factors (factor_type_map_in_state_tagger.py:83-107)
     factor_tagger_of = {}
     for tagger in activator._taggers:
@@ -212,6 +222,11 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
             root_factor_handlers.append(handler)
         elif "RootLeafUnitActiveSwitcher" in names:
             switchers.append(handler)
+        elif "TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential" in names:
+            if leaf_cell_child is None or id(handler) in factor_tagger_of:
+                raise _configuration_error("the piecewise-constant-bound two-leaf handler is supported for the nearby cells "
+                                           "and the surplus of a leaf-level cell system with a charge indicator")
+            near_leaf_handlers.append(handler)
         elif id(handler) in factor_tagger_of and levels == 1:
             # point masses: the factor type map lists the pair factors themselves ("[0, 1], Coulomb" = the active
             # atom with every other atom, factor_type_maps.py:333-347)
@@ -224,7 +239,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                 raise _configuration_error("factor-type-map handler {0} has no device implementation"
                                            .format(type(handler).__name__))
             pair_handlers.append(handler)
-        elif id(handler) in factor_tagger_of and no_cells and \
+        elif id(handler) in factor_tagger_of and (no_cells or leaf_cell_child is not None) and \
                 "TwoCompositeObjectSummedBoundingPotentialEventHandler" in names:
             # "[0, 1, 2, 3], Coulomb": the object of the active leaf with every other object
             factor_map = factor_tagger_of[id(handler)]._factor_type_map
@@ -454,7 +469,7 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
         potential = potential_descriptor(first._potential)
         charge = first._charge
         composite_bounding = "TwoCompositeObjectCellBoundingPotentialEventHandler" in _class_names(first)
-        if composite_bounding != molecules:
+        if composite_bounding != (molecules and leaf_cell_child is None):
             raise _configuration_error("composite-object cell-bounding handlers need root-level cells, leaf-unit ones "
                                        "leaf-level cells")
         for handler in bounding_handlers[1:]:
@@ -503,9 +518,32 @@ def compile_program(activator, extracted_global_state, seed=0, max_surplus=None,
                 raise _configuration_error("a cell-boundary event must trash all or none of the factor-type-map "
                                            "handlers")
             keeps_factors = not (factor_tags and factor_tags <= trashed)
+        if leaf_cell_child is not None:
+            # the two-leaf factor between the stored leaves is found through the cells: nearby cells and surplus by the
+            # piecewise-constant-bound handler, every other cell by the leaf-level cell-bounding handler
+            if not near_leaf_handlers or inter_factors or veto_handlers or not keeps_factors or occupancy.cell_level != 2 or \
+                    not pair_handlers or any(id(h) not in factor_tagger_of for h in pair_handlers):
+                raise _configuration_error("a leaf-level cell system with a charge indicator needs composite-object pair "
+                                           "factors from a factor type map, piecewise-constant-bound handlers for its nearby "
+                                           "cells and a cell-boundary event that keeps the factor-type-map handlers")
+            first = near_leaf_handlers[0]
+            inter_potential = potential_descriptor(first._potential)
+            for handler in near_leaf_handlers:
+                if _charge_name(handler._charges) is not None or handler._offset != first._offset or handler._max_displacement != first._max_displacement or \
+                        not _same_potential(inter_potential, potential_descriptor(handler._potential)):
+                    raise _configuration_error("the piecewise-constant-bound handlers must be alike and chargeless")
+            if bounding_handlers and (bounding_handlers[0]._charge is not None or not _same_potential(
+                    inter_potential, potential_descriptor(bounding_handlers[0]._potential))):
+                raise _configuration_error("the cell-bounding handler of the leaf cells must use the potential of the "
+                                           "piecewise-constant-bound handlers, without charges")
+            inter_factors = [(leaf_cell_child, leaf_cell_child)]
+        elif near_leaf_handlers:
+            raise _configuration_error("piecewise-constant-bound two-leaf handlers need a leaf-level cell system")
         builder.set_molecules(composite_lifting if composite_lifting is not None else abi.LIFTING_INSIDE_FIRST,
                               inter_factors=inter_factors, inter_potential=inter_potential, bending=bending,
                               boundary_keeps_factors=keeps_factors)
+        if leaf_cell_child is not None:
+            builder.set_leaf_cells(leaf_cell_child, near_leaf_handlers[0]._offset, near_leaf_handlers[0]._max_displacement)
     elif veto_handlers and "CompositeObjectCellVetoEventHandler" in _class_names(veto_handlers[0]):
         raise _configuration_error("the composite-object cell-veto handler needs root-level cells")
     # ---- root-unit-active mode: the same factors with the root unit of an object active, and the switchers

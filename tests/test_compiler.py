@@ -225,6 +225,48 @@ def test_dipole_motion_graph_compiles_and_replays(oracle):
         setting.reset()
 
 
+def test_leaf_cell_water_graph_compiles_and_replays(oracle):
+    """The shipped water/coulomb_power_bounded_lj_cell_bounded.ini (oxygen-only cell system, piecewise-constant-bound and
+    cell-bounding Lennard-Jones handlers) sized for twelve molecules -> compiler -> oracle chain reproduces the reference
+    trace of the same configuration bit for bit."""
+    from jellyfysh.base.exceptions import ConfigurationError
+    from jellyfysh_b200 import abi, compiler
+    g = tu.load_trace("trace_water_lj_cell_bounded")
+    n = int(g["meta_n"]) // 3
+    ini = configs.shipped_without_sampling(
+        REF, ("2018_JCP_149_064113", "water", "coulomb_power_bounded_lj_cell_bounded.ini"), end_of_run_time=5.0,
+        replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
+                      ("number_event_handlers = 1", f"number_event_handlers = {n - 1}")])
+    mediator, setting = build_reference_graph(ini, composites=(g["roots0"], g["positions0"].reshape(n, 3, 3)))
+    try:
+        state = mediator._state_handler.extract_global_state()
+        compiled = compiler.compile_program(mediator._activator, state, seed=int(g["seed"][0]))
+        p = compiled.builder.program
+        assert p.no_cells == 0 and p.cell_level == 1 and p.nodes_per_root == 3 and p.cell_child == 2
+        assert [p.cells_per_side[d] for d in range(3)] == [6, 6, 6] and p.neighbor_layers == 1 and p.max_occupants == 1
+        assert p.pair_handler == abi.PAIR_TWO_COMPOSITE_SUMMED_BOUNDING and p.veto_enabled == abi.FAR_CELL_BOUNDING
+        assert p.n_inter_factors == 1 and (p.inter_factors[0][0], p.inter_factors[0][1]) == (1, 1)
+        assert (p.inter_bound_offset, p.inter_bound_max_displacement) == (10.0, 0.24353253124)
+        assert p.boundary_keeps_factors == 1 and p.bending_enabled == 1 and p.n_bonds == 2
+        assert np.array_equal(compiled.builder.tables["bounds"][..., 0], np.nan_to_num(g["bounds"][..., 0]))
+        positions, charges, roots = compiler.positions_and_charges(state, compiled.charge_name)
+        chain = oracle.OracleChain(compiled.builder)
+        chain.set_positions(positions, charges)
+        chain.set_roots(roots)
+        chain.start(stream=int(g["seed"][1]))
+        records = g["records"][:2000]
+        n_done, rec = chain.run(max_events=len(records), record=len(records))
+        assert n_done == len(records) and tu.records_equal_discrete(rec, records)
+        assert np.array_equal(rec["time_q"], records["time_q"]) and np.array_equal(rec["time_r"], records["time_r"])
+        # a cell system that stores two kinds of leaves is refused
+        occupancy = mediator._activator._internal_states[0]
+        occupancy._is_relevant_unit = lambda unit: unit.charge["electric_charge"] > 0
+        with pytest.raises(ConfigurationError, match="charge filter"):
+            compiler.compile_program(mediator._activator, state, seed=1)
+    finally:
+        setting.reset()
+
+
 def test_atom_factors_graph_compiles_and_replays(oracle):
     """The shipped dipoles/atom_factors.ini (Coulomb as bounded leaf-to-leaf factors between the dipoles, no cell system)
     sized for three dipoles -> compiler -> oracle chain reproduces the reference trace bit for bit."""

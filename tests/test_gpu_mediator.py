@@ -546,11 +546,14 @@ def test_shipped_single_hard_disk_dipole_matches_the_analytic_distributions(tmp_
     assert d_rho < bound and d_theta < bound, (d_rho, d_theta, bound)
 
 
-@pytest.mark.parametrize("config", ["coulomb_cell_veto_lj_inverted.ini", "coulomb_power_bounded_lj_inverted.ini"])
+@pytest.mark.parametrize("config", ["coulomb_cell_veto_lj_inverted.ini", "coulomb_power_bounded_lj_inverted.ini",
+                                    "coulomb_power_bounded_lj_cell_bounded.ini"])
 def test_shipped_water_config_matches_reference_statistics(tmp_path, config):
     """C4 statistical check (SURVEY 8c): the shipped water/coulomb_cell_veto_lj_inverted.ini (two SPC/Fw molecules;
     composite-object Coulomb handlers on root-level cells) and water/coulomb_power_bounded_lj_inverted.ini (no cell
-    system, Coulomb as nine bounded leaf-to-leaf factors between the molecules), unchanged except for the mediator line,
+    system, Coulomb as nine bounded leaf-to-leaf factors between the molecules) and
+    water/coulomb_power_bounded_lj_cell_bounded.ini (composite-object Coulomb factors from the factor type map, the
+    Lennard-Jones factor of the oxygens through an oxygen-only cell system), unchanged except for the mediator line,
     the run length, the sampling interval and the output file, run as many independent device chains, reproduce the
     cumulative histogram of the oxygen-oxygen separation the reference ships (ReferenceOOSeparation.dat; fixture
     tests/golden/reference_cdfs.npz)."""
@@ -565,7 +568,8 @@ def test_shipped_water_config_matches_reference_statistics(tmp_path, config):
     # Two molecules that start apart have to find each other. The pairwise factors of the second file move the pair
     # together more slowly than the composite-object handlers with their lifting over six leaves: measured on B200, the
     # distance to the reference histogram after simulated times 500 / 2000 / 8000 is 0.72 / 0.24 / 0.003.
-    chains, end, interval = 1024, 2000.0 if cell_veto else 8000.0, 20.0
+    leaf_cells = config == "coulomb_power_bounded_lj_cell_bounded.ini"
+    chains, end, interval = 1024, 2000.0 if cell_veto or leaf_cells else 8000.0, 20.0
     if cell_veto:
         ini = configs.water_ini(REF, n_molecules=2, end_of_run_time=end, sampling_interval=interval,
                                 output=str(tmp_path / "oo_separation.dat"))
@@ -575,8 +579,8 @@ def test_shipped_water_config_matches_reference_statistics(tmp_path, config):
         ini = ini.replace("filename = config_files/", "filename = " + os.path.join(REF, "jellyfysh", "config_files") + "/")
         ini = ini.replace("end_of_run_time = 500000", "end_of_run_time = %r" % end)
         ini = ini.replace("sampling_interval = 2.6789", "sampling_interval = %r" % interval)
-        ini = ini.replace("output/2018_JCP_149_064113/water/SamplesOfOOSeparation_CoulombPowerBounded_LJInverted.dat",
-                          str(tmp_path / "oo_separation.dat"))
+        ini = ini.replace("output/2018_JCP_149_064113/water/SamplesOfOOSeparation_CoulombPowerBounded_" +
+                          ("LJCellBounded.dat" if leaf_cells else "LJInverted.dat"), str(tmp_path / "oo_separation.dat"))
         assert str(tmp_path) in ini and "sampling_interval = 20.0" in ini
     ini = ini.replace("mediator = single_process_mediator", "mediator = cuda_batched_mediator")
     ini = ini.replace("[SingleProcessMediator]", "[CudaBatchedMediator]\nnumber_of_chains = %d\nseed = 29" % chains)
@@ -595,6 +599,7 @@ def test_shipped_water_config_matches_reference_statistics(tmp_path, config):
     finally:
         setting.reset()
     assert stats["capacity_errors"] == 0 and stats["bond_events"] > 0 and (stats["veto_events"] > 0) == cell_veto
+    assert (stats["boundary_events"] > 0) == (cell_veto or leaf_cells)
     samples = np.loadtxt(tmp_path / "oo_separation.dat", comments="#")
     per_chain = int(end / interval)
     assert len(samples) == chains * per_chain
