@@ -25,8 +25,8 @@ _LIB = None
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference checkout exists) with oracle/Makefile."""
     so = os.path.join(_HERE, "libecmc_oracle.so")
-    src = os.path.join(_HERE, "ecmc_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    sources = [os.path.join(_HERE, "ecmc_oracle.c"), os.path.join(_HERE, "..", "include", "ecmc.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(src) for src in sources):
         subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True)
 
 
