@@ -614,15 +614,20 @@ def leaf_cell_water_traces():
                 mic=[332.0, 3.45, 6, 2], ipcb=[531.2], lj=[0.6217012, 3.165492], harmonic=[529.581, 1.012, 2.0],
                 bending=[75.9, 1.9764], bending_offset=10.0, bending_max_displacement=0.112321434, initial_active=1,
                 lj_offset=10.0, lj_max_displacement=0.24353253124, cell_child=1, far_field=2)
+    # ... and forty in 3^3 cells: 17-18 oxygens in the surplus at all times, every cell nearby
     for name, n, cells, seed, jitter in (("trace_water_lj_cell_bounded", 12, [6, 6, 6], 13, 0.2),
-                                         ("trace_water_lj_cell_bounded_dense", 16, [4, 4, 4], 14, 0.3)):
+                                         ("trace_water_lj_cell_bounded_dense", 16, [4, 4, 4], 14, 0.3),
+                                         ("trace_water_lj_cell_bounded_surplus", 40, [3, 3, 3], 15, 0.3)):
+        if os.environ.get("JF_ONLY_TRACE") not in (None, name):
+            continue
         roots, leaves = configs.water_start(n, 10.0, seed=seed, jitter=jitter)
         ini = configs.shipped_without_sampling(
             REF, ("2018_JCP_149_064113", "water", "coulomb_power_bounded_lj_cell_bounded.ini"),
             replacements=[("number_of_root_nodes = 2", f"number_of_root_nodes = {n}"),
                           ("number_event_handlers = 1", f"number_event_handlers = {n - 1}"),
                           ("cells_per_side = 6, 6, 6", "cells_per_side = " + ", ".join(map(str, cells)))])
-        chain_trace(name, ini, None, seed=41 + n, stream=31 + n, n_events=4000, snapshot_every=250, max_occupants=1,
+        chain_trace(name, ini, None, seed=41 + n, stream=31 + n, n_events=4000 if n < 40 else 2500, snapshot_every=250,
+                    max_occupants=1,
                     composites=(roots, leaves), charges=np.tile([0.41, -0.82, 0.41], n),
                     meta=dict(meta, n=3 * n, cells_per_side=cells))
 

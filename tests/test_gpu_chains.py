@@ -292,7 +292,8 @@ def test_leaf_cell_water_reference_trace_replay(oracle, name):
     system that stores the oxygens only, the Lennard-Jones factor between oxygens through the piecewise-constant-bound
     handler (nearby cells, surplus) and the leaf-level cell-bounding handler (all other cells), cell-boundary events of the
     active oxygen that leave the composite Coulomb factors, bonds and bending running. Every event of the reference traces
-    (12 molecules in 6^3 cells, 16 in 4^3), in stretches that start from the oracle's state; occupancy compared after each."""
+    (12 molecules in 6^3 cells, 16 in 4^3, 40 in 3^3 with 17-18 oxygens in the surplus), in stretches that start from the
+    oracle's state; occupancy and surplus compared after each."""
     g = tu.load_trace(name)
     records = g["records"]
     length = float(g["meta_system_length"])
@@ -334,7 +335,7 @@ def test_leaf_cell_water_reference_trace_replay(oracle, name):
             st, ref_st = eng.chain_states()[0], chain.state()
             assert (int(st["active"]), int(st["active_cell"]), int(st["kept_kind"])) == \
                 (ref_st.active, ref_st.active_cell, ref_st.kept_kind)
-    assert boundaries == int((records["kind"] == 3).sum()) >= 3
+    assert boundaries == int((records["kind"] == 3).sum()) >= 2
 
 
 def test_root_unit_active_mode_reference_trace_replay(oracle):

@@ -187,7 +187,8 @@ def test_no_cells_composite_chain_replay_bit_exact(oracle, name):
 
 @pytest.mark.parametrize("name", tu.LEAF_CELL_WATER_TRACES)
 def test_leaf_cell_water_chain_replay_bit_exact(oracle, name):
-    """The shipped water/coulomb_power_bounded_lj_cell_bounded.ini (twelve molecules in its 6^3 cells, sixteen in 4^3 cells):
+    """The shipped water/coulomb_power_bounded_lj_cell_bounded.ini (twelve molecules in its 6^3 cells, sixteen in 4^3 cells,
+    forty in 3^3 cells with a permanently filled surplus list):
     a cell system that stores the oxygens only; the Lennard-Jones factor between oxygens through
     TwoLeafUnitEventHandlerWithPiecewiseConstantBoundingPotential (nearby cells) and
     TwoLeafUnitCellBoundingPotentialEventHandler (all other cells), cell-boundary events of the active oxygen that leave the
@@ -214,8 +215,13 @@ def test_leaf_cell_water_chain_replay_bit_exact(oracle, name):
             assert np.array_equal(chain.roots(), g["snap_roots"][k])
             occ, surplus = chain.cells()
             assert np.array_equal(occ, g["snap_occupants"][k])
+            ns = int(g["snap_n_surplus"][k])
+            assert sorted(surplus.tolist()) == sorted(g["snap_surplus"][k][:ns].tolist())
     kinds = np.bincount(records["kind"], minlength=9)
-    assert kinds[5] > 1000 and kinds[7] > 40 and kinds[3] >= 3 and kinds[1] > 1500
+    if name.endswith("_surplus"):  # 3^3 cells: every cell is nearby, 17-18 of the forty oxygens in the surplus
+        assert kinds[5] == 0 and kinds[7] > 900 and kinds[3] >= 2 and int(g["snap_n_surplus"].min()) >= 15
+    else:
+        assert kinds[5] > 1000 and kinds[7] > 40 and kinds[3] >= 3 and kinds[1] > 1500
     assert np.array_equal(chain.positions(), g["final_positions"]) and np.array_equal(chain.roots(), g["final_roots"])
     assert chain.stats()["capacity_errors"] == 0
 

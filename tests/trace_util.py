@@ -195,7 +195,8 @@ def water_builder_of(g, builder_cls, max_surplus=None):
     return pb
 
 
-LEAF_CELL_WATER_TRACES = ["trace_water_lj_cell_bounded", "trace_water_lj_cell_bounded_dense"]
+LEAF_CELL_WATER_TRACES = ["trace_water_lj_cell_bounded", "trace_water_lj_cell_bounded_dense",
+                          "trace_water_lj_cell_bounded_surplus"]
 
 
 def leaf_cell_water_builder_of(g, builder_cls):
